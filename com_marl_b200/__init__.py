@@ -1,0 +1,23 @@
+"""com_marl_b200 — B200-native batched rollout engine for Com-MARL (PredatorPrey / Coverage step +
+communication graph / packet loss + comm-GNN policy forward).  See DESIGN.md."""
+from .scenario import ScenarioSpec  # noqa: F401
+
+__all__ = ["ScenarioSpec", "BatchedEnv", "PredatorPreyWrapper", "CoverageWrapper", "CommCategoricalMLPPolicy",
+           "RolloutEngine", "DeviceRolloutSampler"]
+
+
+def __getattr__(name):
+    # torch-dependent modules are imported lazily so that `import com_marl_b200` stays cheap
+    if name in ("BatchedEnv", "PredatorPreyWrapper", "CoverageWrapper"):
+        from . import envs
+        return getattr(envs, name)
+    if name == "CommCategoricalMLPPolicy":
+        from .policy import CommCategoricalMLPPolicy
+        return CommCategoricalMLPPolicy
+    if name == "RolloutEngine":
+        from .rollout import RolloutEngine
+        return RolloutEngine
+    if name == "DeviceRolloutSampler":
+        from .sampler import DeviceRolloutSampler
+        return DeviceRolloutSampler
+    raise AttributeError(name)

@@ -1,0 +1,680 @@
+// env_kernels.cu — batched PredatorPrey / Coverage step, reset, observation windows and communication
+// state for sm_100a.  One warp owns one environment instance.
+//
+// B200 mapping: state lives in HBM as SoA rows (positions u16, flags u8, bit rows u64);
+// a warp stages its env in shared memory, rebuilds the occupancy of the grid as 64-bit ROW BITMAPS
+// (agents / preys or visited / walls) instead of the reference's grid of strings, runs the two
+// order-dependent loops (agent moves, prey capture+walk) on one lane over those bitmaps while all the
+// order-independent work (neighbour counts, candidate screening, watching flags, window extraction,
+// adjacency, channel draws) is done lane-parallel, and streams the fp32 observation block out with
+// fully coalesced stores.  Everything here is integer/bit work bound by HBM traffic and issue slots;
+// no tensor cores are involved on purpose.
+//
+// Semantics follow the reference exactly (file:line cited at each step); the data model does not.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "commarl_b200.h"
+#include "common.cuh"
+
+namespace cm {
+
+typedef unsigned long long u64;
+
+static constexpr int kWarpsPerCta = 8;
+
+struct EnvArgs {
+    cm_env_desc d;
+    cm_env_state s;
+    cm_step_io io;
+    const uint8_t *mask;
+    int mode;        // 0 step, 1 reset, 2 comm only
+    int at_reset;    // comm-only: GE branch selector
+    int n_pad, p_pad;
+    int warp_bytes;  // dynamic shared memory per warp
+};
+
+// per-warp scratch carved out of dynamic shared memory
+struct Scratch {
+    u64 *occA;       // [G] agent rows
+    u64 *occB;       // [G] prey rows (PredatorPrey) / visited rows (Coverage)
+    uint32_t *win;   // [3][n_pad] window bits per agent
+    uint16_t *posA;  // [n_pad]
+    uint16_t *posP;  // [p_pad]
+    uint8_t *alive;  // [p_pad]
+    int8_t *act;     // [n_pad]
+    uint8_t *kcnt;   // [p_pad] agents around prey j
+    int8_t *mv;      // [p_pad] screened random move of prey j
+};
+
+__host__ __device__ inline int env_warp_bytes(int n_pad, int p_pad, int G)
+{
+    return 2 * G * 8 + 3 * n_pad * 4 + n_pad * 2 + p_pad * 2 + p_pad + n_pad + p_pad + p_pad;
+}
+
+__device__ __forceinline__ Scratch carve(unsigned char *base, int n_pad, int p_pad, int G)
+{
+    Scratch s;
+    s.occA = reinterpret_cast<u64 *>(base);
+    s.occB = s.occA + G;
+    s.win = reinterpret_cast<uint32_t *>(s.occB + G);
+    s.posA = reinterpret_cast<uint16_t *>(s.win + 3 * n_pad);
+    s.posP = s.posA + n_pad;
+    s.alive = reinterpret_cast<uint8_t *>(s.posP + p_pad);
+    s.act = reinterpret_cast<int8_t *>(s.alive + p_pad);
+    s.kcnt = reinterpret_cast<uint8_t *>(s.act + n_pad);
+    s.mv = reinterpret_cast<int8_t *>(s.kcnt + p_pad);
+    return s;
+}
+
+// action -> displacement: 0 down(+row) 1 left(-col) 2 up(-row) 3 right(+col) 4 noop
+// (predator_prey.py:240-253,640-646; coverage.py:336-345)
+__device__ __forceinline__ int d_row(int a) { return a == 0 ? 1 : (a == 2 ? -1 : 0); }
+__device__ __forceinline__ int d_col(int a) { return a == 3 ? 1 : (a == 1 ? -1 : 0); }
+
+__device__ __forceinline__ int bit_at(const u64 *rows, int r, int c, int G)
+{
+    return (r >= 0 && r < G && c >= 0 && c < G) ? (int)((rows[r] >> c) & 1ull) : 0;
+}
+
+// entities of `rows` in the 4-neighbourhood of (r,c); (r,c) itself may lie outside the grid, each
+// neighbour is bounds-checked on its own (predator_prey.py:309-329).
+__device__ __forceinline__ int count4(const u64 *rows, int r, int c, int G)
+{
+    return bit_at(rows, r + 1, c, G) + bit_at(rows, r - 1, c, G) + bit_at(rows, r, c + 1, G) + bit_at(rows, r, c - 1, G);
+}
+
+// (2R+1) bits of row `r` centred on column c, LSB = column c-R; cells outside the grid read `oob`.
+__device__ __forceinline__ uint32_t window_row(const u64 *rows, int r, int c, int R, int G, int oob)
+{
+    const uint32_t mask = (1u << (2 * R + 1)) - 1u;
+    if (r < 0 || r >= G) return oob ? mask : 0u;
+    u64 v = rows[r];
+    if (oob) v |= ~((G >= 64) ? ~0ull : ((1ull << G) - 1ull));  // columns >= G
+    int sh = c - R;
+    uint32_t seg;
+    if (sh >= 0) seg = (uint32_t)(v >> sh);
+    else {
+        seg = (uint32_t)(v << (-sh));
+        if (oob) seg |= (1u << (-sh)) - 1u;                      // columns < 0
+    }
+    return seg & mask;
+}
+
+__device__ __forceinline__ uint32_t window_bits(const u64 *rows, int r, int c, int R, int G, int oob)
+{
+    const int w = 2 * R + 1;
+    uint32_t bits = 0;
+    for (int dr = 0; dr < w; ++dr) bits |= window_row(rows, r - R + dr, c, R, G, oob) << (dr * w);
+    return bits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// random streams (generated mode): Philox4x32-10 keyed by (seed; env id, tick, stream|episode<<8, index)
+// ------------------------------------------------------------------------------------------------
+struct RngKey {
+    uint32_t env, tick, episode;
+    uint2 key;
+};
+
+__device__ __forceinline__ uint4 rng_block(const RngKey &k, uint32_t stream, uint32_t index)
+{
+    return philox4x32_10(make_uint4(k.env, k.tick, stream | (k.episode << 8), index), k.key);
+}
+
+struct ChanSrc {
+    const float *u;  // injected planes of this env, or nullptr
+    RngKey key;
+    int n;
+    uint32_t cached_idx;
+    uint4 cached;
+    __device__ __forceinline__ float draw(int plane, int i, int j)
+    {
+        if (u) return __ldg(u + ((size_t)plane * n + i) * n + j);
+        uint32_t q = (uint32_t)((plane * n + i) * n + j);
+        if ((q >> 2) != cached_idx) {
+            cached_idx = q >> 2;
+            cached = rng_block(key, kStreamChan, cached_idx);
+        }
+        uint32_t w = (q & 3) == 0 ? cached.x : ((q & 3) == 1 ? cached.y : ((q & 3) == 2 ? cached.z : cached.w));
+        return u24(w);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// communication state: get_graph + channels (env_communication.py:91-157,200-243)
+// ------------------------------------------------------------------------------------------------
+__device__ void comm_update(const EnvArgs &A, const Scratch &S, int64_t b, int lane, const RngKey &key, bool at_reset)
+{
+    const cm_env_desc &d = A.d;
+    const int n = d.n_agents, L = d.n_layers, W = (n + 31) >> 5;
+    // adjacency rows: dr^2 + dc^2 <= 2 Rcom^2 (== cdist <= sqrt(2 Rcom^2) on integer coordinates, :230);
+    // Rcom == 0 means fully connected (:219-223)
+    int deg = 0;
+    for (int item = lane; item < n * W; item += 32) {
+        const int i = item / W, w = item - i * W;
+        uint32_t bits = 0;
+        const int jn = min(32, n - w * 32);
+        if (d.rcom2 < 0) bits = jn == 32 ? 0xFFFFFFFFu : ((1u << jn) - 1u);
+        else {
+            const int ri = S.posA[i] & 0xFF, ci = S.posA[i] >> 8;
+            for (int jj = 0; jj < jn; ++jj) {
+                const uint16_t pj = S.posA[w * 32 + jj];
+                const int dr = ri - (pj & 0xFF), dc = ci - (pj >> 8);
+                bits |= (uint32_t)(dr * dr + dc * dc <= d.rcom2) << jj;
+            }
+        }
+        deg += __popc(bits);
+        if (A.io.adj_bits) A.io.adj_bits[(b * n + i) * W + w] = bits;
+    }
+    if (A.io.ave_deg) {
+        deg = warp_sum(deg);
+        // float32 dist_adj.sum(axis=1).mean(axis=0) (:232); the fully connected branch returns n (:221)
+        if (lane == 0) A.io.ave_deg[b] = d.rcom2 < 0 ? (float)n : __fdiv_rn((float)deg, (float)n);
+    }
+    if (!A.io.chan_bits && d.channel != CM_CH_GE) return;
+    uint32_t *out = A.io.chan_bits ? A.io.chan_bits + (size_t)b * L * n * W : nullptr;
+    ChanSrc src;
+    src.u = A.io.chan_u ? A.io.chan_u + (size_t)b * A.io.chan_planes * n * n : nullptr;
+    src.key = key;
+    src.n = n;
+    src.cached_idx = 0xFFFFFFFFu;
+    if (d.channel == CM_CH_FC || d.channel == CM_CH_FL) {                    // :93-100
+        for (int item = lane; item < L * n * W; item += 32) {
+            const int w = item % W, i = (item / W) % n;
+            const int jn = min(32, n - w * 32);
+            uint32_t bits = jn == 32 ? 0xFFFFFFFFu : ((1u << jn) - 1u);
+            if (d.channel == CM_CH_FL) bits = ((i >> 5) == w) ? (1u << (i & 31)) : 0u;
+            out[item] = bits;
+        }
+    } else if (d.channel == CM_CH_IID) {                                      // get_iid_channel :200-214
+        for (int item = lane; item < L * n * W; item += 32) {
+            const int w = item % W, i = (item / W) % n, l = item / (W * n);
+            const int jn = min(32, n - w * 32);
+            uint32_t bits = 0;
+            for (int jj = 0; jj < jn; ++jj) {
+                const int j = w * 32 + jj;
+                const float eye = (i == j) ? 1.0f : 0.0f;
+                bits |= (uint32_t)(__fadd_rn(src.draw(l, i, j), eye) >= d.p_loss) << jj;
+            }
+            out[item] = bits;
+        }
+    } else {                                                                   // GE :106-157
+        uint32_t *state = A.s.ge_state + (size_t)b * n * W;
+        for (int item = lane; item < n * W; item += 32) {
+            const int i = item / W, w = item - i * W;
+            const int jn = min(32, n - w * 32);
+            const uint32_t full = jn == 32 ? 0xFFFFFFFFu : ((1u << jn) - 1u);
+            uint32_t st;
+            int plane = 0, first_layer = 0;
+            if (at_reset) {
+                if (d.ge_init == 1) st = full;
+                else if (d.ge_init == 0) st = 0u;
+                else {                                  // get_init_state, gilbert_elliot_loss_model.py:84-87
+                    st = 0u;
+                    for (int jj = 0; jj < jn; ++jj) st |= (uint32_t)(src.draw(0, i, w * 32 + jj) >= d.ge_bad_rate) << jj;
+                    plane = 1;
+                }
+                if (d.loss_apply == 0) {
+                    if (out) for (int l = 0; l < L; ++l) out[(l * n + i) * W + w] = st;
+                    state[item] = st;
+                    continue;
+                }
+                if (out) out[(0 * n + i) * W + w] = st;  // include_prev=True: layer 0 is the initial state
+                first_layer = 1;
+            } else {
+                st = state[item];
+            }
+            const int n_trans = d.loss_apply == 0 ? 1 : L - first_layer;
+            for (int tr = 0; tr < n_trans; ++tr) {      // get_next_state_matrix :137-148: g2b draw, then b2g draw
+                uint32_t g2b = 0, b2g = 0;
+                for (int jj = 0; jj < jn; ++jj) {
+                    const int j = w * 32 + jj;
+                    const float eye = (i == j) ? 1.0f : 0.0f;
+                    g2b |= (uint32_t)(__fadd_rn(src.draw(plane, i, j), eye) < d.pgb) << jj;
+                }
+                for (int jj = 0; jj < jn; ++jj) {
+                    const int j = w * 32 + jj;
+                    const float eye = (i == j) ? 1.0f : 0.0f;
+                    b2g |= (uint32_t)(__fadd_rn(src.draw(plane + 1, i, j), eye) < d.pbg) << jj;
+                }
+                plane += 2;
+                st = (st & ~(st & g2b)) | (~st & b2g & full);
+                if (out) {
+                    if (d.loss_apply == 0) for (int l = 0; l < L; ++l) out[(l * n + i) * W + w] = st;
+                    else out[((first_layer + tr) * n + i) * W + w] = st;
+                }
+            }
+            state[item] = st;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reset / spawn (predator_prey.py:150-171,206-232; coverage.py:172-196,221-246)
+// ------------------------------------------------------------------------------------------------
+__device__ void reset_env(const EnvArgs &A, const Scratch &S, const u64 *wall, int64_t b, int lane,
+                          RngKey &key, int &t, int &total_capture)
+{
+    const cm_env_desc &d = A.d;
+    const int n = d.n_agents, p = d.n_preys, G = d.grid;
+    const bool co = d.scenario == CM_COVERAGE;
+    for (int r = lane; r < G; r += 32) { S.occA[r] = 0ull; S.occB[r] = 0ull; }
+    __syncwarp();
+    if (A.io.spawn_agent) {
+        int ep = (int)key.episode;
+        if (ep >= A.io.spawn_episodes) {          // queue exhausted: flag it, reuse the last entry
+            if (lane == 0 && A.io.error_flag) atomicExch(A.io.error_flag, (int)CM_EINVAL);
+            ep = A.io.spawn_episodes - 1;
+        }
+        for (int i = lane; i < n; i += 32) {
+            const uint16_t q = A.io.spawn_agent[((size_t)b * A.io.spawn_episodes + ep) * n + i];
+            S.posA[i] = q;
+            atomicOr(&S.occA[q & 0xFF], 1ull << (q >> 8));
+            if (co) atomicOr(&S.occB[q & 0xFF], 1ull << (q >> 8));     // coverage.py:188 start cells are visited
+        }
+        for (int j = lane; j < p; j += 32) {
+            const uint16_t q = A.io.spawn_prey[((size_t)b * A.io.spawn_episodes + ep) * p + j];
+            S.posP[j] = q;
+            S.alive[j] = 1;
+            atomicOr(&S.occB[q & 0xFF], 1ull << (q >> 8));
+        }
+    } else if (lane == 0) {
+        // sequential rejection sampling on one lane; a reset happens once per episode, not per step
+        const int lo = co ? 1 : 0, span = co ? G - 2 : G;
+        uint32_t ctr = 0;
+        uint4 blk = make_uint4(0, 0, 0, 0);
+        auto draw = [&](int &r, int &c) {
+            if ((ctr & 1u) == 0) blk = rng_block(key, kStreamSpawn, ctr >> 1);
+            const uint32_t wr = (ctr & 1u) ? blk.z : blk.x, wc = (ctr & 1u) ? blk.w : blk.y;
+            ++ctr;
+            r = lo + (int)__umulhi(wr, (uint32_t)span);
+            c = lo + (int)__umulhi(wc, (uint32_t)span);
+        };
+        for (int i = 0; i < n; ++i) {
+            int r = 0, c = 0;
+            for (int tries = 0; tries <= (1 << 20); ++tries) {
+                draw(r, c);
+                const u64 busy = S.occA[r] | (co ? wall[r] : 0ull);
+                if (!((busy >> c) & 1ull)) break;
+            }
+            S.posA[i] = (uint16_t)(r | (c << 8));
+            S.occA[r] |= 1ull << c;
+            if (co) S.occB[r] |= 1ull << c;
+        }
+        for (int j = 0; j < p; ++j) {
+            int r = 0, c = 0;
+            for (int tries = 0; tries <= (1 << 20); ++tries) {
+                draw(r, c);
+                // vacant and no agent in the 4-neighbourhood (predator_prey.py:166)
+                if (!(((S.occA[r] | S.occB[r]) >> c) & 1ull) && count4(S.occA, r, c, G) == 0) break;
+            }
+            S.posP[j] = (uint16_t)(r | (c << 8));
+            S.alive[j] = 1;
+            S.occB[r] |= 1ull << c;
+        }
+    }
+    __syncwarp();
+    t = 0;
+    total_capture = 0;
+    key.episode += 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// observations (predator_prey.py:173-204; coverage.py:198-212,448-480)
+// ------------------------------------------------------------------------------------------------
+__device__ void write_obs(const EnvArgs &A, const Scratch &S, const u64 *wall, int64_t b, int lane, int t)
+{
+    const cm_env_desc &d = A.d;
+    if (!A.io.obs) return;
+    const int n = d.n_agents, G = d.grid, R = d.sensing, w = 2 * R + 1, ww = w * w;
+    const bool co = d.scenario == CM_COVERAGE;
+    const int nwin = co ? 3 : 2, D = nwin * ww + (co ? 2 : 3);
+    // window bits of every agent, lane-parallel
+    for (int i = lane; i < n; i += 32) {
+        const int r = S.posA[i] & 0xFF, c = S.posA[i] >> 8;
+        if (co) {
+            S.win[0 * A.n_pad + i] = window_bits(wall, r, c, R, G, 1);     // wall channel, out-of-grid = wall (:464-466)
+            S.win[1 * A.n_pad + i] = window_bits(S.occA, r, c, R, G, 0);   // agents, self included
+            S.win[2 * A.n_pad + i] = window_bits(S.occB, r, c, R, G, 0);   // visited
+        } else {
+            S.win[0 * A.n_pad + i] = window_bits(S.occA, r, c, R, G, 0);   // agents, self included
+            S.win[1 * A.n_pad + i] = window_bits(S.occB, r, c, R, G, 0);   // preys
+        }
+    }
+    __syncwarp();
+    const float *lut_row = d.lut, *lut_col = d.lut + G, *lut_t = d.lut + 2 * G;
+    float *out = A.io.obs + (size_t)b * n * D;
+    // the env's [n][D] block is contiguous: consecutive lanes store consecutive floats
+    for (int i = 0; i < n; ++i) {
+        const uint32_t w0 = S.win[i], w1 = S.win[A.n_pad + i], w2 = co ? S.win[2 * A.n_pad + i] : 0u;
+        const int r = S.posA[i] & 0xFF, c = S.posA[i] >> 8;
+        for (int e = lane; e < D; e += 32) {
+            float v;
+            if (e < ww) v = (float)((w0 >> e) & 1u);
+            else if (e < 2 * ww) v = (float)((w1 >> (e - ww)) & 1u);
+            else if (e < nwin * ww) v = (float)((w2 >> (e - 2 * ww)) & 1u);
+            else {
+                const int k = e - nwin * ww;
+                v = k == 0 ? __ldg(lut_row + r) : (k == 1 ? __ldg(lut_col + c) : __ldg(lut_t + t));
+            }
+            out[i * D + e] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel: mode 0 = VecEnvExecutor.step, 1 = reset(mask), 2 = comm only
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const cm_env_desc &d = A.d;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = d.n_agents, p = d.n_preys, G = d.grid;
+    const bool co = d.scenario == CM_COVERAGE;
+    u64 *wall = reinterpret_cast<u64 *>(smem);               // [G] shared by the CTA (Coverage)
+    if (co) {
+        for (int r = threadIdx.x; r < G; r += blockDim.x) wall[r] = d.wall_rows[r];
+    }
+    __syncthreads();
+    const Scratch S = carve(smem + 64 * 8 + (size_t)warp * A.warp_bytes, A.n_pad, A.p_pad, G);
+    const int64_t total_warps = (int64_t)gridDim.x * kWarpsPerCta;
+    for (int64_t b = (int64_t)blockIdx.x * kWarpsPerCta + warp; b < A.s.n_envs; b += total_warps) {
+        if (A.mode == 1 && A.mask && !A.mask[b]) continue;
+        __syncwarp();
+        RngKey key;
+        key.env = (uint32_t)(d.env_id0 + b);
+        key.key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
+        key.tick = A.s.tick[b];
+        key.episode = A.s.episode[b];
+        int t = A.s.step_count[b];
+        int total_capture = co ? A.s.total_capture[b] : 0;
+        bool did_reset = false;
+
+        if (A.mode == 1) {
+            reset_env(A, S, wall, b, lane, key, t, total_capture);
+            did_reset = true;
+        } else {
+            // ---- stage the env in shared memory and rebuild the row bitmaps from the positions ----
+            for (int r = lane; r < G; r += 32) { S.occA[r] = 0ull; S.occB[r] = co ? A.s.visited[b * G + r] : 0ull; }
+            for (int i = lane; i < n; i += 32) S.posA[i] = A.s.agent_pos[b * n + i];
+            for (int j = lane; j < p; j += 32) { S.posP[j] = A.s.prey_pos[b * p + j]; S.alive[j] = A.s.prey_alive[b * p + j]; }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) atomicOr(&S.occA[S.posA[i] & 0xFF], 1ull << (S.posA[i] >> 8));
+            for (int j = lane; j < p; j += 32)
+                if (S.alive[j]) atomicOr(&S.occB[S.posP[j] & 0xFF], 1ull << (S.posP[j] >> 8));
+            __syncwarp();
+        }
+
+        if (A.mode == 0) {
+            // =================================== env.step ===================================
+            t += 1;
+            key.tick += 1;                        // every draw of this step is keyed with the new tick
+            int moved = 0, bad = 0;
+            for (int i = lane; i < n; i += 32) {
+                int a = A.io.actions[b * n + i];
+                if (a < 0 || a > 4) { bad = 1; a = 4; }
+                S.act[i] = (int8_t)a;
+                moved += (a != 4);
+            }
+            moved = warp_sum(moved);
+            if (__any_sync(0xFFFFFFFFu, bad) && lane == 0 && A.io.error_flag) atomicExch(A.io.error_flag, (int)CM_EACTION);
+            __syncwarp();
+            int c0 = 0, c2 = 0, c3 = 0, c4 = 0;   // counts (see commarl_b200.h)
+            double reward = 0.0;
+            int env_done = 0;
+            uint8_t success = A.s.success[b];
+            if (!co) {
+                // ---- agents move one after another, lower index first (predator_prey.py:497-500,240-261) ----
+                if (lane == 0) {
+                    for (int i = 0; i < n; ++i) {
+                        const int a = S.act[i];
+                        if (a == 4) continue;
+                        const int r = S.posA[i] & 0xFF, c = S.posA[i] >> 8;
+                        const int nr = r + d_row(a), nc = c + d_col(a);
+                        if (nr < 0 || nr >= G || nc < 0 || nc >= G) continue;
+                        if (((S.occA[nr] | S.occB[nr]) >> nc) & 1ull) continue;
+                        S.occA[r] &= ~(1ull << c);
+                        S.occA[nr] |= 1ull << nc;
+                        S.posA[i] = (uint16_t)(nr | (nc << 8));
+                    }
+                }
+                __syncwarp();
+                // ---- order-independent part of the prey loop, lane-parallel ----
+                // Agents stand still while preys are processed, and prey j's own position / alive flag only
+                // change in its own turn, so: the agent count around prey j (:419/:462), the screening of its
+                // <= 5 move candidates against agent neighbourhoods (:400-404) and the prey_watching flags
+                // (:421-422) do not depend on the processing order.
+                for (int j = lane; j < p; j += 32) {
+                    if (!S.alive[j]) continue;
+                    const int r = S.posP[j] & 0xFF, c = S.posP[j] >> 8;
+                    S.kcnt[j] = (uint8_t)count4(S.occA, r, c, G);
+                    uint32_t words[5];
+                    if (!A.io.prey_cand) {
+                        const uint4 q0 = rng_block(key, kStreamPrey, 2 * j), q1 = rng_block(key, kStreamPrey, 2 * j + 1);
+                        words[0] = q0.x; words[1] = q0.y; words[2] = q0.z; words[3] = q0.w; words[4] = q1.x;
+                    }
+                    int mv = 4;
+                    for (int tr = 0; tr < 5; ++tr) {
+                        const int cnd = A.io.prey_cand ? (int)A.io.prey_cand[((size_t)b * p + j) * 5 + tr]
+                                                       : prey_move_from_bits(words[tr]);
+                        if (count4(S.occA, r + d_row(cnd), c + d_col(cnd), G) == 0) { mv = cnd; break; }
+                    }
+                    S.mv[j] = (int8_t)mv;
+                }
+                int watching = 0;
+                for (int i = lane; i < n; i += 32)
+                    watching += count4(S.occB, S.posA[i] & 0xFF, S.posA[i] >> 8, G) > 0;
+                c3 = warp_sum(watching);
+                __syncwarp();
+                // ---- order-dependent part: capture test against the preys still standing, then the walk ----
+                if (lane == 0) {
+                    int capture = 0, penalty = 0;
+                    for (int j = 0; j < p; ++j) {
+                        if (!S.alive[j]) continue;
+                        const int r = S.posP[j] & 0xFF, c = S.posP[j] >> 8;
+                        const int k = S.kcnt[j];
+                        if (k >= 1) {
+                            int need = d.load;
+                            if (d.load != 2) {   // reward_individual :469-470; edges dict :123-144 (corner 2, border 3, else load)
+                                const int re = (r == 0 || r == G - 1), ce = (c == 0 || c == G - 1);
+                                const int nadj = (re && ce) ? 2 : ((re || ce) ? 3 : d.load);
+                                need = min(d.load, nadj - count4(S.occB, r, c, G));
+                            }
+                            if (need <= k) {     // captured: leaves the grid at once (:301)
+                                ++capture;
+                                S.alive[j] = 0;
+                                S.occB[r] &= ~(1ull << c);
+                                continue;
+                            }
+                            ++penalty;
+                        }
+                        const int mv = S.mv[j];
+                        if (mv != 4) {           // __update_prey_pos :276-299
+                            const int nr = r + d_row(mv), nc = c + d_col(mv);
+                            if (nr >= 0 && nr < G && nc >= 0 && nc < G && !(((S.occA[nr] | S.occB[nr]) >> nc) & 1ull)) {
+                                S.occB[r] &= ~(1ull << c);
+                                S.occB[nr] |= 1ull << nc;
+                                S.posP[j] = (uint16_t)(nr | (nc << 8));
+                            }
+                        }
+                    }
+                    c0 = capture;
+                    c2 = penalty;
+                    // :434 / :480, fixed left-to-right fp64 evaluation, no contraction
+                    reward = __dadd_rn(__dadd_rn(d.step_cost, __dmul_rn(d.capture_reward, (double)capture)),
+                                       __ddiv_rn(__dmul_rn(d.moving_cost, (double)moved), (double)n));
+                    if (d.load == 2) reward = __dadd_rn(reward, __dmul_rn(d.penalty, (double)penalty));
+                }
+                __syncwarp();
+                int any_alive = 0;
+                for (int j = lane; j < p; j += 32) {
+                    any_alive |= S.alive[j];
+                    if (A.io.prey_alive_out) A.io.prey_alive_out[b * p + j] = S.alive[j];
+                }
+                any_alive = __any_sync(0xFFFFFFFFu, any_alive);
+                if (t >= d.max_steps || !any_alive) {            // :511-517
+                    success = any_alive ? 0 : 1;
+                    env_done = 1;
+                }
+            } else {
+                // ---- Coverage.step (coverage.py:319-401): sequential moves over wall | agent rows ----
+                if (lane == 0) {
+                    int cap = 0, pen = 0, rev = 0;
+                    for (int i = 0; i < n; ++i) {
+                        const int a = S.act[i];
+                        if (a == 4) continue;                    // lazy, counted below
+                        const int r = S.posA[i] & 0xFF, c = S.posA[i] >> 8;
+                        const int nr = r + d_row(a), nc = c + d_col(a);
+                        if (nr < 0 || nr >= G || nc < 0 || nc >= G || (((S.occA[nr] | wall[nr]) >> nc) & 1ull)) { ++pen; continue; }
+                        if ((S.occB[nr] >> nc) & 1ull) ++rev;
+                        else { S.occB[nr] |= 1ull << nc; ++cap; }
+                        S.occA[r] &= ~(1ull << c);
+                        S.occA[nr] |= 1ull << nc;
+                        S.posA[i] = (uint16_t)(nr | (nc << 8));
+                    }
+                    const int lazy = n - moved;
+                    c0 = cap; c2 = pen; c3 = rev; c4 = lazy;
+                    total_capture += cap;
+                    double final_reward = 0.0;
+                    if (total_capture == d.n_empty_cells) { final_reward = d.final_reward; env_done = 1; }   // :378-382
+                    if (t >= d.max_steps) { success = env_done ? 1 : 0; env_done = 1; }                       // :385-390
+                    const double dn = (double)n;                                                              // get_reward :300-306
+                    reward = __dadd_rn(d.step_cost, __dmul_rn(d.capture_reward, __ddiv_rn((double)cap, dn)));
+                    reward = __dadd_rn(reward, __dmul_rn(d.moving_cost, __ddiv_rn((double)moved, dn)));
+                    reward = __dadd_rn(reward, __dmul_rn(d.penalty, __ddiv_rn((double)pen, dn)));
+                    reward = __dadd_rn(reward, __dmul_rn(d.lazy_penalty, __ddiv_rn((double)lazy, dn)));
+                    reward = __dadd_rn(reward, __dmul_rn(d.revisit_penalty, __ddiv_rn((double)rev, dn)));
+                    reward = __dadd_rn(reward, final_reward);
+                }
+                __syncwarp();
+                env_done = __shfl_sync(0xFFFFFFFFu, env_done, 0);
+                total_capture = __shfl_sync(0xFFFFFFFFu, total_capture, 0);
+                success = (uint8_t)__shfl_sync(0xFFFFFFFFu, (int)success, 0);
+            }
+            int done = env_done;
+            if (d.max_path_length > 0 && t >= d.max_path_length) done = 1;   // vec_env_executor.py:33-35
+            if (lane == 0) {
+                if (A.io.reward) A.io.reward[b] = reward;
+                if (A.io.done) A.io.done[b] = (uint8_t)done;
+                if (A.io.counts) {
+                    int32_t *cn = A.io.counts + b * 6;
+                    cn[0] = c0; cn[1] = moved; cn[2] = c2; cn[3] = c3; cn[4] = c4; cn[5] = 0;
+                }
+                A.s.success[b] = success;
+                if (A.io.stats) {                 // episode accounting (sampler bookkeeping, ...vectorized_sampler.py:158-227)
+                    double *st = A.io.stats + b * 16;
+                    const double run[7] = {st[0] + reward, st[1] + 1.0, st[2] + c0, st[3] + moved, st[4] + c2, st[5] + c3, st[6] + c4};
+                    if (done) {
+                        st[7] += 1.0; st[8] += run[0]; st[9] += run[1]; st[10] += (double)success;
+                        for (int k = 0; k < 5; ++k) st[11 + k] += run[2 + k];
+                        for (int k = 0; k < 7; ++k) st[k] = 0.0;
+                    } else {
+                        for (int k = 0; k < 7; ++k) st[k] = run[k];
+                    }
+                }
+            }
+            if (done && A.io.auto_reset) {        // vec_env_executor.py:36-43
+                reset_env(A, S, wall, b, lane, key, t, total_capture);
+                did_reset = true;
+            }
+        }
+
+        if (A.mode != 2) {
+            // ---- write the state back ----
+            for (int i = lane; i < n; i += 32) A.s.agent_pos[b * n + i] = S.posA[i];
+            for (int j = lane; j < p; j += 32) { A.s.prey_pos[b * p + j] = S.posP[j]; A.s.prey_alive[b * p + j] = S.alive[j]; }
+            if (co) for (int r = lane; r < G; r += 32) A.s.visited[b * G + r] = S.occB[r];
+            if (lane == 0) {
+                A.s.step_count[b] = t;
+                A.s.tick[b] = key.tick;
+                A.s.episode[b] = key.episode;
+                if (co) A.s.total_capture[b] = total_capture;
+            }
+            write_obs(A, S, wall, b, lane, t);
+        }
+        comm_update(A, S, b, lane, key, A.mode == 2 ? (A.at_reset != 0) : did_reset);
+    }
+}
+
+static int validate(const cm_env_desc *d, const cm_env_state *s, const cm_step_io *io, int mode)
+{
+    if (!d || !s || !io) return CM_EINVAL;
+    if (s->n_envs < 0) return CM_EINVAL;
+    if (d->n_agents < 1 || d->n_agents > CM_MAX_AGENTS || d->n_preys < 0 || d->n_preys > CM_MAX_AGENTS) return CM_EUNSUPPORTED;
+    if (d->grid < 2 || d->grid > CM_MAX_GRID || d->sensing < 0 || d->sensing > 2) return CM_EUNSUPPORTED;
+    if (d->n_layers < 1 || d->n_layers > CM_MAX_LAYERS) return CM_EUNSUPPORTED;
+    if (d->scenario == CM_PREDATOR_PREY) {
+        if (d->load < 2 || d->load > 4) return CM_EUNSUPPORTED;          // capv undefined otherwise (predator_prey.py:77-79)
+        if (!s->prey_pos || !s->prey_alive) return CM_EINVAL;
+    } else if (d->scenario == CM_COVERAGE) {
+        if (d->n_preys != 0) return CM_EINVAL;
+        if (!d->wall_rows || !s->visited || !s->total_capture) return CM_EINVAL;
+    } else return CM_EINVAL;
+    if (d->channel < CM_CH_FC || d->channel > CM_CH_GE) return CM_EINVAL;
+    if (d->channel == CM_CH_GE) {
+        if (d->ge_init == -1 && d->loss_apply == 0) return CM_EUNSUPPORTED;  // broken in the reference (env_communication.py:121)
+        if (!s->ge_state) return CM_EINVAL;
+    }
+    if (!s->agent_pos || !s->step_count || !s->success || !s->episode || !s->tick) return CM_EINVAL;
+    if (!d->lut && io->obs) return CM_EINVAL;
+    if (mode == 0 && !io->actions) return CM_EINVAL;
+    if (io->spawn_agent && (io->spawn_episodes < 1 || (d->n_preys > 0 && !io->spawn_prey))) return CM_EINVAL;
+    if (io->chan_u) {
+        int need = d->channel == CM_CH_IID ? d->n_layers : (d->channel == CM_CH_GE ? 2 * d->n_layers + 1 : 0);
+        if (io->chan_planes < need) return CM_EINVAL;
+    }
+    return CM_OK;
+}
+
+static int launch(const cm_env_desc *d, const cm_env_state *s, const cm_step_io *io, const uint8_t *mask, int mode,
+                  int at_reset, cudaStream_t stream)
+{
+    int rc = validate(d, s, io, mode);
+    if (rc) return rc;
+    if (s->n_envs == 0) return CM_OK;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ENODEVICE);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ECUDA);
+    EnvArgs A;
+    A.d = *d; A.s = *s; A.io = *io; A.mask = mask; A.mode = mode; A.at_reset = at_reset;
+    A.n_pad = (d->n_agents + 7) & ~7;
+    A.p_pad = (d->n_preys + 7) & ~7;
+    A.warp_bytes = (env_warp_bytes(A.n_pad, A.p_pad, d->grid) + 15) & ~15;
+    const size_t smem = 64 * 8 + (size_t)kWarpsPerCta * A.warp_bytes;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
+    }
+    int ctas_per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, env_kernel, kWarpsPerCta * 32, smem);
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    // persistent grid: a whole number of CTAs per SM, warps stride over the envs
+    int64_t want = (s->n_envs + kWarpsPerCta - 1) / kWarpsPerCta;
+    int64_t cap = (int64_t)sms * ctas_per_sm;
+    int grid = (int)(want < cap ? want : cap);
+    env_kernel<<<grid, kWarpsPerCta * 32, smem, stream>>>(A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
+    return CM_OK;
+}
+
+}  // namespace cm
+
+extern "C" int cm_env_reset(const cm_env_desc *desc, const cm_env_state *state, const cm_step_io *io,
+                            const uint8_t *mask, cm_stream_t stream)
+{
+    return cm::launch(desc, state, io, mask, 1, 1, (cudaStream_t)stream);
+}
+
+extern "C" int cm_env_step(const cm_env_desc *desc, const cm_env_state *state, const cm_step_io *io, cm_stream_t stream)
+{
+    return cm::launch(desc, state, io, nullptr, 0, 0, (cudaStream_t)stream);
+}
+
+extern "C" int cm_comm_update(const cm_env_desc *desc, const cm_env_state *state, const cm_step_io *io, int at_reset,
+                              cm_stream_t stream)
+{
+    return cm::launch(desc, state, io, nullptr, 2, at_reset, (cudaStream_t)stream);
+}

@@ -1,0 +1,250 @@
+"""CommCategoricalMLPPolicy with the reference's call signature and state_dict, backed by the fused
+CUDA forward (cm_policy_forward, include/commarl_b200.h).
+
+Mirrors com_marl/torch/policies/comm_categorical_mlp_policy.py:8-140 and
+com_marl/torch/modules/comm_base_net.py:11-110:
+  * same constructor arguments and defaults, same ``state_dict`` parameter names/shapes,
+    so reference checkpoints load with ``load_state_dict``;
+  * ``get_actions(obs_n, avail_actions_n, dist_adj, channels, greedy)`` — the rollout call — runs the
+    hand-written kernel (no torch ops on the hot path) and returns what the reference returns;
+  * ``forward(..., get_actions=False)`` / ``entropy`` / ``log_likelihood`` — the differentiable training
+    path used by the PPO update, which is outside the rollout hot path — is the same
+    formula written with torch ops so that autograd works.
+"""
+import ctypes as C
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+from torch import nn
+from torch.distributions import Categorical
+
+from . import _native as N
+
+
+class _MLP(nn.Module):
+    """Parameter layout of garage's MultiHeadedMLPModule with one head
+    (garage/torch/modules/multi_headed_mlp_module.py:60-100): _layers.i.linear, _output_layers.0.linear."""
+
+    def __init__(self, input_dim, hidden_sizes, output_dim, output_tanh):
+        super().__init__()
+        self._layers = nn.ModuleList()
+        prev = input_dim
+        for size in hidden_sizes:
+            lin = nn.Linear(prev, size)
+            nn.init.xavier_uniform_(lin.weight)
+            nn.init.zeros_(lin.bias)
+            self._layers.append(nn.Sequential(OrderedDict(linear=lin)))
+            prev = size
+        lin = nn.Linear(prev, output_dim)
+        nn.init.xavier_uniform_(lin.weight)
+        nn.init.zeros_(lin.bias)
+        self._output_layers = nn.ModuleList([nn.Sequential(OrderedDict(linear=lin))])
+        self._output_tanh = output_tanh
+
+    def forward(self, x):
+        for layer in self._layers:
+            x = torch.tanh(layer(x))
+        x = self._output_layers[0](x)
+        return torch.tanh(x) if self._output_tanh else x
+
+
+class _Attention(nn.Module):
+    """attention_module.py:15-51, attention_type='general'"""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.linear_in = nn.Linear(dim, dim, bias=False)
+
+    def forward(self, query):
+        context = query.transpose(-2, -1)
+        return torch.softmax(torch.matmul(self.linear_in(query), context), dim=-1)
+
+
+class _GraphConv(nn.Module):
+    """graph_conv_module.py:22-72: weight is (in, out), U(+-1/sqrt(out)) init"""
+
+    def __init__(self, dim, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(dim, dim))
+        stdv = 1.0 / math.sqrt(dim)
+        self.weight.data.uniform_(-stdv, stdv)
+        if bias:
+            self.bias = nn.Parameter(torch.empty(dim))
+            self.bias.data.uniform_(-stdv, stdv)
+        else:
+            self.register_parameter("bias", None)
+
+    def forward(self, inputs, A):
+        out = torch.matmul(A, torch.matmul(inputs, self.weight))
+        return torch.tanh(out + self.bias) if self.bias is not None else torch.tanh(out)
+
+
+class CommCategoricalMLPPolicy(nn.Module):
+    def __init__(self, env_spec, n_agents, encoder_hidden_sizes=(128,), embedding_dim=64, attention_type="general",
+                 n_gcn_layers=2, residual=True, gcn_bias=True, categorical_mlp_hidden_sizes=(128, 64, 32),
+                 name="comm_categorical_mlp_policy", device="cuda", seed=1):
+        super().__init__()
+        if not hasattr(env_spec.action_space, "n"):
+            raise AssertionError("Categorical policy only works with akro.Discrete action space.")
+        if tuple(encoder_hidden_sizes) != (128,) or embedding_dim != 64 or tuple(categorical_mlp_hidden_sizes) != (128, 64, 32):
+            raise NotImplementedError("the fused kernel is specialised for the reference's default sizes "
+                                      "(encoder (128,), embedding 64, head (128, 64, 32))")
+        if attention_type != "general":
+            raise NotImplementedError("only attention_type='general' (the reference default) is implemented")
+        self.name, self.device = name, torch.device(device)
+        self.comm, self.centralized, self.step, self.eps = True, True, 0, 1e-12
+        self.residual = bool(residual)
+        self._n_agents = int(n_agents)
+        self._cent_obs_dim = env_spec.observation_space.flat_dim
+        self._dec_obs_dim = int(self._cent_obs_dim / n_agents)
+        self._action_dim = env_spec.action_space.n
+        self._embedding_dim = embedding_dim
+        self.n_gcn_layers = int(n_gcn_layers)
+        self.seed = int(seed)
+        self.encoder = _MLP(self._dec_obs_dim, encoder_hidden_sizes, embedding_dim, output_tanh=True)
+        self.attention_layer = _Attention(embedding_dim)
+        self.gcn_layers = nn.ModuleList([_GraphConv(embedding_dim, gcn_bias) for _ in range(self.n_gcn_layers)])
+        self.categorical_output_layer = _MLP(embedding_dim, categorical_mlp_hidden_sizes, self._action_dim, output_tanh=False)
+        self.to(self.device)
+        self._blob = None
+        self._blob_sig = None
+
+    # ---- weight blob (layout in include/commarl_b200.h) ----------------------------------------------
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def weight_blob(self):
+        """float32 device blob, every dense weight k-major; rebuilt when a parameter changed."""
+        sig = self._signature()
+        if self._blob is None or sig != self._blob_sig:
+            sd = self.state_dict()
+            L, E = self.n_gcn_layers, self._embedding_dim
+            parts = [sd["encoder._layers.0.linear.weight"].t(), sd["encoder._layers.0.linear.bias"],
+                     sd["encoder._output_layers.0.linear.weight"].t(), sd["encoder._output_layers.0.linear.bias"],
+                     sd["attention_layer.linear_in.weight"].t()]
+            parts += [sd[f"gcn_layers.{l}.weight"] for l in range(L)]
+            parts += [sd.get(f"gcn_layers.{l}.bias", torch.zeros(E, device=self.device)) for l in range(L)]
+            for i in range(3):
+                parts += [sd[f"categorical_output_layer._layers.{i}.linear.weight"].t(),
+                          sd[f"categorical_output_layer._layers.{i}.linear.bias"]]
+            parts += [sd["categorical_output_layer._output_layers.0.linear.weight"].t(),
+                      sd["categorical_output_layer._output_layers.0.linear.bias"]]
+            blob = torch.cat([p.detach().to(self.device, torch.float32).contiguous().reshape(-1) for p in parts])
+            expect = N.lib().cm_policy_blob_floats(self._dec_obs_dim, L)
+            assert blob.numel() == expect, (blob.numel(), expect)
+            self._blob, self._blob_sig = blob.contiguous(), sig
+        return self._blob
+
+    # ---- device fast path (no host copies) --------------------------------------------------------------
+    def act_device(self, obs, adj_bits=None, chan_bits=None, avail_bits=None, sample_u=None, tick=None, episode=None,
+                   greedy=False, probs=None, logits=None, attention=None, actions=None, env_id0=0):
+        """Fused forward on device tensors.  obs: float32 (B, n, D) / (B, n*D).  Outputs are written into the
+        given tensors (allocate once, reuse: the call is CUDA-graph capturable)."""
+        n, D, L = self._n_agents, self._dec_obs_dim, self.n_gcn_layers
+        B = obs.shape[0]
+        desc = N.PolicyDesc(n, D, L, int(self.residual), int(greedy), self.seed, env_id0)
+        io = N.PolicyIO()
+        io.n_envs = B
+        io.weights = N.ptr(self.weight_blob())
+        for k, v in (("obs", obs), ("adj_bits", adj_bits), ("chan_bits", chan_bits), ("avail_bits", avail_bits),
+                     ("sample_u", sample_u), ("tick", tick), ("episode", episode), ("probs", probs), ("logits", logits),
+                     ("attention", attention), ("actions", actions)):
+            setattr(io, k, N.ptr(v))
+        with torch.cuda.device(self.device):
+            N.check("cm_policy_forward", N.lib().cm_policy_forward(C.byref(desc), C.byref(io), N.stream_ptr()))
+
+    @staticmethod
+    def pack_mask(dense, n):
+        """dense float32 (..., n, n) device tensor -> int32 bit rows (..., n, ceil(n/32))"""
+        dense = dense.contiguous()
+        rows = dense.numel() // n
+        W = (n + 31) // 32
+        bits = torch.empty(dense.shape[:-1] + (W,), dtype=torch.int32, device=dense.device)
+        with torch.cuda.device(dense.device):
+            N.check("cm_mask_pack", N.lib().cm_mask_pack(N.ptr(dense), N.ptr(bits), rows, n, N.stream_ptr()))
+        return bits
+
+    # ---- reference call surface --------------------------------------------------------------------------
+    def _run_host(self, obs_n, avail_actions_n, dist_adj, channels, greedy, want_actions):
+        n, D, L, dev = self._n_agents, self._dec_obs_dim, self.n_gcn_layers, self.device
+        obs = torch.as_tensor(np.asarray(obs_n), dtype=torch.float32)
+        single = obs.dim() == 1
+        obs = obs.reshape(-1, n, D).to(dev, non_blocking=True)
+        B = obs.shape[0]
+        adj = torch.as_tensor(np.asarray(dist_adj), dtype=torch.float32).reshape(B, n, n).to(dev, non_blocking=True)
+        ch = torch.as_tensor(np.asarray(channels), dtype=torch.float32).reshape(B, L, n, n).to(dev, non_blocking=True)
+        av = torch.as_tensor(np.asarray(avail_actions_n), dtype=torch.float32).reshape(B, n, self._action_dim)
+        weights = torch.tensor([1, 2, 4, 8, 16], dtype=torch.float32)
+        avail_bits = ((av != 0).float() * weights).sum(-1).to(torch.uint8).to(dev, non_blocking=True)
+        probs = torch.empty((B, n, self._action_dim), dtype=torch.float32, device=dev)
+        attn = torch.empty((B, n, n), dtype=torch.float32, device=dev)
+        actions = torch.empty((B, n), dtype=torch.int8, device=dev) if want_actions else None
+        # host-call sampling stream: keyed by the policy's own call counter (the env arrays are not visible here)
+        tick = torch.full((B,), self.step & 0x7FFFFFFF, dtype=torch.int32, device=dev)
+        episode = torch.full((B,), self._host_calls & 0xFFFFFF, dtype=torch.int32, device=dev)
+        self._host_calls += 1
+        self.act_device(obs, self.pack_mask(adj, n), self.pack_mask(ch, n), avail_bits, None, tick, episode, greedy,
+                        probs, None, attn, actions)
+        return single, probs, attn, actions
+
+    _host_calls = 0
+
+    def forward(self, obs_n, avail_actions_n, dist_adj, channels, get_actions=False):
+        """comm_categorical_mlp_policy.py:48-96.  get_actions=True: numpy in, CPU tensors out (kernel path).
+        get_actions=False: torch tensors shaped (n_paths, T, ...) in, differentiable (torch ops)."""
+        n = self._n_agents
+        if get_actions:
+            single, probs, attn, _ = self._run_host(obs_n, avail_actions_n, dist_adj, channels, False, False)
+            probs, attn = probs.cpu(), attn.cpu()
+            if single:
+                probs, attn = probs[0], attn[0]
+            return Categorical(probs=probs), attn
+        obs_n = obs_n.reshape(obs_n.shape[:-1] + (n, -1))
+        avail_actions_n = avail_actions_n.reshape(avail_actions_n.shape[:-1] + (n, -1))
+        channels = channels.reshape(channels.shape[:-2] + (len(self.gcn_layers), n, n))
+        if dist_adj.shape[-2:] != torch.Size((n, n)):
+            dist_adj = dist_adj.reshape(dist_adj.shape[:-1] + (n, n))
+        E = self.encoder(obs_n)
+        M = self.attention_layer(E)
+        H = E
+        for l, gcn in enumerate(self.gcn_layers):
+            A = M * dist_adj * channels[..., l, :, :]
+            A = A / (A.sum(dim=-1, keepdim=True) + self.eps)
+            H = gcn(H, A)
+        X = E + H if self.residual else H
+        dist = Categorical(logits=self.categorical_output_layer(X))
+        masked = dist.probs * avail_actions_n
+        masked = masked / masked.sum(dim=-1, keepdim=True)
+        return Categorical(probs=masked), M
+
+    def get_actions(self, obs_n, avail_actions_n, dist_adj, channels, greedy=False):
+        """comm_categorical_mlp_policy.py:98-119: (actions int64 (B,n)|(n,), {'action_probs': [...],
+        'attention_weights': [...]})"""
+        with torch.no_grad():
+            single, probs, attn, actions = self._run_host(obs_n, avail_actions_n, dist_adj, channels, greedy, True)
+            probs, attn, actions = probs.cpu().numpy(), attn.cpu().numpy(), actions.cpu().numpy().astype(np.int64)
+            if single:
+                probs, attn, actions = probs[0], attn[0], actions[0]
+            infos = {"action_probs": [probs[i] for i in range(len(actions))],
+                     "attention_weights": [attn[i, :] for i in range(len(actions))]}
+            return actions, infos
+
+    def entropy(self, observations, avail_actions, dist_adj, channels):
+        dists_n, _ = self.forward(observations, avail_actions, dist_adj, channels)
+        return dists_n.entropy().mean(axis=-1)
+
+    def log_likelihood(self, observations, avail_actions, dist_adj, channels, actions):
+        dists_n, _ = self.forward(observations, avail_actions, dist_adj, channels)
+        return dists_n.log_prob(actions).sum(axis=-1)
+
+    def reset(self, dones=None):
+        return
+
+    def grad_norm(self):
+        return np.sqrt(np.sum([p.grad.norm(2).item() ** 2 for p in self.parameters()]))
+
+    @property
+    def recurrent(self):
+        return False

@@ -1,0 +1,207 @@
+/*
+ * commarl_b200.h — C ABI of the B200-native batched rollout engine for Com-MARL.
+ *
+ * The reference (cnuns/Com-MARL) is 100 % Python and has no FFI/plugin layer; its
+ * rollout path is reached through three duck-typed Python interfaces.  This header is the thin C
+ * boundary underneath our Python mirror of those interfaces (com_marl_b200/).  Each entry point names
+ * the reference code it replaces.  Conventions (all entry points):
+ *
+ *   - extern "C", plain pointers and sizes only; no torch / C++ types.
+ *   - every pointer inside cm_env_state / cm_step_io / cm_policy_io is a DEVICE pointer owned by the
+ *     caller (the Python side hands in torch tensor data_ptr()s); descriptors are HOST structs read at
+ *     call time.  The library never allocates, never synchronises, never touches a global/default
+ *     stream: work is enqueued on the given stream (a cudaStream_t) and is CUDA-graph capturable.
+ *   - returns CM_OK (0) or a negative cm_error; never throws.  cm_strerror() names the code.
+ *   - there is no CPU path: without a device every compute call returns CM_ENODEVICE.
+ *
+ * Data layout (device, SoA, env-major, one row of each array per environment instance):
+ *   agent_pos  u16 [B][n]     row | col << 8            (PredatorPrey: 0..map-1, Coverage: 1..map)
+ *   prey_pos   u16 [B][p]     same packing; stale for dead preys, like the reference's prey_pos dict
+ *   prey_alive u8  [B][p]
+ *   visited    u64 [B][G]     Coverage visited map, one 64-bit word per grid row, bit c = column c
+ *   step_count i32 [B]        env._step_count
+ *   total_capture i32 [B]     Coverage.total_capture_cnt
+ *   success    u8  [B]        env.success, latched exactly like the reference (coverage.py:385-390 quirk)
+ *   episode    u32 [B]        number of resets so far (RNG key + index into an injected spawn queue)
+ *   tick       u32 [B]        steps since creation, never reset (RNG key)
+ *   ge_state   u32 [B][n][W]  last Gilbert-Elliot link state, bit j of word j/32 of row i;  W = ceil(n/32)
+ * Outputs of a step / reset:
+ *   obs        f32 [B][n][D]  == np.concatenate(obs_n) of the wrappers (predatorprey_wrapper.py:61-66)
+ *   reward     f64 [B]        fp64, reference evaluation order
+ *   done       u8  [B]        np.all(dones) | time limit (vec_env_executor.py:33-35)
+ *   counts     i32 [B][6]     PP: capture, moved, penalty, watching, 0, 0;  CO: capture, moved, penalty,
+ *                              revisit, lazy, 0 — the integer sums the reference's reward_details are means of
+ *   prey_alive_out u8 [B][p]  env_infos['prey_alive'] of the step (pre-reset)
+ *   adj_bits   u32 [B][n][W]  dist_adj rows as bit masks
+ *   chan_bits  u32 [B][L][n][W] channels[l] rows as bit masks
+ *   ave_deg    f32 [B]
+ */
+#ifndef COMMARL_B200_H_
+#define COMMARL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CM_ABI_VERSION 1
+#define CM_MAX_AGENTS 256   /* n, p */
+#define CM_MAX_GRID 64      /* grid side incl. Coverage's wall border */
+#define CM_MAX_LAYERS 4     /* n_gcn_layers */
+#define CM_ACTIONS 5
+
+typedef void *cm_stream_t;  /* cudaStream_t */
+
+enum cm_scenario { CM_PREDATOR_PREY = 0, CM_COVERAGE = 1 };
+enum cm_channel { CM_CH_FC = 0, CM_CH_FL = 1, CM_CH_IID = 2, CM_CH_GE = 3 };
+enum cm_error {
+    CM_OK = 0,
+    CM_EINVAL = -1,       /* null pointer / bad size */
+    CM_EUNSUPPORTED = -2, /* n > CM_MAX_AGENTS, grid > CM_MAX_GRID, load not in {2,3,4}, GE_INIT=-1 with loss_apply=0 ... */
+    CM_ECUDA = -3,        /* a CUDA runtime call failed; cm_last_cuda_error() has the code */
+    CM_ENODEVICE = -4,
+    CM_EACTION = -5       /* an action outside 0..4 was seen ('Action Not found!', predator_prey.py:255) */
+};
+
+/* Scenario description (host).  Replaces the attribute soup PredatorPrey.__init__ / Coverage.__init__ /
+ * init_communication build from `params` (predator_prey.py:51-108, coverage.py:39-109,
+ * env_communication.py:10-77). */
+typedef struct cm_env_desc {
+    int32_t scenario;          /* cm_scenario */
+    int32_t n_agents;          /* n */
+    int32_t n_preys;           /* p (PredatorPrey) */
+    int32_t grid;              /* G: map (PredatorPrey) or map + 2 (Coverage, wall border included) */
+    int32_t sensing;           /* Rsen */
+    int32_t max_steps;         /* T = env._max_steps */
+    int32_t max_path_length;   /* VecEnvExecutor time limit; 0 = none */
+    int32_t load;              /* PredatorPrey capture load: 2 -> reward_default, 3/4 -> reward_individual */
+    int32_t n_layers;          /* L = n_gcn_layers */
+    int32_t n_empty_cells;     /* Coverage: free cells - n (coverage.py:228-230) */
+    int32_t rcom2;             /* 2*Rcom^2, adjacency <=> dr^2+dc^2 <= rcom2; -1 = fully connected (Rcom == 0) */
+    int32_t channel;           /* cm_channel */
+    int32_t loss_apply;        /* GE: 1 = a transition per GCN layer, 0 = one per env step */
+    int32_t ge_init;           /* GE_INIT: 1 good, 0 bad, -1 proportional */
+    float p_loss;              /* IID: float32(Ploss) */
+    float pgb, pbg;            /* GE: float32(Pgb), float32(Pbg) */
+    float ge_bad_rate;         /* GE: float32(Pgb / (Pgb + Pbg)) */
+    double capture_reward, step_cost, moving_cost, penalty, lazy_penalty, revisit_penalty, final_reward;
+                               /* signed as the reference stores them (predator_prey.py:66-69, coverage.py:86-92) */
+    uint64_t seed;             /* Philox key for generated streams */
+    int64_t env_id0;           /* global id of env 0 of this shard: results do not depend on the sharding */
+    const uint64_t *wall_rows; /* DEVICE u64 [G]: Coverage wall bitmap rows (border + obstacles); NULL for PredatorPrey */
+    const float *lut;          /* DEVICE f32 [G + G + T + 1]: obs scalar features row[r], col[c], time[t] */
+} cm_env_desc;
+
+typedef struct cm_env_state {
+    int64_t n_envs;            /* B */
+    uint16_t *agent_pos;
+    uint16_t *prey_pos;
+    uint8_t *prey_alive;
+    uint64_t *visited;
+    int32_t *step_count;
+    int32_t *total_capture;
+    uint8_t *success;
+    uint32_t *episode;
+    uint32_t *tick;
+    uint32_t *ge_state;
+} cm_env_state;
+
+typedef struct cm_step_io {
+    /* inputs */
+    const int8_t *actions;     /* [B][n] (step only) */
+    const int8_t *prey_cand;   /* [B][p][5] pre-drawn prey-move candidates, or NULL -> Philox */
+    const uint16_t *spawn_agent; /* [B][E][n] injected spawn queue (packed like agent_pos), or NULL -> Philox */
+    const uint16_t *spawn_prey;  /* [B][E][p] */
+    int32_t spawn_episodes;    /* E */
+    const float *chan_u;       /* [B][planes][n][n] pre-drawn channel uniforms, or NULL -> Philox */
+    int32_t chan_planes;
+    int32_t auto_reset;        /* 1: reset finished envs inside the step (VecEnvExecutor), obs/comm are post-reset */
+    /* outputs (any may be NULL to skip, except where noted) */
+    float *obs;
+    double *reward;
+    uint8_t *done;
+    int32_t *counts;
+    uint8_t *prey_alive_out;
+    uint32_t *adj_bits;
+    uint32_t *chan_bits;
+    float *ave_deg;
+    int32_t *error_flag;       /* DEVICE i32[1]: set to CM_EACTION when an invalid action is seen (optional) */
+    double *stats;             /* [B][16] per-env episode accounting updated by every step (optional):
+                                  running  [0] return [1] length [2..6] counts[0..4]
+                                  finished [7] episodes [8] return sum [9] length sum [10] success sum [11..15] counts sums
+                                  — the sums behind AverageReturn / SuccessRate / AverageCaptureCount ... that
+                                  centralized_ma_ppo.py:345-372 logs from `paths` */
+} cm_step_io;
+
+/* Weight blob of CommCategoricalMLPPolicy (comm_categorical_mlp_policy.py + comm_base_net.py), float32,
+ * every dense weight stored K-major ([in][out]) so that a warp reads consecutive output columns:
+ *   enc_w1 [D][H1]  enc_b1 [H1]  enc_w2 [H1][E]  enc_b2 [E]  att_w [E][E]
+ *   gcn_w[l] [E][E]  gcn_b[l] [E]    for l < L
+ *   head_w1 [E][C1] head_b1 [C1] head_w2 [C1][C2] head_b2 [C2] head_w3 [C2][C3] head_b3 [C3] head_w4 [C3][5] head_b4 [5]
+ * with the reference's default sizes H1=128, E=64, (C1,C2,C3)=(128,64,32); cm_policy_blob_floats() gives
+ * the length, com_marl_b200.policy packs a reference state_dict into it. */
+typedef struct cm_policy_desc {
+    int32_t n_agents;          /* n */
+    int32_t obs_dim;           /* D per agent */
+    int32_t n_layers;          /* L */
+    int32_t residual;          /* comm_categorical_mlp_policy.py:74-77 */
+    int32_t greedy;            /* argmax instead of sampling (:109-112) */
+    uint64_t seed;
+    int64_t env_id0;
+} cm_policy_desc;
+
+typedef struct cm_policy_io {
+    int64_t n_envs;            /* B */
+    const float *weights;      /* blob described above */
+    const float *obs;          /* [B][n][D] */
+    const uint32_t *adj_bits;  /* [B][n][W] or NULL = all ones */
+    const uint32_t *chan_bits; /* [B][L][n][W] or NULL = all ones */
+    const uint8_t *avail_bits; /* [B][n] bit a = action a available, or NULL = all available */
+    const float *sample_u;     /* [B][n] pre-drawn uniforms for action sampling, or NULL -> Philox(tick, episode) */
+    const uint32_t *tick;      /* [B] RNG key words (the env state's arrays); may be NULL when sample_u or greedy */
+    const uint32_t *episode;   /* [B] */
+    float *probs;              /* [B][n][5] masked, renormalised action probabilities */
+    float *logits;             /* [B][n][5] raw head output, or NULL */
+    float *attention;          /* [B][n][n] unmasked attention softmax (agent_infos['attention_weights']), or NULL */
+    int8_t *actions;           /* [B][n], or NULL */
+} cm_policy_io;
+
+int cm_abi_version(void);
+const char *cm_strerror(int err);
+int cm_last_cuda_error(void);
+int cm_device_count(void);
+
+/* env.reset() for the envs whose mask byte is non-zero (mask == NULL: all), followed by the observation
+ * and update_communication_state of those envs.
+ * Replaces PredatorPrey.reset / Coverage.reset (predator_prey.py:206-232, coverage.py:221-246) as
+ * called by VecEnvExecutor.reset (vec_env_executor.py:47-54). */
+int cm_env_reset(const cm_env_desc *desc, const cm_env_state *state, const cm_step_io *io,
+                 const uint8_t *mask, cm_stream_t stream);
+
+/* One VecEnvExecutor.step over all B envs (vec_env_executor.py:19-45): PredatorPrey.step /
+ * Coverage.step (predator_prey.py:494-519, coverage.py:319-401), time limit, auto-reset, observation
+ * windows (predator_prey.py:173-204, coverage.py:198-212,448-480) and update_communication_state
+ * (env_communication.py:91-157: get_graph, FC/FL/IID/GE channels). */
+int cm_env_step(const cm_env_desc *desc, const cm_env_state *state, const cm_step_io *io, cm_stream_t stream);
+
+/* update_communication_state alone, from the positions currently in `state` (env_communication.py:91-157,
+ * 200-243; gilbert_elliot_loss_model.py:84-87,121-150).  at_reset selects the GE (re)initialisation branch. */
+int cm_comm_update(const cm_env_desc *desc, const cm_env_state *state, const cm_step_io *io, int at_reset,
+                   cm_stream_t stream);
+
+/* CommCategoricalMLPPolicy.forward(get_actions=True) + sampling for B envs in one fused kernel
+ * (comm_categorical_mlp_policy.py:48-119, comm_base_net.py:80-108, attention_module.py:26-51,
+ * graph_conv_module.py:51-72, categorical_mlp_module.py:64-80, multi_headed_mlp_module.py:134-149). */
+int cm_policy_forward(const cm_policy_desc *desc, const cm_policy_io *io, cm_stream_t stream);
+size_t cm_policy_blob_floats(int32_t obs_dim, int32_t n_layers);
+
+/* dense float32 masks (the reference's dist_adj (B,n,n) / channels (B,L,n,n)) <-> bit rows */
+int cm_mask_pack(const float *dense, uint32_t *bits, int64_t rows, int32_t n, cm_stream_t stream);
+int cm_mask_unpack(const uint32_t *bits, float *dense, int64_t rows, int32_t n, cm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMMARL_B200_H_ */
