@@ -16,7 +16,7 @@ CH_FC, CH_FL, CH_IID, CH_GE = 0, 1, 2, 3
 MAX_AGENTS, MAX_GRID, MAX_LAYERS = 256, 64, 4
 
 EXPORTS = ("cm_abi_version", "cm_strerror", "cm_last_cuda_error", "cm_device_count", "cm_env_reset", "cm_env_step",
-           "cm_comm_update", "cm_policy_forward", "cm_policy_blob_floats", "cm_mask_pack", "cm_mask_unpack")
+           "cm_comm_update", "cm_policy_forward", "cm_policy_blob_floats", "cm_policy_workspace_bytes", "cm_mask_pack", "cm_mask_unpack")
 
 
 class EnvDesc(C.Structure):
@@ -40,7 +40,7 @@ class StepIO(C.Structure):
                 ("spawn_prey", C.c_void_p), ("spawn_episodes", C.c_int32), ("chan_u", C.c_void_p),
                 ("chan_planes", C.c_int32), ("auto_reset", C.c_int32), ("obs", C.c_void_p), ("reward", C.c_void_p),
                 ("done", C.c_void_p), ("counts", C.c_void_p), ("prey_alive_out", C.c_void_p),
-                ("adj_bits", C.c_void_p), ("chan_bits", C.c_void_p), ("ave_deg", C.c_void_p),
+                ("success_out", C.c_void_p), ("adj_bits", C.c_void_p), ("chan_bits", C.c_void_p), ("ave_deg", C.c_void_p),
                 ("error_flag", C.c_void_p), ("stats", C.c_void_p)]
 
 
@@ -52,7 +52,8 @@ class PolicyDesc(C.Structure):
 class PolicyIO(C.Structure):
     _fields_ = [("n_envs", C.c_int64)] + \
                [(k, C.c_void_p) for k in ("weights", "obs", "adj_bits", "chan_bits", "avail_bits", "sample_u", "tick",
-                                          "episode", "probs", "logits", "attention", "actions")]
+                                          "episode", "probs", "logits", "attention", "actions", "workspace")] + \
+               [("workspace_bytes", C.c_size_t)]
 
 
 class NativeError(RuntimeError):
@@ -84,6 +85,8 @@ def lib():
     L.cm_policy_forward.argtypes = [C.POINTER(PolicyDesc), C.POINTER(PolicyIO), C.c_void_p]
     L.cm_policy_blob_floats.restype = C.c_size_t
     L.cm_policy_blob_floats.argtypes = [C.c_int32, C.c_int32]
+    L.cm_policy_workspace_bytes.restype = C.c_size_t
+    L.cm_policy_workspace_bytes.argtypes = [C.c_int32, C.c_int64]
     L.cm_mask_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     L.cm_mask_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     for fn in ("cm_env_reset", "cm_env_step", "cm_comm_update", "cm_policy_forward", "cm_mask_pack", "cm_mask_unpack"):

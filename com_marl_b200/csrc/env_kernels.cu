@@ -563,6 +563,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
                     cn[0] = c0; cn[1] = moved; cn[2] = c2; cn[3] = c3; cn[4] = c4; cn[5] = 0;
                 }
                 A.s.success[b] = success;
+                if (A.io.success_out) A.io.success_out[b] = success;
                 if (A.io.stats) {                 // episode accounting (sampler bookkeeping, ...vectorized_sampler.py:158-227)
                     double *st = A.io.stats + b * 16;
                     const double run[7] = {st[0] + reward, st[1] + 1.0, st[2] + c0, st[3] + moved, st[4] + c2, st[5] + c3, st[6] + c4};
@@ -634,25 +635,31 @@ static int launch(const cm_env_desc *d, const cm_env_state *s, const cm_step_io 
     int rc = validate(d, s, io, mode);
     if (rc) return rc;
     if (s->n_envs == 0) return CM_OK;
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ENODEVICE);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ECUDA);
     EnvArgs A;
     A.d = *d; A.s = *s; A.io = *io; A.mask = mask; A.mode = mode; A.at_reset = at_reset;
     A.n_pad = (d->n_agents + 7) & ~7;
     A.p_pad = (d->n_preys + 7) & ~7;
     A.warp_bytes = (env_warp_bytes(A.n_pad, A.p_pad, d->grid) + 15) & ~15;
     const size_t smem = 64 * 8 + (size_t)kWarpsPerCta * A.warp_bytes;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
+    // launch geometry is cached per (device, smem) so that steady-state calls issue nothing but the launch
+    // (keeps the call CUDA-graph capturable)
+    static thread_local struct { int dev; size_t smem; int ctas_per_sm; int sms; } cache = {-1, 0, 0, 0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ENODEVICE);
+    if (cache.dev != dev || cache.smem != smem) {
+        int sms = 0, ctas = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ECUDA);
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
+        }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, env_kernel, kWarpsPerCta * 32, smem) != cudaSuccess)
+            return set_cuda_error(cudaGetLastError(), CM_ECUDA);
+        cache.dev = dev; cache.smem = smem; cache.ctas_per_sm = ctas < 1 ? 1 : ctas; cache.sms = sms;
     }
-    int ctas_per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, env_kernel, kWarpsPerCta * 32, smem);
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
     // persistent grid: a whole number of CTAs per SM, warps stride over the envs
     int64_t want = (s->n_envs + kWarpsPerCta - 1) / kWarpsPerCta;
-    int64_t cap = (int64_t)sms * ctas_per_sm;
+    int64_t cap = (int64_t)cache.sms * cache.ctas_per_sm;
     int grid = (int)(want < cap ? want : cap);
     env_kernel<<<grid, kWarpsPerCta * 32, smem, stream>>>(A);
     cudaError_t e = cudaGetLastError();

@@ -1,0 +1,67 @@
+"""Multi-GPU plumbing: one process per GPU, envs sharded contiguously, no data-path collective.
+
+Env instances are independent, so each rank steps its own slice; the RNG streams are keyed
+by GLOBAL env id, which makes results independent of the sharding.  The only exchange is the all-gather of
+the per-rank episode-statistics vector once per obtain_samples (NCCL over NVLink on GPUs; gloo in the CPU
+tests) — a few dozen bytes, latency bound.
+"""
+import os
+from typing import Dict, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .rollout import STAT_KEYS
+
+
+def shard_range(n_envs_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of the global env ids owned by `rank`; sizes differ by at most one."""
+    base, rem = divmod(int(n_envs_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def init_from_env(backend: str = None) -> Tuple[int, int, int]:
+    """(rank, local_rank, world) from torchrun's environment; initialises the default process group when
+    WORLD_SIZE > 1.  Single-process runs need no process group."""
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local_rank, world
+
+
+def gather_stats(local: torch.Tensor, group=None) -> torch.Tensor:
+    """all-gather of the per-rank float64 [len(STAT_KEYS)] sums -> [world, len(STAT_KEYS)]"""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local.reshape(1, -1).clone()
+    world = dist.get_world_size(group)
+    out = torch.empty((world, local.numel()), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous().reshape(1, -1), group=group)
+    return out
+
+
+def summarize_stats(per_rank: torch.Tensor, scenario: str, n_agents: int) -> Dict[str, float]:
+    """The per-epoch tabular keys the reference logs from `paths` (centralized_ma_ppo.py:345-372), from the
+    whole-job sums: AverageReturn, SuccessRate, AverageStepCount and the per-episode count means."""
+    tot = per_rank.sum(dim=0).double().cpu()
+    s = dict(zip(STAT_KEYS, tot.tolist()))
+    ep = max(s["episodes"], 1.0)
+    n = float(n_agents)
+    out = dict(NumEpisodes=s["episodes"], AverageReturn=s["return_sum"] / ep, SuccessRate=s["success_sum"] / ep,
+               AverageStepCount=s["length_sum"] / ep)
+    if scenario == "pp":      # capture / penalty are counts, moved / watching are per-step means over agents
+        out.update(AverageCaptureCount=s["c0_sum"] / ep, AverageMovingCount=s["moved_sum"] / n / ep,
+                   AveragePenaltyCount=s["c2_sum"] / ep, AverageVariable=s["c3_sum"] / n / ep, AverageVar2=0.0)
+    else:                     # every Coverage detail is a per-step mean over agents
+        out.update(AverageCaptureCount=s["c0_sum"] / n / ep, AverageMovingCount=s["moved_sum"] / n / ep,
+                   AveragePenaltyCount=s["c2_sum"] / n / ep, AverageVariable=s["c3_sum"] / n / ep,
+                   AverageVar2=s["c4_sum"] / n / ep)
+    return out

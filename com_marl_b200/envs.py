@@ -67,6 +67,7 @@ class BatchedEnv:
         self.done = z((B,), torch.uint8)
         self.counts = z((B, 6), torch.int32)
         self.prey_alive_out = z((B, max(p, 1)), torch.uint8)
+        self.success_out = z((B,), torch.uint8)
         self.adj_bits = z((B, n, self.W), torch.int32)
         self.chan_bits = z((B, L, n, self.W), torch.int32)
         self.ave_deg = z((B,), torch.float32)
@@ -113,8 +114,8 @@ class BatchedEnv:
         io.chan_planes = 0 if chan_u is None else int(chan_u.shape[1])
         io.spawn_agent, io.spawn_prey, io.spawn_episodes = N.ptr(self._spawn_agent), N.ptr(self._spawn_prey), self._spawn_episodes
         io.auto_reset = int(self.auto_reset if auto_reset is None else auto_reset)
-        for k in ("obs", "reward", "done", "counts", "prey_alive_out", "adj_bits", "chan_bits", "ave_deg", "error_flag",
-                  "stats"):
+        for k in ("obs", "reward", "done", "counts", "prey_alive_out", "success_out", "adj_bits", "chan_bits", "ave_deg",
+                  "error_flag", "stats"):
             t = out[k] if (out is not None and k in out) else getattr(self, k)
             setattr(io, k, N.ptr(t))
         return io

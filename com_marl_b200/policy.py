@@ -110,6 +110,7 @@ class CommCategoricalMLPPolicy(nn.Module):
         self.to(self.device)
         self._blob = None
         self._blob_sig = None
+        self._workspace = None
 
     # ---- weight blob (layout in include/commarl_b200.h) ----------------------------------------------
     def _signature(self):
@@ -152,6 +153,11 @@ class CommCategoricalMLPPolicy(nn.Module):
                      ("sample_u", sample_u), ("tick", tick), ("episode", episode), ("probs", probs), ("logits", logits),
                      ("attention", attention), ("actions", actions)):
             setattr(io, k, N.ptr(v))
+        if n > 64:      # large teams: per-CTA scratch, allocated once and reused
+            need = N.lib().cm_policy_workspace_bytes(n, B)
+            if self._workspace is None or self._workspace.numel() * 4 < need:
+                self._workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
+            io.workspace, io.workspace_bytes = N.ptr(self._workspace), self._workspace.numel() * 4
         with torch.cuda.device(self.device):
             N.check("cm_policy_forward", N.lib().cm_policy_forward(C.byref(desc), C.byref(io), N.stream_ptr()))
 

@@ -124,6 +124,7 @@ typedef struct cm_step_io {
     uint8_t *done;
     int32_t *counts;
     uint8_t *prey_alive_out;
+    uint8_t *success_out;      /* [B] env.success as the sampler reads it when the step reports done */
     uint32_t *adj_bits;
     uint32_t *chan_bits;
     float *ave_deg;
@@ -166,6 +167,8 @@ typedef struct cm_policy_io {
     float *logits;             /* [B][n][5] raw head output, or NULL */
     float *attention;          /* [B][n][n] unmasked attention softmax (agent_infos['attention_weights']), or NULL */
     int8_t *actions;           /* [B][n], or NULL */
+    float *workspace;          /* teams with n > 64 only: cm_policy_workspace_bytes() bytes of scratch (stays L2 resident) */
+    size_t workspace_bytes;
 } cm_policy_io;
 
 int cm_abi_version(void);
@@ -196,6 +199,8 @@ int cm_comm_update(const cm_env_desc *desc, const cm_env_state *state, const cm_
  * graph_conv_module.py:51-72, categorical_mlp_module.py:64-80, multi_headed_mlp_module.py:134-149). */
 int cm_policy_forward(const cm_policy_desc *desc, const cm_policy_io *io, cm_stream_t stream);
 size_t cm_policy_blob_floats(int32_t obs_dim, int32_t n_layers);
+/* scratch the forward needs for teams larger than one 64-row tile (0 for n <= 64) */
+size_t cm_policy_workspace_bytes(int32_t n_agents, int64_t n_envs);
 
 /* dense float32 masks (the reference's dist_adj (B,n,n) / channels (B,L,n,n)) <-> bit rows */
 int cm_mask_pack(const float *dense, uint32_t *bits, int64_t rows, int32_t n, cm_stream_t stream);

@@ -45,8 +45,10 @@ def test_policy_kernel_matches_reference_golden(name):
     assert np.abs(logits.cpu().numpy() - c.logits).max() <= 1e-5 * scale
     # and the differentiable torch path of the same module (used by the PPO update) agrees too
     with torch.no_grad():
+        # shaped like process_samples hands them over: adj (.., n*n), channels (.., L*n, n)  (…vectorized_sampler.py:176,183)
         d2, _ = pol.forward(torch.from_numpy(c.obs.reshape(c.B, -1)).to(dev), torch.from_numpy(c.avail.reshape(c.B, -1)).to(dev),
-                            torch.from_numpy(c.adj.astype(np.float32)).to(dev), torch.from_numpy(c.chan.astype(np.float32)).to(dev))
+                            torch.from_numpy(c.adj.astype(np.float32).reshape(c.B, -1)).to(dev),
+                            torch.from_numpy(c.chan.astype(np.float32).reshape(c.B, c.L * c.n, c.n)).to(dev))
     assert np.abs(d2.probs.cpu().numpy() - c.probs).max() <= 1e-5
 
 

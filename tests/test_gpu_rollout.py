@@ -1,0 +1,113 @@
+"""GPU tests of the fused device rollout (policy forward + sampling -> env step -> comm update), its CUDA-graph
+replay, the in-kernel episode accounting and the garage `paths` contract of DeviceRolloutSampler."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import ref_harness  # noqa: E402  (only its params helper is used; it never touches /root/reference here)
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("pp", 20, 2, 0.08, 4, 0.2, 256, {"max_env_steps": 30}), ("co", 10, 1, 0.03, 2, 0.0, 512, {"max_env_steps": 40}),
+         ("pp", 30, 2, 0.08, 4, 0.0, 24, {"max_env_steps": 12})]
+
+
+def _mk(scen, m, sen, den, cap, loss, over, seed=9):
+    from com_marl_b200.scenario import ScenarioSpec
+    params = ref_harness.scenario_params(scen, m, sen, den, cap=cap, loss=loss, **over)
+    return params, ScenarioSpec.from_params(scen, params, seed=seed)
+
+
+@pytest.mark.parametrize("cfg", CASES, ids=["pp20", "co10", "pp30_large_team"])
+def test_fused_rollout_matches_oracle(cfg):
+    """Every iteration of the device loop is replayed on the oracle with the kernel's own sampled actions:
+    observations, rewards, dones and masks stay bit-identical across auto-resets; the sampled actions equal the
+    oracle's inverse-CDF draw on the kernel's probabilities (Philox action stream)."""
+    from com_marl_b200.rollout import RolloutEngine, make_policy
+    scen, m, sen, den, cap, loss, B, over = cfg
+    params, spec = _mk(scen, m, sen, den, cap, loss, over)
+    pol = make_policy(spec)
+    eng = RolloutEngine(spec, pol, B, ring=8, use_graph=True)
+    oenv = orc.OracleVecEnv(orc.spec_from_params(scen, params, seed=9), B)
+    eng.reset()
+    oenv.reset()
+    n = spec.n_agents
+    ret = np.zeros(B); fin_ret = 0.0; fin_eps = 0; fin_len = 0; length = np.zeros(B)
+    for chunk in range(10):
+        eng.run_chunk()      # chunk 0 eager, then one captured graph replayed
+        t = {k: v.cpu().numpy() for k, v in eng.traj.items()}
+        for k in range(eng.K):
+            assert np.array_equal(t["obs"][k], oenv.obs), f"obs differ at chunk {chunk} step {k}"
+            want = oenv.sample_actions(t["probs"][k])
+            assert np.array_equal(t["actions"][k], want), "sampled actions differ from the stream specification"
+            oenv.step(t["actions"][k])
+            assert np.array_equal(t["reward"][k], oenv.reward)
+            assert np.array_equal(t["done"][k], oenv.done)
+            assert np.array_equal(t["success"][k], oenv.success)
+            ret += oenv.reward; length += 1
+            d = oenv.done.astype(bool)
+            fin_ret += ret[d].sum(); fin_len += length[d].sum(); fin_eps += int(d.sum())
+            ret[d] = 0; length[d] = 0
+        assert np.array_equal(t["obs"][eng.K], oenv.obs)
+    eng.env.check_errors()
+    st = eng.local_stats().cpu().numpy()
+    assert fin_eps > 0 and st[0] == fin_eps and st[2] == fin_len
+    assert st[1] == pytest.approx(fin_ret, rel=1e-12)
+    assert eng.agent_steps() == 10 * eng.K * B * n
+    assert eng.kernel_launches == 2 * 10 * eng.K
+
+
+def test_graph_replay_equals_eager():
+    from com_marl_b200.rollout import RolloutEngine, make_policy
+    params, spec = _mk("pp", 10, 1, 0.08, 2, 0.3, {"max_env_steps": 20})
+    pol = make_policy(spec)
+    a = RolloutEngine(spec, pol, 300, ring=5, use_graph=True)
+    b = RolloutEngine(spec, pol, 300, ring=5, use_graph=False)
+    for e in (a, b):
+        e.reset()
+        e.run(40)
+    for k in ("obs", "actions", "reward", "done", "chan_bits"):
+        assert torch.equal(a.traj[k], b.traj[k]), k
+    assert torch.equal(a.env.stats, b.env.stats)
+
+
+def test_sampler_paths_contract():
+    """obtain_samples returns the reference's path dicts (keys / shapes of SURVEY.md §8a a21)."""
+    from types import SimpleNamespace
+    from com_marl_b200.envs import PredatorPreyWrapper
+    from com_marl_b200.rollout import make_policy
+    from com_marl_b200.sampler import DeviceRolloutSampler
+    params = ref_harness.scenario_params("pp", 10, 1, 0.08, cap=2, loss=0.2, max_env_steps=20)
+    env = PredatorPreyWrapper(centralized=True, other_agent_visible=True, params=params)
+    spec = env.spec_b200
+    n, D, p, L = spec.n_agents, spec.obs_dim, spec.n_preys, spec.n_layers
+    algo = SimpleNamespace(policy=make_policy(spec), max_path_length=20)
+    sampler = DeviceRolloutSampler(algo, env, n_envs=16, chunk=10)
+    sampler.start_worker()
+    paths = sampler.obtain_samples(0, batch_size=16 * 20 * n)
+    assert sum(len(pth["rewards"]) for pth in paths) * n >= 16 * 20 * n
+    for pth in paths:
+        T = len(pth["rewards"])
+        assert 1 <= T <= 20
+        assert pth["observations"].shape == (T, n * D) and pth["actions"].shape == (T, n) and pth["actions"].dtype == np.int64
+        assert pth["avail_actions"].shape == (T, n * 5) and pth["dones"].shape == (T,) and pth["dones"][-1]
+        assert not pth["dones"][:-1].any()
+        assert pth["dist_adjs"].shape == (T, n * n) and pth["channels"].shape == (T, L * n, n)
+        assert pth["attentions"].shape == (T, n, n) and pth["agent_infos"]["action_probs"].shape == (T, n, 5)
+        assert pth["env_infos"]["prey_alive"].shape == (T, p) and pth["success"].shape == (16,)
+        assert pth["rewards_details"].shape == (T,) and set(pth["rewards_details"][0]) >= {"reward", "capture_cnt", "move_cnt"}
+        assert np.allclose(pth["agent_infos"]["action_probs"].sum(-1), 1.0, atol=1e-5)
+        assert np.allclose(pth["attentions"].sum(-1), 1.0, atol=1e-5)
+        # the time feature of the first observation is t/T = 0: the path starts at a reset observation
+        assert pth["observations"][0].reshape(n, D)[0, -1] == 0.0
+        # a path that ended early is a success (all preys captured), one that hit the limit is not
+        assert bool(pth["success"][0]) == (not pth["env_infos"]["prey_alive"][-1].any())
+    short = sampler.obtain_samples(1, batch_size=50 * n, whole_paths=False)
+    assert sum(len(pth["rewards"]) for pth in short) * n <= 50 * n + n * 20
+    sampler.shutdown_worker()

@@ -1,0 +1,152 @@
+"""CPU-side tests: the C-ABI library loads and exports what include/commarl_b200.h declares, the product's
+host logic (scenario derivation, sharding, statistics, path truncation) agrees with the oracle's independent
+restatement, the N>1 plumbing works under gloo with world_size 2, and the product refuses to run without a GPU."""
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import EnvCase, env_cases
+from oracle import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from com_marl_b200 import _native as N
+    header = open(os.path.join(ROOT, "include", "commarl_b200.h")).read()
+    declared = set(re.findall(r"\b(cm_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(N.EXPORTS), declared ^ set(N.EXPORTS)
+    lib = N.lib()
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+    assert lib.cm_abi_version() == 1
+    assert lib.cm_strerror(N.CM_EACTION) == b"Action Not found!"
+    assert lib.cm_policy_blob_floats(21, 2) == 42309 and lib.cm_policy_blob_floats(53, 2) == 46405
+    assert lib.cm_policy_workspace_bytes(32, 100) == 0 and lib.cm_policy_workspace_bytes(200, 4) == 4 * 3 * 64 * 256 * 4
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    from com_marl_b200 import _native as N
+    from com_marl_b200.envs import BatchedEnv
+    from com_marl_b200.scenario import ScenarioSpec
+    assert N.lib().cm_device_count() == 0
+    buf = np.zeros(64, dtype=np.float32)
+    assert N.lib().cm_mask_pack(buf.ctypes.data, buf.ctypes.data, 1, 4, None) == N.CM_ENODEVICE
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        BatchedEnv(ScenarioSpec.from_cli("pp", 10, 1, 0.04), 4)
+
+
+@pytest.mark.parametrize("name", env_cases())
+def test_scenario_spec_matches_oracle_derivation(name):
+    """com_marl_b200.scenario (product) vs oracle.spec_from_params (checker): two independent restatements of
+    PredatorPrey/Coverage.__init__ + init_communication, and both match what the reference reported."""
+    from com_marl_b200.scenario import ScenarioSpec
+    case = EnvCase(name)
+    spec = ScenarioSpec.from_params(case.scenario, case.params, max_path_length=case.max_path_length,
+                                    channel_type="GE" if case.ge else None)
+    o = orc.spec_from_params(case.scenario, case.params, max_path_length=case.max_path_length, ge=case.ge)
+    assert (spec.n_agents, spec.n_preys, spec.grid, spec.sensing, spec.max_steps, spec.n_layers) == \
+        (o["n"], o["p"], o["G"], o["R"], o["T"], o["L"])
+    assert spec.obs_dim == o["D"] == case.z["obs"].shape[1] // case.n
+    assert spec.rcom2 == o["rcom2"] and spec.channel == o["chan_type"]
+    assert spec.rcom == case.meta["Rcom"]
+    for k in ("capture_reward", "step_cost", "moving_cost", "penalty", "lazy_penalty", "revisit_penalty", "final_reward"):
+        assert getattr(spec, k) == o[k], k
+    assert np.array_equal(spec.lut()[:2 * spec.grid], np.concatenate([o["lut_row"], o["lut_col"]]))
+    if case.scenario == "pp":
+        assert np.array_equal(spec.lut()[2 * spec.grid:], o["lut_t"])
+    else:
+        assert np.array_equal(spec.wall, o["wall"])
+        assert spec.n_empty_cells == o["n_empty_cells"] == case.meta["n_empty_cells"]
+        rows = spec.wall_rows()
+        back = ((rows[:, None] >> np.arange(spec.grid, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.uint8)
+        assert np.array_equal(back, spec.wall)
+    assert spec.bound_return == pytest.approx(case.meta["bound_return"], rel=0, abs=1e-12)
+    d = spec.to_desc(None, None)
+    assert d.p_loss == np.float32(case.meta["pl"])
+
+
+def test_scenario_cli_sizing_rule():
+    """n_agents = int(int(den*100) * (map/10)^2) for the five BASELINE.json configs"""
+    from com_marl_b200.scenario import ScenarioSpec
+    want = {("pp", 10, 1, 0.04): (4, 21), ("co", 10, 1, 0.03): (3, 29), ("pp", 20, 2, 0.08): (32, 53),
+            ("co", 30, 2, 0.06): (54, 77), ("pp", 50, 2, 0.08): (200, 53)}
+    for (scen, m, sen, den), (n, D) in want.items():
+        s = ScenarioSpec.from_cli(scen, m, sen, den, cap=4 if m > 10 else 2)
+        assert (s.n_agents, s.obs_dim) == (n, D)
+    with pytest.raises(ValueError):
+        ScenarioSpec.from_cli("pp", 10, 1, 0.04, cap=5)
+    with pytest.raises(ValueError):
+        ScenarioSpec.from_cli("pp", 10, 1, 0.04, loss=0.2, channel_type="GE", GE_INIT=-1, loss_apply=0)
+    with pytest.raises(ValueError):
+        ScenarioSpec.from_cli("co", 15, 1, 0.03)
+
+
+def test_shard_range_partitions_everything():
+    from com_marl_b200.distributed import shard_range
+    for total in (0, 1, 7, 16384, 65537):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_summarize_stats():
+    from com_marl_b200.distributed import summarize_stats
+    per_rank = torch.tensor([[2, 30.0, 400, 1, 6, 800, 3, 120, 0], [2, 10.0, 400, 0, 2, 800, 1, 40, 0]], dtype=torch.float64)
+    s = summarize_stats(per_rank, "pp", 4)
+    assert s["NumEpisodes"] == 4 and s["AverageReturn"] == 10.0 and s["SuccessRate"] == 0.25
+    assert s["AverageStepCount"] == 200 and s["AverageCaptureCount"] == 2 and s["AverageMovingCount"] == 100.0
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    from com_marl_b200 import distributed as D
+    r, lr, w = D.init_from_env(backend="gloo")
+    lo, hi = D.shard_range(1001, r, w)
+    local = torch.tensor([hi - lo, 10.0 * (r + 1), 3, 1, 0, 0, 0, 0, 0], dtype=torch.float64)
+    out = D.gather_stats(local)
+    q.put((r, out.tolist()))
+    torch.distributed.destroy_process_group()
+
+
+def test_stats_all_gather_world_size_2_gloo():
+    """The only collective on the path (episode statistics all-gather), on CPU with gloo and two ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0] == res[1]
+    assert [row[0] for row in res[0]] == [501.0, 500.0] and [row[1] for row in res[0]] == [10.0, 20.0]
+
+
+def test_truncate_paths():
+    from com_marl_b200.sampler import _truncate_paths
+    mk = lambda T: dict(rewards=np.zeros(T), observations=np.zeros((T, 8)), env_infos={"prey_alive": np.zeros((T, 2))},  # noqa: E731
+                        success=np.zeros(3))
+    out = _truncate_paths([mk(10), mk(10), mk(10)], max_samples=4 * 14, n_agents=4)
+    assert [len(p["rewards"]) for p in out] == [10, 4]
+    assert out[1]["observations"].shape == (4, 8) and out[1]["env_infos"]["prey_alive"].shape == (4, 2)
