@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — agent-steps/s of the batched rollout hot path (env step + comm + comm-GNN policy forward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one rollout iteration over the whole batch: cm_policy_forward (forward + action sampling) followed by
+cm_env_step (PredatorPrey/Coverage step, auto-reset, observation windows, adjacency + channel masks).  The default
+workload is BASELINE.json configs[1]: Coverage --map 10 --sen 1 --den 0.03 --loss 0, 16384 envs per B200 (weak
+scaling: every GPU steps its own 16384 envs; the only collective is the episode-statistics all-gather after the
+timed region).  One JSON line is printed by rank 0:
+
+  value      device-resident rollout: inputs live in HBM, K steps replayed from one CUDA graph.
+  e2e        the same loop through the host-buffer API (BatchedEnv.step_host + policy.get_actions_host): every step
+             copies observations + masks host->device for the policy, actions host->device for the env and reads
+             observations / rewards / dones / masks / probabilities back into pinned host memory.
+  roofline   the dominant kernel (policy forward, fp32 FFMA) against the measured bf16 tensor peak, plus the env
+             kernel against the measured HBM copy bandwidth (kernel durations from CUDA events around each launch).
+  cpu_baseline  the oracle port (C env oracle + numpy policy) on the box's host cores, bounded sample.
+
+`--impl reference` times that CPU port on all host cores (the reference itself is pure Python and is not present
+on the GPU box; oracle/ is its pinned restatement).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (scenario, map, sen, den, cap, loss, envs per GPU)  — BASELINE.json configs[0..4]
+    "c1": ("pp", 10, 1, 0.04, 2, 0.0, 16384),
+    "c2": ("co", 10, 1, 0.03, 2, 0.0, 16384),
+    "c3": ("pp", 20, 2, 0.08, 4, 0.2, 65536),
+    "c4": ("co", 30, 2, 0.06, 2, 0.1, 16384),
+    "c5": ("pp", 50, 2, 0.08, 4, 0.0, 2048),
+}
+WORKLOAD_TEXT = {
+    "c1": "Predator-Prey --map 10 --sen 1 --den 0.04 --cap 2 --loss 0",
+    "c2": "Coverage --map 10 --sen 1 --den 0.03 --loss 0, 16384 batched envs per B200",
+    "c3": "Predator-Prey --map 20 --sen 2 --den 0.08 --cap 4 --loss 0.2 (IID drops), 65536 envs per B200",
+    "c4": "Coverage --map 30 --sen 2 --den 0.06 --loss 0.1",
+    "c5": "Predator-Prey --map 50 --sen 2 --den 0.08 --cap 4",
+}
+METRIC = "agent-steps/sec, batched PP/Coverage step+comm+policy rollout"
+UNIT = "agent-steps/s"
+
+
+def params_for(cfg):
+    scen, m, sen, den, cap, loss, _ = CONFIGS[cfg]
+    n = int(int(den * 100) * (m / 10) ** 2)
+    p = dict(grid_size=m, Rsen=sen, n_agents=n, n_gcn_layers=2, loss_apply=1, mode="train", trpl=loss, trRcom=9, rm=0)
+    if scen == "pp":
+        p.update(n_preys=n, load=cap, max_env_steps=200, capture_reward=10, step_cost=0.1, penalty=0)
+    else:
+        p.update(n_groups=3, obstComplex="Easy", load=2, capture_reward=2, step_cost=0, penalty=1, revisit_penalty=0.5,
+                 lazy_penalty=1, max_env_steps=400)
+    return scen, p
+
+
+def policy_flops_per_agent(D, n, L):
+    return 2 * (D * 128 + 128 * 64) + 2 * 64 * 64 + 2 * 64 * n + L * (2 * 64 * 64 + 2 * n * 64) + \
+        2 * (64 * 128 + 128 * 64 + 64 * 32 + 32 * 5)
+
+
+def env_bytes_per_agent_step(spec):
+    """4 D [obs write] + S [state r/w] + (1+L) ceil(n/32) 4 [adj + channel rows] + E/n"""
+    n, L, G = spec.n_agents, spec.n_layers, spec.grid
+    S = 11.0 if spec.scenario == "pp" else 5.0 + 2.0 * ((G * G + 7) // 8) / n
+    masks = (1 + L) * ((n + 31) // 32) * 4
+    if spec.channel == 3:
+        masks += 2 * L * ((n + 31) // 32) * 4
+    return 4.0 * spec.obs_dim + S + masks + 16.0 / n
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU port (oracle): the reference arm and the cpu_baseline leg
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    cfg, B, steps, seed, env_id0 = args
+    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = "1"
+    from oracle import oracle as orc
+    scen, params = params_for(cfg)
+    ospec = orc.spec_from_params(scen, params, seed=seed)
+    env = orc.OracleVecEnv(ospec, B, env_id0=env_id0)
+    rng = np.random.default_rng(seed)
+    n, D, L = ospec["n"], ospec["D"], ospec["L"]
+    w = _random_weights(D, L, rng)
+    env.reset()
+    # one untimed iteration, then the timed sample
+    t0 = None
+    for s in range(steps + 1):
+        if s == 1:
+            t0 = time.perf_counter()
+        _, probs, _ = orc.policy_forward(w, env.obs, None, env.adj, env.chan)
+        acts = env.sample_actions(probs)
+        env.step(acts)
+    return B * n * steps, time.perf_counter() - t0
+
+
+def _random_weights(D, L, rng):
+    def xav(o, i):
+        lim = np.sqrt(6.0 / (i + o))
+        return rng.uniform(-lim, lim, size=(o, i)).astype(np.float32)
+    w = {"encoder._layers.0.linear.weight": xav(128, D), "encoder._layers.0.linear.bias": np.zeros(128, np.float32),
+         "encoder._output_layers.0.linear.weight": xav(64, 128), "encoder._output_layers.0.linear.bias": np.zeros(64, np.float32),
+         "attention_layer.linear_in.weight": xav(64, 64)}
+    for l in range(L):
+        w[f"gcn_layers.{l}.weight"] = rng.uniform(-0.125, 0.125, size=(64, 64)).astype(np.float32)
+        w[f"gcn_layers.{l}.bias"] = rng.uniform(-0.125, 0.125, size=64).astype(np.float32)
+    for i, (o, k) in enumerate(((128, 64), (64, 128), (32, 64))):
+        w[f"categorical_output_layer._layers.{i}.linear.weight"] = xav(o, k)
+        w[f"categorical_output_layer._layers.{i}.linear.bias"] = np.zeros(o, np.float32)
+    w["categorical_output_layer._output_layers.0.linear.weight"] = xav(5, 32)
+    w["categorical_output_layer._output_layers.0.linear.bias"] = np.zeros(5, np.float32)
+    return w
+
+
+def cpu_port_throughput(cfg, procs, envs_per_proc, steps):
+    """P independent processes, each a single-threaded oracle rollout of its own envs; rates are summed
+    (the reference cannot use more than one env per core either)."""
+    import multiprocessing as mp
+    from oracle import oracle as orc
+    orc.build()
+    jobs = [(cfg, envs_per_proc, steps, 1 + i, i * envs_per_proc) for i in range(procs)]
+    if procs == 1:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(1):               # "cores": 1 means one thread, BLAS included
+            res = [_cpu_worker(jobs[0])]
+    else:
+        for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[k] = "1"                  # inherited by the spawned workers before they import numpy
+        with mp.get_context("spawn").Pool(procs) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    return sum(a / t for a, t in res), sum(a for a, _ in res)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    scen, params = params_for(args.config)
+    n = params["n_agents"]
+    # bounded sample: every "step" of this arm is one policy+env iteration over envs_per_proc envs on every core
+    envs_per_proc = max(4, min(256, 20000 // max(n, 1)))
+    steps_cpu = max(10, min(args.steps, 200))    # bounded: the whole run stays within a few minutes
+    t0 = time.perf_counter()
+    rate, agent_steps = cpu_port_throughput(args.config, cores, envs_per_proc, steps_cpu)
+    wall = time.perf_counter() - t0
+    line = {"metric": METRIC, "value": rate, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * cores * envs_per_proc * n / rate,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+int", "data": "synthetic",
+            "config": {"workload": WORKLOAD_TEXT[args.config], "config": args.config},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{cores} processes x {envs_per_proc} envs x {steps_cpu} steps of the oracle port "
+                                       f"(C env oracle + numpy fp32 policy, 1 thread each), wall {wall:.1f}s"},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t_lo, t_hi):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mxc = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx = mxc
+            if t_lo - 0.05 <= ts <= t_hi + 0.15:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # timed region shorter than one sample: fall back to every sample taken
+            sm = [float(ln.split(",")[1]) for _, ln in self.lines if len(ln.split(",")) >= 9] or [0.0]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from com_marl_b200 import distributed as D
+    from com_marl_b200.rollout import RolloutEngine, make_policy
+    from com_marl_b200.scenario import ScenarioSpec
+
+    rank, local_rank, world = D.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a GPU: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    scen, params = params_for(args.config)
+    spec = ScenarioSpec.from_params(scen, params, seed=1)
+    B = args.envs or CONFIGS[args.config][6]
+    n, Dobs, L = spec.n_agents, spec.obs_dim, spec.n_layers
+    ring = args.ring
+    steps = max(ring, (args.steps // ring) * ring)
+    warm = max(3 * ring, ((args.warmup + ring - 1) // ring) * ring)
+    pol = make_policy(spec, device=dev)
+    eng = RolloutEngine(spec, pol, B, device=dev, env_id0=rank * B, ring=ring, use_graph=True)
+    eng.reset()
+    eng.run(warm)                                   # untimed: first chunk eager, graph captured on the second
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.25)
+    # ---------------- value: device-resident rollout ----------------
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.kernel_launches
+    barrier(); torch.cuda.synchronize(dev)
+    t_lo = time.time()
+    ev0.record()
+    eng.run(steps)
+    ev1.record()
+    torch.cuda.synchronize(dev); barrier()
+    t_hi = time.time()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.kernel_launches - launches0
+    eng.env.check_errors()
+    # ---------------- per-kernel durations (CUDA events around each launch, eager) ----------------
+    kt = {"policy": [], "env": []}
+    probe_steps = min(steps, 4 * ring)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(probe_steps)]
+    eng._carry()
+    for i in range(probe_steps):
+        k = i % ring
+        if i and k == 0:
+            eng._carry()
+        t, e = eng.traj, eng.env
+        evs[i][0].record()
+        pol.act_device(t["obs"][k], t["adj_bits"][k], t["chan_bits"][k], tick=e.tick, episode=e.episode, probs=t["probs"][k],
+                       actions=t["actions"][k], env_id0=e.env_id0)
+        evs[i][1].record()
+        e.step(t["actions"][k], out=dict(obs=t["obs"][k + 1], adj_bits=t["adj_bits"][k + 1], chan_bits=t["chan_bits"][k + 1],
+                                         ave_deg=t["ave_deg"][k + 1], reward=t["reward"][k], done=t["done"][k],
+                                         counts=t["counts"][k], prey_alive_out=t["prey_alive_out"][k], success_out=t["success"][k]))
+        evs[i][2].record()
+    torch.cuda.synchronize(dev)
+    for a, b, c in evs[2:]:
+        kt["policy"].append(a.elapsed_time(b))
+        kt["env"].append(b.elapsed_time(c))
+    pol_ms, env_ms = float(np.mean(kt["policy"])), float(np.mean(kt["env"]))
+    eng.steps_done += probe_steps
+    clock_info = clocks.stop(t_lo, t_hi) if rank == 0 else None
+    # ---------------- e2e: host buffers through the public step / get_actions API ----------------
+    from com_marl_b200.envs import BatchedEnv
+    henv = BatchedEnv(spec, B, device=dev, env_id0=rank * B)
+    out = henv.reset_host()
+    e2e_steps = max(5, min(steps, args.e2e_steps))
+    for _ in range(3):
+        acts, _ = pol.get_actions_host(out["obs"], out["adj_bits"], out["chan_bits"])
+        out = henv.step_host(acts)
+    barrier(); torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        acts, probs = pol.get_actions_host(out["obs"], out["adj_bits"], out["chan_bits"])
+        out = henv.step_host(acts)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    ph2d, pd2h = pol.host_call_bytes(B)
+    eh2d, ed2h = henv.host_step_bytes()
+    # ---------------- reduce over ranks ----------------
+    vec = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.MAX)
+    ms_max, e2e_max = float(vec[0]), float(vec[1])
+    stats = D.gather_stats(eng.local_stats())          # the path's only collective (NCCL over NVLink)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    agent_steps = steps * B * n * world
+    value = agent_steps / (ms_max * 1e-3)
+    e2e_value = e2e_steps * B * n * world / e2e_max
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    flops = policy_flops_per_agent(Dobs, n, L) * B * n
+    env_bytes = env_bytes_per_agent_step(spec) * B * n
+    pol_tflops = flops / (pol_ms * 1e-3) / 1e12
+    env_gbs = env_bytes / (env_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (policy) + u8/u16/u64 bit rows (env, comm)", "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT[args.config], "config": args.config, "envs_per_gpu": B, "n_agents": n,
+                   "obs_dim": Dobs, "ring_slots": ring,
+                   "l2": f"inputs are produced by the previous step; the trajectory ring ({ring + 1} slots, "
+                         f"{(ring + 1) * B * n * Dobs * 4 / 2**20:.0f} MiB of observations) is larger than the 126 MB L2, "
+                         "so no slot survives a ring cycle in cache",
+                   "streams": "on-device Philox4x32-10 (spawn, prey walk, channel draws, action sampling)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ph2d + eh2d, "d2h_bytes_per_step": pd2h + ed2h,
+                "steps": e2e_steps, "api": "policy.get_actions_host + BatchedEnv.step_host (pinned host buffers, per-step sync)"},
+        "gpu_launches": launches * world,
+        "roofline": {"bound": "tensor", "kernel": "policy_small_kernel" if n <= 64 else "policy_large_kernel",
+                     "achieved": pol_tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": pol_tflops / tc_peak, "traffic": None,
+                     "peak_source": peak_src + ", bf16 dense sustained; the kernel itself is exact fp32 FFMA",
+                     "flop_per_launch": flops, "ms_per_launch": pol_ms, "share_of_step": pol_ms / (pol_ms + env_ms)},
+        "roofline_env": {"bound": "hbm", "kernel": "env_kernel", "achieved": env_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": env_gbs / hbm_peak, "traffic": None, "bytes_per_launch": env_bytes, "ms_per_launch": env_ms,
+                         "bytes_per_agent_step": env_bytes_per_agent_step(spec), "peak_source": peak_src},
+        "clocks": clock_info,
+        "episode_stats": D.summarize_stats(stats, spec.scenario, n),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        Bc, Sc = max(8, min(512, 40000 // n)), 60
+        rate, _ = cpu_port_throughput(args.config, 1, Bc, Sc)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{Bc} envs x {Sc} steps of the oracle port (C env oracle + numpy fp32 policy), "
+                                          f"1 thread, {time.perf_counter() - t0:.1f}s"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2048)
+    ap.add_argument("--warmup", type=int, default=192)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the config's)")
+    ap.add_argument("--ring", type=int, default=64, help="trajectory ring slots = steps per CUDA graph")
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -145,6 +145,43 @@ class BatchedEnv:
             N.check("cm_env_step", N.lib().cm_env_step(C.byref(self.desc), C.byref(self.state), C.byref(io), N.stream_ptr()))
         return self.obs.view(self.B, -1), self.reward, self.done
 
+    # ---- host-buffer surface: the drop-in call with numpy in / numpy out ------------------------------
+    def _pinned(self):
+        if getattr(self, "_pin", None) is None:
+            pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
+            self._pin = dict(actions=torch.empty((self.B, self.n), dtype=torch.int8, pin_memory=True),
+                             obs=pin(self.obs), reward=pin(self.reward), done=pin(self.done), counts=pin(self.counts),
+                             adj_bits=pin(self.adj_bits), chan_bits=pin(self.chan_bits), ave_deg=pin(self.ave_deg),
+                             prey_alive_out=pin(self.prey_alive_out), success=pin(self.success))
+            self._act_dev = torch.empty((self.B, self.n), dtype=torch.int8, device=self.device)
+        return self._pin
+
+    def step_host(self, actions):
+        """VecEnvExecutor.step with HOST buffers: numpy actions in, numpy (views of pinned buffers) out.
+        Copies: H2D actions; D2H obs, reward, done, counts, adj/chan bit rows, ave_deg, prey_alive, success."""
+        pin = self._pinned()
+        pin["actions"].numpy()[...] = np.asarray(actions, dtype=np.int8).reshape(self.B, self.n)
+        self._act_dev.copy_(pin["actions"], non_blocking=True)
+        self.step(self._act_dev)
+        for k in ("obs", "reward", "done", "counts", "adj_bits", "chan_bits", "ave_deg", "prey_alive_out", "success"):
+            pin[k].copy_(getattr(self, k), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return {k: v.numpy() for k, v in pin.items() if k != "actions"}
+
+    def reset_host(self):
+        pin = self._pinned()
+        self.reset()
+        for k in ("obs", "adj_bits", "chan_bits", "ave_deg"):
+            pin[k].copy_(getattr(self, k), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return {k: pin[k].numpy() for k in ("obs", "adj_bits", "chan_bits", "ave_deg")}
+
+    def host_step_bytes(self):
+        """(h2d, d2h) bytes moved by one step_host call"""
+        pin = self._pinned()
+        d2h = sum(v.numel() * v.element_size() for k, v in pin.items() if k != "actions")
+        return pin["actions"].numel(), d2h
+
     def comm_update(self, at_reset=False, chan_u=None):
         """update_communication_state alone from the current positions (env_communication.py:91-157)."""
         u = self._dev(chan_u, torch.float32)

@@ -197,6 +197,38 @@ class CommCategoricalMLPPolicy(nn.Module):
 
     _host_calls = 0
 
+    def get_actions_host(self, obs, adj_bits, chan_bits, greedy=False):
+        """Batched rollout call with HOST buffers and bit-row masks (what BatchedEnv.step_host returns): numpy obs
+        (B, n, D) / (B, n*D), int32 bit rows in; numpy actions (B, n) int8 and probs (B, n, 5) out.  Pinned staging
+        buffers are allocated once.  Copies: H2D obs + masks; D2H actions + probs."""
+        n, D, L, dev = self._n_agents, self._dec_obs_dim, self.n_gcn_layers, self.device
+        B = obs.shape[0]
+        st = getattr(self, "_stage", None)
+        if st is None or st["B"] != B:
+            W = (n + 31) // 32
+            mk = lambda shape, dt: (torch.empty(shape, dtype=dt, pin_memory=True), torch.empty(shape, dtype=dt, device=dev))  # noqa: E731
+            st = dict(B=B, obs=mk((B, n, D), torch.float32), adj=mk((B, n, W), torch.int32), chan=mk((B, L, n, W), torch.int32),
+                      probs=mk((B, n, 5), torch.float32), actions=mk((B, n), torch.int8),
+                      tick=torch.zeros((B,), dtype=torch.int32, device=dev), episode=torch.zeros((B,), dtype=torch.int32, device=dev))
+            self._stage = st
+        for k, src in (("obs", obs), ("adj", adj_bits), ("chan", chan_bits)):
+            h, d = st[k]
+            h.numpy()[...] = np.asarray(src).reshape(h.shape)
+            d.copy_(h, non_blocking=True)
+        st["tick"].fill_(self._host_calls & 0x7FFFFFFF)
+        self._host_calls += 1
+        self.act_device(st["obs"][1], st["adj"][1], st["chan"][1], tick=st["tick"], episode=st["episode"], greedy=greedy,
+                        probs=st["probs"][1], actions=st["actions"][1])
+        st["probs"][0].copy_(st["probs"][1], non_blocking=True)
+        st["actions"][0].copy_(st["actions"][1], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return st["actions"][0].numpy(), st["probs"][0].numpy()
+
+    def host_call_bytes(self, B):
+        n, D, L = self._n_agents, self._dec_obs_dim, self.n_gcn_layers
+        W = (n + 31) // 32
+        return B * n * D * 4 + B * n * W * 4 * (1 + L), B * n * 5 * 4 + B * n
+
     def forward(self, obs_n, avail_actions_n, dist_adj, channels, get_actions=False):
         """comm_categorical_mlp_policy.py:48-96.  get_actions=True: numpy in, CPU tensors out (kernel path).
         get_actions=False: torch tensors shaped (n_paths, T, ...) in, differentiable (torch ops)."""

@@ -53,7 +53,8 @@ def test_policy_kernel_matches_reference_golden(name):
 
 
 @pytest.mark.parametrize("n,D,B,ploss", [(3, 29, 16384, 0.0), (4, 21, 5000, 0.3), (32, 53, 2048, 0.2), (54, 77, 777, 0.1),
-                                         (7, 53, 1001, 0.5), (64, 29, 64, 0.4), (1, 21, 100, 0.0)])
+                                         (7, 53, 1001, 0.5), (64, 29, 64, 0.4), (1, 21, 100, 0.0),
+                                         (65, 21, 70, 0.2), (72, 53, 301, 0.3), (200, 53, 97, 0.2), (256, 29, 9, 0.5)])
 def test_policy_kernel_matches_oracle_batched(n, D, B, ploss):
     """Random binary observations + random masks on big ragged batches (last tile partial) vs the numpy
     restatement; sampling reproduces the inverse-CDF stream specification exactly."""
