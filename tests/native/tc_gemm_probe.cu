@@ -1,0 +1,79 @@
+// tc_gemm_probe.cu — test-only probe of the tcgen05 building block used by the policy kernel:
+// C[128][N] = A[128][K] * B[N][K]^T with error-compensated TF32 (passes = 3: hi*hi + lo*hi + hi*lo).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tc_common.cuh"
+
+using namespace cm::tc;
+
+__global__ void __launch_bounds__(128) tc_gemm_probe_kernel(const float *A, const float *B, float *C, int N, int K, int passes, int *status)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    float *Ahi = reinterpret_cast<float *>(smem);
+    float *Alo = Ahi + 128 * K;
+    float *Bhi = Alo + 128 * K;
+    float *Blo = Bhi + N * K;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 128);
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    // operands into the canonical layout, split hi / lo
+    for (int kc = 0; kc < K / 4; ++kc) {
+        const float4 a = *reinterpret_cast<const float4 *>(A + (size_t)tid * K + 4 * kc);
+        const float4 h = make_float4(tf32_hi(a.x), tf32_hi(a.y), tf32_hi(a.z), tf32_hi(a.w));
+        const uint32_t off = canon_off(tid, 4 * kc, K);
+        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(Ahi) + off) = h;
+        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(Alo) + off) = make_float4(a.x - h.x, a.y - h.y, a.z - h.z, a.w - h.w);
+    }
+    for (int r = tid; r < N; r += 128)
+        for (int kc = 0; kc < K / 4; ++kc) {
+            const float4 b = *reinterpret_cast<const float4 *>(B + (size_t)r * K + 4 * kc);
+            const float4 h = make_float4(tf32_hi(b.x), tf32_hi(b.y), tf32_hi(b.z), tf32_hi(b.w));
+            const uint32_t off = canon_off(r, 4 * kc, K);
+            *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(Bhi) + off) = h;
+            *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(Blo) + off) = make_float4(b.x - h.x, b.y - h.y, b.z - h.z, b.w - h.w);
+        }
+    fence_proxy_async();
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc_tf32(128, N);
+        uint32_t acc = 0;
+        for (int p = 0; p < passes; ++p) {
+            const float *a = (p == 1) ? Alo : Ahi;
+            const float *b = (p == 2) ? Blo : Bhi;
+            for (int j = 0; j < K / 8; ++j) {
+                mma_tf32(tmem_base, make_smem_desc(smem_u32(a), K, j), make_smem_desc(smem_u32(b), K, j), idesc, acc);
+                acc = 1;
+            }
+        }
+        mma_commit(&bar);
+    }
+    const bool ok = mbar_wait(&bar, 0);
+    if (!ok && tid == 0) atomicExch(status, 1);
+    fence_after_thread_sync();
+    if (ok) {
+        for (int c = 0; c < N; c += 8) {
+            float v[8];
+            tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+            tmem_ld_wait();
+            for (int i = 0; i < 8; ++i) C[(size_t)tid * N + c + i] = v[i];
+        }
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+extern "C" int tc_gemm_probe(const float *A, const float *B, float *C, int N, int K, int passes, int *status, void *stream)
+{
+    const size_t smem = (size_t)(2 * 128 * K + 2 * N * K) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    tc_gemm_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, C, N, K, passes, status);
+    return (int)cudaGetLastError();
+}
