@@ -16,7 +16,8 @@ CH_FC, CH_FL, CH_IID, CH_GE = 0, 1, 2, 3
 MAX_AGENTS, MAX_GRID, MAX_LAYERS = 256, 64, 4
 
 EXPORTS = ("cm_abi_version", "cm_strerror", "cm_last_cuda_error", "cm_device_count", "cm_env_reset", "cm_env_step",
-           "cm_comm_update", "cm_policy_forward", "cm_policy_blob_floats", "cm_policy_workspace_bytes", "cm_mask_pack", "cm_mask_unpack")
+           "cm_comm_update", "cm_policy_forward", "cm_policy_blob_floats", "cm_policy_workspace_bytes", "cm_policy_tc_blob_floats", "cm_policy_tc_prepare", "cm_mask_pack",
+           "cm_mask_unpack")
 
 
 class EnvDesc(C.Structure):
@@ -46,13 +47,14 @@ class StepIO(C.Structure):
 
 class PolicyDesc(C.Structure):
     _fields_ = [("n_agents", C.c_int32), ("obs_dim", C.c_int32), ("n_layers", C.c_int32), ("residual", C.c_int32),
-                ("greedy", C.c_int32), ("seed", C.c_uint64), ("env_id0", C.c_int64)]
+                ("greedy", C.c_int32), ("math", C.c_int32), ("seed", C.c_uint64), ("env_id0", C.c_int64)]
 
 
 class PolicyIO(C.Structure):
     _fields_ = [("n_envs", C.c_int64)] + \
                [(k, C.c_void_p) for k in ("weights", "obs", "adj_bits", "chan_bits", "avail_bits", "sample_u", "tick",
-                                          "episode", "probs", "logits", "attention", "actions", "workspace")] + \
+                                          "episode", "probs", "logits", "attention", "actions", "tc_weights",
+                                          "error_flag", "workspace")] + \
                [("workspace_bytes", C.c_size_t)]
 
 
@@ -85,6 +87,10 @@ def lib():
     L.cm_policy_forward.argtypes = [C.POINTER(PolicyDesc), C.POINTER(PolicyIO), C.c_void_p]
     L.cm_policy_blob_floats.restype = C.c_size_t
     L.cm_policy_blob_floats.argtypes = [C.c_int32, C.c_int32]
+    L.cm_policy_tc_blob_floats.restype = C.c_size_t
+    L.cm_policy_tc_blob_floats.argtypes = [C.c_int32, C.c_int32]
+    L.cm_policy_tc_prepare.restype = C.c_int
+    L.cm_policy_tc_prepare.argtypes = [C.POINTER(PolicyDesc), C.c_void_p, C.c_void_p, C.c_void_p]
     L.cm_policy_workspace_bytes.restype = C.c_size_t
     L.cm_policy_workspace_bytes.argtypes = [C.c_int32, C.c_int64]
     L.cm_mask_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]

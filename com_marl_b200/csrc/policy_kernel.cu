@@ -26,48 +26,13 @@
 
 #include "commarl_b200.h"
 #include "common.cuh"
+#include "policy_layout.cuh"
 
 namespace cm {
 
 static constexpr int kTile = 64;        // agent rows per CTA tile
 static constexpr int kPitch = 68;       // floats per k-major row (64 + 4: keeps float4 alignment, spreads banks)
 static constexpr int kThreads = 256;
-static constexpr int kH1 = 128, kE = 64, kC1 = 128, kC2 = 64, kC3 = 32;
-
-struct Blob {   // float offsets into the weight blob (commarl_b200.h)
-    int enc_w1, enc_b1, enc_w2, enc_b2, att_w, gcn_w, gcn_b, head_w1, head_b1, head_w2, head_b2, head_w3, head_b3,
-        head_w4, head_b4, total;
-};
-
-__host__ __device__ inline Blob blob_layout(int D, int L)
-{
-    Blob o;
-    int p = 0;
-    o.enc_w1 = p; p += D * kH1;
-    o.enc_b1 = p; p += kH1;
-    o.enc_w2 = p; p += kH1 * kE;
-    o.enc_b2 = p; p += kE;
-    o.att_w = p; p += kE * kE;
-    o.gcn_w = p; p += L * kE * kE;
-    o.gcn_b = p; p += L * kE;
-    o.head_w1 = p; p += kE * kC1;
-    o.head_b1 = p; p += kC1;
-    o.head_w2 = p; p += kC1 * kC2;
-    o.head_b2 = p; p += kC2;
-    o.head_w3 = p; p += kC2 * kC3;
-    o.head_b3 = p; p += kC3;
-    o.head_w4 = p; p += kC3 * CM_ACTIONS;
-    o.head_b4 = p; p += CM_ACTIONS;
-    o.total = p;
-    return o;
-}
-
-struct PolicyArgs {
-    cm_policy_desc d;
-    cm_policy_io io;
-    int envs_per_tile;
-    int64_t n_tiles;
-};
 
 // ------------------------------------------------------------------------------------------------
 // 64-row register-tiled product: acc[r][q] = sum_k At[k][4ty + r] * Bm[k][col(q)]
@@ -599,6 +564,8 @@ static size_t large_smem_bytes() { return small_smem_bytes() + (size_t)(2 * CM_M
 static int round_up_tile(int n) { return (n + kTile - 1) / kTile * kTile; }
 static size_t large_ws_floats(int n) { return (size_t)3 * kE * round_up_tile(n); }
 
+int launch_policy_tc(const cm_policy_desc *desc, const cm_policy_io *io, cudaStream_t stream);   // policy_tc_kernel.cu
+
 struct LaunchCache { int dev; int ctas_per_sm; int sms; };
 
 template <typename K>
@@ -645,6 +612,8 @@ extern "C" int cm_policy_forward(const cm_policy_desc *desc, const cm_policy_io 
     if (io->actions && !desc->greedy && !io->sample_u && (!io->tick || !io->episode)) return CM_EINVAL;
     if (io->n_envs < 0) return CM_EINVAL;
     if (io->n_envs == 0) return CM_OK;
+    if (desc->math == 1) return launch_policy_tc(desc, io, (cudaStream_t)stream);
+    if (desc->math != 0) return CM_EINVAL;
     PolicyArgs A;
     A.d = *desc;
     A.io = *io;

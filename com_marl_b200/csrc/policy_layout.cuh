@@ -1,0 +1,85 @@
+// policy_layout.cuh — weight-blob layouts shared by the policy kernels (fp32 FFMA and tcgen05 variants).
+#pragma once
+#include <stdint.h>
+
+#include "commarl_b200.h"
+
+namespace cm {
+
+static constexpr int kH1 = 128, kE = 64, kC1 = 128, kC2 = 64, kC3 = 32;
+
+struct Blob {   // float offsets into the weight blob (commarl_b200.h)
+    int enc_w1, enc_b1, enc_w2, enc_b2, att_w, gcn_w, gcn_b, head_w1, head_b1, head_w2, head_b2, head_w3, head_b3,
+        head_w4, head_b4, total;
+};
+
+__host__ __device__ inline Blob blob_layout(int D, int L)
+{
+    Blob o;
+    int p = 0;
+    o.enc_w1 = p; p += D * kH1;
+    o.enc_b1 = p; p += kH1;
+    o.enc_w2 = p; p += kH1 * kE;
+    o.enc_b2 = p; p += kE;
+    o.att_w = p; p += kE * kE;
+    o.gcn_w = p; p += L * kE * kE;
+    o.gcn_b = p; p += L * kE;
+    o.head_w1 = p; p += kE * kC1;
+    o.head_b1 = p; p += kC1;
+    o.head_w2 = p; p += kC1 * kC2;
+    o.head_b2 = p; p += kC2;
+    o.head_w3 = p; p += kC2 * kC3;
+    o.head_b3 = p; p += kC3;
+    o.head_w4 = p; p += kC3 * CM_ACTIONS;
+    o.head_b4 = p; p += CM_ACTIONS;
+    o.total = p;
+    return o;
+}
+
+struct PolicyArgs {
+    cm_policy_desc d;
+    cm_policy_io io;
+    int envs_per_tile;
+    int64_t n_tiles;
+};
+
+
+// ---- tcgen05 variant: one "stage" = the B operand of one tcgen05 product, N rows x Kp columns, stored in the
+// canonical K-major core-matrix layout as a hi block followed by a lo block (error-compensated TF32) ----
+struct TcStage { int w_off, src_off, N, Kp, k0, Ksrc, Nsrc; };
+struct TcPlan {
+    int n_stages, total_floats;
+    int iW1a, iW1b, iW2a, iWQ, iWG, iH1, iH2a, iH3, iH4;   // iW2a/iH2a are followed by their second K panel, iWQ by Wg_0..Wg_{L-1}
+    TcStage st[16];
+};
+
+__host__ __device__ inline TcPlan make_tc_plan(int D, int L)
+{
+    const Blob o = blob_layout(D, L);
+    TcPlan P;
+    int s = 0, off = 0;
+    auto add = [&](int src_off, int N, int Kp, int k0, int Ksrc, int Nsrc) {
+        P.st[s].w_off = off; P.st[s].src_off = src_off; P.st[s].N = N; P.st[s].Kp = Kp; P.st[s].k0 = k0;
+        P.st[s].Ksrc = Ksrc; P.st[s].Nsrc = Nsrc;
+        off += 2 * N * Kp;
+        return s++;
+    };
+    const int Dp = (D + 7) / 8 * 8;
+    P.iW1a = add(o.enc_w1, kH1, Dp <= 64 ? Dp : 64, 0, D, kH1);
+    P.iW1b = Dp > 64 ? add(o.enc_w1, kH1, Dp - 64, 64, D, kH1) : -1;
+    P.iW2a = add(o.enc_w2, kE, 64, 0, kH1, kE);
+    add(o.enc_w2, kE, 64, 64, kH1, kE);
+    P.iWQ = add(o.att_w, kE, 64, 0, kE, kE);
+    P.iWG = s;
+    for (int l = 0; l < L; ++l) add(o.gcn_w + l * kE * kE, kE, 64, 0, kE, kE);
+    P.iH1 = add(o.head_w1, kC1, 64, 0, kE, kC1);
+    P.iH2a = add(o.head_w2, kC2, 64, 0, kC1, kC2);
+    add(o.head_w2, kC2, 64, 64, kC1, kC2);
+    P.iH3 = add(o.head_w3, kC3, 64, 0, kC2, kC3);
+    P.iH4 = add(o.head_w4, 16, 32, 0, kC3, CM_ACTIONS);     // 5 logits padded to N = 16
+    P.n_stages = s;
+    P.total_floats = off;
+    return P;
+}
+
+}  // namespace cm

@@ -1,0 +1,485 @@
+// policy_tc_kernel.cu — CommCategoricalMLPPolicy forward on the 5th-generation tensor cores (tcgen05).
+//
+// Same formula and outputs as policy_kernel.cu (see its header for the reference lines), different machine
+// mapping: a CTA of 512 threads owns a tile of 128 agent rows (whole environments, n <= 64) and runs
+//   * every row-wise dense layer (encoder, attention query, H_l Wg_l, the categorical head) as
+//     tcgen05.mma.kind::tf32 with the accumulator in tensor memory.  fp32-level accuracy is kept by error
+//     compensation: each product is issued three times, A_hi B_hi + A_lo B_hi + A_hi B_lo, with
+//     x_hi = x & 0xFFFFE000 (exactly representable in TF32) and x_lo = x - x_hi.  Weights are pre-split and
+//     pre-arranged in the canonical K-major core-matrix layout by cm_policy_tc_prepare(), so that a layer's
+//     B operand is ONE bulk async copy (TMA engine, mbarrier completion) issued while the previous layer's
+//     epilogue runs;
+//   * the per-environment pieces (n x n scores, softmax, masked renormalisation, aggregation over
+//     neighbours) exactly — not as padded tile products — on the CUDA cores from k-major fp32 copies of E, Q
+//     and H_l Wg_l in shared memory.
+// TMEM lane = tile row = thread (row = 32 * (warp % 4) + lane); the four warps that share a lane quadrant
+// split the accumulator columns.  Epilogues read TMEM with tcgen05.ld, apply bias + tanh, and write the next
+// A operand (hi / lo) straight into the canonical layout.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "commarl_b200.h"
+#include "common.cuh"
+#include "policy_layout.cuh"
+#include "tc_common.cuh"
+
+namespace cm {
+
+using namespace tc;
+
+static constexpr int kTcRows = 128;
+static constexpr int kTcThreads = 512;
+static constexpr int kActBytes = 65536, kWBytes = 65536;
+static constexpr int kTPitch = 128;     // floats per k-major row of ET / QT / HWT
+
+struct TcArgs {
+    cm_policy_desc d;
+    cm_policy_io io;
+    TcPlan plan;
+    int envs_per_tile;
+    int64_t n_tiles;
+};
+
+template <int CW>
+__device__ __forceinline__ void ld_cols(uint32_t taddr, float (&v)[CW])
+{
+    static_assert(CW == 8 || CW == 16, "column chunk");
+#pragma unroll
+    for (int c = 0; c < CW; c += 8) {
+        float t[8];
+        tmem_ld8(taddr + (uint32_t)c, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[c + i] = t[i];
+    }
+    tmem_ld_wait();
+}
+
+// write CW consecutive columns (starting at local column c0 of a Kp-wide panel) of row `row` as the next A operand
+template <int CW>
+__device__ __forceinline__ void write_act(unsigned char *act, int Kp, int row, int c0, const float (&v)[CW])
+{
+    const uint32_t lo_off = (uint32_t)kTcRows * Kp * 4;
+#pragma unroll
+    for (int g = 0; g < CW; g += 4) {
+        const float4 h = make_float4(tf32_hi(v[g]), tf32_hi(v[g + 1]), tf32_hi(v[g + 2]), tf32_hi(v[g + 3]));
+        const float4 l = make_float4(tf32_lo(v[g], h.x), tf32_lo(v[g + 1], h.y), tf32_lo(v[g + 2], h.z), tf32_lo(v[g + 3], h.w));
+        const uint32_t off = canon_off(row, c0 + g, Kp);
+        *reinterpret_cast<float4 *>(act + off) = h;
+        *reinterpret_cast<float4 *>(act + lo_off + off) = l;
+    }
+}
+
+// one thread: D[tmem] (+)= ACT * W^T, error-compensated (hi*hi + lo*hi + hi*lo)
+__device__ __forceinline__ void issue_layer(uint32_t d_tmem, const unsigned char *act, const unsigned char *wblk, int N, int Kp,
+                                            uint32_t accumulate)
+{
+    const uint32_t a_hi = smem_u32(act), a_lo = a_hi + (uint32_t)kTcRows * Kp * 4;
+    const uint32_t b_hi = smem_u32(wblk), b_lo = b_hi + (uint32_t)N * Kp * 4;
+    const uint32_t idesc = make_idesc_tf32(kTcRows, N);
+    uint32_t acc = accumulate;
+#pragma unroll 1
+    for (int p = 0; p < 3; ++p) {
+        const uint32_t a = (p == 1) ? a_lo : a_hi, b = (p == 2) ? b_lo : b_hi;
+#pragma unroll 1
+        for (int j = 0; j < Kp / 8; ++j) {
+            mma_tf32(d_tmem, make_smem_desc(a, Kp, j), make_smem_desc(b, Kp, j), idesc, acc);
+            acc = 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *ACT = smem;
+    unsigned char *WBUF = smem + kActBytes;
+    float *ET = reinterpret_cast<float *>(smem + kActBytes + kWBytes);   // [64][128] E^T   (keys, residual)
+    float *QT = ET + 64 * kTPitch;                                       // [64][128] Q^T, then M^T [n][128]
+    float *HWT = QT + 64 * kTPitch;                                      // [64][128] (H_l Wg_l)^T; softmax scratch before that
+    uint64_t *bars = reinterpret_cast<uint64_t *>(HWT + 64 * kTPitch);   // [0] weights landed, [1] MMAs done
+    uint32_t *tmem_s = reinterpret_cast<uint32_t *>(bars + 2);
+    int *fail_s = reinterpret_cast<int *>(tmem_s + 1);
+
+    const cm_policy_desc &d = A.d;
+    const cm_policy_io &io = A.io;
+    const TcPlan &P = A.plan;
+    const int n = d.n_agents, D = d.obs_dim, L = d.n_layers, W = (n + 31) >> 5;
+    const Blob o = blob_layout(D, L);
+    const float *__restrict__ wts = io.weights;
+    const float *tcw = io.tc_weights;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, sub = warp >> 2, row = quad * 32 + lane;
+
+    if (warp == 0) tmem_alloc(tmem_s, 256);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+        *fail_s = 0;
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem = *tmem_s;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    const uint32_t DA = 0, DB = 128;          // accumulator column regions
+    uint32_t w_phase = 0, m_phase = 0;        // mbarrier parities (w_phase is only used by thread 0)
+    bool ok = true;
+
+    // thread 0: start the bulk copy of stage(s) [s0, s0 + cnt) into WBUF
+    auto load_w = [&](int s0, int cnt) {
+        if (tid == 0) {
+            uint32_t bytes = 0;
+            for (int s = s0; s < s0 + cnt; ++s) bytes += (uint32_t)(2 * P.st[s].N * P.st[s].Kp * 4);
+            mbar_expect_tx(&bars[0], bytes);
+            bulk_g2s(WBUF, tcw + P.st[s0].w_off, bytes, &bars[0]);
+        }
+    };
+    // all threads: ACT is written -> thread 0 issues `issue()` once the weights have landed -> everybody waits
+    auto run_mma = [&](auto issue) {
+        fence_proxy_async();
+        fence_before_thread_sync();
+        __syncthreads();
+        if (tid == 0) {
+            ok = mbar_wait(&bars[0], w_phase) && ok;
+            w_phase ^= 1;
+            fence_after_thread_sync();
+            issue();
+            mma_commit(&bars[1]);
+        }
+        ok = mbar_wait(&bars[1], m_phase) && ok;
+        m_phase ^= 1;
+        fence_after_thread_sync();
+    };
+
+    for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+        const int64_t env0 = tile * A.envs_per_tile;
+        const int envs = (int)min((int64_t)A.envs_per_tile, io.n_envs - env0);
+        const int rows = envs * n;
+        const int64_t row0 = env0 * n;
+        const bool valid = row < rows;
+        const int el = valid ? row / n : 0, il = row - el * n, j0 = el * n;
+        const int64_t env = env0 + el, g = row0 + row;
+
+        // ---------------- encoder layer 1: obs panels -> DA[0:128] ----------------
+        load_w(P.iW1a, 1);
+        {
+            const int Kp = P.st[P.iW1a].Kp;
+            const float *src = io.obs + row0 * D;
+            const uint32_t lo_off = (uint32_t)kTcRows * Kp * 4;
+            for (int e = tid; e < kTcRows * Kp; e += kTcThreads) {
+                const int r = e / Kp, k = e - r * Kp;
+                const float v = (r < rows && k < D) ? __ldg(src + (size_t)r * D + k) : 0.0f;
+                const float h = tf32_hi(v);
+                const uint32_t off = canon_off(r, k, Kp);
+                *reinterpret_cast<float *>(ACT + off) = h;
+                *reinterpret_cast<float *>(ACT + lo_off + off) = tf32_lo(v, h);
+            }
+            run_mma([&] { issue_layer(tmem + DA, ACT, WBUF, 128, Kp, 0); });
+        }
+        if (P.iW1b >= 0) {               // observation wider than 64: second K panel accumulates
+            load_w(P.iW1b, 1);
+            const int Kp = P.st[P.iW1b].Kp;
+            const float *src = io.obs + row0 * D;
+            const uint32_t lo_off = (uint32_t)kTcRows * Kp * 4;
+            for (int e = tid; e < kTcRows * Kp; e += kTcThreads) {
+                const int r = e / Kp, k = e - r * Kp;
+                const float v = (r < rows && 64 + k < D) ? __ldg(src + (size_t)r * D + 64 + k) : 0.0f;
+                const float h = tf32_hi(v);
+                const uint32_t off = canon_off(r, k, Kp);
+                *reinterpret_cast<float *>(ACT + off) = h;
+                *reinterpret_cast<float *>(ACT + lo_off + off) = tf32_lo(v, h);
+            }
+            run_mma([&] { issue_layer(tmem + DA, ACT, WBUF, 128, Kp, 1); });
+        }
+        // ---------------- encoder layer 2 (K = 128 as two panels of h) -> DB[0:64] ----------------
+        for (int p = 0; p < 2; ++p) {
+            load_w(P.iW2a + p, 1);
+            float v[16];
+            ld_cols<16>(lane_addr + DA + 64 * p + 16 * sub, v);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = tanhf(v[c] + __ldg(wts + o.enc_b1 + 64 * p + 16 * sub + c));
+            write_act<16>(ACT, 64, row, 16 * sub, v);
+            run_mma([&] { issue_layer(tmem + DB, ACT, WBUF, 64, 64, (uint32_t)p); });
+        }
+        // ---------------- E = tanh(. + b2): k-major fp32 copy + A operand; Q and H_0 Wg_0 -> DA[0:64], DA[64:128] ----------------
+        load_w(P.iWQ, 2);                 // Wa and Wg_0 are adjacent in the blob: one copy
+        {
+            float v[16];
+            ld_cols<16>(lane_addr + DB + 16 * sub, v);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                v[c] = tanhf(v[c] + __ldg(wts + o.enc_b2 + 16 * sub + c));
+                ET[(16 * sub + c) * kTPitch + row] = v[c];
+            }
+            write_act<16>(ACT, 64, row, 16 * sub, v);
+            run_mma([&] {
+                issue_layer(tmem + DA, ACT, WBUF, 64, 64, 0);
+                issue_layer(tmem + DA + 64, ACT, WBUF + 2 * 64 * 64 * 4, 64, 64, 0);
+            });
+        }
+        if (L > 1) load_w(P.iWG + 1, 1); else load_w(P.iH1, 1);
+        // ---------------- scores, softmax (exact per environment, CUDA cores) ----------------
+        {
+            float v[16];
+            ld_cols<16>(lane_addr + DA + 16 * sub, v);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) QT[(16 * sub + c) * kTPitch + row] = v[c];
+        }
+        __syncthreads();
+        float *red = HWT;                 // [2][4][128] softmax scratch (HWT is filled after the softmax)
+        float sc[16];
+        const int nk = valid ? (n - sub + 3) / 4 : 0;          // my keys: jj = sub, sub + 4, ...
+        {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) sc[t] = 0.0f;
+            for (int k = 0; k < 64; ++k) {
+                const float qv = QT[k * kTPitch + row];
+                const float *er = ET + k * kTPitch + j0 + sub;
+#pragma unroll
+                for (int t = 0; t < 16; ++t)
+                    if (t < nk) sc[t] = fmaf(qv, er[4 * t], sc[t]);
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+                if (t < nk) mx = fmaxf(mx, sc[t]);
+            red[sub * kTPitch + row] = mx;
+        }
+        __syncthreads();
+        {
+            const float mx = fmaxf(fmaxf(red[row], red[kTPitch + row]), fmaxf(red[2 * kTPitch + row], red[3 * kTPitch + row]));
+            float sum = 0.0f;
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+                if (t < nk) { sc[t] = expf(sc[t] - mx); sum += sc[t]; }
+            red[(4 + sub) * kTPitch + row] = sum;
+        }
+        __syncthreads();                  // everybody has read QT: it becomes M^T [n][128]
+        {
+            const float z = red[4 * kTPitch + row] + red[5 * kTPitch + row] + red[6 * kTPitch + row] + red[7 * kTPitch + row];
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+                if (t < nk) QT[(sub + 4 * t) * kTPitch + row] = sc[t] / z;
+        }
+        __syncthreads();
+        const float *MT = QT;
+        if (io.attention) {               // unmasked softmax (agent_infos['attention_weights'])
+            float *dst = io.attention + row0 * n;
+            for (int e = tid; e < rows * n; e += kTcThreads) {
+                const int r = e / n, jl = e - r * n;
+                dst[e] = MT[jl * kTPitch + r];
+            }
+        }
+        // H_0 Wg_0 out of tensor memory (the softmax scratch is dead now)
+        {
+            float v[16];
+            ld_cols<16>(lane_addr + DA + 64 + 16 * sub, v);
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) HWT[(16 * sub + c) * kTPitch + row] = v[c];
+        }
+        __syncthreads();
+        // ---------------- graph convolutions ----------------
+        for (int l = 0; l < L; ++l) {
+            // A_l = M * Range * chan_l / (sum + 1e-12); out = A_l (H_l Wg_l)   (comm_base_net.py:101-103, graph_conv_module.py:51-72)
+            uint32_t m0 = 0u, m1 = 0u;
+            if (valid) {
+                m0 = m1 = 0xFFFFFFFFu;
+                if (io.adj_bits) {
+                    const uint32_t *p = io.adj_bits + (env * n + il) * W;
+                    m0 &= __ldg(p);
+                    if (W > 1) m1 &= __ldg(p + 1);
+                }
+                if (io.chan_bits) {
+                    const uint32_t *p = io.chan_bits + ((env * L + l) * n + il) * W;
+                    m0 &= __ldg(p);
+                    if (W > 1) m1 &= __ldg(p + 1);
+                }
+            }
+            float acc[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+            float den = 0.0f;
+            const int nn = valid ? n : 0;
+            for (int jj = 0; jj < nn; ++jj) {
+                const uint32_t bit = ((jj < 32 ? m0 : m1) >> (jj & 31)) & 1u;
+                const float a = bit ? MT[jj * kTPitch + row] : 0.0f;
+                den += a;
+                const float *hw = HWT + (16 * sub) * kTPitch + j0 + jj;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[c] = fmaf(a, hw[c * kTPitch], acc[c]);
+            }
+            const float inv = 1.0f / (den + 1e-12f);
+            float v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                v[c] = tanhf(acc[c] * inv + __ldg(wts + o.gcn_b + l * 64 + 16 * sub + c));
+                if (l + 1 == L && d.residual) v[c] += ET[(16 * sub + c) * kTPitch + row];   // X = E + H_L
+            }
+            write_act<16>(ACT, 64, row, 16 * sub, v);
+            if (l + 1 < L) {
+                run_mma([&] { issue_layer(tmem + DB, ACT, WBUF, 64, 64, 0); });
+                if (l + 2 < L) load_w(P.iWG + l + 2, 1); else load_w(P.iH1, 1);
+                float hv[16];
+                ld_cols<16>(lane_addr + DB + 16 * sub, hv);
+                __syncthreads();          // every thread is done reading HWT of layer l
+#pragma unroll
+                for (int c = 0; c < 16; ++c) HWT[(16 * sub + c) * kTPitch + row] = hv[c];
+                __syncthreads();
+            }
+        }
+        // ---------------- categorical head ----------------
+        run_mma([&] { issue_layer(tmem + DA, ACT, WBUF, 128, 64, 0); });        // 64 -> 128
+        for (int p = 0; p < 2; ++p) {                                             // 128 -> 64 as two K panels
+            load_w(P.iH2a + p, 1);
+            float v[16];
+            ld_cols<16>(lane_addr + DA + 64 * p + 16 * sub, v);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = tanhf(v[c] + __ldg(wts + o.head_b1 + 64 * p + 16 * sub + c));
+            write_act<16>(ACT, 64, row, 16 * sub, v);
+            run_mma([&] { issue_layer(tmem + DB, ACT, WBUF, 64, 64, (uint32_t)p); });
+        }
+        load_w(P.iH3, 1);
+        {                                                                         // 64 -> 32
+            float v[16];
+            ld_cols<16>(lane_addr + DB + 16 * sub, v);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = tanhf(v[c] + __ldg(wts + o.head_b2 + 16 * sub + c));
+            write_act<16>(ACT, 64, row, 16 * sub, v);
+            run_mma([&] { issue_layer(tmem + DA, ACT, WBUF, 32, 64, 0); });
+        }
+        load_w(P.iH4, 1);
+        {                                                                         // 32 -> 5 (padded to 8)
+            float v[8];
+            ld_cols<8>(lane_addr + DA + 8 * sub, v);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = tanhf(v[c] + __ldg(wts + o.head_b3 + 8 * sub + c));
+            write_act<8>(ACT, 32, row, 8 * sub, v);
+            run_mma([&] { issue_layer(tmem + DB, ACT, WBUF, 16, 32, 0); });   // N padded to 16
+        }
+        // ---------------- softmax, availability mask, renormalise, sample ----------------
+        if (sub == 0) {
+            float lg8[8];
+            ld_cols<8>(lane_addr + DB, lg8);
+            if (valid) {
+                float lg[CM_ACTIONS], pr[CM_ACTIONS];
+                float mx = -INFINITY;
+#pragma unroll
+                for (int a = 0; a < CM_ACTIONS; ++a) { lg[a] = lg8[a] + __ldg(wts + o.head_b4 + a); mx = fmaxf(mx, lg[a]); }
+                float sum = 0.0f;
+#pragma unroll
+                for (int a = 0; a < CM_ACTIONS; ++a) { pr[a] = expf(lg[a] - mx); sum += pr[a]; }
+                const uint32_t av = io.avail_bits ? io.avail_bits[g] : 0x1Fu;
+                float msum = 0.0f;
+#pragma unroll
+                for (int a = 0; a < CM_ACTIONS; ++a) { pr[a] = ((av >> a) & 1u) ? pr[a] / sum : 0.0f; msum += pr[a]; }
+#pragma unroll
+                for (int a = 0; a < CM_ACTIONS; ++a) pr[a] = pr[a] / msum;
+                if (io.logits) for (int a = 0; a < CM_ACTIONS; ++a) io.logits[g * CM_ACTIONS + a] = lg[a];
+                if (io.probs) for (int a = 0; a < CM_ACTIONS; ++a) io.probs[g * CM_ACTIONS + a] = pr[a];
+                if (io.actions) {
+                    int act;
+                    if (d.greedy) {
+                        act = 0;
+                        for (int a = 1; a < CM_ACTIONS; ++a) if (pr[a] > pr[act]) act = a;
+                    } else {
+                        float u;
+                        if (io.sample_u) u = io.sample_u[g];
+                        else {
+                            const uint4 blk = philox4x32_10(
+                                make_uint4((uint32_t)(d.env_id0 + env), io.tick[env], kStreamAct | (io.episode[env] << 8), (uint32_t)(il >> 2)),
+                                make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32)));
+                            const uint32_t w = (il & 3) == 0 ? blk.x : ((il & 3) == 1 ? blk.y : ((il & 3) == 2 ? blk.z : blk.w));
+                            u = u24(w);
+                        }
+                        int last = 4;
+                        for (int a = 0; a < CM_ACTIONS; ++a) if (pr[a] > 0.0f) last = a;
+                        act = -1;
+                        float c = 0.0f;
+                        for (int a = 0; a < CM_ACTIONS; ++a) { c += pr[a]; if (act < 0 && u < c) act = a; }
+                        if (act < 0) act = last;
+                    }
+                    io.actions[g] = (int8_t)act;
+                }
+            }
+        }
+        // the next tile's first MMA must not overwrite accumulators that are still being read
+        fence_before_thread_sync();
+        __syncthreads();
+        fence_after_thread_sync();
+    }
+    if (!ok && io.error_flag) atomicExch(io.error_flag, (int)CM_ECUDA);
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight preparation: fp32 k-major blob -> per-stage canonical hi | lo panels
+// ------------------------------------------------------------------------------------------------
+__global__ void tc_prepare_kernel(const float *__restrict__ w, float *__restrict__ out, const TcPlan P)
+{
+    for (int s = 0; s < P.n_stages; ++s) {
+        const TcStage st = P.st[s];
+        const int total = st.N * st.Kp;
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+            const int r = e / st.Kp, k = e - r * st.Kp;
+            float v = 0.0f;
+            if (r < st.Nsrc && st.k0 + k < st.Ksrc) v = w[st.src_off + (size_t)(st.k0 + k) * st.Nsrc + r];
+            const float h = tc::tf32_hi(v);
+            const int idx = (r >> 3) * (st.Kp >> 2) * 32 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3);
+            out[st.w_off + idx] = h;
+            out[st.w_off + total + idx] = tc::tf32_lo(v, h);
+        }
+    }
+}
+
+static size_t tc_smem_bytes() { return (size_t)kActBytes + kWBytes + 3 * 64 * kTPitch * 4 + 64; }
+
+int launch_policy_tc(const cm_policy_desc *desc, const cm_policy_io *io, cudaStream_t stream)
+{
+    if (!io->tc_weights) return CM_EINVAL;
+    if (desc->n_agents > 64 || desc->obs_dim > 128) return CM_EUNSUPPORTED;
+    TcArgs A;
+    A.d = *desc;
+    A.io = *io;
+    A.plan = make_tc_plan(desc->obs_dim, desc->n_layers);
+    A.envs_per_tile = kTcRows / desc->n_agents;
+    A.n_tiles = (io->n_envs + A.envs_per_tile - 1) / A.envs_per_tile;
+    const size_t smem = tc_smem_bytes();
+    static thread_local struct { int dev; int sms; } cache = {-1, 0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ENODEVICE);
+    if (cache.dev != dev) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ECUDA);
+        cudaError_t e = cudaFuncSetAttribute(policy_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
+        cache.dev = dev; cache.sms = sms;
+    }
+    const int grid = (int)(A.n_tiles < cache.sms ? A.n_tiles : cache.sms);   // persistent: one CTA per SM
+    policy_tc_kernel<<<grid, kTcThreads, smem, stream>>>(A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
+    return CM_OK;
+}
+
+}  // namespace cm
+
+extern "C" size_t cm_policy_tc_blob_floats(int32_t obs_dim, int32_t n_layers)
+{
+    return (size_t)cm::make_tc_plan(obs_dim, n_layers).total_floats;
+}
+
+extern "C" int cm_policy_tc_prepare(const cm_policy_desc *desc, const float *weights, float *tc_weights, cm_stream_t stream)
+{
+    if (!desc || !weights || !tc_weights) return CM_EINVAL;
+    if (desc->n_layers < 1 || desc->n_layers > CM_MAX_LAYERS || desc->obs_dim < 1 || desc->obs_dim > 128) return CM_EUNSUPPORTED;
+    if (cm_device_count() < 1) return CM_ENODEVICE;
+    const cm::TcPlan P = cm::make_tc_plan(desc->obs_dim, desc->n_layers);
+    cm::tc_prepare_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(weights, tc_weights, P);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? CM_OK : cm::set_cuda_error(e, CM_ECUDA);
+}

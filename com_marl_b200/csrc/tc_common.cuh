@@ -125,8 +125,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// tf32 split: hi keeps the 10 explicit mantissa bits tf32 has, lo is the exact remainder
-__device__ __forceinline__ float tf32_hi(float a) { return __uint_as_float(__float_as_uint(a) & 0xFFFFE000u); }
+// Error-compensated TF32 split: hi = x rounded to nearest TF32 (low 13 bits zero), lo = the exact remainder
+// x - hi, itself rounded to nearest TF32.  Rounding to NEAREST (cvt.rna) instead of letting the tensor core
+// truncate keeps the representation errors unbiased, so they accumulate like a random walk over K instead of
+// coherently.
+__device__ __forceinline__ float tf32_rna(float a)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float tf32_hi(float a) { return tf32_rna(a); }
+__device__ __forceinline__ float tf32_lo(float a, float hi) { return tf32_rna(a - hi); }
 
 }  // namespace tc
 }  // namespace cm

@@ -84,7 +84,7 @@ class _GraphConv(nn.Module):
 class CommCategoricalMLPPolicy(nn.Module):
     def __init__(self, env_spec, n_agents, encoder_hidden_sizes=(128,), embedding_dim=64, attention_type="general",
                  n_gcn_layers=2, residual=True, gcn_bias=True, categorical_mlp_hidden_sizes=(128, 64, 32),
-                 name="comm_categorical_mlp_policy", device="cuda", seed=1):
+                 name="comm_categorical_mlp_policy", device="cuda", seed=1, math="auto"):
         super().__init__()
         if not hasattr(env_spec.action_space, "n"):
             raise AssertionError("Categorical policy only works with akro.Discrete action space.")
@@ -103,6 +103,11 @@ class CommCategoricalMLPPolicy(nn.Module):
         self._embedding_dim = embedding_dim
         self.n_gcn_layers = int(n_gcn_layers)
         self.seed = int(seed)
+        # kernel variant: 'fp32' = exact FFMA kernels; 'tf32x3' = tcgen05 tensor cores with error-compensated TF32
+        # (fp32-level accuracy, teams of n <= 64); 'auto' picks tf32x3 whenever the team fits one tile
+        if math not in ("auto", "fp32", "tf32x3"):
+            raise ValueError("math must be 'auto', 'fp32' or 'tf32x3'")
+        self.math = math
         self.encoder = _MLP(self._dec_obs_dim, encoder_hidden_sizes, embedding_dim, output_tanh=True)
         self.attention_layer = _Attention(embedding_dim)
         self.gcn_layers = nn.ModuleList([_GraphConv(embedding_dim, gcn_bias) for _ in range(self.n_gcn_layers)])
@@ -110,6 +115,9 @@ class CommCategoricalMLPPolicy(nn.Module):
         self.to(self.device)
         self._blob = None
         self._blob_sig = None
+        self._tc_blob = None
+        self._tc_sig = None
+        self._tc_error = None
         self._workspace = None
 
     # ---- weight blob (layout in include/commarl_b200.h) ----------------------------------------------
@@ -138,6 +146,29 @@ class CommCategoricalMLPPolicy(nn.Module):
             self._blob, self._blob_sig = blob.contiguous(), sig
         return self._blob
 
+    def uses_tensor_cores(self):
+        return self.math == "tf32x3" or (self.math == "auto" and self._n_agents <= 64)
+
+    def tc_weight_blob(self):
+        """pre-split (hi | lo), pre-laid-out B operands of the tcgen05 variant; rebuilt when a parameter changed"""
+        blob = self.weight_blob()
+        if self._tc_blob is None or self._tc_sig != self._blob_sig:
+            L = self.n_gcn_layers
+            n_floats = N.lib().cm_policy_tc_blob_floats(self._dec_obs_dim, L)
+            out = torch.empty(n_floats, dtype=torch.float32, device=self.device)
+            desc = N.PolicyDesc(self._n_agents, self._dec_obs_dim, L, int(self.residual), 0, 1, self.seed, 0)
+            with torch.cuda.device(self.device):
+                N.check("cm_policy_tc_prepare", N.lib().cm_policy_tc_prepare(C.byref(desc), N.ptr(blob), N.ptr(out), N.stream_ptr()))
+            self._tc_blob, self._tc_sig = out, self._blob_sig
+            if self._tc_error is None:
+                self._tc_error = torch.zeros(1, dtype=torch.int32, device=self.device)
+        return self._tc_blob
+
+    def check_errors(self):
+        if self._tc_error is not None and int(self._tc_error.item()):
+            self._tc_error.zero_()
+            raise N.NativeError("policy_tc_kernel", N.CM_ECUDA, "a bounded device-side wait timed out")
+
     # ---- device fast path (no host copies) --------------------------------------------------------------
     def act_device(self, obs, adj_bits=None, chan_bits=None, avail_bits=None, sample_u=None, tick=None, episode=None,
                    greedy=False, probs=None, logits=None, attention=None, actions=None, env_id0=0):
@@ -145,10 +176,16 @@ class CommCategoricalMLPPolicy(nn.Module):
         given tensors (allocate once, reuse: the call is CUDA-graph capturable)."""
         n, D, L = self._n_agents, self._dec_obs_dim, self.n_gcn_layers
         B = obs.shape[0]
-        desc = N.PolicyDesc(n, D, L, int(self.residual), int(greedy), self.seed, env_id0)
+        tc = self.uses_tensor_cores()
+        if tc and n > 64:
+            raise ValueError("math='tf32x3' supports teams of at most 64 agents; use math='fp32'")
+        desc = N.PolicyDesc(n, D, L, int(self.residual), int(greedy), int(tc), self.seed, env_id0)
         io = N.PolicyIO()
         io.n_envs = B
         io.weights = N.ptr(self.weight_blob())
+        if tc:
+            io.tc_weights = N.ptr(self.tc_weight_blob())
+            io.error_flag = N.ptr(self._tc_error)
         for k, v in (("obs", obs), ("adj_bits", adj_bits), ("chan_bits", chan_bits), ("avail_bits", avail_bits),
                      ("sample_u", sample_u), ("tick", tick), ("episode", episode), ("probs", probs), ("logits", logits),
                      ("attention", attention), ("actions", actions)):

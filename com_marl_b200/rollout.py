@@ -21,13 +21,14 @@ from .spaces import Box, Discrete, EnvSpec
 STAT_KEYS = ("episodes", "return_sum", "length_sum", "success_sum", "c0_sum", "moved_sum", "c2_sum", "c3_sum", "c4_sum")
 
 
-def make_policy(spec: ScenarioSpec, device="cuda", seed: Optional[int] = None, torch_seed: int = 1) -> CommCategoricalMLPPolicy:
+def make_policy(spec: ScenarioSpec, device="cuda", seed: Optional[int] = None, torch_seed: int = 1,
+                math: str = "auto") -> CommCategoricalMLPPolicy:
     """Policy with the reference initialisation under torch.manual_seed(torch_seed)."""
     n, D = spec.n_agents, spec.obs_dim
     env_spec = EnvSpec(Box(np.zeros(n * D, np.float32), np.ones(n * D, np.float32)), Discrete(5))
     torch.manual_seed(torch_seed)
     return CommCategoricalMLPPolicy(env_spec, n, n_gcn_layers=spec.n_layers, device=device,
-                                    seed=spec.seed if seed is None else seed)
+                                    seed=spec.seed if seed is None else seed, math=math)
 
 
 class RolloutEngine:

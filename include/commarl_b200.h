@@ -149,6 +149,8 @@ typedef struct cm_policy_desc {
     int32_t n_layers;          /* L */
     int32_t residual;          /* comm_categorical_mlp_policy.py:74-77 */
     int32_t greedy;            /* argmax instead of sampling (:109-112) */
+    int32_t math;              /* 0: exact fp32 FFMA kernels; 1: tcgen05 tensor cores with error-compensated TF32
+                                  (fp32-level accuracy, teams with n <= 64; needs io.tc_weights) */
     uint64_t seed;
     int64_t env_id0;
 } cm_policy_desc;
@@ -167,6 +169,8 @@ typedef struct cm_policy_io {
     float *logits;             /* [B][n][5] raw head output, or NULL */
     float *attention;          /* [B][n][n] unmasked attention softmax (agent_infos['attention_weights']), or NULL */
     int8_t *actions;           /* [B][n], or NULL */
+    const float *tc_weights;   /* math == 1: blob written by cm_policy_tc_prepare() (cm_policy_tc_blob_floats() floats) */
+    int32_t *error_flag;       /* DEVICE i32[1], optional: set when a bounded device-side wait times out */
     float *workspace;          /* teams with n > 64 only: cm_policy_workspace_bytes() bytes of scratch (stays L2 resident) */
     size_t workspace_bytes;
 } cm_policy_io;
@@ -199,6 +203,10 @@ int cm_comm_update(const cm_env_desc *desc, const cm_env_state *state, const cm_
  * graph_conv_module.py:51-72, categorical_mlp_module.py:64-80, multi_headed_mlp_module.py:134-149). */
 int cm_policy_forward(const cm_policy_desc *desc, const cm_policy_io *io, cm_stream_t stream);
 size_t cm_policy_blob_floats(int32_t obs_dim, int32_t n_layers);
+/* tcgen05 variant: re-lays the fp32 weight blob out as pre-split (hi | lo) K-major core-matrix panels, one per
+ * tensor-core product, so that the kernel fetches a layer's B operand with one bulk async copy */
+size_t cm_policy_tc_blob_floats(int32_t obs_dim, int32_t n_layers);
+int cm_policy_tc_prepare(const cm_policy_desc *desc, const float *weights, float *tc_weights, cm_stream_t stream);
 /* scratch the forward needs for teams larger than one 64-row tile (0 for n <= 64) */
 size_t cm_policy_workspace_bytes(int32_t n_agents, int64_t n_envs);
 

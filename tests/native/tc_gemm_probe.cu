@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(128) tc_gemm_probe_kernel(const float *A, cons
         const float4 h = make_float4(tf32_hi(a.x), tf32_hi(a.y), tf32_hi(a.z), tf32_hi(a.w));
         const uint32_t off = canon_off(tid, 4 * kc, K);
         *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(Ahi) + off) = h;
-        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(Alo) + off) = make_float4(a.x - h.x, a.y - h.y, a.z - h.z, a.w - h.w);
+        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(Alo) + off) = make_float4(tf32_lo(a.x, h.x), tf32_lo(a.y, h.y), tf32_lo(a.z, h.z), tf32_lo(a.w, h.w));
     }
     for (int r = tid; r < N; r += 128)
         for (int kc = 0; kc < K / 4; ++kc) {
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128) tc_gemm_probe_kernel(const float *A, cons
             const float4 h = make_float4(tf32_hi(b.x), tf32_hi(b.y), tf32_hi(b.z), tf32_hi(b.w));
             const uint32_t off = canon_off(r, 4 * kc, K);
             *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(Bhi) + off) = h;
-            *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(Blo) + off) = make_float4(b.x - h.x, b.y - h.y, b.z - h.z, b.w - h.w);
+            *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(Blo) + off) = make_float4(tf32_lo(b.x, h.x), tf32_lo(b.y, h.y), tf32_lo(b.z, h.z), tf32_lo(b.w, h.w));
         }
     fence_proxy_async();
     fence_before_thread_sync();

@@ -15,20 +15,23 @@ pytestmark = pytest.mark.gpu
 SMALL = policy_cases()
 
 
-def _policy(n, D, L, weights=None, seed=0):
+def _policy(n, D, L, weights=None, seed=0, math="fp32"):
     from com_marl_b200.policy import CommCategoricalMLPPolicy
     from com_marl_b200.spaces import Box, Discrete, EnvSpec
     torch.manual_seed(seed)
-    pol = CommCategoricalMLPPolicy(EnvSpec(Box(np.zeros(n * D), np.ones(n * D)), Discrete(5)), n, n_gcn_layers=L)
+    pol = CommCategoricalMLPPolicy(EnvSpec(Box(np.zeros(n * D), np.ones(n * D)), Discrete(5)), n, n_gcn_layers=L, math=math)
     if weights is not None:
         pol.load_state_dict({k: torch.as_tensor(v) for k, v in weights.items()})   # reference checkpoints load as is
     return pol
 
 
+@pytest.mark.parametrize("math", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("name", SMALL)
-def test_policy_kernel_matches_reference_golden(name):
+def test_policy_kernel_matches_reference_golden(name, math):
     c = PolicyCase(name)
-    pol = _policy(c.n, c.D, c.L, c.weights)
+    if math == "tf32x3" and c.n > 64:
+        pytest.skip("the tcgen05 variant covers teams of n <= 64; larger teams run the fp32 kernel")
+    pol = _policy(c.n, c.D, c.L, c.weights, math=math)
     dist, attn = pol.forward(c.obs.reshape(c.B, -1), c.avail.reshape(c.B, -1), c.adj.astype(np.float32),
                              c.chan.astype(np.float32), get_actions=True)
     probs = dist.probs.numpy()
@@ -41,8 +44,11 @@ def test_policy_kernel_matches_reference_golden(name):
     ch = pol.pack_mask(torch.from_numpy(c.chan.astype(np.float32)).to(dev), c.n)
     logits = torch.empty((c.B, c.n, 5), device=dev)
     pol.act_device(obs, adj, ch, logits=logits, greedy=True)
+    pol.check_errors()
     scale = max(1.0, float(np.abs(c.logits).max()))
-    assert np.abs(logits.cpu().numpy() - c.logits).max() <= 1e-5 * scale
+    err = np.abs(logits.cpu().numpy() - c.logits).max() / scale
+    print(f"{name} {math}: logits rel err {err:.2e}")
+    assert err <= 1e-5
     # and the differentiable torch path of the same module (used by the PPO update) agrees too
     with torch.no_grad():
         # shaped like process_samples hands them over: adj (.., n*n), channels (.., L*n, n)  (…vectorized_sampler.py:176,183)
@@ -52,14 +58,17 @@ def test_policy_kernel_matches_reference_golden(name):
     assert np.abs(d2.probs.cpu().numpy() - c.probs).max() <= 1e-5
 
 
+@pytest.mark.parametrize("math", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("n,D,B,ploss", [(3, 29, 16384, 0.0), (4, 21, 5000, 0.3), (32, 53, 2048, 0.2), (54, 77, 777, 0.1),
                                          (7, 53, 1001, 0.5), (64, 29, 64, 0.4), (1, 21, 100, 0.0),
                                          (65, 21, 70, 0.2), (72, 53, 301, 0.3), (200, 53, 97, 0.2), (256, 29, 9, 0.5)])
-def test_policy_kernel_matches_oracle_batched(n, D, B, ploss):
+def test_policy_kernel_matches_oracle_batched(n, D, B, ploss, math):
     """Random binary observations + random masks on big ragged batches (last tile partial) vs the numpy
     restatement; sampling reproduces the inverse-CDF stream specification exactly."""
+    if math == "tf32x3" and n > 64:
+        pytest.skip("the tcgen05 variant covers teams of n <= 64")
     rng = np.random.default_rng(n * 1000 + D)
-    pol = _policy(n, D, 2, seed=n)
+    pol = _policy(n, D, 2, seed=n, math=math)
     with torch.no_grad():
         for k, v in pol.state_dict().items():
             if k.endswith("bias"):
@@ -81,9 +90,12 @@ def test_policy_kernel_matches_oracle_batched(n, D, B, ploss):
     attn = torch.empty((B, n, n), device=dev)
     actions = torch.empty((B, n), dtype=torch.int8, device=dev)
     pol.act_device(t(obs), adj_b, ch_b, av_b, t(u), probs=probs, logits=logits, attention=attn, actions=actions)
+    pol.check_errors()
     ref_logits, ref_probs, ref_attn = orc.policy_forward(w, obs, avail, adj, chan, dtype=np.float64)
     scale = max(1.0, float(np.abs(ref_logits).max()))
-    assert np.abs(logits.cpu().numpy() - ref_logits).max() <= 1e-5 * scale
+    err = np.abs(logits.cpu().numpy() - ref_logits).max() / scale
+    print(f"n={n} D={D} {math}: logits rel err {err:.2e}")
+    assert err <= 1e-5
     assert np.abs(probs.cpu().numpy() - ref_probs).max() <= 1e-5
     assert np.abs(attn.cpu().numpy() - ref_attn).max() <= 1e-5
     # sampling: exact against the oracle's inverse CDF evaluated on the kernel's own probabilities
@@ -106,7 +118,7 @@ def test_policy_kernel_matches_oracle_batched(n, D, B, ploss):
 
 def test_get_actions_contract():
     """get_actions returns what the reference returns: int64 actions (B,n), lists of per-env arrays."""
-    pol = _policy(4, 21, 2)
+    pol = _policy(4, 21, 2, math="auto")
     rng = np.random.default_rng(0)
     obs = rng.random((5, 84)).astype(np.float32)
     acts, infos = pol.get_actions(obs, np.ones((5, 20)), np.ones((5, 4, 4)), np.ones((5, 2, 4, 4)))
