@@ -70,36 +70,94 @@ __device__ __forceinline__ void write_act(unsigned char *act, int Kp, int row, i
     }
 }
 
-// one thread: D[tmem] (+)= ACT * W^T, error-compensated (hi*hi + lo*hi + hi*lo)
+// tanh through ex2.approx / rcp.approx: |error| <= ~3e-7 absolute (two units of fp32 rounding at 1.0), an order
+// of magnitude below what the 3xTF32 products contribute and ~4x fewer instructions than tanhf.
+__device__ __forceinline__ float tanh_fast(float x)
+{
+    const float e = __expf(2.0f * x);
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+
+// one converged warp: D[tmem] (+)= ACT * W^T, error-compensated (hi*hi + lo*hi + hi*lo).  All lanes run the loop
+// (descriptors stay warp-uniform), the elected lane issues.
 __device__ __forceinline__ void issue_layer(uint32_t d_tmem, const unsigned char *act, const unsigned char *wblk, int N, int Kp,
                                             uint32_t accumulate)
 {
     const uint32_t a_hi = smem_u32(act), a_lo = a_hi + (uint32_t)kTcRows * Kp * 4;
     const uint32_t b_hi = smem_u32(wblk), b_lo = b_hi + (uint32_t)N * Kp * 4;
     const uint32_t idesc = make_idesc_tf32(kTcRows, N);
+    const int nk = Kp >> 3;
     uint32_t acc = accumulate;
 #pragma unroll 1
     for (int p = 0; p < 3; ++p) {
-        const uint32_t a = (p == 1) ? a_lo : a_hi, b = (p == 2) ? b_lo : b_hi;
-#pragma unroll 1
-        for (int j = 0; j < Kp / 8; ++j) {
-            mma_tf32(d_tmem, make_smem_desc(a, Kp, j), make_smem_desc(b, Kp, j), idesc, acc);
+        uint64_t da = make_smem_desc((p == 1) ? a_lo : a_hi, Kp, 0), db = make_smem_desc((p == 2) ? b_lo : b_hi, Kp, 0);
+#pragma unroll 2
+        for (int j = 0; j < nk; ++j) {
+            if (elect_one()) mma_tf32(d_tmem, da, db, idesc, acc);
             acc = 1;
+            da += 16;     // next K = 8 slice: start address + 256 bytes (>> 4)
+            db += 16;
         }
     }
+    __syncwarp();
 }
+
+// Exact per-environment attention row: thread (row, sub) owns the keys jj = sub, sub + 4, ... of its env (at most
+// KT of them), scores = Q[row] . E[key], softmax across the four threads of the row through `red`, result into
+// M^T[jj][row] (which overwrites Q^T once every thread has read it).
+template <int KT>
+__device__ __forceinline__ void scores_softmax(float *QT, const float *ET, float *red, int row, int j0, int sub, int n, bool valid)
+{
+    float sc[KT];
+    const int nk = valid ? (n - sub + 3) / 4 : 0;
+#pragma unroll
+    for (int t = 0; t < KT; ++t) sc[t] = 0.0f;
+    if (nk > 0) {
+#pragma unroll 4
+        for (int k = 0; k < 64; ++k) {
+            const float qv = QT[k * kTPitch + row];
+            const float *er = ET + k * kTPitch + j0 + sub;
+#pragma unroll
+            for (int t = 0; t < KT; ++t)
+                if (t < nk) sc[t] = fmaf(qv, er[4 * t], sc[t]);
+        }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < KT; ++t)
+        if (t < nk) mx = fmaxf(mx, sc[t]);
+    red[sub * kTPitch + row] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[row], red[kTPitch + row]), fmaxf(red[2 * kTPitch + row], red[3 * kTPitch + row]));
+    float sum = 0.0f;
+#pragma unroll
+    for (int t = 0; t < KT; ++t)
+        if (t < nk) { sc[t] = expf(sc[t] - mx); sum += sc[t]; }
+    red[(4 + sub) * kTPitch + row] = sum;
+    __syncthreads();                      // everybody has read QT: it becomes M^T [n][128]
+    const float z = red[4 * kTPitch + row] + red[5 * kTPitch + row] + red[6 * kTPitch + row] + red[7 * kTPitch + row];
+#pragma unroll
+    for (int t = 0; t < KT; ++t)
+        if (t < nk) QT[(sub + 4 * t) * kTPitch + row] = sc[t] / z;
+    __syncthreads();
+}
+
+// bias offsets inside the shared-memory bias table
+static constexpr int kBEnc1 = 0, kBEnc2 = 128, kBGcn = 192, kBH1 = 448, kBH2 = 576, kBH3 = 640, kBH4 = 672, kBiasFloats = 704;
+
+struct MmaOp { uint32_t dcol, acc; };
 
 __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *ACT = smem;
-    unsigned char *WBUF = smem + kActBytes;
+    unsigned char *WB = smem + kActBytes;                                // weight ring: 2 slots of 32 KB
     float *ET = reinterpret_cast<float *>(smem + kActBytes + kWBytes);   // [64][128] E^T   (keys, residual)
     float *QT = ET + 64 * kTPitch;                                       // [64][128] Q^T, then M^T [n][128]
     float *HWT = QT + 64 * kTPitch;                                      // [64][128] (H_l Wg_l)^T; softmax scratch before that
-    uint64_t *bars = reinterpret_cast<uint64_t *>(HWT + 64 * kTPitch);   // [0] weights landed, [1] MMAs done
-    uint32_t *tmem_s = reinterpret_cast<uint32_t *>(bars + 2);
-    int *fail_s = reinterpret_cast<int *>(tmem_s + 1);
+    float *bias_s = HWT + 64 * kTPitch;                                  // [704]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + kBiasFloats); // [0],[1] weight slot full, [2] MMAs done
+    uint32_t *tmem_s = reinterpret_cast<uint32_t *>(bars + 3);
 
     const cm_policy_desc &d = A.d;
     const cm_policy_io &io = A.io;
@@ -115,8 +173,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
         fence_mbar_init();
-        *fail_s = 0;
+    }
+    for (int i = tid; i < kBiasFloats; i += kTcThreads) {
+        float v = 0.0f;
+        if (i < kBEnc2) v = wts[o.enc_b1 + i];
+        else if (i < kBGcn) v = wts[o.enc_b2 + i - kBEnc2];
+        else if (i < kBH1) { if (i - kBGcn < L * 64) v = wts[o.gcn_b + i - kBGcn]; }
+        else if (i < kBH2) v = wts[o.head_b1 + i - kBH1];
+        else if (i < kBH3) v = wts[o.head_b2 + i - kBH2];
+        else if (i < kBH4) v = wts[o.head_b3 + i - kBH3];
+        else if (i < kBH4 + CM_ACTIONS) v = wts[o.head_b4 + i - kBH4];
+        bias_s[i] = v;
     }
     fence_before_thread_sync();
     __syncthreads();
@@ -124,34 +193,58 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
     const uint32_t tmem = *tmem_s;
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     const uint32_t DA = 0, DB = 128;          // accumulator column regions
-    uint32_t w_phase = 0, m_phase = 0;        // mbarrier parities (w_phase is only used by thread 0)
+    uint32_t m_phase = 0;
     bool ok = true;
 
-    // thread 0: start the bulk copy of stage(s) [s0, s0 + cnt) into WBUF
-    auto load_w = [&](int s0, int cnt) {
-        if (tid == 0) {
-            uint32_t bytes = 0;
-            for (int s = s0; s < s0 + cnt; ++s) bytes += (uint32_t)(2 * P.st[s].N * P.st[s].Kp * 4);
-            mbar_expect_tx(&bars[0], bytes);
-            bulk_g2s(WBUF, tcw + P.st[s0].w_off, bytes, &bars[0]);
+    // ---- weight stream: the stages of the plan are consumed in order, tile after tile; thread 0 keeps the
+    // two ring slots full (a slot is refilled as soon as the product that read it has completed) ----
+    const uint32_t my_tiles = (uint32_t)((A.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const uint32_t total_blocks = my_tiles * (uint32_t)P.seq_len;
+    uint32_t consumed = 0;                    // blocks consumed so far (uniform)
+    uint32_t issued = 0, issued_si = 0;       // warp 0: blocks requested so far, and their stage index
+    auto issue_loads = [&]() {          // warp 0, converged
+        if (warp == 0) {
+            while (issued < consumed + 2 && issued < total_blocks) {
+                const TcStage &st = P.st[issued_si];
+                const uint32_t bytes = (uint32_t)(2 * st.N * st.Kp * 4), slot = issued & 1u;
+                if (elect_one()) {
+                    mbar_expect_tx(&bars[slot], bytes);
+                    bulk_g2s(WB + slot * 32768u, tcw + st.w_off, bytes, &bars[slot]);
+                }
+                __syncwarp();
+                ++issued;
+                issued_si = (issued_si + 1 == (uint32_t)P.seq_len) ? 0u : issued_si + 1;
+            }
         }
     };
-    // all threads: ACT is written -> thread 0 issues `issue()` once the weights have landed -> everybody waits
-    auto run_mma = [&](auto issue) {
+    issue_loads();
+    int si = 0;                               // stage index inside the current tile (uniform)
+    // all threads: ACT is written -> thread 0 issues one product per op, each against the next weight block ->
+    // everybody waits for their completion -> the freed ring slots are refilled
+    auto run_mma = [&](int nops, MmaOp op0, MmaOp op1) {
         fence_proxy_async();
         fence_before_thread_sync();
         __syncthreads();
-        if (tid == 0) {
-            ok = mbar_wait(&bars[0], w_phase) && ok;
-            w_phase ^= 1;
+        if (warp == 0) {                 // whole warp, converged: waits for the weights, elected lane issues
             fence_after_thread_sync();
-            issue();
-            mma_commit(&bars[1]);
+            for (int i = 0; i < nops; ++i) {
+                const uint32_t b = consumed + (uint32_t)i;
+                ok = mbar_wait(&bars[b & 1u], (b >> 1) & 1u) && ok;
+                const TcStage &st = P.st[si + i];
+                const MmaOp op = i ? op1 : op0;
+                issue_layer(tmem + op.dcol, ACT, WB + (b & 1u) * 32768u, st.N, st.Kp, op.acc);
+            }
+            if (elect_one()) mma_commit(&bars[2]);
+            __syncwarp();
         }
-        ok = mbar_wait(&bars[1], m_phase) && ok;
+        ok = mbar_wait(&bars[2], m_phase) && ok;
         m_phase ^= 1;
         fence_after_thread_sync();
+        consumed += (uint32_t)nops;
+        si += nops;
+        issue_loads();
     };
+    const MmaOp none = {0u, 0u};
 
     for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
         const int64_t env0 = tile * A.envs_per_tile;
@@ -161,65 +254,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
         const bool valid = row < rows;
         const int el = valid ? row / n : 0, il = row - el * n, j0 = el * n;
         const int64_t env = env0 + el, g = row0 + row;
+        si = 0;
 
         // ---------------- encoder layer 1: obs panels -> DA[0:128] ----------------
-        load_w(P.iW1a, 1);
-        {
-            const int Kp = P.st[P.iW1a].Kp;
+        for (int pnl = 0; pnl < P.l1_panels; ++pnl) {
+            const int Kp = P.st[si].Kp, kofs = 64 * pnl;
             const float *src = io.obs + row0 * D;
             const uint32_t lo_off = (uint32_t)kTcRows * Kp * 4;
             for (int e = tid; e < kTcRows * Kp; e += kTcThreads) {
                 const int r = e / Kp, k = e - r * Kp;
-                const float v = (r < rows && k < D) ? __ldg(src + (size_t)r * D + k) : 0.0f;
+                const float v = (r < rows && kofs + k < D) ? __ldg(src + (size_t)r * D + kofs + k) : 0.0f;
                 const float h = tf32_hi(v);
                 const uint32_t off = canon_off(r, k, Kp);
                 *reinterpret_cast<float *>(ACT + off) = h;
                 *reinterpret_cast<float *>(ACT + lo_off + off) = tf32_lo(v, h);
             }
-            run_mma([&] { issue_layer(tmem + DA, ACT, WBUF, 128, Kp, 0); });
-        }
-        if (P.iW1b >= 0) {               // observation wider than 64: second K panel accumulates
-            load_w(P.iW1b, 1);
-            const int Kp = P.st[P.iW1b].Kp;
-            const float *src = io.obs + row0 * D;
-            const uint32_t lo_off = (uint32_t)kTcRows * Kp * 4;
-            for (int e = tid; e < kTcRows * Kp; e += kTcThreads) {
-                const int r = e / Kp, k = e - r * Kp;
-                const float v = (r < rows && 64 + k < D) ? __ldg(src + (size_t)r * D + 64 + k) : 0.0f;
-                const float h = tf32_hi(v);
-                const uint32_t off = canon_off(r, k, Kp);
-                *reinterpret_cast<float *>(ACT + off) = h;
-                *reinterpret_cast<float *>(ACT + lo_off + off) = tf32_lo(v, h);
-            }
-            run_mma([&] { issue_layer(tmem + DA, ACT, WBUF, 128, Kp, 1); });
+            if (pnl == 0 && P.l1_split) run_mma(2, MmaOp{DA, 0u}, MmaOp{DA + 64, 0u});
+            else run_mma(1, MmaOp{DA, (uint32_t)pnl}, none);
         }
         // ---------------- encoder layer 2 (K = 128 as two panels of h) -> DB[0:64] ----------------
         for (int p = 0; p < 2; ++p) {
-            load_w(P.iW2a + p, 1);
             float v[16];
             ld_cols<16>(lane_addr + DA + 64 * p + 16 * sub, v);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = tanhf(v[c] + __ldg(wts + o.enc_b1 + 64 * p + 16 * sub + c));
+            for (int c = 0; c < 16; ++c) v[c] = tanh_fast(v[c] + bias_s[kBEnc1 + 64 * p + 16 * sub + c]);
             write_act<16>(ACT, 64, row, 16 * sub, v);
-            run_mma([&] { issue_layer(tmem + DB, ACT, WBUF, 64, 64, (uint32_t)p); });
+            run_mma(1, MmaOp{DB, (uint32_t)p}, none);
         }
-        // ---------------- E = tanh(. + b2): k-major fp32 copy + A operand; Q and H_0 Wg_0 -> DA[0:64], DA[64:128] ----------------
-        load_w(P.iWQ, 2);                 // Wa and Wg_0 are adjacent in the blob: one copy
+        // ---------------- E = tanh(. + b2): k-major fp32 copy + A operand; Q -> DA[0:64], H_0 Wg_0 -> DA[64:128] ----------------
         {
             float v[16];
             ld_cols<16>(lane_addr + DB + 16 * sub, v);
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-                v[c] = tanhf(v[c] + __ldg(wts + o.enc_b2 + 16 * sub + c));
+                v[c] = tanh_fast(v[c] + bias_s[kBEnc2 + 16 * sub + c]);
                 ET[(16 * sub + c) * kTPitch + row] = v[c];
             }
             write_act<16>(ACT, 64, row, 16 * sub, v);
-            run_mma([&] {
-                issue_layer(tmem + DA, ACT, WBUF, 64, 64, 0);
-                issue_layer(tmem + DA + 64, ACT, WBUF + 2 * 64 * 64 * 4, 64, 64, 0);
-            });
+            run_mma(2, MmaOp{DA, 0u}, MmaOp{DA + 64, 0u});
         }
-        if (L > 1) load_w(P.iWG + 1, 1); else load_w(P.iH1, 1);
         // ---------------- scores, softmax (exact per environment, CUDA cores) ----------------
         {
             float v[16];
@@ -228,42 +301,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
             for (int c = 0; c < 16; ++c) QT[(16 * sub + c) * kTPitch + row] = v[c];
         }
         __syncthreads();
-        float *red = HWT;                 // [2][4][128] softmax scratch (HWT is filled after the softmax)
-        float sc[16];
-        const int nk = valid ? (n - sub + 3) / 4 : 0;          // my keys: jj = sub, sub + 4, ...
-        {
-#pragma unroll
-            for (int t = 0; t < 16; ++t) sc[t] = 0.0f;
-            for (int k = 0; k < 64; ++k) {
-                const float qv = QT[k * kTPitch + row];
-                const float *er = ET + k * kTPitch + j0 + sub;
-#pragma unroll
-                for (int t = 0; t < 16; ++t)
-                    if (t < nk) sc[t] = fmaf(qv, er[4 * t], sc[t]);
-            }
-            float mx = -INFINITY;
-#pragma unroll
-            for (int t = 0; t < 16; ++t)
-                if (t < nk) mx = fmaxf(mx, sc[t]);
-            red[sub * kTPitch + row] = mx;
+        // scores, row softmax -> M^T; QT is overwritten by M^T once every thread has read it
+        switch (n <= 4 ? 1 : (n <= 8 ? 2 : (n <= 16 ? 4 : (n <= 32 ? 8 : 16)))) {
+        case 1: scores_softmax<1>(QT, ET, HWT, row, j0, sub, n, valid); break;
+        case 2: scores_softmax<2>(QT, ET, HWT, row, j0, sub, n, valid); break;
+        case 4: scores_softmax<4>(QT, ET, HWT, row, j0, sub, n, valid); break;
+        case 8: scores_softmax<8>(QT, ET, HWT, row, j0, sub, n, valid); break;
+        default: scores_softmax<16>(QT, ET, HWT, row, j0, sub, n, valid); break;
         }
-        __syncthreads();
-        {
-            const float mx = fmaxf(fmaxf(red[row], red[kTPitch + row]), fmaxf(red[2 * kTPitch + row], red[3 * kTPitch + row]));
-            float sum = 0.0f;
-#pragma unroll
-            for (int t = 0; t < 16; ++t)
-                if (t < nk) { sc[t] = expf(sc[t] - mx); sum += sc[t]; }
-            red[(4 + sub) * kTPitch + row] = sum;
-        }
-        __syncthreads();                  // everybody has read QT: it becomes M^T [n][128]
-        {
-            const float z = red[4 * kTPitch + row] + red[5 * kTPitch + row] + red[6 * kTPitch + row] + red[7 * kTPitch + row];
-#pragma unroll
-            for (int t = 0; t < 16; ++t)
-                if (t < nk) QT[(sub + 4 * t) * kTPitch + row] = sc[t] / z;
-        }
-        __syncthreads();
         const float *MT = QT;
         if (io.attention) {               // unmasked softmax (agent_infos['attention_weights'])
             float *dst = io.attention + row0 * n;
@@ -315,13 +360,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
             float v[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-                v[c] = tanhf(acc[c] * inv + __ldg(wts + o.gcn_b + l * 64 + 16 * sub + c));
+                v[c] = tanh_fast(acc[c] * inv + bias_s[kBGcn + l * 64 + 16 * sub + c]);
                 if (l + 1 == L && d.residual) v[c] += ET[(16 * sub + c) * kTPitch + row];   // X = E + H_L
             }
             write_act<16>(ACT, 64, row, 16 * sub, v);
             if (l + 1 < L) {
-                run_mma([&] { issue_layer(tmem + DB, ACT, WBUF, 64, 64, 0); });
-                if (l + 2 < L) load_w(P.iWG + l + 2, 1); else load_w(P.iH1, 1);
+                run_mma(1, MmaOp{DB, 0u}, none);
                 float hv[16];
                 ld_cols<16>(lane_addr + DB + 16 * sub, hv);
                 __syncthreads();          // every thread is done reading HWT of layer l
@@ -331,33 +375,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
             }
         }
         // ---------------- categorical head ----------------
-        run_mma([&] { issue_layer(tmem + DA, ACT, WBUF, 128, 64, 0); });        // 64 -> 128
+        if (P.h1_split) run_mma(2, MmaOp{DA, 0u}, MmaOp{DA + 64, 0u});          // 64 -> 128
+        else run_mma(1, MmaOp{DA, 0u}, none);
         for (int p = 0; p < 2; ++p) {                                             // 128 -> 64 as two K panels
-            load_w(P.iH2a + p, 1);
             float v[16];
             ld_cols<16>(lane_addr + DA + 64 * p + 16 * sub, v);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = tanhf(v[c] + __ldg(wts + o.head_b1 + 64 * p + 16 * sub + c));
+            for (int c = 0; c < 16; ++c) v[c] = tanh_fast(v[c] + bias_s[kBH1 + 64 * p + 16 * sub + c]);
             write_act<16>(ACT, 64, row, 16 * sub, v);
-            run_mma([&] { issue_layer(tmem + DB, ACT, WBUF, 64, 64, (uint32_t)p); });
+            run_mma(1, MmaOp{DB, (uint32_t)p}, none);
         }
-        load_w(P.iH3, 1);
         {                                                                         // 64 -> 32
             float v[16];
             ld_cols<16>(lane_addr + DB + 16 * sub, v);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = tanhf(v[c] + __ldg(wts + o.head_b2 + 16 * sub + c));
+            for (int c = 0; c < 16; ++c) v[c] = tanh_fast(v[c] + bias_s[kBH2 + 16 * sub + c]);
             write_act<16>(ACT, 64, row, 16 * sub, v);
-            run_mma([&] { issue_layer(tmem + DA, ACT, WBUF, 32, 64, 0); });
+            run_mma(1, MmaOp{DA, 0u}, none);
         }
-        load_w(P.iH4, 1);
-        {                                                                         // 32 -> 5 (padded to 8)
+        {                                                                         // 32 -> 5 (padded to 16)
             float v[8];
             ld_cols<8>(lane_addr + DA + 8 * sub, v);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v[c] = tanhf(v[c] + __ldg(wts + o.head_b3 + 8 * sub + c));
+            for (int c = 0; c < 8; ++c) v[c] = tanh_fast(v[c] + bias_s[kBH3 + 8 * sub + c]);
             write_act<8>(ACT, 32, row, 8 * sub, v);
-            run_mma([&] { issue_layer(tmem + DB, ACT, WBUF, 16, 32, 0); });   // N padded to 16
+            run_mma(1, MmaOp{DB, 0u}, none);
         }
         // ---------------- softmax, availability mask, renormalise, sample ----------------
         if (sub == 0) {
@@ -367,7 +409,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
                 float lg[CM_ACTIONS], pr[CM_ACTIONS];
                 float mx = -INFINITY;
 #pragma unroll
-                for (int a = 0; a < CM_ACTIONS; ++a) { lg[a] = lg8[a] + __ldg(wts + o.head_b4 + a); mx = fmaxf(mx, lg[a]); }
+                for (int a = 0; a < CM_ACTIONS; ++a) { lg[a] = lg8[a] + bias_s[kBH4 + a]; mx = fmaxf(mx, lg[a]); }
                 float sum = 0.0f;
 #pragma unroll
                 for (int a = 0; a < CM_ACTIONS; ++a) { pr[a] = expf(lg[a] - mx); sum += pr[a]; }
@@ -427,7 +469,7 @@ __global__ void tc_prepare_kernel(const float *__restrict__ w, float *__restrict
         for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
             const int r = e / st.Kp, k = e - r * st.Kp;
             float v = 0.0f;
-            if (r < st.Nsrc && st.k0 + k < st.Ksrc) v = w[st.src_off + (size_t)(st.k0 + k) * st.Nsrc + r];
+            if (st.n0 + r < st.Nsrc && st.k0 + k < st.Ksrc) v = w[st.src_off + (size_t)(st.k0 + k) * st.Nsrc + st.n0 + r];
             const float h = tc::tf32_hi(v);
             const int idx = (r >> 3) * (st.Kp >> 2) * 32 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3);
             out[st.w_off + idx] = h;
@@ -436,7 +478,7 @@ __global__ void tc_prepare_kernel(const float *__restrict__ w, float *__restrict
     }
 }
 
-static size_t tc_smem_bytes() { return (size_t)kActBytes + kWBytes + 3 * 64 * kTPitch * 4 + 64; }
+static size_t tc_smem_bytes() { return (size_t)kActBytes + kWBytes + 3 * 64 * kTPitch * 4 + kBiasFloats * 4 + 64; }
 
 int launch_policy_tc(const cm_policy_desc *desc, const cm_policy_io *io, cudaStream_t stream)
 {

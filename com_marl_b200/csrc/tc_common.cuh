@@ -56,6 +56,20 @@ __device__ __forceinline__ void fence_after_thread_sync() { asm volatile("tcgen0
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core / bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// one lane of a converged warp (warp-uniform code keeps descriptors in uniform registers; the elected lane issues)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
