@@ -31,7 +31,8 @@ struct EnvArgs {
     int mode;        // 0 step, 1 reset, 2 comm only
     int at_reset;    // comm-only: GE branch selector
     int n_pad, p_pad;
-    int warp_bytes;  // dynamic shared memory per warp
+    int warp_bytes;  // dynamic shared memory per environment group
+    int group;       // lanes per environment: 4, 8, 16 or 32
 };
 
 // per-warp scratch carved out of dynamic shared memory
@@ -122,6 +123,22 @@ __device__ __forceinline__ uint4 rng_block(const RngKey &k, uint32_t stream, uin
     return philox4x32_10(make_uint4(k.env, k.tick, stream | (k.episode << 8), index), k.key);
 }
 
+// A group of `gs` consecutive lanes (4, 8, 16 or 32) owns one environment: small teams pack several envs into a warp.
+// Groups of the same warp follow different control flow (different trip counts, resets), so every warp-level
+// primitive below is restricted to the group's own lanes.
+struct Grp {
+    int gs, gl;          // group size, lane index inside the group
+    unsigned mask;       // the group's lanes
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ int sum(int v) const
+    {
+        for (int o = gs >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+        return v;
+    }
+    __device__ __forceinline__ int any(int pred) const { return __any_sync(mask, pred); }
+    __device__ __forceinline__ int bcast0(int v) const { return __shfl_sync(mask, v, 0, gs); }
+};
+
 struct ChanSrc {
     const float *u;  // injected planes of this env, or nullptr
     RngKey key;
@@ -144,14 +161,14 @@ struct ChanSrc {
 // ------------------------------------------------------------------------------------------------
 // communication state: get_graph + channels (env_communication.py:91-157,200-243)
 // ------------------------------------------------------------------------------------------------
-__device__ void comm_update(const EnvArgs &A, const Scratch &S, int64_t b, int lane, const RngKey &key, bool at_reset)
+__device__ void comm_update(const EnvArgs &A, const Scratch &S, int64_t b, const Grp &G, const RngKey &key, bool at_reset)
 {
     const cm_env_desc &d = A.d;
     const int n = d.n_agents, L = d.n_layers, W = (n + 31) >> 5;
     // adjacency rows: dr^2 + dc^2 <= 2 Rcom^2 (== cdist <= sqrt(2 Rcom^2) on integer coordinates, :230);
     // Rcom == 0 means fully connected (:219-223)
     int deg = 0;
-    for (int item = lane; item < n * W; item += 32) {
+    for (int item = G.gl; item < n * W; item += G.gs) {
         const int i = item / W, w = item - i * W;
         uint32_t bits = 0;
         const int jn = min(32, n - w * 32);
@@ -168,9 +185,9 @@ __device__ void comm_update(const EnvArgs &A, const Scratch &S, int64_t b, int l
         if (A.io.adj_bits) A.io.adj_bits[(b * n + i) * W + w] = bits;
     }
     if (A.io.ave_deg) {
-        deg = warp_sum(deg);
+        deg = G.sum(deg);
         // float32 dist_adj.sum(axis=1).mean(axis=0) (:232); the fully connected branch returns n (:221)
-        if (lane == 0) A.io.ave_deg[b] = d.rcom2 < 0 ? (float)n : __fdiv_rn((float)deg, (float)n);
+        if (G.gl == 0) A.io.ave_deg[b] = d.rcom2 < 0 ? (float)n : __fdiv_rn((float)deg, (float)n);
     }
     if (!A.io.chan_bits && d.channel != CM_CH_GE) return;
     uint32_t *out = A.io.chan_bits ? A.io.chan_bits + (size_t)b * L * n * W : nullptr;
@@ -180,7 +197,7 @@ __device__ void comm_update(const EnvArgs &A, const Scratch &S, int64_t b, int l
     src.n = n;
     src.cached_idx = 0xFFFFFFFFu;
     if (d.channel == CM_CH_FC || d.channel == CM_CH_FL) {                    // :93-100
-        for (int item = lane; item < L * n * W; item += 32) {
+        for (int item = G.gl; item < L * n * W; item += G.gs) {
             const int w = item % W, i = (item / W) % n;
             const int jn = min(32, n - w * 32);
             uint32_t bits = jn == 32 ? 0xFFFFFFFFu : ((1u << jn) - 1u);
@@ -188,7 +205,7 @@ __device__ void comm_update(const EnvArgs &A, const Scratch &S, int64_t b, int l
             out[item] = bits;
         }
     } else if (d.channel == CM_CH_IID) {                                      // get_iid_channel :200-214
-        for (int item = lane; item < L * n * W; item += 32) {
+        for (int item = G.gl; item < L * n * W; item += G.gs) {
             const int w = item % W, i = (item / W) % n, l = item / (W * n);
             const int jn = min(32, n - w * 32);
             uint32_t bits = 0;
@@ -201,7 +218,7 @@ __device__ void comm_update(const EnvArgs &A, const Scratch &S, int64_t b, int l
         }
     } else {                                                                   // GE :106-157
         uint32_t *state = A.s.ge_state + (size_t)b * n * W;
-        for (int item = lane; item < n * W; item += 32) {
+        for (int item = G.gl; item < n * W; item += G.gs) {
             const int i = item / W, w = item - i * W;
             const int jn = min(32, n - w * 32);
             const uint32_t full = jn == 32 ? 0xFFFFFFFFu : ((1u << jn) - 1u);
@@ -253,35 +270,35 @@ __device__ void comm_update(const EnvArgs &A, const Scratch &S, int64_t b, int l
 // ------------------------------------------------------------------------------------------------
 // reset / spawn (predator_prey.py:150-171,206-232; coverage.py:172-196,221-246)
 // ------------------------------------------------------------------------------------------------
-__device__ void reset_env(const EnvArgs &A, const Scratch &S, const u64 *wall, int64_t b, int lane,
+__device__ void reset_env(const EnvArgs &A, const Scratch &S, const u64 *wall, int64_t b, const Grp &G,
                           RngKey &key, int &t, int &total_capture)
 {
     const cm_env_desc &d = A.d;
-    const int n = d.n_agents, p = d.n_preys, G = d.grid;
+    const int n = d.n_agents, p = d.n_preys, Gd = d.grid;
     const bool co = d.scenario == CM_COVERAGE;
-    for (int r = lane; r < G; r += 32) { S.occA[r] = 0ull; S.occB[r] = 0ull; }
-    __syncwarp();
+    for (int r = G.gl; r < Gd; r += G.gs) { S.occA[r] = 0ull; S.occB[r] = 0ull; }
+    G.sync();
     if (A.io.spawn_agent) {
         int ep = (int)key.episode;
         if (ep >= A.io.spawn_episodes) {          // queue exhausted: flag it, reuse the last entry
-            if (lane == 0 && A.io.error_flag) atomicExch(A.io.error_flag, (int)CM_EINVAL);
+            if (G.gl == 0 && A.io.error_flag) atomicExch(A.io.error_flag, (int)CM_EINVAL);
             ep = A.io.spawn_episodes - 1;
         }
-        for (int i = lane; i < n; i += 32) {
+        for (int i = G.gl; i < n; i += G.gs) {
             const uint16_t q = A.io.spawn_agent[((size_t)b * A.io.spawn_episodes + ep) * n + i];
             S.posA[i] = q;
             atomicOr(&S.occA[q & 0xFF], 1ull << (q >> 8));
             if (co) atomicOr(&S.occB[q & 0xFF], 1ull << (q >> 8));     // coverage.py:188 start cells are visited
         }
-        for (int j = lane; j < p; j += 32) {
+        for (int j = G.gl; j < p; j += G.gs) {
             const uint16_t q = A.io.spawn_prey[((size_t)b * A.io.spawn_episodes + ep) * p + j];
             S.posP[j] = q;
             S.alive[j] = 1;
             atomicOr(&S.occB[q & 0xFF], 1ull << (q >> 8));
         }
-    } else if (lane == 0) {
+    } else if (G.gl == 0) {
         // sequential rejection sampling on one lane; a reset happens once per episode, not per step
-        const int lo = co ? 1 : 0, span = co ? G - 2 : G;
+        const int lo = co ? 1 : 0, span = co ? Gd - 2 : Gd;
         uint32_t ctr = 0;
         uint4 blk = make_uint4(0, 0, 0, 0);
         auto draw = [&](int &r, int &c) {
@@ -307,14 +324,14 @@ __device__ void reset_env(const EnvArgs &A, const Scratch &S, const u64 *wall, i
             for (int tries = 0; tries <= (1 << 20); ++tries) {
                 draw(r, c);
                 // vacant and no agent in the 4-neighbourhood (predator_prey.py:166)
-                if (!(((S.occA[r] | S.occB[r]) >> c) & 1ull) && count4(S.occA, r, c, G) == 0) break;
+                if (!(((S.occA[r] | S.occB[r]) >> c) & 1ull) && count4(S.occA, r, c, Gd) == 0) break;
             }
             S.posP[j] = (uint16_t)(r | (c << 8));
             S.alive[j] = 1;
             S.occB[r] |= 1ull << c;
         }
     }
-    __syncwarp();
+    G.sync();
     t = 0;
     total_capture = 0;
     key.episode += 1;
@@ -323,33 +340,33 @@ __device__ void reset_env(const EnvArgs &A, const Scratch &S, const u64 *wall, i
 // ------------------------------------------------------------------------------------------------
 // observations (predator_prey.py:173-204; coverage.py:198-212,448-480)
 // ------------------------------------------------------------------------------------------------
-__device__ void write_obs(const EnvArgs &A, const Scratch &S, const u64 *wall, int64_t b, int lane, int t)
+__device__ void write_obs(const EnvArgs &A, const Scratch &S, const u64 *wall, int64_t b, const Grp &G, int t)
 {
     const cm_env_desc &d = A.d;
     if (!A.io.obs) return;
-    const int n = d.n_agents, G = d.grid, R = d.sensing, w = 2 * R + 1, ww = w * w;
+    const int n = d.n_agents, Gd = d.grid, R = d.sensing, w = 2 * R + 1, ww = w * w;
     const bool co = d.scenario == CM_COVERAGE;
     const int nwin = co ? 3 : 2, D = nwin * ww + (co ? 2 : 3);
     // window bits of every agent, lane-parallel
-    for (int i = lane; i < n; i += 32) {
+    for (int i = G.gl; i < n; i += G.gs) {
         const int r = S.posA[i] & 0xFF, c = S.posA[i] >> 8;
         if (co) {
-            S.win[0 * A.n_pad + i] = window_bits(wall, r, c, R, G, 1);     // wall channel, out-of-grid = wall (:464-466)
-            S.win[1 * A.n_pad + i] = window_bits(S.occA, r, c, R, G, 0);   // agents, self included
-            S.win[2 * A.n_pad + i] = window_bits(S.occB, r, c, R, G, 0);   // visited
+            S.win[0 * A.n_pad + i] = window_bits(wall, r, c, R, Gd, 1);     // wall channel, out-of-grid = wall (:464-466)
+            S.win[1 * A.n_pad + i] = window_bits(S.occA, r, c, R, Gd, 0);   // agents, self included
+            S.win[2 * A.n_pad + i] = window_bits(S.occB, r, c, R, Gd, 0);   // visited
         } else {
-            S.win[0 * A.n_pad + i] = window_bits(S.occA, r, c, R, G, 0);   // agents, self included
-            S.win[1 * A.n_pad + i] = window_bits(S.occB, r, c, R, G, 0);   // preys
+            S.win[0 * A.n_pad + i] = window_bits(S.occA, r, c, R, Gd, 0);   // agents, self included
+            S.win[1 * A.n_pad + i] = window_bits(S.occB, r, c, R, Gd, 0);   // preys
         }
     }
-    __syncwarp();
-    const float *lut_row = d.lut, *lut_col = d.lut + G, *lut_t = d.lut + 2 * G;
+    G.sync();
+    const float *lut_row = d.lut, *lut_col = d.lut + Gd, *lut_t = d.lut + 2 * Gd;
     float *out = A.io.obs + (size_t)b * n * D;
     // the env's [n][D] block is contiguous: consecutive lanes store consecutive floats
     for (int i = 0; i < n; ++i) {
         const uint32_t w0 = S.win[i], w1 = S.win[A.n_pad + i], w2 = co ? S.win[2 * A.n_pad + i] : 0u;
         const int r = S.posA[i] & 0xFF, c = S.posA[i] >> 8;
-        for (int e = lane; e < D; e += 32) {
+        for (int e = G.gl; e < D; e += G.gs) {
             float v;
             if (e < ww) v = (float)((w0 >> e) & 1u);
             else if (e < 2 * ww) v = (float)((w1 >> (e - ww)) & 1u);
@@ -371,18 +388,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
     extern __shared__ __align__(16) unsigned char smem[];
     const cm_env_desc &d = A.d;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n = d.n_agents, p = d.n_preys, G = d.grid;
+    Grp G;
+    G.gs = A.group;
+    G.gl = lane & (A.group - 1);
+    G.mask = A.group == 32 ? 0xFFFFFFFFu : (((1u << A.group) - 1u) << (lane - G.gl));
+    const int epw = 32 / A.group, grp = lane / A.group;          // envs per warp, this lane's group
+    const int n = d.n_agents, p = d.n_preys, Gd = d.grid;
     const bool co = d.scenario == CM_COVERAGE;
-    u64 *wall = reinterpret_cast<u64 *>(smem);               // [G] shared by the CTA (Coverage)
+    u64 *wall = reinterpret_cast<u64 *>(smem);               // [Gd] shared by the CTA (Coverage)
     if (co) {
-        for (int r = threadIdx.x; r < G; r += blockDim.x) wall[r] = d.wall_rows[r];
+        for (int r = threadIdx.x; r < Gd; r += blockDim.x) wall[r] = d.wall_rows[r];
     }
     __syncthreads();
-    const Scratch S = carve(smem + 64 * 8 + (size_t)warp * A.warp_bytes, A.n_pad, A.p_pad, G);
-    const int64_t total_warps = (int64_t)gridDim.x * kWarpsPerCta;
-    for (int64_t b = (int64_t)blockIdx.x * kWarpsPerCta + warp; b < A.s.n_envs; b += total_warps) {
+    const Scratch S = carve(smem + 64 * 8 + (size_t)(warp * epw + grp) * A.warp_bytes, A.n_pad, A.p_pad, Gd);
+    const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta * epw;
+    for (int64_t b = ((int64_t)blockIdx.x * kWarpsPerCta + warp) * epw + grp; b < A.s.n_envs; b += stride) {
         if (A.mode == 1 && A.mask && !A.mask[b]) continue;
-        __syncwarp();
+        G.sync();
         RngKey key;
         key.env = (uint32_t)(d.env_id0 + b);
         key.key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
@@ -393,18 +415,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
         bool did_reset = false;
 
         if (A.mode == 1) {
-            reset_env(A, S, wall, b, lane, key, t, total_capture);
+            reset_env(A, S, wall, b, G, key, t, total_capture);
             did_reset = true;
         } else {
             // ---- stage the env in shared memory and rebuild the row bitmaps from the positions ----
-            for (int r = lane; r < G; r += 32) { S.occA[r] = 0ull; S.occB[r] = co ? A.s.visited[b * G + r] : 0ull; }
-            for (int i = lane; i < n; i += 32) S.posA[i] = A.s.agent_pos[b * n + i];
-            for (int j = lane; j < p; j += 32) { S.posP[j] = A.s.prey_pos[b * p + j]; S.alive[j] = A.s.prey_alive[b * p + j]; }
-            __syncwarp();
-            for (int i = lane; i < n; i += 32) atomicOr(&S.occA[S.posA[i] & 0xFF], 1ull << (S.posA[i] >> 8));
-            for (int j = lane; j < p; j += 32)
+            for (int r = G.gl; r < Gd; r += G.gs) { S.occA[r] = 0ull; S.occB[r] = co ? A.s.visited[b * Gd + r] : 0ull; }
+            for (int i = G.gl; i < n; i += G.gs) S.posA[i] = A.s.agent_pos[b * n + i];
+            for (int j = G.gl; j < p; j += G.gs) { S.posP[j] = A.s.prey_pos[b * p + j]; S.alive[j] = A.s.prey_alive[b * p + j]; }
+            G.sync();
+            for (int i = G.gl; i < n; i += G.gs) atomicOr(&S.occA[S.posA[i] & 0xFF], 1ull << (S.posA[i] >> 8));
+            for (int j = G.gl; j < p; j += G.gs)
                 if (S.alive[j]) atomicOr(&S.occB[S.posP[j] & 0xFF], 1ull << (S.posP[j] >> 8));
-            __syncwarp();
+            G.sync();
         }
 
         if (A.mode == 0) {
@@ -412,44 +434,44 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
             t += 1;
             key.tick += 1;                        // every draw of this step is keyed with the new tick
             int moved = 0, bad = 0;
-            for (int i = lane; i < n; i += 32) {
+            for (int i = G.gl; i < n; i += G.gs) {
                 int a = A.io.actions[b * n + i];
                 if (a < 0 || a > 4) { bad = 1; a = 4; }
                 S.act[i] = (int8_t)a;
                 moved += (a != 4);
             }
-            moved = warp_sum(moved);
-            if (__any_sync(0xFFFFFFFFu, bad) && lane == 0 && A.io.error_flag) atomicExch(A.io.error_flag, (int)CM_EACTION);
-            __syncwarp();
+            moved = G.sum(moved);
+            if (G.any(bad) && G.gl == 0 && A.io.error_flag) atomicExch(A.io.error_flag, (int)CM_EACTION);
+            G.sync();
             int c0 = 0, c2 = 0, c3 = 0, c4 = 0;   // counts (see commarl_b200.h)
             double reward = 0.0;
             int env_done = 0;
             uint8_t success = A.s.success[b];
             if (!co) {
                 // ---- agents move one after another, lower index first (predator_prey.py:497-500,240-261) ----
-                if (lane == 0) {
+                if (G.gl == 0) {
                     for (int i = 0; i < n; ++i) {
                         const int a = S.act[i];
                         if (a == 4) continue;
                         const int r = S.posA[i] & 0xFF, c = S.posA[i] >> 8;
                         const int nr = r + d_row(a), nc = c + d_col(a);
-                        if (nr < 0 || nr >= G || nc < 0 || nc >= G) continue;
+                        if (nr < 0 || nr >= Gd || nc < 0 || nc >= Gd) continue;
                         if (((S.occA[nr] | S.occB[nr]) >> nc) & 1ull) continue;
                         S.occA[r] &= ~(1ull << c);
                         S.occA[nr] |= 1ull << nc;
                         S.posA[i] = (uint16_t)(nr | (nc << 8));
                     }
                 }
-                __syncwarp();
+                G.sync();
                 // ---- order-independent part of the prey loop, lane-parallel ----
                 // Agents stand still while preys are processed, and prey j's own position / alive flag only
                 // change in its own turn, so: the agent count around prey j (:419/:462), the screening of its
                 // <= 5 move candidates against agent neighbourhoods (:400-404) and the prey_watching flags
                 // (:421-422) do not depend on the processing order.
-                for (int j = lane; j < p; j += 32) {
+                for (int j = G.gl; j < p; j += G.gs) {
                     if (!S.alive[j]) continue;
                     const int r = S.posP[j] & 0xFF, c = S.posP[j] >> 8;
-                    S.kcnt[j] = (uint8_t)count4(S.occA, r, c, G);
+                    S.kcnt[j] = (uint8_t)count4(S.occA, r, c, Gd);
                     uint32_t words[5];
                     if (!A.io.prey_cand) {
                         const uint4 q0 = rng_block(key, kStreamPrey, 2 * j), q1 = rng_block(key, kStreamPrey, 2 * j + 1);
@@ -459,17 +481,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
                     for (int tr = 0; tr < 5; ++tr) {
                         const int cnd = A.io.prey_cand ? (int)A.io.prey_cand[((size_t)b * p + j) * 5 + tr]
                                                        : prey_move_from_bits(words[tr]);
-                        if (count4(S.occA, r + d_row(cnd), c + d_col(cnd), G) == 0) { mv = cnd; break; }
+                        if (count4(S.occA, r + d_row(cnd), c + d_col(cnd), Gd) == 0) { mv = cnd; break; }
                     }
                     S.mv[j] = (int8_t)mv;
                 }
                 int watching = 0;
-                for (int i = lane; i < n; i += 32)
-                    watching += count4(S.occB, S.posA[i] & 0xFF, S.posA[i] >> 8, G) > 0;
-                c3 = warp_sum(watching);
-                __syncwarp();
+                for (int i = G.gl; i < n; i += G.gs)
+                    watching += count4(S.occB, S.posA[i] & 0xFF, S.posA[i] >> 8, Gd) > 0;
+                c3 = G.sum(watching);
+                G.sync();
                 // ---- order-dependent part: capture test against the preys still standing, then the walk ----
-                if (lane == 0) {
+                if (G.gl == 0) {
                     int capture = 0, penalty = 0;
                     for (int j = 0; j < p; ++j) {
                         if (!S.alive[j]) continue;
@@ -478,9 +500,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
                         if (k >= 1) {
                             int need = d.load;
                             if (d.load != 2) {   // reward_individual :469-470; edges dict :123-144 (corner 2, border 3, else load)
-                                const int re = (r == 0 || r == G - 1), ce = (c == 0 || c == G - 1);
+                                const int re = (r == 0 || r == Gd - 1), ce = (c == 0 || c == Gd - 1);
                                 const int nadj = (re && ce) ? 2 : ((re || ce) ? 3 : d.load);
-                                need = min(d.load, nadj - count4(S.occB, r, c, G));
+                                need = min(d.load, nadj - count4(S.occB, r, c, Gd));
                             }
                             if (need <= k) {     // captured: leaves the grid at once (:301)
                                 ++capture;
@@ -493,7 +515,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
                         const int mv = S.mv[j];
                         if (mv != 4) {           // __update_prey_pos :276-299
                             const int nr = r + d_row(mv), nc = c + d_col(mv);
-                            if (nr >= 0 && nr < G && nc >= 0 && nc < G && !(((S.occA[nr] | S.occB[nr]) >> nc) & 1ull)) {
+                            if (nr >= 0 && nr < Gd && nc >= 0 && nc < Gd && !(((S.occA[nr] | S.occB[nr]) >> nc) & 1ull)) {
                                 S.occB[r] &= ~(1ull << c);
                                 S.occB[nr] |= 1ull << nc;
                                 S.posP[j] = (uint16_t)(nr | (nc << 8));
@@ -507,27 +529,27 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
                                        __ddiv_rn(__dmul_rn(d.moving_cost, (double)moved), (double)n));
                     if (d.load == 2) reward = __dadd_rn(reward, __dmul_rn(d.penalty, (double)penalty));
                 }
-                __syncwarp();
+                G.sync();
                 int any_alive = 0;
-                for (int j = lane; j < p; j += 32) {
+                for (int j = G.gl; j < p; j += G.gs) {
                     any_alive |= S.alive[j];
                     if (A.io.prey_alive_out) A.io.prey_alive_out[b * p + j] = S.alive[j];
                 }
-                any_alive = __any_sync(0xFFFFFFFFu, any_alive);
+                any_alive = G.any(any_alive);
                 if (t >= d.max_steps || !any_alive) {            // :511-517
                     success = any_alive ? 0 : 1;
                     env_done = 1;
                 }
             } else {
                 // ---- Coverage.step (coverage.py:319-401): sequential moves over wall | agent rows ----
-                if (lane == 0) {
+                if (G.gl == 0) {
                     int cap = 0, pen = 0, rev = 0;
                     for (int i = 0; i < n; ++i) {
                         const int a = S.act[i];
                         if (a == 4) continue;                    // lazy, counted below
                         const int r = S.posA[i] & 0xFF, c = S.posA[i] >> 8;
                         const int nr = r + d_row(a), nc = c + d_col(a);
-                        if (nr < 0 || nr >= G || nc < 0 || nc >= G || (((S.occA[nr] | wall[nr]) >> nc) & 1ull)) { ++pen; continue; }
+                        if (nr < 0 || nr >= Gd || nc < 0 || nc >= Gd || (((S.occA[nr] | wall[nr]) >> nc) & 1ull)) { ++pen; continue; }
                         if ((S.occB[nr] >> nc) & 1ull) ++rev;
                         else { S.occB[nr] |= 1ull << nc; ++cap; }
                         S.occA[r] &= ~(1ull << c);
@@ -548,14 +570,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
                     reward = __dadd_rn(reward, __dmul_rn(d.revisit_penalty, __ddiv_rn((double)rev, dn)));
                     reward = __dadd_rn(reward, final_reward);
                 }
-                __syncwarp();
-                env_done = __shfl_sync(0xFFFFFFFFu, env_done, 0);
-                total_capture = __shfl_sync(0xFFFFFFFFu, total_capture, 0);
-                success = (uint8_t)__shfl_sync(0xFFFFFFFFu, (int)success, 0);
+                G.sync();
+                env_done = G.bcast0(env_done);
+                total_capture = G.bcast0(total_capture);
+                success = (uint8_t)G.bcast0((int)success);
             }
             int done = env_done;
             if (d.max_path_length > 0 && t >= d.max_path_length) done = 1;   // vec_env_executor.py:33-35
-            if (lane == 0) {
+            if (G.gl == 0) {
                 if (A.io.reward) A.io.reward[b] = reward;
                 if (A.io.done) A.io.done[b] = (uint8_t)done;
                 if (A.io.counts) {
@@ -577,25 +599,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
                 }
             }
             if (done && A.io.auto_reset) {        // vec_env_executor.py:36-43
-                reset_env(A, S, wall, b, lane, key, t, total_capture);
+                reset_env(A, S, wall, b, G, key, t, total_capture);
                 did_reset = true;
             }
         }
 
         if (A.mode != 2) {
             // ---- write the state back ----
-            for (int i = lane; i < n; i += 32) A.s.agent_pos[b * n + i] = S.posA[i];
-            for (int j = lane; j < p; j += 32) { A.s.prey_pos[b * p + j] = S.posP[j]; A.s.prey_alive[b * p + j] = S.alive[j]; }
-            if (co) for (int r = lane; r < G; r += 32) A.s.visited[b * G + r] = S.occB[r];
-            if (lane == 0) {
+            for (int i = G.gl; i < n; i += G.gs) A.s.agent_pos[b * n + i] = S.posA[i];
+            for (int j = G.gl; j < p; j += G.gs) { A.s.prey_pos[b * p + j] = S.posP[j]; A.s.prey_alive[b * p + j] = S.alive[j]; }
+            if (co) for (int r = G.gl; r < Gd; r += G.gs) A.s.visited[b * Gd + r] = S.occB[r];
+            if (G.gl == 0) {
                 A.s.step_count[b] = t;
                 A.s.tick[b] = key.tick;
                 A.s.episode[b] = key.episode;
                 if (co) A.s.total_capture[b] = total_capture;
             }
-            write_obs(A, S, wall, b, lane, t);
+            write_obs(A, S, wall, b, G, t);
         }
-        comm_update(A, S, b, lane, key, A.mode == 2 ? (A.at_reset != 0) : did_reset);
+        comm_update(A, S, b, G, key, A.mode == 2 ? (A.at_reset != 0) : did_reset);
     }
 }
 
@@ -640,7 +662,10 @@ static int launch(const cm_env_desc *d, const cm_env_state *s, const cm_step_io 
     A.n_pad = (d->n_agents + 7) & ~7;
     A.p_pad = (d->n_preys + 7) & ~7;
     A.warp_bytes = (env_warp_bytes(A.n_pad, A.p_pad, d->grid) + 15) & ~15;
-    const size_t smem = 64 * 8 + (size_t)kWarpsPerCta * A.warp_bytes;
+    const int team = d->n_agents > d->n_preys ? d->n_agents : d->n_preys;
+    A.group = team <= 4 ? 4 : (team <= 8 ? 8 : (team <= 16 ? 16 : 32));
+    const int envs_per_cta = kWarpsPerCta * (32 / A.group);
+    const size_t smem = 64 * 8 + (size_t)envs_per_cta * A.warp_bytes;
     // launch geometry is cached per (device, smem) so that steady-state calls issue nothing but the launch
     // (keeps the call CUDA-graph capturable)
     static thread_local struct { int dev; size_t smem; int ctas_per_sm; int sms; } cache = {-1, 0, 0, 0};
@@ -658,7 +683,7 @@ static int launch(const cm_env_desc *d, const cm_env_state *s, const cm_step_io 
         cache.dev = dev; cache.smem = smem; cache.ctas_per_sm = ctas < 1 ? 1 : ctas; cache.sms = sms;
     }
     // persistent grid: a whole number of CTAs per SM, warps stride over the envs
-    int64_t want = (s->n_envs + kWarpsPerCta - 1) / kWarpsPerCta;
+    int64_t want = (s->n_envs + envs_per_cta - 1) / envs_per_cta;
     int64_t cap = (int64_t)cache.sms * cache.ctas_per_sm;
     int grid = (int)(want < cap ? want : cap);
     env_kernel<<<grid, kWarpsPerCta * 32, smem, stream>>>(A);
