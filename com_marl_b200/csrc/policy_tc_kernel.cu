@@ -261,13 +261,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
             const int Kp = P.st[si].Kp, kofs = 64 * pnl;
             const float *src = io.obs + row0 * D;
             const uint32_t lo_off = (uint32_t)kTcRows * Kp * 4;
-            for (int e = tid; e < kTcRows * Kp; e += kTcThreads) {
+            // all global loads first (independent, 128 * Kp / 512 <= 16 per thread), then the split + stores
+            float ov[16];
+            const int total = kTcRows * Kp;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int e = tid + q * kTcThreads;
                 const int r = e / Kp, k = e - r * Kp;
-                const float v = (r < rows && kofs + k < D) ? __ldg(src + (size_t)r * D + kofs + k) : 0.0f;
-                const float h = tf32_hi(v);
-                const uint32_t off = canon_off(r, k, Kp);
-                *reinterpret_cast<float *>(ACT + off) = h;
-                *reinterpret_cast<float *>(ACT + lo_off + off) = tf32_lo(v, h);
+                ov[q] = (e < total && r < rows && kofs + k < D) ? __ldg(src + (size_t)r * D + kofs + k) : 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int e = tid + q * kTcThreads;
+                if (e < total) {
+                    const int r = e / Kp, k = e - r * Kp;
+                    const float h = tf32_hi(ov[q]);
+                    const uint32_t off = canon_off(r, k, Kp);
+                    *reinterpret_cast<float *>(ACT + off) = h;
+                    *reinterpret_cast<float *>(ACT + lo_off + off) = tf32_lo(ov[q], h);
+                }
             }
             if (pnl == 0 && P.l1_split) run_mma(2, MmaOp{DA, 0u}, MmaOp{DA + 64, 0u});
             else run_mma(1, MmaOp{DA, (uint32_t)pnl}, none);
