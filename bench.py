@@ -325,6 +325,11 @@ def run_b200_arm(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.config, {}) if B == CONFIGS[args.config][6] else {}
+    except Exception:
+        pass
     flops = policy_flops_per_agent(Dobs, n, L) * B * n
     env_bytes = env_bytes_per_agent_step(spec) * B * n
     tc = pol.uses_tensor_cores()
@@ -353,11 +358,11 @@ def run_b200_arm(args):
                 "steps": e2e_steps, "api": "policy.get_actions_host + BatchedEnv.step_host (pinned host buffers, per-step sync)"},
         "gpu_launches": launches * world,
         "roofline": {"bound": "tensor", "kernel": kname,
-                     "achieved": pol_tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": pol_tflops / tc_peak, "traffic": None,
+                     "achieved": pol_tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": pol_tflops / tc_peak, "traffic": traffic.get(kname),
                      "peak_source": peak_src + ", bf16 dense sustained; " + kdesc,
                      "flop_per_launch": flops, "tensor_flop_issued_per_launch": tc_flops, "ms_per_launch": pol_ms, "share_of_step": pol_ms / (pol_ms + env_ms)},
         "roofline_env": {"bound": "hbm", "kernel": "env_kernel", "achieved": env_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": env_gbs / hbm_peak, "traffic": None, "bytes_per_launch": env_bytes, "ms_per_launch": env_ms,
+                         "frac": env_gbs / hbm_peak, "traffic": traffic.get("env_kernel"), "bytes_per_launch": env_bytes, "ms_per_launch": env_ms,
                          "bytes_per_agent_step": env_bytes_per_agent_step(spec), "peak_source": peak_src},
         "clocks": clock_info,
         "episode_stats": D.summarize_stats(stats, spec.scenario, n),
