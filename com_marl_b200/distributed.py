@@ -65,3 +65,24 @@ def summarize_stats(per_rank: torch.Tensor, scenario: str, n_agents: int) -> Dic
                    AveragePenaltyCount=s["c2_sum"] / n / ep, AverageVariable=s["c3_sum"] / n / ep,
                    AverageVar2=s["c4_sum"] / n / ep)
     return out
+
+
+def allreduce_gradients(module: torch.nn.Module, group=None) -> int:
+    """Data-parallel gradient averaging for the PPO update of BASELINE config 5: ONE all-reduce over
+    a flattened fp32 bucket of every parameter gradient (policy 46 405 + critic ~32 k floats = ~313 KB, latency bound on
+    NVLink), then divide by the world size.  Returns the number of floats reduced.  A no-op without a process group.
+    The reference computes `loss.backward()` in a single process (centralized_ma_ppo.py:243,251); with envs sharded
+    over GPUs each rank back-propagates its own slice and calls this before `optimizer.step()`."""
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if not grads:
+        return 0
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return sum(g.numel() for g in grads)
+    flat = torch.cat([g.reshape(-1).float() for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    return off

@@ -160,13 +160,18 @@ class BatchedEnv:
         """VecEnvExecutor.step with HOST buffers: numpy actions in, numpy (views of pinned buffers) out.
         Copies: H2D actions; D2H obs, reward, done, counts, adj/chan bit rows, ave_deg, prey_alive, success."""
         pin = self._pinned()
-        pin["actions"].numpy()[...] = np.asarray(actions, dtype=np.int8).reshape(self.B, self.n)
-        self._act_dev.copy_(pin["actions"], non_blocking=True)
+        if isinstance(actions, torch.Tensor) and actions.is_pinned() and actions.dtype == torch.int8:
+            self._act_dev.copy_(actions.view(self.B, self.n), non_blocking=True)     # already pinned: no staging copy
+        else:
+            pin["actions"].numpy()[...] = np.asarray(actions, dtype=np.int8).reshape(self.B, self.n)
+            self._act_dev.copy_(pin["actions"], non_blocking=True)
         self.step(self._act_dev)
         for k in ("obs", "reward", "done", "counts", "adj_bits", "chan_bits", "ave_deg", "prey_alive_out", "success"):
             pin[k].copy_(getattr(self, k), non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return {k: v.numpy() for k, v in pin.items() if k != "actions"}
+        out = {k: v.numpy() for k, v in pin.items() if k != "actions"}
+        out["pinned"] = pin            # the same buffers as torch pinned tensors (zero-copy hand-over to the policy)
+        return out
 
     def reset_host(self):
         pin = self._pinned()
@@ -174,7 +179,9 @@ class BatchedEnv:
         for k in ("obs", "adj_bits", "chan_bits", "ave_deg"):
             pin[k].copy_(getattr(self, k), non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return {k: pin[k].numpy() for k in ("obs", "adj_bits", "chan_bits", "ave_deg")}
+        out = {k: pin[k].numpy() for k in ("obs", "adj_bits", "chan_bits", "ave_deg")}
+        out["pinned"] = pin
+        return out
 
     def host_step_bytes(self):
         """(h2d, d2h) bytes moved by one step_host call"""

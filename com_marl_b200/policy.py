@@ -234,10 +234,11 @@ class CommCategoricalMLPPolicy(nn.Module):
 
     _host_calls = 0
 
-    def get_actions_host(self, obs, adj_bits, chan_bits, greedy=False):
+    def get_actions_host(self, obs, adj_bits, chan_bits, greedy=False, return_pinned=False):
         """Batched rollout call with HOST buffers and bit-row masks (what BatchedEnv.step_host returns): numpy obs
         (B, n, D) / (B, n*D), int32 bit rows in; numpy actions (B, n) int8 and probs (B, n, 5) out.  Pinned staging
-        buffers are allocated once.  Copies: H2D obs + masks; D2H actions + probs."""
+        buffers are allocated once; inputs that already are pinned torch tensors (e.g. ``step_host(...)["pinned"]``) are
+        copied to the device directly.  Copies: H2D obs + masks; D2H actions + probs."""
         n, D, L, dev = self._n_agents, self._dec_obs_dim, self.n_gcn_layers, self.device
         B = obs.shape[0]
         st = getattr(self, "_stage", None)
@@ -250,8 +251,11 @@ class CommCategoricalMLPPolicy(nn.Module):
             self._stage = st
         for k, src in (("obs", obs), ("adj", adj_bits), ("chan", chan_bits)):
             h, d = st[k]
-            h.numpy()[...] = np.asarray(src).reshape(h.shape)
-            d.copy_(h, non_blocking=True)
+            if isinstance(src, torch.Tensor) and src.is_pinned() and src.dtype == h.dtype:
+                d.copy_(src.view(h.shape), non_blocking=True)      # caller's buffer is already pinned: no staging copy
+            else:
+                h.numpy()[...] = np.asarray(src).reshape(h.shape)
+                d.copy_(h, non_blocking=True)
         st["tick"].fill_(self._host_calls & 0x7FFFFFFF)
         self._host_calls += 1
         self.act_device(st["obs"][1], st["adj"][1], st["chan"][1], tick=st["tick"], episode=st["episode"], greedy=greedy,
@@ -259,6 +263,8 @@ class CommCategoricalMLPPolicy(nn.Module):
         st["probs"][0].copy_(st["probs"][1], non_blocking=True)
         st["actions"][0].copy_(st["actions"][1], non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
+        if return_pinned:
+            return st["actions"][0], st["probs"][0]
         return st["actions"][0].numpy(), st["probs"][0].numpy()
 
     def host_call_bytes(self, B):

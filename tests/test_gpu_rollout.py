@@ -111,3 +111,31 @@ def test_sampler_paths_contract():
     short = sampler.obtain_samples(1, batch_size=50 * n, whole_paths=False)
     assert sum(len(pth["rewards"]) for pth in short) * n <= 50 * n + n * 20
     sampler.shutdown_worker()
+
+
+def test_host_buffer_api_equals_device_path():
+    """BatchedEnv.step_host / policy.get_actions_host (the e2e path: pinned host buffers, H2D + D2H every step)
+    produce the same trajectory as the device-resident calls."""
+    from com_marl_b200.envs import BatchedEnv
+    from com_marl_b200.rollout import make_policy
+    params, spec = _mk("pp", 10, 1, 0.08, 2, 0.3, {"max_env_steps": 15})
+    pol = make_policy(spec)
+    B, n = 200, spec.n_agents
+    host, devc = BatchedEnv(spec, B), BatchedEnv(spec, B)
+    out = host.reset_host()
+    devc.reset()
+    probs = torch.empty((B, n, 5), device="cuda")
+    actions = torch.empty((B, n), dtype=torch.int8, device="cuda")
+    tick = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    h2d, d2h = host.host_step_bytes()
+    assert h2d == B * n and d2h > B * n * spec.obs_dim * 4
+    for s in range(40):
+        acts_np, probs_np = pol.get_actions_host(out["obs"], out["adj_bits"], out["chan_bits"])
+        tick.fill_(pol._host_calls - 1)
+        pol.act_device(devc.obs, devc.adj_bits, devc.chan_bits, tick=tick, episode=torch.zeros_like(tick), probs=probs, actions=actions)
+        assert np.array_equal(acts_np, actions.cpu().numpy()) and np.array_equal(probs_np, probs.cpu().numpy())
+        out = host.step_host(acts_np if s % 2 else out["pinned"] and torch.from_numpy(acts_np.copy()).pin_memory())
+        devc.step(actions)
+        assert np.array_equal(out["obs"], devc.obs.cpu().numpy())
+        assert np.array_equal(out["reward"], devc.reward.cpu().numpy()) and np.array_equal(out["done"], devc.done.cpu().numpy())
+        assert np.array_equal(out["chan_bits"], devc.chan_bits.cpu().numpy())

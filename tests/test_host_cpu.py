@@ -122,7 +122,13 @@ def _gloo_worker(rank, world, port, q):
     lo, hi = D.shard_range(1001, r, w)
     local = torch.tensor([hi - lo, 10.0 * (r + 1), 3, 1, 0, 0, 0, 0, 0], dtype=torch.float64)
     out = D.gather_stats(local)
-    q.put((r, out.tolist()))
+    # gradient bucket all-reduce (config 5's PPO data parallelism): rank r holds gradient r+1 everywhere
+    lin = torch.nn.Linear(4, 3)
+    for p in lin.parameters():
+        p.grad = torch.full_like(p, float(r + 1))
+    nfl = D.allreduce_gradients(lin)
+    gmean = [float(p.grad.mean()) for p in lin.parameters()]
+    q.put((r, (out.tolist(), nfl, gmean)))
     torch.distributed.destroy_process_group()
 
 
@@ -140,7 +146,9 @@ def test_stats_all_gather_world_size_2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res[0] == res[1]
-    assert [row[0] for row in res[0]] == [501.0, 500.0] and [row[1] for row in res[0]] == [10.0, 20.0]
+    stats, nfl, gmean = res[0]
+    assert [row[0] for row in stats] == [501.0, 500.0] and [row[1] for row in stats] == [10.0, 20.0]
+    assert nfl == 15 and gmean == [1.5, 1.5]
 
 
 def test_truncate_paths():
