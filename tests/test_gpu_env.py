@@ -125,6 +125,10 @@ GENERATED = [
     ("ge_prop", "co", 20, 1, 0.03, 2, 0.2, 512, 100, {"max_env_steps": 45}, dict(Pgb=0.0196, Pbg=0.282, GE_INIT=-1, loss_apply=1)),
     ("ge_l0", "pp", 10, 1, 0.08, 2, 0.2, 512, 90, {"max_env_steps": 40}, dict(Pgb=0.2, Pbg=0.3, GE_INIT=0, loss_apply=0)),
     ("hard", "co", 10, 2, 0.06, 2, 1.0, 1024, 120, {"obstComplex": "Hard", "trRcom": 3, "max_env_steps": 50}, None),
+    # maximum sizes: 256 agents + 256 preys on a 64 x 64 grid (full-width 64-bit rows); Coverage map 60 (grid 62), 216 agents
+    ("max_pp", "pp", 64, 2, 0.08, 4, 0.1, 6, 26, {"n_agents": 256, "n_preys": 256, "max_env_steps": 12}, None),
+    ("max_co", "co", 60, 2, 0.06, 2, 0.1, 6, 26, {"max_env_steps": 12}, None),
+    ("tiny", "pp", 10, 0, 0.01, 2, 0.0, 300, 30, {"n_agents": 1, "n_preys": 1, "max_env_steps": 10}, None),
 ]
 
 
