@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcommarl_b200.so")
+LIB_PATH = os.environ.get("COM_MARL_B200_LIB") or os.path.join(_HERE, "lib", "libcommarl_b200.so")
 
 CM_OK, CM_EINVAL, CM_EUNSUPPORTED, CM_ECUDA, CM_ENODEVICE, CM_EACTION = 0, -1, -2, -3, -4, -5
 PREDATOR_PREY, COVERAGE = 0, 1

@@ -24,6 +24,10 @@
 #include "policy_layout.cuh"
 #include "tc_common.cuh"
 
+#ifndef CM_TC_DEBUG
+#define CM_TC_DEBUG 0   // timing experiments only: 1 skip MMAs, 2 skip tanh, 4 skip attention loops, 8 skip weight copies
+#endif
+
 namespace cm {
 
 using namespace tc;
@@ -74,6 +78,7 @@ __device__ __forceinline__ void write_act(unsigned char *act, int Kp, int row, i
 // of magnitude below what the 3xTF32 products contribute and ~4x fewer instructions than tanhf.
 __device__ __forceinline__ float tanh_fast(float x)
 {
+    if (CM_TC_DEBUG & 2) return x;
     const float e = __expf(2.0f * x);
     return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
@@ -93,7 +98,7 @@ __device__ __forceinline__ void issue_layer(uint32_t d_tmem, const unsigned char
         uint64_t da = make_smem_desc((p == 1) ? a_lo : a_hi, Kp, 0), db = make_smem_desc((p == 2) ? b_lo : b_hi, Kp, 0);
 #pragma unroll 2
         for (int j = 0; j < nk; ++j) {
-            if (elect_one()) mma_tf32(d_tmem, da, db, idesc, acc);
+            if (!(CM_TC_DEBUG & 1) && elect_one()) mma_tf32(d_tmem, da, db, idesc, acc);
             acc = 1;
             da += 16;     // next K = 8 slice: start address + 256 bytes (>> 4)
             db += 16;
@@ -112,7 +117,7 @@ __device__ __forceinline__ void scores_softmax(float *QT, const float *ET, float
     const int nk = valid ? (n - sub + 3) / 4 : 0;
 #pragma unroll
     for (int t = 0; t < KT; ++t) sc[t] = 0.0f;
-    if (nk > 0) {
+    if (nk > 0 && !(CM_TC_DEBUG & 4)) {
 #pragma unroll 4
         for (int k = 0; k < 64; ++k) {
             const float qv = QT[k * kTPitch + row];
@@ -208,8 +213,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
                 const TcStage &st = P.st[issued_si];
                 const uint32_t bytes = (uint32_t)(2 * st.N * st.Kp * 4), slot = issued & 1u;
                 if (elect_one()) {
-                    mbar_expect_tx(&bars[slot], bytes);
-                    bulk_g2s(WB + slot * 32768u, tcw + st.w_off, bytes, &bars[slot]);
+                    if (CM_TC_DEBUG & 8) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[slot])) : "memory"); }
+                    else {
+                        mbar_expect_tx(&bars[slot], bytes);
+                        bulk_g2s(WB + slot * 32768u, tcw + st.w_off, bytes, &bars[slot]);
+                    }
                 }
                 __syncwarp();
                 ++issued;
@@ -222,9 +230,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
     // all threads: ACT is written -> thread 0 issues one product per op, each against the next weight block ->
     // everybody waits for their completion -> the freed ring slots are refilled
     auto run_mma = [&](int nops, MmaOp op0, MmaOp op1) {
+#ifdef CM_TC_TRACE
+        long long tr0 = clock64(), tr1, tr2 = 0, tr3;
+#endif
         fence_proxy_async();
         fence_before_thread_sync();
         __syncthreads();
+#ifdef CM_TC_TRACE
+        tr1 = clock64();
+#endif
         if (warp == 0) {                 // whole warp, converged: waits for the weights, elected lane issues
             fence_after_thread_sync();
             for (int i = 0; i < nops; ++i) {
@@ -236,10 +250,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
             }
             if (elect_one()) mma_commit(&bars[2]);
             __syncwarp();
+#ifdef CM_TC_TRACE
+            tr2 = clock64();
+#endif
         }
         ok = mbar_wait(&bars[2], m_phase) && ok;
         m_phase ^= 1;
         fence_after_thread_sync();
+#ifdef CM_TC_TRACE
+        tr3 = clock64();
+        if (blockIdx.x == 0 && tid == 0 && consumed < 64 && io.workspace) {
+            long long *tb = reinterpret_cast<long long *>(io.workspace) + 4 * consumed;
+            tb[0] = tr0; tb[1] = tr1; tb[2] = tr2; tb[3] = tr3;
+        }
+#endif
         consumed += (uint32_t)nops;
         si += nops;
         issue_loads();
@@ -359,7 +383,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
 #pragma unroll
             for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
             float den = 0.0f;
-            const int nn = valid ? n : 0;
+            const int nn = (valid && !(CM_TC_DEBUG & 4)) ? n : 0;
             for (int jj = 0; jj < nn; ++jj) {
                 const uint32_t bit = ((jj < 32 ? m0 : m1) >> (jj & 31)) & 1u;
                 const float a = bit ? MT[jj * kTPitch + row] : 0.0f;

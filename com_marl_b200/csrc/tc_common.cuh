@@ -34,6 +34,37 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, int K, in
     return d;
 }
 
+// ---- 16-bit operands (kind::f16): core matrix = 8 rows x 16 bytes = 8 elements; one MMA consumes K = 16 ----
+__device__ __forceinline__ uint32_t canon_off16(int r, int k, int K)
+{
+    return (uint32_t)((r >> 3) * (K >> 3) * 128 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2);
+}
+__device__ __forceinline__ uint64_t make_smem_desc16(uint32_t smem_addr, int K, int kslice)
+{
+    const uint32_t start = smem_addr + (uint32_t)kslice * 256u;
+    uint64_t d = 0;
+    d |= (uint64_t)((start & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(128u >> 4) << 16;
+    d |= (uint64_t)(((uint32_t)(K >> 3) * 128u) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// kind::f16 with fp16 operands (format 0), fp32 accumulate
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N)
+{
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // 32-bit instruction descriptor, kind::tf32, fp32 accumulate, A and B K-major, M x N tile
 __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N)
 {

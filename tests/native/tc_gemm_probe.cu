@@ -69,6 +69,74 @@ __global__ void __launch_bounds__(128) tc_gemm_probe_kernel(const float *A, cons
     if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
+// fp16 split with a scaled remainder and a stacked B operand:
+//   x = x_hi + 2^-12 x_lo',  x_hi = fp16(x), x_lo' = fp16((x - x_hi) * 4096)
+//   pass 1: A_hi x [B_hi ; B_lo'] (N' = 2N)  -> D[:, 0:N] = hi*hi, D[:, N:2N] = hi*lo'
+//   pass 2: A_lo' x B_hi (N' = N)            -> accumulates into D[:, N:2N]
+//   C = D[:, c] + 2^-12 D[:, N + c]
+#include <cuda_fp16.h>
+__global__ void __launch_bounds__(128) tc_gemm_probe16_kernel(const float *A, const float *B, float *C, int N, int K, int *status)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    unsigned char *Ahi = smem, *Alo = Ahi + 128 * K * 2, *Bst = Alo + 128 * K * 2;   // Bst: 2N rows x K
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    for (int k = 0; k < K; ++k) {
+        const float a = A[(size_t)tid * K + k];
+        const __half h = __float2half_rn(a);
+        const __half l = __float2half_rn((a - __half2float(h)) * 4096.0f);
+        *reinterpret_cast<__half *>(Ahi + canon_off16(tid, k, K)) = h;
+        *reinterpret_cast<__half *>(Alo + canon_off16(tid, k, K)) = l;
+    }
+    for (int r = tid; r < N; r += 128)
+        for (int k = 0; k < K; ++k) {
+            const float b = B[(size_t)r * K + k];
+            const __half h = __float2half_rn(b);
+            const __half l = __float2half_rn((b - __half2float(h)) * 4096.0f);
+            *reinterpret_cast<__half *>(Bst + canon_off16(r, k, K)) = h;
+            *reinterpret_cast<__half *>(Bst + canon_off16(N + r, k, K)) = l;
+        }
+    fence_proxy_async();
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        for (int j = 0; j < K / 16; ++j)
+            mma_f16(tmem_base, make_smem_desc16(smem_u32(Ahi), K, j), make_smem_desc16(smem_u32(Bst), K, j), make_idesc_f16(128, 2 * N), j > 0);
+        for (int j = 0; j < K / 16; ++j)
+            mma_f16(tmem_base + N, make_smem_desc16(smem_u32(Alo), K, j), make_smem_desc16(smem_u32(Bst), K, j), make_idesc_f16(128, N), 1);
+        mma_commit(&bar);
+    }
+    const bool ok = mbar_wait(&bar, 0);
+    if (!ok && tid == 0) atomicExch(status, 1);
+    fence_after_thread_sync();
+    if (ok) {
+        for (int c = 0; c < N; c += 8) {
+            float v[8], w[8];
+            tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+            tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(N + c), w);
+            tmem_ld_wait();
+            for (int i = 0; i < 8; ++i) C[(size_t)tid * N + c + i] = v[i] + w[i] * (1.0f / 4096.0f);
+        }
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+extern "C" int tc_gemm_probe16(const float *A, const float *B, float *C, int N, int K, int *status, void *stream)
+{
+    const size_t smem = (size_t)(2 * 128 * K + 2 * N * K) * 2;
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_probe16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    tc_gemm_probe16_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, C, N, K, status);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int tc_gemm_probe(const float *A, const float *B, float *C, int N, int K, int passes, int *status, void *stream)
 {
     const size_t smem = (size_t)(2 * 128 * K + 2 * N * K) * sizeof(float);

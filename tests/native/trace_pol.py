@@ -1,0 +1,33 @@
+import sys, torch, numpy as np, ctypes as C
+sys.path.insert(0, '.')
+from com_marl_b200.scenario import ScenarioSpec
+from com_marl_b200.rollout import make_policy
+from com_marl_b200.envs import BatchedEnv
+from com_marl_b200 import _native as N
+cfg = sys.argv[1] if len(sys.argv) > 1 else 'c2'
+spec = {'c2': ScenarioSpec.from_cli('co',10,1,0.03), 'c3': ScenarioSpec.from_cli('pp',20,2,0.08,cap=4,loss=0.2)}[cfg]
+B = 16384
+env = BatchedEnv(spec, B); env.reset()
+pol = make_policy(spec)
+n=spec.n_agents
+probs=torch.empty((B,n,5),device='cuda'); acts=torch.empty((B,n),dtype=torch.int8,device='cuda')
+pol._workspace = torch.zeros(4096, dtype=torch.float32, device='cuda')
+orig = pol.act_device
+def run():
+    n_, D, L = pol._n_agents, pol._dec_obs_dim, pol.n_gcn_layers
+    desc = N.PolicyDesc(n_, D, L, 1, 0, 1, pol.seed, 0)
+    io = N.PolicyIO(); io.n_envs = B; io.weights = N.ptr(pol.weight_blob()); io.tc_weights = N.ptr(pol.tc_weight_blob())
+    io.obs=N.ptr(env.obs); io.adj_bits=N.ptr(env.adj_bits); io.chan_bits=N.ptr(env.chan_bits); io.tick=N.ptr(env.tick); io.episode=N.ptr(env.episode)
+    io.probs=N.ptr(probs); io.actions=N.ptr(acts); io.workspace=N.ptr(pol._workspace); io.workspace_bytes=16384; io.error_flag=N.ptr(pol._tc_error)
+    N.check('f', N.lib().cm_policy_forward(C.byref(desc), C.byref(io), N.stream_ptr()))
+for _ in range(3): run()
+torch.cuda.synchronize()
+t = pol._workspace.cpu().numpy().view(np.int64).reshape(-1,4)[:48]
+t0 = t[0,0]
+prev3 = None
+print("stage  epi  sync  issue  mmawait(after sync)   total")
+for i,(a,b,c,d) in enumerate(t):
+    if a == 0: continue
+    epi = (a - prev3) if prev3 is not None else 0
+    print(f"{i:3d} {epi:6d} {b-a:6d} {c-b if c else 0:6d} {d-b:6d} {d-(prev3 if prev3 else a):7d}")
+    prev3 = d
