@@ -337,10 +337,11 @@ def run_b200_arm(args):
     env_bytes = env_bytes_per_agent_step(spec) * B * n
     tc = pol.uses_tensor_cores()
     kname = "policy_tc_kernel" if tc else ("policy_small_kernel" if n <= 64 else "policy_large_kernel")
-    kdesc = ("the kernel issues 3 TF32 tcgen05 products per algorithmic product (error compensation) on K padded to 8/64, "
-             "so the tensor pipe executes ~3.3x the algorithmic FLOPs counted here" if tc else "the kernel itself is exact fp32 FFMA")
+    kdesc = ("the kernel issues A_hi x [B_hi;B_lo] and A_lo x B_hi in fp16 per algorithmic product (error compensation) on K "
+             "padded to 16/64, so the tensor pipe executes ~3.3x the algorithmic FLOPs counted here" if tc
+             else "the kernel itself is exact fp32 FFMA")
     # what the tensor pipe actually executes per 128-row tile: 3 passes over the padded dense layers
-    Dp = (Dobs + 7) // 8 * 8
+    Dp = (Dobs + 15) // 16 * 16
     dense_mac = Dp * 128 + 128 * 64 + 64 * 64 * (1 + L) + 64 * 128 + 128 * 64 + 64 * 32 + 32 * 16
     tc_flops = (3 * 2 * dense_mac * 128 * ((B * n + (128 // n) * n - 1) // ((128 // n) * n))) if tc else 0
     pol_tflops = flops / (pol_ms * 1e-3) / 1e12
@@ -348,7 +349,7 @@ def run_b200_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": ("f32-equivalent: error-compensated 3xTF32 tcgen05 products with fp32 accumulation in TMEM (policy)"
+        "dtype": ("f32-equivalent: error-compensated fp16-split tcgen05 products (x = hi + 2^-12 lo) with fp32 accumulation in TMEM (policy)"
                   if tc else "f32 FFMA (policy)") + " + u8/u16/u64 bit rows (env, comm)",
         "data": "synthetic",
         "config": {"workload": WORKLOAD_TEXT[args.config], "config": args.config, "envs_per_gpu": B, "n_agents": n,

@@ -44,16 +44,19 @@ struct PolicyArgs {
 };
 
 
-// ---- tcgen05 variant: one "stage" = the B operand of one tcgen05 product, N rows x Kp columns, stored in the
-// canonical K-major core-matrix layout as a hi block followed by a lo block (error-compensated TF32).  Every
-// stage is at most 32 KB so that two of them fit the kernel's weight ring; wide layers (N = 128 with Kp = 64)
-// are split into two N = 64 stages.  `seq` is the order in which one tile consumes the stages. ----
-struct TcStage { int w_off, src_off, N, Kp, k0, n0, Ksrc, Nsrc; };
+// ---- tcgen05 variant.  Every dense product runs on the tensor cores in fp16 with error compensation:
+//   x = x_hi + 2^-12 x_lo,   x_hi = fp16(x),   x_lo = fp16((x - x_hi) * 4096)        (22+ significant bits)
+//   D[:, 0:N]  = A_hi B_hi^T                     (one accumulator)
+//   D[:, N:2N] = A_hi B_lo^T + A_lo B_hi^T       (second accumulator, weight 2^-12 in the epilogue)
+// One "stage" = the B operand of one product: [B_hi ; B_lo] stacked along N (2N rows x Kp fp16) in the canonical
+// K-major core-matrix layout, so that A_hi x stage yields both accumulators with ONE series of K/16 instructions and
+// A_lo x (first N rows) adds the remaining cross term with another K/16.  Stages are at most 32 KB (a slot of the
+// kernel's weight ring) and are stored in the order in which a tile consumes them.  Offsets are in halves. ----
+struct TcStage { int w_off, src_off, N, Kp, k0, Ksrc, Nsrc; };
 struct TcPlan {
-    int n_stages, total_floats, seq_len;
-    int l1_panels, l1_split, h1_split;      // obs K panels (1 or 2); L1 / head-1 issued as two N = 64 halves?
-    int bias_floats;
-    TcStage st[24];
+    int n_stages, total_halves, seq_len;
+    int l1_panels;                          // obs K panels (1 or 2)
+    TcStage st[16];
 };
 
 __host__ __device__ inline TcPlan make_tc_plan(int D, int L)
@@ -61,36 +64,28 @@ __host__ __device__ inline TcPlan make_tc_plan(int D, int L)
     const Blob o = blob_layout(D, L);
     TcPlan P;
     int s = 0, off = 0;
-    auto add = [&](int src_off, int N, int Kp, int k0, int n0, int Ksrc, int Nsrc) {
-        P.st[s].w_off = off; P.st[s].src_off = src_off; P.st[s].N = N; P.st[s].Kp = Kp; P.st[s].k0 = k0; P.st[s].n0 = n0;
+    auto add = [&](int src_off, int N, int Kp, int k0, int Ksrc, int Nsrc) {
+        P.st[s].w_off = off; P.st[s].src_off = src_off; P.st[s].N = N; P.st[s].Kp = Kp; P.st[s].k0 = k0;
         P.st[s].Ksrc = Ksrc; P.st[s].Nsrc = Nsrc;
         off += 2 * N * Kp;
         return s++;
     };
-    // a wide (N = 128) product is one stage when it fits 32 KB, otherwise two N = 64 halves
-    auto add_wide = [&](int src_off, int Kp, int k0, int Ksrc) {
-        if (2 * 128 * Kp * 4 <= 32768) { add(src_off, 128, Kp, k0, 0, Ksrc, 128); return 0; }
-        add(src_off, 64, Kp, k0, 0, Ksrc, 128);
-        add(src_off, 64, Kp, k0, 64, Ksrc, 128);
-        return 1;
-    };
-    const int Dp = (D + 7) / 8 * 8;
+    const int Dp = (D + 15) / 16 * 16;
     P.l1_panels = Dp > 64 ? 2 : 1;
-    P.l1_split = add_wide(o.enc_w1, Dp <= 64 ? Dp : 64, 0, D);
-    if (Dp > 64) add(o.enc_w1, kH1, Dp - 64, 64, 0, D, kH1);            // second K panel: at most 128 x 64 ... (Dp-64 <= 64)
-    add(o.enc_w2, kE, 64, 0, 0, kH1, kE);
-    add(o.enc_w2, kE, 64, 64, 0, kH1, kE);
-    add(o.att_w, kE, 64, 0, 0, kE, kE);
-    for (int l = 0; l < L; ++l) add(o.gcn_w + l * kE * kE, kE, 64, 0, 0, kE, kE);
-    P.h1_split = add_wide(o.head_w1, 64, 0, kE);
-    add(o.head_w2, kC2, 64, 0, 0, kC1, kC2);
-    add(o.head_w2, kC2, 64, 64, 0, kC1, kC2);
-    add(o.head_w3, kC3, 64, 0, 0, kC2, kC3);
-    add(o.head_w4, 16, 32, 0, 0, kC3, CM_ACTIONS);                       // 5 logits padded to N = 16
+    add(o.enc_w1, kH1, Dp <= 64 ? Dp : 64, 0, D, kH1);
+    if (Dp > 64) add(o.enc_w1, kH1, Dp - 64, 64, D, kH1);
+    add(o.enc_w2, kE, 64, 0, kH1, kE);
+    add(o.enc_w2, kE, 64, 64, kH1, kE);
+    add(o.att_w, kE, 64, 0, kE, kE);
+    for (int l = 0; l < L; ++l) add(o.gcn_w + l * kE * kE, kE, 64, 0, kE, kE);
+    add(o.head_w1, kC1, 64, 0, kE, kC1);
+    add(o.head_w2, kC2, 64, 0, kC1, kC2);
+    add(o.head_w2, kC2, 64, 64, kC1, kC2);
+    add(o.head_w3, kC3, 64, 0, kC2, kC3);
+    add(o.head_w4, 16, 32, 0, kC3, CM_ACTIONS);                          // 5 logits padded to N = 16
     P.n_stages = s;
-    P.seq_len = s;                                                        // stages are stored in consumption order
-    P.total_floats = off;
-    P.bias_floats = o.total - o.enc_b1;                                  // upper bound, biases are read from the fp32 blob
+    P.seq_len = s;
+    P.total_halves = off;
     return P;
 }
 

@@ -3,18 +3,20 @@
 // Same formula and outputs as policy_kernel.cu (see its header for the reference lines), different machine
 // mapping: a CTA of 512 threads owns a tile of 128 agent rows (whole environments, n <= 64) and runs
 //   * every row-wise dense layer (encoder, attention query, H_l Wg_l, the categorical head) as
-//     tcgen05.mma.kind::tf32 with the accumulator in tensor memory.  fp32-level accuracy is kept by error
-//     compensation: each product is issued three times, A_hi B_hi + A_lo B_hi + A_hi B_lo, with
-//     x_hi = x & 0xFFFFE000 (exactly representable in TF32) and x_lo = x - x_hi.  Weights are pre-split and
+//     tcgen05.mma.kind::f16 (fp16 operands, fp32 accumulators in tensor memory).  fp32-level accuracy is kept by
+//     error compensation: x = x_hi + 2^-12 x_lo with x_hi = fp16(x), x_lo = fp16((x - x_hi) * 4096);
+//     A_hi x [B_hi ; B_lo] (B stacked along N) gives hi*hi and hi*lo in two accumulators with one series of K/16
+//     instructions, A_lo x B_hi adds the other cross term, the epilogue forms acc0 + 2^-12 acc1 (dropped term:
+//     2^-24).  Measured error of one product 1-3e-7 of scale, i.e. fp32 level.  Weights are pre-split, stacked and
 //     pre-arranged in the canonical K-major core-matrix layout by cm_policy_tc_prepare(), so that a layer's
-//     B operand is ONE bulk async copy (TMA engine, mbarrier completion) issued while the previous layer's
-//     epilogue runs;
+//     B operand is ONE bulk async copy (TMA engine, mbarrier completion) issued one to two layers ahead;
 //   * the per-environment pieces (n x n scores, softmax, masked renormalisation, aggregation over
 //     neighbours) exactly — not as padded tile products — on the CUDA cores from k-major fp32 copies of E, Q
 //     and H_l Wg_l in shared memory.
 // TMEM lane = tile row = thread (row = 32 * (warp % 4) + lane); the four warps that share a lane quadrant
 // split the accumulator columns.  Epilogues read TMEM with tcgen05.ld, apply bias + tanh, and write the next
 // A operand (hi / lo) straight into the canonical layout.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -34,7 +36,7 @@ using namespace tc;
 
 static constexpr int kTcRows = 128;
 static constexpr int kTcThreads = 512;
-static constexpr int kActBytes = 65536, kWBytes = 65536;
+static constexpr int kActBytes = 32768, kWBytes = 65536;   // A operand hi|lo (128 x 64 fp16 each); weight ring 2 x 32 KB
 static constexpr int kTPitch = 128;     // floats per k-major row of ET / QT / HWT
 
 struct TcArgs {
@@ -59,18 +61,27 @@ __device__ __forceinline__ void ld_cols(uint32_t taddr, float (&v)[CW])
     tmem_ld_wait();
 }
 
-// write CW consecutive columns (starting at local column c0 of a Kp-wide panel) of row `row` as the next A operand
+// fp16 split of one value: hi = fp16(x), lo = fp16((x - hi) * 4096)
+__device__ __forceinline__ void split16(float x, __half &hi, __half &lo)
+{
+    hi = __float2half_rn(x);
+    lo = __float2half_rn((x - __half2float(hi)) * 4096.0f);
+}
+
+// write CW (8 or 16) consecutive columns, starting at local column c0 (a multiple of 8) of a Kp-wide panel, of row `row`
+// as the next A operand: hi block, then the lo block 128 * Kp halves further
 template <int CW>
 __device__ __forceinline__ void write_act(unsigned char *act, int Kp, int row, int c0, const float (&v)[CW])
 {
-    const uint32_t lo_off = (uint32_t)kTcRows * Kp * 4;
+    const uint32_t lo_off = (uint32_t)kTcRows * Kp * 2;
 #pragma unroll
-    for (int g = 0; g < CW; g += 4) {
-        const float4 h = make_float4(tf32_hi(v[g]), tf32_hi(v[g + 1]), tf32_hi(v[g + 2]), tf32_hi(v[g + 3]));
-        const float4 l = make_float4(tf32_lo(v[g], h.x), tf32_lo(v[g + 1], h.y), tf32_lo(v[g + 2], h.z), tf32_lo(v[g + 3], h.w));
-        const uint32_t off = canon_off(row, c0 + g, Kp);
-        *reinterpret_cast<float4 *>(act + off) = h;
-        *reinterpret_cast<float4 *>(act + lo_off + off) = l;
+    for (int g = 0; g < CW; g += 8) {
+        __align__(16) __half h[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split16(v[g + i], h[i], l[i]);
+        const uint32_t off = canon_off16(row, c0 + g, Kp);
+        *reinterpret_cast<uint4 *>(act + off) = *reinterpret_cast<const uint4 *>(h);
+        *reinterpret_cast<uint4 *>(act + lo_off + off) = *reinterpret_cast<const uint4 *>(l);
     }
 }
 
@@ -83,28 +94,55 @@ __device__ __forceinline__ float tanh_fast(float x)
     return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
-// one converged warp: D[tmem] (+)= ACT * W^T, error-compensated (hi*hi + lo*hi + hi*lo).  All lanes run the loop
+// one converged warp: D[:, 0:N] (+)= A_hi B_hi^T, D[:, N:2N] (+)= A_hi B_lo^T + A_lo B_hi^T.  All lanes run the loop
 // (descriptors stay warp-uniform), the elected lane issues.
 __device__ __forceinline__ void issue_layer(uint32_t d_tmem, const unsigned char *act, const unsigned char *wblk, int N, int Kp,
                                             uint32_t accumulate)
 {
-    const uint32_t a_hi = smem_u32(act), a_lo = a_hi + (uint32_t)kTcRows * Kp * 4;
-    const uint32_t b_hi = smem_u32(wblk), b_lo = b_hi + (uint32_t)N * Kp * 4;
-    const uint32_t idesc = make_idesc_tf32(kTcRows, N);
-    const int nk = Kp >> 3;
-    uint32_t acc = accumulate;
-#pragma unroll 1
-    for (int p = 0; p < 3; ++p) {
-        uint64_t da = make_smem_desc((p == 1) ? a_lo : a_hi, Kp, 0), db = make_smem_desc((p == 2) ? b_lo : b_hi, Kp, 0);
+    const uint32_t a_hi = smem_u32(act), a_lo = a_hi + (uint32_t)kTcRows * Kp * 2, b = smem_u32(wblk);
+    const int nk = Kp >> 4;
+    {   // A_hi x [B_hi ; B_lo]  (N' = 2N)
+        const uint32_t idesc = make_idesc_f16(kTcRows, 2 * N);
+        uint64_t da = make_smem_desc16(a_hi, Kp, 0), db = make_smem_desc16(b, Kp, 0);
+        uint32_t acc = accumulate;
 #pragma unroll 2
         for (int j = 0; j < nk; ++j) {
-            if (!(CM_TC_DEBUG & 1) && elect_one()) mma_tf32(d_tmem, da, db, idesc, acc);
+            if (!(CM_TC_DEBUG & 1) && elect_one()) mma_f16(d_tmem, da, db, idesc, acc);
             acc = 1;
-            da += 16;     // next K = 8 slice: start address + 256 bytes (>> 4)
+            da += 16;     // next K = 16 slice: start address + 256 bytes (>> 4)
+            db += 16;
+        }
+    }
+    {   // A_lo x B_hi  (N' = N) into the cross-term accumulator
+        const uint32_t idesc = make_idesc_f16(kTcRows, N);
+        uint64_t da = make_smem_desc16(a_lo, Kp, 0), db = make_smem_desc16(b, Kp, 0);
+#pragma unroll 2
+        for (int j = 0; j < nk; ++j) {
+            if (!(CM_TC_DEBUG & 1) && elect_one()) mma_f16(d_tmem + (uint32_t)N, da, db, idesc, 1u);
+            da += 16;
             db += 16;
         }
     }
     __syncwarp();
+}
+
+// accumulator read-out: acc0 + 2^-12 acc1 for CW columns starting at column `col` of a product whose D block starts at
+// `base` and is 2N columns wide
+template <int CW>
+__device__ __forceinline__ void ld_acc(uint32_t lane_addr, uint32_t base, int N, int col, float (&v)[CW])
+{
+    float w[CW];
+#pragma unroll
+    for (int c = 0; c < CW; c += 8) {
+        float t0[8], t1[8];
+        tmem_ld8(lane_addr + base + (uint32_t)(col + c), t0);
+        tmem_ld8(lane_addr + base + (uint32_t)(N + col + c), t1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[c + i] = t0[i]; w[c + i] = t1[i]; }
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < CW; ++c) v[c] = fmaf(w[c], 1.0f / 4096.0f, v[c]);
 }
 
 // Exact per-environment attention row: thread (row, sub) owns the keys jj = sub, sub + 4, ... of its env (at most
@@ -170,11 +208,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
     const int n = d.n_agents, D = d.obs_dim, L = d.n_layers, W = (n + 31) >> 5;
     const Blob o = blob_layout(D, L);
     const float *__restrict__ wts = io.weights;
-    const float *tcw = io.tc_weights;
+    const __half *tcw = reinterpret_cast<const __half *>(io.tc_weights);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int quad = warp & 3, sub = warp >> 2, row = quad * 32 + lane;
 
-    if (warp == 0) tmem_alloc(tmem_s, 256);
+    if (warp == 0) tmem_alloc(tmem_s, 512);
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -197,7 +235,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
     fence_after_thread_sync();
     const uint32_t tmem = *tmem_s;
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    const uint32_t DA = 0, DB = 128;          // accumulator column regions
+    const uint32_t DA = 0, DB = 256;          // accumulator column regions (a product's D block is 2N columns wide)
     uint32_t m_phase = 0;
     bool ok = true;
 
@@ -211,7 +249,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
         if (warp == 0) {
             while (issued < consumed + 2 && issued < total_blocks) {
                 const TcStage &st = P.st[issued_si];
-                const uint32_t bytes = (uint32_t)(2 * st.N * st.Kp * 4), slot = issued & 1u;
+                const uint32_t bytes = (uint32_t)(2 * st.N * st.Kp * 2), slot = issued & 1u;
                 if (elect_one()) {
                     if (CM_TC_DEBUG & 8) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[slot])) : "memory"); }
                     else {
@@ -284,7 +322,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
         for (int pnl = 0; pnl < P.l1_panels; ++pnl) {
             const int Kp = P.st[si].Kp, kofs = 64 * pnl;
             const float *src = io.obs + row0 * D;
-            const uint32_t lo_off = (uint32_t)kTcRows * Kp * 4;
+            const uint32_t lo_off = (uint32_t)kTcRows * Kp * 2;
             // all global loads first (independent, 128 * Kp / 512 <= 16 per thread), then the split + stores
             float ov[16];
             const int total = kTcRows * Kp;
@@ -299,19 +337,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
                 const int e = tid + q * kTcThreads;
                 if (e < total) {
                     const int r = e / Kp, k = e - r * Kp;
-                    const float h = tf32_hi(ov[q]);
-                    const uint32_t off = canon_off(r, k, Kp);
-                    *reinterpret_cast<float *>(ACT + off) = h;
-                    *reinterpret_cast<float *>(ACT + lo_off + off) = tf32_lo(ov[q], h);
+                    __half h, l;
+                    split16(ov[q], h, l);
+                    const uint32_t off = canon_off16(r, k, Kp);
+                    *reinterpret_cast<__half *>(ACT + off) = h;
+                    *reinterpret_cast<__half *>(ACT + lo_off + off) = l;
                 }
             }
-            if (pnl == 0 && P.l1_split) run_mma(2, MmaOp{DA, 0u}, MmaOp{DA + 64, 0u});
-            else run_mma(1, MmaOp{DA, (uint32_t)pnl}, none);
+            run_mma(1, MmaOp{DA, (uint32_t)pnl}, none);
         }
         // ---------------- encoder layer 2 (K = 128 as two panels of h) -> DB[0:64] ----------------
         for (int p = 0; p < 2; ++p) {
             float v[16];
-            ld_cols<16>(lane_addr + DA + 64 * p + 16 * sub, v);
+            ld_acc<16>(lane_addr, DA, 128, 64 * p + 16 * sub, v);
 #pragma unroll
             for (int c = 0; c < 16; ++c) v[c] = tanh_fast(v[c] + bias_s[kBEnc1 + 64 * p + 16 * sub + c]);
             write_act<16>(ACT, 64, row, 16 * sub, v);
@@ -320,19 +358,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
         // ---------------- E = tanh(. + b2): k-major fp32 copy + A operand; Q -> DA[0:64], H_0 Wg_0 -> DA[64:128] ----------------
         {
             float v[16];
-            ld_cols<16>(lane_addr + DB + 16 * sub, v);
+            ld_acc<16>(lane_addr, DB, 64, 16 * sub, v);
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 v[c] = tanh_fast(v[c] + bias_s[kBEnc2 + 16 * sub + c]);
                 ET[(16 * sub + c) * kTPitch + row] = v[c];
             }
             write_act<16>(ACT, 64, row, 16 * sub, v);
-            run_mma(2, MmaOp{DA, 0u}, MmaOp{DA + 64, 0u});
+            run_mma(2, MmaOp{DA, 0u}, MmaOp{DA + 128, 0u});
         }
         // ---------------- scores, softmax (exact per environment, CUDA cores) ----------------
         {
             float v[16];
-            ld_cols<16>(lane_addr + DA + 16 * sub, v);
+            ld_acc<16>(lane_addr, DA, 64, 16 * sub, v);
 #pragma unroll
             for (int c = 0; c < 16; ++c) QT[(16 * sub + c) * kTPitch + row] = v[c];
         }
@@ -356,7 +394,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
         // H_0 Wg_0 out of tensor memory (the softmax scratch is dead now)
         {
             float v[16];
-            ld_cols<16>(lane_addr + DA + 64 + 16 * sub, v);
+            ld_acc<16>(lane_addr, DA + 128, 64, 16 * sub, v);
             __syncthreads();
 #pragma unroll
             for (int c = 0; c < 16; ++c) HWT[(16 * sub + c) * kTPitch + row] = v[c];
@@ -403,7 +441,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
             if (l + 1 < L) {
                 run_mma(1, MmaOp{DB, 0u}, none);
                 float hv[16];
-                ld_cols<16>(lane_addr + DB + 16 * sub, hv);
+                ld_acc<16>(lane_addr, DB, 64, 16 * sub, hv);
                 __syncthreads();          // every thread is done reading HWT of layer l
 #pragma unroll
                 for (int c = 0; c < 16; ++c) HWT[(16 * sub + c) * kTPitch + row] = hv[c];
@@ -411,11 +449,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
             }
         }
         // ---------------- categorical head ----------------
-        if (P.h1_split) run_mma(2, MmaOp{DA, 0u}, MmaOp{DA + 64, 0u});          // 64 -> 128
-        else run_mma(1, MmaOp{DA, 0u}, none);
+        run_mma(1, MmaOp{DA, 0u}, none);                                          // 64 -> 128
         for (int p = 0; p < 2; ++p) {                                             // 128 -> 64 as two K panels
             float v[16];
-            ld_cols<16>(lane_addr + DA + 64 * p + 16 * sub, v);
+            ld_acc<16>(lane_addr, DA, 128, 64 * p + 16 * sub, v);
 #pragma unroll
             for (int c = 0; c < 16; ++c) v[c] = tanh_fast(v[c] + bias_s[kBH1 + 64 * p + 16 * sub + c]);
             write_act<16>(ACT, 64, row, 16 * sub, v);
@@ -423,7 +460,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
         }
         {                                                                         // 64 -> 32
             float v[16];
-            ld_cols<16>(lane_addr + DB + 16 * sub, v);
+            ld_acc<16>(lane_addr, DB, 64, 16 * sub, v);
 #pragma unroll
             for (int c = 0; c < 16; ++c) v[c] = tanh_fast(v[c] + bias_s[kBH2 + 16 * sub + c]);
             write_act<16>(ACT, 64, row, 16 * sub, v);
@@ -431,7 +468,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
         }
         {                                                                         // 32 -> 5 (padded to 16)
             float v[8];
-            ld_cols<8>(lane_addr + DA + 8 * sub, v);
+            ld_acc<8>(lane_addr, DA, 32, 8 * sub, v);
 #pragma unroll
             for (int c = 0; c < 8; ++c) v[c] = tanh_fast(v[c] + bias_s[kBH3 + 8 * sub + c]);
             write_act<8>(ACT, 32, row, 8 * sub, v);
@@ -440,7 +477,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
         // ---------------- softmax, availability mask, renormalise, sample ----------------
         if (sub == 0) {
             float lg8[8];
-            ld_cols<8>(lane_addr + DB, lg8);
+            ld_acc<8>(lane_addr, DB, 16, 0, lg8);
             if (valid) {
                 float lg[CM_ACTIONS], pr[CM_ACTIONS];
                 float mx = -INFINITY;
@@ -491,13 +528,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
     if (!ok && io.error_flag) atomicExch(io.error_flag, (int)CM_ECUDA);
     fence_before_thread_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
 // weight preparation: fp32 k-major blob -> per-stage canonical hi | lo panels
 // ------------------------------------------------------------------------------------------------
-__global__ void tc_prepare_kernel(const float *__restrict__ w, float *__restrict__ out, const TcPlan P)
+__global__ void tc_prepare_kernel(const float *__restrict__ w, __half *__restrict__ out, const TcPlan P)
 {
     for (int s = 0; s < P.n_stages; ++s) {
         const TcStage st = P.st[s];
@@ -505,11 +542,13 @@ __global__ void tc_prepare_kernel(const float *__restrict__ w, float *__restrict
         for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
             const int r = e / st.Kp, k = e - r * st.Kp;
             float v = 0.0f;
-            if (st.n0 + r < st.Nsrc && st.k0 + k < st.Ksrc) v = w[st.src_off + (size_t)(st.k0 + k) * st.Nsrc + st.n0 + r];
-            const float h = tc::tf32_hi(v);
-            const int idx = (r >> 3) * (st.Kp >> 2) * 32 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3);
-            out[st.w_off + idx] = h;
-            out[st.w_off + total + idx] = tc::tf32_lo(v, h);
+            if (r < st.Nsrc && st.k0 + k < st.Ksrc) v = w[st.src_off + (size_t)(st.k0 + k) * st.Nsrc + r];
+            const __half h = __float2half_rn(v);
+            const __half l = __float2half_rn((v - __half2float(h)) * 4096.0f);
+            // canonical K-major layout over the stacked 2N rows: hi rows [0, N), lo rows [N, 2N)
+            auto idx = [&](int rr) { return (rr >> 3) * (st.Kp >> 3) * 64 + (k >> 3) * 64 + (rr & 7) * 8 + (k & 7); };
+            out[st.w_off + idx(r)] = h;
+            out[st.w_off + idx(st.N + r)] = l;
         }
     }
 }
@@ -548,7 +587,7 @@ int launch_policy_tc(const cm_policy_desc *desc, const cm_policy_io *io, cudaStr
 
 extern "C" size_t cm_policy_tc_blob_floats(int32_t obs_dim, int32_t n_layers)
 {
-    return (size_t)cm::make_tc_plan(obs_dim, n_layers).total_floats;
+    return (size_t)(cm::make_tc_plan(obs_dim, n_layers).total_halves + 1) / 2;
 }
 
 extern "C" int cm_policy_tc_prepare(const cm_policy_desc *desc, const float *weights, float *tc_weights, cm_stream_t stream)
@@ -557,7 +596,7 @@ extern "C" int cm_policy_tc_prepare(const cm_policy_desc *desc, const float *wei
     if (desc->n_layers < 1 || desc->n_layers > CM_MAX_LAYERS || desc->obs_dim < 1 || desc->obs_dim > 128) return CM_EUNSUPPORTED;
     if (cm_device_count() < 1) return CM_ENODEVICE;
     const cm::TcPlan P = cm::make_tc_plan(desc->obs_dim, desc->n_layers);
-    cm::tc_prepare_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(weights, tc_weights, P);
+    cm::tc_prepare_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(weights, reinterpret_cast<__half *>(tc_weights), P);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? CM_OK : cm::set_cuda_error(e, CM_ECUDA);
 }

@@ -103,10 +103,10 @@ class CommCategoricalMLPPolicy(nn.Module):
         self._embedding_dim = embedding_dim
         self.n_gcn_layers = int(n_gcn_layers)
         self.seed = int(seed)
-        # kernel variant: 'fp32' = exact FFMA kernels; 'tf32x3' = tcgen05 tensor cores with error-compensated TF32
-        # (fp32-level accuracy, teams of n <= 64); 'auto' picks tf32x3 whenever the team fits one tile
-        if math not in ("auto", "fp32", "tf32x3"):
-            raise ValueError("math must be 'auto', 'fp32' or 'tf32x3'")
+        # kernel variant: 'fp32' = exact FFMA kernels; 'tc' = tcgen05 tensor cores, error-compensated fp16 products with
+        # fp32 accumulation (fp32-level accuracy, teams of n <= 64); 'auto' picks 'tc' whenever the team fits one tile
+        if math not in ("auto", "fp32", "tc"):
+            raise ValueError("math must be 'auto', 'fp32' or 'tc'")
         self.math = math
         self.encoder = _MLP(self._dec_obs_dim, encoder_hidden_sizes, embedding_dim, output_tanh=True)
         self.attention_layer = _Attention(embedding_dim)
@@ -147,7 +147,7 @@ class CommCategoricalMLPPolicy(nn.Module):
         return self._blob
 
     def uses_tensor_cores(self):
-        return self.math == "tf32x3" or (self.math == "auto" and self._n_agents <= 64)
+        return self.math == "tc" or (self.math == "auto" and self._n_agents <= 64)
 
     def tc_weight_blob(self):
         """pre-split (hi | lo), pre-laid-out B operands of the tcgen05 variant; rebuilt when a parameter changed"""
@@ -178,7 +178,7 @@ class CommCategoricalMLPPolicy(nn.Module):
         B = obs.shape[0]
         tc = self.uses_tensor_cores()
         if tc and n > 64:
-            raise ValueError("math='tf32x3' supports teams of at most 64 agents; use math='fp32'")
+            raise ValueError("math='tc' supports teams of at most 64 agents; use math='fp32'")
         desc = N.PolicyDesc(n, D, L, int(self.residual), int(greedy), int(tc), self.seed, env_id0)
         io = N.PolicyIO()
         io.n_envs = B

@@ -149,8 +149,9 @@ typedef struct cm_policy_desc {
     int32_t n_layers;          /* L */
     int32_t residual;          /* comm_categorical_mlp_policy.py:74-77 */
     int32_t greedy;            /* argmax instead of sampling (:109-112) */
-    int32_t math;              /* 0: exact fp32 FFMA kernels; 1: tcgen05 tensor cores with error-compensated TF32
-                                  (fp32-level accuracy, teams with n <= 64; needs io.tc_weights) */
+    int32_t math;              /* 0: exact fp32 FFMA kernels; 1: tcgen05 tensor cores, error-compensated fp16 products
+                                  (x = x_hi + 2^-12 x_lo) with fp32 accumulation in tensor memory: fp32-level accuracy,
+                                  teams with n <= 64; needs io.tc_weights */
     uint64_t seed;
     int64_t env_id0;
 } cm_policy_desc;
@@ -203,8 +204,8 @@ int cm_comm_update(const cm_env_desc *desc, const cm_env_state *state, const cm_
  * graph_conv_module.py:51-72, categorical_mlp_module.py:64-80, multi_headed_mlp_module.py:134-149). */
 int cm_policy_forward(const cm_policy_desc *desc, const cm_policy_io *io, cm_stream_t stream);
 size_t cm_policy_blob_floats(int32_t obs_dim, int32_t n_layers);
-/* tcgen05 variant: re-lays the fp32 weight blob out as pre-split (hi | lo) K-major core-matrix panels, one per
- * tensor-core product, so that the kernel fetches a layer's B operand with one bulk async copy */
+/* tcgen05 variant: re-lays the fp32 weight blob out as pre-split fp16 ([B_hi ; B_lo] stacked) K-major core-matrix
+ * panels, one per tensor-core product, so that the kernel fetches a layer's B operand with one bulk async copy */
 size_t cm_policy_tc_blob_floats(int32_t obs_dim, int32_t n_layers);
 int cm_policy_tc_prepare(const cm_policy_desc *desc, const float *weights, float *tc_weights, cm_stream_t stream);
 /* scratch the forward needs for teams larger than one 64-row tile (0 for n <= 64) */
