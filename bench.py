@@ -261,30 +261,41 @@ def run_b200_arm(args):
     ms = ev0.elapsed_time(ev1)
     launches = eng.kernel_launches - launches0
     eng.env.check_errors()
-    # ---------------- per-kernel durations (CUDA events around each launch, eager) ----------------
-    kt = {"policy": [], "env": []}
-    probe_steps = min(steps, 4 * ring)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(probe_steps)]
+    # ---------------- per-kernel durations: CUDA events around a CUDA graph of 32 launches of ONE kernel ----------------
+    # (events around single eager launches would include the host's launch gaps, which are of the order of these kernels)
     eng._carry()
-    for i in range(probe_steps):
-        k = i % ring
-        if i and k == 0:
-            eng._carry()
-        t, e = eng.traj, eng.env
-        evs[i][0].record()
+    t, e = eng.traj, eng.env
+    reps = 32
+
+    def policy_once(k):
         pol.act_device(t["obs"][k], t["adj_bits"][k], t["chan_bits"][k], tick=e.tick, episode=e.episode, probs=t["probs"][k],
                        actions=t["actions"][k], env_id0=e.env_id0)
-        evs[i][1].record()
+
+    def env_once(k):
         e.step(t["actions"][k], out=dict(obs=t["obs"][k + 1], adj_bits=t["adj_bits"][k + 1], chan_bits=t["chan_bits"][k + 1],
                                          ave_deg=t["ave_deg"][k + 1], reward=t["reward"][k], done=t["done"][k],
                                          counts=t["counts"][k], prey_alive_out=t["prey_alive_out"][k], success_out=t["success"][k]))
-        evs[i][2].record()
-    torch.cuda.synchronize(dev)
-    for a, b, c in evs[2:]:
-        kt["policy"].append(a.elapsed_time(b))
-        kt["env"].append(b.elapsed_time(c))
-    pol_ms, env_ms = float(np.mean(kt["policy"])), float(np.mean(kt["env"]))
-    eng.steps_done += probe_steps
+
+    def time_graph(fn):
+        for k in range(2):
+            fn(k)                                   # warm (also keeps the ring consistent: slot k feeds slot k + 1)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for k in range(reps):
+                fn(k % ring)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g.replay()
+        a.record()
+        for _ in range(3):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / (3 * reps)
+
+    pol_ms = time_graph(policy_once)
+    env_ms = time_graph(env_once)
+    eng.steps_done += 4 * reps
     clock_info = clocks.stop(t_lo, t_hi) if rank == 0 else None
     # ---------------- e2e: host buffers through the public step / get_actions API ----------------
     from com_marl_b200.envs import BatchedEnv
