@@ -26,6 +26,9 @@
 #include "policy_layout.cuh"
 #include "tc_common.cuh"
 
+#ifndef CM_TC_OBS_PREFETCH
+#define CM_TC_OBS_PREFETCH 0   // measured slower on B200 (C2 0.082 vs 0.076 ms): the held registers cost more than the hidden latency
+#endif
 #ifndef CM_TC_DEBUG
 #define CM_TC_DEBUG 0   // timing experiments only: 1 skip MMAs, 2 skip tanh, 4 skip attention loops, 8 skip weight copies
 #endif
@@ -308,6 +311,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
     };
     const MmaOp none = {0u, 0u};
 
+    // observation panel `pnl` (64 columns, the first one Kp0 wide) of tile `tl` -> registers, 128 * Kp / 512 <= 16 per thread
+    float ov[16];
+    bool ov_ready = false;
+    auto load_obs_panel = [&](float (&dst)[16], int64_t tl, int pnl) {
+        const int Kp = P.st[pnl].Kp, kofs = 64 * pnl, total = kTcRows * Kp;
+        const int64_t e0 = tl * A.envs_per_tile;
+        const int rws = (int)min((int64_t)A.envs_per_tile, io.n_envs - e0) * n;
+        const float *src = io.obs + e0 * n * D;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int e = tid + q * kTcThreads;
+            const int r = e / Kp, k = e - r * Kp;
+            dst[q] = (e < total && r < rws && kofs + k < D) ? __ldg(src + (size_t)r * D + kofs + k) : 0.0f;
+        }
+    };
+
     for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
         const int64_t env0 = tile * A.envs_per_tile;
         const int envs = (int)min((int64_t)A.envs_per_tile, io.n_envs - env0);
@@ -317,21 +336,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
         const int el = valid ? row / n : 0, il = row - el * n, j0 = el * n;
         const int64_t env = env0 + el, g = row0 + row;
         si = 0;
+        // neighbour masks of this row for every layer: fetched now, used after the attention (global latency hidden)
+        uint32_t msk0[CM_MAX_LAYERS], msk1[CM_MAX_LAYERS];
+#pragma unroll
+        for (int l = 0; l < CM_MAX_LAYERS; ++l) {
+            uint32_t m0 = 0u, m1 = 0u;
+            if (valid && l < L) {
+                m0 = m1 = 0xFFFFFFFFu;
+                if (io.adj_bits) {
+                    const uint32_t *p = io.adj_bits + (env * n + il) * W;
+                    m0 &= __ldg(p);
+                    if (W > 1) m1 &= __ldg(p + 1);
+                }
+                if (io.chan_bits) {
+                    const uint32_t *p = io.chan_bits + ((env * L + l) * n + il) * W;
+                    m0 &= __ldg(p);
+                    if (W > 1) m1 &= __ldg(p + 1);
+                }
+            }
+            msk0[l] = m0;
+            msk1[l] = m1;
+        }
 
         // ---------------- encoder layer 1: obs panels -> DA[0:128] ----------------
         for (int pnl = 0; pnl < P.l1_panels; ++pnl) {
-            const int Kp = P.st[si].Kp, kofs = 64 * pnl;
-            const float *src = io.obs + row0 * D;
+            const int Kp = P.st[si].Kp;
             const uint32_t lo_off = (uint32_t)kTcRows * Kp * 2;
-            // all global loads first (independent, 128 * Kp / 512 <= 16 per thread), then the split + stores
-            float ov[16];
+            // all global loads first (independent, 128 * Kp / 512 <= 16 per thread), then the split + stores; the first
+            // panel was already fetched into `ov` while the previous tile was in its head layers
             const int total = kTcRows * Kp;
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int e = tid + q * kTcThreads;
-                const int r = e / Kp, k = e - r * Kp;
-                ov[q] = (e < total && r < rows && kofs + k < D) ? __ldg(src + (size_t)r * D + kofs + k) : 0.0f;
-            }
+            if (pnl > 0 || !ov_ready) load_obs_panel(ov, tile, pnl);
+            ov_ready = false;
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const int e = tid + q * kTcThreads;
@@ -404,19 +439,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
         for (int l = 0; l < L; ++l) {
             // A_l = M * Range * chan_l / (sum + 1e-12); out = A_l (H_l Wg_l)   (comm_base_net.py:101-103, graph_conv_module.py:51-72)
             uint32_t m0 = 0u, m1 = 0u;
-            if (valid) {
-                m0 = m1 = 0xFFFFFFFFu;
-                if (io.adj_bits) {
-                    const uint32_t *p = io.adj_bits + (env * n + il) * W;
-                    m0 &= __ldg(p);
-                    if (W > 1) m1 &= __ldg(p + 1);
-                }
-                if (io.chan_bits) {
-                    const uint32_t *p = io.chan_bits + ((env * L + l) * n + il) * W;
-                    m0 &= __ldg(p);
-                    if (W > 1) m1 &= __ldg(p + 1);
-                }
-            }
+#pragma unroll
+            for (int q = 0; q < CM_MAX_LAYERS; ++q)
+                if (q == l) { m0 = msk0[q]; m1 = msk1[q]; }
             float acc[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
@@ -449,6 +474,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
             }
         }
         // ---------------- categorical head ----------------
+        if (CM_TC_OBS_PREFETCH && tile + gridDim.x < A.n_tiles) {       // next tile's first observation panel: in flight during the head
+            load_obs_panel(ov, tile + gridDim.x, 0);
+            ov_ready = true;
+        }
         run_mma(1, MmaOp{DA, 0u}, none);                                          // 64 -> 128
         for (int p = 0; p < 2; ++p) {                                             // 128 -> 64 as two K panels
             float v[16];
