@@ -50,50 +50,47 @@ struct PolicyArgs {
 //   D[:, N:2N] = A_hi B_lo^T + A_lo B_hi^T       (second accumulator, weight 2^-12 in the epilogue)
 // One "stage" = the B operand of one product: [B_hi ; B_lo] stacked along N (2N rows x Kp fp16) in the canonical
 // K-major core-matrix layout, so that A_hi x stage yields both accumulators with ONE series of K/16 instructions and
-// A_lo x (first N rows) adds the remaining cross term with another K/16.  Stages are at most 32 KB (a slot of the
-// kernel's weight ring) and are stored in the order in which a tile consumes them.  Offsets are in halves. ----
+// A_lo x (first N rows) adds the remaining cross term with another K/16.  Every product has N <= 64 (the two 128-wide
+// layers are split into output halves, n0 = 0 / 64) and K <= 64 (wide inputs are split into K panels, k0 = 0 / 64), so
+// a stage is at most 16 KB (a slot of the kernel's weight ring) and an accumulator block at most 128 tensor-memory
+// columns: a CTA needs 256 columns and ~103 KB of shared memory, and TWO tiles stay resident per SM.  Stages are
+// stored in the order in which a tile consumes them.  Offsets are in halves. ----
 struct TcStage { int w_off, src_off, N, Kp, k0, n0, Ksrc, Nsrc; };
+static constexpr int kTcMaxStages = 20;
 struct TcPlan {
     int n_stages, total_halves, seq_len;
     int l1_panels;                          // obs K panels (1 or 2)
-    TcStage st[16];
+    TcStage st[kTcMaxStages];
 };
 
-// narrow = true: every product has N <= 64 (wide layers are split into two halves) and every stage is at most 16 KB —
-// the variant for small teams that keeps two tiles resident per SM (256 TMEM columns and ~107 KB per CTA).
-__host__ __device__ inline TcPlan make_tc_plan(int D, int L, bool narrow = false)
+__host__ __device__ inline TcPlan make_tc_plan(int D, int L)
 {
     const Blob o = blob_layout(D, L);
     TcPlan P;
     int s = 0, off = 0;
-    auto add = [&](int src_off, int N, int Kp, int k0, int Ksrc, int Nsrc) {
-        P.st[s].w_off = off; P.st[s].src_off = src_off; P.st[s].N = N; P.st[s].Kp = Kp; P.st[s].k0 = k0; P.st[s].n0 = 0;
+    auto add = [&](int src_off, int N, int Kp, int k0, int n0, int Ksrc, int Nsrc) {
+        P.st[s].w_off = off; P.st[s].src_off = src_off; P.st[s].N = N; P.st[s].Kp = Kp; P.st[s].k0 = k0; P.st[s].n0 = n0;
         P.st[s].Ksrc = Ksrc; P.st[s].Nsrc = Nsrc;
         off += 2 * N * Kp;
         return s++;
-    };
-    auto add_half = [&](int src_off, int Kp, int k0, int n0, int Ksrc, int Nsrc) {   // rows n0 .. n0+63 of a wide layer
-        const int id = add(src_off, 64, Kp, k0, Ksrc, Nsrc);
-        P.st[id].n0 = n0;
-        return id;
     };
     const int Dp = (D + 15) / 16 * 16;
     P.l1_panels = Dp > 64 ? 2 : 1;
     for (int pnl = 0; pnl < P.l1_panels; ++pnl) {
         const int Kp = pnl == 0 ? (Dp <= 64 ? Dp : 64) : Dp - 64;
-        if (narrow) { add_half(o.enc_w1, Kp, 64 * pnl, 0, D, kH1); add_half(o.enc_w1, Kp, 64 * pnl, 64, D, kH1); }
-        else add(o.enc_w1, kH1, Kp, 64 * pnl, D, kH1);
+        add(o.enc_w1, 64, Kp, 64 * pnl, 0, D, kH1);                      // h[:, 0:64]
+        add(o.enc_w1, 64, Kp, 64 * pnl, 64, D, kH1);                     // h[:, 64:128]
     }
-    add(o.enc_w2, kE, 64, 0, kH1, kE);
-    add(o.enc_w2, kE, 64, 64, kH1, kE);
-    add(o.att_w, kE, 64, 0, kE, kE);
-    for (int l = 0; l < L; ++l) add(o.gcn_w + l * kE * kE, kE, 64, 0, kE, kE);
-    if (narrow) { add_half(o.head_w1, 64, 0, 0, kE, kC1); add_half(o.head_w1, 64, 0, 64, kE, kC1); }
-    else add(o.head_w1, kC1, 64, 0, kE, kC1);
-    add(o.head_w2, kC2, 64, 0, kC1, kC2);
-    add(o.head_w2, kC2, 64, 64, kC1, kC2);
-    add(o.head_w3, kC3, 64, 0, kC2, kC3);
-    add(o.head_w4, 16, 32, 0, kC3, CM_ACTIONS);                          // 5 logits padded to N = 16
+    add(o.enc_w2, kE, 64, 0, 0, kH1, kE);
+    add(o.enc_w2, kE, 64, 64, 0, kH1, kE);
+    add(o.att_w, kE, 64, 0, 0, kE, kE);
+    for (int l = 0; l < L; ++l) add(o.gcn_w + l * kE * kE, kE, 64, 0, 0, kE, kE);
+    add(o.head_w1, 64, 64, 0, 0, kE, kC1);
+    add(o.head_w1, 64, 64, 0, 64, kE, kC1);
+    add(o.head_w2, kC2, 64, 0, 0, kC1, kC2);
+    add(o.head_w2, kC2, 64, 64, 0, kC1, kC2);
+    add(o.head_w3, kC3, 64, 0, 0, kC2, kC3);
+    add(o.head_w4, 16, 32, 0, 0, kC3, CM_ACTIONS);                       // 5 logits padded to N = 16
     P.n_stages = s;
     P.seq_len = s;
     P.total_halves = off;

@@ -1,18 +1,23 @@
 // policy_tc_kernel.cu — CommCategoricalMLPPolicy forward on the 5th-generation tensor cores (tcgen05).
 //
 // Same formula and outputs as policy_kernel.cu (see its header for the reference lines), different machine
-// mapping: a CTA of 512 threads owns a tile of 128 agent rows (whole environments, n <= 64) and runs
-//   * every row-wise dense layer (encoder, attention query, H_l Wg_l, the categorical head) as
+// mapping: a CTA of 512 threads owns a tile of 128 agent rows (whole environments, n <= 64); TWO such CTAs are
+// resident per SM (256 tensor-memory columns and ~103 KB of shared memory each), so that one tile's epilogue
+// (CUDA cores) runs while the other tile's products (tensor cores) and weight copies (TMA engine) are in flight.
+//   * every row-wise dense layer (encoder, attention query, H_l Wg_l, the categorical head) is a series of
 //     tcgen05.mma.kind::f16 (fp16 operands, fp32 accumulators in tensor memory).  fp32-level accuracy is kept by
 //     error compensation: x = x_hi + 2^-12 x_lo with x_hi = fp16(x), x_lo = fp16((x - x_hi) * 4096);
 //     A_hi x [B_hi ; B_lo] (B stacked along N) gives hi*hi and hi*lo in two accumulators with one series of K/16
 //     instructions, A_lo x B_hi adds the other cross term, the epilogue forms acc0 + 2^-12 acc1 (dropped term:
 //     2^-24).  Measured error of one product 1-3e-7 of scale, i.e. fp32 level.  Weights are pre-split, stacked and
-//     pre-arranged in the canonical K-major core-matrix layout by cm_policy_tc_prepare(), so that a layer's
-//     B operand is ONE bulk async copy (TMA engine, mbarrier completion) issued one to two layers ahead;
+//     pre-arranged in the canonical K-major core-matrix layout by cm_policy_tc_prepare(), so that a product's
+//     B operand is ONE bulk async copy (TMA engine, mbarrier completion) issued one to two products ahead;
 //   * the per-environment pieces (n x n scores, softmax, masked renormalisation, aggregation over
-//     neighbours) exactly — not as padded tile products — on the CUDA cores from k-major fp32 copies of E, Q
-//     and H_l Wg_l in shared memory.
+//     neighbours) exactly — not as padded tile products — on the CUDA cores.  Keys (E) and values (H_l Wg_l) share
+//     ONE k-major fp32 buffer in shared memory; everything that is private to a row — the query, the attention
+//     row, the residual copy of E — stays in TENSOR MEMORY: the query is read straight from its accumulator by
+//     all four warps of the row's lane quadrant, the attention row and E are parked in dead accumulator columns
+//     with tcgen05.st and read back with tcgen05.ld.
 // TMEM lane = tile row = thread (row = 32 * (warp % 4) + lane); the four warps that share a lane quadrant
 // split the accumulator columns.  Epilogues read TMEM with tcgen05.ld, apply bias + tanh, and write the next
 // A operand (hi / lo) straight into the canonical layout.
@@ -20,15 +25,13 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "commarl_b200.h"
 #include "common.cuh"
 #include "policy_layout.cuh"
 #include "tc_common.cuh"
 
-#ifndef CM_TC_OBS_PREFETCH
-#define CM_TC_OBS_PREFETCH 0   // measured slower on B200 (C2 0.082 vs 0.076 ms): the held registers cost more than the hidden latency
-#endif
 #ifndef CM_TC_DEBUG
 #define CM_TC_DEBUG 0   // timing experiments only: 1 skip MMAs, 2 skip tanh, 4 skip attention loops, 8 skip weight copies
 #endif
@@ -39,8 +42,12 @@ using namespace tc;
 
 static constexpr int kTcRows = 128;
 static constexpr int kTcThreads = 512;
-static constexpr int kActBytes = 32768, kWBytes = 65536;   // A operand hi|lo (128 x 64 fp16 each); weight ring 2 x 32 KB
-static constexpr int kTPitch = 128;     // floats per k-major row of ET / QT / HWT
+static constexpr int kActBytes = 32768;                     // A operand hi | lo (128 x 64 fp16 each)
+static constexpr int kSlotBytes = 16384, kWBytes = 2 * kSlotBytes;   // weight ring: 2 slots
+static constexpr int kTPitch = 128;                         // floats per k-major row of the key / value buffer
+static constexpr uint32_t kTmemCols = 256;                  // two accumulator blocks of 128 columns
+static constexpr uint32_t kR0 = 0, kR1 = 128;               // accumulator blocks (a product's D block is 2N <= 128 columns)
+static constexpr uint32_t kColM = kR0, kColE = kR0 + 64;    // scratch during the graph convolutions: attention row, residual E
 
 struct TcArgs {
     cm_policy_desc d;
@@ -49,20 +56,6 @@ struct TcArgs {
     int envs_per_tile;
     int64_t n_tiles;
 };
-
-template <int CW>
-__device__ __forceinline__ void ld_cols(uint32_t taddr, float (&v)[CW])
-{
-    static_assert(CW == 8 || CW == 16, "column chunk");
-#pragma unroll
-    for (int c = 0; c < CW; c += 8) {
-        float t[8];
-        tmem_ld8(taddr + (uint32_t)c, t);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[c + i] = t[i];
-    }
-    tmem_ld_wait();
-}
 
 // fp16 split of one value: hi = fp16(x), lo = fp16((x - hi) * 4096)
 __device__ __forceinline__ void split16(float x, __half &hi, __half &lo)
@@ -89,7 +82,7 @@ __device__ __forceinline__ void write_act(unsigned char *act, int Kp, int row, i
 }
 
 // tanh through ex2.approx / rcp.approx: |error| <= ~3e-7 absolute (two units of fp32 rounding at 1.0), an order
-// of magnitude below what the 3xTF32 products contribute and ~4x fewer instructions than tanhf.
+// of magnitude below the tolerance and ~4x fewer instructions than tanhf.
 __device__ __forceinline__ float tanh_fast(float x)
 {
     if (CM_TC_DEBUG & 2) return x;
@@ -130,16 +123,16 @@ __device__ __forceinline__ void issue_layer(uint32_t d_tmem, const unsigned char
 }
 
 // accumulator read-out: acc0 + 2^-12 acc1 for CW columns starting at column `col` of a product whose D block starts at
-// `base` and is 2N columns wide
+// TMEM address `blk` (lane quadrant included) and is 2N columns wide.  Warp-collective (tcgen05.ld is .sync.aligned).
 template <int CW>
-__device__ __forceinline__ void ld_acc(uint32_t lane_addr, uint32_t base, int N, int col, float (&v)[CW])
+__device__ __forceinline__ void ld_acc(uint32_t blk, int N, int col, float (&v)[CW])
 {
     float w[CW];
 #pragma unroll
     for (int c = 0; c < CW; c += 8) {
         float t0[8], t1[8];
-        tmem_ld8(lane_addr + base + (uint32_t)(col + c), t0);
-        tmem_ld8(lane_addr + base + (uint32_t)(N + col + c), t1);
+        tmem_ld8(blk + (uint32_t)(col + c), t0);
+        tmem_ld8(blk + (uint32_t)(N + col + c), t1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) { v[c + i] = t0[i]; w[c + i] = t1[i]; }
     }
@@ -148,44 +141,72 @@ __device__ __forceinline__ void ld_acc(uint32_t lane_addr, uint32_t base, int N,
     for (int c = 0; c < CW; ++c) v[c] = fmaf(w[c], 1.0f / 4096.0f, v[c]);
 }
 
-// Exact per-environment attention row: thread (row, sub) owns the keys jj = sub, sub + 4, ... of its env (at most
-// KT of them), scores = Q[row] . E[key], softmax across the four threads of the row through `red`, result into
-// M^T[jj][row] (which overwrites Q^T once every thread has read it).
+// Exact per-environment attention row.  Thread (row, sub) owns the KT consecutive keys sub * KT .. of its env
+// (4 * KT >= n); scores = Q[row] . E[key] with the query read from its accumulator block in tensor memory (16 columns
+// at a time) and the keys from the k-major buffer.  The softmax needs ONE exchange between the four threads of a row:
+// each publishes the maximum m_s and the sum l_s = sum exp(score - m_s) of its keys, after the barrier
+// p = exp(score - m_s) * exp(m_s - M) / sum_s l_s exp(m_s - M).  Returns with every thread past the barrier (the
+// query block and the keys are dead); the caller parks the probabilities sc[] in tensor memory.
 template <int KT>
-__device__ __forceinline__ void scores_softmax(float *QT, const float *ET, float *red, int row, int j0, int sub, int n, bool valid)
+__device__ __forceinline__ void scores_softmax(uint32_t lane_addr, const float *KV, float *red, float *attn_row, int row, int j0,
+                                               int sub, int n, bool valid)
 {
+    const int k0 = sub * KT;
+    const int nk = valid ? min(KT, n - k0) : 0;        // may be <= 0
     float sc[KT];
-    const int nk = valid ? (n - sub + 3) / 4 : 0;
 #pragma unroll
     for (int t = 0; t < KT; ++t) sc[t] = 0.0f;
-    if (nk > 0 && !(CM_TC_DEBUG & 4)) {
-#pragma unroll 4
-        for (int k = 0; k < 64; ++k) {
-            const float qv = QT[k * kTPitch + row];
-            const float *er = ET + k * kTPitch + j0 + sub;
+    const float *er0 = KV + j0 + k0;
+    for (int c = 0; c < 64; c += 16) {                 // warp-uniform trip count: the TMEM loads are collective
+        float q[16];
+        ld_acc<16>(lane_addr + kR0, 64, c, q);
+        if (nk > 0 && !(CM_TC_DEBUG & 4)) {
 #pragma unroll
-            for (int t = 0; t < KT; ++t)
-                if (t < nk) sc[t] = fmaf(qv, er[4 * t], sc[t]);
+            for (int kk = 0; kk < 16; ++kk) {
+                const float *er = er0 + (c + kk) * kTPitch;
+#pragma unroll
+                for (int t = 0; t < KT; ++t)
+                    if (t < nk) sc[t] = fmaf(q[kk], er[t], sc[t]);
+            }
         }
     }
     float mx = -INFINITY;
 #pragma unroll
     for (int t = 0; t < KT; ++t)
         if (t < nk) mx = fmaxf(mx, sc[t]);
-    red[sub * kTPitch + row] = mx;
-    __syncthreads();
-    mx = fmaxf(fmaxf(red[row], red[kTPitch + row]), fmaxf(red[2 * kTPitch + row], red[3 * kTPitch + row]));
     float sum = 0.0f;
 #pragma unroll
-    for (int t = 0; t < KT; ++t)
-        if (t < nk) { sc[t] = expf(sc[t] - mx); sum += sc[t]; }
+    for (int t = 0; t < KT; ++t) {
+        sc[t] = t < nk ? __expf(sc[t] - mx) : 0.0f;
+        sum += sc[t];
+    }
+    red[sub * kTPitch + row] = mx;
     red[(4 + sub) * kTPitch + row] = sum;
-    __syncthreads();                      // everybody has read QT: it becomes M^T [n][128]
-    const float z = red[4 * kTPitch + row] + red[5 * kTPitch + row] + red[6 * kTPitch + row] + red[7 * kTPitch + row];
+    fence_before_thread_sync();
+    __syncthreads();                      // every thread has read the query block and the keys
+    fence_after_thread_sync();
+    float gm = -INFINITY;
 #pragma unroll
-    for (int t = 0; t < KT; ++t)
-        if (t < nk) QT[(sub + 4 * t) * kTPitch + row] = sc[t] / z;
-    __syncthreads();
+    for (int s = 0; s < 4; ++s) gm = fmaxf(gm, red[s * kTPitch + row]);
+    float z = 0.0f;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const float ms = red[s * kTPitch + row];
+        z += ms > -INFINITY ? red[(4 + s) * kTPitch + row] * __expf(ms - gm) : 0.0f;
+    }
+    const float scale = nk > 0 ? __expf(mx - gm) / z : 0.0f;
+#pragma unroll
+    for (int t = 0; t < KT; ++t) sc[t] *= scale;
+    if (attn_row) {                       // unmasked softmax (agent_infos['attention_weights'])
+#pragma unroll
+        for (int t = 0; t < KT; ++t)
+            if (t < nk) attn_row[k0 + t] = sc[t];
+    }
+    if constexpr (KT <= 8) tmem_st<KT>(lane_addr + kColM + (uint32_t)k0, sc);
+    else {
+        tmem_st<8>(lane_addr + kColM + (uint32_t)k0, sc);
+        tmem_st<8>(lane_addr + kColM + (uint32_t)k0 + 8u, sc + 8);
+    }
 }
 
 // bias offsets inside the shared-memory bias table
@@ -193,15 +214,14 @@ static constexpr int kBEnc1 = 0, kBEnc2 = 128, kBGcn = 192, kBH1 = 448, kBH2 = 5
 
 struct MmaOp { uint32_t dcol, acc; };
 
-__global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A)
+__global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *ACT = smem;
-    unsigned char *WB = smem + kActBytes;                                // weight ring: 2 slots of 32 KB
-    float *ET = reinterpret_cast<float *>(smem + kActBytes + kWBytes);   // [64][128] E^T   (keys, residual)
-    float *QT = ET + 64 * kTPitch;                                       // [64][128] Q^T, then M^T [n][128]
-    float *HWT = QT + 64 * kTPitch;                                      // [64][128] (H_l Wg_l)^T; softmax scratch before that
-    float *bias_s = HWT + 64 * kTPitch;                                  // [704]
+    unsigned char *WB = smem + kActBytes;                                // weight ring: 2 slots of 16 KB
+    float *KV = reinterpret_cast<float *>(smem + kActBytes + kWBytes);   // [64][128] E^T (keys), then (H_l Wg_l)^T (values)
+    float *red = KV + 64 * kTPitch;                                      // [8][128] softmax max / sum exchange
+    float *bias_s = red + 8 * kTPitch;                                   // [704]
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + kBiasFloats); // [0],[1] weight slot full, [2] MMAs done
     uint32_t *tmem_s = reinterpret_cast<uint32_t *>(bars + 3);
 
@@ -215,7 +235,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int quad = warp & 3, sub = warp >> 2, row = quad * 32 + lane;
 
-    if (warp == 0) tmem_alloc(tmem_s, 512);
+    if (warp == 0) tmem_alloc(tmem_s, kTmemCols);
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -238,13 +258,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
     fence_after_thread_sync();
     const uint32_t tmem = *tmem_s;
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    const uint32_t DA = 0, DB = 256;          // accumulator column regions (a product's D block is 2N columns wide)
     uint32_t m_phase = 0;
     bool ok = true;
 
-    // ---- weight stream: the stages of the plan are consumed in order, tile after tile; thread 0 keeps the
+    // ---- weight stream: the stages of the plan are consumed in order, tile after tile; warp 0 keeps the
     // two ring slots full (a slot is refilled as soon as the product that read it has completed) ----
-    const uint32_t my_tiles = (uint32_t)((A.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const int n_tiles = (int)A.n_tiles, n_envs = (int)io.n_envs;
+    const uint32_t my_tiles = (uint32_t)((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
     const uint32_t total_blocks = my_tiles * (uint32_t)P.seq_len;
     uint32_t consumed = 0;                    // blocks consumed so far (uniform)
     uint32_t issued = 0, issued_si = 0;       // warp 0: blocks requested so far, and their stage index
@@ -257,7 +277,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
                     if (CM_TC_DEBUG & 8) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[slot])) : "memory"); }
                     else {
                         mbar_expect_tx(&bars[slot], bytes);
-                        bulk_g2s(WB + slot * 32768u, tcw + st.w_off, bytes, &bars[slot]);
+                        bulk_g2s(WB + slot * (uint32_t)kSlotBytes, tcw + st.w_off, bytes, &bars[slot]);
                     }
                 }
                 __syncwarp();
@@ -268,7 +288,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
     };
     issue_loads();
     int si = 0;                               // stage index inside the current tile (uniform)
-    // all threads: ACT is written -> thread 0 issues one product per op, each against the next weight block ->
+    // all threads: ACT is written -> warp 0 issues one product per op, each against the next weight block ->
     // everybody waits for their completion -> the freed ring slots are refilled
     auto run_mma = [&](int nops, MmaOp op0, MmaOp op1) {
 #ifdef CM_TC_TRACE
@@ -287,7 +307,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
                 ok = mbar_wait(&bars[b & 1u], (b >> 1) & 1u) && ok;
                 const TcStage &st = P.st[si + i];
                 const MmaOp op = i ? op1 : op0;
-                issue_layer(tmem + op.dcol, ACT, WB + (b & 1u) * 32768u, st.N, st.Kp, op.acc);
+                issue_layer(tmem + op.dcol, ACT, WB + (b & 1u) * (uint32_t)kSlotBytes, st.N, st.Kp, op.acc);
             }
             if (elect_one()) mma_commit(&bars[2]);
             __syncwarp();
@@ -311,202 +331,240 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
     };
     const MmaOp none = {0u, 0u};
 
-    // observation panel `pnl` (64 columns, the first one Kp0 wide) of tile `tl` -> registers, 128 * Kp / 512 <= 16 per thread
-    float ov[16];
-    bool ov_ready = false;
-    auto load_obs_panel = [&](float (&dst)[16], int64_t tl, int pnl) {
-        const int Kp = P.st[pnl].Kp, kofs = 64 * pnl, total = kTcRows * Kp;
-        const int64_t e0 = tl * A.envs_per_tile;
-        const int rws = (int)min((int64_t)A.envs_per_tile, io.n_envs - e0) * n;
-        const float *src = io.obs + e0 * n * D;
+    // dense epilogue of a 64-wide product: this thread's 16 columns -> bias, tanh -> next A operand (K panel of 64)
+    auto epi64 = [&](uint32_t blk, int bias0) {
+        float v[16];
+        ld_acc<16>(lane_addr + blk, 64, 16 * sub, v);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int e = tid + q * kTcThreads;
-            const int r = e / Kp, k = e - r * Kp;
-            dst[q] = (e < total && r < rws && kofs + k < D) ? __ldg(src + (size_t)r * D + kofs + k) : 0.0f;
+        for (int c = 0; c < 16; ++c) v[c] = tanh_fast(v[c] + bias_s[bias0 + 16 * sub + c]);
+        write_act<16>(ACT, 64, row, 16 * sub, v);
+    };
+    // neighbour mask of this row for layer l (dist_adj & channels[l], comm_base_net.py:101)
+    uint32_t m0 = 0u, m1 = 0u;
+    auto load_mask = [&](int env, int il, int l, bool valid) {
+        m0 = m1 = 0u;
+        if (valid) {
+            m0 = m1 = 0xFFFFFFFFu;
+            if (io.adj_bits) {
+                const uint32_t *p = io.adj_bits + (size_t)(env * n + il) * W;
+                m0 &= __ldg(p);
+                if (W > 1) m1 &= __ldg(p + 1);
+            }
+            if (io.chan_bits) {
+                const uint32_t *p = io.chan_bits + (size_t)((env * L + l) * n + il) * W;
+                m0 &= __ldg(p);
+                if (W > 1) m1 &= __ldg(p + 1);
+            }
         }
     };
 
-    for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-        const int64_t env0 = tile * A.envs_per_tile;
-        const int envs = (int)min((int64_t)A.envs_per_tile, io.n_envs - env0);
+    // ---- observation staging: a tile's observations are ONE contiguous block of rows * D floats.  It is copied
+    // with cp.async (no registers held, 16-byte copies where source and destination are congruent mod 16) into the
+    // key/value + softmax scratch area while that area is idle (from the head of the previous tile on), and converted
+    // to the fp16 hi/lo A operand when the tile starts.  Staged element i of the block lives at stage[(src & 3) + i].
+    float *stage = KV;
+    constexpr int kStageFloats = (64 + 8) * kTPitch - 4;
+    auto stage_obs = [&](int tl) {
+        const int e0 = tl * A.envs_per_tile;
+        const int rws = min(A.envs_per_tile, n_envs - e0) * n;
+        const float *src = io.obs + (size_t)e0 * n * D;
+        const int a = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
+        const int ns = min(rws * D, kStageFloats);
+        const int nq = (a + ns + 3) >> 2;
+        const uint32_t sbase = smem_u32(stage);
+        for (int q = tid; q < nq; q += kTcThreads) {
+            const int i0 = 4 * q - a;                   // block element of the quad's first float
+            if (i0 >= 0 && i0 + 4 <= ns)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * (uint32_t)q), "l"(src + i0) : "memory");
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (i0 + j >= 0 && i0 + j < ns)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbase + 4u * (uint32_t)(4 * q + j)), "l"(src + i0 + j)
+                                     : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if ((int)blockIdx.x < n_tiles) stage_obs((int)blockIdx.x);
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int env0 = tile * A.envs_per_tile;
+        const int envs = min(A.envs_per_tile, n_envs - env0);
         const int rows = envs * n;
-        const int64_t row0 = env0 * n;
+        const int row0 = env0 * n;
         const bool valid = row < rows;
         const int el = valid ? row / n : 0, il = row - el * n, j0 = el * n;
-        const int64_t env = env0 + el, g = row0 + row;
+        const int env = env0 + el, g = row0 + row;
         si = 0;
-        // neighbour masks of this row for every layer: fetched now, used after the attention (global latency hidden)
-        uint32_t msk0[CM_MAX_LAYERS], msk1[CM_MAX_LAYERS];
-#pragma unroll
-        for (int l = 0; l < CM_MAX_LAYERS; ++l) {
-            uint32_t m0 = 0u, m1 = 0u;
-            if (valid && l < L) {
-                m0 = m1 = 0xFFFFFFFFu;
-                if (io.adj_bits) {
-                    const uint32_t *p = io.adj_bits + (env * n + il) * W;
-                    m0 &= __ldg(p);
-                    if (W > 1) m1 &= __ldg(p + 1);
-                }
-                if (io.chan_bits) {
-                    const uint32_t *p = io.chan_bits + ((env * L + l) * n + il) * W;
-                    m0 &= __ldg(p);
-                    if (W > 1) m1 &= __ldg(p + 1);
-                }
-            }
-            msk0[l] = m0;
-            msk1[l] = m1;
-        }
 
-        // ---------------- encoder layer 1: obs panels -> DA[0:128] ----------------
-        for (int pnl = 0; pnl < P.l1_panels; ++pnl) {
-            const int Kp = P.st[si].Kp;
-            const uint32_t lo_off = (uint32_t)kTcRows * Kp * 2;
-            // all global loads first (independent, 128 * Kp / 512 <= 16 per thread), then the split + stores; the first
-            // panel was already fetched into `ov` while the previous tile was in its head layers
-            const int total = kTcRows * Kp;
-            if (pnl > 0 || !ov_ready) load_obs_panel(ov, tile, pnl);
-            ov_ready = false;
+        // ---------------- encoder layer 1: obs panels -> h[:, 0:64] in R0, h[:, 64:128] in R1 ----------------
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                   // the staged observations of this tile are visible
+        {
+            const float *src = io.obs + (size_t)row0 * D;
+            const int a = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
+            const int total_f = rows * D, ns = min(total_f, kStageFloats);
+            for (int pnl = 0; pnl < P.l1_panels; ++pnl) {
+                const int Kp = P.st[si].Kp, kofs = 64 * pnl, kg = Kp >> 3;          // kg = 2, 4, 6 or 8 groups of 8 columns
+                const uint32_t lo_off = (uint32_t)kTcRows * Kp * 2, inv = (65536u + (uint32_t)kg - 1u) / (uint32_t)kg;
+                for (int e8 = tid; e8 < kTcRows * kg; e8 += kTcThreads) {           // one group of 8 columns of one row
+                    const int r = (int)(((uint32_t)e8 * inv) >> 16), k8 = (e8 - r * kg) << 3;
+                    __align__(16) __half h[8], l[8];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int e = tid + q * kTcThreads;
-                if (e < total) {
-                    const int r = e / Kp, k = e - r * Kp;
-                    __half h, l;
-                    split16(ov[q], h, l);
-                    const uint32_t off = canon_off16(r, k, Kp);
-                    *reinterpret_cast<__half *>(ACT + off) = h;
-                    *reinterpret_cast<__half *>(ACT + lo_off + off) = l;
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = kofs + k8 + j, i = r * D + k;
+                        float x = 0.0f;
+                        if (r < rows && k < D) x = i < ns ? stage[a + i] : __ldg(src + i);
+                        split16(x, h[j], l[j]);
+                    }
+                    const uint32_t off = canon_off16(r, k8, Kp);
+                    *reinterpret_cast<uint4 *>(ACT + off) = *reinterpret_cast<const uint4 *>(h);
+                    *reinterpret_cast<uint4 *>(ACT + lo_off + off) = *reinterpret_cast<const uint4 *>(l);
                 }
+                run_mma(2, MmaOp{kR0, (uint32_t)pnl}, MmaOp{kR1, (uint32_t)pnl});
             }
-            run_mma(1, MmaOp{DA, (uint32_t)pnl}, none);
         }
-        // ---------------- encoder layer 2 (K = 128 as two panels of h) -> DB[0:64] ----------------
-        for (int p = 0; p < 2; ++p) {
-            float v[16];
-            ld_acc<16>(lane_addr, DA, 128, 64 * p + 16 * sub, v);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = tanh_fast(v[c] + bias_s[kBEnc1 + 64 * p + 16 * sub + c]);
-            write_act<16>(ACT, 64, row, 16 * sub, v);
-            run_mma(1, MmaOp{DB, (uint32_t)p}, none);
-        }
-        // ---------------- E = tanh(. + b2): k-major fp32 copy + A operand; Q -> DA[0:64], H_0 Wg_0 -> DA[64:128] ----------------
+        // ---------------- encoder layer 2 (K = 128 as the two panels of h) -> R0 ----------------
+        epi64(kR0, kBEnc1);
+        run_mma(1, MmaOp{kR0, 0u}, none);
+        epi64(kR1, kBEnc1 + 64);
+        run_mma(1, MmaOp{kR0, 1u}, none);
+        // ---------------- E = tanh(. + b2): keys (k-major fp32) + A operand; Q -> R0, H_0 Wg_0 -> R1 ----------------
         {
             float v[16];
-            ld_acc<16>(lane_addr, DB, 64, 16 * sub, v);
+            ld_acc<16>(lane_addr + kR0, 64, 16 * sub, v);
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 v[c] = tanh_fast(v[c] + bias_s[kBEnc2 + 16 * sub + c]);
-                ET[(16 * sub + c) * kTPitch + row] = v[c];
+                KV[(16 * sub + c) * kTPitch + row] = v[c];
             }
             write_act<16>(ACT, 64, row, 16 * sub, v);
-            run_mma(2, MmaOp{DA, 0u}, MmaOp{DA + 128, 0u});
+            load_mask(env, il, 0, valid);
+            run_mma(2, MmaOp{kR0, 0u}, MmaOp{kR1, 0u});
         }
-        // ---------------- scores, softmax (exact per environment, CUDA cores) ----------------
+        // ---------------- scores, softmax (exact per environment, CUDA cores); attention row -> TMEM ----------------
         {
-            float v[16];
-            ld_acc<16>(lane_addr, DA, 64, 16 * sub, v);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) QT[(16 * sub + c) * kTPitch + row] = v[c];
-        }
-        __syncthreads();
-        // scores, row softmax -> M^T; QT is overwritten by M^T once every thread has read it
-        switch (n <= 4 ? 1 : (n <= 8 ? 2 : (n <= 16 ? 4 : (n <= 32 ? 8 : 16)))) {
-        case 1: scores_softmax<1>(QT, ET, HWT, row, j0, sub, n, valid); break;
-        case 2: scores_softmax<2>(QT, ET, HWT, row, j0, sub, n, valid); break;
-        case 4: scores_softmax<4>(QT, ET, HWT, row, j0, sub, n, valid); break;
-        case 8: scores_softmax<8>(QT, ET, HWT, row, j0, sub, n, valid); break;
-        default: scores_softmax<16>(QT, ET, HWT, row, j0, sub, n, valid); break;
-        }
-        const float *MT = QT;
-        if (io.attention) {               // unmasked softmax (agent_infos['attention_weights'])
-            float *dst = io.attention + row0 * n;
-            for (int e = tid; e < rows * n; e += kTcThreads) {
-                const int r = e / n, jl = e - r * n;
-                dst[e] = MT[jl * kTPitch + r];
+            float *attn_row = (io.attention && valid) ? io.attention + (size_t)g * n : nullptr;
+            switch (n <= 4 ? 1 : (n <= 8 ? 2 : (n <= 16 ? 4 : (n <= 32 ? 8 : 16)))) {
+            case 1: scores_softmax<1>(lane_addr, KV, red, attn_row, row, j0, sub, n, valid); break;
+            case 2: scores_softmax<2>(lane_addr, KV, red, attn_row, row, j0, sub, n, valid); break;
+            case 4: scores_softmax<4>(lane_addr, KV, red, attn_row, row, j0, sub, n, valid); break;
+            case 8: scores_softmax<8>(lane_addr, KV, red, attn_row, row, j0, sub, n, valid); break;
+            default: scores_softmax<16>(lane_addr, KV, red, attn_row, row, j0, sub, n, valid); break;
             }
         }
-        // H_0 Wg_0 out of tensor memory (the softmax scratch is dead now)
+        // H_0 Wg_0 replaces the keys (everybody is past the softmax barrier)
         {
             float v[16];
-            ld_acc<16>(lane_addr, DA + 128, 64, 16 * sub, v);
-            __syncthreads();
+            ld_acc<16>(lane_addr + kR1, 64, 16 * sub, v);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) HWT[(16 * sub + c) * kTPitch + row] = v[c];
+            for (int c = 0; c < 16; ++c) KV[(16 * sub + c) * kTPitch + row] = v[c];
+            tmem_st_wait();
+            fence_before_thread_sync();
+            __syncthreads();              // values and attention rows (TMEM scratch) are visible
+            fence_after_thread_sync();
         }
-        __syncthreads();
         // ---------------- graph convolutions ----------------
         for (int l = 0; l < L; ++l) {
             // A_l = M * Range * chan_l / (sum + 1e-12); out = A_l (H_l Wg_l)   (comm_base_net.py:101-103, graph_conv_module.py:51-72)
-            uint32_t m0 = 0u, m1 = 0u;
-#pragma unroll
-            for (int q = 0; q < CM_MAX_LAYERS; ++q)
-                if (q == l) { m0 = msk0[q]; m1 = msk1[q]; }
             float acc[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
             float den = 0.0f;
-            const int nn = (valid && !(CM_TC_DEBUG & 4)) ? n : 0;
-            for (int jj = 0; jj < nn; ++jj) {
-                const uint32_t bit = ((jj < 32 ? m0 : m1) >> (jj & 31)) & 1u;
-                const float a = bit ? MT[jj * kTPitch + row] : 0.0f;
-                den += a;
-                const float *hw = HWT + (16 * sub) * kTPitch + j0 + jj;
+            const float *hw0 = KV + (16 * sub) * kTPitch + j0;
+            for (int c0 = 0; c0 < n; c0 += 8) {          // warp-uniform: the TMEM loads are collective
+                float a8[8];
+                tmem_ld8(lane_addr + kColM + (uint32_t)c0, a8);
+                tmem_ld_wait();
+                if (!(CM_TC_DEBUG & 4)) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) acc[c] = fmaf(a, hw[c * kTPitch], acc[c]);
+                    for (int j = 0; j < 8; ++j) {
+                        const int jj = c0 + j;
+                        if (jj < n) {
+                            const uint32_t bit = ((jj < 32 ? m0 : m1) >> (jj & 31)) & 1u;
+                            const float a = bit ? a8[j] : 0.0f;
+                            den += a;
+                            const float *hw = hw0 + jj;
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) acc[c] = fmaf(a, hw[c * kTPitch], acc[c]);
+                        }
+                    }
+                }
             }
             const float inv = 1.0f / (den + 1e-12f);
             float v[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                v[c] = tanh_fast(acc[c] * inv + bias_s[kBGcn + l * 64 + 16 * sub + c]);
-                if (l + 1 == L && d.residual) v[c] += ET[(16 * sub + c) * kTPitch + row];   // X = E + H_L
+            for (int c = 0; c < 16; ++c) v[c] = tanh_fast(acc[c] * inv + bias_s[kBGcn + l * 64 + 16 * sub + c]);
+            if (d.residual) {                             // X = E + H_L (comm_base_net.py:105-106)
+                // E is still in the A operand buffer (this thread wrote these 16 columns itself) until the first layer's
+                // output replaces it; with more than one layer it is parked in tensor memory meanwhile
+                if (l == 0) {
+                    float ev[16];
+#pragma unroll
+                    for (int g8 = 0; g8 < 16; g8 += 8) {
+                        const uint32_t off = canon_off16(row, 16 * sub + g8, 64);
+                        const uint4 hq = *reinterpret_cast<const uint4 *>(ACT + off);
+                        const uint4 lq = *reinterpret_cast<const uint4 *>(ACT + (uint32_t)kTcRows * 64 * 2 + off);
+                        const __half2 *hh = reinterpret_cast<const __half2 *>(&hq), *ll = reinterpret_cast<const __half2 *>(&lq);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 hf = __half22float2(hh[i]), lf = __half22float2(ll[i]);
+                            ev[g8 + 2 * i] = fmaf(lf.x, 1.0f / 4096.0f, hf.x);
+                            ev[g8 + 2 * i + 1] = fmaf(lf.y, 1.0f / 4096.0f, hf.y);
+                        }
+                    }
+                    if (L == 1) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) v[c] += ev[c];
+                    } else {
+                        tmem_st<8>(lane_addr + kColE + (uint32_t)(16 * sub), ev);
+                        tmem_st<8>(lane_addr + kColE + (uint32_t)(16 * sub + 8), ev + 8);
+                        tmem_st_wait();
+                    }
+                } else if (l + 1 == L) {
+                    float ev[16];
+                    tmem_ld8(lane_addr + kColE + (uint32_t)(16 * sub), *reinterpret_cast<float(*)[8]>(ev));
+                    tmem_ld8(lane_addr + kColE + (uint32_t)(16 * sub + 8), *reinterpret_cast<float(*)[8]>(ev + 8));
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) v[c] += ev[c];
+                }
             }
             write_act<16>(ACT, 64, row, 16 * sub, v);
             if (l + 1 < L) {
-                run_mma(1, MmaOp{DB, 0u}, none);
+                load_mask(env, il, l + 1, valid);
+                run_mma(1, MmaOp{kR1, 0u}, none);         // every thread is done with the values of layer l here
                 float hv[16];
-                ld_acc<16>(lane_addr, DB, 64, 16 * sub, hv);
-                __syncthreads();          // every thread is done reading HWT of layer l
+                ld_acc<16>(lane_addr + kR1, 64, 16 * sub, hv);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) HWT[(16 * sub + c) * kTPitch + row] = hv[c];
+                for (int c = 0; c < 16; ++c) KV[(16 * sub + c) * kTPitch + row] = hv[c];
                 __syncthreads();
             }
         }
         // ---------------- categorical head ----------------
-        if (CM_TC_OBS_PREFETCH && tile + gridDim.x < A.n_tiles) {       // next tile's first observation panel: in flight during the head
-            load_obs_panel(ov, tile + gridDim.x, 0);
-            ov_ready = true;
-        }
-        run_mma(1, MmaOp{DA, 0u}, none);                                          // 64 -> 128
-        for (int p = 0; p < 2; ++p) {                                             // 128 -> 64 as two K panels
-            float v[16];
-            ld_acc<16>(lane_addr, DA, 128, 64 * p + 16 * sub, v);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = tanh_fast(v[c] + bias_s[kBH1 + 64 * p + 16 * sub + c]);
-            write_act<16>(ACT, 64, row, 16 * sub, v);
-            run_mma(1, MmaOp{DB, (uint32_t)p}, none);
-        }
-        {                                                                         // 64 -> 32
-            float v[16];
-            ld_acc<16>(lane_addr, DB, 64, 16 * sub, v);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = tanh_fast(v[c] + bias_s[kBH2 + 16 * sub + c]);
-            write_act<16>(ACT, 64, row, 16 * sub, v);
-            run_mma(1, MmaOp{DA, 0u}, none);
-        }
+        run_mma(2, MmaOp{kR0, 0u}, MmaOp{kR1, 0u});                               // 64 -> 128 as two output halves
+        if (tile + (int)gridDim.x < n_tiles) stage_obs(tile + (int)gridDim.x);            // keys / values are dead: next tile's obs
+        uint32_t tk = 0u, ep = 0u;                                                // sampling keys: latency hidden by the head
+        if (sub == 0 && valid && io.actions && !d.greedy && !io.sample_u) { tk = __ldg(io.tick + env); ep = __ldg(io.episode + env); }
+        epi64(kR0, kBH1);                                                         // 128 -> 64 as two K panels
+        run_mma(1, MmaOp{kR0, 0u}, none);
+        epi64(kR1, kBH1 + 64);
+        run_mma(1, MmaOp{kR0, 1u}, none);
+        epi64(kR0, kBH2);                                                         // 64 -> 32
+        run_mma(1, MmaOp{kR1, 0u}, none);
         {                                                                         // 32 -> 5 (padded to 16)
             float v[8];
-            ld_acc<8>(lane_addr, DA, 32, 8 * sub, v);
+            ld_acc<8>(lane_addr + kR1, 32, 8 * sub, v);
 #pragma unroll
             for (int c = 0; c < 8; ++c) v[c] = tanh_fast(v[c] + bias_s[kBH3 + 8 * sub + c]);
             write_act<8>(ACT, 32, row, 8 * sub, v);
-            run_mma(1, MmaOp{DB, 0u}, none);
+            run_mma(1, MmaOp{kR0, 0u}, none);
         }
         // ---------------- softmax, availability mask, renormalise, sample ----------------
         if (sub == 0) {
             float lg8[8];
-            ld_acc<8>(lane_addr, DB, 16, 0, lg8);
+            ld_acc<8>(lane_addr + kR0, 16, 0, lg8);
             if (valid) {
                 float lg[CM_ACTIONS], pr[CM_ACTIONS];
                 float mx = -INFINITY;
@@ -521,8 +579,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
                 for (int a = 0; a < CM_ACTIONS; ++a) { pr[a] = ((av >> a) & 1u) ? pr[a] / sum : 0.0f; msum += pr[a]; }
 #pragma unroll
                 for (int a = 0; a < CM_ACTIONS; ++a) pr[a] = pr[a] / msum;
-                if (io.logits) for (int a = 0; a < CM_ACTIONS; ++a) io.logits[g * CM_ACTIONS + a] = lg[a];
-                if (io.probs) for (int a = 0; a < CM_ACTIONS; ++a) io.probs[g * CM_ACTIONS + a] = pr[a];
+                if (io.logits) for (int a = 0; a < CM_ACTIONS; ++a) io.logits[(size_t)g * CM_ACTIONS + a] = lg[a];
+                if (io.probs) for (int a = 0; a < CM_ACTIONS; ++a) io.probs[(size_t)g * CM_ACTIONS + a] = pr[a];
                 if (io.actions) {
                     int act;
                     if (d.greedy) {
@@ -533,7 +591,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
                         if (io.sample_u) u = io.sample_u[g];
                         else {
                             const uint4 blk = philox4x32_10(
-                                make_uint4((uint32_t)(d.env_id0 + env), io.tick[env], kStreamAct | (io.episode[env] << 8), (uint32_t)(il >> 2)),
+                                make_uint4((uint32_t)(d.env_id0 + env), tk, kStreamAct | (ep << 8), (uint32_t)(il >> 2)),
                                 make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32)));
                             const uint32_t w = (il & 3) == 0 ? blk.x : ((il & 3) == 1 ? blk.y : ((il & 3) == 2 ? blk.z : blk.w));
                             u = u24(w);
@@ -549,15 +607,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const TcArgs A
                 }
             }
         }
-        // the next tile's first MMA must not overwrite accumulators that are still being read
-        fence_before_thread_sync();
-        __syncthreads();
-        fence_after_thread_sync();
+        // the next tile's first products overwrite R0 / R1 only after the barrier inside run_mma, which the threads that
+        // are still reading the logits have not reached yet
     }
     if (!ok && io.error_flag) atomicExch(io.error_flag, (int)CM_ECUDA);
     fence_before_thread_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
+    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -571,7 +627,7 @@ __global__ void tc_prepare_kernel(const float *__restrict__ w, __half *__restric
         for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
             const int r = e / st.Kp, k = e - r * st.Kp;
             float v = 0.0f;
-            if (r < st.Nsrc && st.k0 + k < st.Ksrc) v = w[st.src_off + (size_t)(st.k0 + k) * st.Nsrc + r];
+            if (st.n0 + r < st.Nsrc && st.k0 + k < st.Ksrc) v = w[st.src_off + (size_t)(st.k0 + k) * st.Nsrc + st.n0 + r];
             const __half h = __float2half_rn(v);
             const __half l = __float2half_rn((v - __half2float(h)) * 4096.0f);
             // canonical K-major layout over the stacked 2N rows: hi rows [0, N), lo rows [N, 2N)
@@ -582,12 +638,13 @@ __global__ void tc_prepare_kernel(const float *__restrict__ w, __half *__restric
     }
 }
 
-static size_t tc_smem_bytes() { return (size_t)kActBytes + kWBytes + 3 * 64 * kTPitch * 4 + kBiasFloats * 4 + 64; }
+static size_t tc_smem_bytes() { return (size_t)kActBytes + kWBytes + (64 + 8) * kTPitch * 4 + kBiasFloats * 4 + 64; }
 
 int launch_policy_tc(const cm_policy_desc *desc, const cm_policy_io *io, cudaStream_t stream)
 {
     if (!io->tc_weights) return CM_EINVAL;
     if (desc->n_agents > 64 || desc->obs_dim > 128) return CM_EUNSUPPORTED;
+    if (io->n_envs * desc->n_agents > (int64_t)1 << 23) return CM_EUNSUPPORTED;      // 32-bit element indices inside the kernel
     TcArgs A;
     A.d = *desc;
     A.io = *io;
@@ -603,9 +660,15 @@ int launch_policy_tc(const cm_policy_desc *desc, const cm_policy_io *io, cudaStr
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ECUDA);
         cudaError_t e = cudaFuncSetAttribute(policy_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
+        e = cudaFuncSetAttribute(policy_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
         cache.dev = dev; cache.sms = sms;
     }
-    const int grid = (int)(A.n_tiles < cache.sms ? A.n_tiles : cache.sms);   // persistent: one CTA per SM
+    int slots = 2 * cache.sms;                                                // persistent: two CTAs per SM
+#ifdef CM_TC_TRACE
+    if (const char *ev = getenv("CM_TC_SLOTS")) slots = atoi(ev) * cache.sms;   // experiments only
+#endif
+    const int grid = (int)(A.n_tiles < slots ? A.n_tiles : slots);
     policy_tc_kernel<<<grid, kTcThreads, smem, stream>>>(A);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);

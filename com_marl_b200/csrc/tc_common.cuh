@@ -170,6 +170,31 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// registers -> TMEM: this warp's 32 lanes x NC (1, 2, 4 or 8) consecutive fp32 columns starting at column `col`.
+// Tensor memory doubles as a per-row scratch pad: a lane (= tile row) is private to the row, and every warp of the
+// row's lane quadrant can read it back, so row-private exchanges between those warps need no shared memory.
+template <int NC>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const float *v)
+{
+    static_assert(NC == 1 || NC == 2 || NC == 4 || NC == 8, "tmem_st width");
+    if constexpr (NC == 1)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(__float_as_uint(v[0])) : "memory");
+    else if constexpr (NC == 2)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                     "r"(__float_as_uint(v[1]))
+                     : "memory");
+    else if constexpr (NC == 4)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                     "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+                     : "memory");
+    else
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                     "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                     "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                     : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // Error-compensated TF32 split: hi = x rounded to nearest TF32 (low 13 bits zero), lo = the exact remainder
 // x - hi, itself rounded to nearest TF32.  Rounding to NEAREST (cvt.rna) instead of letting the tensor core
 // truncate keeps the representation errors unbiased, so they accumulate like a random walk over K instead of
