@@ -90,7 +90,7 @@ __host__ __device__ inline TcPlan make_tc_plan(int D, int L)
     add(o.head_w2, kC2, 64, 0, 0, kC1, kC2);
     add(o.head_w2, kC2, 64, 64, 0, kC1, kC2);
     add(o.head_w3, kC3, 64, 0, 0, kC2, kC3);
-    add(o.head_w4, 16, 32, 0, 0, kC3, CM_ACTIONS);                       // 5 logits padded to N = 16
+    // (the last layer, 32 -> 5, runs on the CUDA cores in exact fp32)
     P.n_stages = s;
     P.seq_len = s;
     P.total_halves = off;

@@ -210,9 +210,16 @@ __device__ __forceinline__ void scores_softmax(uint32_t lane_addr, const float *
 }
 
 // bias offsets inside the shared-memory bias table
-static constexpr int kBEnc1 = 0, kBEnc2 = 128, kBGcn = 192, kBH1 = 448, kBH2 = 576, kBH3 = 640, kBH4 = 672, kBiasFloats = 704;
+static constexpr int kBEnc1 = 0, kBEnc2 = 128, kBGcn = 192, kBH1 = 448, kBH2 = 576, kBH3 = 640, kBH4 = 672, kW4 = 680, kBiasFloats = 680 + kC3 * CM_ACTIONS;   // kW4: head_w4 [32][5] k-major
 
-struct MmaOp { uint32_t dcol, acc; };
+struct MmaOp { uint32_t dcol, acc, abuf; };   // accumulator block, accumulate flag, A operand buffer (0: ACT, 1: ACT2)
+
+#ifdef CM_TC_TRACE
+#define CM_TP(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && io.workspace && tile == (int)blockIdx.x) \
+    reinterpret_cast<long long *>(io.workspace)[320 + (slot)] = clock64(); } while (0)
+#else
+#define CM_TP(slot) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A)
 {
@@ -220,6 +227,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
     unsigned char *ACT = smem;
     unsigned char *WB = smem + kActBytes;                                // weight ring: 2 slots of 16 KB
     float *KV = reinterpret_cast<float *>(smem + kActBytes + kWBytes);   // [64][128] E^T (keys), then (H_l Wg_l)^T (values)
+    unsigned char *ACT2 = smem + kActBytes + kWBytes;                    // second A operand (aliases KV while it is idle)
     float *red = KV + 64 * kTPitch;                                      // [8][128] softmax max / sum exchange
     float *bias_s = red + 8 * kTPitch;                                   // [704]
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + kBiasFloats); // [0],[1] weight slot full, [2] MMAs done
@@ -251,6 +259,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         else if (i < kBH3) v = wts[o.head_b2 + i - kBH2];
         else if (i < kBH4) v = wts[o.head_b3 + i - kBH3];
         else if (i < kBH4 + CM_ACTIONS) v = wts[o.head_b4 + i - kBH4];
+        else if (i >= kW4) v = wts[o.head_w4 + i - kW4];
         bias_s[i] = v;
     }
     fence_before_thread_sync();
@@ -307,7 +316,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                 ok = mbar_wait(&bars[b & 1u], (b >> 1) & 1u) && ok;
                 const TcStage &st = P.st[si + i];
                 const MmaOp op = i ? op1 : op0;
-                issue_layer(tmem + op.dcol, ACT, WB + (b & 1u) * (uint32_t)kSlotBytes, st.N, st.Kp, op.acc);
+                issue_layer(tmem + op.dcol, op.abuf ? ACT2 : ACT, WB + (b & 1u) * (uint32_t)kSlotBytes, st.N, st.Kp, op.acc);
             }
             if (elect_one()) mma_commit(&bars[2]);
             __syncwarp();
@@ -329,15 +338,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         si += nops;
         issue_loads();
     };
-    const MmaOp none = {0u, 0u};
+    const MmaOp none = {0u, 0u, 0u};
 
     // dense epilogue of a 64-wide product: this thread's 16 columns -> bias, tanh -> next A operand (K panel of 64)
-    auto epi64 = [&](uint32_t blk, int bias0) {
+    auto epi64 = [&](uint32_t blk, int bias0, unsigned char *dst) {
         float v[16];
         ld_acc<16>(lane_addr + blk, 64, 16 * sub, v);
 #pragma unroll
         for (int c = 0; c < 16; ++c) v[c] = tanh_fast(v[c] + bias_s[bias0 + 16 * sub + c]);
-        write_act<16>(ACT, 64, row, 16 * sub, v);
+        write_act<16>(dst, 64, row, 16 * sub, v);
     };
     // neighbour mask of this row for layer l (dist_adj & channels[l], comm_base_net.py:101)
     uint32_t m0 = 0u, m1 = 0u;
@@ -399,8 +408,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         si = 0;
 
         // ---------------- encoder layer 1: obs panels -> h[:, 0:64] in R0, h[:, 64:128] in R1 ----------------
+        CM_TP(18);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                                   // the staged observations of this tile are visible
+        CM_TP(19);
         {
             const float *src = io.obs + (size_t)row0 * D;
             const int a = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
@@ -422,14 +433,14 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                     *reinterpret_cast<uint4 *>(ACT + off) = *reinterpret_cast<const uint4 *>(h);
                     *reinterpret_cast<uint4 *>(ACT + lo_off + off) = *reinterpret_cast<const uint4 *>(l);
                 }
-                run_mma(2, MmaOp{kR0, (uint32_t)pnl}, MmaOp{kR1, (uint32_t)pnl});
+                run_mma(2, MmaOp{kR0, (uint32_t)pnl, 0u}, MmaOp{kR1, (uint32_t)pnl, 0u});
             }
         }
         // ---------------- encoder layer 2 (K = 128 as the two panels of h) -> R0 ----------------
-        epi64(kR0, kBEnc1);
-        run_mma(1, MmaOp{kR0, 0u}, none);
-        epi64(kR1, kBEnc1 + 64);
-        run_mma(1, MmaOp{kR0, 1u}, none);
+        // (the second K panel of the A operand lives in the idle key / value buffer, so both products issue together)
+        epi64(kR0, kBEnc1, ACT);
+        epi64(kR1, kBEnc1 + 64, ACT2);
+        run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR0, 1u, 1u});
         // ---------------- E = tanh(. + b2): keys (k-major fp32) + A operand; Q -> R0, H_0 Wg_0 -> R1 ----------------
         {
             float v[16];
@@ -441,9 +452,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
             }
             write_act<16>(ACT, 64, row, 16 * sub, v);
             load_mask(env, il, 0, valid);
-            run_mma(2, MmaOp{kR0, 0u}, MmaOp{kR1, 0u});
+            run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR1, 0u, 0u});
         }
         // ---------------- scores, softmax (exact per environment, CUDA cores); attention row -> TMEM ----------------
+        CM_TP(0);
         {
             float *attn_row = (io.attention && valid) ? io.attention + (size_t)g * n : nullptr;
             switch (n <= 4 ? 1 : (n <= 8 ? 2 : (n <= 16 ? 4 : (n <= 32 ? 8 : 16)))) {
@@ -455,6 +467,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
             }
         }
         // H_0 Wg_0 replaces the keys (everybody is past the softmax barrier)
+        CM_TP(1);
         {
             float v[16];
             ld_acc<16>(lane_addr + kR1, 64, 16 * sub, v);
@@ -466,6 +479,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
             fence_after_thread_sync();
         }
         // ---------------- graph convolutions ----------------
+        CM_TP(2);
         for (int l = 0; l < L; ++l) {
             // A_l = M * Range * chan_l / (sum + 1e-12); out = A_l (H_l Wg_l)   (comm_base_net.py:101-103, graph_conv_module.py:51-72)
             float acc[16];
@@ -492,6 +506,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                     }
                 }
             }
+            CM_TP(3 + 4 * l);
             const float inv = 1.0f / (den + 1e-12f);
             float v[16];
 #pragma unroll
@@ -532,9 +547,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                 }
             }
             write_act<16>(ACT, 64, row, 16 * sub, v);
+            CM_TP(4 + 4 * l);
             if (l + 1 < L) {
                 load_mask(env, il, l + 1, valid);
-                run_mma(1, MmaOp{kR1, 0u}, none);         // every thread is done with the values of layer l here
+                run_mma(1, MmaOp{kR1, 0u, 0u}, none);         // every thread is done with the values of layer l here
+                CM_TP(5 + 4 * l);
                 float hv[16];
                 ld_acc<16>(lane_addr + kR1, 64, 16 * sub, hv);
 #pragma unroll
@@ -543,33 +560,52 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
             }
         }
         // ---------------- categorical head ----------------
-        run_mma(2, MmaOp{kR0, 0u}, MmaOp{kR1, 0u});                               // 64 -> 128 as two output halves
-        if (tile + (int)gridDim.x < n_tiles) stage_obs(tile + (int)gridDim.x);            // keys / values are dead: next tile's obs
+        run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR1, 0u, 0u});                       // 64 -> 128 as two output halves
         uint32_t tk = 0u, ep = 0u;                                                // sampling keys: latency hidden by the head
         if (sub == 0 && valid && io.actions && !d.greedy && !io.sample_u) { tk = __ldg(io.tick + env); ep = __ldg(io.episode + env); }
-        epi64(kR0, kBH1);                                                         // 128 -> 64 as two K panels
-        run_mma(1, MmaOp{kR0, 0u}, none);
-        epi64(kR1, kBH1 + 64);
-        run_mma(1, MmaOp{kR0, 1u}, none);
-        epi64(kR0, kBH2);                                                         // 64 -> 32
-        run_mma(1, MmaOp{kR1, 0u}, none);
-        {                                                                         // 32 -> 5 (padded to 16)
-            float v[8];
+        epi64(kR0, kBH1, ACT);                                                    // 128 -> 64: two K panels, issued together
+        epi64(kR1, kBH1 + 64, ACT2);
+        run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR0, 1u, 1u});
+        if (tile + (int)gridDim.x < n_tiles) stage_obs(tile + (int)gridDim.x);    // keys / values / ACT2 are dead: next tile's obs
+        epi64(kR0, kBH2, ACT);                                                    // 64 -> 32
+        run_mma(1, MmaOp{kR1, 0u, 0u}, none);
+        {   // 32 -> 5 on the CUDA cores (exact fp32): this thread's 8 inputs -> 5 partial logits, parked in tensor memory
+            float v[8], part[8];
             ld_acc<8>(lane_addr + kR1, 32, 8 * sub, v);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v[c] = tanh_fast(v[c] + bias_s[kBH3 + 8 * sub + c]);
-            write_act<8>(ACT, 32, row, 8 * sub, v);
-            run_mma(1, MmaOp{kR0, 0u}, none);
+            for (int a = 0; a < 8; ++a) part[a] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                v[c] = tanh_fast(v[c] + bias_s[kBH3 + 8 * sub + c]);
+                const float *w4 = bias_s + kW4 + (8 * sub + c) * CM_ACTIONS;
+#pragma unroll
+                for (int a = 0; a < CM_ACTIONS; ++a) part[a] = fmaf(v[c], w4[a], part[a]);
+            }
+            tmem_st<8>(lane_addr + kR0 + (uint32_t)(8 * sub), part);
+            tmem_st_wait();
+            fence_before_thread_sync();
+            __syncthreads();
+            fence_after_thread_sync();
         }
         // ---------------- softmax, availability mask, renormalise, sample ----------------
+        CM_TP(16);
         if (sub == 0) {
             float lg8[8];
-            ld_acc<8>(lane_addr + kR0, 16, 0, lg8);
+#pragma unroll
+            for (int a = 0; a < 8; ++a) lg8[a] = a < CM_ACTIONS ? bias_s[kBH4 + a] : 0.0f;
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+                float pq[8];
+                tmem_ld8(lane_addr + kR0 + (uint32_t)(8 * s4), pq);
+                tmem_ld_wait();
+#pragma unroll
+                for (int a = 0; a < 8; ++a) lg8[a] += pq[a];
+            }
             if (valid) {
                 float lg[CM_ACTIONS], pr[CM_ACTIONS];
                 float mx = -INFINITY;
 #pragma unroll
-                for (int a = 0; a < CM_ACTIONS; ++a) { lg[a] = lg8[a] + bias_s[kBH4 + a]; mx = fmaxf(mx, lg[a]); }
+                for (int a = 0; a < CM_ACTIONS; ++a) { lg[a] = lg8[a]; mx = fmaxf(mx, lg[a]); }
                 float sum = 0.0f;
 #pragma unroll
                 for (int a = 0; a < CM_ACTIONS; ++a) { pr[a] = expf(lg[a] - mx); sum += pr[a]; }
@@ -607,6 +643,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                 }
             }
         }
+        CM_TP(17);
         // the next tile's first products overwrite R0 / R1 only after the barrier inside run_mma, which the threads that
         // are still reading the logits have not reached yet
     }

@@ -31,3 +31,9 @@ for i,(a,b,c,d) in enumerate(t):
     epi = (a - prev3) if prev3 is not None else 0
     print(f"{i:3d} {epi:6d} {b-a:6d} {c-b if c else 0:6d} {d-b:6d} {d-(prev3 if prev3 else a):7d}")
     prev3 = d
+
+x = pol._workspace.cpu().numpy().view(np.int64)[320:344]
+names = {0:'scores start',1:'softmax done',2:'HW0->KV + barrier',3:'aggr l0',4:'epi l0',5:'mma HW1',6:'HW1->KV',7:'aggr l1',8:'epi l1',16:'head done',17:'final done',18:'tile start',19:'obs staged'}
+base = x[18]
+for k in sorted(names):
+    if x[k]: print(f"{names[k]:20s} {x[k]-base:8d}")
