@@ -90,36 +90,29 @@ __device__ __forceinline__ float tanh_fast(float x)
     return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
-// one converged warp: D[:, 0:N] (+)= A_hi B_hi^T, D[:, N:2N] (+)= A_hi B_lo^T + A_lo B_hi^T.  All lanes run the loop
-// (descriptors stay warp-uniform), the elected lane issues.
+// one converged warp: D[:, 0:N] (+)= A_hi B_hi^T, D[:, N:2N] (+)= A_hi B_lo^T + A_lo B_hi^T.  All lanes run the code
+// (descriptors stay in uniform registers); the instructions are predicated on the leader lane.
 __device__ __forceinline__ void issue_layer(uint32_t d_tmem, const unsigned char *act, const unsigned char *wblk, int N, int Kp,
-                                            uint32_t accumulate)
+                                            uint32_t accumulate, uint32_t leader)
 {
+    if (CM_TC_DEBUG & 1) return;
     const uint32_t a_hi = smem_u32(act), a_lo = a_hi + (uint32_t)kTcRows * Kp * 2, b = smem_u32(wblk);
-    const int nk = Kp >> 4;
+    const int nk = Kp >> 4;                     // 1 .. 4 instructions of K = 16; the next slice starts 256 bytes (16 >> 4) further
+    const uint64_t db = make_smem_desc16(b, Kp, 0);
     {   // A_hi x [B_hi ; B_lo]  (N' = 2N)
         const uint32_t idesc = make_idesc_f16(kTcRows, 2 * N);
-        uint64_t da = make_smem_desc16(a_hi, Kp, 0), db = make_smem_desc16(b, Kp, 0);
-        uint32_t acc = accumulate;
-#pragma unroll 2
-        for (int j = 0; j < nk; ++j) {
-            if (!(CM_TC_DEBUG & 1) && elect_one()) mma_f16(d_tmem, da, db, idesc, acc);
-            acc = 1;
-            da += 16;     // next K = 16 slice: start address + 256 bytes (>> 4)
-            db += 16;
-        }
+        const uint64_t da = make_smem_desc16(a_hi, Kp, 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nk) mma_f16_pred(d_tmem, da + 16 * j, db + 16 * j, idesc, j ? 1u : accumulate, leader);
     }
     {   // A_lo x B_hi  (N' = N) into the cross-term accumulator
         const uint32_t idesc = make_idesc_f16(kTcRows, N);
-        uint64_t da = make_smem_desc16(a_lo, Kp, 0), db = make_smem_desc16(b, Kp, 0);
-#pragma unroll 2
-        for (int j = 0; j < nk; ++j) {
-            if (!(CM_TC_DEBUG & 1) && elect_one()) mma_f16(d_tmem + (uint32_t)N, da, db, idesc, 1u);
-            da += 16;
-            db += 16;
-        }
+        const uint64_t da = make_smem_desc16(a_lo, Kp, 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nk) mma_f16_pred(d_tmem + (uint32_t)N, da + 16 * j, db + 16 * j, idesc, 1u, leader);
     }
-    __syncwarp();
 }
 
 // accumulator read-out: acc0 + 2^-12 acc1 for CW columns starting at column `col` of a product whose D block starts at
@@ -216,7 +209,7 @@ struct MmaOp { uint32_t dcol, acc, abuf; };   // accumulator block, accumulate f
 
 #ifdef CM_TC_TRACE
 #define CM_TP(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && io.workspace && tile == (int)blockIdx.x) \
-    reinterpret_cast<long long *>(io.workspace)[320 + (slot)] = clock64(); } while (0)
+    reinterpret_cast<long long *>(io.workspace)[600 + (slot)] = clock64(); } while (0)
 #else
 #define CM_TP(slot) do { } while (0)
 #endif
@@ -301,7 +294,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
     // everybody waits for their completion -> the freed ring slots are refilled
     auto run_mma = [&](int nops, MmaOp op0, MmaOp op1) {
 #ifdef CM_TC_TRACE
-        long long tr0 = clock64(), tr1, tr2 = 0, tr3;
+        long long tr0 = clock64(), tr1, tr2 = 0, tr3, trw[2] = {0, 0};
 #endif
         fence_proxy_async();
         fence_before_thread_sync();
@@ -309,29 +302,37 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
 #ifdef CM_TC_TRACE
         tr1 = clock64();
 #endif
-        if (warp == 0) {                 // whole warp, converged: waits for the weights, elected lane issues
+        if (warp == 0) {                 // whole warp, converged: waits for the weights, the leader lane issues
             fence_after_thread_sync();
+            const uint32_t leader = elect_one() ? 1u : 0u;
             for (int i = 0; i < nops; ++i) {
                 const uint32_t b = consumed + (uint32_t)i;
                 ok = mbar_wait(&bars[b & 1u], (b >> 1) & 1u) && ok;
+#ifdef CM_TC_TRACE
+                trw[i] = clock64();
+#endif
                 const TcStage &st = P.st[si + i];
                 const MmaOp op = i ? op1 : op0;
-                issue_layer(tmem + op.dcol, op.abuf ? ACT2 : ACT, WB + (b & 1u) * (uint32_t)kSlotBytes, st.N, st.Kp, op.acc);
+                issue_layer(tmem + op.dcol, op.abuf ? ACT2 : ACT, WB + (b & 1u) * (uint32_t)kSlotBytes, st.N, st.Kp, op.acc, leader);
             }
-            if (elect_one()) mma_commit(&bars[2]);
+            mma_commit_pred(&bars[2], leader);
             __syncwarp();
 #ifdef CM_TC_TRACE
             tr2 = clock64();
 #endif
+            // only this warp polls the completion barrier; the other fifteen sleep in the CTA barrier below and leave
+            // the issue slots to the co-resident tile
+            ok = mbar_wait(&bars[2], m_phase) && ok;
+            fence_before_thread_sync();
         }
-        ok = mbar_wait(&bars[2], m_phase) && ok;
         m_phase ^= 1;
+        __syncthreads();
         fence_after_thread_sync();
 #ifdef CM_TC_TRACE
         tr3 = clock64();
         if (blockIdx.x == 0 && tid == 0 && consumed < 64 && io.workspace) {
-            long long *tb = reinterpret_cast<long long *>(io.workspace) + 4 * consumed;
-            tb[0] = tr0; tb[1] = tr1; tb[2] = tr2; tb[3] = tr3;
+            long long *tb = reinterpret_cast<long long *>(io.workspace) + 8 * consumed;
+            tb[0] = tr0; tb[1] = tr1; tb[2] = tr2; tb[3] = tr3; tb[4] = trw[0]; tb[5] = trw[1];
         }
 #endif
         consumed += (uint32_t)nops;

@@ -22,17 +22,16 @@ def run():
     N.check('f', N.lib().cm_policy_forward(C.byref(desc), C.byref(io), N.stream_ptr()))
 for _ in range(3): run()
 torch.cuda.synchronize()
-t = pol._workspace.cpu().numpy().view(np.int64).reshape(-1,4)[:48]
-t0 = t[0,0]
+t = pol._workspace.cpu().numpy().view(np.int64)[:512].reshape(-1,8)[:48]
 prev3 = None
-print("stage  epi  sync  issue  mmawait(after sync)   total")
-for i,(a,b,c,d) in enumerate(t):
+print("stage  epi  sync  wwait0 issue0 wwait1 issue1+commit  mmawait  total")
+for i,(a,b,c,d,w0,w1,_,_) in enumerate(t):
     if a == 0: continue
     epi = (a - prev3) if prev3 is not None else 0
-    print(f"{i:3d} {epi:6d} {b-a:6d} {c-b if c else 0:6d} {d-b:6d} {d-(prev3 if prev3 else a):7d}")
+    if w1: print(f"{i:3d} {epi:6d} {b-a:6d} {w0-b:6d} {'':6s} {w1-w0:6d}(wait1+issue0) {c-w1:6d} {d-c:6d} {d-(prev3 if prev3 else a):7d}")
+    else: print(f"{i:3d} {epi:6d} {b-a:6d} {w0-b:6d} {c-w0:6d} {'':6s} {'':6s} {d-c:6d} {d-(prev3 if prev3 else a):7d}")
     prev3 = d
-
-x = pol._workspace.cpu().numpy().view(np.int64)[320:344]
+x = pol._workspace.cpu().numpy().view(np.int64)[600:624]
 names = {0:'scores start',1:'softmax done',2:'HW0->KV + barrier',3:'aggr l0',4:'epi l0',5:'mma HW1',6:'HW1->KV',7:'aggr l1',8:'epi l1',16:'head done',17:'final done',18:'tile start',19:'obs staged'}
 base = x[18]
 for k in sorted(names):
