@@ -235,7 +235,8 @@ def run_b200_arm(args):
     steps = max(ring, (args.steps // ring) * ring)
     warm = max(3 * ring, ((args.warmup + ring - 1) // ring) * ring)
     pol = make_policy(spec, device=dev)
-    eng = RolloutEngine(spec, pol, B, device=dev, env_id0=rank * B, ring=ring, use_graph=True)
+    groups = args.groups if args.groups > 0 else (4 if n <= 64 else 1)
+    eng = RolloutEngine(spec, pol, B, device=dev, env_id0=rank * B, ring=ring, use_graph=True, groups=groups)
     eng.reset()
     eng.run(warm)                                   # untimed: first chunk eager, graph captured on the second
     torch.cuda.synchronize(dev)
@@ -264,17 +265,22 @@ def run_b200_arm(args):
     # ---------------- per-kernel durations: CUDA events around a CUDA graph of 32 launches of ONE kernel ----------------
     # (events around single eager launches would include the host's launch gaps, which are of the order of these kernels)
     eng._carry()
-    t, e = eng.traj, eng.env
+    t = eng.traj
     reps = 32
 
+    # the launches of the timed region are per env group: time exactly that launch size (group 0), alone
+    gb0, gb1 = eng._ranges[0]
+    Bk, ek = gb1 - gb0, eng._envs[0]
+
     def policy_once(k):
-        pol.act_device(t["obs"][k], t["adj_bits"][k], t["chan_bits"][k], tick=e.tick, episode=e.episode, probs=t["probs"][k],
-                       actions=t["actions"][k], env_id0=e.env_id0)
+        pol.act_device(t["obs"][k, gb0:gb1], t["adj_bits"][k, gb0:gb1], t["chan_bits"][k, gb0:gb1], tick=ek.tick, episode=ek.episode,
+                       probs=t["probs"][k, gb0:gb1], actions=t["actions"][k, gb0:gb1], env_id0=ek.env_id0)
 
     def env_once(k):
-        e.step(t["actions"][k], out=dict(obs=t["obs"][k + 1], adj_bits=t["adj_bits"][k + 1], chan_bits=t["chan_bits"][k + 1],
-                                         ave_deg=t["ave_deg"][k + 1], reward=t["reward"][k], done=t["done"][k],
-                                         counts=t["counts"][k], prey_alive_out=t["prey_alive_out"][k], success_out=t["success"][k]))
+        ek.step(t["actions"][k, gb0:gb1],
+                out=dict(obs=t["obs"][k + 1, gb0:gb1], adj_bits=t["adj_bits"][k + 1, gb0:gb1], chan_bits=t["chan_bits"][k + 1, gb0:gb1],
+                         ave_deg=t["ave_deg"][k + 1, gb0:gb1], reward=t["reward"][k, gb0:gb1], done=t["done"][k, gb0:gb1],
+                         counts=t["counts"][k, gb0:gb1], prey_alive_out=t["prey_alive_out"][k, gb0:gb1], success_out=t["success"][k, gb0:gb1]))
 
     def time_graph(fn):
         for k in range(2):
@@ -344,8 +350,8 @@ def run_b200_arm(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.config, {}) if B == CONFIGS[args.config][6] else {}
     except Exception:
         pass
-    flops = policy_flops_per_agent(Dobs, n, L) * B * n
-    env_bytes = env_bytes_per_agent_step(spec) * B * n
+    flops = policy_flops_per_agent(Dobs, n, L) * Bk * n               # per launch (one env group)
+    env_bytes = env_bytes_per_agent_step(spec) * Bk * n
     tc = pol.uses_tensor_cores()
     kname = "policy_tc_kernel" if tc else ("policy_small_kernel" if n <= 64 else "policy_large_kernel")
     kdesc = ("the kernel issues A_hi x [B_hi;B_lo] and A_lo x B_hi in fp16 per algorithmic product (error compensation) on K "
@@ -354,7 +360,7 @@ def run_b200_arm(args):
     # what the tensor pipe actually executes per 128-row tile: 3 passes over the padded dense layers
     Dp = (Dobs + 15) // 16 * 16
     dense_mac = Dp * 128 + 128 * 64 + 64 * 64 * (1 + L) + 64 * 128 + 128 * 64 + 64 * 32 + 32 * 16
-    tc_flops = (3 * 2 * dense_mac * 128 * ((B * n + (128 // n) * n - 1) // ((128 // n) * n))) if tc else 0
+    tc_flops = (3 * 2 * dense_mac * 128 * ((Bk * n + (128 // n) * n - 1) // ((128 // n) * n))) if tc else 0
     pol_tflops = flops / (pol_ms * 1e-3) / 1e12
     env_gbs = env_bytes / (env_ms * 1e-3) / 1e9
     line = {
@@ -364,7 +370,7 @@ def run_b200_arm(args):
                   if tc else "f32 FFMA (policy)") + " + u8/u16/u64 bit rows (env, comm)",
         "data": "synthetic",
         "config": {"workload": WORKLOAD_TEXT[args.config], "config": args.config, "envs_per_gpu": B, "n_agents": n,
-                   "obs_dim": Dobs, "ring_slots": ring,
+                   "obs_dim": Dobs, "ring_slots": ring, "env_groups": len(eng._ranges),
                    "l2": f"inputs are produced by the previous step; the trajectory ring ({ring + 1} slots, "
                          f"{(ring + 1) * B * n * Dobs * 4 / 2**20:.0f} MiB of observations) is larger than the 126 MB L2, "
                          "so no slot survives a ring cycle in cache",
@@ -375,10 +381,13 @@ def run_b200_arm(args):
         "roofline": {"bound": "tensor", "kernel": kname,
                      "achieved": pol_tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": pol_tflops / tc_peak, "traffic": traffic.get(kname),
                      "peak_source": peak_src + ", bf16 dense sustained; " + kdesc,
-                     "flop_per_launch": flops, "tensor_flop_issued_per_launch": tc_flops, "ms_per_launch": pol_ms, "share_of_step": pol_ms / (pol_ms + env_ms)},
+                     "flop_per_launch": flops, "tensor_flop_issued_per_launch": tc_flops, "ms_per_launch": pol_ms, "share_of_step": pol_ms / (pol_ms + env_ms),
+                     "envs_per_launch": Bk, "launches_per_step": len(eng._ranges),
+                     "note": "one launch = one env group, timed alone (CUDA graph of 32 launches); in the timed region the groups' chains overlap on separate streams"},
         "roofline_env": {"bound": "hbm", "kernel": "env_kernel", "achieved": env_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": env_gbs / hbm_peak, "traffic": traffic.get("env_kernel"), "bytes_per_launch": env_bytes, "ms_per_launch": env_ms,
-                         "bytes_per_agent_step": env_bytes_per_agent_step(spec), "peak_source": peak_src},
+                         "bytes_per_agent_step": env_bytes_per_agent_step(spec), "peak_source": peak_src, "envs_per_launch": Bk,
+                         "launches_per_step": len(eng._ranges)},
         "clocks": clock_info,
         "episode_stats": D.summarize_stats(stats, spec.scenario, n),
     }
@@ -414,6 +423,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the config's)")
     ap.add_argument("--ring", type=int, default=64, help="trajectory ring slots = steps per CUDA graph")
     ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--groups", type=int, default=0, help="independent env groups, each a policy->step chain on its own stream (0: 4 for teams <= 64, else 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.out = _quiet_stdout()

@@ -161,6 +161,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, uint32_t spins = 1u << 22)
 {
     const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t i = 0; i < spins; ++i) {
         uint32_t ok;
         asm volatile(

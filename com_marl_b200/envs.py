@@ -86,6 +86,31 @@ class BatchedEnv:
         self._spawn_episodes = 0
         self._io_cache = {}
 
+    _SLICED = ("agent_pos", "prey_pos", "prey_alive", "visited", "step_count", "total_capture", "success", "episode", "tick",
+               "ge_state", "obs", "reward", "done", "counts", "prey_alive_out", "success_out", "adj_bits", "chan_bits", "ave_deg",
+               "stats", "_spawn_agent", "_spawn_prey")
+
+    def slice(self, b0: int, b1: int) -> "BatchedEnv":
+        """View of the envs [b0, b1): shares every buffer with this object (all arrays are env-major, so the slices are
+        contiguous), with its own descriptor (global env id offset) and state struct.  Independent env groups can then be
+        stepped by separate launches on separate streams (RolloutEngine(groups=...)); the random streams are keyed by the
+        global env id, so results do not depend on the grouping."""
+        v = object.__new__(BatchedEnv)
+        v.__dict__.update(self.__dict__)
+        v.B, v.env_id0 = int(b1 - b0), self.env_id0 + int(b0)
+        for k in self._SLICED:
+            t = getattr(self, k, None)
+            setattr(v, k, None if t is None else t[b0:b1])
+        v.desc = self.spec.to_desc(N.ptr(self._wall), N.ptr(self._lut), env_id0=v.env_id0)
+        v.state = N.EnvState()
+        v.state.n_envs = v.B
+        for k in ("agent_pos", "prey_pos", "prey_alive", "visited", "step_count", "total_capture", "success",
+                  "episode", "tick", "ge_state"):
+            setattr(v.state, k, N.ptr(getattr(v, k)))
+        v._io_cache = {}
+        v._pin = None
+        return v
+
     # ---- injected streams (parity mode) ---------------------------------------------------------
     def set_spawn_queue(self, spawn_agent, spawn_prey=None):
         """spawn_agent int [B,E,n,2], spawn_prey int [B,E,p,2]: positions used by each env's e-th reset

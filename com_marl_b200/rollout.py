@@ -33,10 +33,22 @@ def make_policy(spec: ScenarioSpec, device="cuda", seed: Optional[int] = None, t
 
 class RolloutEngine:
     def __init__(self, spec: ScenarioSpec, policy: CommCategoricalMLPPolicy, n_envs: int, device="cuda", env_id0: int = 0,
-                 ring: int = 8, record_attention: bool = False, greedy: bool = False, use_graph: bool = True):
+                 ring: int = 8, record_attention: bool = False, greedy: bool = False, use_graph: bool = True,
+                 groups: int = 1):
         self.spec, self.policy, self.B = spec, policy, int(n_envs)
         self.device = torch.device(device)
         self.env = BatchedEnv(spec, n_envs, device=device, env_id0=env_id0, auto_reset=True)
+        # Env groups: the envs are independent, so G contiguous groups form G independent policy -> step -> policy ...
+        # chains.  Each chain runs on its own stream (forked / joined inside the captured graph): there is no device-wide
+        # barrier between a step of one group and the next step of another, so partially filled waves of one launch
+        # are covered by the launches of the other groups.  Results are identical for every G (global env ids key the
+        # random streams).  Large teams (n > 64) share one policy scratch buffer and stay in a single group.
+        G = max(1, min(int(groups), self.B)) if spec.n_agents <= 64 else 1
+        self.groups = G
+        cuts = [self.B * g // G for g in range(G + 1)]
+        self._ranges = [(cuts[g], cuts[g + 1]) for g in range(G) if cuts[g + 1] > cuts[g]]
+        self._envs = [self.env] if len(self._ranges) == 1 else [self.env.slice(b0, b1) for b0, b1 in self._ranges]
+        self._streams = None
         self.K, self.greedy, self.use_graph = int(ring), bool(greedy), bool(use_graph)
         e, K, B, dev = self.env, self.K, self.B, self.device
         n, L, W, D, p = e.n, e.L, e.W, e.D, max(e.p, 1)
@@ -59,15 +71,22 @@ class RolloutEngine:
         self.kernel_launches = 0
 
     # ---- single iteration --------------------------------------------------------------------------
-    def _iteration(self, k: int):
-        t, e = self.traj, self.env
-        self.policy.act_device(t["obs"][k], t["adj_bits"][k], t["chan_bits"][k], tick=e.tick, episode=e.episode,
-                               greedy=self.greedy, probs=t["probs"][k], actions=t["actions"][k],
-                               attention=t["attention"][k] if "attention" in t else None, env_id0=e.env_id0)
-        e.step(t["actions"][k], out=dict(obs=t["obs"][k + 1], adj_bits=t["adj_bits"][k + 1], chan_bits=t["chan_bits"][k + 1],
-                                         ave_deg=t["ave_deg"][k + 1], reward=t["reward"][k], done=t["done"][k],
-                                         counts=t["counts"][k], prey_alive_out=t["prey_alive_out"][k],
-                                         success_out=t["success"][k]))
+    def _iteration(self, k: int, g: int = None):
+        """policy forward + sampling, then env step, for ring slot k (group g of the envs, or all groups one after another)"""
+        if g is None:
+            for gi in range(len(self._ranges)):
+                self._iteration(k, gi)
+            return
+        t, e = self.traj, self._envs[g]
+        b0, b1 = self._ranges[g]
+        self.policy.act_device(t["obs"][k, b0:b1], t["adj_bits"][k, b0:b1], t["chan_bits"][k, b0:b1], tick=e.tick, episode=e.episode,
+                               greedy=self.greedy, probs=t["probs"][k, b0:b1], actions=t["actions"][k, b0:b1],
+                               attention=t["attention"][k, b0:b1] if "attention" in t else None, env_id0=e.env_id0)
+        e.step(t["actions"][k, b0:b1],
+               out=dict(obs=t["obs"][k + 1, b0:b1], adj_bits=t["adj_bits"][k + 1, b0:b1], chan_bits=t["chan_bits"][k + 1, b0:b1],
+                        ave_deg=t["ave_deg"][k + 1, b0:b1], reward=t["reward"][k, b0:b1], done=t["done"][k, b0:b1],
+                        counts=t["counts"][k, b0:b1], prey_alive_out=t["prey_alive_out"][k, b0:b1],
+                        success_out=t["success"][k, b0:b1]))
         self.kernel_launches += 2
 
     def _carry(self):
@@ -82,8 +101,24 @@ class RolloutEngine:
         self.steps_done = 0
 
     def _chunk_eager(self):
-        for k in range(self.K):
-            self._iteration(k)
+        if len(self._ranges) == 1:
+            for k in range(self.K):
+                self._iteration(k, 0)
+            return
+        # one chain per group, each on its own stream (fork / join on events: capturable)
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in self._ranges]
+        main = torch.cuda.current_stream(self.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for g, st in enumerate(self._streams):
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                for k in range(self.K):
+                    self._iteration(k, g)
+                join = torch.cuda.Event()
+                join.record(st)
+            main.wait_event(join)
 
     def _capture(self):
         g = torch.cuda.CUDAGraph()
@@ -102,7 +137,7 @@ class RolloutEngine:
             if self._graph is None:
                 self._capture()
             self._graph.replay()
-            self.kernel_launches += 2 * self.K
+            self.kernel_launches += 2 * self.K * len(self._ranges)
         else:
             self._chunk_eager()
             self._warm = True
