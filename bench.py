@@ -151,7 +151,9 @@ def run_reference_arm(args):
     n = params["n_agents"]
     # bounded sample: every "step" of this arm is one policy+env iteration over envs_per_proc envs on every core
     envs_per_proc = max(4, min(256, 20000 // max(n, 1)))
-    steps_cpu = max(10, min(args.steps, 200))    # bounded: the whole run stays within a few minutes
+    # bounded: a single-process pilot fixes the step count so that every core works for ~15 s (the run stays within minutes)
+    pilot_rate, _ = cpu_port_throughput(args.config, 1, envs_per_proc, 10)
+    steps_cpu = int(max(10, min(200000, 15.0 * pilot_rate / (envs_per_proc * n))))
     t0 = time.perf_counter()
     rate, agent_steps = cpu_port_throughput(args.config, cores, envs_per_proc, steps_cpu)
     wall = time.perf_counter() - t0
@@ -299,9 +301,55 @@ def run_b200_arm(args):
         torch.cuda.synchronize(dev)
         return a.elapsed_time(b) / (3 * reps)
 
-    pol_ms = time_graph(policy_once)
-    env_ms = time_graph(env_once)
-    eng.steps_done += 4 * reps
+    pol_alone_ms = time_graph(policy_once)
+    env_alone_ms = time_graph(env_once)
+
+    def time_groups(which):
+        """all env groups' launches of one kernel, concurrently on the groups' streams like in the timed region: the
+        wall time of one such round / number of groups = the launch duration under the concurrency it really runs at"""
+        G = len(eng._ranges)
+        if G == 1:
+            return pol_alone_ms if which == "policy" else env_alone_ms
+
+        def round_(k):
+            if which == "policy":
+                for g, (b0, b1) in enumerate(eng._ranges):
+                    eg = eng._envs[g]
+                    with torch.cuda.stream(eng._streams[g]):
+                        pol.act_device(t["obs"][k, b0:b1], t["adj_bits"][k, b0:b1], t["chan_bits"][k, b0:b1], tick=eg.tick,
+                                       episode=eg.episode, probs=t["probs"][k, b0:b1], actions=t["actions"][k, b0:b1], env_id0=eg.env_id0)
+            else:
+                for g, (b0, b1) in enumerate(eng._ranges):
+                    eg = eng._envs[g]
+                    with torch.cuda.stream(eng._streams[g]):
+                        eg.step(t["actions"][k, b0:b1],
+                                out=dict(obs=t["obs"][k + 1, b0:b1], adj_bits=t["adj_bits"][k + 1, b0:b1], chan_bits=t["chan_bits"][k + 1, b0:b1],
+                                         ave_deg=t["ave_deg"][k + 1, b0:b1], reward=t["reward"][k, b0:b1], done=t["done"][k, b0:b1],
+                                         counts=t["counts"][k, b0:b1], prey_alive_out=t["prey_alive_out"][k, b0:b1],
+                                         success_out=t["success"][k, b0:b1]))
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            main = torch.cuda.current_stream(dev)
+            fork = torch.cuda.Event(); fork.record(main)
+            for st in eng._streams:
+                st.wait_event(fork)
+            for k in range(reps):
+                round_(k % ring)
+            for st in eng._streams:
+                j = torch.cuda.Event(); j.record(st); main.wait_event(j)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gr.replay()
+        a.record()
+        for _ in range(3):
+            gr.replay()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / (3 * reps * G)
+
+    pol_ms = time_groups("policy")
+    env_ms = time_groups("env")
+    eng.steps_done += 16 * reps
     clock_info = clocks.stop(t_lo, t_hi) if rank == 0 else None
     # ---------------- e2e: host buffers through the public step / get_actions API ----------------
     from com_marl_b200.envs import BatchedEnv
@@ -383,17 +431,21 @@ def run_b200_arm(args):
                      "peak_source": peak_src + ", bf16 dense sustained; " + kdesc,
                      "flop_per_launch": flops, "tensor_flop_issued_per_launch": tc_flops, "ms_per_launch": pol_ms, "share_of_step": pol_ms / (pol_ms + env_ms),
                      "envs_per_launch": Bk, "launches_per_step": len(eng._ranges),
-                     "note": "one launch = one env group, timed alone (CUDA graph of 32 launches); in the timed region the groups' chains overlap on separate streams"},
+                     "ms_per_launch_alone": pol_alone_ms,
+                     "note": "one launch = one env group; ms_per_launch = wall time of the groups' concurrent launches (separate streams, as in "
+                             "the timed region; CUDA graph of 32 rounds, CUDA events) / number of groups; ms_per_launch_alone = the same launch with the GPU to itself"},
         "roofline_env": {"bound": "hbm", "kernel": "env_kernel", "achieved": env_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": env_gbs / hbm_peak, "traffic": traffic.get("env_kernel"), "bytes_per_launch": env_bytes, "ms_per_launch": env_ms,
                          "bytes_per_agent_step": env_bytes_per_agent_step(spec), "peak_source": peak_src, "envs_per_launch": Bk,
-                         "launches_per_step": len(eng._ranges)},
+                         "launches_per_step": len(eng._ranges), "ms_per_launch_alone": env_alone_ms},
         "clocks": clock_info,
         "episode_stats": D.summarize_stats(stats, spec.scenario, n),
     }
     if world == 1 and not args.no_cpu_baseline:
         t0 = time.perf_counter()
-        Bc, Sc = max(8, min(512, 40000 // n)), 60
+        Bc = max(8, min(512, 40000 // n))
+        pilot_rate, _ = cpu_port_throughput(args.config, 1, Bc, 10)
+        Sc = int(max(10, min(200000, 10.0 * pilot_rate / (Bc * n))))      # ~10 s of single-thread CPU work
         rate, _ = cpu_port_throughput(args.config, 1, Bc, Sc)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"{Bc} envs x {Sc} steps of the oracle port (C env oracle + numpy fp32 policy), "
