@@ -81,13 +81,26 @@ __device__ __forceinline__ void write_act(unsigned char *act, int Kp, int row, i
     }
 }
 
-// tanh through ex2.approx / rcp.approx: |error| <= ~3e-7 absolute (two units of fp32 rounding at 1.0), an order
-// of magnitude below the tolerance and ~4x fewer instructions than tanhf.
-__device__ __forceinline__ float tanh_fast(float x)
+// tanh through ex2.approx / rcp.approx on a PRE-SCALED argument a = 2 log2(e) x:  tanh(x) = 1 - 2 / (2^a + 1).
+// |error| <= ~3e-7 absolute (two units of fp32 rounding at 1.0), an order of magnitude below the tolerance; the scale
+// is folded into the accumulator read-out (one FFMA per element does "combine hi/lo accumulators, add bias, scale"),
+// and the shared-memory bias table holds 2 log2(e) * bias.  Saturates correctly: 2^a = inf -> 1, 2^a = 0 -> -1.
+static constexpr float kTanhScale = 2.8853900817779268f;            // 2 log2(e)
+static constexpr float kTanhScaleLo = 2.8853900817779268f / 4096.0f;
+__device__ __forceinline__ float tanh_scaled(float a)
 {
-    if (CM_TC_DEBUG & 2) return x;
-    const float e = __expf(2.0f * x);
-    return 1.0f - __fdividef(2.0f, e + 1.0f);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+// tanh(acc0 + 2^-12 acc1 + bias) for 4 consecutive columns, bias4 = 2 log2(e) * bias from the shared-memory table
+__device__ __forceinline__ void tanh4(float *v, const float *w, const float4 b4)
+{
+    v[0] = tanh_scaled(fmaf(v[0], kTanhScale, fmaf(w[0], kTanhScaleLo, b4.x)));
+    v[1] = tanh_scaled(fmaf(v[1], kTanhScale, fmaf(w[1], kTanhScaleLo, b4.y)));
+    v[2] = tanh_scaled(fmaf(v[2], kTanhScale, fmaf(w[2], kTanhScaleLo, b4.z)));
+    v[3] = tanh_scaled(fmaf(v[3], kTanhScale, fmaf(w[3], kTanhScaleLo, b4.w)));
 }
 
 // one converged warp: D[:, 0:N] (+)= A_hi B_hi^T, D[:, N:2N] (+)= A_hi B_lo^T + A_lo B_hi^T.  All lanes run the code
@@ -113,6 +126,18 @@ __device__ __forceinline__ void issue_layer(uint32_t d_tmem, const unsigned char
         for (int j = 0; j < 4; ++j)
             if (j < nk) mma_f16_pred(d_tmem + (uint32_t)N, da + 16 * j, db + 16 * j, idesc, 1u, leader);
     }
+}
+
+// raw accumulator read-out: acc0 -> v, acc1 -> w (the caller fuses the combination with bias and scale)
+template <int CW>
+__device__ __forceinline__ void ld_acc_raw(uint32_t blk, int N, int col, float (&v)[CW], float (&w)[CW])
+{
+#pragma unroll
+    for (int c = 0; c < CW; c += 8) {
+        tmem_ld8(blk + (uint32_t)(col + c), *reinterpret_cast<float(*)[8]>(&v[c]));
+        tmem_ld8(blk + (uint32_t)(N + col + c), *reinterpret_cast<float(*)[8]>(&w[c]));
+    }
+    tmem_ld_wait();
 }
 
 // accumulator read-out: acc0 + 2^-12 acc1 for CW columns starting at column `col` of a product whose D block starts at
@@ -208,15 +233,25 @@ static constexpr int kBEnc1 = 0, kBEnc2 = 128, kBGcn = 192, kBH1 = 448, kBH2 = 5
 struct MmaOp { uint32_t dcol, acc, abuf; };   // accumulator block, accumulate flag, A operand buffer (0: ACT, 1: ACT2)
 
 #ifdef CM_TC_TRACE
+#define CM_TPK(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && A.io.workspace) \
+    reinterpret_cast<long long *>(A.io.workspace)[600 + (slot)] = clock64(); } while (0)
 #define CM_TP(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && io.workspace && tile == (int)blockIdx.x) \
     reinterpret_cast<long long *>(io.workspace)[600 + (slot)] = clock64(); } while (0)
 #else
 #define CM_TP(slot) do { } while (0)
+#define CM_TPK(slot) do { } while (0)
 #endif
 
 __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
+    CM_TPK(20);
+#ifdef CM_TC_TRACE
+    if (threadIdx.x == 0 && A.io.workspace) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        reinterpret_cast<unsigned long long *>(A.io.workspace)[1024 + 2 * blockIdx.x] = gt;
+    }
+#endif
     unsigned char *ACT = smem;
     unsigned char *WB = smem + kActBytes;                                // weight ring: 2 slots of 16 KB
     float *KV = reinterpret_cast<float *>(smem + kActBytes + kWBytes);   // [64][128] E^T (keys), then (H_l Wg_l)^T (values)
@@ -242,18 +277,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         mbar_init(&bars[1], 1);
         mbar_init(&bars[2], 1);
         fence_mbar_init();
-    }
-    for (int i = tid; i < kBiasFloats; i += kTcThreads) {
-        float v = 0.0f;
-        if (i < kBEnc2) v = wts[o.enc_b1 + i];
-        else if (i < kBGcn) v = wts[o.enc_b2 + i - kBEnc2];
-        else if (i < kBH1) { if (i - kBGcn < L * 64) v = wts[o.gcn_b + i - kBGcn]; }
-        else if (i < kBH2) v = wts[o.head_b1 + i - kBH1];
-        else if (i < kBH3) v = wts[o.head_b2 + i - kBH2];
-        else if (i < kBH4) v = wts[o.head_b3 + i - kBH3];
-        else if (i < kBH4 + CM_ACTIONS) v = wts[o.head_b4 + i - kBH4];
-        else if (i >= kW4) v = wts[o.head_w4 + i - kW4];
-        bias_s[i] = v;
     }
     fence_before_thread_sync();
     __syncthreads();
@@ -343,10 +366,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
 
     // dense epilogue of a 64-wide product: this thread's 16 columns -> bias, tanh -> next A operand (K panel of 64)
     auto epi64 = [&](uint32_t blk, int bias0, unsigned char *dst) {
-        float v[16];
-        ld_acc<16>(lane_addr + blk, 64, 16 * sub, v);
+        float v[16], w[16];
+        ld_acc_raw<16>(lane_addr + blk, 64, 16 * sub, v, w);
+        const float4 *bp = reinterpret_cast<const float4 *>(bias_s + bias0 + 16 * sub);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = tanh_fast(v[c] + bias_s[bias0 + 16 * sub + c]);
+        for (int q = 0; q < 4; ++q) tanh4(v + 4 * q, w + 4 * q, bp[q]);
         write_act<16>(dst, 64, row, 16 * sub, v);
     };
     // neighbour mask of this row for layer l (dist_adj & channels[l], comm_base_net.py:101)
@@ -397,6 +421,21 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if ((int)blockIdx.x < n_tiles) stage_obs((int)blockIdx.x);
+    // bias table (and the last layer's weights) — after the first weight stages and the observations have been requested,
+    // so that the three global round trips of the prologue overlap
+    for (int i = tid; i < kBiasFloats; i += kTcThreads) {
+        float v = 0.0f;
+        if (i < kBEnc2) v = wts[o.enc_b1 + i];
+        else if (i < kBGcn) v = wts[o.enc_b2 + i - kBEnc2];
+        else if (i < kBH1) { if (i - kBGcn < L * 64) v = wts[o.gcn_b + i - kBGcn]; }
+        else if (i < kBH2) v = wts[o.head_b1 + i - kBH1];
+        else if (i < kBH3) v = wts[o.head_b2 + i - kBH2];
+        else if (i < kBH4) v = wts[o.head_b3 + i - kBH3];
+        else if (i < kBH4 + CM_ACTIONS) v = wts[o.head_b4 + i - kBH4];
+        else if (i >= kW4) v = wts[o.head_w4 + i - kW4];
+        bias_s[i] = i < kBH4 ? v * kTanhScale : v;        // every bias below kBH4 feeds a tanh (see tanh_scaled)
+    }
+    __syncthreads();
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int env0 = tile * A.envs_per_tile;
@@ -444,13 +483,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR0, 1u, 1u});
         // ---------------- E = tanh(. + b2): keys (k-major fp32) + A operand; Q -> R0, H_0 Wg_0 -> R1 ----------------
         {
-            float v[16];
-            ld_acc<16>(lane_addr + kR0, 64, 16 * sub, v);
+            float v[16], w[16];
+            ld_acc_raw<16>(lane_addr + kR0, 64, 16 * sub, v, w);
+            const float4 *bp = reinterpret_cast<const float4 *>(bias_s + kBEnc2 + 16 * sub);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                v[c] = tanh_fast(v[c] + bias_s[kBEnc2 + 16 * sub + c]);
-                KV[(16 * sub + c) * kTPitch + row] = v[c];
-            }
+            for (int q = 0; q < 4; ++q) tanh4(v + 4 * q, w + 4 * q, bp[q]);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) KV[(16 * sub + c) * kTPitch + row] = v[c];
             write_act<16>(ACT, 64, row, 16 * sub, v);
             load_mask(env, il, 0, valid);
             run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR1, 0u, 0u});
@@ -508,10 +547,17 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                 }
             }
             CM_TP(3 + 4 * l);
-            const float inv = 1.0f / (den + 1e-12f);
+            const float inv = kTanhScale / (den + 1e-12f);            // scale of tanh_scaled folded into the normalisation
             float v[16];
+            const float4 *bp = reinterpret_cast<const float4 *>(bias_s + kBGcn + l * 64 + 16 * sub);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = tanh_fast(acc[c] * inv + bias_s[kBGcn + l * 64 + 16 * sub + c]);
+            for (int q = 0; q < 4; ++q) {
+                const float4 b4 = bp[q];
+                v[4 * q + 0] = tanh_scaled(fmaf(acc[4 * q + 0], inv, b4.x));
+                v[4 * q + 1] = tanh_scaled(fmaf(acc[4 * q + 1], inv, b4.y));
+                v[4 * q + 2] = tanh_scaled(fmaf(acc[4 * q + 2], inv, b4.z));
+                v[4 * q + 3] = tanh_scaled(fmaf(acc[4 * q + 3], inv, b4.w));
+            }
             if (d.residual) {                             // X = E + H_L (comm_base_net.py:105-106)
                 // E is still in the A operand buffer (this thread wrote these 16 columns itself) until the first layer's
                 // output replaces it; with more than one layer it is parked in tensor memory meanwhile
@@ -571,13 +617,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         epi64(kR0, kBH2, ACT);                                                    // 64 -> 32
         run_mma(1, MmaOp{kR1, 0u, 0u}, none);
         {   // 32 -> 5 on the CUDA cores (exact fp32): this thread's 8 inputs -> 5 partial logits, parked in tensor memory
-            float v[8], part[8];
-            ld_acc<8>(lane_addr + kR1, 32, 8 * sub, v);
+            float v[8], w[8], part[8];
+            ld_acc_raw<8>(lane_addr + kR1, 32, 8 * sub, v, w);
+            const float4 *bp = reinterpret_cast<const float4 *>(bias_s + kBH3 + 8 * sub);
+            tanh4(v, w, bp[0]);
+            tanh4(v + 4, w + 4, bp[1]);
 #pragma unroll
             for (int a = 0; a < 8; ++a) part[a] = 0.0f;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                v[c] = tanh_fast(v[c] + bias_s[kBH3 + 8 * sub + c]);
                 const float *w4 = bias_s + kW4 + (8 * sub + c) * CM_ACTIONS;
 #pragma unroll
                 for (int a = 0; a < CM_ACTIONS; ++a) part[a] = fmaf(v[c], w4[a], part[a]);
@@ -652,6 +700,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
     fence_before_thread_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+    CM_TPK(21);
+#ifdef CM_TC_TRACE
+    if (threadIdx.x == 0 && A.io.workspace) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        reinterpret_cast<unsigned long long *>(A.io.workspace)[1024 + 2 * blockIdx.x + 1] = gt;
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
