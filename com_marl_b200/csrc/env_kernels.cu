@@ -22,6 +22,8 @@ namespace cm {
 typedef unsigned long long u64;
 
 static constexpr int kWarpsPerCta = 8;
+// per-CTA constants in shared memory: wall rows [64] u64 | k / n as IEEE doubles for k = 0 .. n (<= 256) [257] f64
+static constexpr int kConstBytes = 64 * 8 + 264 * 8;
 
 struct EnvArgs {
     cm_env_desc d;
@@ -39,7 +41,7 @@ struct EnvArgs {
 struct Scratch {
     u64 *occA;       // [G] agent rows
     u64 *occB;       // [G] prey rows (PredatorPrey) / visited rows (Coverage)
-    uint32_t *win;   // [3][n_pad] window bits per agent
+    uint32_t *win;   // [6][n_pad] per agent: 3 words of packed window bits, 3 scalar features (float bits)
     uint16_t *posA;  // [n_pad]
     uint16_t *posP;  // [p_pad]
     uint8_t *alive;  // [p_pad]
@@ -50,7 +52,7 @@ struct Scratch {
 
 __host__ __device__ inline int env_warp_bytes(int n_pad, int p_pad, int G)
 {
-    return 2 * G * 8 + 3 * n_pad * 4 + n_pad * 2 + p_pad * 2 + p_pad + n_pad + p_pad + p_pad;
+    return 2 * G * 8 + 6 * n_pad * 4 + n_pad * 2 + p_pad * 2 + p_pad + n_pad + p_pad + p_pad;
 }
 
 __device__ __forceinline__ Scratch carve(unsigned char *base, int n_pad, int p_pad, int G)
@@ -59,13 +61,19 @@ __device__ __forceinline__ Scratch carve(unsigned char *base, int n_pad, int p_p
     s.occA = reinterpret_cast<u64 *>(base);
     s.occB = s.occA + G;
     s.win = reinterpret_cast<uint32_t *>(s.occB + G);
-    s.posA = reinterpret_cast<uint16_t *>(s.win + 3 * n_pad);
+    s.posA = reinterpret_cast<uint16_t *>(s.win + 6 * n_pad);
     s.posP = s.posA + n_pad;
     s.alive = reinterpret_cast<uint8_t *>(s.posP + p_pad);
     s.act = reinterpret_cast<int8_t *>(s.alive + p_pad);
     s.kcnt = reinterpret_cast<uint8_t *>(s.act + n_pad);
     s.mv = reinterpret_cast<int8_t *>(s.kcnt + p_pad);
     return s;
+}
+
+// set bit c of row r from several lanes at once: native 32-bit shared-memory atomics on the row's halves
+__device__ __forceinline__ void set_bit(u64 *rows, int r, int c)
+{
+    atomicOr(reinterpret_cast<unsigned int *>(rows + r) + (c >> 5), 1u << (c & 31));
 }
 
 // action -> displacement: 0 down(+row) 1 left(-col) 2 up(-row) 3 right(+col) 4 noop
@@ -158,6 +166,38 @@ struct ChanSrc {
     }
 };
 
+// 32 links of one row: bit jj = ((u(plane, i, 32 w + jj) + [i == j]) < thr) if kLess else (... >= thr).  Generated mode
+// walks the Philox blocks that cover the row (4 draws per block) instead of testing a block cache per draw.
+template <bool kLess>
+__device__ __forceinline__ uint32_t link_row_bits(ChanSrc &src, int plane, int i, int w, int jn, float thr)
+{
+    uint32_t bits = 0;
+    const int n = src.n;
+    if (src.u) {
+        for (int jj = 0; jj < jn; ++jj) {
+            const int j = w * 32 + jj;
+            const float v = __fadd_rn(__ldg(src.u + ((size_t)plane * n + i) * n + j), (i == j) ? 1.0f : 0.0f);
+            bits |= (uint32_t)(kLess ? (v < thr) : (v >= thr)) << jj;
+        }
+        return bits;
+    }
+    const uint32_t q0 = (uint32_t)((plane * n + i) * n + w * 32), q1 = q0 + (uint32_t)jn;   // draw indices [q0, q1)
+    for (uint32_t blk = q0 >> 2; blk <= (q1 - 1u) >> 2; ++blk) {
+        const uint4 r4 = rng_block(src.key, kStreamChan, blk);
+        const uint32_t ws[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t q = blk * 4u + (uint32_t)k;
+            if (q >= q0 && q < q1) {
+                const int jj = (int)(q - q0);
+                const float v = __fadd_rn(u24(ws[k]), (i == w * 32 + jj) ? 1.0f : 0.0f);
+                bits |= (uint32_t)(kLess ? (v < thr) : (v >= thr)) << jj;
+            }
+        }
+    }
+    return bits;
+}
+
 // ------------------------------------------------------------------------------------------------
 // communication state: get_graph + channels (env_communication.py:91-157,200-243)
 // ------------------------------------------------------------------------------------------------
@@ -208,13 +248,7 @@ __device__ void comm_update(const EnvArgs &A, const Scratch &S, int64_t b, const
         for (int item = G.gl; item < L * n * W; item += G.gs) {
             const int w = item % W, i = (item / W) % n, l = item / (W * n);
             const int jn = min(32, n - w * 32);
-            uint32_t bits = 0;
-            for (int jj = 0; jj < jn; ++jj) {
-                const int j = w * 32 + jj;
-                const float eye = (i == j) ? 1.0f : 0.0f;
-                bits |= (uint32_t)(__fadd_rn(src.draw(l, i, j), eye) >= d.p_loss) << jj;
-            }
-            out[item] = bits;
+            out[item] = link_row_bits<false>(src, l, i, w, jn, d.p_loss);
         }
     } else {                                                                   // GE :106-157
         uint32_t *state = A.s.ge_state + (size_t)b * n * W;
@@ -244,17 +278,8 @@ __device__ void comm_update(const EnvArgs &A, const Scratch &S, int64_t b, const
             }
             const int n_trans = d.loss_apply == 0 ? 1 : L - first_layer;
             for (int tr = 0; tr < n_trans; ++tr) {      // get_next_state_matrix :137-148: g2b draw, then b2g draw
-                uint32_t g2b = 0, b2g = 0;
-                for (int jj = 0; jj < jn; ++jj) {
-                    const int j = w * 32 + jj;
-                    const float eye = (i == j) ? 1.0f : 0.0f;
-                    g2b |= (uint32_t)(__fadd_rn(src.draw(plane, i, j), eye) < d.pgb) << jj;
-                }
-                for (int jj = 0; jj < jn; ++jj) {
-                    const int j = w * 32 + jj;
-                    const float eye = (i == j) ? 1.0f : 0.0f;
-                    b2g |= (uint32_t)(__fadd_rn(src.draw(plane + 1, i, j), eye) < d.pbg) << jj;
-                }
+                const uint32_t g2b = link_row_bits<true>(src, plane, i, w, jn, d.pgb);
+                const uint32_t b2g = link_row_bits<true>(src, plane + 1, i, w, jn, d.pbg);
                 plane += 2;
                 st = (st & ~(st & g2b)) | (~st & b2g & full);
                 if (out) {
@@ -287,14 +312,14 @@ __device__ void reset_env(const EnvArgs &A, const Scratch &S, const u64 *wall, i
         for (int i = G.gl; i < n; i += G.gs) {
             const uint16_t q = A.io.spawn_agent[((size_t)b * A.io.spawn_episodes + ep) * n + i];
             S.posA[i] = q;
-            atomicOr(&S.occA[q & 0xFF], 1ull << (q >> 8));
-            if (co) atomicOr(&S.occB[q & 0xFF], 1ull << (q >> 8));     // coverage.py:188 start cells are visited
+            set_bit(S.occA, q & 0xFF, q >> 8);
+            if (co) set_bit(S.occB, q & 0xFF, q >> 8);                // coverage.py:188 start cells are visited
         }
         for (int j = G.gl; j < p; j += G.gs) {
             const uint16_t q = A.io.spawn_prey[((size_t)b * A.io.spawn_episodes + ep) * p + j];
             S.posP[j] = q;
             S.alive[j] = 1;
-            atomicOr(&S.occB[q & 0xFF], 1ull << (q >> 8));
+            set_bit(S.occB, q & 0xFF, q >> 8);
         }
     } else if (G.gl == 0) {
         // sequential rejection sampling on one lane; a reset happens once per episode, not per step
@@ -340,51 +365,70 @@ __device__ void reset_env(const EnvArgs &A, const Scratch &S, const u64 *wall, i
 // ------------------------------------------------------------------------------------------------
 // observations (predator_prey.py:173-204; coverage.py:198-212,448-480)
 // ------------------------------------------------------------------------------------------------
+// Phase 1, one lane per agent: the windows are extracted into registers and packed into ONE bit string per agent
+// (window after window, <= 75 bits -> 3 words) next to the agent's 3 scalar features.  Phase 2: the env's [n][D] block is
+// contiguous, so the group streams it out flat — consecutive lanes store consecutive floats (fully coalesced), one
+// shift + mask + convert per float, no divergent select chain.
 __device__ void write_obs(const EnvArgs &A, const Scratch &S, const u64 *wall, int64_t b, const Grp &G, int t)
 {
     const cm_env_desc &d = A.d;
     if (!A.io.obs) return;
-    const int n = d.n_agents, Gd = d.grid, R = d.sensing, w = 2 * R + 1, ww = w * w;
+    const int n = d.n_agents, Gd = d.grid, R = d.sensing, w = 2 * R + 1, ww = w * w, np_ = A.n_pad;
     const bool co = d.scenario == CM_COVERAGE;
-    const int nwin = co ? 3 : 2, D = nwin * ww + (co ? 2 : 3);
-    // window bits of every agent, lane-parallel
+    const int nbits = (co ? 3 : 2) * ww, D = nbits + (co ? 2 : 3);
+    const float *lut_row = d.lut, *lut_col = d.lut + Gd, *lut_t = d.lut + 2 * Gd;
+    const float ft = co ? 0.0f : __ldg(lut_t + t);
     for (int i = G.gl; i < n; i += G.gs) {
         const int r = S.posA[i] & 0xFF, c = S.posA[i] >> 8;
+        const float fr = __ldg(lut_row + r), fc = __ldg(lut_col + c);      // in flight while the windows are extracted
+        u64 lo;
+        uint32_t hi = 0u;
         if (co) {
-            S.win[0 * A.n_pad + i] = window_bits(wall, r, c, R, Gd, 1);     // wall channel, out-of-grid = wall (:464-466)
-            S.win[1 * A.n_pad + i] = window_bits(S.occA, r, c, R, Gd, 0);   // agents, self included
-            S.win[2 * A.n_pad + i] = window_bits(S.occB, r, c, R, Gd, 0);   // visited
+            const uint32_t w0 = window_bits(wall, r, c, R, Gd, 1);          // wall channel, out-of-grid = wall (:464-466)
+            const uint32_t w1 = window_bits(S.occA, r, c, R, Gd, 0);        // agents, self included
+            const uint32_t w2 = window_bits(S.occB, r, c, R, Gd, 0);        // visited
+            lo = (u64)w0 | ((u64)w1 << ww) | ((u64)w2 << (2 * ww));
+            if (3 * ww > 64) hi = w2 >> (64 - 2 * ww);
         } else {
-            S.win[0 * A.n_pad + i] = window_bits(S.occA, r, c, R, Gd, 0);   // agents, self included
-            S.win[1 * A.n_pad + i] = window_bits(S.occB, r, c, R, Gd, 0);   // preys
+            const uint32_t w0 = window_bits(S.occA, r, c, R, Gd, 0);        // agents, self included
+            const uint32_t w1 = window_bits(S.occB, r, c, R, Gd, 0);        // preys
+            lo = (u64)w0 | ((u64)w1 << ww);
         }
+        S.win[0 * np_ + i] = (uint32_t)lo;
+        S.win[1 * np_ + i] = (uint32_t)(lo >> 32);
+        S.win[2 * np_ + i] = hi;
+        S.win[3 * np_ + i] = __float_as_uint(fr);
+        S.win[4 * np_ + i] = __float_as_uint(fc);
+        S.win[5 * np_ + i] = __float_as_uint(ft);
     }
     G.sync();
-    const float *lut_row = d.lut, *lut_col = d.lut + Gd, *lut_t = d.lut + 2 * Gd;
     float *out = A.io.obs + (size_t)b * n * D;
-    // the env's [n][D] block is contiguous: consecutive lanes store consecutive floats
-    for (int i = 0; i < n; ++i) {
-        const uint32_t w0 = S.win[i], w1 = S.win[A.n_pad + i], w2 = co ? S.win[2 * A.n_pad + i] : 0u;
-        const int r = S.posA[i] & 0xFF, c = S.posA[i] >> 8;
-        for (int e = G.gl; e < D; e += G.gs) {
-            float v;
-            if (e < ww) v = (float)((w0 >> e) & 1u);
-            else if (e < 2 * ww) v = (float)((w1 >> (e - ww)) & 1u);
-            else if (e < nwin * ww) v = (float)((w2 >> (e - 2 * ww)) & 1u);
-            else {
-                const int k = e - nwin * ww;
-                v = k == 0 ? __ldg(lut_row + r) : (k == 1 ? __ldg(lut_col + c) : __ldg(lut_t + t));
-            }
-            out[i * D + e] = v;
-        }
+    const int total = n * D;
+    const uint32_t magic = (uint32_t)((0x100000000ull + (u64)D - 1ull) / (u64)D);   // e / D == umulhi(e, magic) for e < 2^25
+#pragma unroll 4
+    for (int e = G.gl; e < total; e += G.gs) {
+        const int i = (int)__umulhi((uint32_t)e, magic), k = e - i * D;
+        const int kk = k < nbits ? k : 96 + 32 * (k - nbits);             // bit index, or the word of the scalar feature
+        const uint32_t word = S.win[(kk >> 5) * np_ + i];
+        out[e] = k < nbits ? (float)((word >> (kk & 31)) & 1u) : __uint_as_float(word);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // the kernel: mode 0 = VecEnvExecutor.step, 1 = reset(mask), 2 = comm only
 // ------------------------------------------------------------------------------------------------
+#ifdef CM_ENV_TRACE
+#define CM_ETP(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) trace_t[k] = clock64(); } while (0)
+#else
+#define CM_ETP(k) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
 {
+#ifdef CM_ENV_TRACE
+    long long trace_t[12] = {0};
+#endif
+    CM_ETP(0);
     extern __shared__ __align__(16) unsigned char smem[];
     const cm_env_desc &d = A.d;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -396,11 +440,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
     const int n = d.n_agents, p = d.n_preys, Gd = d.grid;
     const bool co = d.scenario == CM_COVERAGE;
     u64 *wall = reinterpret_cast<u64 *>(smem);               // [Gd] shared by the CTA (Coverage)
+    double *mean_lut = reinterpret_cast<double *>(smem + 64 * 8);   // k / n, correctly rounded: mean(x) = sum / len (coverage.py:601-602)
     if (co) {
         for (int r = threadIdx.x; r < Gd; r += blockDim.x) wall[r] = d.wall_rows[r];
+        for (int k = threadIdx.x; k <= n; k += blockDim.x) mean_lut[k] = __ddiv_rn((double)k, (double)n);
     }
     __syncthreads();
-    const Scratch S = carve(smem + 64 * 8 + (size_t)(warp * epw + grp) * A.warp_bytes, A.n_pad, A.p_pad, Gd);
+    CM_ETP(1);
+    const Scratch S = carve(smem + kConstBytes + (size_t)(warp * epw + grp) * A.warp_bytes, A.n_pad, A.p_pad, Gd);
     const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta * epw;
     for (int64_t b = ((int64_t)blockIdx.x * kWarpsPerCta + warp) * epw + grp; b < A.s.n_envs; b += stride) {
         if (A.mode == 1 && A.mask && !A.mask[b]) continue;
@@ -413,6 +460,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
         int t = A.s.step_count[b];
         int total_capture = co ? A.s.total_capture[b] : 0;
         bool did_reset = false;
+        // every global read of this env is issued here, in one batch: the state, the actions, the success latch and the
+        // running episode accumulators (used only at the end of the step) — one memory round trip instead of four
+        uint8_t success = 0;
+        double run7[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        int moved = 0, bad = 0;
+        CM_ETP(2);
 
         if (A.mode == 1) {
             reset_env(A, S, wall, b, G, key, t, total_capture);
@@ -422,38 +475,50 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
             for (int r = G.gl; r < Gd; r += G.gs) { S.occA[r] = 0ull; S.occB[r] = co ? A.s.visited[b * Gd + r] : 0ull; }
             for (int i = G.gl; i < n; i += G.gs) S.posA[i] = A.s.agent_pos[b * n + i];
             for (int j = G.gl; j < p; j += G.gs) { S.posP[j] = A.s.prey_pos[b * p + j]; S.alive[j] = A.s.prey_alive[b * p + j]; }
+            if (A.mode == 0) {
+                success = A.s.success[b];
+                if (G.gl == 0 && A.io.stats) {
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) run7[k] = A.io.stats[b * 16 + k];
+                }
+                for (int i = G.gl; i < n; i += G.gs) {
+                    int a = A.io.actions[b * n + i];
+                    if (a < 0 || a > 4) { bad = 1; a = 4; }
+                    S.act[i] = (int8_t)a;
+                    moved += (a != 4);
+                }
+            }
             G.sync();
-            for (int i = G.gl; i < n; i += G.gs) atomicOr(&S.occA[S.posA[i] & 0xFF], 1ull << (S.posA[i] >> 8));
+            for (int i = G.gl; i < n; i += G.gs) set_bit(S.occA, S.posA[i] & 0xFF, S.posA[i] >> 8);
             for (int j = G.gl; j < p; j += G.gs)
-                if (S.alive[j]) atomicOr(&S.occB[S.posP[j] & 0xFF], 1ull << (S.posP[j] >> 8));
+                if (S.alive[j]) set_bit(S.occB, S.posP[j] & 0xFF, S.posP[j] >> 8);
             G.sync();
         }
 
+        CM_ETP(3);
         if (A.mode == 0) {
             // =================================== env.step ===================================
             t += 1;
             key.tick += 1;                        // every draw of this step is keyed with the new tick
-            int moved = 0, bad = 0;
-            for (int i = G.gl; i < n; i += G.gs) {
-                int a = A.io.actions[b * n + i];
-                if (a < 0 || a > 4) { bad = 1; a = 4; }
-                S.act[i] = (int8_t)a;
-                moved += (a != 4);
-            }
             moved = G.sum(moved);
             if (G.any(bad) && G.gl == 0 && A.io.error_flag) atomicExch(A.io.error_flag, (int)CM_EACTION);
-            G.sync();
+            CM_ETP(4);
             int c0 = 0, c2 = 0, c3 = 0, c4 = 0;   // counts (see commarl_b200.h)
             double reward = 0.0;
             int env_done = 0;
-            uint8_t success = A.s.success[b];
             if (!co) {
                 // ---- agents move one after another, lower index first (predator_prey.py:497-500,240-261) ----
                 if (G.gl == 0) {
+                    // the action and position of agent i + 1 are loaded while agent i is resolved: the only loop-carried
+                    // dependency left is the occupancy rows themselves
+                    int a_nx = S.act[0];
+                    uint16_t q_nx = S.posA[0];
                     for (int i = 0; i < n; ++i) {
-                        const int a = S.act[i];
+                        const int a = a_nx;
+                        const uint16_t q = q_nx;
+                        if (i + 1 < n) { a_nx = S.act[i + 1]; q_nx = S.posA[i + 1]; }
                         if (a == 4) continue;
-                        const int r = S.posA[i] & 0xFF, c = S.posA[i] >> 8;
+                        const int r = q & 0xFF, c = q >> 8;
                         const int nr = r + d_row(a), nc = c + d_col(a);
                         if (nr < 0 || nr >= Gd || nc < 0 || nc >= Gd) continue;
                         if (((S.occA[nr] | S.occB[nr]) >> nc) & 1ull) continue;
@@ -493,10 +558,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
                 // ---- order-dependent part: capture test against the preys still standing, then the walk ----
                 if (G.gl == 0) {
                     int capture = 0, penalty = 0;
+                    // prey j + 1's flags are loaded while prey j is resolved (a prey only changes its own entries)
+                    int al_nx = S.alive[0], k_nx = S.kcnt[0], mv_nx = S.mv[0];
+                    uint16_t q_nx = S.posP[0];
                     for (int j = 0; j < p; ++j) {
-                        if (!S.alive[j]) continue;
-                        const int r = S.posP[j] & 0xFF, c = S.posP[j] >> 8;
-                        const int k = S.kcnt[j];
+                        const int al = al_nx, k = k_nx, mvj = mv_nx;
+                        const uint16_t q = q_nx;
+                        if (j + 1 < p) { al_nx = S.alive[j + 1]; k_nx = S.kcnt[j + 1]; mv_nx = S.mv[j + 1]; q_nx = S.posP[j + 1]; }
+                        if (!al) continue;
+                        const int r = q & 0xFF, c = q >> 8;
                         if (k >= 1) {
                             int need = d.load;
                             if (d.load != 2) {   // reward_individual :469-470; edges dict :123-144 (corner 2, border 3, else load)
@@ -512,7 +582,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
                             }
                             ++penalty;
                         }
-                        const int mv = S.mv[j];
+                        const int mv = mvj;
                         if (mv != 4) {           // __update_prey_pos :276-299
                             const int nr = r + d_row(mv), nc = c + d_col(mv);
                             if (nr >= 0 && nr < Gd && nc >= 0 && nc < Gd && !(((S.occA[nr] | S.occB[nr]) >> nc) & 1ull)) {
@@ -544,10 +614,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
                 // ---- Coverage.step (coverage.py:319-401): sequential moves over wall | agent rows ----
                 if (G.gl == 0) {
                     int cap = 0, pen = 0, rev = 0;
+                    int a_nx = S.act[0];
+                    uint16_t q_nx = S.posA[0];
                     for (int i = 0; i < n; ++i) {
-                        const int a = S.act[i];
+                        const int a = a_nx;
+                        const uint16_t q = q_nx;
+                        if (i + 1 < n) { a_nx = S.act[i + 1]; q_nx = S.posA[i + 1]; }
                         if (a == 4) continue;                    // lazy, counted below
-                        const int r = S.posA[i] & 0xFF, c = S.posA[i] >> 8;
+                        const int r = q & 0xFF, c = q >> 8;
                         const int nr = r + d_row(a), nc = c + d_col(a);
                         if (nr < 0 || nr >= Gd || nc < 0 || nc >= Gd || (((S.occA[nr] | wall[nr]) >> nc) & 1ull)) { ++pen; continue; }
                         if ((S.occB[nr] >> nc) & 1ull) ++rev;
@@ -562,12 +636,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
                     double final_reward = 0.0;
                     if (total_capture == d.n_empty_cells) { final_reward = d.final_reward; env_done = 1; }   // :378-382
                     if (t >= d.max_steps) { success = env_done ? 1 : 0; env_done = 1; }                       // :385-390
-                    const double dn = (double)n;                                                              // get_reward :300-306
-                    reward = __dadd_rn(d.step_cost, __dmul_rn(d.capture_reward, __ddiv_rn((double)cap, dn)));
-                    reward = __dadd_rn(reward, __dmul_rn(d.moving_cost, __ddiv_rn((double)moved, dn)));
-                    reward = __dadd_rn(reward, __dmul_rn(d.penalty, __ddiv_rn((double)pen, dn)));
-                    reward = __dadd_rn(reward, __dmul_rn(d.lazy_penalty, __ddiv_rn((double)lazy, dn)));
-                    reward = __dadd_rn(reward, __dmul_rn(d.revisit_penalty, __ddiv_rn((double)rev, dn)));
+                    // get_reward :300-306; mean(x) = sum / n comes from the table of correctly rounded k / n
+                    reward = __dadd_rn(d.step_cost, __dmul_rn(d.capture_reward, mean_lut[cap]));
+                    reward = __dadd_rn(reward, __dmul_rn(d.moving_cost, mean_lut[moved]));
+                    reward = __dadd_rn(reward, __dmul_rn(d.penalty, mean_lut[pen]));
+                    reward = __dadd_rn(reward, __dmul_rn(d.lazy_penalty, mean_lut[lazy]));
+                    reward = __dadd_rn(reward, __dmul_rn(d.revisit_penalty, mean_lut[rev]));
                     reward = __dadd_rn(reward, final_reward);
                 }
                 G.sync();
@@ -575,6 +649,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
                 total_capture = G.bcast0(total_capture);
                 success = (uint8_t)G.bcast0((int)success);
             }
+            CM_ETP(5);
             int done = env_done;
             if (d.max_path_length > 0 && t >= d.max_path_length) done = 1;   // vec_env_executor.py:33-35
             if (G.gl == 0) {
@@ -588,7 +663,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
                 if (A.io.success_out) A.io.success_out[b] = success;
                 if (A.io.stats) {                 // episode accounting (sampler bookkeeping, ...vectorized_sampler.py:158-227)
                     double *st = A.io.stats + b * 16;
-                    const double run[7] = {st[0] + reward, st[1] + 1.0, st[2] + c0, st[3] + moved, st[4] + c2, st[5] + c3, st[6] + c4};
+                    const double run[7] = {run7[0] + reward, run7[1] + 1.0, run7[2] + c0, run7[3] + moved, run7[4] + c2, run7[5] + c3, run7[6] + c4};
                     if (done) {
                         st[7] += 1.0; st[8] += run[0]; st[9] += run[1]; st[10] += (double)success;
                         for (int k = 0; k < 5; ++k) st[11 + k] += run[2 + k];
@@ -598,12 +673,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
                     }
                 }
             }
+            CM_ETP(6);
             if (done && A.io.auto_reset) {        // vec_env_executor.py:36-43
                 reset_env(A, S, wall, b, G, key, t, total_capture);
                 did_reset = true;
             }
         }
 
+        CM_ETP(7);
         if (A.mode != 2) {
             // ---- write the state back ----
             for (int i = G.gl; i < n; i += G.gs) A.s.agent_pos[b * n + i] = S.posA[i];
@@ -615,9 +692,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
                 A.s.episode[b] = key.episode;
                 if (co) A.s.total_capture[b] = total_capture;
             }
+            CM_ETP(8);
             write_obs(A, S, wall, b, G, t);
         }
+        CM_ETP(9);
         comm_update(A, S, b, G, key, A.mode == 2 ? (A.at_reset != 0) : did_reset);
+        CM_ETP(10);
+#ifdef CM_ENV_TRACE
+        if (blockIdx.x == 0 && threadIdx.x == 0 && A.io.stats && A.mode == 0) {
+            long long *tb = reinterpret_cast<long long *>(A.io.stats);
+            for (int k = 0; k < 11; ++k) tb[k] = trace_t[k];
+        }
+#endif
     }
 }
 
@@ -665,7 +751,7 @@ static int launch(const cm_env_desc *d, const cm_env_state *s, const cm_step_io 
     const int team = d->n_agents > d->n_preys ? d->n_agents : d->n_preys;
     A.group = team <= 4 ? 4 : (team <= 8 ? 8 : (team <= 16 ? 16 : 32));
     const int envs_per_cta = kWarpsPerCta * (32 / A.group);
-    const size_t smem = 64 * 8 + (size_t)envs_per_cta * A.warp_bytes;
+    const size_t smem = kConstBytes + (size_t)envs_per_cta * A.warp_bytes;
     // launch geometry is cached per (device, smem) so that steady-state calls issue nothing but the launch
     // (keeps the call CUDA-graph capturable)
     static thread_local struct { int dev; size_t smem; int ctas_per_sm; int sms; } cache = {-1, 0, 0, 0};
