@@ -3,7 +3,7 @@ communication graph / packet loss + comm-GNN policy forward).  See DESIGN.md."""
 from .scenario import ScenarioSpec  # noqa: F401
 
 __all__ = ["ScenarioSpec", "BatchedEnv", "PredatorPreyWrapper", "CoverageWrapper", "CommCategoricalMLPPolicy",
-           "RolloutEngine", "DeviceRolloutSampler"]
+           "DecCategoricalMLPPolicy", "RolloutEngine", "DeviceRolloutSampler"]
 
 
 def __getattr__(name):
@@ -11,9 +11,9 @@ def __getattr__(name):
     if name in ("BatchedEnv", "PredatorPreyWrapper", "CoverageWrapper"):
         from . import envs
         return getattr(envs, name)
-    if name == "CommCategoricalMLPPolicy":
-        from .policy import CommCategoricalMLPPolicy
-        return CommCategoricalMLPPolicy
+    if name in ("CommCategoricalMLPPolicy", "DecCategoricalMLPPolicy"):
+        from . import policy
+        return getattr(policy, name)
     if name == "RolloutEngine":
         from .rollout import RolloutEngine
         return RolloutEngine

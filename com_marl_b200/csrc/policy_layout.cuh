@@ -63,7 +63,7 @@ struct TcPlan {
     TcStage st[kTcMaxStages];
 };
 
-__host__ __device__ inline TcPlan make_tc_plan(int D, int L)
+__host__ __device__ inline TcPlan make_tc_plan(int D, int L, int kind = CM_POLICY_COMM)
 {
     const Blob o = blob_layout(D, L);
     TcPlan P;
@@ -83,12 +83,14 @@ __host__ __device__ inline TcPlan make_tc_plan(int D, int L)
     }
     add(o.enc_w2, kE, 64, 0, 0, kH1, kE);
     add(o.enc_w2, kE, 64, 64, 0, kH1, kE);
-    add(o.att_w, kE, 64, 0, 0, kE, kE);
-    for (int l = 0; l < L; ++l) add(o.gcn_w + l * kE * kE, kE, 64, 0, 0, kE, kE);
-    add(o.head_w1, 64, 64, 0, 0, kE, kC1);
-    add(o.head_w1, 64, 64, 0, 64, kE, kC1);
-    add(o.head_w2, kC2, 64, 0, 0, kC1, kC2);
-    add(o.head_w2, kC2, 64, 64, 0, kC1, kC2);
+    if (kind == CM_POLICY_COMM) {
+        add(o.att_w, kE, 64, 0, 0, kE, kE);
+        for (int l = 0; l < L; ++l) add(o.gcn_w + l * kE * kE, kE, 64, 0, 0, kE, kE);
+        add(o.head_w1, 64, 64, 0, 0, kE, kC1);
+        add(o.head_w1, 64, 64, 0, 64, kE, kC1);
+        add(o.head_w2, kC2, 64, 0, 0, kC1, kC2);
+        add(o.head_w2, kC2, 64, 64, 0, kC1, kC2);
+    }                                                                    // Obs-DP: the embedding feeds the 64 -> 32 layer directly
     add(o.head_w3, kC3, 64, 0, 0, kC2, kC3);
     // (the last layer, 32 -> 5, runs on the CUDA cores in exact fp32)
     P.n_stages = s;

@@ -398,10 +398,17 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
     // to the fp16 hi/lo A operand when the tile starts.  Staged element i of the block lives at stage[(src & 3) + i].
     float *stage = KV;
     constexpr int kStageFloats = (64 + 8) * kTPitch - 4;
+    // rows of tile tl: whole environments (Comm-DP: the attention stays inside a tile) or any 128 agent rows (Obs-DP)
+    const bool dec = d.kind == CM_POLICY_DEC;
+    const int total_rows = n_envs * n;
+    auto tile_rows = [&](int tl, int &r0, int &nr) {
+        if (dec) { r0 = tl * kTcRows; nr = min(kTcRows, total_rows - r0); }
+        else { const int e0 = tl * A.envs_per_tile; r0 = e0 * n; nr = min(A.envs_per_tile, n_envs - e0) * n; }
+    };
     auto stage_obs = [&](int tl) {
-        const int e0 = tl * A.envs_per_tile;
-        const int rws = min(A.envs_per_tile, n_envs - e0) * n;
-        const float *src = io.obs + (size_t)e0 * n * D;
+        int r0s, rws;
+        tile_rows(tl, r0s, rws);
+        const float *src = io.obs + (size_t)r0s * D;
         const int a = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
         const int ns = min(rws * D, kStageFloats);
         const int nq = (a + ns + 3) >> 2;
@@ -438,13 +445,14 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
     __syncthreads();
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int env0 = tile * A.envs_per_tile;
-        const int envs = min(A.envs_per_tile, n_envs - env0);
-        const int rows = envs * n;
-        const int row0 = env0 * n;
+        int row0, rows;
+        tile_rows(tile, row0, rows);
         const bool valid = row < rows;
-        const int el = valid ? row / n : 0, il = row - el * n, j0 = el * n;
-        const int env = env0 + el, g = row0 + row;
+        const int g = row0 + row;
+        // Comm-DP: env index inside the tile / agent index / first row of the env; Obs-DP rows are independent
+        const int el = valid ? (dec ? g / n : row / n) : 0;
+        const int il = valid ? (dec ? g - el * n : row - el * n) : 0, j0 = dec ? 0 : el * n;
+        const int env = dec ? el : row0 / n + el;
         si = 0;
 
         // ---------------- encoder layer 1: obs panels -> h[:, 0:64] in R0, h[:, 64:128] in R1 ----------------
@@ -488,12 +496,21 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
             const float4 *bp = reinterpret_cast<const float4 *>(bias_s + kBEnc2 + 16 * sub);
 #pragma unroll
             for (int q = 0; q < 4; ++q) tanh4(v + 4 * q, w + 4 * q, bp[q]);
+            if (!dec) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) KV[(16 * sub + c) * kTPitch + row] = v[c];
+                for (int c = 0; c < 16; ++c) KV[(16 * sub + c) * kTPitch + row] = v[c];
+            }
             write_act<16>(ACT, 64, row, 16 * sub, v);
-            load_mask(env, il, 0, valid);
-            run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR1, 0u, 0u});
         }
+        uint32_t tk = 0u, ep = 0u;                                                // sampling keys: latency hidden by the head
+        if (sub == 0 && valid && io.actions && !d.greedy && !io.sample_u) { tk = __ldg(io.tick + env); ep = __ldg(io.episode + env); }
+        if (dec) {
+            // Obs-DP (dec_categorical_mlp_policy.py:107-124): the embedding is the input of the 64 -> 32 layer
+            if (tile + (int)gridDim.x < n_tiles) stage_obs(tile + (int)gridDim.x);    // the second-operand / key-value area is idle
+            run_mma(1, MmaOp{kR1, 0u, 0u}, none);
+        } else {
+        load_mask(env, il, 0, valid);
+        run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR1, 0u, 0u});
         // ---------------- scores, softmax (exact per environment, CUDA cores); attention row -> TMEM ----------------
         CM_TP(0);
         {
@@ -608,14 +625,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         }
         // ---------------- categorical head ----------------
         run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR1, 0u, 0u});                       // 64 -> 128 as two output halves
-        uint32_t tk = 0u, ep = 0u;                                                // sampling keys: latency hidden by the head
-        if (sub == 0 && valid && io.actions && !d.greedy && !io.sample_u) { tk = __ldg(io.tick + env); ep = __ldg(io.episode + env); }
         epi64(kR0, kBH1, ACT);                                                    // 128 -> 64: two K panels, issued together
         epi64(kR1, kBH1 + 64, ACT2);
         run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR0, 1u, 1u});
         if (tile + (int)gridDim.x < n_tiles) stage_obs(tile + (int)gridDim.x);    // keys / values / ACT2 are dead: next tile's obs
         epi64(kR0, kBH2, ACT);                                                    // 64 -> 32
         run_mma(1, MmaOp{kR1, 0u, 0u}, none);
+        }   // Comm-DP
         {   // 32 -> 5 on the CUDA cores (exact fp32): this thread's 8 inputs -> 5 partial logits, parked in tensor memory
             float v[8], w[8], part[8];
             ld_acc_raw<8>(lane_addr + kR1, 32, 8 * sub, v, w);
@@ -736,14 +752,15 @@ static size_t tc_smem_bytes() { return (size_t)kActBytes + kWBytes + (64 + 8) * 
 int launch_policy_tc(const cm_policy_desc *desc, const cm_policy_io *io, cudaStream_t stream)
 {
     if (!io->tc_weights) return CM_EINVAL;
-    if (desc->n_agents > 64 || desc->obs_dim > 128) return CM_EUNSUPPORTED;
+    const bool dec = desc->kind == CM_POLICY_DEC;
+    if ((!dec && desc->n_agents > 64) || desc->obs_dim > 128) return CM_EUNSUPPORTED;
     if (io->n_envs * desc->n_agents > (int64_t)1 << 23) return CM_EUNSUPPORTED;      // 32-bit element indices inside the kernel
     TcArgs A;
     A.d = *desc;
     A.io = *io;
-    A.plan = make_tc_plan(desc->obs_dim, desc->n_layers);
-    A.envs_per_tile = kTcRows / desc->n_agents;
-    A.n_tiles = (io->n_envs + A.envs_per_tile - 1) / A.envs_per_tile;
+    A.plan = make_tc_plan(desc->obs_dim, desc->n_layers, desc->kind);
+    A.envs_per_tile = dec ? 0 : kTcRows / desc->n_agents;
+    A.n_tiles = dec ? (io->n_envs * desc->n_agents + kTcRows - 1) / kTcRows : (io->n_envs + A.envs_per_tile - 1) / A.envs_per_tile;
     const size_t smem = tc_smem_bytes();
     static thread_local struct { int dev; int sms; } cache = {-1, 0};
     int dev = 0;
@@ -780,7 +797,7 @@ extern "C" int cm_policy_tc_prepare(const cm_policy_desc *desc, const float *wei
     if (!desc || !weights || !tc_weights) return CM_EINVAL;
     if (desc->n_layers < 1 || desc->n_layers > CM_MAX_LAYERS || desc->obs_dim < 1 || desc->obs_dim > 128) return CM_EUNSUPPORTED;
     if (cm_device_count() < 1) return CM_ENODEVICE;
-    const cm::TcPlan P = cm::make_tc_plan(desc->obs_dim, desc->n_layers);
+    const cm::TcPlan P = cm::make_tc_plan(desc->obs_dim, desc->n_layers, desc->kind);
     cm::tc_prepare_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(weights, reinterpret_cast<__half *>(tc_weights), P);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? CM_OK : cm::set_cuda_error(e, CM_ECUDA);

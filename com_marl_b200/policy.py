@@ -82,6 +82,8 @@ class _GraphConv(nn.Module):
 
 
 class CommCategoricalMLPPolicy(nn.Module):
+    _kind = N.POLICY_COMM
+
     def __init__(self, env_spec, n_agents, encoder_hidden_sizes=(128,), embedding_dim=64, attention_type="general",
                  n_gcn_layers=2, residual=True, gcn_bias=True, categorical_mlp_hidden_sizes=(128, 64, 32),
                  name="comm_categorical_mlp_policy", device="cuda", seed=1, math="auto"):
@@ -156,7 +158,7 @@ class CommCategoricalMLPPolicy(nn.Module):
             L = self.n_gcn_layers
             n_floats = N.lib().cm_policy_tc_blob_floats(self._dec_obs_dim, L)
             out = torch.empty(n_floats, dtype=torch.float32, device=self.device)
-            desc = N.PolicyDesc(self._n_agents, self._dec_obs_dim, L, int(self.residual), 0, 1, self.seed, 0)
+            desc = N.PolicyDesc(self._n_agents, self._dec_obs_dim, L, int(self.residual), 0, 1, self.seed, 0, self._kind)
             with torch.cuda.device(self.device):
                 N.check("cm_policy_tc_prepare", N.lib().cm_policy_tc_prepare(C.byref(desc), N.ptr(blob), N.ptr(out), N.stream_ptr()))
             self._tc_blob, self._tc_sig = out, self._blob_sig
@@ -177,9 +179,9 @@ class CommCategoricalMLPPolicy(nn.Module):
         n, D, L = self._n_agents, self._dec_obs_dim, self.n_gcn_layers
         B = obs.shape[0]
         tc = self.uses_tensor_cores()
-        if tc and n > 64:
+        if tc and n > 64 and self._kind == N.POLICY_COMM:
             raise ValueError("math='tc' supports teams of at most 64 agents; use math='fp32'")
-        desc = N.PolicyDesc(n, D, L, int(self.residual), int(greedy), int(tc), self.seed, env_id0)
+        desc = N.PolicyDesc(n, D, L, int(self.residual), int(greedy), int(tc), self.seed, env_id0, self._kind)
         io = N.PolicyIO()
         io.n_envs = B
         io.weights = N.ptr(self.weight_blob())
@@ -190,7 +192,7 @@ class CommCategoricalMLPPolicy(nn.Module):
                      ("sample_u", sample_u), ("tick", tick), ("episode", episode), ("probs", probs), ("logits", logits),
                      ("attention", attention), ("actions", actions)):
             setattr(io, k, N.ptr(v))
-        if n > 64:      # large teams: per-CTA scratch, allocated once and reused
+        if n > 64 and self._kind == N.POLICY_COMM:      # large teams: per-CTA scratch, allocated once and reused
             need = N.lib().cm_policy_workspace_bytes(n, B)
             if self._workspace is None or self._workspace.numel() * 4 < need:
                 self._workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
@@ -325,6 +327,129 @@ class CommCategoricalMLPPolicy(nn.Module):
 
     def grad_norm(self):
         return np.sqrt(np.sum([p.grad.norm(2).item() ** 2 for p in self.parameters()]))
+
+    @property
+    def recurrent(self):
+        return False
+
+
+
+class DecCategoricalMLPPolicy(nn.Module):
+    """Obs-DP policy (no communication) with the reference's call signature and state_dict, backed by the same fused
+    tensor-core kernel (cm_policy_desc.kind = CM_POLICY_DEC).
+
+    Mirrors com_marl/torch/policies/dec_categorical_mlp_policy.py:14-232: per-agent encoder D -> hidden_sizes[0] ->
+    hidden_sizes[1] (tanh, MLPEncoderModule) followed by CategoricalMLPModule hidden_sizes[1] -> hidden_sizes[-1]
+    (tanh) -> 5 (:76-102); the policy itself IS the categorical module, so its parameters are ``_layers.0.linear.*`` /
+    ``_output_layers.0.linear.*`` next to ``encoder.*`` and reference checkpoints load with ``load_state_dict``.
+    ``get_actions(observations, avail_actions, greedy)`` runs the kernel; ``forward`` / ``entropy`` / ``log_likelihood``
+    (the differentiable training path, :198-226) are the same formula in torch ops."""
+    _kind = N.POLICY_DEC
+
+    def __init__(self, env_spec, n_agents, hidden_sizes=(128, 64, 32), name="DecCategoricalMLPPolicy", device="cuda", seed=1):
+        super().__init__()
+        if not hasattr(env_spec.action_space, "n"):
+            raise AssertionError("CategoricalMLPPolicy only works with akro.Discrete action space.")
+        if tuple(hidden_sizes) != (128, 64, 32):
+            raise NotImplementedError("the fused kernel is specialised for the runners' sizes hidden_sizes=(128, 64, 32) "
+                                      "(exp_runners/env_uitils.py:188-189)")
+        self.name, self.device = name, torch.device(device)
+        self.comm, self.centralized, self.step = False, True, 0
+        self.residual, self.math, self.n_gcn_layers = False, "tc", 1      # blob layout of one (unused) GCN layer
+        self._n_agents = int(n_agents)
+        self._dec_obs_dim = int(env_spec.observation_space.flat_dim / n_agents)
+        self._obs_dim = self._dec_obs_dim
+        self._action_dim = env_spec.action_space.n
+        self._embedding_dim = hidden_sizes[1]
+        self.seed = int(seed)
+        head = _MLP(self._embedding_dim, (hidden_sizes[-1],), self._action_dim, output_tanh=False)   # created first, like the reference
+        self._layers, self._output_layers = head._layers, head._output_layers
+        self.encoder = _MLP(self._dec_obs_dim, (hidden_sizes[0],), self._embedding_dim, output_tanh=True)
+        self.to(self.device)
+        self._blob = self._blob_sig = self._tc_blob = self._tc_sig = self._tc_error = self._workspace = None
+
+    _signature = CommCategoricalMLPPolicy._signature
+    tc_weight_blob = CommCategoricalMLPPolicy.tc_weight_blob
+    check_errors = CommCategoricalMLPPolicy.check_errors
+    _act_device = CommCategoricalMLPPolicy.act_device
+
+    def uses_tensor_cores(self):
+        return True
+
+    def weight_blob(self):
+        """the Comm-DP blob layout (include/commarl_b200.h) with the unused blocks zero: enc_w1/b1, enc_w2/b2 <- encoder,
+        head_w3/b3 <- _layers.0, head_w4/b4 <- _output_layers.0"""
+        sig = self._signature()
+        if self._blob is None or sig != self._blob_sig:
+            sd, E, dev = self.state_dict(), self._embedding_dim, self.device
+            z = lambda *shape: torch.zeros(shape, device=dev)  # noqa: E731
+            parts = [sd["encoder._layers.0.linear.weight"].t(), sd["encoder._layers.0.linear.bias"],
+                     sd["encoder._output_layers.0.linear.weight"].t(), sd["encoder._output_layers.0.linear.bias"],
+                     z(E, E), z(E, E), z(E), z(E, 128), z(128), z(128, 64), z(64),
+                     sd["_layers.0.linear.weight"].t(), sd["_layers.0.linear.bias"],
+                     sd["_output_layers.0.linear.weight"].t(), sd["_output_layers.0.linear.bias"]]
+            blob = torch.cat([p.detach().to(dev, torch.float32).contiguous().reshape(-1) for p in parts])
+            assert blob.numel() == N.lib().cm_policy_blob_floats(self._dec_obs_dim, 1)
+            self._blob, self._blob_sig = blob.contiguous(), sig
+        return self._blob
+
+    def act_device(self, obs, avail_bits=None, sample_u=None, tick=None, episode=None, greedy=False, probs=None, logits=None,
+                   actions=None, env_id0=0, **_unused):
+        """fused forward on device tensors (see CommCategoricalMLPPolicy.act_device); no masks, no attention output"""
+        self._act_device(obs, None, None, avail_bits, sample_u, tick, episode, greedy, probs, logits, None, actions, env_id0)
+
+    # ---- reference call surface ----
+    def forward(self, obs, avail_actions, get_actions=False):
+        if get_actions:
+            obs = torch.as_tensor(np.asarray(obs), dtype=torch.float32, device=self.device)
+            avail_actions = torch.as_tensor(np.asarray(avail_actions), dtype=torch.float32, device=self.device)
+        obs = obs.reshape(obs.shape[:-1] + (self._n_agents, -1))
+        x = self.encoder(obs)
+        x = torch.tanh(self._layers[0](x))
+        probs = torch.softmax(self._output_layers[0](x), dim=-1)
+        avail = avail_actions.reshape(avail_actions.shape[:-1] + (self._n_agents, -1))
+        masked = probs * avail
+        masked = masked / masked.sum(dim=-1, keepdim=True)
+        return Categorical(probs=masked.cpu() if get_actions else masked)
+
+    _host_calls = 0
+
+    def get_actions(self, observations, avail_actions, greedy=False):
+        """(B, n*D) observations, (B, n*5) availability -> (actions int64 (B, n), {'action_probs': [...]}) through the kernel"""
+        n, D, dev = self._n_agents, self._dec_obs_dim, self.device
+        obs = torch.as_tensor(np.asarray(observations), dtype=torch.float32)
+        single = obs.dim() == 1
+        obs = obs.reshape(-1, n, D).to(dev)
+        B = obs.shape[0]
+        av = torch.as_tensor(np.asarray(avail_actions), dtype=torch.float32).reshape(B, n, self._action_dim)
+        avail_bits = ((av != 0).float() * torch.tensor([1, 2, 4, 8, 16], dtype=torch.float32)).sum(-1).to(torch.uint8).to(dev)
+        probs = torch.empty((B, n, self._action_dim), dtype=torch.float32, device=dev)
+        actions = torch.empty((B, n), dtype=torch.int8, device=dev)
+        tick = torch.full((B,), self.step & 0x7FFFFFFF, dtype=torch.int32, device=dev)
+        episode = torch.full((B,), self._host_calls & 0xFFFFFF, dtype=torch.int32, device=dev)
+        self._host_calls += 1
+        self.act_device(obs, avail_bits, None, tick, episode, greedy, probs, None, actions)
+        self.check_errors()
+        a, pr = actions.cpu().numpy().astype(np.int64), probs.cpu().numpy()
+        if single:
+            a, pr = a[0], pr[0]
+        return a, {"action_probs": [pr[i] for i in range(len(a))]}
+
+    def log_likelihood(self, observations, avail_actions, actions):
+        return self.forward(observations, avail_actions).log_prob(actions).sum(axis=-1)
+
+    def entropy(self, observations, avail_actions):
+        return self.forward(observations, avail_actions).entropy().mean(axis=-1)
+
+    def reset(self, dones=None):
+        pass
+
+    def grad_norm(self):
+        return math.sqrt(sum(p.grad.norm(2).item() ** 2 for p in self.parameters() if p.grad is not None))
+
+    @property
+    def vectorized(self):
+        return True
 
     @property
     def recurrent(self):

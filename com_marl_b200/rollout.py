@@ -22,11 +22,14 @@ STAT_KEYS = ("episodes", "return_sum", "length_sum", "success_sum", "c0_sum", "m
 
 
 def make_policy(spec: ScenarioSpec, device="cuda", seed: Optional[int] = None, torch_seed: int = 1,
-                math: str = "auto") -> CommCategoricalMLPPolicy:
+                math: str = "auto", kind: str = "comm"):
     """Policy with the reference initialisation under torch.manual_seed(torch_seed)."""
     n, D = spec.n_agents, spec.obs_dim
     env_spec = EnvSpec(Box(np.zeros(n * D, np.float32), np.ones(n * D, np.float32)), Discrete(5))
     torch.manual_seed(torch_seed)
+    if kind == "dec":      # Obs-DP: no communication (dec_categorical_mlp_policy.py)
+        from .policy import DecCategoricalMLPPolicy
+        return DecCategoricalMLPPolicy(env_spec, n, device=device, seed=spec.seed if seed is None else seed)
     return CommCategoricalMLPPolicy(env_spec, n, n_gcn_layers=spec.n_layers, device=device,
                                     seed=spec.seed if seed is None else seed, math=math)
 
@@ -43,7 +46,7 @@ class RolloutEngine:
         # barrier between a step of one group and the next step of another, so partially filled waves of one launch
         # are covered by the launches of the other groups.  Results are identical for every G (global env ids key the
         # random streams).  Large teams (n > 64) share one policy scratch buffer and stay in a single group.
-        G = max(1, min(int(groups), self.B)) if spec.n_agents <= 64 else 1
+        G = max(1, min(int(groups), self.B)) if (spec.n_agents <= 64 or not getattr(policy, "comm", True)) else 1
         self.groups = G
         cuts = [self.B * g // G for g in range(G + 1)]
         self._ranges = [(cuts[g], cuts[g + 1]) for g in range(G) if cuts[g + 1] > cuts[g]]
@@ -79,7 +82,7 @@ class RolloutEngine:
             return
         t, e = self.traj, self._envs[g]
         b0, b1 = self._ranges[g]
-        self.policy.act_device(t["obs"][k, b0:b1], t["adj_bits"][k, b0:b1], t["chan_bits"][k, b0:b1], tick=e.tick, episode=e.episode,
+        self.policy.act_device(t["obs"][k, b0:b1], adj_bits=t["adj_bits"][k, b0:b1], chan_bits=t["chan_bits"][k, b0:b1], tick=e.tick, episode=e.episode,
                                greedy=self.greedy, probs=t["probs"][k, b0:b1], actions=t["actions"][k, b0:b1],
                                attention=t["attention"][k, b0:b1] if "attention" in t else None, env_id0=e.env_id0)
         e.step(t["actions"][k, b0:b1],

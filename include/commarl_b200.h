@@ -154,7 +154,14 @@ typedef struct cm_policy_desc {
                                   teams with n <= 64; needs io.tc_weights */
     uint64_t seed;
     int64_t env_id0;
+    int32_t kind;              /* cm_policy_kind: 0 = Comm-DP (CommCategoricalMLPPolicy), 1 = Obs-DP (DecCategoricalMLPPolicy:
+                                  per-agent encoder D -> 128 -> 64 (tanh) and head 64 -> 32 (tanh) -> 5, no communication;
+                                  dec_categorical_mlp_policy.py:107-124).  Obs-DP uses the same blob layout with enc_w1/b1,
+                                  enc_w2/b2, head_w3/b3, head_w4/b4 filled; tensor-core path only, any team size */
+    int32_t reserved_;
 } cm_policy_desc;
+
+typedef enum cm_policy_kind { CM_POLICY_COMM = 0, CM_POLICY_DEC = 1 } cm_policy_kind;
 
 typedef struct cm_policy_io {
     int64_t n_envs;            /* B */

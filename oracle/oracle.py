@@ -314,3 +314,24 @@ def policy_forward(w, obs, avail, adj, chan, dtype=np.float32):
         pr = pr * np.asarray(avail, dtype=f)
     pr = pr / pr.sum(axis=-1, keepdims=True)
     return logits.astype(f), pr.astype(f), M
+
+
+
+def policy_forward_dec(w, obs, avail, dtype=np.float32):
+    """Obs-DP forward (dec_categorical_mlp_policy.py:107-124): per-agent encoder (tanh, tanh) then the categorical MLP
+    (tanh, linear), softmax, availability mask, renormalisation.  w: dict keyed like the reference state_dict;
+    obs (B,n,D); avail (B,n,5) or None.  Returns logits, masked probs."""
+    f = dtype
+    g = lambda k: np.asarray(w[k], dtype=f)  # noqa: E731
+    x = np.asarray(obs, dtype=f)
+    h = np.tanh(x @ g("encoder._layers.0.linear.weight").T + g("encoder._layers.0.linear.bias"))
+    E = np.tanh(h @ g("encoder._output_layers.0.linear.weight").T + g("encoder._output_layers.0.linear.bias"))
+    X = np.tanh(E @ g("_layers.0.linear.weight").T + g("_layers.0.linear.bias"))
+    logits = X @ g("_output_layers.0.linear.weight").T + g("_output_layers.0.linear.bias")
+    z = logits - logits.max(axis=-1, keepdims=True)
+    pr = np.exp(z)
+    pr = pr / pr.sum(axis=-1, keepdims=True)
+    if avail is not None:
+        pr = pr * np.asarray(avail, dtype=f)
+    pr = pr / pr.sum(axis=-1, keepdims=True)
+    return logits.astype(f), pr.astype(f)

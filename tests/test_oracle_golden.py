@@ -3,6 +3,8 @@
 Bit-exact for grid state, observations, adjacency / channel masks, rewards, dones, counts
 (BASELINE.json north_star); policy logits within 1e-5 of the reference torch forward.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -90,3 +92,22 @@ def test_policy_oracle_matches_reference(name):
     # float64 evaluation agrees as well (the float32 reference is within rounding of the exact formula)
     logits64, _, _ = orc.policy_forward(c.weights, c.obs, c.avail, c.adj, c.chan, dtype=np.float64)
     assert np.abs(logits64 - c.logits).max() <= 1e-5 * scale
+
+
+def _dec_cases():
+    import glob
+    return sorted(os.path.basename(p)[7:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "decpol_*.npz")))
+
+
+@pytest.mark.parametrize("name", _dec_cases())
+def test_dec_policy_oracle_matches_reference(name):
+    """Obs-DP forward restatement (oracle.policy_forward_dec) against the vectors recorded from the unmodified reference
+    DecCategoricalMLPPolicy (tests/golden/make_golden_dec.py)."""
+    import json
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"decpol_{name}.npz"))
+    meta = json.loads(str(z["meta"]))
+    n, D, B = meta["n"], meta["D"], meta["B"]
+    w = {k[3:]: z[k] for k in z.files if k.startswith("w::")}
+    logits, probs = orc.policy_forward_dec(w, z["obs"].reshape(B, n, D), z["avail"].reshape(B, n, 5))
+    assert np.abs(logits - z["logits"].reshape(B, n, 5)).max() <= 1e-5
+    assert np.abs(probs - z["probs"].reshape(B, n, 5)).max() <= 1e-5
