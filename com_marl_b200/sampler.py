@@ -52,8 +52,11 @@ class DeviceRolloutSampler:
         spec = self._spec
         spec.max_path_length = int(self.algo.max_path_length or 0)
         policy = self.algo.policy
+        # a policy without communication (Obs-DP) has no attention: the reference stores None per step then
+        # (agent_info.get('attention_weights'), ...vectorized_sampler.py:186)
+        self._comm = bool(getattr(policy, "comm", False))
         self._engine = RolloutEngine(spec, policy, self._n_envs, device=policy.device, ring=self._chunk,
-                                     record_attention=True, use_graph=False)
+                                     record_attention=self._comm, use_graph=False)
 
     def shutdown_worker(self):
         self._engine = None
@@ -93,20 +96,26 @@ class DeviceRolloutSampler:
                     r["ave_deg"].append(t["ave_deg"][start:stop, b])
                     r["actions"].append(t["actions"][start:stop, b].astype(np.int64))
                     r["probs"].append(t["probs"][start:stop, b])
-                    r["attention"].append(t["attention"][start:stop, b])
+                    if self._comm:
+                        r["attention"].append(t["attention"][start:stop, b])
                     r["reward"].append(t["reward"][start:stop, b])
                     r["done"].append(t["done"][start:stop, b].astype(bool))
                     r["counts"].append(t["counts"][start:stop, b])
                     r["prey_alive"].append(t["prey_alive_out"][start:stop, b, :max(p, 1)].astype(bool))
                     if finished:
-                        c = {k: np.concatenate(v) for k, v in r.items()}
+                        c = {k: np.concatenate(v) for k, v in r.items() if v}
                         T_ = len(c["reward"])
+                        agent_infos = {"action_probs": c["probs"]}
+                        if self._comm:
+                            agent_infos["attention_weights"] = c["attention"]
+                        else:
+                            c["attention"] = np.full(T_, None, dtype=object)
                         paths.append(dict(
                             observations=c["obs"], actions=c["actions"],
                             avail_actions=np.ones((T_, n * 5), dtype=np.int64),
                             rewards=c["reward"], rewards_details=np.asarray(details_fn(c["counts"], c["reward"])),
                             env_infos={"prey_alive": c["prey_alive"]} if p else {},
-                            agent_infos={"action_probs": c["probs"], "attention_weights": c["attention"]},
+                            agent_infos=agent_infos,
                             dones=c["done"], dist_adjs=c["adj"],
                             ave_degs=(np.full(T_, n) if spec.rcom == 0 else c["ave_deg"]),
                             diameters=np.full(T_, n if spec.rcom == 0 else 0),

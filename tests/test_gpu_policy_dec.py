@@ -124,3 +124,30 @@ def test_dec_rollout_matches_oracle(scen):
             oenv.step(t["actions"][k])
             assert np.array_equal(t["reward"][k], oenv.reward) and np.array_equal(t["done"][k], oenv.done)
     eng.env.check_errors(); pol.check_errors()
+
+
+def test_dec_sampler_paths_contract():
+    """obtain_samples with the Obs-DP policy: the reference's path dicts, attentions = None per step (no communication)"""
+    import sys
+    from types import SimpleNamespace
+    sys.path.insert(0, GOLDEN)
+    import ref_harness
+    from com_marl_b200.envs import PredatorPreyWrapper
+    from com_marl_b200.rollout import make_policy
+    from com_marl_b200.sampler import DeviceRolloutSampler
+    params = ref_harness.scenario_params("pp", 10, 1, 0.08, cap=2, loss=0.2, max_env_steps=20)
+    env = PredatorPreyWrapper(centralized=True, other_agent_visible=True, params=params)
+    spec = env.spec_b200
+    n, D = spec.n_agents, spec.obs_dim
+    algo = SimpleNamespace(policy=make_policy(spec, kind="dec"), max_path_length=20)
+    sampler = DeviceRolloutSampler(algo, env, n_envs=8, chunk=10)
+    sampler.start_worker()
+    paths = sampler.obtain_samples(0, batch_size=8 * 20 * n)
+    assert paths
+    for pth in paths:
+        T = len(pth["rewards"])
+        assert pth["observations"].shape == (T, n * D) and pth["actions"].shape == (T, n)
+        assert set(pth["agent_infos"].keys()) == {"action_probs"} and pth["agent_infos"]["action_probs"].shape == (T, n, 5)
+        assert pth["attentions"].shape == (T,) and all(a is None for a in pth["attentions"])
+        assert pth["dist_adjs"].shape == (T, n * n) and pth["dones"][-1]
+    sampler.shutdown_worker()
