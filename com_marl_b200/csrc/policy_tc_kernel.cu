@@ -165,7 +165,7 @@ __device__ __forceinline__ void ld_acc(uint32_t blk, int N, int col, float (&v)[
 // each publishes the maximum m_s and the sum l_s = sum exp(score - m_s) of its keys, after the barrier
 // p = exp(score - m_s) * exp(m_s - M) / sum_s l_s exp(m_s - M).  Returns with every thread past the barrier (the
 // query block and the keys are dead); the caller parks the probabilities sc[] in tensor memory.
-template <int KT>
+template <int KT, int kVec>
 __device__ __forceinline__ void scores_softmax(uint32_t lane_addr, const float *KV, float *red, float *attn_row, int row, int j0,
                                                int sub, int n, bool valid)
 {
@@ -179,12 +179,42 @@ __device__ __forceinline__ void scores_softmax(uint32_t lane_addr, const float *
         float q[16];
         ld_acc<16>(lane_addr + kR0, 64, c, q);
         if (nk > 0 && !(CM_TC_DEBUG & 4)) {
+            // the keys of a thread are consecutive floats of a k-major row: 128-bit / 64-bit shared-memory loads when the
+            // team size keeps them aligned (the loop is bound by shared-memory instructions, not by the FMAs)
+            if (KT >= 4 && kVec == 4) {
 #pragma unroll
-            for (int kk = 0; kk < 16; ++kk) {
-                const float *er = er0 + (c + kk) * kTPitch;
+                for (int kk = 0; kk < 16; ++kk) {
+                    const float4 *e4 = reinterpret_cast<const float4 *>(er0 + (c + kk) * kTPitch);
 #pragma unroll
-                for (int t = 0; t < KT; ++t)
-                    if (t < nk) sc[t] = fmaf(q[kk], er[t], sc[t]);
+                    for (int t = 0; t < KT; t += 4)
+                        if (t < nk) {
+                            const float4 ev = e4[t >> 2];
+                            sc[t] = fmaf(q[kk], ev.x, sc[t]);
+                            sc[(t + 1) % KT] = fmaf(q[kk], ev.y, sc[(t + 1) % KT]);
+                            sc[(t + 2) % KT] = fmaf(q[kk], ev.z, sc[(t + 2) % KT]);
+                            sc[(t + 3) % KT] = fmaf(q[kk], ev.w, sc[(t + 3) % KT]);
+                        }
+                }
+            } else if (KT >= 2 && kVec >= 2) {
+#pragma unroll
+                for (int kk = 0; kk < 16; ++kk) {
+                    const float2 *e2 = reinterpret_cast<const float2 *>(er0 + (c + kk) * kTPitch);
+#pragma unroll
+                    for (int t = 0; t < KT; t += 2)
+                        if (t < nk) {
+                            const float2 ev = e2[t >> 1];
+                            sc[t] = fmaf(q[kk], ev.x, sc[t]);
+                            sc[(t + 1) % KT] = fmaf(q[kk], ev.y, sc[(t + 1) % KT]);
+                        }
+                }
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < 16; ++kk) {
+                    const float *er = er0 + (c + kk) * kTPitch;
+#pragma unroll
+                    for (int t = 0; t < KT; ++t)
+                        if (t < nk) sc[t] = fmaf(q[kk], er[t], sc[t]);
+                }
             }
         }
     }
@@ -242,6 +272,10 @@ struct MmaOp { uint32_t dcol, acc, abuf; };   // accumulator block, accumulate f
 #define CM_TPK(slot) do { } while (0)
 #endif
 
+// kVec: width (in floats) of the shared-memory loads of the attention loops — 4 when the team size is a multiple of 4,
+// 2 when it is even, else 1 (the keys / values of an env start at a multiple of n floats).  One instantiation per width,
+// so that small odd teams (n = 3) carry none of the vector code.
+template <int kVec>
 __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -516,11 +550,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         {
             float *attn_row = (io.attention && valid) ? io.attention + (size_t)g * n : nullptr;
             switch (n <= 4 ? 1 : (n <= 8 ? 2 : (n <= 16 ? 4 : (n <= 32 ? 8 : 16)))) {
-            case 1: scores_softmax<1>(lane_addr, KV, red, attn_row, row, j0, sub, n, valid); break;
-            case 2: scores_softmax<2>(lane_addr, KV, red, attn_row, row, j0, sub, n, valid); break;
-            case 4: scores_softmax<4>(lane_addr, KV, red, attn_row, row, j0, sub, n, valid); break;
-            case 8: scores_softmax<8>(lane_addr, KV, red, attn_row, row, j0, sub, n, valid); break;
-            default: scores_softmax<16>(lane_addr, KV, red, attn_row, row, j0, sub, n, valid); break;
+            case 1: scores_softmax<1, kVec>(lane_addr, KV, red, attn_row, row, j0, sub, n, valid); break;
+            case 2: scores_softmax<2, kVec>(lane_addr, KV, red, attn_row, row, j0, sub, n, valid); break;
+            case 4: scores_softmax<4, kVec>(lane_addr, KV, red, attn_row, row, j0, sub, n, valid); break;
+            case 8: scores_softmax<8, kVec>(lane_addr, KV, red, attn_row, row, j0, sub, n, valid); break;
+            default: scores_softmax<16, kVec>(lane_addr, KV, red, attn_row, row, j0, sub, n, valid); break;
             }
         }
         // H_0 Wg_0 replaces the keys (everybody is past the softmax barrier)
@@ -549,17 +583,42 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                 tmem_ld8(lane_addr + kColM + (uint32_t)c0, a8);
                 tmem_ld_wait();
                 if (!(CM_TC_DEBUG & 4)) {
+                    // mask the chunk's attention values (same key order as the scalar loop: the sums are bit-identical)
+                    const uint32_t mbits = (c0 < 32 ? m0 : m1) >> (c0 & 31);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int jj = c0 + j;
-                        if (jj < n) {
-                            const uint32_t bit = ((jj < 32 ? m0 : m1) >> (jj & 31)) & 1u;
-                            const float a = bit ? a8[j] : 0.0f;
-                            den += a;
-                            const float *hw = hw0 + jj;
+                    for (int j = 0; j < 8; ++j) a8[j] = (c0 + j < n && ((mbits >> j) & 1u)) ? a8[j] : 0.0f;
+                    // the values of consecutive keys are consecutive floats of a k-major row: vector loads when aligned
+                    if (kVec == 4) {
 #pragma unroll
-                            for (int c = 0; c < 16; ++c) acc[c] = fmaf(a, hw[c * kTPitch], acc[c]);
-                        }
+                        for (int j = 0; j < 8; j += 4)
+                            if (c0 + j < n) {
+                                den += a8[j]; den += a8[j + 1]; den += a8[j + 2]; den += a8[j + 3];
+#pragma unroll
+                                for (int c = 0; c < 16; ++c) {
+                                    const float4 h = *reinterpret_cast<const float4 *>(hw0 + c * kTPitch + c0 + j);
+                                    acc[c] = fmaf(a8[j + 3], h.w, fmaf(a8[j + 2], h.z, fmaf(a8[j + 1], h.y, fmaf(a8[j], h.x, acc[c]))));
+                                }
+                            }
+                    } else if (kVec == 2) {
+#pragma unroll
+                        for (int j = 0; j < 8; j += 2)
+                            if (c0 + j < n) {
+                                den += a8[j]; den += a8[j + 1];
+#pragma unroll
+                                for (int c = 0; c < 16; ++c) {
+                                    const float2 h = *reinterpret_cast<const float2 *>(hw0 + c * kTPitch + c0 + j);
+                                    acc[c] = fmaf(a8[j + 1], h.y, fmaf(a8[j], h.x, acc[c]));
+                                }
+                            }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (c0 + j < n) {
+                                den += a8[j];
+                                const float *hw = hw0 + c0 + j;
+#pragma unroll
+                                for (int c = 0; c < 16; ++c) acc[c] = fmaf(a8[j], hw[c * kTPitch], acc[c]);
+                            }
                     }
                 }
             }
@@ -762,24 +821,27 @@ int launch_policy_tc(const cm_policy_desc *desc, const cm_policy_io *io, cudaStr
     A.envs_per_tile = dec ? 0 : kTcRows / desc->n_agents;
     A.n_tiles = dec ? (io->n_envs * desc->n_agents + kTcRows - 1) / kTcRows : (io->n_envs + A.envs_per_tile - 1) / A.envs_per_tile;
     const size_t smem = tc_smem_bytes();
-    static thread_local struct { int dev; int sms; } cache = {-1, 0};
+    const int vec = dec ? 1 : ((desc->n_agents & 3) == 0 ? 4 : ((desc->n_agents & 1) == 0 ? 2 : 1));
+    void (*kernel)(const TcArgs) = vec == 4 ? policy_tc_kernel<4> : (vec == 2 ? policy_tc_kernel<2> : policy_tc_kernel<1>);
+    static thread_local struct { int dev; int sms; } cache[3] = {{-1, 0}, {-1, 0}, {-1, 0}};
+    auto &cc = cache[vec >> 1];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ENODEVICE);
-    if (cache.dev != dev) {
+    if (cc.dev != dev) {
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ECUDA);
-        cudaError_t e = cudaFuncSetAttribute(policy_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
-        e = cudaFuncSetAttribute(policy_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
-        cache.dev = dev; cache.sms = sms;
+        cc.dev = dev; cc.sms = sms;
     }
-    int slots = 2 * cache.sms;                                                // persistent: two CTAs per SM
+    int slots = 2 * cc.sms;                                                   // persistent: two CTAs per SM
 #ifdef CM_TC_TRACE
-    if (const char *ev = getenv("CM_TC_SLOTS")) slots = atoi(ev) * cache.sms;   // experiments only
+    if (const char *ev = getenv("CM_TC_SLOTS")) slots = atoi(ev) * cc.sms;      // experiments only
 #endif
     const int grid = (int)(A.n_tiles < slots ? A.n_tiles : slots);
-    policy_tc_kernel<<<grid, kTcThreads, smem, stream>>>(A);
+    kernel<<<grid, kTcThreads, smem, stream>>>(A);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
     return CM_OK;

@@ -6,6 +6,7 @@ usage: python tools/summarize_ncu.py <tag> <cfg>
 """
 import csv
 import json
+import re
 import os
 import shutil
 import sys
@@ -30,6 +31,11 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__warp_issue_stalled_not_selected_per_warp_active.pct", "smsp__warp_issue_stalled_selected_per_warp_active.pct"]
 
 
+def _kname(full):
+    """cm::policy_tc_kernel<1>(cm::TcArgs) -> policy_tc_kernel"""
+    return re.sub(r"<.*>", "", full.split("(")[0]).split("::")[-1].strip()
+
+
 def main(tag, cfg):
     out = os.path.join(ROOT, "gpurun_out")
     prof = os.path.join(ROOT, "profiles")
@@ -43,7 +49,7 @@ def main(tag, cfg):
         hdr = rows[0]
         ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
         for r in rows[1:]:
-            k = r[ki].split("(")[0]
+            k = _kname(r[ki])
             tot[k] += float(r[vi].replace(",", "")); cnt[k] += 1
         s = sum(tot.values())
         for k in tot:
@@ -63,7 +69,7 @@ def main(tag, cfg):
             csv.writer(f).writerows(lines)
         tr = {}
         for d in data:
-            k = d[col["Kernel Name"]].split("(")[0]
+            k = _kname(d[col["Kernel Name"]])
             def val(name):
                 v = float(d[col[name]].replace(",", "")); u = units[col[name]].lower()
                 return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
