@@ -423,7 +423,7 @@ __device__ void write_obs(const EnvArgs &A, const Scratch &S, const u64 *wall, i
 #define CM_ETP(k) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32) env_kernel(const EnvArgs A)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) env_kernel(const EnvArgs A)
 {
 #ifdef CM_ENV_TRACE
     long long trace_t[12] = {0};

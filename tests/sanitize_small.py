@@ -29,6 +29,16 @@ def main():
         pol.check_errors()
         assert np.isfinite(eng.traj["probs"].cpu().numpy()).all()
         print(scen, m, "n =", spec.n_agents, "episodes finished:", int(eng.local_stats()[0].item()))
+    # Obs-DP policy (rows independent of the team) and env groups on separate streams inside a captured graph
+    spec = ScenarioSpec.from_cli("co", 10, 1, 0.03, cap=2, loss=0.1, seed=3, max_env_steps=6)
+    pol = make_policy(spec, kind="dec")
+    eng = RolloutEngine(spec, pol, 50, ring=3, use_graph=True, groups=3)
+    eng.reset()
+    eng.run(9)
+    torch.cuda.synchronize()
+    eng.env.check_errors()
+    pol.check_errors()
+    print("obs-dp / env groups ok")
     # Gilbert-Elliot channel + comm-only entry point + mask converters
     spec = ScenarioSpec.from_cli("pp", 10, 1, 0.08, cap=2, loss=0.2, channel_type="GE", max_env_steps=5)
     from com_marl_b200.envs import BatchedEnv
