@@ -33,7 +33,7 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 def _kname(full):
     """cm::policy_tc_kernel<1>(cm::TcArgs) -> policy_tc_kernel"""
-    return re.sub(r"<.*>", "", full.split("(")[0]).split("::")[-1].strip()
+    return re.sub(r"<.*>", "", full.split("(")[0]).split("::")[-1].replace("void ", "").strip()
 
 
 def main(tag, cfg):
