@@ -3,7 +3,7 @@ communication graph / packet loss + comm-GNN policy forward).  See DESIGN.md."""
 from .scenario import ScenarioSpec  # noqa: F401
 
 __all__ = ["ScenarioSpec", "BatchedEnv", "PredatorPreyWrapper", "CoverageWrapper", "CommCategoricalMLPPolicy",
-           "DecCategoricalMLPPolicy", "RolloutEngine", "DeviceRolloutSampler"]
+           "DecCategoricalMLPPolicy", "RolloutEngine", "eval_model", "DeviceRolloutSampler"]
 
 
 def __getattr__(name):
@@ -17,6 +17,9 @@ def __getattr__(name):
     if name == "RolloutEngine":
         from .rollout import RolloutEngine
         return RolloutEngine
+    if name == "eval_model":
+        from .evaluate import eval_model
+        return eval_model
     if name == "DeviceRolloutSampler":
         from .sampler import DeviceRolloutSampler
         return DeviceRolloutSampler

@@ -37,10 +37,10 @@ def make_policy(spec: ScenarioSpec, device="cuda", seed: Optional[int] = None, t
 class RolloutEngine:
     def __init__(self, spec: ScenarioSpec, policy: CommCategoricalMLPPolicy, n_envs: int, device="cuda", env_id0: int = 0,
                  ring: int = 8, record_attention: bool = False, greedy: bool = False, use_graph: bool = True,
-                 groups: int = 1):
+                 groups: int = 1, auto_reset: bool = True):
         self.spec, self.policy, self.B = spec, policy, int(n_envs)
         self.device = torch.device(device)
-        self.env = BatchedEnv(spec, n_envs, device=device, env_id0=env_id0, auto_reset=True)
+        self.env = BatchedEnv(spec, n_envs, device=device, env_id0=env_id0, auto_reset=auto_reset)
         # Env groups: the envs are independent, so G contiguous groups form G independent policy -> step -> policy ...
         # chains.  Each chain runs on its own stream (forked / joined inside the captured graph): there is no device-wide
         # barrier between a step of one group and the next step of another, so partially filled waves of one launch
