@@ -151,3 +151,21 @@ def test_dec_sampler_paths_contract():
         assert pth["attentions"].shape == (T,) and all(a is None for a in pth["attentions"])
         assert pth["dist_adjs"].shape == (T, n * n) and pth["dones"][-1]
     sampler.shutdown_worker()
+
+
+def test_policy_kind_error_codes():
+    """C-ABI error behaviour of the new descriptor field: unknown kinds are rejected, Obs-DP needs the tensor-core path."""
+    import ctypes as C
+    from com_marl_b200 import _native as N
+    n, D, B = 3, 29, 8
+    pol = _policy(n, D)
+    obs = torch.zeros((B, n, D), device="cuda")
+    probs = torch.empty((B, n, 5), device="cuda")
+    io = N.PolicyIO()
+    io.n_envs, io.weights, io.tc_weights = B, N.ptr(pol.weight_blob()), N.ptr(pol.tc_weight_blob())
+    io.obs, io.probs = N.ptr(obs), N.ptr(probs)
+    for kind, math, expect in ((7, 1, N.CM_EINVAL), (N.POLICY_DEC, 0, N.CM_EUNSUPPORTED), (N.POLICY_DEC, 1, N.CM_OK)):
+        desc = N.PolicyDesc(n, D, 1, 0, 1, math, 1, 0, kind)
+        assert N.lib().cm_policy_forward(C.byref(desc), C.byref(io), N.stream_ptr()) == expect, (kind, math)
+    torch.cuda.synchronize()
+    assert torch.isfinite(probs).all()
