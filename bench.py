@@ -401,14 +401,16 @@ def run_b200_arm(args):
     flops = policy_flops_per_agent(Dobs, n, L) * Bk * n               # per launch (one env group)
     env_bytes = env_bytes_per_agent_step(spec) * Bk * n
     tc = pol.uses_tensor_cores()
-    kname = "policy_tc_kernel" if tc else ("policy_small_kernel" if n <= 64 else "policy_large_kernel")
+    kname = ("policy_tc_kernel" if n <= 64 else "policy_tc_kernel(enc) + policy_attn_kernel + policy_tc_kernel(head)") if tc \
+        else ("policy_small_kernel" if n <= 64 else "policy_large_kernel")
     kdesc = ("the kernel issues A_hi x [B_hi;B_lo] and A_lo x B_hi in fp16 per algorithmic product (error compensation) on K "
              "padded to 16/64, so the tensor pipe executes ~3.3x the algorithmic FLOPs counted here" if tc
              else "the kernel itself is exact fp32 FFMA")
     # what the tensor pipe actually executes per 128-row tile: 3 passes over the padded dense layers
     Dp = (Dobs + 15) // 16 * 16
     dense_mac = Dp * 128 + 128 * 64 + 64 * 64 * (1 + L) + 64 * 128 + 128 * 64 + 64 * 32 + 32 * 16
-    tc_flops = (3 * 2 * dense_mac * 128 * ((Bk * n + (128 // n) * n - 1) // ((128 // n) * n))) if tc else 0
+    rows_per_tile = (128 // n) * n if n <= 64 else 128            # whole envs per tile (n <= 64) / any 128 rows (large teams)
+    tc_flops = (3 * 2 * dense_mac * 128 * ((Bk * n + rows_per_tile - 1) // rows_per_tile)) if tc else 0
     pol_tflops = flops / (pol_ms * 1e-3) / 1e12
     env_gbs = env_bytes / (env_ms * 1e-3) / 1e9
     line = {

@@ -565,6 +565,7 @@ static int round_up_tile(int n) { return (n + kTile - 1) / kTile * kTile; }
 static size_t large_ws_floats(int n) { return (size_t)3 * kE * round_up_tile(n); }
 
 int launch_policy_tc(const cm_policy_desc *desc, const cm_policy_io *io, cudaStream_t stream);   // policy_tc_kernel.cu
+size_t tc_large_ws_floats(int n, int64_t n_envs);                                                // policy_attn_kernel.cu
 
 struct LaunchCache { int dev; int ctas_per_sm; int sms; };
 
@@ -599,7 +600,8 @@ extern "C" size_t cm_policy_workspace_bytes(int32_t n_agents, int64_t n_envs)
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     else cudaGetLastError();
     const int64_t ctas = n_envs < 2 * (int64_t)sms ? n_envs : 2 * (int64_t)sms;
-    return (size_t)ctas * cm::large_ws_floats(n_agents) * sizeof(float);
+    const size_t ffma = (size_t)ctas * cm::large_ws_floats(n_agents), tcp = cm::tc_large_ws_floats(n_agents, n_envs);
+    return (ffma > tcp ? ffma : tcp) * sizeof(float);      // whichever kernel family the caller picks with desc.math
 }
 
 extern "C" int cm_policy_forward(const cm_policy_desc *desc, const cm_policy_io *io, cm_stream_t stream)

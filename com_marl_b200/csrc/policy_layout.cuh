@@ -63,40 +63,66 @@ struct TcPlan {
     TcStage st[kTcMaxStages];
 };
 
-__host__ __device__ inline TcPlan make_tc_plan(int D, int L, int kind = CM_POLICY_COMM)
+// Kernel modes.  COMM and DEC are the public policy kinds; ENC and HEAD are the row-wise halves of the large-team
+// pipeline (teams of more than 64 agents: encoder + first value projection, then the attention kernel, then the head).
+// All of them read the SAME prepared blob: the stage list of COMM contains every product, the other modes use a
+// sub-list of it with the original offsets.
+enum { kTcModeComm = 0, kTcModeDec = 1, kTcModeEnc = 2, kTcModeHead = 3 };
+
+__host__ __device__ inline TcPlan make_tc_plan(int D, int L, int mode = kTcModeComm)
 {
     const Blob o = blob_layout(D, L);
-    TcPlan P;
+    TcPlan F;                                 // the full (COMM) list
     int s = 0, off = 0;
     auto add = [&](int src_off, int N, int Kp, int k0, int n0, int Ksrc, int Nsrc) {
-        P.st[s].w_off = off; P.st[s].src_off = src_off; P.st[s].N = N; P.st[s].Kp = Kp; P.st[s].k0 = k0; P.st[s].n0 = n0;
-        P.st[s].Ksrc = Ksrc; P.st[s].Nsrc = Nsrc;
+        F.st[s].w_off = off; F.st[s].src_off = src_off; F.st[s].N = N; F.st[s].Kp = Kp; F.st[s].k0 = k0; F.st[s].n0 = n0;
+        F.st[s].Ksrc = Ksrc; F.st[s].Nsrc = Nsrc;
         off += 2 * N * Kp;
         return s++;
     };
     const int Dp = (D + 15) / 16 * 16;
-    P.l1_panels = Dp > 64 ? 2 : 1;
-    for (int pnl = 0; pnl < P.l1_panels; ++pnl) {
+    const int panels = Dp > 64 ? 2 : 1;
+    for (int pnl = 0; pnl < panels; ++pnl) {
         const int Kp = pnl == 0 ? (Dp <= 64 ? Dp : 64) : Dp - 64;
         add(o.enc_w1, 64, Kp, 64 * pnl, 0, D, kH1);                      // h[:, 0:64]
         add(o.enc_w1, 64, Kp, 64 * pnl, 64, D, kH1);                     // h[:, 64:128]
     }
     add(o.enc_w2, kE, 64, 0, 0, kH1, kE);
     add(o.enc_w2, kE, 64, 64, 0, kH1, kE);
-    if (kind == CM_POLICY_COMM) {
-        add(o.att_w, kE, 64, 0, 0, kE, kE);
-        for (int l = 0; l < L; ++l) add(o.gcn_w + l * kE * kE, kE, 64, 0, 0, kE, kE);
-        add(o.head_w1, 64, 64, 0, 0, kE, kC1);
-        add(o.head_w1, 64, 64, 0, 64, kE, kC1);
-        add(o.head_w2, kC2, 64, 0, 0, kC1, kC2);
-        add(o.head_w2, kC2, 64, 64, 0, kC1, kC2);
-    }                                                                    // Obs-DP: the embedding feeds the 64 -> 32 layer directly
+    const int i_att = s;
+    add(o.att_w, kE, 64, 0, 0, kE, kE);
+    for (int l = 0; l < L; ++l) add(o.gcn_w + l * kE * kE, kE, 64, 0, 0, kE, kE);
+    const int i_head = s;
+    add(o.head_w1, 64, 64, 0, 0, kE, kC1);
+    add(o.head_w1, 64, 64, 0, 64, kE, kC1);
+    add(o.head_w2, kC2, 64, 0, 0, kC1, kC2);
+    add(o.head_w2, kC2, 64, 64, 0, kC1, kC2);
+    const int i_head3 = s;
     add(o.head_w3, kC3, 64, 0, 0, kC2, kC3);
     // (the last layer, 32 -> 5, runs on the CUDA cores in exact fp32)
-    P.n_stages = s;
-    P.seq_len = s;
+    F.n_stages = s;
+    F.total_halves = off;
+    // sub-list of the mode
+    TcPlan P;
     P.total_halves = off;
+    P.l1_panels = mode == kTcModeHead ? 1 : panels;
+    int t = 0;
+    auto take = [&](int a, int b) { for (int i = a; i < b; ++i) P.st[t++] = F.st[i]; };
+    if (mode == kTcModeComm) take(0, s);
+    else if (mode == kTcModeDec) { take(0, i_att); take(i_head3, s); }        // Obs-DP: the embedding feeds the 64 -> 32 layer
+    else if (mode == kTcModeEnc) take(0, i_att + 2);                          // ... attention query, H_0 Wg_0
+    else take(i_head, s);                                                     // head on X = E + H_L
+    P.n_stages = t;
+    P.seq_len = t;
     return P;
+}
+
+// offset (in halves) of the graph-convolution weight stage of layer l inside the prepared blob
+__host__ __device__ inline TcStage tc_gcn_stage(int D, int L, int l)
+{
+    const TcPlan F = make_tc_plan(D, L, kTcModeComm);
+    const int panels = ((D + 15) / 16 * 16) > 64 ? 2 : 1;
+    return F.st[2 * panels + 2 + 1 + l];
 }
 
 }  // namespace cm

@@ -55,6 +55,9 @@ struct TcArgs {
     TcPlan plan;
     int envs_per_tile;
     int64_t n_tiles;
+    int mode;                    // kTcModeComm / Dec / Enc / Head
+    int in_dim;                  // width of the input rows (obs_dim; 64 in head mode: the rows are X = E + H_L)
+    float *scr_e, *scr_q, *scr_hw;   // encoder mode: row-major [rows][64] outputs E, Q = E Wq, H_0 Wg_0 (large-team pipeline)
 };
 
 // fp16 split of one value: hi = fp16(x), lo = fp16((x - hi) * 4096)
@@ -433,7 +436,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
     float *stage = KV;
     constexpr int kStageFloats = (64 + 8) * kTPitch - 4;
     // rows of tile tl: whole environments (Comm-DP: the attention stays inside a tile) or any 128 agent rows (Obs-DP)
-    const bool dec = d.kind == CM_POLICY_DEC;
+    const int mode = A.mode, Din = A.in_dim;
+    const bool dec = mode != kTcModeComm;            // every mode but Comm-DP treats the agent rows independently
     const int total_rows = n_envs * n;
     auto tile_rows = [&](int tl, int &r0, int &nr) {
         if (dec) { r0 = tl * kTcRows; nr = min(kTcRows, total_rows - r0); }
@@ -442,9 +446,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
     auto stage_obs = [&](int tl) {
         int r0s, rws;
         tile_rows(tl, r0s, rws);
-        const float *src = io.obs + (size_t)r0s * D;
+        const float *src = io.obs + (size_t)r0s * Din;
         const int a = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
-        const int ns = min(rws * D, kStageFloats);
+        const int ns = min(rws * Din, kStageFloats);
         const int nq = (a + ns + 3) >> 2;
         const uint32_t sbase = smem_u32(stage);
         for (int q = tid; q < nq; q += kTcThreads) {
@@ -487,6 +491,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         const int el = valid ? (dec ? g / n : row / n) : 0;
         const int il = valid ? (dec ? g - el * n : row - el * n) : 0, j0 = dec ? 0 : el * n;
         const int env = dec ? el : row0 / n + el;
+        const bool next_has = tile + (int)gridDim.x < n_tiles;
         si = 0;
 
         // ---------------- encoder layer 1: obs panels -> h[:, 0:64] in R0, h[:, 64:128] in R1 ----------------
@@ -495,9 +500,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         __syncthreads();                                   // the staged observations of this tile are visible
         CM_TP(19);
         {
-            const float *src = io.obs + (size_t)row0 * D;
+            const float *src = io.obs + (size_t)row0 * Din;
             const int a = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
-            const int total_f = rows * D, ns = min(total_f, kStageFloats);
+            const int total_f = rows * Din, ns = min(total_f, kStageFloats);
             for (int pnl = 0; pnl < P.l1_panels; ++pnl) {
                 const int Kp = P.st[si].Kp, kofs = 64 * pnl, kg = Kp >> 3;          // kg = 2, 4, 6 or 8 groups of 8 columns
                 const uint32_t lo_off = (uint32_t)kTcRows * Kp * 2, inv = (65536u + (uint32_t)kg - 1u) / (uint32_t)kg;
@@ -506,9 +511,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                     __align__(16) __half h[8], l[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int k = kofs + k8 + j, i = r * D + k;
+                        const int k = kofs + k8 + j, i = r * Din + k;
                         float x = 0.0f;
-                        if (r < rows && k < D) x = i < ns ? stage[a + i] : __ldg(src + i);
+                        if (r < rows && k < Din) x = i < ns ? stage[a + i] : __ldg(src + i);
                         split16(x, h[j], l[j]);
                     }
                     const uint32_t off = canon_off16(r, k8, Kp);
@@ -519,6 +524,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
             }
         }
         // ---------------- encoder layer 2 (K = 128 as the two panels of h) -> R0 ----------------
+        if (mode != kTcModeHead) {          // head mode: the two products above already were the first head layer
         // (the second K panel of the A operand lives in the idle key / value buffer, so both products issue together)
         epi64(kR0, kBEnc1, ACT);
         epi64(kR1, kBEnc1 + 64, ACT2);
@@ -534,15 +540,38 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
 #pragma unroll
                 for (int c = 0; c < 16; ++c) KV[(16 * sub + c) * kTPitch + row] = v[c];
             }
+            if (mode == kTcModeEnc && valid) {                        // E rows for the attention kernel (keys, residual)
+#pragma unroll
+                for (int c = 0; c < 16; c += 4)
+                    *reinterpret_cast<float4 *>(A.scr_e + (size_t)g * kE + 16 * sub + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            }
             write_act<16>(ACT, 64, row, 16 * sub, v);
         }
+        }   // mode != head
         uint32_t tk = 0u, ep = 0u;                                                // sampling keys: latency hidden by the head
-        if (sub == 0 && valid && io.actions && !d.greedy && !io.sample_u) { tk = __ldg(io.tick + env); ep = __ldg(io.episode + env); }
-        if (dec) {
+        if (mode != kTcModeEnc && sub == 0 && valid && io.actions && !d.greedy && !io.sample_u) { tk = __ldg(io.tick + env); ep = __ldg(io.episode + env); }
+        if (mode == kTcModeEnc) {
+            // large-team pipeline, first half: Q = E Wq and H_0 Wg_0 as rows in global scratch; the attention kernel takes over
+            if (next_has) stage_obs(tile + (int)gridDim.x);
+            run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR1, 0u, 0u});
+            float q[16], hw[16];
+            ld_acc<16>(lane_addr + kR0, 64, 16 * sub, q);
+            ld_acc<16>(lane_addr + kR1, 64, 16 * sub, hw);
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 16; c += 4) {
+                    *reinterpret_cast<float4 *>(A.scr_q + (size_t)g * kE + 16 * sub + c) = make_float4(q[c], q[c + 1], q[c + 2], q[c + 3]);
+                    *reinterpret_cast<float4 *>(A.scr_hw + (size_t)g * kE + 16 * sub + c) = make_float4(hw[c], hw[c + 1], hw[c + 2], hw[c + 3]);
+                }
+            }
+            continue;
+        }
+        if (mode == kTcModeDec) {
             // Obs-DP (dec_categorical_mlp_policy.py:107-124): the embedding is the input of the 64 -> 32 layer
-            if (tile + (int)gridDim.x < n_tiles) stage_obs(tile + (int)gridDim.x);    // the second-operand / key-value area is idle
+            if (next_has) stage_obs(tile + (int)gridDim.x);                           // the second-operand / key-value area is idle
             run_mma(1, MmaOp{kR1, 0u, 0u}, none);
         } else {
+        if (mode == kTcModeComm) {
         load_mask(env, il, 0, valid);
         run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR1, 0u, 0u});
         // ---------------- scores, softmax (exact per environment, CUDA cores); attention row -> TMEM ----------------
@@ -684,13 +713,14 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         }
         // ---------------- categorical head ----------------
         run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR1, 0u, 0u});                       // 64 -> 128 as two output halves
+        }   // Comm-DP only (head mode enters here: its first two products came with the input rows)
         epi64(kR0, kBH1, ACT);                                                    // 128 -> 64: two K panels, issued together
         epi64(kR1, kBH1 + 64, ACT2);
         run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR0, 1u, 1u});
-        if (tile + (int)gridDim.x < n_tiles) stage_obs(tile + (int)gridDim.x);    // keys / values / ACT2 are dead: next tile's obs
+        if (next_has) stage_obs(tile + (int)gridDim.x);                           // keys / values / ACT2 are dead: next tile's obs
         epi64(kR0, kBH2, ACT);                                                    // 64 -> 32
         run_mma(1, MmaOp{kR1, 0u, 0u}, none);
-        }   // Comm-DP
+        }   // Comm-DP / head
         {   // 32 -> 5 on the CUDA cores (exact fp32): this thread's 8 inputs -> 5 partial logits, parked in tensor memory
             float v[8], w[8], part[8];
             ld_acc_raw<8>(lane_addr + kR1, 32, 8 * sub, v, w);
@@ -808,20 +838,24 @@ __global__ void tc_prepare_kernel(const float *__restrict__ w, __half *__restric
 
 static size_t tc_smem_bytes() { return (size_t)kActBytes + kWBytes + (64 + 8) * kTPitch * 4 + kBiasFloats * 4 + 64; }
 
-int launch_policy_tc(const cm_policy_desc *desc, const cm_policy_io *io, cudaStream_t stream)
+static int launch_tc_mode(const cm_policy_desc *desc, const cm_policy_io *io, int mode, int in_dim, float *scr_e, float *scr_q,
+                          float *scr_hw, cudaStream_t stream)
 {
     if (!io->tc_weights) return CM_EINVAL;
-    const bool dec = desc->kind == CM_POLICY_DEC;
-    if ((!dec && desc->n_agents > 64) || desc->obs_dim > 128) return CM_EUNSUPPORTED;
+    const bool rows_mode = mode != kTcModeComm;
+    if ((!rows_mode && desc->n_agents > 64) || desc->obs_dim > 128) return CM_EUNSUPPORTED;
     if (io->n_envs * desc->n_agents > (int64_t)1 << 23) return CM_EUNSUPPORTED;      // 32-bit element indices inside the kernel
     TcArgs A;
     A.d = *desc;
     A.io = *io;
-    A.plan = make_tc_plan(desc->obs_dim, desc->n_layers, desc->kind);
-    A.envs_per_tile = dec ? 0 : kTcRows / desc->n_agents;
-    A.n_tiles = dec ? (io->n_envs * desc->n_agents + kTcRows - 1) / kTcRows : (io->n_envs + A.envs_per_tile - 1) / A.envs_per_tile;
+    A.mode = mode;
+    A.in_dim = in_dim;
+    A.scr_e = scr_e; A.scr_q = scr_q; A.scr_hw = scr_hw;
+    A.plan = make_tc_plan(desc->obs_dim, desc->n_layers, mode);
+    A.envs_per_tile = rows_mode ? 0 : kTcRows / desc->n_agents;
+    A.n_tiles = rows_mode ? (io->n_envs * desc->n_agents + kTcRows - 1) / kTcRows : (io->n_envs + A.envs_per_tile - 1) / A.envs_per_tile;
     const size_t smem = tc_smem_bytes();
-    const int vec = dec ? 1 : ((desc->n_agents & 3) == 0 ? 4 : ((desc->n_agents & 1) == 0 ? 2 : 1));
+    const int vec = rows_mode ? 1 : ((desc->n_agents & 3) == 0 ? 4 : ((desc->n_agents & 1) == 0 ? 2 : 1));
     void (*kernel)(const TcArgs) = vec == 4 ? policy_tc_kernel<4> : (vec == 2 ? policy_tc_kernel<2> : policy_tc_kernel<1>);
     static thread_local struct { int dev; int sms; } cache[3] = {{-1, 0}, {-1, 0}, {-1, 0}};
     auto &cc = cache[vec >> 1];
@@ -847,6 +881,27 @@ int launch_policy_tc(const cm_policy_desc *desc, const cm_policy_io *io, cudaStr
     return CM_OK;
 }
 
+int launch_policy_tc_large(const cm_policy_desc *desc, const cm_policy_io *io, cudaStream_t stream);   // policy_attn_kernel.cu
+
+int launch_policy_tc(const cm_policy_desc *desc, const cm_policy_io *io, cudaStream_t stream)
+{
+    if (desc->kind == CM_POLICY_COMM && desc->n_agents > 64) return launch_policy_tc_large(desc, io, stream);
+    const int mode = desc->kind == CM_POLICY_DEC ? kTcModeDec : kTcModeComm;
+    return launch_tc_mode(desc, io, mode, desc->obs_dim, nullptr, nullptr, nullptr, stream);
+}
+
+// large-team pipeline halves (policy_attn_kernel.cu drives them): rows -> E, Q, H_0 Wg_0 ; X rows -> logits / actions
+int launch_policy_tc_encode(const cm_policy_desc *desc, const cm_policy_io *io, float *scr_e, float *scr_q, float *scr_hw, cudaStream_t stream)
+{
+    return launch_tc_mode(desc, io, kTcModeEnc, desc->obs_dim, scr_e, scr_q, scr_hw, stream);
+}
+int launch_policy_tc_head(const cm_policy_desc *desc, const cm_policy_io *io, const float *x_rows, cudaStream_t stream)
+{
+    cm_policy_io io2 = *io;
+    io2.obs = x_rows;
+    return launch_tc_mode(desc, &io2, kTcModeHead, kE, nullptr, nullptr, nullptr, stream);
+}
+
 }  // namespace cm
 
 extern "C" size_t cm_policy_tc_blob_floats(int32_t obs_dim, int32_t n_layers)
@@ -859,7 +914,7 @@ extern "C" int cm_policy_tc_prepare(const cm_policy_desc *desc, const float *wei
     if (!desc || !weights || !tc_weights) return CM_EINVAL;
     if (desc->n_layers < 1 || desc->n_layers > CM_MAX_LAYERS || desc->obs_dim < 1 || desc->obs_dim > 128) return CM_EUNSUPPORTED;
     if (cm_device_count() < 1) return CM_ENODEVICE;
-    const cm::TcPlan P = cm::make_tc_plan(desc->obs_dim, desc->n_layers, desc->kind);
+    const cm::TcPlan P = cm::make_tc_plan(desc->obs_dim, desc->n_layers, cm::kTcModeComm);   // every mode reads this blob
     cm::tc_prepare_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(weights, reinterpret_cast<__half *>(tc_weights), P);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? CM_OK : cm::set_cuda_error(e, CM_ECUDA);

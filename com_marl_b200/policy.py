@@ -106,7 +106,8 @@ class CommCategoricalMLPPolicy(nn.Module):
         self.n_gcn_layers = int(n_gcn_layers)
         self.seed = int(seed)
         # kernel variant: 'fp32' = exact FFMA kernels; 'tc' = tcgen05 tensor cores, error-compensated fp16 products with
-        # fp32 accumulation (fp32-level accuracy, teams of n <= 64); 'auto' picks 'tc' whenever the team fits one tile
+        # fp32 accumulation (fp32-level accuracy; teams of n > 64 run encoder / head on the tensor cores and the n x n
+        # attention in exact fp32 between them); 'auto' = 'tc'
         if math not in ("auto", "fp32", "tc"):
             raise ValueError("math must be 'auto', 'fp32' or 'tc'")
         self.math = math
@@ -149,7 +150,7 @@ class CommCategoricalMLPPolicy(nn.Module):
         return self._blob
 
     def uses_tensor_cores(self):
-        return self.math == "tc" or (self.math == "auto" and self._n_agents <= 64)
+        return self.math in ("tc", "auto")
 
     def tc_weight_blob(self):
         """pre-split (hi | lo), pre-laid-out B operands of the tcgen05 variant; rebuilt when a parameter changed"""
@@ -179,8 +180,6 @@ class CommCategoricalMLPPolicy(nn.Module):
         n, D, L = self._n_agents, self._dec_obs_dim, self.n_gcn_layers
         B = obs.shape[0]
         tc = self.uses_tensor_cores()
-        if tc and n > 64 and self._kind == N.POLICY_COMM:
-            raise ValueError("math='tc' supports teams of at most 64 agents; use math='fp32'")
         desc = N.PolicyDesc(n, D, L, int(self.residual), int(greedy), int(tc), self.seed, env_id0, self._kind)
         io = N.PolicyIO()
         io.n_envs = B

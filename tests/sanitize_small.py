@@ -20,7 +20,7 @@ def main():
              ("pp", 30, 2, 0.08, 4, 0.0, 3, "auto", {"max_env_steps": 4})]         # n = 72: large-team FFMA kernel
     for scen, m, sen, den, cap, loss, B, math, over in cases:
         spec = ScenarioSpec.from_cli(scen, m, sen, den, cap=cap, loss=loss, seed=3, **over)
-        pol = make_policy(spec, math=math if spec.n_agents <= 64 else "fp32")
+        pol = make_policy(spec, math=math)
         eng = RolloutEngine(spec, pol, B, ring=4, use_graph=False, record_attention=True)
         eng.reset()
         eng.run(12)
