@@ -352,26 +352,61 @@ def run_b200_arm(args):
     eng.steps_done += 16 * reps
     clock_info = clocks.stop(t_lo, t_hi) if rank == 0 else None
     # ---------------- e2e: host buffers through the public step / get_actions API ----------------
+    # The env batch is cut into `e2e_batches` independent halves that ping-pong through the split-phase host API on their own
+    # streams: while one half's step results travel device -> host, the other half's observations travel host -> device
+    # (PCIe is full duplex).  Every iteration still moves EVERY env's inputs H2D and results D2H and advances all of them.
     from com_marl_b200.envs import BatchedEnv
-    henv = BatchedEnv(spec, B, device=dev, env_id0=rank * B)
-    out = henv.reset_host()
+    NB = args.e2e_batches if (args.e2e_batches > 0 and B % max(1, args.e2e_batches) == 0) else 1
+    Bh = B // NB
+    henvs = [BatchedEnv(spec, Bh, device=dev, env_id0=rank * B + h * Bh) for h in range(NB)]
+    hstreams = [torch.cuda.Stream(dev) for _ in range(NB)]
+    outs = [e.reset_host() for e in henvs]
+    torch.cuda.synchronize(dev)
     e2e_steps = max(5, min(steps, args.e2e_steps))
-    def e2e_iteration(out):
-        pin = out["pinned"]            # host (pinned) buffers filled by the previous step
-        acts, probs = pol.get_actions_host(pin["obs"], pin["adj_bits"], pin["chan_bits"], return_pinned=True)
-        return henv.step_host(acts)
+
+    def pol_phase(h):
+        pin = outs[h]["pinned"]            # host (pinned) buffers filled by the previous step of this half
+        a, _, ev = pol.get_actions_host(pin["obs"], pin["adj_bits"], pin["chan_bits"], slot=h, sync=False, stream=hstreams[h])
+        return a, ev
+
+    def env_phase(h, acts):
+        return henvs[h].step_host(acts, sync=False, stream=hstreams[h])
+
+    # event-driven ping-pong: a half's next call is enqueued as soon as ITS previous call has finished, while the other
+    # halves' copies / kernels keep the bus and the SMs busy.  Odd halves start one policy phase ahead (antiphase).
+    phase, pend, evs = {}, {}, {}
+    for h in range(NB):
+        pend[h], evs[h] = pol_phase(h)
+        phase[h] = "pol"
+        if h % 2 == 1:
+            evs[h].synchronize()
+            outs[h], evs[h] = env_phase(h, pend[h])
+            phase[h] = "env"
+
+    def e2e_iteration():                   # every half advances by one full step (one policy call + one env step)
+        for _ in range(2):
+            for h in range(NB):
+                evs[h].synchronize()
+                if phase[h] == "pol":
+                    outs[h], evs[h] = env_phase(h, pend[h])
+                    phase[h] = "env"
+                else:
+                    pend[h], evs[h] = pol_phase(h)
+                    phase[h] = "pol"
 
     for _ in range(3):
-        out = e2e_iteration(out)
+        e2e_iteration()
     barrier(); torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        out = e2e_iteration(out)
+        e2e_iteration()
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     barrier()
+    for e in henvs:
+        e.check_errors()
     ph2d, pd2h = pol.host_call_bytes(B)
-    eh2d, ed2h = henv.host_step_bytes()
+    eh2d, ed2h = [sum(x) for x in zip(*[e.host_step_bytes() for e in henvs])]
     # ---------------- reduce over ranks ----------------
     vec = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -426,7 +461,11 @@ def run_b200_arm(args):
                          "so no slot survives a ring cycle in cache",
                    "streams": "on-device Philox4x32-10 (spawn, prey walk, channel draws, action sampling)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ph2d + eh2d, "d2h_bytes_per_step": pd2h + ed2h,
-                "steps": e2e_steps, "api": "policy.get_actions_host + BatchedEnv.step_host (pinned host buffers, per-step sync)"},
+                "steps": e2e_steps, "batches": NB,
+                "api": "policy.get_actions_host + BatchedEnv.step_host = cm_policy_forward_host + cm_env_step_host (one C call each: H2D, kernel, "
+                       f"D2H on pinned host buffers); split-phase calls, the env batch cut into {NB} independent halves on their own "
+                       "streams in antiphase, so one half's kernels and host work hide behind the other's copies; every env's "
+                       "observations + masks + actions go H2D and its results D2H every step, one host wait per call"},
         "gpu_launches": launches * world,
         "roofline": {"bound": "tensor", "kernel": kname,
                      "achieved": pol_tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": pol_tflops / tc_peak, "traffic": traffic.get(kname),
@@ -477,6 +516,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the config's)")
     ap.add_argument("--ring", type=int, default=64, help="trajectory ring slots = steps per CUDA graph")
     ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--e2e-batches", type=int, default=4, help="independent env halves of the e2e (host-buffer) loop")
     ap.add_argument("--groups", type=int, default=0, help="independent env groups, each a policy->step chain on its own stream (0: 4 for teams <= 64, else 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -18,7 +18,7 @@ MAX_AGENTS, MAX_GRID, MAX_LAYERS = 256, 64, 4
 
 EXPORTS = ("cm_abi_version", "cm_strerror", "cm_last_cuda_error", "cm_device_count", "cm_env_reset", "cm_env_step",
            "cm_comm_update", "cm_policy_forward", "cm_policy_blob_floats", "cm_policy_workspace_bytes", "cm_policy_tc_blob_floats", "cm_policy_tc_prepare", "cm_mask_pack",
-           "cm_mask_unpack")
+           "cm_mask_unpack", "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host")
 
 
 class EnvDesc(C.Structure):
@@ -97,7 +97,11 @@ def lib():
     L.cm_policy_workspace_bytes.argtypes = [C.c_int32, C.c_int64]
     L.cm_mask_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     L.cm_mask_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
-    for fn in ("cm_env_reset", "cm_env_step", "cm_comm_update", "cm_policy_forward", "cm_mask_pack", "cm_mask_unpack"):
+    L.cm_policy_forward_host.argtypes = [C.POINTER(PolicyDesc), C.POINTER(PolicyIO), C.POINTER(PolicyIO), C.c_int64, C.c_void_p]
+    L.cm_env_step_host.argtypes = [C.POINTER(EnvDesc), C.POINTER(EnvState), C.POINTER(StepIO), C.POINTER(StepIO), C.c_void_p]
+    L.cm_env_reset_host.argtypes = [C.POINTER(EnvDesc), C.POINTER(EnvState), C.POINTER(StepIO), C.POINTER(StepIO), C.c_void_p]
+    for fn in ("cm_env_reset", "cm_env_step", "cm_comm_update", "cm_policy_forward", "cm_mask_pack", "cm_mask_unpack",
+               "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host"):
         getattr(L, fn).restype = C.c_int
     if L.cm_abi_version() != 1:
         raise ImportError("libcommarl_b200.so ABI version mismatch")
@@ -112,6 +116,27 @@ def check(fn, rc):
         if rc == CM_ECUDA:
             msg += f", cudaError={L.cm_last_cuda_error()}"
         raise NativeError(fn, rc, msg)
+
+
+def arena(specs, device=None, pinned=False, align=256):
+    """Tensors carved from ONE allocation: specs = [(name, shape, dtype)] -> {name: tensor}.  Arrays that travel together
+    between host and device live in arenas with the same order and padding on both sides, so the host-buffer calls of the
+    library move them with a single DMA transfer (csrc/host_abi.cu merges adjacent copies)."""
+    import torch
+    offs, total = [], 0
+    for _, shape, dt in specs:
+        nbytes = int(torch.empty((), dtype=dt).element_size())
+        for d in shape:
+            nbytes *= int(d)
+        offs.append((total, nbytes))
+        total += (nbytes + align - 1) // align * align
+    buf = torch.zeros(max(total, align), dtype=torch.uint8, pin_memory=True) if pinned else \
+        torch.zeros(max(total, align), dtype=torch.uint8, device=device)
+    out = {}
+    for (name, shape, dt), (o, nbytes) in zip(specs, offs):
+        out[name] = buf[o:o + nbytes].view(dt).view(tuple(int(d) for d in shape))
+    out["_arena"] = buf
+    return out
 
 
 def ptr(t):

@@ -1,0 +1,138 @@
+// host_abi.cu — host-buffer entry points of the C ABI: the reference-facing calls (numpy arrays in, numpy arrays out,
+// like VecEnvExecutor.step and policy.get_actions) as ONE C call each: asynchronous H2D copies of the inputs, the kernel,
+// asynchronous D2H copies of the outputs, all on the caller's stream.  Nothing here synchronises or allocates: the caller
+// owns pinned host buffers and device staging buffers of the same shapes and waits on the stream (or an event) before it
+// reads the host outputs.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "commarl_b200.h"
+#include "common.cuh"
+
+namespace cm {
+
+__global__ void fill_u32_kernel(uint32_t *__restrict__ p, int64_t n, uint32_t v)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// A run of copies in one direction.  Consecutive entries whose source AND destination continue the previous entry with
+// the same small gap (arrays carved from one arena on both sides, same alignment padding) are merged into ONE
+// cudaMemcpyAsync: a DMA transfer has a fixed cost of several microseconds on the device timeline, which dominates the
+// small arrays (reward, done, counts, masks of small teams ...).  The padding bytes between merged arrays are copied too.
+struct CopyRun {
+    cudaStream_t s;
+    cudaMemcpyKind kind;
+    char *dst = nullptr;
+    const char *src = nullptr;
+    size_t bytes = 0;
+    int rc = CM_OK;
+    CopyRun(cudaStream_t s_, cudaMemcpyKind k_) : s(s_), kind(k_) {}
+    void flush()
+    {
+        if (bytes && rc == CM_OK) {
+            const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, s);
+            if (e != cudaSuccess) rc = set_cuda_error(e, CM_ECUDA);
+        }
+        bytes = 0;
+    }
+    void add(void *d, const void *sr, size_t n)
+    {
+        if (!d || !sr || n == 0) return;
+        char *dc = static_cast<char *>(d);
+        const char *sc = static_cast<const char *>(sr);
+        if (bytes) {
+            const ptrdiff_t gd = dc - (dst + bytes), gs = sc - (src + bytes);
+            if (gd == gs && gd >= 0 && gd <= 1024) { bytes += (size_t)gd + n; return; }
+            flush();
+        }
+        dst = dc; src = sc; bytes = n;
+    }
+    int done() { flush(); return rc; }
+};
+
+}  // namespace cm
+
+#define CM_TRY(x) do { const int rc_ = (x); if (rc_ != CM_OK) return rc_; } while (0)
+
+extern "C" int cm_policy_forward_host(const cm_policy_desc *desc, const cm_policy_io *dev, const cm_policy_io *host, int64_t tick_all,
+                                      cm_stream_t stream)
+{
+    using namespace cm;
+    if (!desc || !dev || !host) return CM_EINVAL;
+    if (desc->n_agents < 1 || desc->n_agents > CM_MAX_AGENTS || desc->obs_dim < 1 || dev->n_envs < 0) return CM_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t B = (size_t)dev->n_envs, n = (size_t)desc->n_agents, D = (size_t)desc->obs_dim, L = (size_t)desc->n_layers;
+    const size_t W = (n + 31) / 32, rows = B * n;
+    if (B == 0) return CM_OK;
+    CopyRun up(s, cudaMemcpyHostToDevice);
+    up.add(const_cast<float *>(dev->obs), host->obs, rows * D * 4);
+    up.add(const_cast<uint32_t *>(dev->adj_bits), host->adj_bits, rows * W * 4);
+    up.add(const_cast<uint32_t *>(dev->chan_bits), host->chan_bits, rows * L * W * 4);
+    up.add(const_cast<uint8_t *>(dev->avail_bits), host->avail_bits, rows);
+    up.add(const_cast<float *>(dev->sample_u), host->sample_u, rows * 4);
+    up.add(const_cast<uint32_t *>(dev->episode), host->episode, B * 4);
+    if (tick_all < 0) up.add(const_cast<uint32_t *>(dev->tick), host->tick, B * 4);
+    CM_TRY(up.done());
+    if (tick_all >= 0 && dev->tick) {
+        const int grid = (int)((B + 255) / 256 < 148 ? (B + 255) / 256 : 148);
+        fill_u32_kernel<<<grid, 256, 0, s>>>(const_cast<uint32_t *>(dev->tick), (int64_t)B, (uint32_t)tick_all);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
+    }
+    CM_TRY(cm_policy_forward(desc, dev, stream));
+    CopyRun down(s, cudaMemcpyDeviceToHost);
+    down.add(host->actions, dev->actions, rows);
+    down.add(host->probs, dev->probs, rows * CM_ACTIONS * 4);
+    down.add(host->logits, dev->logits, rows * CM_ACTIONS * 4);
+    down.add(host->attention, dev->attention, rows * n * 4);
+    return down.done();
+}
+
+static size_t env_obs_dim(const cm_env_desc *d)
+{
+    const size_t ww = (size_t)(2 * d->sensing + 1) * (size_t)(2 * d->sensing + 1);
+    return d->scenario == CM_COVERAGE ? 3 * ww + 2 : 2 * ww + 3;      /* coverage.py:111-117, predator_prey.py:95-98 */
+}
+
+static int env_outputs_to_host(const cm_env_desc *desc, size_t B, const cm_step_io *dev, const cm_step_io *host, cudaStream_t s)
+{
+    using namespace cm;
+    const size_t n = (size_t)desc->n_agents, p = (size_t)(desc->n_preys > 0 ? desc->n_preys : 1), L = (size_t)desc->n_layers;
+    const size_t W = (n + 31) / 32, D = env_obs_dim(desc);
+    CopyRun down(s, cudaMemcpyDeviceToHost);
+    down.add(host->obs, dev->obs, B * n * D * 4);
+    down.add(host->adj_bits, dev->adj_bits, B * n * W * 4);
+    down.add(host->chan_bits, dev->chan_bits, B * L * n * W * 4);
+    down.add(host->reward, dev->reward, B * 8);
+    down.add(host->done, dev->done, B);
+    down.add(host->counts, dev->counts, B * 6 * 4);
+    down.add(host->prey_alive_out, dev->prey_alive_out, B * p);
+    down.add(host->success_out, dev->success_out, B);
+    down.add(host->ave_deg, dev->ave_deg, B * 4);
+    return down.done();
+}
+
+extern "C" int cm_env_step_host(const cm_env_desc *desc, const cm_env_state *state, const cm_step_io *dev, const cm_step_io *host,
+                                cm_stream_t stream)
+{
+    using namespace cm;
+    if (!desc || !state || !dev || !host || !dev->actions || !host->actions) return CM_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t B = (size_t)state->n_envs, n = (size_t)desc->n_agents;
+    if (B == 0) return CM_OK;
+    CopyRun up(s, cudaMemcpyHostToDevice);
+    up.add(const_cast<int8_t *>(dev->actions), host->actions, B * n);
+    CM_TRY(up.done());
+    CM_TRY(cm_env_step(desc, state, dev, stream));
+    return env_outputs_to_host(desc, B, dev, host, s);
+}
+
+extern "C" int cm_env_reset_host(const cm_env_desc *desc, const cm_env_state *state, const cm_step_io *dev, const cm_step_io *host,
+                                 cm_stream_t stream)
+{
+    if (!desc || !state || !dev || !host) return CM_EINVAL;
+    if (state->n_envs == 0) return CM_OK;
+    CM_TRY(cm_env_reset(desc, state, dev, nullptr, stream));
+    return env_outputs_to_host(desc, (size_t)state->n_envs, dev, host, (cudaStream_t)stream);
+}

@@ -61,16 +61,9 @@ class BatchedEnv:
         self.episode = z((B,), torch.int32)
         self.tick = z((B,), torch.int32)
         self.ge_state = z((B, n, self.W), torch.int32) if spec.channel == N.CH_GE else None
-        # ---- outputs ----
-        self.obs = z((B, n, self.D), torch.float32)
-        self.reward = z((B,), torch.float64)
-        self.done = z((B,), torch.uint8)
-        self.counts = z((B, 6), torch.int32)
-        self.prey_alive_out = z((B, max(p, 1)), torch.uint8)
-        self.success_out = z((B,), torch.uint8)
-        self.adj_bits = z((B, n, self.W), torch.int32)
-        self.chan_bits = z((B, L, n, self.W), torch.int32)
-        self.ave_deg = z((B,), torch.float32)
+        # ---- outputs: one arena, in the order the host-buffer call copies them (one DMA transfer, csrc/host_abi.cu) ----
+        for k, v in N.arena(self._out_specs(), device=dev).items():
+            setattr(self, "_out_arena" if k == "_arena" else k, v)
         self.error_flag = z((1,), torch.int32)
         self.stats = z((B, 16), torch.float64)      # episode accounting, layout in include/commarl_b200.h
         # ---- constants ----
@@ -85,6 +78,13 @@ class BatchedEnv:
         self._spawn_agent = self._spawn_prey = None
         self._spawn_episodes = 0
         self._io_cache = {}
+
+    def _out_specs(self):
+        B, n, p, L = self.B, self.n, self.p, self.L
+        return [("obs", (B, n, self.D), torch.float32), ("adj_bits", (B, n, self.W), torch.int32),
+                ("chan_bits", (B, L, n, self.W), torch.int32), ("reward", (B,), torch.float64), ("done", (B,), torch.uint8),
+                ("counts", (B, 6), torch.int32), ("prey_alive_out", (B, max(p, 1)), torch.uint8),
+                ("success_out", (B,), torch.uint8), ("ave_deg", (B,), torch.float32)]
 
     _SLICED = ("agent_pos", "prey_pos", "prey_alive", "visited", "step_count", "total_capture", "success", "episode", "tick",
                "ge_state", "obs", "reward", "done", "counts", "prey_alive_out", "success_out", "adj_bits", "chan_bits", "ave_deg",
@@ -108,7 +108,7 @@ class BatchedEnv:
                   "episode", "tick", "ge_state"):
             setattr(v.state, k, N.ptr(getattr(v, k)))
         v._io_cache = {}
-        v._pin = None
+        v._pin = v._hio = None
         return v
 
     # ---- injected streams (parity mode) ---------------------------------------------------------
@@ -118,6 +118,7 @@ class BatchedEnv:
         reset() and inject into the engine')."""
         sa = pack_positions(spawn_agent)
         assert sa.shape[0] == self.B and sa.shape[2] == self.n
+        self._hio = None                         # the cached host-call structs carry the spawn queue pointers
         self._spawn_agent = torch.from_numpy(sa.view(np.int16)).to(self.device).contiguous()
         self._spawn_episodes = sa.shape[1]
         if self.p:
@@ -173,36 +174,68 @@ class BatchedEnv:
     # ---- host-buffer surface: the drop-in call with numpy in / numpy out ------------------------------
     def _pinned(self):
         if getattr(self, "_pin", None) is None:
-            pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
+            pa = N.arena(self._out_specs(), pinned=True)          # mirrors the device arena: one D2H transfer per step
             self._pin = dict(actions=torch.empty((self.B, self.n), dtype=torch.int8, pin_memory=True),
-                             obs=pin(self.obs), reward=pin(self.reward), done=pin(self.done), counts=pin(self.counts),
-                             adj_bits=pin(self.adj_bits), chan_bits=pin(self.chan_bits), ave_deg=pin(self.ave_deg),
-                             prey_alive_out=pin(self.prey_alive_out), success=pin(self.success))
+                             obs=pa["obs"], reward=pa["reward"], done=pa["done"], counts=pa["counts"], adj_bits=pa["adj_bits"],
+                             chan_bits=pa["chan_bits"], ave_deg=pa["ave_deg"], prey_alive_out=pa["prey_alive_out"],
+                             success=pa["success_out"])
+            self._pin_arena = pa["_arena"]
             self._act_dev = torch.empty((self.B, self.n), dtype=torch.int8, device=self.device)
+            self._host_out = {k: v.numpy() for k, v in self._pin.items() if k != "actions"}
+            self._host_out["pinned"] = self._pin   # the same buffers as torch pinned tensors (zero-copy hand-over to the policy)
         return self._pin
 
-    def step_host(self, actions):
-        """VecEnvExecutor.step with HOST buffers: numpy actions in, numpy (views of pinned buffers) out.
-        Copies: H2D actions; D2H obs, reward, done, counts, adj/chan bit rows, ave_deg, prey_alive, success."""
-        pin = self._pinned()
-        if isinstance(actions, torch.Tensor) and actions.is_pinned() and actions.dtype == torch.int8:
-            self._act_dev.copy_(actions.view(self.B, self.n), non_blocking=True)     # already pinned: no staging copy
+    _HOST_OUT = ("obs", "reward", "done", "counts", "adj_bits", "chan_bits", "ave_deg", "prey_alive_out", "success")
+
+    def _host_io(self):
+        """host-side cm_step_io (pinned buffers) + device-side cm_step_io of the host-buffer calls, built once"""
+        if getattr(self, "_hio", None) is None:
+            pin = self._pinned()
+            hio = N.StepIO()
+            hio.actions = pin["actions"].data_ptr()
+            for k in self._HOST_OUT:
+                setattr(hio, "success_out" if k == "success" else k, pin[k].data_ptr())
+            self._hio = hio
+            self._dio = self._io(self._act_dev)
+            self._host_event = torch.cuda.Event()
+        return self._hio, self._dio
+
+    def step_host(self, actions, sync=True, stream=None):
+        """VecEnvExecutor.step with HOST buffers: numpy actions in, numpy (views of pinned buffers) out, as ONE C call
+        (cm_env_step_host): H2D actions, the step kernel, D2H obs, reward, done, counts, adj/chan bit rows, ave_deg,
+        prey_alive, success (env.success as the sampler reads it at this step).
+        ``sync=False`` (split phase): enqueue on the current stream and return ``(out, event)`` at once; the buffers are
+        valid after ``event.synchronize()`` — lets several env batches overlap their copies on different streams."""
+        hio, dio = self._host_io()
+        pin = self._pin
+        if actions is getattr(self, "_last_actions", None):
+            pass                                                                     # the same pinned tensor as last time
+        elif isinstance(actions, torch.Tensor) and actions.is_pinned() and actions.dtype == torch.int8 and actions.numel() == self.B * self.n:
+            hio.actions = actions.data_ptr()                                         # already pinned: no staging copy
+            self._last_actions = actions
         else:
             pin["actions"].numpy()[...] = np.asarray(actions, dtype=np.int8).reshape(self.B, self.n)
-            self._act_dev.copy_(pin["actions"], non_blocking=True)
-        self.step(self._act_dev)
-        for k in ("obs", "reward", "done", "counts", "adj_bits", "chan_bits", "ave_deg", "prey_alive_out", "success"):
-            pin[k].copy_(getattr(self, k), non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        out = {k: v.numpy() for k, v in pin.items() if k != "actions"}
-        out["pinned"] = pin            # the same buffers as torch pinned tensors (zero-copy hand-over to the policy)
+            hio.actions = pin["actions"].data_ptr()
+            self._last_actions = None
+        if self.device.index is not None and torch.cuda.current_device() != self.device.index:
+            torch.cuda.set_device(self.device)   # the library launches on the current device
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        N.check("cm_env_step_host", N.lib().cm_env_step_host(C.byref(self.desc), C.byref(self.state), C.byref(dio), C.byref(hio),
+                                                             stream.cuda_stream))
+        out = self._host_out
+        if not sync:
+            self._host_event.record(stream)
+            return out, self._host_event
+        stream.synchronize()
         return out
 
     def reset_host(self):
         pin = self._pinned()
-        self.reset()
-        for k in ("obs", "adj_bits", "chan_bits", "ave_deg"):
-            pin[k].copy_(getattr(self, k), non_blocking=True)
+        hio, dio = self._host_io()
+        with torch.cuda.device(self.device):
+            N.check("cm_env_reset_host", N.lib().cm_env_reset_host(C.byref(self.desc), C.byref(self.state), C.byref(dio), C.byref(hio),
+                                                                   N.stream_ptr()))
         torch.cuda.current_stream(self.device).synchronize()
         out = {k: pin[k].numpy() for k in ("obs", "adj_bits", "chan_bits", "ave_deg")}
         out["pinned"] = pin

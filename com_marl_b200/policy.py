@@ -125,7 +125,10 @@ class CommCategoricalMLPPolicy(nn.Module):
 
     # ---- weight blob (layout in include/commarl_b200.h) ----------------------------------------------
     def _signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        plist = self.__dict__.get("_plist")
+        if plist is None:                        # (walking the module tree costs more than the whole check)
+            plist = self.__dict__["_plist"] = list(self.parameters())
+        return tuple([(p.data_ptr(), p._version) for p in plist])
 
     def weight_blob(self):
         """float32 device blob, every dense weight k-major; rebuilt when a parameter changed."""
@@ -174,30 +177,42 @@ class CommCategoricalMLPPolicy(nn.Module):
 
     # ---- device fast path (no host copies) --------------------------------------------------------------
     def act_device(self, obs, adj_bits=None, chan_bits=None, avail_bits=None, sample_u=None, tick=None, episode=None,
-                   greedy=False, probs=None, logits=None, attention=None, actions=None, env_id0=0):
+                   greedy=False, probs=None, logits=None, attention=None, actions=None, env_id0=0, ws_slot=0):
         """Fused forward on device tensors.  obs: float32 (B, n, D) / (B, n*D).  Outputs are written into the
         given tensors (allocate once, reuse: the call is CUDA-graph capturable)."""
+        desc, io = self._call_structs(obs, adj_bits, chan_bits, avail_bits, sample_u, tick, episode, greedy, probs, logits,
+                                      attention, actions, env_id0, ws_slot)
+        with torch.cuda.device(self.device):
+            N.check("cm_policy_forward", N.lib().cm_policy_forward(C.byref(desc), C.byref(io), N.stream_ptr()))
+
+    def _call_structs(self, obs, adj_bits, chan_bits, avail_bits, sample_u, tick, episode, greedy, probs, logits, attention,
+                      actions, env_id0, ws_slot):
+        """descriptor + io struct of one cm_policy_forward call on device tensors"""
         n, D, L = self._n_agents, self._dec_obs_dim, self.n_gcn_layers
         B = obs.shape[0]
         tc = self.uses_tensor_cores()
         desc = N.PolicyDesc(n, D, L, int(self.residual), int(greedy), int(tc), self.seed, env_id0, self._kind)
         io = N.PolicyIO()
         io.n_envs = B
-        io.weights = N.ptr(self.weight_blob())
         if tc:
-            io.tc_weights = N.ptr(self.tc_weight_blob())
+            io.tc_weights = N.ptr(self.tc_weight_blob())      # (refreshes the fp32 blob as well)
             io.error_flag = N.ptr(self._tc_error)
+            io.weights = N.ptr(self._blob)
+        else:
+            io.weights = N.ptr(self.weight_blob())
         for k, v in (("obs", obs), ("adj_bits", adj_bits), ("chan_bits", chan_bits), ("avail_bits", avail_bits),
                      ("sample_u", sample_u), ("tick", tick), ("episode", episode), ("probs", probs), ("logits", logits),
                      ("attention", attention), ("actions", actions)):
             setattr(io, k, N.ptr(v))
-        if n > 64 and self._kind == N.POLICY_COMM:      # large teams: per-CTA scratch, allocated once and reused
+        if n > 64 and self._kind == N.POLICY_COMM:      # large teams: scratch, allocated once per concurrent caller and reused
             need = N.lib().cm_policy_workspace_bytes(n, B)
-            if self._workspace is None or self._workspace.numel() * 4 < need:
-                self._workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
-            io.workspace, io.workspace_bytes = N.ptr(self._workspace), self._workspace.numel() * 4
-        with torch.cuda.device(self.device):
-            N.check("cm_policy_forward", N.lib().cm_policy_forward(C.byref(desc), C.byref(io), N.stream_ptr()))
+            if self._workspace is None:
+                self._workspace = {}
+            ws = self._workspace.get(ws_slot)
+            if ws is None or ws.numel() * 4 < need:
+                ws = self._workspace[ws_slot] = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
+            io.workspace, io.workspace_bytes = N.ptr(ws), ws.numel() * 4
+        return desc, io
 
     @staticmethod
     def pack_mask(dense, n):
@@ -235,35 +250,72 @@ class CommCategoricalMLPPolicy(nn.Module):
 
     _host_calls = 0
 
-    def get_actions_host(self, obs, adj_bits, chan_bits, greedy=False, return_pinned=False):
+    def get_actions_host(self, obs, adj_bits, chan_bits, greedy=False, return_pinned=False, slot=0, sync=True, stream=None):
         """Batched rollout call with HOST buffers and bit-row masks (what BatchedEnv.step_host returns): numpy obs
         (B, n, D) / (B, n*D), int32 bit rows in; numpy actions (B, n) int8 and probs (B, n, 5) out.  Pinned staging
         buffers are allocated once; inputs that already are pinned torch tensors (e.g. ``step_host(...)["pinned"]``) are
-        copied to the device directly.  Copies: H2D obs + masks; D2H actions + probs."""
+        copied to the device directly.  Copies: H2D obs + masks; D2H actions + probs.
+
+        Split-phase use (``sync=False``): everything is enqueued on the CURRENT stream and the call returns
+        ``(actions, probs, event)`` at once; the outputs are valid after ``event.synchronize()``.  ``slot`` selects an
+        independent set of staging buffers, so that several env batches can be in flight on different streams (the
+        H2D copies of one batch then overlap the D2H copies of another: PCIe is full duplex)."""
         n, D, L, dev = self._n_agents, self._dec_obs_dim, self.n_gcn_layers, self.device
         B = obs.shape[0]
-        st = getattr(self, "_stage", None)
+        stages = self.__dict__.setdefault("_stages", {})
+        st = stages.get(slot)
         if st is None or st["B"] != B:
             W = (n + 31) // 32
-            mk = lambda shape, dt: (torch.empty(shape, dtype=dt, pin_memory=True), torch.empty(shape, dtype=dt, device=dev))  # noqa: E731
-            st = dict(B=B, obs=mk((B, n, D), torch.float32), adj=mk((B, n, W), torch.int32), chan=mk((B, L, n, W), torch.int32),
-                      probs=mk((B, n, 5), torch.float32), actions=mk((B, n), torch.int8),
-                      tick=torch.zeros((B,), dtype=torch.int32, device=dev), episode=torch.zeros((B,), dtype=torch.int32, device=dev))
-            self._stage = st
-        for k, src in (("obs", obs), ("adj", adj_bits), ("chan", chan_bits)):
-            h, d = st[k]
-            if isinstance(src, torch.Tensor) and src.is_pinned() and src.dtype == h.dtype:
-                d.copy_(src.view(h.shape), non_blocking=True)      # caller's buffer is already pinned: no staging copy
-            else:
-                h.numpy()[...] = np.asarray(src).reshape(h.shape)
-                d.copy_(h, non_blocking=True)
-        st["tick"].fill_(self._host_calls & 0x7FFFFFFF)
+            # inputs and outputs as arenas with the same order / padding on both sides (and as the env's host buffers):
+            # the library moves each group with one DMA transfer
+            ins = [("obs", (B, n, D), torch.float32), ("adj", (B, n, W), torch.int32), ("chan", (B, L, n, W), torch.int32)]
+            outs = [("actions", (B, n), torch.int8), ("probs", (B, n, 5), torch.float32)]
+            hi, di = N.arena(ins, pinned=True), N.arena(ins, device=dev)
+            ho, do = N.arena(outs, pinned=True), N.arena(outs, device=dev)
+            st = dict(B=B, tick=torch.zeros((B,), dtype=torch.int32, device=dev), episode=torch.zeros((B,), dtype=torch.int32, device=dev),
+                      event=torch.cuda.Event(), _keep=(hi, di, ho, do))
+            for k in ("obs", "adj", "chan"):
+                st[k] = (hi[k], di[k])
+            for k in ("actions", "probs"):
+                st[k] = (ho[k], do[k])
+            stages[slot] = st
+        hio = st.get("hio")
+        if hio is None:
+            hio = st["hio"] = N.PolicyIO()
+            hio.actions, hio.probs = st["actions"][0].data_ptr(), st["probs"][0].data_ptr()
+            st["last_in"] = (None, None, None)
+        if not (obs is st["last_in"][0] and adj_bits is st["last_in"][1] and chan_bits is st["last_in"][2]):
+            pinned_in = True
+            for k, f, src in (("obs", "obs", obs), ("adj", "adj_bits", adj_bits), ("chan", "chan_bits", chan_bits)):
+                h, d = st[k]
+                if isinstance(src, torch.Tensor) and src.is_pinned() and src.dtype == h.dtype and src.numel() == h.numel():
+                    setattr(hio, f, src.data_ptr())                 # caller's buffer is already pinned: no staging copy
+                else:
+                    h.numpy()[...] = np.asarray(src).reshape(h.shape)
+                    setattr(hio, f, h.data_ptr())
+                    pinned_in = False
+            # the same pinned tensors again (the env's persistent host buffers): nothing to re-derive next time
+            st["last_in"] = (obs, adj_bits, chan_bits) if pinned_in else (None, None, None)
+        sig = self._signature()
+        cs = st.get("structs")
+        if cs is None or cs[0] != (sig, bool(greedy)):
+            desc, dio = self._call_structs(st["obs"][1], st["adj"][1], st["chan"][1], None, None, st["tick"], st["episode"], greedy,
+                                           st["probs"][1], None, None, st["actions"][1], 0, slot)
+            cs = st["structs"] = ((sig, bool(greedy)), desc, dio)
+        desc, dio = cs[1], cs[2]
+        tick_all = self._host_calls & 0x7FFFFFFF
         self._host_calls += 1
-        self.act_device(st["obs"][1], st["adj"][1], st["chan"][1], tick=st["tick"], episode=st["episode"], greedy=greedy,
-                        probs=st["probs"][1], actions=st["actions"][1])
-        st["probs"][0].copy_(st["probs"][1], non_blocking=True)
-        st["actions"][0].copy_(st["actions"][1], non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        # ONE C call: H2D obs + masks, tick fill, the forward, D2H actions + probs (include/commarl_b200.h)
+        if dev.index is not None and torch.cuda.current_device() != dev.index:
+            torch.cuda.set_device(dev)           # the library launches on the current device
+        if stream is None:
+            stream = torch.cuda.current_stream(dev)
+        N.check("cm_policy_forward_host", N.lib().cm_policy_forward_host(C.byref(desc), C.byref(dio), C.byref(hio), tick_all,
+                                                                         stream.cuda_stream))
+        if not sync:
+            st["event"].record(stream)
+            return st["actions"][0], st["probs"][0], st["event"]
+        stream.synchronize()
         if return_pinned:
             return st["actions"][0], st["probs"][0]
         return st["actions"][0].numpy(), st["probs"][0].numpy()
@@ -371,6 +423,7 @@ class DecCategoricalMLPPolicy(nn.Module):
     tc_weight_blob = CommCategoricalMLPPolicy.tc_weight_blob
     check_errors = CommCategoricalMLPPolicy.check_errors
     _act_device = CommCategoricalMLPPolicy.act_device
+    _call_structs = CommCategoricalMLPPolicy._call_structs
 
     def uses_tensor_cores(self):
         return True

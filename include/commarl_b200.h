@@ -218,6 +218,26 @@ int cm_policy_tc_prepare(const cm_policy_desc *desc, const float *weights, float
 /* scratch the forward needs for teams larger than one 64-row tile (0 for n <= 64) */
 size_t cm_policy_workspace_bytes(int32_t n_agents, int64_t n_envs);
 
+/* ---- host-buffer calls: the reference-facing form of the three entry points above ------------------------------
+ * The reference's callers hand NumPy arrays to env.step / policy.get_actions and get NumPy arrays back
+ * (vec_env_executor.py:19-45, comm_categorical_mlp_policy.py:98-119).  These calls take TWO io structs of the same
+ * type: `dev` exactly as for the device call (device staging buffers the kernel works on; weights / tc_weights /
+ * workspace / error_flag / stats / spawn queues live only there) and `host`, whose non-NULL members are HOST buffers
+ * (pinned, for the copies to be asynchronous) of the same shapes.  One call = H2D copies of the inputs named in `host`
+ * -> the kernel -> D2H copies of the outputs named in `host`, all enqueued on `stream`; it never synchronises: wait
+ * on the stream (or an event recorded after the call) before reading the host outputs.
+ *   cm_policy_forward_host  inputs obs, adj_bits, chan_bits, avail_bits, sample_u, episode, tick; outputs actions, probs,
+ *                           logits, attention.  tick_all >= 0 fills dev->tick with that value instead of copying host->tick
+ *                           (the host loop's call counter as the sampling key).
+ *   cm_env_step_host        input actions; outputs obs, adj_bits, chan_bits, reward, done, counts, prey_alive_out,
+ *                           success_out, ave_deg.   cm_env_reset_host: the same outputs after a reset of all envs. */
+int cm_policy_forward_host(const cm_policy_desc *desc, const cm_policy_io *dev, const cm_policy_io *host, int64_t tick_all,
+                           cm_stream_t stream);
+int cm_env_step_host(const cm_env_desc *desc, const cm_env_state *state, const cm_step_io *dev, const cm_step_io *host,
+                     cm_stream_t stream);
+int cm_env_reset_host(const cm_env_desc *desc, const cm_env_state *state, const cm_step_io *dev, const cm_step_io *host,
+                      cm_stream_t stream);
+
 /* dense float32 masks (the reference's dist_adj (B,n,n) / channels (B,L,n,n)) <-> bit rows */
 int cm_mask_pack(const float *dense, uint32_t *bits, int64_t rows, int32_t n, cm_stream_t stream);
 int cm_mask_unpack(const uint32_t *bits, float *dense, int64_t rows, int32_t n, cm_stream_t stream);

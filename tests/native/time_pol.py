@@ -4,8 +4,9 @@ from com_marl_b200.scenario import ScenarioSpec
 from com_marl_b200.rollout import make_policy
 from com_marl_b200.envs import BatchedEnv
 cfg = sys.argv[1] if len(sys.argv) > 1 else 'c2'
-spec = {'c2': ScenarioSpec.from_cli('co',10,1,0.03), 'c3': ScenarioSpec.from_cli('pp',20,2,0.08,cap=4,loss=0.2)}[cfg]
-B = {'c2':16384,'c3':16384}[cfg]
+spec = {'c2': ScenarioSpec.from_cli('co',10,1,0.03), 'c3': ScenarioSpec.from_cli('pp',20,2,0.08,cap=4,loss=0.2),
+        'c5': ScenarioSpec.from_cli('pp',50,2,0.08,cap=4)}[cfg]
+B = {'c2':16384,'c3':16384,'c5':2048}[cfg]
 env = BatchedEnv(spec, B); env.reset()
 pol = make_policy(spec)
 n=spec.n_agents
