@@ -18,7 +18,7 @@ MAX_AGENTS, MAX_GRID, MAX_LAYERS = 256, 64, 4
 
 EXPORTS = ("cm_abi_version", "cm_strerror", "cm_last_cuda_error", "cm_device_count", "cm_env_reset", "cm_env_step",
            "cm_comm_update", "cm_policy_forward", "cm_policy_blob_floats", "cm_policy_workspace_bytes", "cm_policy_tc_blob_floats", "cm_policy_tc_prepare", "cm_mask_pack",
-           "cm_mask_unpack", "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host")
+           "cm_mask_unpack", "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host", "cm_ppo_advantages", "cm_adam_step")
 
 
 class EnvDesc(C.Structure):
@@ -100,8 +100,12 @@ def lib():
     L.cm_policy_forward_host.argtypes = [C.POINTER(PolicyDesc), C.POINTER(PolicyIO), C.POINTER(PolicyIO), C.c_int64, C.c_void_p]
     L.cm_env_step_host.argtypes = [C.POINTER(EnvDesc), C.POINTER(EnvState), C.POINTER(StepIO), C.POINTER(StepIO), C.c_void_p]
     L.cm_env_reset_host.argtypes = [C.POINTER(EnvDesc), C.POINTER(EnvState), C.POINTER(StepIO), C.POINTER(StepIO), C.c_void_p]
+    L.cm_ppo_advantages.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int32,
+                                    C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cm_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
+                               C.c_float, C.c_int32, C.c_float, C.c_void_p]
     for fn in ("cm_env_reset", "cm_env_step", "cm_comm_update", "cm_policy_forward", "cm_mask_pack", "cm_mask_unpack",
-               "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host"):
+               "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host", "cm_ppo_advantages", "cm_adam_step"):
         getattr(L, fn).restype = C.c_int
     if L.cm_abi_version() != 1:
         raise ImportError("libcommarl_b200.so ABI version mismatch")

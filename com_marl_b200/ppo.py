@@ -1,0 +1,263 @@
+"""PPO update on the device — the trainer side of the rollout engine.
+
+Mirrors, with the reference's semantics and hyper-parameter names:
+  * ``CommBaseCritic``            — com_marl/torch/baselines/comm_base_critic.py:11-120 (CommBaseNet trunk + a
+                                    GaussianMLPModule aggregator, ``aggregator_type='sum'``), same ``state_dict`` names;
+  * ``DevicePPO.process_samples`` — CentralizedMAPPO.process_samples (centralized_ma_ppo.py:612-659): paths padded to
+                                    ``[P, Tmax, ...]`` (zeros; ones for avail / dist_adj / channels), critic baselines;
+  * ``DevicePPO.compute_loss``    — _compute_loss / _compute_objective (:390-438, 540-589): clipped surrogate with the
+                                    HARD-CODED clip range 0.1 (:121), entropy regularisation, mean over the valid steps;
+  * ``DevicePPO.train_once``      — the optimisation loop of train_once (:207-262): path ids shuffled once, cut into
+                                    ``optimization_n_minibatches`` slices, ``optimization_mini_epochs`` passes, critic loss,
+                                    clip_grad_norm_ on the policy, both Adam steps.
+Returns, GAE advantages and their per-path normalisation run in ``cm_ppo_advantages`` and both Adam steps in
+``cm_adam_step`` (hand-written CUDA over flat parameter buckets, csrc/ppo_kernels.cu); the network forward / backward is
+torch autograd over the policy's differentiable ``forward``.  With more than one rank the flat gradient buckets are
+all-reduced (NCCL) before clipping — the only collective of the update.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import _native as N
+from .policy import _Attention, _GraphConv, _MLP
+
+
+class _GaussianHead(nn.Module):
+    """GaussianMLPModule(input_dim, 1, hidden_sizes, share_std=True) (gaussian_mlp_module.py:64-170): mean MLP +
+    one learnable log-std, clamped at log(1e-6)."""
+
+    def __init__(self, input_dim, hidden_sizes):
+        super().__init__()
+        self._init_std = nn.Parameter(torch.zeros(1))                      # log(init_std = 1)
+        self._mean_module = _MLP(input_dim, hidden_sizes, 1, output_tanh=False)
+
+    def forward(self, x):
+        mean = self._mean_module(x)
+        std = self._init_std.clamp(min=float(np.log(np.float32(1e-6)))).exp()
+        return mean, std
+
+
+class CommBaseCritic(nn.Module):
+    """Centralised value baseline V(s) = sum_i f(E_i + H_L,i) with the policy's comm-GNN trunk."""
+
+    def __init__(self, env_spec, n_agents, encoder_hidden_sizes=(128,), embedding_dim=64, decoder_hidden_sizes=(64,),
+                 attention_type="general", n_gcn_layers=2, residual=True, gcn_bias=True, aggregator_type="sum",
+                 name="base_critic", device="cuda"):
+        super().__init__()
+        if attention_type != "general" or aggregator_type != "sum":
+            raise NotImplementedError("attention_type='general' and aggregator_type='sum' (the runners' settings) only")
+        self.name, self.device = name, torch.device(device)
+        self._n_agents, self.residual, self.eps = int(n_agents), bool(residual), 1e-12
+        self._dec_obs_dim = int(env_spec.observation_space.flat_dim / n_agents)
+        self.encoder = _MLP(self._dec_obs_dim, tuple(encoder_hidden_sizes), embedding_dim, output_tanh=True)
+        self.attention_layer = _Attention(embedding_dim)
+        self.gcn_layers = nn.ModuleList([_GraphConv(embedding_dim, gcn_bias) for _ in range(int(n_gcn_layers))])
+        self.baseline_aggregator = _GaussianHead(embedding_dim, tuple(decoder_hidden_sizes))
+        self.to(self.device)
+
+    def _values(self, obs_n, dist_adj, channels):
+        n = self._n_agents
+        obs_n = obs_n.reshape(obs_n.shape[:-1] + (n, -1))
+        channels = channels.reshape(channels.shape[:-2] + (len(self.gcn_layers), n, n))
+        if dist_adj.shape[-2:] != torch.Size((n, n)):
+            dist_adj = dist_adj.reshape(dist_adj.shape[:-1] + (n, n))
+        E = self.encoder(obs_n)
+        M = self.attention_layer(E)
+        H = E
+        for l, gcn in enumerate(self.gcn_layers):                      # comm_base_net.py:99-104
+            A = M * dist_adj * channels[..., l, :, :]
+            A = A / (A.sum(dim=-1, keepdim=True) + self.eps)
+            H = gcn(H, A)
+        X = E + H if self.residual else H
+        mean, std = self.baseline_aggregator(X)
+        return mean.squeeze(-1).sum(-1), std.mean()
+
+    def forward(self, obs_n, avail_actions_n, dist_adj, channels, get_actions=False):
+        return self._values(obs_n, dist_adj, channels)[0]
+
+    def compute_loss(self, obs_n, returns, dist_adj, channels, get_actions=False):
+        mean, std = self._values(obs_n, dist_adj, channels)           # -Normal(mean, std).log_prob(returns).mean()
+        return (0.5 * ((returns - mean) / std) ** 2 + std.log() + 0.5 * float(np.log(2 * np.pi))).mean()
+
+
+class FlatAdam:
+    """The reference's Adam (my_optimizer/adam.py) over ONE flat fp32 bucket: parameters and gradients of the module are
+    re-seated as views of two flat tensors, so that the gradient all-reduce is one NCCL call, the gradient norm one
+    reduction and the optimizer step one kernel (cm_adam_step)."""
+
+    def __init__(self, module, lr=3e-4, betas=(0.9, 0.999), eps=1e-5):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        o = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[o:o + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + k].view_as(p)
+            p.grad = self.grad[o:o + k].view_as(p)
+            o += k
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        self.lr, self.betas, self.eps, self.steps = float(lr), betas, float(eps), 0
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def all_reduce(self, group=None):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.grad, group=group)
+            self.grad.div_(dist.get_world_size(group))
+
+    def clip_coefficient(self, max_norm):
+        """torch.nn.utils.clip_grad_norm_: min(1, max_norm / (||g|| + 1e-6)); returns (coefficient, norm) as 0-d tensors"""
+        norm = self.grad.norm(2)
+        return torch.clamp(max_norm / (norm + 1e-6), max=1.0), norm
+
+    def step(self, grad_scale=1.0):
+        self.steps += 1
+        with torch.cuda.device(self.flat.device):
+            N.check("cm_adam_step", N.lib().cm_adam_step(N.ptr(self.flat), N.ptr(self.grad), N.ptr(self.exp_avg), N.ptr(self.exp_avg_sq),
+                                                         self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.steps,
+                                                         float(grad_scale), N.stream_ptr()))
+        for p in self.params:                 # the kernel wrote the parameters behind autograd's back: bump the version
+            torch.autograd.graph.increment_version(p)      # counters, so that the policy rebuilds its kernel weight blobs
+
+
+def ppo_advantages(rewards, baselines, valids, discount, gae_lambda, center=True, eps=1e-8):
+    """(returns, raw_adv, adv) float32 [P, T] from float64 rewards, float32 baselines [P, T] and int32 valids [P]"""
+    P, T = rewards.shape
+    rewards = rewards.to(torch.float64).contiguous()
+    baselines = baselines.to(torch.float32).contiguous()
+    valids = valids.to(torch.int32).contiguous()
+    out = [torch.empty((P, T), dtype=torch.float32, device=rewards.device) for _ in range(3)]
+    with torch.cuda.device(rewards.device):
+        N.check("cm_ppo_advantages", N.lib().cm_ppo_advantages(N.ptr(rewards), N.ptr(baselines), N.ptr(valids), P, T, float(discount),
+                                                               float(gae_lambda), int(bool(center)), float(eps), N.ptr(out[0]),
+                                                               N.ptr(out[1]), N.ptr(out[2]), N.stream_ptr()))
+    return out
+
+
+class DevicePPO:
+    """CentralizedMAPPO's update (centralized_ma_ppo.py) for a Comm-DP policy + CommBaseCritic pair on one GPU per rank."""
+
+    def __init__(self, policy, baseline, discount=0.99, gae_lambda=0.97, center_adv=True, positive_adv=False,
+                 policy_ent_coeff=0.1, entropy_method="regularized", clip_grad_norm=7, optimization_n_minibatches=3,
+                 optimization_mini_epochs=10, policy_lr=3e-4, adam_eps=1e-5, process_group=None):
+        if entropy_method not in ("regularized", "no_entropy"):
+            raise NotImplementedError("entropy_method 'max' (entropy added to the rewards) is not implemented")
+        if entropy_method == "no_entropy" and policy_ent_coeff != 0.0:
+            raise ValueError("policy_ent_coeff should be zero when there is no entropy method")
+        self.policy, self.baseline, self.device = policy, baseline, policy.device
+        self.discount, self.gae_lambda = float(discount), float(gae_lambda)
+        self.center_adv, self.positive_adv = bool(center_adv), bool(positive_adv)
+        self.ent_coeff = float(policy_ent_coeff) if entropy_method == "regularized" else 0.0
+        self.lr_clip_range = 0.1                      # centralized_ma_ppo.py:121 overrides the constructor argument
+        self.adv_eps = 1e-8                           # :122
+        self.clip_grad_norm = clip_grad_norm
+        self.n_minibatches, self.mini_epochs = int(optimization_n_minibatches), int(optimization_mini_epochs)
+        self.group = process_group
+        self.opt = FlatAdam(policy, lr=policy_lr, eps=adam_eps)
+        self.baseline_opt = FlatAdam(baseline, lr=policy_lr, eps=adam_eps)
+
+    # ---- process_samples ----------------------------------------------------------------------------------------
+    def process_samples(self, paths):
+        """paths: the sampler's list of dicts (…vectorized_sampler.py:192-224).  Returns a dict of device tensors padded to
+        the longest path like the reference, plus baselines / returns / advantages."""
+        dev, n = self.device, self.policy._n_agents
+        P, Tmax = len(paths), max(len(p["rewards"]) for p in paths)
+
+        def pad(key, dtype, fill):
+            first = np.asarray(paths[0][key])
+            out = np.full((P, Tmax) + first.shape[1:], fill, dtype=dtype)
+            for i, p in enumerate(paths):
+                a = np.asarray(p[key])
+                out[i, :len(a)] = a
+            return torch.from_numpy(out).to(dev)
+
+        b = dict(obs=pad("observations", np.float32, 0), avail=pad("avail_actions", np.float32, 1),
+                 actions=pad("actions", np.int64, 0), rewards=pad("rewards", np.float64, 0),
+                 dist_adjs=pad("dist_adjs", np.float32, 1), channels=pad("channels", np.float32, 1),
+                 valids=torch.tensor([len(p["rewards"]) for p in paths], dtype=torch.int32, device=dev))
+        return self.finish_batch(b)
+
+    def finish_batch(self, b):
+        """baselines (critic, no grad), returns and advantages for a padded device batch with the keys of process_samples"""
+        with torch.no_grad():
+            b["baselines"] = self.baseline.forward(b["obs"], b["avail"], b["dist_adjs"], b["channels"]).float()
+        b["returns"], b["raw_adv"], b["adv"] = ppo_advantages(b["rewards"], b["baselines"], b["valids"], self.discount,
+                                                              self.gae_lambda, self.center_adv, self.adv_eps)
+        T = b["rewards"].shape[1]
+        b["mask"] = torch.arange(T, device=self.device)[None, :] < b["valids"][:, None]
+        return b
+
+    # ---- losses ----------------------------------------------------------------------------------------------------
+    def _dist(self, b, ids):
+        sel = (lambda x: x) if ids is None else (lambda x: x[ids])
+        d, _ = self.policy.forward(sel(b["obs"]), sel(b["avail"]), sel(b["dist_adjs"]), sel(b["channels"]))
+        return d
+
+    def compute_loss(self, b, ids=None, old_ll=None):
+        sel = (lambda x: x) if ids is None else (lambda x: x[ids])
+        d = self._dist(b, ids)
+        new_ll = d.log_prob(sel(b["actions"])).sum(-1)
+        ent = d.entropy().mean(-1)
+        old = new_ll.detach() if old_ll is None else sel(old_ll)
+        adv = sel(b["adv"])
+        if self.positive_adv:
+            adv = adv - adv.min()
+        ratio = (new_ll - old).exp()
+        obj = torch.min(ratio * adv, torch.clamp(ratio, 1 - self.lr_clip_range, 1 + self.lr_clip_range) * adv)
+        if self.ent_coeff:
+            obj = obj + self.ent_coeff * ent
+        return -obj[sel(b["mask"])].mean()
+
+    def kl(self, b, old_probs):
+        new = self._dist(b, None).probs
+        t = old_probs * (old_probs.clamp_min(1e-38).log() - new.clamp_min(1e-38).log())
+        return torch.where(old_probs > 0, t, torch.zeros_like(t)).sum(-1).mean()
+
+    # ---- train_once ------------------------------------------------------------------------------------------------
+    def train_once(self, paths=None, batch=None, shuffled_ids=None):
+        """One policy-optimisation round.  ``paths`` (sampler output) or an already padded device ``batch``.
+        ``shuffled_ids``: the path permutation (np.random.permutation in the reference)."""
+        b = self.process_samples(paths) if batch is None else batch
+        P = b["rewards"].shape[0]
+        with torch.no_grad():
+            d0 = self._dist(b, None)
+            old_probs = d0.probs
+            old_ll = d0.log_prob(b["actions"]).sum(-1)              # the frozen old policy (:204) evaluated once
+            loss_before = float(self.compute_loss(b, None, old_ll))
+        ids_all = np.random.permutation(P) if shuffled_ids is None else np.asarray(shuffled_ids)
+        step = int(np.ceil(P / self.n_minibatches))
+        losses, bl_losses, gnorms = [], [], []
+        for _ in range(self.mini_epochs):
+            for start in range(0, P, step):
+                ids = torch.as_tensor(ids_all[start:min(start + step, P)], device=self.device)
+                self.baseline_opt.zero_grad()
+                self.opt.zero_grad()
+                bl = self.baseline.compute_loss(b["obs"][ids], b["returns"][ids], b["dist_adjs"][ids], b["channels"][ids])
+                bl.backward()
+                loss = self.compute_loss(b, ids, old_ll)
+                loss.backward()
+                self.opt.all_reduce(self.group)
+                self.baseline_opt.all_reduce(self.group)
+                scale = 1.0
+                if self.clip_grad_norm is not None:
+                    coef, norm = self.opt.clip_coefficient(self.clip_grad_norm)
+                    scale = float(coef)
+                    gnorms.append(float(norm) * scale)             # policy.grad_norm() after clipping (:254-255)
+                self.opt.step(scale)
+                self.baseline_opt.step(1.0)
+                losses.append(float(loss.detach())); bl_losses.append(float(bl.detach()))
+        with torch.no_grad():
+            loss_after = float(self.compute_loss(b, None, old_ll))
+            kl = float(self.kl(b, old_probs))
+            d1 = self._dist(b, None)
+            entropy = float(d1.entropy().mean(-1).mean())
+        return dict(loss_before=loss_before, loss_after=loss_after, kl=kl, entropy=entropy, losses=losses,
+                    baseline_losses=bl_losses, grad_norms=gnorms, n_paths=P)

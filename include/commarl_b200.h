@@ -238,6 +238,21 @@ int cm_env_step_host(const cm_env_desc *desc, const cm_env_state *state, const c
 int cm_env_reset_host(const cm_env_desc *desc, const cm_env_state *state, const cm_step_io *dev, const cm_step_io *host,
                       cm_stream_t stream);
 
+/* ---- PPO update helpers (the network forward / backward is torch autograd, com_marl_b200/ppo.py) ----
+ * cm_ppo_advantages: rows of the padded [P][T] batch of CentralizedMAPPO.process_samples (centralized_ma_ppo.py:612-659):
+ *   returns  = tensor_utils.discount_cumsum of the valid steps (garage/misc/tensor_utils.py:7-23; float64 recursion),
+ *   raw_adv  = compute_advantages (garage/torch/algos/_utils.py:56-113) over the whole padded row, baselines of the
+ *              padded tail included like the reference does,
+ *   adv      = per-path normalisation with the mean / biased variance of the valid steps (center_adv,
+ *              centralized_ma_ppo.py:425-429).  Any output may be NULL.
+ * cm_adam_step: one step of the reference's Adam (my_optimizer/adam.py:57-120 -> functional adam; no amsgrad / weight
+ *   decay) over a flat fp32 bucket, grads scaled by grad_scale (the clip_grad_norm_ coefficient) in the same pass. */
+int cm_ppo_advantages(const double *rewards, const float *baselines, const int32_t *valids, int64_t n_paths, int32_t T,
+                      float discount, float gae_lambda, int32_t center, float eps, float *returns, float *raw_adv, float *adv,
+                      cm_stream_t stream);
+int cm_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                 float beta2, float eps, int32_t step, float grad_scale, cm_stream_t stream);
+
 /* dense float32 masks (the reference's dist_adj (B,n,n) / channels (B,L,n,n)) <-> bit rows */
 int cm_mask_pack(const float *dense, uint32_t *bits, int64_t rows, int32_t n, cm_stream_t stream);
 int cm_mask_unpack(const uint32_t *bits, float *dense, int64_t rows, int32_t n, cm_stream_t stream);

@@ -335,3 +335,46 @@ def policy_forward_dec(w, obs, avail, dtype=np.float32):
         pr = pr * np.asarray(avail, dtype=f)
     pr = pr / pr.sum(axis=-1, keepdims=True)
     return logits.astype(f), pr.astype(f)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PPO update pieces — numpy restatement of the reference's tensor code, test infrastructure only
+# ---------------------------------------------------------------------------------------------------------------
+def discount_cumsum(x, discount):
+    """tensor_utils.discount_cumsum (garage/misc/tensor_utils.py:7-23): y[t] = x[t] + discount * y[t+1], float64."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.zeros_like(x)
+    acc = 0.0
+    for t in range(len(x) - 1, -1, -1):
+        acc = x[t] + float(discount) * acc
+        y[t] = acc
+    return y
+
+
+def ppo_advantages(rewards, baselines, valids, discount, gae_lambda, center=True, eps=1e-8):
+    """returns / GAE advantages / per-path normalised advantages of a padded [P, T] batch.
+    rewards: zero-padded float64; baselines: float32 critic values of EVERY padded step (the reference evaluates the
+    critic on the padded observations, centralized_ma_ppo.py:650-657); valids: path lengths.
+    compute_advantages (garage/torch/algos/_utils.py:56-113): deltas = r + g * shift(b) - b, advantages = correlation of
+    the zero-extended deltas with cumprod([1, g*lam, g*lam, ...]) over the whole row; center_adv
+    (centralized_ma_ppo.py:425-429): batch_norm of each row with the mean / biased variance of its valid part."""
+    r32 = np.asarray(rewards, dtype=np.float64).astype(np.float32)
+    b = np.asarray(baselines, dtype=np.float32)
+    P, T = r32.shape
+    filt = np.cumprod(np.concatenate([[1.0], np.full(T - 1, np.float32(discount) * np.float32(gae_lambda))]).astype(np.float32),
+                      dtype=np.float32)
+    b_next = np.concatenate([b[:, 1:], np.zeros((P, 1), np.float32)], axis=1)
+    deltas = (r32 + np.float32(discount) * b_next - b).astype(np.float32)
+    raw = np.zeros((P, T), dtype=np.float32)
+    for t in range(T):
+        raw[:, t] = (deltas[:, t:] * filt[:T - t]).sum(axis=1, dtype=np.float32)
+    returns = np.zeros((P, T), dtype=np.float32)
+    adv = raw.copy()
+    for p in range(P):
+        v = int(valids[p])
+        returns[p, :v] = discount_cumsum(np.asarray(rewards, dtype=np.float64)[p, :v], discount).astype(np.float32)
+        if center:
+            mean = raw[p, :v].mean(dtype=np.float32)
+            var = ((raw[p, :v] - mean) ** 2).mean(dtype=np.float32)
+            adv[p] = (raw[p] - mean) / np.sqrt(var + np.float32(eps))
+    return returns, raw, adv

@@ -1,0 +1,137 @@
+"""PPO update against golden vectors recorded from the UNMODIFIED reference
+(tests/golden/make_golden_ppo.py: CentralizedMAPPO.process_samples / _compute_loss / the optimisation loop of train_once,
+CommBaseCritic, the reference's Adam)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = ["pp", "co"]
+
+
+class PPOCase:
+    def __init__(self, name):
+        z = np.load(os.path.join(HERE, "golden", f"ppo_{name}.npz"))
+        self.z = z
+        self.meta = json.loads(str(z["meta"]))
+        m = self.meta
+        self.paths = [{k: z[f"path{i}::{k}"] for k in ("observations", "actions", "avail_actions", "rewards", "dist_adjs", "channels")}
+                      for i in range(int(m["n_paths"]))]
+        self.sd = {tag: {k.split("::", 1)[1]: z[k] for k in z.files if k.startswith(tag + "::")} for tag in ("pol0", "cri0", "pol1", "cri1")}
+
+    def padded_rewards(self):
+        P, T = len(self.paths), max(len(p["rewards"]) for p in self.paths)
+        r = np.zeros((P, T), dtype=np.float64)
+        for i, p in enumerate(self.paths):
+            r[i, :len(p["rewards"])] = p["rewards"]
+        return r
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_advantages_match_reference(name):
+    """the numpy restatement of discount_cumsum / compute_advantages / center_adv reproduces the reference's tensors"""
+    c = PPOCase(name)
+    m = c.meta
+    returns, raw, adv = orc.ppo_advantages(c.padded_rewards(), c.z["baselines"], c.z["valids"], m["discount"], m["gae_lambda"])
+    assert np.abs(returns - c.z["returns"]).max() <= 1e-5 * max(1.0, np.abs(c.z["returns"]).max())
+    assert np.abs(raw - c.z["raw_adv"]).max() <= 1e-5 * max(1.0, np.abs(c.z["raw_adv"]).max())
+    assert np.abs(adv - c.z["adv"]).max() <= 2e-5 * max(1.0, np.abs(c.z["adv"]).max())
+
+
+def _build(c, device="cuda"):
+    import torch
+    from com_marl_b200.policy import CommCategoricalMLPPolicy
+    from com_marl_b200.ppo import CommBaseCritic, DevicePPO
+    from com_marl_b200.spaces import Box, Discrete, EnvSpec
+    m = c.meta
+    n, D = int(m["n"]), int(m["D"])
+    spec = EnvSpec(Box(np.zeros(n * D), np.ones(n * D)), Discrete(5))
+    pol = CommCategoricalMLPPolicy(spec, n, device=device)
+    cri = CommBaseCritic(spec, n, device=device)
+    pol.load_state_dict({k: torch.as_tensor(v) for k, v in c.sd["pol0"].items()})
+    cri.load_state_dict({k: torch.as_tensor(v) for k, v in c.sd["cri0"].items()})       # reference checkpoints load as is
+    algo = DevicePPO(pol, cri, discount=m["discount"], gae_lambda=m["gae_lambda"], policy_ent_coeff=m["ent_coeff"],
+                     clip_grad_norm=m["clip_grad_norm"], optimization_n_minibatches=int(m["n_minibatches"]),
+                     optimization_mini_epochs=int(m["mini_epochs"]), policy_lr=m["lr"], adam_eps=m["adam_eps"])
+    return pol, cri, algo
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_process_samples_and_loss_match_reference(name):
+    """critic baselines, returns, advantages (cm_ppo_advantages), entropy, log-likelihood and the PPO loss"""
+    import torch
+    c = PPOCase(name)
+    pol, cri, algo = _build(c)
+    b = algo.process_samples(c.paths)
+    z = c.z
+    close = lambda a, ref, tol=1e-5: np.abs(a.detach().cpu().numpy() - ref).max() <= tol * max(1.0, np.abs(ref).max())  # noqa: E731
+    assert np.array_equal(b["valids"].cpu().numpy(), z["valids"])
+    assert close(b["baselines"], z["baselines"])
+    assert close(b["returns"], z["returns"])
+    assert close(b["raw_adv"], z["raw_adv"], 2e-5)
+    assert close(b["adv"], z["adv"], 5e-5)
+    # the kernel against the oracle on the kernel's own baselines
+    ret_o, raw_o, adv_o = orc.ppo_advantages(c.padded_rewards(), b["baselines"].cpu().numpy(), z["valids"], c.meta["discount"], c.meta["gae_lambda"])
+    assert close(b["returns"], ret_o) and close(b["raw_adv"], raw_o) and close(b["adv"], adv_o, 2e-5)
+    with torch.no_grad():
+        d, _ = pol.forward(b["obs"], b["avail"], b["dist_adjs"], b["channels"])
+        assert close(d.entropy().mean(-1), z["entropy"])
+        assert close(d.log_prob(b["actions"]).sum(-1), z["loglik"])
+        assert abs(float(algo.compute_loss(b)) - float(z["loss_before"])) <= 2e-5
+        bl0 = cri.compute_loss(b["obs"], b["returns"], b["dist_adjs"], b["channels"])
+        assert abs(float(bl0) - float(z["baseline_loss0"])) <= 1e-5 * max(1.0, abs(float(z["baseline_loss0"])))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_train_once_matches_reference(name):
+    """the whole optimisation loop (2 mini-epochs x 3 minibatches, clip_grad_norm, both Adam steps through cm_adam_step):
+    per-step losses, gradient norms and the final policy / critic weights equal the reference's"""
+    c = PPOCase(name)
+    pol, cri, algo = _build(c)
+    z = c.z
+    out = algo.train_once(paths=c.paths, shuffled_ids=z["shuffled_ids"])
+    assert abs(out["loss_before"] - float(z["loss_before"])) <= 2e-5
+    assert np.abs(np.array(out["losses"]) - z["losses"]).max() <= 1e-4
+    assert np.abs(np.array(out["baseline_losses"]) - z["baseline_losses"]).max() <= 1e-4 * max(1.0, np.abs(z["baseline_losses"]).max())
+    assert np.abs(np.array(out["grad_norms"]) - z["grad_norms"]).max() <= 1e-3 * max(1.0, np.abs(z["grad_norms"]).max())
+    assert abs(out["loss_after"] - float(z["loss_after"])) <= 1e-4
+    assert abs(out["kl"] - float(z["kl"])) <= 1e-5
+    for tag, mod in (("pol1", pol), ("cri1", cri)):
+        for k, v in mod.state_dict().items():
+            ref, ref0 = c.sd[tag][k], c.sd[tag[:3] + "0"][k]
+            step = np.abs(ref - ref0).max()                       # how far the reference moved this tensor
+            assert np.abs(v.cpu().numpy() - ref).max() <= 0.02 * step + 1e-6, (tag, k)
+    # the rollout kernels see the updated weights (the flat-bucket Adam bumps the parameter versions)
+    import torch
+    n, D = int(c.meta["n"]), int(c.meta["D"])
+    obs = torch.rand((8, n, D), device="cuda")
+    logits = torch.empty((8, n, 5), device="cuda")
+    pol.act_device(obs, logits=logits, greedy=True)
+    w = {k: v.cpu().numpy() for k, v in pol.state_dict().items()}
+    ref_logits, _, _ = orc.policy_forward(w, obs.cpu().numpy(), None, np.ones((8, n, n), np.uint8), np.ones((8, 2, n, n), np.uint8))
+    assert np.abs(logits.cpu().numpy() - ref_logits).max() <= 1e-5 * max(1.0, np.abs(ref_logits).max())
+
+
+@pytest.mark.gpu
+def test_adam_step_kernel_matches_torch():
+    import torch
+    from com_marl_b200 import _native as N
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 100003
+    p = torch.randn(n, device="cuda", generator=g)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([ref], lr=3e-4, eps=1e-5)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 6):
+        grad = torch.randn(n, device="cuda", generator=g)
+        ref.grad = grad.clone() * 0.5
+        opt.step()
+        N.check("cm_adam_step", N.lib().cm_adam_step(N.ptr(p), N.ptr(grad), N.ptr(m), N.ptr(v), n, 3e-4, 0.9, 0.999, 1e-5, step, 0.5,
+                                                     N.stream_ptr()))
+        assert (p - ref.detach()).abs().max().item() <= 1e-6
