@@ -128,6 +128,16 @@ class FlatAdam:
             torch.autograd.graph.increment_version(p)      # counters, so that the policy rebuilds its kernel weight blobs
 
 
+def _unpack_mask(bits, n):
+    """int32 bit rows (..., n, W) -> dense float32 (..., n, n) (cm_mask_unpack)"""
+    bits = bits.contiguous()
+    rows = bits.numel() // bits.shape[-1]
+    out = torch.empty(bits.shape[:-1] + (n,), dtype=torch.float32, device=bits.device)
+    with torch.cuda.device(bits.device):
+        N.check("cm_mask_unpack", N.lib().cm_mask_unpack(N.ptr(bits), N.ptr(out), rows, n, N.stream_ptr()))
+    return out
+
+
 def ppo_advantages(rewards, baselines, valids, discount, gae_lambda, center=True, eps=1e-8):
     """(returns, raw_adv, adv) float32 [P, T] from float64 rewards, float32 baselines [P, T] and int32 valids [P]"""
     P, T = rewards.shape
@@ -183,6 +193,54 @@ class DevicePPO:
                  actions=pad("actions", np.int64, 0), rewards=pad("rewards", np.float64, 0),
                  dist_adjs=pad("dist_adjs", np.float32, 1), channels=pad("channels", np.float32, 1),
                  valids=torch.tensor([len(p["rewards"]) for p in paths], dtype=torch.int32, device=dev))
+        return self.finish_batch(b)
+
+    def batch_from_trajectory(self, traj, K=None):
+        """The same padded batch straight from the rollout engine's device trajectory (``RolloutEngine.traj``: time-major
+        slots ``obs [K+1,B,n,D]``, ``actions [K,B,n]``, ``reward [K,B]``, ``done [K,B]``, bit-row masks) without the host
+        `paths` list: every episode that FINISHED inside the K recorded steps becomes one row (the reference's sampler
+        only appends finished paths too, …vectorized_sampler.py:189-226), ordered env-major then by time."""
+        dev, n = self.device, self.policy._n_agents
+        done = traj["done"] if K is None else traj["done"][:K]
+        K, B = done.shape
+        done = done.to(torch.int64)
+        nth = done.cumsum(0) - done                          # episodes finished before step k in env b = index of k's episode
+        fin = done.sum(0)                                    # finished episodes per env
+        P = int(fin.sum())
+        if P == 0:
+            raise ValueError("no episode finished inside the recorded trajectory")
+        valid = nth < fin[None, :]                           # step belongs to an episode that finishes inside the window
+        off = fin.cumsum(0) - fin                            # first path id of env b
+        pid = off[None, :] + nth                             # [K, B] path id of every step
+        ks = torch.arange(K, device=dev)[:, None].expand(K, B)
+        # step inside its episode: k - (1 + the last step before k at which env b reported done)
+        last_done = torch.where(done.bool(), ks, torch.full_like(ks, -1)).cummax(0).values
+        prev_done = torch.cat([torch.full((1, B), -1, dtype=torch.int64, device=dev), last_done[:-1]], 0)
+        t_in = ks - (prev_done + 1)
+        ends = done.bool() & valid
+        valids = torch.zeros(P, dtype=torch.int64, device=dev)
+        valids.index_put_((pid[ends],), t_in[ends] + 1)
+        Tmax = int(valids.max())
+        src = torch.full((P * Tmax,), -1, dtype=torch.int64, device=dev)
+        flat = (ks * B + torch.arange(B, device=dev)[None, :])
+        src.index_put_(((pid * Tmax + t_in)[valid],), flat[valid])
+        pad = src < 0
+        g = src.clamp(min=0)
+
+        def take(x, fill):
+            y = x[:K].reshape((K * B,) + x.shape[2:]).index_select(0, g)
+            y[pad] = fill
+            return y.reshape((P, Tmax) + x.shape[2:])
+
+        L = traj["chan_bits"].shape[2]
+        adj = _unpack_mask(traj["adj_bits"][:K].reshape(K * B, n, -1).index_select(0, g), n)
+        chan = _unpack_mask(traj["chan_bits"][:K].reshape(K * B, L, n, -1).index_select(0, g), n)
+        adj[pad] = 1.0
+        chan[pad] = 1.0
+        b = dict(obs=take(traj["obs"], 0.0).reshape(P, Tmax, -1), actions=take(traj["actions"], 0).to(torch.int64),
+                 rewards=take(traj["reward"], 0.0), valids=valids.to(torch.int32),
+                 dist_adjs=adj.reshape(P, Tmax, n * n), channels=chan.reshape(P, Tmax, L * n, n),
+                 avail=torch.ones((P, Tmax, n * 5), dtype=torch.float32, device=dev))
         return self.finish_batch(b)
 
     def finish_batch(self, b):

@@ -128,6 +128,13 @@ def _gloo_worker(rank, world, port, q):
         p.grad = torch.full_like(p, float(r + 1))
     nfl = D.allreduce_gradients(lin)
     gmean = [float(p.grad.mean()) for p in lin.parameters()]
+    # the PPO update's flat gradient bucket (com_marl_b200.ppo.FlatAdam): one all-reduce, parameters' .grad are views of it
+    from com_marl_b200.ppo import FlatAdam
+    lin2 = torch.nn.Linear(4, 3)
+    fa = FlatAdam(lin2)
+    fa.grad.fill_(float(r + 1))
+    fa.all_reduce()
+    gmean += [float(fa.grad.mean()), float(lin2.weight.grad.mean()), float(fa.flat.numel())]
     q.put((r, (out.tolist(), nfl, gmean)))
     torch.distributed.destroy_process_group()
 
@@ -148,7 +155,7 @@ def test_stats_all_gather_world_size_2_gloo():
     assert res[0] == res[1]
     stats, nfl, gmean = res[0]
     assert [row[0] for row in stats] == [501.0, 500.0] and [row[1] for row in stats] == [10.0, 20.0]
-    assert nfl == 15 and gmean == [1.5, 1.5]
+    assert nfl == 15 and gmean == [1.5, 1.5, 1.5, 1.5, 15.0]
 
 
 def test_truncate_paths():

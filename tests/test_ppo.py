@@ -119,6 +119,53 @@ def test_train_once_matches_reference(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("scen,m,den,T", [("pp", 10, 0.04, 9), ("co", 10, 0.03, 13)])
+def test_device_trajectory_batch_equals_paths(scen, m, den, T):
+    """DevicePPO.batch_from_trajectory (no host `paths` list) builds exactly the padded batch process_samples builds from
+    the per-episode dicts cut out of the same trajectory; one update round runs on it."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import ref_harness
+    from com_marl_b200.ppo import CommBaseCritic, DevicePPO
+    from com_marl_b200.rollout import RolloutEngine, make_policy
+    from com_marl_b200.scenario import ScenarioSpec
+    from com_marl_b200.spaces import Box, Discrete, EnvSpec
+    params = ref_harness.scenario_params(scen, m, 1, den, cap=2, loss=0.2, max_env_steps=T)
+    spec = ScenarioSpec.from_params(scen, params, seed=3)
+    spec.max_path_length = T
+    pol = make_policy(spec)
+    n, D, L, B, K = spec.n_agents, spec.obs_dim, spec.n_layers, 37, 32
+    cri = CommBaseCritic(EnvSpec(Box(np.zeros(n * D), np.ones(n * D)), Discrete(5)), n)
+    algo = DevicePPO(pol, cri, optimization_mini_epochs=2)
+    eng = RolloutEngine(spec, pol, B, ring=K, use_graph=False)
+    eng.reset()
+    eng.run_chunk()
+    b = algo.batch_from_trajectory(eng.traj)
+    t = {k: v.cpu().numpy() for k, v in eng.traj.items()}
+    unpack = lambda bits: ((bits.view(np.uint32)[..., np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(np.float32)  # noqa: E731
+    paths = []
+    for e in range(B):
+        start = 0
+        for k in np.nonzero(t["done"][:, e])[0]:
+            sl = slice(start, int(k) + 1)
+            T_ = int(k) + 1 - start
+            paths.append(dict(observations=t["obs"][sl, e].reshape(T_, -1), actions=t["actions"][sl, e].astype(np.int64),
+                              avail_actions=np.ones((T_, n * 5)), rewards=t["reward"][sl, e],
+                              dist_adjs=unpack(t["adj_bits"][sl, e]).reshape(T_, n * n),
+                              channels=unpack(t["chan_bits"][sl, e]).reshape(T_, L * n, n)))
+            start = int(k) + 1
+    assert len(paths) >= B * (K // T) - B
+    ref = algo.process_samples(paths)
+    for k in ("obs", "actions", "rewards", "valids", "dist_adjs", "channels", "avail", "mask"):
+        assert torch.equal(b[k], ref[k]), k
+    for k in ("baselines", "returns", "adv"):
+        assert (b[k] - ref[k]).abs().max().item() <= 1e-5 * max(1.0, ref[k].abs().max().item()), k
+    out = algo.train_once(batch=b)
+    assert np.isfinite(out["loss_after"]) and out["loss_after"] < out["loss_before"] and out["kl"] >= 0
+
+
+@pytest.mark.gpu
 def test_adam_step_kernel_matches_torch():
     import torch
     from com_marl_b200 import _native as N
