@@ -278,7 +278,9 @@ struct MmaOp { uint32_t dcol, acc, abuf; };   // accumulator block, accumulate f
 // kVec: width (in floats) of the shared-memory loads of the attention loops — 4 when the team size is a multiple of 4,
 // 2 when it is even, else 1 (the keys / values of an env start at a multiple of n floats).  One instantiation per width,
 // so that small odd teams (n = 3) carry none of the vector code.
-template <int kVec>
+// kMode: kTcModeComm / Dec / Enc / Head as a template parameter, so that the Comm-DP kernel carries none of the other modes'
+// code (the kernel is instruction-fetch sensitive: its SASS is several times the instruction cache).
+template <int kVec, int kMode>
 __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -436,7 +438,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
     float *stage = KV;
     constexpr int kStageFloats = (64 + 8) * kTPitch - 4;
     // rows of tile tl: whole environments (Comm-DP: the attention stays inside a tile) or any 128 agent rows (Obs-DP)
-    const int mode = A.mode, Din = A.in_dim;
+    constexpr int mode = kMode;
+    const int Din = A.in_dim;
     const bool dec = mode != kTcModeComm;            // every mode but Comm-DP treats the agent rows independently
     const int total_rows = n_envs * n;
     auto tile_rows = [&](int tl, int &r0, int &nr) {
@@ -856,9 +859,13 @@ static int launch_tc_mode(const cm_policy_desc *desc, const cm_policy_io *io, in
     A.n_tiles = rows_mode ? (io->n_envs * desc->n_agents + kTcRows - 1) / kTcRows : (io->n_envs + A.envs_per_tile - 1) / A.envs_per_tile;
     const size_t smem = tc_smem_bytes();
     const int vec = rows_mode ? 1 : ((desc->n_agents & 3) == 0 ? 4 : ((desc->n_agents & 1) == 0 ? 2 : 1));
-    void (*kernel)(const TcArgs) = vec == 4 ? policy_tc_kernel<4> : (vec == 2 ? policy_tc_kernel<2> : policy_tc_kernel<1>);
-    static thread_local struct { int dev; int sms; } cache[3] = {{-1, 0}, {-1, 0}, {-1, 0}};
-    auto &cc = cache[vec >> 1];
+    void (*kernel)(const TcArgs) =
+        mode == kTcModeDec ? policy_tc_kernel<1, kTcModeDec>
+        : mode == kTcModeEnc ? policy_tc_kernel<1, kTcModeEnc>
+        : mode == kTcModeHead ? policy_tc_kernel<1, kTcModeHead>
+        : vec == 4 ? policy_tc_kernel<4, kTcModeComm> : (vec == 2 ? policy_tc_kernel<2, kTcModeComm> : policy_tc_kernel<1, kTcModeComm>);
+    static thread_local struct { int dev; int sms; } cache[6] = {{-1, 0}, {-1, 0}, {-1, 0}, {-1, 0}, {-1, 0}, {-1, 0}};
+    auto &cc = cache[mode == kTcModeComm ? (vec >> 1) : 2 + mode];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ENODEVICE);
     if (cc.dev != dev) {
