@@ -26,16 +26,26 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """every translation unit is compiled on its own (in parallel: the templated kernels take a minute or two each), then linked"""
     if not force and not needs_build():
         return OUT
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(_HERE, "csrc"),
-           "-o", OUT] + [os.path.join(_HERE, "csrc", s) for s in SOURCES]
+    objdir = os.path.join(_HERE, "lib", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    common = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(_HERE, "csrc")]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    subprocess.check_call(cmd)
+        common[1:1] = ["-Xptxas", "-v"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        subprocess.check_call(common + ["-c", os.path.join(_HERE, "csrc", src), "-o", obj])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    subprocess.check_call([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", OUT] + objs)
     return OUT
 
 

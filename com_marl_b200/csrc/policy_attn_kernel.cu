@@ -8,8 +8,9 @@
 //   3. policy_tc_kernel<mode Head>: X rows -> logits / probs / actions
 // The n x n pieces are exact fp32 on the CUDA cores.  One CTA of 8 warps owns an environment; the keys E and the values
 // H_l Wg_l of the whole team sit in shared memory (row-major, <= 256 rows), the query rows are processed in blocks of
-// 8 * RT rows, and EVERYTHING between the scores and the next layer's rows is private to a warp: warp w owns RT query
-// rows, computes their scores against all keys with an RT x KT register tile (lane = key mod 32), takes the softmax and
+// RT rows handed out round-robin to the warps (RT is chosen per team size so that the groups divide evenly among the 8
+// warps: 13 rows for 200 agents = 16 groups), and EVERYTHING between the scores and the next layer's rows is private to a
+// warp: it computes its rows' scores against all keys with an RT x KT register tile (lane = key mod 32), takes the softmax and
 // the masked sums with warp shuffles, parks the un-normalised masked attention rows in its own slice of shared memory
 // and multiplies them with the values (lane = 4 output columns x half of the keys).  No CTA barrier inside a layer.
 // The scores are recomputed per layer (64 n^2 FMAs, as many as the aggregation) instead of keeping n x n floats per env.
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(kAThreads, (RT * KT <= 30) ? 2 : 1) policy_att
     float *Aw = As + warp * RT * AP;
     const int n = A.d.n_agents, L = A.d.n_layers, W = (n + 31) >> 5;
     const Blob o = blob_layout(A.d.obs_dim, L);
-    const int block_rows = kAWarps * RT, nb = (n + block_rows - 1) / block_rows;
+    const int n_groups = (n + RT - 1) / RT;      // groups of RT query rows, dealt round-robin to the warps
     const int half = lane >> 4, cl = (lane & 15) << 2;
     const int n_chunks = (n + 3) >> 2;           // key chunks of 4 (attention values / value rows beyond n are zero)
 
@@ -73,9 +74,8 @@ __global__ void __launch_bounds__(kAThreads, (RT * KT <= 30) ? 2 : 1) policy_att
             __syncthreads();
             const float *bias = A.weights + o.gcn_b + l * kE;
             const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + cl));
-            for (int rb = 0; rb < nb; ++rb) {
-                const int i0 = rb * block_rows + warp * RT;          // this warp's first query row
-                if (i0 >= n) break;                                  // warp-uniform: nothing left for this warp
+            for (int grp = warp; grp < n_groups; grp += kAWarps) {
+                const int i0 = grp * RT;                             // first query row of this group
                 // ---- query rows -> the warp's slice ----
                 __syncwarp();
                 for (int e = lane; e < RT * 16; e += 32) {
@@ -85,6 +85,18 @@ __global__ void __launch_bounds__(kAThreads, (RT * KT <= 30) ? 2 : 1) policy_att
                     *reinterpret_cast<float4 *>(Aw + r * AP + c) = v;
                 }
                 __syncwarp();
+                // neighbour masks of the rows (lane t holds word t): requested before the scores so that the L2 round trip
+                // hides behind them
+                uint32_t mw[RT];
+#pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    mw[r] = 0u;
+                    if (i0 + r < n && lane < W) {
+                        mw[r] = 0xFFFFFFFFu;
+                        if (A.adj_bits) mw[r] &= __ldg(A.adj_bits + (r_env + i0 + r) * W + lane);
+                        if (A.chan_bits) mw[r] &= __ldg(A.chan_bits + (((size_t)env * L + l) * n + i0 + r) * W + lane);
+                    }
+                }
                 // ---- scores: s[r][t] = Q[i0 + r] . E[lane + 32 t] ----
                 float s[RT][KT];
 #pragma unroll
@@ -99,9 +111,15 @@ __global__ void __launch_bounds__(kAThreads, (RT * KT <= 30) ? 2 : 1) policy_att
 #pragma unroll
                     for (int t = 0; t < KT; ++t) {
                         const float4 ev = *reinterpret_cast<const float4 *>(Es + (lane + 32 * t) * kEPitch + k);
+                        // (consecutive FMAs are independent: RT accumulators per k, a dependent one only RT instructions later)
 #pragma unroll
-                        for (int r = 0; r < RT; ++r)
-                            s[r][t] = fmaf(q[r].w, ev.w, fmaf(q[r].z, ev.z, fmaf(q[r].y, ev.y, fmaf(q[r].x, ev.x, s[r][t]))));
+                        for (int r = 0; r < RT; ++r) s[r][t] = fmaf(q[r].x, ev.x, s[r][t]);
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) s[r][t] = fmaf(q[r].y, ev.y, s[r][t]);
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) s[r][t] = fmaf(q[r].z, ev.z, s[r][t]);
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) s[r][t] = fmaf(q[r].w, ev.w, s[r][t]);
                     }
                 }
                 __syncwarp();                                        // every lane has read the query rows
@@ -122,19 +140,13 @@ __global__ void __launch_bounds__(kAThreads, (RT * KT <= 30) ? 2 : 1) policy_att
                         sum += s[r][t];
                     }
                     sum = warp_sumf(sum);
-                    uint32_t mw = 0u;                                // lane t holds word t of the row's neighbour mask
-                    if (i < n && lane < W) {
-                        mw = 0xFFFFFFFFu;
-                        if (A.adj_bits) mw &= __ldg(A.adj_bits + (r_env + i) * W + lane);
-                        if (A.chan_bits) mw &= __ldg(A.chan_bits + (((size_t)env * L + l) * n + i) * W + lane);
-                    }
                     float dsum = 0.0f;
 #pragma unroll
                     for (int t = 0; t < KT; ++t) {
                         const float p = s[r][t] / sum;
                         if (l == 0 && A.attention && i < n && lane + 32 * t < n)     // the UNMASKED softmax (comm_base_net.py:93)
                             A.attention[(r_env + i) * n + lane + 32 * t] = p;
-                        const uint32_t word = __shfl_sync(0xFFFFFFFFu, mw, t);
+                        const uint32_t word = __shfl_sync(0xFFFFFFFFu, mw[r], t);
                         const float a = ((word >> lane) & 1u) ? p : 0.0f;
                         dsum += a;
                         Aw[r * AP + lane + 32 * t] = a;
@@ -154,12 +166,24 @@ __global__ void __launch_bounds__(kAThreads, (RT * KT <= 30) ? 2 : 1) policy_att
                     const float4 h2 = *reinterpret_cast<const float4 *>(HWs + (j + 2) * 64 + cl);
                     const float4 h3 = *reinterpret_cast<const float4 *>(HWs + (j + 3) * 64 + cl);
 #pragma unroll
-                    for (int r = 0; r < RT; ++r) {
-                        const float4 a = *reinterpret_cast<const float4 *>(Aw + r * AP + j);
-                        acc[r][0] = fmaf(a.w, h3.x, fmaf(a.z, h2.x, fmaf(a.y, h1.x, fmaf(a.x, h0.x, acc[r][0]))));
-                        acc[r][1] = fmaf(a.w, h3.y, fmaf(a.z, h2.y, fmaf(a.y, h1.y, fmaf(a.x, h0.y, acc[r][1]))));
-                        acc[r][2] = fmaf(a.w, h3.z, fmaf(a.z, h2.z, fmaf(a.y, h1.z, fmaf(a.x, h0.z, acc[r][2]))));
-                        acc[r][3] = fmaf(a.w, h3.w, fmaf(a.z, h2.w, fmaf(a.y, h1.w, fmaf(a.x, h0.w, acc[r][3]))));
+                    for (int r = 0; r < RT; r += 2) {              // two rows at a time: 8 independent FMAs per key
+                        const float4 a0 = *reinterpret_cast<const float4 *>(Aw + r * AP + j);
+                        const float4 a1 = r + 1 < RT ? *reinterpret_cast<const float4 *>(Aw + (r + 1) * AP + j) : a0;
+                        const float av0[4] = {a0.x, a0.y, a0.z, a0.w}, av1[4] = {a1.x, a1.y, a1.z, a1.w};
+                        const float4 hv[4] = {h0, h1, h2, h3};
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            acc[r][0] = fmaf(av0[jj], hv[jj].x, acc[r][0]);
+                            acc[r][1] = fmaf(av0[jj], hv[jj].y, acc[r][1]);
+                            acc[r][2] = fmaf(av0[jj], hv[jj].z, acc[r][2]);
+                            acc[r][3] = fmaf(av0[jj], hv[jj].w, acc[r][3]);
+                            if (r + 1 < RT) {
+                                acc[r + 1][0] = fmaf(av1[jj], hv[jj].x, acc[r + 1][0]);
+                                acc[r + 1][1] = fmaf(av1[jj], hv[jj].y, acc[r + 1][1]);
+                                acc[r + 1][2] = fmaf(av1[jj], hv[jj].z, acc[r + 1][2]);
+                                acc[r + 1][3] = fmaf(av1[jj], hv[jj].w, acc[r + 1][3]);
+                            }
+                        }
                     }
                 }
 #pragma unroll
@@ -194,12 +218,17 @@ __global__ void __launch_bounds__(kAThreads, (RT * KT <= 30) ? 2 : 1) policy_att
                         const float2 w1 = __ldg(reinterpret_cast<const float2 *>(wg + (k + 1) * kE));
                         const float2 w2 = __ldg(reinterpret_cast<const float2 *>(wg + (k + 2) * kE));
                         const float2 w3 = __ldg(reinterpret_cast<const float2 *>(wg + (k + 3) * kE));
+                        float4 hv[RT];
 #pragma unroll
-                        for (int r = 0; r < RT; ++r) {
-                            const float4 hv = *reinterpret_cast<const float4 *>(Aw + r * AP + k);
-                            o2[r][0] = fmaf(hv.w, w3.x, fmaf(hv.z, w2.x, fmaf(hv.y, w1.x, fmaf(hv.x, w0.x, o2[r][0]))));
-                            o2[r][1] = fmaf(hv.w, w3.y, fmaf(hv.z, w2.y, fmaf(hv.y, w1.y, fmaf(hv.x, w0.y, o2[r][1]))));
-                        }
+                        for (int r = 0; r < RT; ++r) hv[r] = *reinterpret_cast<const float4 *>(Aw + r * AP + k);
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) { o2[r][0] = fmaf(hv[r].x, w0.x, o2[r][0]); o2[r][1] = fmaf(hv[r].x, w0.y, o2[r][1]); }
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) { o2[r][0] = fmaf(hv[r].y, w1.x, o2[r][0]); o2[r][1] = fmaf(hv[r].y, w1.y, o2[r][1]); }
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) { o2[r][0] = fmaf(hv[r].z, w2.x, o2[r][0]); o2[r][1] = fmaf(hv[r].z, w2.y, o2[r][1]); }
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) { o2[r][0] = fmaf(hv[r].w, w3.x, o2[r][0]); o2[r][1] = fmaf(hv[r].w, w3.y, o2[r][1]); }
                     }
 #pragma unroll
                     for (int r = 0; r < RT; ++r)
@@ -248,16 +277,57 @@ static int launch_attn_t(const AttnArgs &A, cudaStream_t stream)
     return e == cudaSuccess ? CM_OK : set_cuda_error(e, CM_ECUDA);
 }
 
-template <int RT>
-static int launch_attn_r(int KT, const AttnArgs &A, cudaStream_t stream)
+static constexpr int kMaxRT = 14;
+static constexpr size_t kMaxSmem = 227 * 1024;
+
+constexpr bool attn_fits(int RT, int KT)
 {
-    switch (KT) {
-    case 3: return launch_attn_t<RT, 3>(A, stream);
-    case 4: return launch_attn_t<RT, 4>(A, stream);
-    case 5: return launch_attn_t<RT, 5>(A, stream);
-    case 6: return launch_attn_t<RT, 6>(A, stream);
-    case 7: return launch_attn_t<RT, 7>(A, stream);
-    case 8: return launch_attn_t<RT, 8>(A, stream);
+    return RT * KT <= 98 && (size_t)(32 * KT * kEPitch + 32 * KT * 64 + kAWarps * RT * (32 * KT + 4)) * 4 <= kMaxSmem;
+}
+
+// rows per group: every warp gets ceil(groups / 8) groups, a group costs its RT rows of FMAs plus a fixed part (key loads,
+// query staging, softmax bookkeeping) of about three rows' worth — pick the RT with the smallest makespan that fits the
+// register tile and shared memory
+constexpr int attn_choose_rt(int n, int KT)
+{
+    int best = 5, best_cost = 1 << 30;
+    for (int rt = 5; rt <= kMaxRT; ++rt) {
+        if (!attn_fits(rt, KT)) continue;
+        const int groups = (n + rt - 1) / rt, rounds = (groups + kAWarps - 1) / kAWarps, cost = rounds * (rt + 3);
+        if (cost < best_cost) { best_cost = cost; best = rt; }
+    }
+    return best;
+}
+
+// only the (RT, KT) pairs some team size 65..256 actually selects are instantiated (15 kernels)
+constexpr bool attn_reachable(int RT, int KT)
+{
+    for (int n = 32 * (KT - 1) + 1; n <= 32 * KT; ++n)
+        if (n > 64 && attn_choose_rt(n, KT) == RT) return true;
+    return false;
+}
+
+template <int RT, int KT>
+static int launch_attn_rk(const AttnArgs &A, cudaStream_t stream)
+{
+    if constexpr (attn_fits(RT, KT) && attn_reachable(RT, KT)) return launch_attn_t<RT, KT>(A, stream);
+    else return CM_EUNSUPPORTED;
+}
+
+template <int KT>
+static int launch_attn_k(int RT, const AttnArgs &A, cudaStream_t stream)
+{
+    switch (RT) {
+    case 5: return launch_attn_rk<5, KT>(A, stream);
+    case 6: return launch_attn_rk<6, KT>(A, stream);
+    case 7: return launch_attn_rk<7, KT>(A, stream);
+    case 8: return launch_attn_rk<8, KT>(A, stream);
+    case 9: return launch_attn_rk<9, KT>(A, stream);
+    case 10: return launch_attn_rk<10, KT>(A, stream);
+    case 11: return launch_attn_rk<11, KT>(A, stream);
+    case 12: return launch_attn_rk<12, KT>(A, stream);
+    case 13: return launch_attn_rk<13, KT>(A, stream);
+    case 14: return launch_attn_rk<14, KT>(A, stream);
     }
     return CM_EUNSUPPORTED;
 }
@@ -287,13 +357,14 @@ int launch_policy_tc_large(const cm_policy_desc *desc, const cm_policy_io *io, c
     A.attention = io->attention;
     A.scr_e = scr_e; A.scr_q = scr_q; A.scr_hw = scr_hw;
     A.n_envs = io->n_envs;
-    // query rows per warp: the team is cut into ceil(n / 64) blocks of 8 * RT rows; keys per lane: ceil(n / 32)
-    const int nb = (n + 63) / 64, RT = (n + 8 * nb - 1) / (8 * nb), KT = (n + 31) / 32;
-    switch (RT) {
-    case 5: rc = launch_attn_r<5>(KT, A, stream); break;
-    case 6: rc = launch_attn_r<6>(KT, A, stream); break;
-    case 7: rc = launch_attn_r<7>(KT, A, stream); break;
-    case 8: rc = launch_attn_r<8>(KT, A, stream); break;
+    const int KT = (n + 31) / 32, RT = attn_choose_rt(n, KT);      // keys per lane, query rows per group
+    switch (KT) {
+    case 3: rc = launch_attn_k<3>(RT, A, stream); break;
+    case 4: rc = launch_attn_k<4>(RT, A, stream); break;
+    case 5: rc = launch_attn_k<5>(RT, A, stream); break;
+    case 6: rc = launch_attn_k<6>(RT, A, stream); break;
+    case 7: rc = launch_attn_k<7>(RT, A, stream); break;
+    case 8: rc = launch_attn_k<8>(RT, A, stream); break;
     default: rc = CM_EUNSUPPORTED;
     }
     if (rc) return rc;
