@@ -51,7 +51,39 @@ class DeviceTrainer:
         out.update(rollout_ms=ev[0].elapsed_time(ev[1]), batch_ms=ev[1].elapsed_time(ev[2]), update_ms=ev[2].elapsed_time(ev[3]),
                    agent_steps=self.engine.K * self.engine.B * self.spec.n_agents,
                    episode_stats=D.summarize_stats(stats, self.spec.scenario, self.spec.n_agents))
+        out["tabular"] = self.tabular(batch, out)
         return out
+
+    def tabular(self, batch, out):
+        """The per-epoch columns CentralizedMAPPO.train_once records in dowel's tabular (centralized_ma_ppo.py:345-372 ->
+        progress.csv), from the device batch of THIS rank and the whole-job episode statistics.  Episode-count columns
+        (SuccessRate, Average*Count) come from the kernels' episode accounting over every episode that finished during the
+        round; return columns from the padded batch like the reference (paths that finished inside the window).
+        KLBefore (KL against the policy of the previous round) and GPUMemoryMax are not reproduced."""
+        rewards, mask = batch["rewards"], batch["mask"]
+        und = (rewards * mask).sum(1)
+        es = out["episode_stats"]
+        row = dict(Iteration=self.epoch - 1, NumTrajs=int(rewards.shape[0]) * self.spec.n_agents,
+                   AverageDiscountedReturn=float(batch["returns"][:, 0].double().mean()), AverageReturn=float(und.mean()),
+                   SuccessRate=es["SuccessRate"], AverageCaptureCount=es["AverageCaptureCount"],
+                   AverageStepCount=es["AverageStepCount"], AverageMovingCount=es["AverageMovingCount"],
+                   AveragePenaltyCount=es["AveragePenaltyCount"], AverageVariable=es["AverageVariable"], AverageVar2=es["AverageVar2"],
+                   StdReturn=float(und.std(unbiased=False)), MaxReturn=float(und.max()), MinReturn=float(und.min()),
+                   LossBefore=out["loss_before"], LossAfter=out["loss_after"], dLoss=out["loss_before"] - out["loss_after"],
+                   KL=out["kl"], Entropy=out["entropy"], GradNorm=float(np.mean(out["grad_norms"])) if out["grad_norms"] else 0.0,
+                   EpochTime=out["update_ms"] * 1e-3)
+        # AveDegree: mean over paths of the per-path mean degree (:316-318); Diameter / AveTroughput are constants of the scenario
+        t = self.engine.traj
+        row["AveDegree"] = float(t["ave_deg"][:self.engine.K].double().mean()) if self.spec.rcom != 0 else float(self.spec.n_agents)
+        row["Diameter"] = float(self.spec.n_agents if self.spec.rcom == 0 else 0)
+        row["AveTroughput"] = float(self.spec.ave_trput)
+        try:
+            from dowel import tabular as dt
+            for k, v in row.items():
+                dt.record(k, v)
+        except Exception:                      # dowel is optional here
+            pass
+        return row
 
     def weights_checksum(self):
         """float64 sum of every policy + critic parameter: equal on all ranks when the gradient all-reduce works"""

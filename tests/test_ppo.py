@@ -182,3 +182,29 @@ def test_adam_step_kernel_matches_torch():
         N.check("cm_adam_step", N.lib().cm_adam_step(N.ptr(p), N.ptr(grad), N.ptr(m), N.ptr(v), n, 3e-4, 0.9, 0.999, 1e-5, step, 0.5,
                                                      N.stream_ptr()))
         assert (p - ref.detach()).abs().max().item() <= 1e-6
+
+
+@pytest.mark.gpu
+def test_trainer_round_and_tabular_columns():
+    """DeviceTrainer.train_epoch: rollout of one horizon + update; the tabular row carries the reference's progress.csv
+    columns (centralized_ma_ppo.py:345-372) and its return columns agree with the kernels' episode accounting."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import ref_harness
+    from com_marl_b200.scenario import ScenarioSpec
+    from com_marl_b200.train import DeviceTrainer
+    params = ref_harness.scenario_params("co", 10, 1, 0.03, cap=2, loss=0.0, max_env_steps=20)
+    spec = ScenarioSpec.from_params("co", params, seed=2)
+    tr = DeviceTrainer(spec, 64, optimization_mini_epochs=1)
+    out = tr.train_epoch()
+    row = out["tabular"]
+    for k in ("Iteration", "NumTrajs", "AverageDiscountedReturn", "AverageReturn", "SuccessRate", "AverageCaptureCount",
+              "AverageStepCount", "AverageMovingCount", "AveragePenaltyCount", "AverageVariable", "AverageVar2", "StdReturn",
+              "MaxReturn", "MinReturn", "LossBefore", "LossAfter", "dLoss", "KL", "Entropy", "GradNorm", "EpochTime", "AveDegree",
+              "Diameter", "AveTroughput"):
+        assert k in row and np.isfinite(row[k]), k
+    # every env runs exactly one 20-step episode per round (Coverage cannot finish 86 cells in 20 steps): the batch's
+    # mean return is the kernels' AverageReturn
+    assert row["NumTrajs"] == 64 * spec.n_agents and out["episode_stats"]["NumEpisodes"] == 64
+    assert abs(row["AverageReturn"] - out["episode_stats"]["AverageReturn"]) <= 1e-9 * max(1.0, abs(row["AverageReturn"]))
+    assert row["MinReturn"] <= row["AverageReturn"] <= row["MaxReturn"]
