@@ -333,6 +333,8 @@ static int launch_attn_k(int RT, const AttnArgs &A, cudaStream_t stream)
 }
 
 int launch_policy_tc_encode(const cm_policy_desc *desc, const cm_policy_io *io, float *scr_e, float *scr_q, float *scr_hw, cudaStream_t stream);
+int launch_policy_attn_mma(const cm_policy_desc *desc, const cm_policy_io *io, const float *scr_e, float *scr_q, float *scr_hw,
+                           cudaStream_t stream);                                                // policy_attn_mma_kernel.cu
 int launch_policy_tc_head(const cm_policy_desc *desc, const cm_policy_io *io, const float *x_rows, cudaStream_t stream);
 
 size_t tc_large_ws_floats(int n, int64_t n_envs) { return (size_t)3 * (size_t)n_envs * (size_t)n * kE; }
@@ -349,6 +351,12 @@ int launch_policy_tc_large(const cm_policy_desc *desc, const cm_policy_io *io, c
     float *scr_e = io->workspace, *scr_q = scr_e + rows * kE, *scr_hw = scr_q + rows * kE;
     int rc = launch_policy_tc_encode(desc, io, scr_e, scr_q, scr_hw, stream);
     if (rc) return rc;
+    if (desc->math == 1) {                 // attention on the warp-level tensor path (default); math == 2: exact fp32 below
+        rc = launch_policy_attn_mma(desc, io, scr_e, scr_q, scr_hw, stream);
+        if (rc) return rc;
+        if (!io->probs && !io->actions && !io->logits) return CM_OK;
+        return launch_policy_tc_head(desc, io, scr_q, stream);
+    }
     AttnArgs A;
     A.d = *desc;
     A.weights = io->weights;

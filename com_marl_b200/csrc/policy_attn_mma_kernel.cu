@@ -1,0 +1,370 @@
+// policy_attn_mma_kernel.cu — attention + graph convolutions for large teams (64 < n <= 256) on the warp-level tensor
+// path (mma.sync.m16n8k16, SASS HMMA): same stage of the large-team pipeline and same interface as policy_attn_kernel.cu
+// (which stays as the exact-fp32 cross-check, cm_policy_desc.math = 2).
+//
+// Why mma.sync here and not tcgen05: the unit of work is a 16-row x n-key strip of ONE environment whose softmax, masking
+// and re-normalisation sit between the two products; with mma.sync the strip never leaves the warp's registers — the score
+// accumulators ARE the A operand of the aggregation (the C fragment of two adjacent 8-key tiles is exactly the A fragment of
+// a 16-key slice) — and there is no CTA-wide barrier, TMEM hand-over or shared-memory round trip per strip.  Measured issue
+// rate on B200 (tests/native/mma_sync_probe.cu): one m16n8k16 per 8 cycles per SM sub-partition = 1019 MAC/clk/SM, against
+// ~43 MAC/clk/SM the FFMA kernel reaches.
+//
+// fp32-level accuracy comes from the same error compensation as the tcgen05 kernel: x = hi + lo, hi = fp16(x),
+// lo = fp16(x - hi); a product is hi*hi + hi*lo + lo*hi accumulated in fp32 in ONE accumulator (the dropped lo*lo term is
+// 2^-22 relative).  lo is NOT rescaled: below 6e-5 it is an fp16 subnormal with an absolute step of 6e-8, i.e. an absolute
+// error <= 3e-8 per operand of magnitude <= 1 — two orders of magnitude below the 1e-5 tolerance.
+//
+// One CTA of 8 warps per env.  Shared memory: keys E as fp16 hi / lo [key][64] (B operand of the scores), values H_l Wg_l
+// TRANSPOSED as fp16 hi / lo [col][key] (B operand of the aggregation), Wg_{l+1} transposed hi / lo (B operand of the next
+// layer's H Wg product), and a private slice per warp (its 16 query rows in fp32, its rows' neighbour mask words).
+// Strips of 16 query rows are dealt round-robin to the warps; per strip: scores (4 k-slices x NT key tiles x 3 HMMA),
+// softmax / mask / masked sum in the C fragments (quad shuffles), aggregation (NK/16 key slices x 8 column tiles x 3 HMMA),
+// / (sum + 1e-12) + bias, tanh, then H Wg_{l+1} (4 x 8 x 3 HMMA) -> fp32 rows for the next layer, or X = E + H_L.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "commarl_b200.h"
+#include "common.cuh"
+#include "policy_layout.cuh"
+
+namespace cm {
+
+static constexpr int kMThreads = 256, kMWarps = 8;
+static constexpr int kEhPitch = 72;          // halves per key row of E hi / lo (144 B: 8 rows x 4 lanes hit 32 distinct banks)
+static constexpr int kQPitch = 72;           // floats per query row of a warp's slice
+static constexpr int kWgPitch = 72;          // halves per output column of the transposed Wg
+
+struct AttnMmaArgs {
+    cm_policy_desc d;
+    const float *weights;
+    const uint32_t *adj_bits, *chan_bits;
+    float *attention;
+    const float *scr_e;
+    float *scr_q;
+    float *scr_hw;
+    int64_t n_envs;
+};
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// (x, y) -> packed fp16 hi pair and lo pair: hi = fp16(v), lo = fp16(v - hi)
+__device__ __forceinline__ void split2(float x, float y, uint32_t &hi, uint32_t &lo)
+{
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+__device__ __forceinline__ float quad_max(float v)
+{
+    v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v)
+{
+    v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+    return v + __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+}
+
+// NS = number of 16-key slices (NK = 16 NS keys >= n)
+template <int NS>
+__global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const AttnMmaArgs A)
+{
+    constexpr int NK = 16 * NS, NT = 2 * NS, HWP = NK + 8;     // keys, 8-key tiles, halves per row of the transposed values
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __half *Eh = reinterpret_cast<__half *>(smraw);            // [NK][72]
+    __half *El = Eh + NK * kEhPitch;
+    __half *Vh = El + NK * kEhPitch;                           // [64][HWP]   (H_l Wg_l)^T hi
+    __half *Vl = Vh + 64 * HWP;
+    __half *Wh = Vl + 64 * HWP;                                // [64][72]    Wg_{l+1}^T hi
+    __half *Wl = Wh + 64 * kWgPitch;
+    float *Qs = reinterpret_cast<float *>(Wl + 64 * kWgPitch); // [8 warps][16][72] query rows
+    uint32_t *Ms = reinterpret_cast<uint32_t *>(Qs + kMWarps * 16 * kQPitch);   // [8 warps][16][8] mask words
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    float *Qw = Qs + warp * 16 * kQPitch;
+    uint32_t *Mw = Ms + warp * 16 * 8;
+    const int n = A.d.n_agents, L = A.d.n_layers, W = (n + 31) >> 5;
+    const Blob o = blob_layout(A.d.obs_dim, L);
+    const int n_strips = (n + 15) >> 4;
+
+    for (int64_t env = blockIdx.x; env < A.n_envs; env += gridDim.x) {
+        const size_t r_env = (size_t)env * n;
+        __syncthreads();                                       // the previous env's operands are dead
+        // ---- keys: E rows -> fp16 hi / lo ----
+        for (int e = tid; e < NK * 16; e += kMThreads) {
+            const int j = e >> 4, c = (e & 15) << 2;
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (j < n) v = __ldcg(reinterpret_cast<const float4 *>(A.scr_e + (r_env + j) * 64 + c));
+            uint32_t h0, l0, h1, l1;
+            split2(v.x, v.y, h0, l0);
+            split2(v.z, v.w, h1, l1);
+            *reinterpret_cast<uint2 *>(Eh + j * kEhPitch + c) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2 *>(El + j * kEhPitch + c) = make_uint2(l0, l1);
+        }
+        for (int l = 0; l < L; ++l) {
+            if (l) __syncthreads();                            // every warp wrote its H_l Wg_l rows and is done with the old operands
+            // ---- values: H_l Wg_l rows -> transposed fp16 hi / lo [col][key] ----
+            for (int e = tid; e < NK * 16; e += kMThreads) {
+                const int j = e % NK, c = (e / NK) << 2;       // consecutive threads take consecutive keys: neighbouring halves
+                float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (j < n) v = __ldcg(reinterpret_cast<const float4 *>(A.scr_hw + (r_env + j) * 64 + c));
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const __half h = __float2half_rn(vv[q]);
+                    Vh[(c + q) * HWP + j] = h;
+                    Vl[(c + q) * HWP + j] = __float2half_rn(vv[q] - __half2float(h));
+                }
+            }
+            // ---- Wg_{l+1} (k-major [k][c] in the blob) -> transposed fp16 hi / lo [c][k] ----
+            if (l + 1 < L) {
+                const float *wg = A.weights + o.gcn_w + (size_t)(l + 1) * kE * kE;
+                for (int e = tid; e < kE * kE; e += kMThreads) {
+                    const int k = e >> 6, c = e & 63;
+                    const float v = __ldg(wg + e);
+                    const __half h = __float2half_rn(v);
+                    Wh[c * kWgPitch + k] = h;
+                    Wl[c * kWgPitch + k] = __float2half_rn(v - __half2float(h));
+                }
+            }
+            __syncthreads();
+            const float *bias = A.weights + o.gcn_b + l * kE;
+            for (int strip = warp; strip < n_strips; strip += kMWarps) {
+                const int i0 = strip << 4;                     // first query row of the strip; this lane owns rows i0+g, i0+g+8
+                __syncwarp();
+                // ---- query rows and neighbour mask words -> the warp's slice ----
+                for (int e = lane; e < 16 * 16; e += 32) {
+                    const int r = e >> 4, c = (e & 15) << 2;
+                    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (i0 + r < n) v = __ldcg(reinterpret_cast<const float4 *>(A.scr_q + (r_env + i0 + r) * 64 + c));
+                    *reinterpret_cast<float4 *>(Qw + r * kQPitch + c) = v;
+                }
+                for (int e = lane; e < 16 * 8; e += 32) {
+                    const int r = e >> 3, w = e & 7;
+                    uint32_t m = 0u;
+                    if (i0 + r < n && w < W) {
+                        m = 0xFFFFFFFFu;
+                        if (A.adj_bits) m &= __ldg(A.adj_bits + (r_env + i0 + r) * W + w);
+                        if (A.chan_bits) m &= __ldg(A.chan_bits + (((size_t)env * L + l) * n + i0 + r) * W + w);
+                    }
+                    Mw[e] = m;
+                }
+                __syncwarp();
+                // ---- scores: S[16][NK] = Q E^T, three fp16 products per tile into one fp32 accumulator ----
+                float s[NT][4];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const int k0 = 16 * ks + 2 * t;
+                    const float2 q00 = *reinterpret_cast<const float2 *>(Qw + g * kQPitch + k0);
+                    const float2 q10 = *reinterpret_cast<const float2 *>(Qw + (g + 8) * kQPitch + k0);
+                    const float2 q01 = *reinterpret_cast<const float2 *>(Qw + g * kQPitch + k0 + 8);
+                    const float2 q11 = *reinterpret_cast<const float2 *>(Qw + (g + 8) * kQPitch + k0 + 8);
+                    uint32_t ah[4], al[4];
+                    split2(q00.x, q00.y, ah[0], al[0]);
+                    split2(q10.x, q10.y, ah[1], al[1]);
+                    split2(q01.x, q01.y, ah[2], al[2]);
+                    split2(q11.x, q11.y, ah[3], al[3]);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const __half *eh = Eh + (8 * nt + g) * kEhPitch + k0, *el = El + (8 * nt + g) * kEhPitch + k0;
+                        const uint32_t bh0 = *reinterpret_cast<const uint32_t *>(eh), bh1 = *reinterpret_cast<const uint32_t *>(eh + 8);
+                        const uint32_t bl0 = *reinterpret_cast<const uint32_t *>(el), bl1 = *reinterpret_cast<const uint32_t *>(el + 8);
+                        mma16816(s[nt], ah, bh0, bh1);
+                        mma16816(s[nt], ah, bl0, bl1);
+                        mma16816(s[nt], al, bh0, bh1);
+                    }
+                }
+                // ---- softmax over the keys (attention_module.py:44-49): rows g (c0, c1) and g + 8 (c2, c3) of every tile ----
+                float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int key = 8 * nt + 2 * t;
+                    if (key < n) { mx0 = fmaxf(mx0, s[nt][0]); mx1 = fmaxf(mx1, s[nt][2]); }
+                    if (key + 1 < n) { mx0 = fmaxf(mx0, s[nt][1]); mx1 = fmaxf(mx1, s[nt][3]); }
+                }
+                mx0 = quad_max(mx0);
+                mx1 = quad_max(mx1);
+                float sum0 = 0.0f, sum1 = 0.0f;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int key = 8 * nt + 2 * t;
+                    s[nt][0] = key < n ? __expf(s[nt][0] - mx0) : 0.0f;
+                    s[nt][1] = key + 1 < n ? __expf(s[nt][1] - mx0) : 0.0f;
+                    s[nt][2] = key < n ? __expf(s[nt][2] - mx1) : 0.0f;
+                    s[nt][3] = key + 1 < n ? __expf(s[nt][3] - mx1) : 0.0f;
+                    sum0 += s[nt][0] + s[nt][1];
+                    sum1 += s[nt][2] + s[nt][3];
+                }
+                sum0 = quad_sum(sum0);
+                sum1 = quad_sum(sum1);
+                // ---- mask, masked sums (comm_base_net.py:101-103); the un-normalised masked rows stay in the accumulators ----
+                const bool v0 = i0 + g < n, v1 = i0 + g + 8 < n;
+                float den0 = 0.0f, den1 = 0.0f;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int key = 8 * nt + 2 * t;
+                    const float p00 = s[nt][0] / sum0, p01 = s[nt][1] / sum0, p10 = s[nt][2] / sum1, p11 = s[nt][3] / sum1;
+                    if (l == 0 && A.attention) {               // the UNMASKED softmax (comm_base_net.py:93)
+                        if (v0 && key < n) A.attention[(r_env + i0 + g) * n + key] = p00;
+                        if (v0 && key + 1 < n) A.attention[(r_env + i0 + g) * n + key + 1] = p01;
+                        if (v1 && key < n) A.attention[(r_env + i0 + g + 8) * n + key] = p10;
+                        if (v1 && key + 1 < n) A.attention[(r_env + i0 + g + 8) * n + key + 1] = p11;
+                    }
+                    const uint32_t w0 = Mw[g * 8 + (nt >> 2)] >> (8 * (nt & 3) + 2 * t);
+                    const uint32_t w1 = Mw[(g + 8) * 8 + (nt >> 2)] >> (8 * (nt & 3) + 2 * t);
+                    s[nt][0] = (w0 & 1u) ? p00 : 0.0f;
+                    s[nt][1] = (w0 & 2u) ? p01 : 0.0f;
+                    s[nt][2] = (w1 & 1u) ? p10 : 0.0f;
+                    s[nt][3] = (w1 & 2u) ? p11 : 0.0f;
+                    den0 += s[nt][0] + s[nt][1];
+                    den1 += s[nt][2] + s[nt][3];
+                }
+                den0 = quad_sum(den0) + 1e-12f;
+                den1 = quad_sum(den1) + 1e-12f;
+                // ---- aggregation: out[16][64] = A (H_l Wg_l): the C fragments of tiles 2s, 2s+1 are the A fragment of key slice s ----
+                float oacc[8][4];
+#pragma unroll
+                for (int ot = 0; ot < 8; ++ot) oacc[ot][0] = oacc[ot][1] = oacc[ot][2] = oacc[ot][3] = 0.0f;
+#pragma unroll
+                for (int ss = 0; ss < NS; ++ss) {
+                    uint32_t ah[4], al[4];
+                    split2(s[2 * ss][0], s[2 * ss][1], ah[0], al[0]);
+                    split2(s[2 * ss][2], s[2 * ss][3], ah[1], al[1]);
+                    split2(s[2 * ss + 1][0], s[2 * ss + 1][1], ah[2], al[2]);
+                    split2(s[2 * ss + 1][2], s[2 * ss + 1][3], ah[3], al[3]);
+                    const int k0 = 16 * ss + 2 * t;
+#pragma unroll
+                    for (int ot = 0; ot < 8; ++ot) {
+                        const __half *vh = Vh + (8 * ot + g) * HWP + k0, *vl = Vl + (8 * ot + g) * HWP + k0;
+                        const uint32_t bh0 = *reinterpret_cast<const uint32_t *>(vh), bh1 = *reinterpret_cast<const uint32_t *>(vh + 8);
+                        const uint32_t bl0 = *reinterpret_cast<const uint32_t *>(vl), bl1 = *reinterpret_cast<const uint32_t *>(vl + 8);
+                        mma16816(oacc[ot], ah, bh0, bh1);
+                        mma16816(oacc[ot], ah, bl0, bl1);
+                        mma16816(oacc[ot], al, bh0, bh1);
+                    }
+                }
+                // ---- H_{l+1} = tanh(out / (sum + 1e-12) + b): rows g / g + 8, columns 8 ot + 2t, + 1 ----
+#pragma unroll
+                for (int ot = 0; ot < 8; ++ot) {
+                    const float2 b2 = __ldg(reinterpret_cast<const float2 *>(bias + 8 * ot + 2 * t));
+                    oacc[ot][0] = tanhf(oacc[ot][0] / den0 + b2.x);
+                    oacc[ot][1] = tanhf(oacc[ot][1] / den0 + b2.y);
+                    oacc[ot][2] = tanhf(oacc[ot][2] / den1 + b2.x);
+                    oacc[ot][3] = tanhf(oacc[ot][3] / den1 + b2.y);
+                }
+                if (l + 1 < L) {
+                    // ---- next layer's value rows: H_{l+1} Wg_{l+1}, the H fragments again being the A operand ----
+                    float hacc[8][4];
+#pragma unroll
+                    for (int ot = 0; ot < 8; ++ot) hacc[ot][0] = hacc[ot][1] = hacc[ot][2] = hacc[ot][3] = 0.0f;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        uint32_t ah[4], al[4];
+                        split2(oacc[2 * ks][0], oacc[2 * ks][1], ah[0], al[0]);
+                        split2(oacc[2 * ks][2], oacc[2 * ks][3], ah[1], al[1]);
+                        split2(oacc[2 * ks + 1][0], oacc[2 * ks + 1][1], ah[2], al[2]);
+                        split2(oacc[2 * ks + 1][2], oacc[2 * ks + 1][3], ah[3], al[3]);
+                        const int k0 = 16 * ks + 2 * t;
+#pragma unroll
+                        for (int ot = 0; ot < 8; ++ot) {
+                            const __half *wh = Wh + (8 * ot + g) * kWgPitch + k0, *wl = Wl + (8 * ot + g) * kWgPitch + k0;
+                            const uint32_t bh0 = *reinterpret_cast<const uint32_t *>(wh), bh1 = *reinterpret_cast<const uint32_t *>(wh + 8);
+                            const uint32_t bl0 = *reinterpret_cast<const uint32_t *>(wl), bl1 = *reinterpret_cast<const uint32_t *>(wl + 8);
+                            mma16816(hacc[ot], ah, bh0, bh1);
+                            mma16816(hacc[ot], ah, bl0, bl1);
+                            mma16816(hacc[ot], al, bh0, bh1);
+                        }
+                    }
+#pragma unroll
+                    for (int ot = 0; ot < 8; ++ot) {
+                        if (v0) *reinterpret_cast<float2 *>(A.scr_hw + (r_env + i0 + g) * 64 + 8 * ot + 2 * t) = make_float2(hacc[ot][0], hacc[ot][1]);
+                        if (v1) *reinterpret_cast<float2 *>(A.scr_hw + (r_env + i0 + g + 8) * 64 + 8 * ot + 2 * t) = make_float2(hacc[ot][2], hacc[ot][3]);
+                    }
+                } else {
+                    // ---- X = E + H_L (comm_base_net.py:105-106), written over the strip's query rows ----
+#pragma unroll
+                    for (int ot = 0; ot < 8; ++ot) {
+                        const int c = 8 * ot + 2 * t;
+                        if (v0) {
+                            float2 x = make_float2(oacc[ot][0], oacc[ot][1]);
+                            if (A.d.residual) { const float2 ev = __ldcg(reinterpret_cast<const float2 *>(A.scr_e + (r_env + i0 + g) * 64 + c)); x.x += ev.x; x.y += ev.y; }
+                            *reinterpret_cast<float2 *>(A.scr_q + (r_env + i0 + g) * 64 + c) = x;
+                        }
+                        if (v1) {
+                            float2 x = make_float2(oacc[ot][2], oacc[ot][3]);
+                            if (A.d.residual) { const float2 ev = __ldcg(reinterpret_cast<const float2 *>(A.scr_e + (r_env + i0 + g + 8) * 64 + c)); x.x += ev.x; x.y += ev.y; }
+                            *reinterpret_cast<float2 *>(A.scr_q + (r_env + i0 + g + 8) * 64 + c) = x;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int NS>
+static int launch_attn_mma_t(const AttnMmaArgs &A, cudaStream_t stream)
+{
+    constexpr int NK = 16 * NS;
+    constexpr size_t smem = (size_t)(2 * NK * kEhPitch + 2 * 64 * (NK + 8) + 2 * 64 * kWgPitch) * sizeof(__half) +
+                            (size_t)kMWarps * 16 * kQPitch * sizeof(float) + (size_t)kMWarps * 16 * 8 * sizeof(uint32_t);
+    static thread_local struct { int dev; int slots; } cache = {-1, 0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ENODEVICE);
+    if (cache.dev != dev) {
+        int sms = 0, ctas = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ECUDA);
+        cudaError_t e = cudaFuncSetAttribute(policy_attn_mma_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, policy_attn_mma_kernel<NS>, kMThreads, smem) != cudaSuccess)
+            return set_cuda_error(cudaGetLastError(), CM_ECUDA);
+        cache.dev = dev;
+        cache.slots = sms * (ctas < 1 ? 1 : ctas);
+    }
+    const int grid = (int)(A.n_envs < cache.slots ? A.n_envs : cache.slots);
+    policy_attn_mma_kernel<NS><<<grid, kMThreads, smem, stream>>>(A);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? CM_OK : set_cuda_error(e, CM_ECUDA);
+}
+
+int launch_policy_attn_mma(const cm_policy_desc *desc, const cm_policy_io *io, const float *scr_e, float *scr_q, float *scr_hw,
+                           cudaStream_t stream)
+{
+    AttnMmaArgs A;
+    A.d = *desc;
+    A.weights = io->weights;
+    A.adj_bits = io->adj_bits;
+    A.chan_bits = io->chan_bits;
+    A.attention = io->attention;
+    A.scr_e = scr_e; A.scr_q = scr_q; A.scr_hw = scr_hw;
+    A.n_envs = io->n_envs;
+    switch ((desc->n_agents + 15) / 16) {
+    case 5: return launch_attn_mma_t<5>(A, stream);
+    case 6: return launch_attn_mma_t<6>(A, stream);
+    case 7: return launch_attn_mma_t<7>(A, stream);
+    case 8: return launch_attn_mma_t<8>(A, stream);
+    case 9: return launch_attn_mma_t<9>(A, stream);
+    case 10: return launch_attn_mma_t<10>(A, stream);
+    case 11: return launch_attn_mma_t<11>(A, stream);
+    case 12: return launch_attn_mma_t<12>(A, stream);
+    case 13: return launch_attn_mma_t<13>(A, stream);
+    case 14: return launch_attn_mma_t<14>(A, stream);
+    case 15: return launch_attn_mma_t<15>(A, stream);
+    case 16: return launch_attn_mma_t<16>(A, stream);
+    }
+    return CM_EUNSUPPORTED;
+}
+
+}  // namespace cm

@@ -615,7 +615,7 @@ extern "C" int cm_policy_forward(const cm_policy_desc *desc, const cm_policy_io 
     if (io->n_envs < 0) return CM_EINVAL;
     if (io->n_envs == 0) return CM_OK;
     if (desc->kind != CM_POLICY_COMM && desc->kind != CM_POLICY_DEC) return CM_EINVAL;
-    if (desc->math == 1) return launch_policy_tc(desc, io, (cudaStream_t)stream);
+    if (desc->math == 1 || desc->math == 2) return launch_policy_tc(desc, io, (cudaStream_t)stream);
     if (desc->kind == CM_POLICY_DEC) return CM_EUNSUPPORTED;       // Obs-DP runs on the tensor-core kernel only
     if (desc->math != 0) return CM_EINVAL;
     PolicyArgs A;

@@ -108,8 +108,8 @@ class CommCategoricalMLPPolicy(nn.Module):
         # kernel variant: 'fp32' = exact FFMA kernels; 'tc' = tcgen05 tensor cores, error-compensated fp16 products with
         # fp32 accumulation (fp32-level accuracy; teams of n > 64 run encoder / head on the tensor cores and the n x n
         # attention in exact fp32 between them); 'auto' = 'tc'
-        if math not in ("auto", "fp32", "tc"):
-            raise ValueError("math must be 'auto', 'fp32' or 'tc'")
+        if math not in ("auto", "fp32", "tc", "tc_fp32attn"):
+            raise ValueError("math must be 'auto', 'fp32', 'tc' or 'tc_fp32attn'")
         self.math = math
         self.encoder = _MLP(self._dec_obs_dim, encoder_hidden_sizes, embedding_dim, output_tanh=True)
         self.attention_layer = _Attention(embedding_dim)
@@ -153,7 +153,7 @@ class CommCategoricalMLPPolicy(nn.Module):
         return self._blob
 
     def uses_tensor_cores(self):
-        return self.math in ("tc", "auto")
+        return self.math in ("tc", "auto", "tc_fp32attn")
 
     def tc_weight_blob(self):
         """pre-split (hi | lo), pre-laid-out B operands of the tcgen05 variant; rebuilt when a parameter changed"""
@@ -191,7 +191,8 @@ class CommCategoricalMLPPolicy(nn.Module):
         n, D, L = self._n_agents, self._dec_obs_dim, self.n_gcn_layers
         B = obs.shape[0]
         tc = self.uses_tensor_cores()
-        desc = N.PolicyDesc(n, D, L, int(self.residual), int(greedy), int(tc), self.seed, env_id0, self._kind)
+        desc = N.PolicyDesc(n, D, L, int(self.residual), int(greedy), (2 if self.math == "tc_fp32attn" else 1) if tc else 0,
+                            self.seed, env_id0, self._kind)
         io = N.PolicyIO()
         io.n_envs = B
         if tc:

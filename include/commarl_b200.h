@@ -149,9 +149,11 @@ typedef struct cm_policy_desc {
     int32_t n_layers;          /* L */
     int32_t residual;          /* comm_categorical_mlp_policy.py:74-77 */
     int32_t greedy;            /* argmax instead of sampling (:109-112) */
-    int32_t math;              /* 0: exact fp32 FFMA kernels; 1: tcgen05 tensor cores, error-compensated fp16 products
-                                  (x = x_hi + 2^-12 x_lo) with fp32 accumulation in tensor memory: fp32-level accuracy,
-                                  teams with n <= 64; needs io.tc_weights */
+    int32_t math;              /* 0: exact fp32 FFMA kernels; 1: tensor cores, error-compensated fp16 products (x = hi + lo)
+                                  with fp32 accumulation: fp32-level accuracy; needs io.tc_weights.  Teams with n <= 64: one
+                                  fused tcgen05 kernel; larger teams: tcgen05 encoder -> attention / graph convolutions on
+                                  mma.sync -> tcgen05 head, rows handed over through io.workspace.  2: like 1 with the large-team
+                                  attention in exact fp32 on the CUDA cores (cross-check) */
     uint64_t seed;
     int64_t env_id0;
     int32_t kind;              /* cm_policy_kind: 0 = Comm-DP (CommCategoricalMLPPolicy), 1 = Obs-DP (DecCategoricalMLPPolicy:

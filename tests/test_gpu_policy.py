@@ -56,7 +56,7 @@ def test_policy_kernel_matches_reference_golden(name, math):
     assert np.abs(d2.probs.cpu().numpy() - c.probs).max() <= 1e-5
 
 
-@pytest.mark.parametrize("math", ["fp32", "tc"])
+@pytest.mark.parametrize("math", ["fp32", "tc", "tc_fp32attn"])
 @pytest.mark.parametrize("n,D,B,ploss", [(3, 29, 16384, 0.0), (4, 21, 5000, 0.3), (32, 53, 2048, 0.2), (54, 77, 777, 0.1),
                                          (7, 53, 1001, 0.5), (64, 29, 64, 0.4), (1, 21, 100, 0.0),
                                          (65, 21, 70, 0.2), (72, 53, 301, 0.3), (200, 53, 97, 0.2), (256, 29, 9, 0.5),
@@ -64,6 +64,8 @@ def test_policy_kernel_matches_reference_golden(name, math):
 def test_policy_kernel_matches_oracle_batched(n, D, B, ploss, math):
     """Random binary observations + random masks on big ragged batches (last tile partial) vs the numpy
     restatement; sampling reproduces the inverse-CDF stream specification exactly."""
+    if math == "tc_fp32attn" and n <= 64:
+        pytest.skip("differs from 'tc' for teams of more than 64 agents only")
     rng = np.random.default_rng(n * 1000 + D)
     pol = _policy(n, D, 2, seed=n, math=math)
     with torch.no_grad():
