@@ -64,6 +64,16 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t &hi, uint32_t 
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
+// tanh(x) = 1 - 2 / (2^(2 log2(e) x) + 1) through ex2.approx / rcp.approx (|error| ~3e-7, saturates correctly); the same
+// formulation as the tcgen05 kernel's epilogues
+__device__ __forceinline__ float tanh_fast(float x)
+{
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+
 __device__ __forceinline__ float quad_max(float v)
 {
     v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, 1));
@@ -101,6 +111,7 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
         const size_t r_env = (size_t)env * n;
         __syncthreads();                                       // the previous env's operands are dead
         // ---- keys: E rows -> fp16 hi / lo ----
+#pragma unroll 4
         for (int e = tid; e < NK * 16; e += kMThreads) {
             const int j = e >> 4, c = (e & 15) << 2;
             float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -114,6 +125,7 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
         for (int l = 0; l < L; ++l) {
             if (l) __syncthreads();                            // every warp wrote its H_l Wg_l rows and is done with the old operands
             // ---- values: H_l Wg_l rows -> transposed fp16 hi / lo [col][key] ----
+#pragma unroll 4
             for (int e = tid; e < NK * 16; e += kMThreads) {
                 const int j = e % NK, c = (e / NK) << 2;       // consecutive threads take consecutive keys: neighbouring halves
                 float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -129,6 +141,7 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
             // ---- Wg_{l+1} (k-major [k][c] in the blob) -> transposed fp16 hi / lo [c][k] ----
             if (l + 1 < L) {
                 const float *wg = A.weights + o.gcn_w + (size_t)(l + 1) * kE * kE;
+#pragma unroll 4
                 for (int e = tid; e < kE * kE; e += kMThreads) {
                     const int k = e >> 6, c = e & 63;
                     const float v = __ldg(wg + e);
@@ -164,8 +177,8 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
                 float s[NT][4];
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll 1
+                for (int ks = 0; ks < 4; ++ks) {                    // (rolled: the body alone is 3 NT HMMAs; the kernel is I-cache bound otherwise)
                     const int k0 = 16 * ks + 2 * t;
                     const float2 q00 = *reinterpret_cast<const float2 *>(Qw + g * kQPitch + k0);
                     const float2 q10 = *reinterpret_cast<const float2 *>(Qw + (g + 8) * kQPitch + k0);
@@ -176,14 +189,24 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
                     split2(q10.x, q10.y, ah[1], al[1]);
                     split2(q01.x, q01.y, ah[2], al[2]);
                     split2(q11.x, q11.y, ah[3], al[3]);
+                    // four key tiles at a time: the three products of a tile go into ONE accumulator, so they are issued
+                    // four tiles apart (an HMMA needs its accumulator back before the next one on it can start)
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-                        const __half *eh = Eh + (8 * nt + g) * kEhPitch + k0, *el = El + (8 * nt + g) * kEhPitch + k0;
-                        const uint32_t bh0 = *reinterpret_cast<const uint32_t *>(eh), bh1 = *reinterpret_cast<const uint32_t *>(eh + 8);
-                        const uint32_t bl0 = *reinterpret_cast<const uint32_t *>(el), bl1 = *reinterpret_cast<const uint32_t *>(el + 8);
-                        mma16816(s[nt], ah, bh0, bh1);
-                        mma16816(s[nt], ah, bl0, bl1);
-                        mma16816(s[nt], al, bh0, bh1);
+                    for (int n0 = 0; n0 < NT; n0 += 4) {
+                        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (n0 + u < NT) {
+                                const __half *eh = Eh + (8 * (n0 + u) + g) * kEhPitch + k0, *el = El + (8 * (n0 + u) + g) * kEhPitch + k0;
+                                bh[u][0] = *reinterpret_cast<const uint32_t *>(eh); bh[u][1] = *reinterpret_cast<const uint32_t *>(eh + 8);
+                                bl[u][0] = *reinterpret_cast<const uint32_t *>(el); bl[u][1] = *reinterpret_cast<const uint32_t *>(el + 8);
+                            }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) if (n0 + u < NT) mma16816(s[n0 + u], ah, bh[u][0], bh[u][1]);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) if (n0 + u < NT) mma16816(s[n0 + u], ah, bl[u][0], bl[u][1]);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) if (n0 + u < NT) mma16816(s[n0 + u], al, bh[u][0], bh[u][1]);
                     }
                 }
                 // ---- softmax over the keys (attention_module.py:44-49): rows g (c0, c1) and g + 8 (c2, c3) of every tile ----
@@ -211,11 +234,12 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
                 sum1 = quad_sum(sum1);
                 // ---- mask, masked sums (comm_base_net.py:101-103); the un-normalised masked rows stay in the accumulators ----
                 const bool v0 = i0 + g < n, v1 = i0 + g + 8 < n;
+                const float is0 = 1.0f / sum0, is1 = 1.0f / sum1;
                 float den0 = 0.0f, den1 = 0.0f;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const int key = 8 * nt + 2 * t;
-                    const float p00 = s[nt][0] / sum0, p01 = s[nt][1] / sum0, p10 = s[nt][2] / sum1, p11 = s[nt][3] / sum1;
+                    const float p00 = s[nt][0] * is0, p01 = s[nt][1] * is0, p10 = s[nt][2] * is1, p11 = s[nt][3] * is1;
                     if (l == 0 && A.attention) {               // the UNMASKED softmax (comm_base_net.py:93)
                         if (v0 && key < n) A.attention[(r_env + i0 + g) * n + key] = p00;
                         if (v0 && key + 1 < n) A.attention[(r_env + i0 + g) * n + key + 1] = p01;
@@ -231,8 +255,8 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
                     den0 += s[nt][0] + s[nt][1];
                     den1 += s[nt][2] + s[nt][3];
                 }
-                den0 = quad_sum(den0) + 1e-12f;
-                den1 = quad_sum(den1) + 1e-12f;
+                den0 = 1.0f / (quad_sum(den0) + 1e-12f);       // (reciprocals: one division per row instead of one per element)
+                den1 = 1.0f / (quad_sum(den1) + 1e-12f);
                 // ---- aggregation: out[16][64] = A (H_l Wg_l): the C fragments of tiles 2s, 2s+1 are the A fragment of key slice s ----
                 float oacc[8][4];
 #pragma unroll
@@ -246,23 +270,30 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
                     split2(s[2 * ss + 1][2], s[2 * ss + 1][3], ah[3], al[3]);
                     const int k0 = 16 * ss + 2 * t;
 #pragma unroll
-                    for (int ot = 0; ot < 8; ++ot) {
-                        const __half *vh = Vh + (8 * ot + g) * HWP + k0, *vl = Vl + (8 * ot + g) * HWP + k0;
-                        const uint32_t bh0 = *reinterpret_cast<const uint32_t *>(vh), bh1 = *reinterpret_cast<const uint32_t *>(vh + 8);
-                        const uint32_t bl0 = *reinterpret_cast<const uint32_t *>(vl), bl1 = *reinterpret_cast<const uint32_t *>(vl + 8);
-                        mma16816(oacc[ot], ah, bh0, bh1);
-                        mma16816(oacc[ot], ah, bl0, bl1);
-                        mma16816(oacc[ot], al, bh0, bh1);
+                    for (int o0 = 0; o0 < 8; o0 += 4) {
+                        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const __half *vh = Vh + (8 * (o0 + u) + g) * HWP + k0, *vl = Vl + (8 * (o0 + u) + g) * HWP + k0;
+                            bh[u][0] = *reinterpret_cast<const uint32_t *>(vh); bh[u][1] = *reinterpret_cast<const uint32_t *>(vh + 8);
+                            bl[u][0] = *reinterpret_cast<const uint32_t *>(vl); bl[u][1] = *reinterpret_cast<const uint32_t *>(vl + 8);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) mma16816(oacc[o0 + u], ah, bh[u][0], bh[u][1]);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) mma16816(oacc[o0 + u], ah, bl[u][0], bl[u][1]);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) mma16816(oacc[o0 + u], al, bh[u][0], bh[u][1]);
                     }
                 }
                 // ---- H_{l+1} = tanh(out / (sum + 1e-12) + b): rows g / g + 8, columns 8 ot + 2t, + 1 ----
 #pragma unroll
                 for (int ot = 0; ot < 8; ++ot) {
                     const float2 b2 = __ldg(reinterpret_cast<const float2 *>(bias + 8 * ot + 2 * t));
-                    oacc[ot][0] = tanhf(oacc[ot][0] / den0 + b2.x);
-                    oacc[ot][1] = tanhf(oacc[ot][1] / den0 + b2.y);
-                    oacc[ot][2] = tanhf(oacc[ot][2] / den1 + b2.x);
-                    oacc[ot][3] = tanhf(oacc[ot][3] / den1 + b2.y);
+                    oacc[ot][0] = tanh_fast(fmaf(oacc[ot][0], den0, b2.x));
+                    oacc[ot][1] = tanh_fast(fmaf(oacc[ot][1], den0, b2.y));
+                    oacc[ot][2] = tanh_fast(fmaf(oacc[ot][2], den1, b2.x));
+                    oacc[ot][3] = tanh_fast(fmaf(oacc[ot][3], den1, b2.y));
                 }
                 if (l + 1 < L) {
                     // ---- next layer's value rows: H_{l+1} Wg_{l+1}, the H fragments again being the A operand ----
@@ -278,13 +309,20 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
                         split2(oacc[2 * ks + 1][2], oacc[2 * ks + 1][3], ah[3], al[3]);
                         const int k0 = 16 * ks + 2 * t;
 #pragma unroll
-                        for (int ot = 0; ot < 8; ++ot) {
-                            const __half *wh = Wh + (8 * ot + g) * kWgPitch + k0, *wl = Wl + (8 * ot + g) * kWgPitch + k0;
-                            const uint32_t bh0 = *reinterpret_cast<const uint32_t *>(wh), bh1 = *reinterpret_cast<const uint32_t *>(wh + 8);
-                            const uint32_t bl0 = *reinterpret_cast<const uint32_t *>(wl), bl1 = *reinterpret_cast<const uint32_t *>(wl + 8);
-                            mma16816(hacc[ot], ah, bh0, bh1);
-                            mma16816(hacc[ot], ah, bl0, bl1);
-                            mma16816(hacc[ot], al, bh0, bh1);
+                        for (int o0 = 0; o0 < 8; o0 += 4) {
+                            uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const __half *wh = Wh + (8 * (o0 + u) + g) * kWgPitch + k0, *wl = Wl + (8 * (o0 + u) + g) * kWgPitch + k0;
+                                bh[u][0] = *reinterpret_cast<const uint32_t *>(wh); bh[u][1] = *reinterpret_cast<const uint32_t *>(wh + 8);
+                                bl[u][0] = *reinterpret_cast<const uint32_t *>(wl); bl[u][1] = *reinterpret_cast<const uint32_t *>(wl + 8);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) mma16816(hacc[o0 + u], ah, bh[u][0], bh[u][1]);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) mma16816(hacc[o0 + u], ah, bl[u][0], bl[u][1]);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) mma16816(hacc[o0 + u], al, bh[u][0], bh[u][1]);
                         }
                     }
 #pragma unroll
@@ -299,12 +337,20 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
                         const int c = 8 * ot + 2 * t;
                         if (v0) {
                             float2 x = make_float2(oacc[ot][0], oacc[ot][1]);
-                            if (A.d.residual) { const float2 ev = __ldcg(reinterpret_cast<const float2 *>(A.scr_e + (r_env + i0 + g) * 64 + c)); x.x += ev.x; x.y += ev.y; }
+                            if (A.d.residual) {            // E = hi + lo from the key operand (|error| <= 3e-8)
+                                const float2 eh = __half22float2(*reinterpret_cast<const __half2 *>(Eh + (i0 + g) * kEhPitch + c));
+                                const float2 el = __half22float2(*reinterpret_cast<const __half2 *>(El + (i0 + g) * kEhPitch + c));
+                                x.x += eh.x + el.x; x.y += eh.y + el.y;
+                            }
                             *reinterpret_cast<float2 *>(A.scr_q + (r_env + i0 + g) * 64 + c) = x;
                         }
                         if (v1) {
                             float2 x = make_float2(oacc[ot][2], oacc[ot][3]);
-                            if (A.d.residual) { const float2 ev = __ldcg(reinterpret_cast<const float2 *>(A.scr_e + (r_env + i0 + g + 8) * 64 + c)); x.x += ev.x; x.y += ev.y; }
+                            if (A.d.residual) {
+                                const float2 eh = __half22float2(*reinterpret_cast<const __half2 *>(Eh + (i0 + g + 8) * kEhPitch + c));
+                                const float2 el = __half22float2(*reinterpret_cast<const __half2 *>(El + (i0 + g + 8) * kEhPitch + c));
+                                x.x += eh.x + el.x; x.y += eh.y + el.y;
+                            }
                             *reinterpret_cast<float2 *>(A.scr_q + (r_env + i0 + g + 8) * 64 + c) = x;
                         }
                     }
