@@ -111,11 +111,13 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
         const size_t r_env = (size_t)env * n;
         __syncthreads();                                       // the previous env's operands are dead
         // ---- keys: E rows -> fp16 hi / lo ----
+        // (unconditional loads from a clamped row, zeroed afterwards: predicated loads are not batched by the compiler)
 #pragma unroll 4
-        for (int e = tid; e < NK * 16; e += kMThreads) {
+        for (int it = 0; it < NS; ++it) {
+            const int e = tid + it * kMThreads;
             const int j = e >> 4, c = (e & 15) << 2;
-            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (j < n) v = __ldcg(reinterpret_cast<const float4 *>(A.scr_e + (r_env + j) * 64 + c));
+            float4 v = __ldcg(reinterpret_cast<const float4 *>(A.scr_e + (r_env + min(j, n - 1)) * 64 + c));
+            if (j >= n) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             uint32_t h0, l0, h1, l1;
             split2(v.x, v.y, h0, l0);
             split2(v.z, v.w, h1, l1);
@@ -126,10 +128,11 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
             if (l) __syncthreads();                            // every warp wrote its H_l Wg_l rows and is done with the old operands
             // ---- values: H_l Wg_l rows -> transposed fp16 hi / lo [col][key] ----
 #pragma unroll 4
-            for (int e = tid; e < NK * 16; e += kMThreads) {
+            for (int it = 0; it < NS; ++it) {
+                const int e = tid + it * kMThreads;
                 const int j = e % NK, c = (e / NK) << 2;       // consecutive threads take consecutive keys: neighbouring halves
-                float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (j < n) v = __ldcg(reinterpret_cast<const float4 *>(A.scr_hw + (r_env + j) * 64 + c));
+                float4 v = __ldcg(reinterpret_cast<const float4 *>(A.scr_hw + (r_env + min(j, n - 1)) * 64 + c));
+                if (j >= n) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -142,7 +145,8 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
             if (l + 1 < L) {
                 const float *wg = A.weights + o.gcn_w + (size_t)(l + 1) * kE * kE;
 #pragma unroll 4
-                for (int e = tid; e < kE * kE; e += kMThreads) {
+                for (int it = 0; it < kE * kE / kMThreads; ++it) {
+                    const int e = tid + it * kMThreads;
                     const int k = e >> 6, c = e & 63;
                     const float v = __ldg(wg + e);
                     const __half h = __float2half_rn(v);
@@ -156,22 +160,35 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
                 const int i0 = strip << 4;                     // first query row of the strip; this lane owns rows i0+g, i0+g+8
                 __syncwarp();
                 // ---- query rows and neighbour mask words -> the warp's slice ----
-                for (int e = lane; e < 16 * 16; e += 32) {
-                    const int r = e >> 4, c = (e & 15) << 2;
-                    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    if (i0 + r < n) v = __ldcg(reinterpret_cast<const float4 *>(A.scr_q + (r_env + i0 + r) * 64 + c));
-                    *reinterpret_cast<float4 *>(Qw + r * kQPitch + c) = v;
+                // (all 8 + 8 loads of the strip are issued before the first store: one L2 round trip per strip)
+                float4 qv[8];
+                uint32_t mv[4];
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int e = lane + 32 * it, r = e >> 4, c = (e & 15) << 2;
+                    qv[it] = __ldcg(reinterpret_cast<const float4 *>(A.scr_q + (r_env + min(i0 + r, n - 1)) * 64 + c));
                 }
-                for (int e = lane; e < 16 * 8; e += 32) {
-                    const int r = e >> 3, w = e & 7;
-                    uint32_t m = 0u;
-                    if (i0 + r < n && w < W) {
-                        m = 0xFFFFFFFFu;
-                        if (A.adj_bits) m &= __ldg(A.adj_bits + (r_env + i0 + r) * W + w);
-                        if (A.chan_bits) m &= __ldg(A.chan_bits + (((size_t)env * L + l) * n + i0 + r) * W + w);
-                    }
-                    Mw[e] = m;
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int e = lane + 32 * it, r = e >> 3, w = e & 7;
+                    const size_t row = r_env + min(i0 + r, n - 1);
+                    const int wc = min(w, W - 1);
+                    const uint32_t ma = A.adj_bits ? __ldg(A.adj_bits + row * W + wc) : 0xFFFFFFFFu;
+                    const uint32_t mc = A.chan_bits ? __ldg(A.chan_bits + (((size_t)env * L + l) * n + min(i0 + r, n - 1)) * W + wc) : 0xFFFFFFFFu;
+                    mv[it] = (i0 + r < n && w < W) ? (ma & mc) : 0u;
                 }
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int e = lane + 32 * it, r = e >> 4;
+                    if (i0 + r >= n) qv[it] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int e = lane + 32 * it, r = e >> 4, c = (e & 15) << 2;
+                    *reinterpret_cast<float4 *>(Qw + r * kQPitch + c) = qv[it];
+                }
+#pragma unroll
+                for (int it = 0; it < 4; ++it) Mw[lane + 32 * it] = mv[it];
                 __syncwarp();
                 // ---- scores: S[16][NK] = Q E^T, three fp16 products per tile into one fp32 accumulator ----
                 float s[NT][4];
