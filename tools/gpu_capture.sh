@@ -8,6 +8,6 @@ OUT=gpurun_out; mkdir -p $OUT
 CMD="python bench.py --config $CFG --steps 128 --warmup 64 --no-cpu-baseline --e2e-steps 5"
 $CMD > $OUT/${TAG}_${CFG}_plain.json 2> $OUT/${TAG}_${CFG}_plain.err || { echo "plain run failed"; tail -5 $OUT/${TAG}_${CFG}_plain.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file $OUT/${TAG}_${CFG}_launches.csv $CMD > $OUT/${TAG}_${CFG}_ncu_l.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'policy_tc_kernel|env_kernel|policy_small|policy_large' -s 200 -c 4 -o $OUT/${TAG}_${CFG}_full -f $CMD > $OUT/${TAG}_${CFG}_ncu_f.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'policy_tc_kernel|env_kernel|policy_small|policy_large|policy_attn' -s 200 -c 6 -o $OUT/${TAG}_${CFG}_full -f $CMD > $OUT/${TAG}_${CFG}_ncu_f.log 2>&1
 ncu -i $OUT/${TAG}_${CFG}_full.ncu-rep --page raw --csv > $OUT/${TAG}_${CFG}_raw.csv 2>/dev/null
 echo "capture done: $TAG $CFG"; ls -la $OUT | grep ${TAG}_${CFG}
