@@ -13,11 +13,12 @@ LIB_PATH = os.environ.get("COM_MARL_B200_LIB") or os.path.join(_HERE, "lib", "li
 CM_OK, CM_EINVAL, CM_EUNSUPPORTED, CM_ECUDA, CM_ENODEVICE, CM_EACTION = 0, -1, -2, -3, -4, -5
 PREDATOR_PREY, COVERAGE = 0, 1
 CH_FC, CH_FL, CH_IID, CH_GE = 0, 1, 2, 3
-POLICY_COMM, POLICY_DEC = 0, 1
+POLICY_COMM, POLICY_DEC, POLICY_CENT = 0, 1, 2
+POLICY_FLAG_RELU = 1
 MAX_AGENTS, MAX_GRID, MAX_LAYERS = 256, 64, 4
 
 EXPORTS = ("cm_abi_version", "cm_strerror", "cm_last_cuda_error", "cm_device_count", "cm_env_reset", "cm_env_step",
-           "cm_comm_update", "cm_policy_forward", "cm_policy_blob_floats", "cm_policy_workspace_bytes", "cm_policy_tc_blob_floats", "cm_policy_tc_prepare", "cm_mask_pack",
+           "cm_comm_update", "cm_policy_forward", "cm_policy_blob_floats", "cm_policy_cent_blob_floats", "cm_policy_workspace_bytes", "cm_policy_tc_blob_floats", "cm_policy_tc_prepare", "cm_mask_pack",
            "cm_mask_unpack", "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host", "cm_ppo_advantages", "cm_adam_step")
 
 
@@ -49,7 +50,7 @@ class StepIO(C.Structure):
 class PolicyDesc(C.Structure):
     _fields_ = [("n_agents", C.c_int32), ("obs_dim", C.c_int32), ("n_layers", C.c_int32), ("residual", C.c_int32),
                 ("greedy", C.c_int32), ("math", C.c_int32), ("seed", C.c_uint64), ("env_id0", C.c_int64),
-                ("kind", C.c_int32), ("reserved_", C.c_int32)]
+                ("kind", C.c_int32), ("flags", C.c_int32)]
 
 
 class PolicyIO(C.Structure):
@@ -89,6 +90,8 @@ def lib():
     L.cm_policy_forward.argtypes = [C.POINTER(PolicyDesc), C.POINTER(PolicyIO), C.c_void_p]
     L.cm_policy_blob_floats.restype = C.c_size_t
     L.cm_policy_blob_floats.argtypes = [C.c_int32, C.c_int32]
+    L.cm_policy_cent_blob_floats.restype = C.c_size_t
+    L.cm_policy_cent_blob_floats.argtypes = [C.c_int32, C.c_int32]
     L.cm_policy_tc_blob_floats.restype = C.c_size_t
     L.cm_policy_tc_blob_floats.argtypes = [C.c_int32, C.c_int32]
     L.cm_policy_tc_prepare.restype = C.c_int

@@ -57,4 +57,50 @@ __device__ __forceinline__ float warp_sumf(float v)
     return v;
 }
 
+// Tail of every categorical policy: softmax of one agent's logits, availability mask, renormalisation
+// (comm_categorical_mlp_policy.py:86-94, centralized_categorical_mlp_policy.py:84-96), then argmax (np.argmax: first maximum)
+// or inverse-CDF sampling with a sequential fp32 cumulative sum (stream spec).  g = env * n + il.
+__device__ __forceinline__ void categorical_finish(const cm_policy_desc &d, const cm_policy_io &io, const float (&lg)[CM_ACTIONS],
+                                                   int64_t g, int64_t env, int il)
+{
+    float pr[CM_ACTIONS];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int a = 0; a < CM_ACTIONS; ++a) mx = fmaxf(mx, lg[a]);
+    float sum = 0.0f;
+#pragma unroll
+    for (int a = 0; a < CM_ACTIONS; ++a) { pr[a] = expf(lg[a] - mx); sum += pr[a]; }
+    const uint32_t av = io.avail_bits ? io.avail_bits[g] : 0x1Fu;
+    float msum = 0.0f;
+#pragma unroll
+    for (int a = 0; a < CM_ACTIONS; ++a) { pr[a] = ((av >> a) & 1u) ? pr[a] / sum : 0.0f; msum += pr[a]; }
+#pragma unroll
+    for (int a = 0; a < CM_ACTIONS; ++a) pr[a] = pr[a] / msum;
+    if (io.logits) for (int a = 0; a < CM_ACTIONS; ++a) io.logits[g * CM_ACTIONS + a] = lg[a];
+    if (io.probs) for (int a = 0; a < CM_ACTIONS; ++a) io.probs[g * CM_ACTIONS + a] = pr[a];
+    if (!io.actions) return;
+    int act;
+    if (d.greedy) {
+        act = 0;
+        for (int a = 1; a < CM_ACTIONS; ++a) if (pr[a] > pr[act]) act = a;
+    } else {
+        float u;
+        if (io.sample_u) u = io.sample_u[g];
+        else {
+            const uint4 blk = philox4x32_10(
+                make_uint4((uint32_t)(d.env_id0 + env), io.tick[env], kStreamAct | (io.episode[env] << 8), (uint32_t)(il >> 2)),
+                make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32)));
+            const uint32_t w = (il & 3) == 0 ? blk.x : ((il & 3) == 1 ? blk.y : ((il & 3) == 2 ? blk.z : blk.w));
+            u = u24(w);
+        }
+        int last = 4;
+        for (int a = 0; a < CM_ACTIONS; ++a) if (pr[a] > 0.0f) last = a;
+        act = -1;
+        float c = 0.0f;
+        for (int a = 0; a < CM_ACTIONS; ++a) { c += pr[a]; if (act < 0 && u < c) act = a; }
+        if (act < 0) act = last;
+    }
+    io.actions[g] = (int8_t)act;
+}
+
 }  // namespace cm

@@ -158,47 +158,10 @@ __device__ void head_and_sample(const PolicyArgs &A, const Blob &o, const float 
     if (tid < rows) {
         const int r = tid;
         const int64_t g = g0 + r;
-        float lg[CM_ACTIONS], pr[CM_ACTIONS];
-        float mx = -INFINITY;
+        float lg[CM_ACTIONS];
 #pragma unroll
-        for (int a = 0; a < CM_ACTIONS; ++a) { lg[a] = logit_s[r * CM_ACTIONS + a]; mx = fmaxf(mx, lg[a]); }
-        float sum = 0.0f;
-#pragma unroll
-        for (int a = 0; a < CM_ACTIONS; ++a) { pr[a] = expf(lg[a] - mx); sum += pr[a]; }
-        const uint32_t av = io.avail_bits ? io.avail_bits[g] : 0x1Fu;
-        float msum = 0.0f;
-#pragma unroll
-        for (int a = 0; a < CM_ACTIONS; ++a) { pr[a] = ((av >> a) & 1u) ? pr[a] / sum : 0.0f; msum += pr[a]; }
-#pragma unroll
-        for (int a = 0; a < CM_ACTIONS; ++a) pr[a] = pr[a] / msum;
-        if (io.logits) for (int a = 0; a < CM_ACTIONS; ++a) io.logits[g * CM_ACTIONS + a] = lg[a];
-        if (io.probs) for (int a = 0; a < CM_ACTIONS; ++a) io.probs[g * CM_ACTIONS + a] = pr[a];
-        if (io.actions) {
-            int act;
-            if (d.greedy) {                    // np.argmax: first maximum (comm_categorical_mlp_policy.py:111-112)
-                act = 0;
-                for (int a = 1; a < CM_ACTIONS; ++a) if (pr[a] > pr[act]) act = a;
-            } else {                           // inverse CDF, sequential fp32 cumulative sum (stream spec)
-                const int64_t env = n_div > 0 ? env_base + r / n_div : env_base;
-                const int il = n_div > 0 ? r % n_div : il_base + r;
-                float u;
-                if (io.sample_u) u = io.sample_u[g];
-                else {
-                    const uint4 blk = philox4x32_10(
-                        make_uint4((uint32_t)(d.env_id0 + env), io.tick[env], kStreamAct | (io.episode[env] << 8), (uint32_t)(il >> 2)),
-                        make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32)));
-                    const uint32_t w = (il & 3) == 0 ? blk.x : ((il & 3) == 1 ? blk.y : ((il & 3) == 2 ? blk.z : blk.w));
-                    u = u24(w);
-                }
-                int last = 4;
-                for (int a = 0; a < CM_ACTIONS; ++a) if (pr[a] > 0.0f) last = a;
-                act = -1;
-                float c = 0.0f;
-                for (int a = 0; a < CM_ACTIONS; ++a) { c += pr[a]; if (act < 0 && u < c) act = a; }
-                if (act < 0) act = last;
-            }
-            io.actions[g] = (int8_t)act;
-        }
+        for (int a = 0; a < CM_ACTIONS; ++a) lg[a] = logit_s[r * CM_ACTIONS + a];
+        categorical_finish(d, io, lg, g, n_div > 0 ? env_base + r / n_div : env_base, n_div > 0 ? r % n_div : il_base + r);
     }
 }
 
@@ -565,6 +528,7 @@ static int round_up_tile(int n) { return (n + kTile - 1) / kTile * kTile; }
 static size_t large_ws_floats(int n) { return (size_t)3 * kE * round_up_tile(n); }
 
 int launch_policy_tc(const cm_policy_desc *desc, const cm_policy_io *io, cudaStream_t stream);   // policy_tc_kernel.cu
+int launch_policy_cent(const cm_policy_desc *desc, const cm_policy_io *io, cudaStream_t stream); // policy_cent_kernel.cu
 size_t tc_large_ws_floats(int n, int64_t n_envs);                                                // policy_attn_kernel.cu
 
 struct LaunchCache { int dev; int ctas_per_sm; int sms; };
@@ -614,7 +578,8 @@ extern "C" int cm_policy_forward(const cm_policy_desc *desc, const cm_policy_io 
     if (io->actions && !desc->greedy && !io->sample_u && (!io->tick || !io->episode)) return CM_EINVAL;
     if (io->n_envs < 0) return CM_EINVAL;
     if (io->n_envs == 0) return CM_OK;
-    if (desc->kind != CM_POLICY_COMM && desc->kind != CM_POLICY_DEC) return CM_EINVAL;
+    if (desc->kind != CM_POLICY_COMM && desc->kind != CM_POLICY_DEC && desc->kind != CM_POLICY_CENT) return CM_EINVAL;
+    if (desc->kind == CM_POLICY_CENT) return launch_policy_cent(desc, io, (cudaStream_t)stream);
     if (desc->math == 1 || desc->math == 2) return launch_policy_tc(desc, io, (cudaStream_t)stream);
     if (desc->kind == CM_POLICY_DEC) return CM_EUNSUPPORTED;       // Obs-DP runs on the tensor-core kernel only
     if (desc->math != 0) return CM_EINVAL;

@@ -36,6 +36,26 @@ __host__ __device__ inline Blob blob_layout(int D, int L)
     return o;
 }
 
+// CENT policy blob (CentralizedCategoricalMLPPolicy: one MLP over the concatenated observation, K = n*D inputs, 5n outputs),
+// every dense weight K-major like the Comm-DP blob:  w1 [n*D][128] b1 [128] w2 [128][64] b2 [64] w3 [64][32] b3 [32] w4 [32][5n] b4 [5n]
+struct CentBlob { int w1, b1, w2, b2, w3, b3, w4, b4, total; };
+
+__host__ __device__ inline CentBlob cent_blob_layout(int n, int D)
+{
+    CentBlob o;
+    int p = 0;
+    o.w1 = p; p += n * D * kC1;
+    o.b1 = p; p += kC1;
+    o.w2 = p; p += kC1 * kC2;
+    o.b2 = p; p += kC2;
+    o.w3 = p; p += kC2 * kC3;
+    o.b3 = p; p += kC3;
+    o.w4 = p; p += kC3 * n * CM_ACTIONS;
+    o.b4 = p; p += n * CM_ACTIONS;
+    o.total = p;
+    return o;
+}
+
 struct PolicyArgs {
     cm_policy_desc d;
     cm_policy_io io;

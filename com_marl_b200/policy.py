@@ -507,3 +507,117 @@ class DecCategoricalMLPPolicy(nn.Module):
     @property
     def recurrent(self):
         return False
+
+
+class CentralizedCategoricalMLPPolicy(nn.Module):
+    """CENT policy (one MLP over the concatenated observation of the team) with the reference's call signature and
+    state_dict, backed by ``policy_cent_kernel`` (cm_policy_desc.kind = CM_POLICY_CENT).
+
+    Mirrors com_marl/torch/policies/centralized_categorical_mlp_policy.py:11-137: the policy IS garage's MLPModule
+    ``n*D -> hidden_sizes -> 5n`` (xavier_uniform weights, zero biases, :16-21,43-53), so its parameters are
+    ``_layers.i.linear.*`` / ``_output_layers.0.linear.*`` and reference checkpoints load with ``load_state_dict``; the
+    logits are reshaped to ``(..., n, 5)``, softmax per agent, availability mask, renormalisation (:73-96).
+    ``get_actions(obs_n, avail_actions_n, greedy)`` (:98-117) runs the kernel; ``forward`` / ``entropy`` /
+    ``log_likelihood`` (:122-137, the differentiable training path) are the same formula in torch ops.  The runners build
+    it with ``hidden_sizes=[128, 64, 32]`` and tanh or relu (runner_*_cent.py:48-58, env_uitils.py:188-189) — the sizes the
+    kernel is specialised for; note that the class default ``(32, 32)`` of the reference is never used by its runners."""
+    _kind = N.POLICY_CENT
+
+    def __init__(self, env_spec, n_agents, hidden_sizes=(128, 64, 32), hidden_nonlinearity=torch.tanh,
+                 name="CentralizedCategoricalMLPPolicy", device="cuda", seed=1):
+        super().__init__()
+        if not hasattr(env_spec.action_space, "n"):
+            raise AssertionError("Categorical policy only works with akro.Discrete action space.")
+        if tuple(hidden_sizes) != (128, 64, 32):
+            raise NotImplementedError("the kernel is specialised for the runners' sizes hidden_sizes=(128, 64, 32) "
+                                      "(exp_runners/env_uitils.py:188-189)")
+        if hidden_nonlinearity in (torch.tanh, "tanh"):
+            self._relu = False
+        elif hidden_nonlinearity in (torch.relu, torch.nn.functional.relu, "relu"):
+            self._relu = True
+        else:
+            raise NotImplementedError("hidden_nonlinearity must be tanh or relu (runner_*_cent.py:49)")
+        self.name, self.device = name, torch.device(device)
+        self.centralized, self.vectorized, self.step = True, True, 0          # (no `comm` attribute: the sampler's switch)
+        self._n_agents = int(n_agents)
+        self._obs_dim = int(env_spec.observation_space.flat_dim)
+        self._dec_obs_dim = self._obs_dim // self._n_agents
+        self._action_dim = env_spec.action_space.n
+        self.seed = int(seed)
+        mlp = _MLP(self._obs_dim, tuple(hidden_sizes), self._action_dim * self._n_agents, output_tanh=False)
+        self._layers, self._output_layers = mlp._layers, mlp._output_layers
+        self.layers = [self]
+        self.to(self.device)
+        self._blob = self._blob_sig = None
+
+    _signature = CommCategoricalMLPPolicy._signature
+
+    def uses_tensor_cores(self):
+        return False
+
+    def check_errors(self):
+        pass
+
+    def weight_blob(self):
+        """w1 [n*D][128] b1 w2 [128][64] b2 w3 [64][32] b3 w4 [32][5n] b4 (include/commarl_b200.h), rebuilt when a parameter changed"""
+        sig = self._signature()
+        if self._blob is None or sig != self._blob_sig:
+            sd = self.state_dict()
+            parts = []
+            for i in range(3):
+                parts += [sd[f"_layers.{i}.linear.weight"].t(), sd[f"_layers.{i}.linear.bias"]]
+            parts += [sd["_output_layers.0.linear.weight"].t(), sd["_output_layers.0.linear.bias"]]
+            blob = torch.cat([p.detach().to(self.device, torch.float32).contiguous().reshape(-1) for p in parts])
+            assert blob.numel() == N.lib().cm_policy_cent_blob_floats(self._n_agents, self._dec_obs_dim)
+            self._blob, self._blob_sig = blob.contiguous(), sig
+        return self._blob
+
+    def act_device(self, obs, avail_bits=None, sample_u=None, tick=None, episode=None, greedy=False, probs=None, logits=None,
+                   actions=None, env_id0=0, **_unused):
+        """forward + sampling on device tensors (obs float32 (B, n, D) / (B, n*D)); no masks, no attention output.
+        Outputs are written into the given tensors; the call is CUDA-graph capturable."""
+        desc = N.PolicyDesc(self._n_agents, self._dec_obs_dim, 1, 0, int(greedy), 0, self.seed, env_id0, self._kind,
+                            N.POLICY_FLAG_RELU if self._relu else 0)
+        io = N.PolicyIO()
+        io.n_envs = obs.shape[0]
+        io.weights = N.ptr(self.weight_blob())
+        for k, v in (("obs", obs), ("avail_bits", avail_bits), ("sample_u", sample_u), ("tick", tick), ("episode", episode),
+                     ("probs", probs), ("logits", logits), ("actions", actions)):
+            setattr(io, k, N.ptr(v))
+        with torch.cuda.device(self.device):
+            N.check("cm_policy_forward", N.lib().cm_policy_forward(C.byref(desc), C.byref(io), N.stream_ptr()))
+
+    # ---- reference call surface ----
+    def forward(self, obs_n, avail_actions_n, get_actions=False):
+        if get_actions:
+            obs_n = torch.as_tensor(np.asarray(obs_n), dtype=torch.float32, device=self.device)
+            avail_actions_n = torch.as_tensor(np.asarray(avail_actions_n), dtype=torch.float32, device=self.device)
+        x = obs_n
+        for layer in self._layers:
+            x = torch.relu(layer(x)) if self._relu else torch.tanh(layer(x))
+        logits = self._output_layers[0](x)
+        logits = logits.reshape(logits.shape[:-1] + (self._n_agents, -1))
+        probs = torch.softmax(logits, dim=-1)
+        avail = avail_actions_n.reshape(avail_actions_n.shape[:-1] + (self._n_agents, -1))
+        masked = probs * avail
+        masked = masked / masked.sum(dim=-1, keepdim=True)
+        return Categorical(probs=masked.cpu() if get_actions else masked)
+
+    _host_calls = 0
+    get_actions = DecCategoricalMLPPolicy.get_actions
+
+    def log_likelihood(self, observations, avail_actions_n, actions):
+        return self.forward(observations, avail_actions_n).log_prob(actions).sum(axis=-1)
+
+    def entropy(self, observations, avail_actions_n):
+        return self.forward(observations, avail_actions_n).entropy().mean(axis=-1)
+
+    def reset(self, dones=None):
+        pass
+
+    def grad_norm(self):
+        return math.sqrt(sum(p.grad.norm(2).item() ** 2 for p in self.parameters() if p.grad is not None))
+
+    @property
+    def recurrent(self):
+        return False

@@ -30,6 +30,9 @@ def make_policy(spec: ScenarioSpec, device="cuda", seed: Optional[int] = None, t
     if kind == "dec":      # Obs-DP: no communication (dec_categorical_mlp_policy.py)
         from .policy import DecCategoricalMLPPolicy
         return DecCategoricalMLPPolicy(env_spec, n, device=device, seed=spec.seed if seed is None else seed)
+    if kind == "cent":     # CENT: one MLP over the concatenated observation (centralized_categorical_mlp_policy.py)
+        from .policy import CentralizedCategoricalMLPPolicy
+        return CentralizedCategoricalMLPPolicy(env_spec, n, device=device, seed=spec.seed if seed is None else seed)
     return CommCategoricalMLPPolicy(env_spec, n, n_gcn_layers=spec.n_layers, device=device,
                                     seed=spec.seed if seed is None else seed, math=math)
 

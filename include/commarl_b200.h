@@ -159,11 +159,17 @@ typedef struct cm_policy_desc {
     int32_t kind;              /* cm_policy_kind: 0 = Comm-DP (CommCategoricalMLPPolicy), 1 = Obs-DP (DecCategoricalMLPPolicy:
                                   per-agent encoder D -> 128 -> 64 (tanh) and head 64 -> 32 (tanh) -> 5, no communication;
                                   dec_categorical_mlp_policy.py:107-124).  Obs-DP uses the same blob layout with enc_w1/b1,
-                                  enc_w2/b2, head_w3/b3, head_w4/b4 filled; tensor-core path only, any team size */
-    int32_t reserved_;
+                                  enc_w2/b2, head_w3/b3, head_w4/b4 filled; tensor-core path only, any team size.
+                                  2 = CENT (CentralizedCategoricalMLPPolicy, centralized_categorical_mlp_policy.py:11-97): one
+                                  MLP n*D -> 128 -> 64 -> 32 -> 5n over the concatenated observation of the team, softmax per
+                                  agent; its own blob (cm_policy_cent_blob_floats):
+                                    w1 [n*D][128] b1 [128] w2 [128][64] b2 [64] w3 [64][32] b3 [32] w4 [32][5n] b4 [5n]
+                                  exact fp32 (math = 0) only; n_layers / residual / masks / attention are not used */
+    int32_t flags;             /* CM_POLICY_FLAG_*; CENT only */
 } cm_policy_desc;
 
-typedef enum cm_policy_kind { CM_POLICY_COMM = 0, CM_POLICY_DEC = 1 } cm_policy_kind;
+typedef enum cm_policy_kind { CM_POLICY_COMM = 0, CM_POLICY_DEC = 1, CM_POLICY_CENT = 2 } cm_policy_kind;
+#define CM_POLICY_FLAG_RELU 1  /* hidden_nonlinearity = relu instead of tanh (runner_*_cent.py:49) */
 
 typedef struct cm_policy_io {
     int64_t n_envs;            /* B */
@@ -213,6 +219,9 @@ int cm_comm_update(const cm_env_desc *desc, const cm_env_state *state, const cm_
  * graph_conv_module.py:51-72, categorical_mlp_module.py:64-80, multi_headed_mlp_module.py:134-149). */
 int cm_policy_forward(const cm_policy_desc *desc, const cm_policy_io *io, cm_stream_t stream);
 size_t cm_policy_blob_floats(int32_t obs_dim, int32_t n_layers);
+/* CENT: CentralizedCategoricalMLPPolicy.forward(get_actions=True) + sampling through the same cm_policy_forward call
+ * (desc.kind = CM_POLICY_CENT; centralized_categorical_mlp_policy.py:61-117); length of its weight blob in floats */
+size_t cm_policy_cent_blob_floats(int32_t n_agents, int32_t obs_dim);
 /* tcgen05 variant: re-lays the fp32 weight blob out as pre-split fp16 ([B_hi ; B_lo] stacked) K-major core-matrix
  * panels, one per tensor-core product, so that the kernel fetches a layer's B operand with one bulk async copy */
 size_t cm_policy_tc_blob_floats(int32_t obs_dim, int32_t n_layers);

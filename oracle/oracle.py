@@ -337,6 +337,30 @@ def policy_forward_dec(w, obs, avail, dtype=np.float32):
     return logits.astype(f), pr.astype(f)
 
 
+def policy_forward_cent(w, obs, avail, relu=False, dtype=np.float32):
+    """CENT forward (centralized_categorical_mlp_policy.py:61-97): one MLP over the concatenated observation (hidden tanh | relu,
+    linear output of 5n logits), reshaped to (B,n,5), softmax per agent, availability mask, renormalisation.  w: dict keyed
+    like the reference state_dict; obs (B,n*D) or (B,n,D); avail (B,n,5) or None.  Returns logits (B,n,5), masked probs."""
+    f = dtype
+    g = lambda k: np.asarray(w[k], dtype=f)  # noqa: E731
+    x = np.asarray(obs, dtype=f)
+    x = x.reshape(x.shape[0], -1)
+    i = 0
+    while f"_layers.{i}.linear.weight" in w:
+        x = x @ g(f"_layers.{i}.linear.weight").T + g(f"_layers.{i}.linear.bias")
+        x = np.maximum(x, 0) if relu else np.tanh(x)
+        i += 1
+    logits = x @ g("_output_layers.0.linear.weight").T + g("_output_layers.0.linear.bias")
+    logits = logits.reshape(logits.shape[0], -1, 5)
+    z = logits - logits.max(axis=-1, keepdims=True)
+    pr = np.exp(z)
+    pr = pr / pr.sum(axis=-1, keepdims=True)
+    if avail is not None:
+        pr = pr * np.asarray(avail, dtype=f).reshape(pr.shape)
+    pr = pr / pr.sum(axis=-1, keepdims=True)
+    return logits.astype(f), pr.astype(f)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # PPO update pieces (SURVEY.md §8f.1) — numpy restatement of the reference's tensor code, test infrastructure only
 # ---------------------------------------------------------------------------------------------------------------

@@ -111,3 +111,22 @@ def test_dec_policy_oracle_matches_reference(name):
     logits, probs = orc.policy_forward_dec(w, z["obs"].reshape(B, n, D), z["avail"].reshape(B, n, 5))
     assert np.abs(logits - z["logits"].reshape(B, n, 5)).max() <= 1e-5
     assert np.abs(probs - z["probs"].reshape(B, n, 5)).max() <= 1e-5
+
+
+def _cent_cases():
+    import glob
+    return sorted(os.path.basename(p)[8:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "centpol_*.npz")))
+
+
+@pytest.mark.parametrize("name", _cent_cases())
+def test_cent_policy_oracle_matches_reference(name):
+    """CENT forward restatement (oracle.policy_forward_cent) against the vectors recorded from the unmodified reference
+    CentralizedCategoricalMLPPolicy (tests/golden/make_golden_cent.py)."""
+    import json
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"centpol_{name}.npz"))
+    meta = json.loads(str(z["meta"]))
+    n, B = meta["n"], meta["B"]
+    w = {k[3:]: z[k] for k in z.files if k.startswith("w::")}
+    logits, probs = orc.policy_forward_cent(w, z["obs"], z["avail"].reshape(B, n, 5), relu=bool(meta["relu"]))
+    assert np.abs(logits - z["logits"].reshape(B, n, 5)).max() <= 1e-5 * max(1.0, np.abs(z["logits"]).max())
+    assert np.abs(probs - z["probs"].reshape(B, n, 5)).max() <= 1e-5
