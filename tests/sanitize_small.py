@@ -41,6 +41,16 @@ def main():
     eng.env.check_errors()
     pol.check_errors()
     print("obs-dp / env groups ok")
+    # CENT policy: ragged last tile (70 envs = 64 + 6), K = n*D not a multiple of the 32-wide chunk, 2 output passes
+    spec = ScenarioSpec.from_cli("pp", 20, 1, 0.05, cap=2, loss=0.0, seed=3, max_env_steps=6)
+    pol = make_policy(spec, kind="cent")
+    eng = RolloutEngine(spec, pol, 70, ring=3, use_graph=False, groups=2)
+    eng.reset()
+    eng.run(6)
+    torch.cuda.synchronize()
+    eng.env.check_errors()
+    assert np.isfinite(eng.traj["probs"].cpu().numpy()).all()
+    print("cent ok, n =", spec.n_agents)
     # Gilbert-Elliot channel + comm-only entry point + mask converters
     spec = ScenarioSpec.from_cli("pp", 10, 1, 0.08, cap=2, loss=0.2, channel_type="GE", max_env_steps=5)
     from com_marl_b200.envs import BatchedEnv
