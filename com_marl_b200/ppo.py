@@ -84,6 +84,40 @@ class CommBaseCritic(nn.Module):
         return (0.5 * ((returns - mean) / std) ** 2 + std.log() + 0.5 * float(np.log(2 * np.pi))).mean()
 
 
+class _GaussianMean(nn.Module):
+    """parameter layout of garage's GaussianMLPModule (garage/torch/modules/gaussian_mlp_module.py:118-127,260-271):
+    ``_init_std`` = log(init_std), ``_mean_module`` = MLPModule"""
+
+    def __init__(self, input_dim, hidden_sizes, init_std):
+        super().__init__()
+        self._init_std = nn.Parameter(torch.tensor([float(init_std)]).log())
+        self._mean_module = _MLP(input_dim, tuple(hidden_sizes), 1, output_tanh=False)
+
+
+class GaussianMLPBaseline(nn.Module):
+    """Value baseline of the Obs-DP and CENT runners (com_marl/torch/baselines/gaussian_mlp_baseline.py:7-117, built with
+    hidden_sizes=(64, 64, 64) at runner_*_cent.py:60-62): V(s) = MLP(concatenated observation), fitted as the mean of a
+    Gaussian with one learnt log-std (GaussianMLPModule, std_parameterization='exp', no clamps).  Same ``state_dict`` names
+    (``module._init_std``, ``module._mean_module._layers.i.linear.*``): reference baselines load unchanged."""
+
+    def __init__(self, env_spec, hidden_sizes=(32, 32), init_std=1.0, name="GaussianMLPBaseline", device="cuda"):
+        super().__init__()
+        self.name, self.device = name, torch.device(device)
+        self.input_dim = int(env_spec.observation_space.flat_dim)
+        self.module = _GaussianMean(self.input_dim, hidden_sizes, init_std)
+        self.to(self.device)
+
+    def forward(self, obs):
+        """(P, T, O) -> (P, T) predicted values (:104-117)"""
+        return self.module._mean_module(obs).flatten(-2)
+
+    def compute_loss(self, obs, returns):
+        """-mean log N(returns; V(obs), exp(log_std)) over every step of the padded batch (:83-101)"""
+        mean = self.module._mean_module(obs.reshape(-1, self.input_dim))
+        std = self.module._init_std.exp().expand_as(mean)
+        return -torch.distributions.Normal(mean, std).log_prob(returns.reshape(-1, 1)).sum(-1).mean()
+
+
 class FlatAdam:
     """The reference's Adam (my_optimizer/adam.py) over ONE flat fp32 bucket: parameters and gradients of the module are
     re-seated as views of two flat tensors, so that the gradient all-reduce is one NCCL call, the gradient norm one
@@ -153,7 +187,10 @@ def ppo_advantages(rewards, baselines, valids, discount, gae_lambda, center=True
 
 
 class DevicePPO:
-    """CentralizedMAPPO's update (centralized_ma_ppo.py) for a Comm-DP policy + CommBaseCritic pair on one GPU per rank."""
+    """CentralizedMAPPO's update (centralized_ma_ppo.py) on one GPU per rank, for the three runner families: a Comm-DP or Obs-DP
+    policy with CommBaseCritic (runner_*_comm.py, runner_*_obsDP.py:61), or a CENT policy with GaussianMLPBaseline.  Like the reference, the policy call takes the
+    communication masks iff the policy has them (`hasattr(policy, 'comm')`, :455-490) and the baseline call iff it is the
+    'base_critic' (:229-232, :653-657)."""
 
     def __init__(self, policy, baseline, discount=0.99, gae_lambda=0.97, center_adv=True, positive_adv=False,
                  policy_ent_coeff=0.1, entropy_method="regularized", clip_grad_norm=7, optimization_n_minibatches=3,
@@ -163,6 +200,8 @@ class DevicePPO:
         if entropy_method == "no_entropy" and policy_ent_coeff != 0.0:
             raise ValueError("policy_ent_coeff should be zero when there is no entropy method")
         self.policy, self.baseline, self.device = policy, baseline, policy.device
+        self._comm = bool(getattr(policy, "comm", False))
+        self._critic_comm = getattr(baseline, "name", "") == "base_critic"
         self.discount, self.gae_lambda = float(discount), float(gae_lambda)
         self.center_adv, self.positive_adv = bool(center_adv), bool(positive_adv)
         self.ent_coeff = float(policy_ent_coeff) if entropy_method == "regularized" else 0.0
@@ -246,7 +285,10 @@ class DevicePPO:
     def finish_batch(self, b):
         """baselines (critic, no grad), returns and advantages for a padded device batch with the keys of process_samples"""
         with torch.no_grad():
-            b["baselines"] = self.baseline.forward(b["obs"], b["avail"], b["dist_adjs"], b["channels"]).float()
+            if self._critic_comm:
+                b["baselines"] = self.baseline.forward(b["obs"], b["avail"], b["dist_adjs"], b["channels"]).float()
+            else:
+                b["baselines"] = self.baseline.forward(b["obs"]).float()
         b["returns"], b["raw_adv"], b["adv"] = ppo_advantages(b["rewards"], b["baselines"], b["valids"], self.discount,
                                                               self.gae_lambda, self.center_adv, self.adv_eps)
         T = b["rewards"].shape[1]
@@ -256,6 +298,8 @@ class DevicePPO:
     # ---- losses ----------------------------------------------------------------------------------------------------
     def _dist(self, b, ids):
         sel = (lambda x: x) if ids is None else (lambda x: x[ids])
+        if not self._comm:
+            return self.policy.forward(sel(b["obs"]), sel(b["avail"]))
         d, _ = self.policy.forward(sel(b["obs"]), sel(b["avail"]), sel(b["dist_adjs"]), sel(b["channels"]))
         return d
 
@@ -298,7 +342,10 @@ class DevicePPO:
                 ids = torch.as_tensor(ids_all[start:min(start + step, P)], device=self.device)
                 self.baseline_opt.zero_grad()
                 self.opt.zero_grad()
-                bl = self.baseline.compute_loss(b["obs"][ids], b["returns"][ids], b["dist_adjs"][ids], b["channels"][ids])
+                if self._critic_comm:
+                    bl = self.baseline.compute_loss(b["obs"][ids], b["returns"][ids], b["dist_adjs"][ids], b["channels"][ids])
+                else:
+                    bl = self.baseline.compute_loss(b["obs"][ids], b["returns"][ids])
                 bl.backward()
                 loss = self.compute_loss(b, ids, old_ll)
                 loss.backward()

@@ -11,20 +11,25 @@ import torch
 import torch.distributed as dist
 
 from . import distributed as D
-from .ppo import CommBaseCritic, DevicePPO
+from .ppo import CommBaseCritic, DevicePPO, GaussianMLPBaseline
 from .rollout import RolloutEngine, make_policy
 from .spaces import Box, Discrete, EnvSpec
 
 
 class DeviceTrainer:
-    def __init__(self, spec, n_envs, device="cuda", env_id0=0, seed=1, **ppo_args):
+    def __init__(self, spec, n_envs, device="cuda", env_id0=0, seed=1, kind="comm", **ppo_args):
+        """kind: 'comm' / 'dec' (runner_*_comm.py / runner_*_obsDP.py:61: Comm-DP / Obs-DP policy + CommBaseCritic), 'cent'
+        (runner_*_cent.py:60-62: CENT policy + GaussianMLPBaseline(hidden_sizes=(64, 64, 64)))"""
         self.spec, self.device = spec, torch.device(device)
         n, Dobs = spec.n_agents, spec.obs_dim
         spec.max_path_length = spec.max_steps
         torch.manual_seed(seed)                              # identical initial weights on every rank
-        self.policy = make_policy(spec, device=self.device)
-        self.critic = CommBaseCritic(EnvSpec(Box(np.zeros(n * Dobs), np.ones(n * Dobs)), Discrete(5)), n,
-                                     n_gcn_layers=spec.n_layers, device=self.device)
+        self.policy = make_policy(spec, device=self.device, kind=kind)
+        env_spec = EnvSpec(Box(np.zeros(n * Dobs), np.ones(n * Dobs)), Discrete(5))
+        if kind != "cent":
+            self.critic = CommBaseCritic(env_spec, n, n_gcn_layers=spec.n_layers, device=self.device)
+        else:
+            self.critic = GaussianMLPBaseline(env_spec, hidden_sizes=(64, 64, 64), device=self.device)
         self.algo = DevicePPO(self.policy, self.critic, **ppo_args)
         # one chunk = one episode horizon: every env finishes at least one episode per round (time limit)
         self.engine = RolloutEngine(spec, self.policy, n_envs, device=self.device, env_id0=env_id0, ring=spec.max_steps,

@@ -31,8 +31,17 @@ def main():
     from com_marl.sampler import CentralizedMAOnPolicyVectorizedSampler
     from garage.torch.algos import compute_advantages
 
-    for case, (scenario, m, sen, den, cap, loss, T, n_paths) in dict(
-            pp=("pp", 10, 1, 0.04, 2, 0.3, 14, 7), co=("co", 10, 1, 0.03, 2, 0.0, 11, 6)).items():
+    from com_marl.torch.baselines.gaussian_mlp_baseline import GaussianMLPBaseline
+    from com_marl.torch.policies import CentralizedCategoricalMLPPolicy, DecCategoricalMLPPolicy
+    only = set(sys.argv[1:])
+    # kind: comm = runner_*_comm.py (Comm-DP + CommBaseCritic), dec = runner_*_obsDP.py:50-74 (Obs-DP + CommBaseCritic),
+    #       cent = runner_*_cent.py:48-63 (CENT + GaussianMLPBaseline(64, 64, 64))
+    for case, (scenario, m, sen, den, cap, loss, T, n_paths, kind) in dict(
+            pp=("pp", 10, 1, 0.04, 2, 0.3, 14, 7, "comm"), co=("co", 10, 1, 0.03, 2, 0.0, 11, 6, "comm"),
+            pp_dec=("pp", 10, 1, 0.04, 2, 0.3, 12, 6, "dec"), co_cent=("co", 10, 1, 0.03, 2, 0.0, 13, 7, "cent")).items():
+        if only and case not in only:
+            continue
+        comm = kind == "comm"
         seed = 5
         random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
         params = H.scenario_params(scenario, m, sen, den, cap=cap, loss=loss, max_env_steps=T)
@@ -43,8 +52,17 @@ def main():
         genv = ns.GarageEnv(env)
         n = env.n_agents
         torch.manual_seed(1)
-        policy = ns.CommCategoricalMLPPolicy(genv.spec, n_agents=n)
-        critic = CommBaseCritic(genv.spec, n_agents=n)
+        if kind == "comm":
+            policy = ns.CommCategoricalMLPPolicy(genv.spec, n_agents=n)
+        elif kind == "dec":
+            policy = DecCategoricalMLPPolicy(genv.spec, n_agents=n, hidden_sizes=(128, 64, 32))
+        else:
+            policy = CentralizedCategoricalMLPPolicy(genv.spec, n_agents=n, hidden_nonlinearity=torch.tanh,
+                                                     hidden_sizes=[128, 64, 32], name="centralized")
+        critic = GaussianMLPBaseline(env_spec=genv.spec, hidden_sizes=(64, 64, 64)) if kind == "cent" \
+            else CommBaseCritic(genv.spec, n_agents=n)
+        critic_comm = kind != "cent"
+        bl_loss = (lambda o, r, a, c: critic.compute_loss(o, r, a, c)) if critic_comm else (lambda o, r, a, c: critic.compute_loss(o, r))
         g = torch.Generator().manual_seed(seed)
         with torch.no_grad():       # non-zero biases (xavier init zeroes them)
             for mod in (policy, critic):
@@ -85,8 +103,11 @@ def main():
         with torch.no_grad():
             loss_before = algo._compute_loss(0, obs, avail, actions, rewards, valids, baselines, dist_adjs, channels)
             ent = algo._compute_policy_entropy(obs, avail, dist_adjs, channels)
-            ll = policy.log_likelihood(observations=obs, avail_actions=avail, dist_adj=dist_adjs, channels=channels, actions=actions)
-            bl_loss0 = critic.compute_loss(obs, returns, dist_adjs, channels)
+            if comm:
+                ll = policy.log_likelihood(observations=obs, avail_actions=avail, dist_adj=dist_adjs, channels=channels, actions=actions)
+            else:
+                ll = policy.log_likelihood(obs, avail, actions)
+            bl_loss0 = bl_loss(obs, returns, dist_adjs, channels)
         algo._compute_objective = orig
         raw_adv = compute_advantages(0.99, 0.97, algo.temp_max_path_length, baselines, rewards, "cpu")
         # ---- the optimisation loop of train_once (centralized_ma_ppo.py:207-262) ----
@@ -100,7 +121,7 @@ def main():
                 ids = shuffled_ids[start:min(start + step_size, len(rewards))]
                 loss = algo._compute_loss(0, obs[ids], avail[ids], actions[ids], rewards[ids], valids[ids], baselines[ids],
                                           dist_adjs[ids], channels[ids])
-                baseline_loss = critic.compute_loss(obs[ids], returns[ids], dist_adjs[ids], channels[ids])
+                baseline_loss = bl_loss(obs[ids], returns[ids], dist_adjs[ids], channels[ids])
                 algo._baseline_optimizer.zero_grad()
                 baseline_loss.backward()
                 algo._optimizer.zero_grad()
@@ -114,7 +135,7 @@ def main():
             kl = algo._compute_kl_constraint(obs, avail, dist_adjs, channels, actions)
         sd1 = {f"pol1::{k}": v.detach().numpy().copy() for k, v in policy.state_dict().items()}
         sd1.update({f"cri1::{k}": v.detach().numpy().copy() for k, v in critic.state_dict().items()})
-        meta = dict(case=case, scenario=scenario, n=n, D=int(obs.shape[-1] // n), L=2, n_paths=len(paths), T=T,
+        meta = dict(case=case, kind=kind, scenario=scenario, n=n, D=int(obs.shape[-1] // n), L=2, n_paths=len(paths), T=T,
                     Tmax=int(algo.temp_max_path_length), discount=0.99, gae_lambda=0.97, ent_coeff=0.1, clip=0.1, lr=3e-4,
                     adam_eps=1e-5, clip_grad_norm=7, n_minibatches=3, mini_epochs=2, map=m, sen=sen, den=den, cap=cap, loss=loss)
         np.savez_compressed(os.path.join(HERE, f"ppo_{case}.npz"), meta=np.array(json.dumps(meta, default=lambda o: float(o))),

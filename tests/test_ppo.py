@@ -1,6 +1,7 @@
 """PPO update against golden vectors recorded from the UNMODIFIED reference
 (tests/golden/make_golden_ppo.py: CentralizedMAPPO.process_samples / _compute_loss / the optimisation loop of train_once,
-CommBaseCritic, the reference's Adam)."""
+CommBaseCritic / GaussianMLPBaseline, the reference's Adam) for the three runner families: Comm-DP + CommBaseCritic (pp, co),
+Obs-DP + CommBaseCritic (pp_dec), CENT + GaussianMLPBaseline (co_cent)."""
 import json
 import os
 
@@ -10,7 +11,7 @@ import pytest
 from oracle import oracle as orc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CASES = ["pp", "co"]
+CASES = ["pp", "co", "pp_dec", "co_cent"]
 
 
 class PPOCase:
@@ -44,14 +45,15 @@ def test_oracle_advantages_match_reference(name):
 
 def _build(c, device="cuda"):
     import torch
-    from com_marl_b200.policy import CommCategoricalMLPPolicy
-    from com_marl_b200.ppo import CommBaseCritic, DevicePPO
+    from com_marl_b200.policy import CentralizedCategoricalMLPPolicy, CommCategoricalMLPPolicy, DecCategoricalMLPPolicy
+    from com_marl_b200.ppo import CommBaseCritic, DevicePPO, GaussianMLPBaseline
     from com_marl_b200.spaces import Box, Discrete, EnvSpec
     m = c.meta
-    n, D = int(m["n"]), int(m["D"])
+    n, D, kind = int(m["n"]), int(m["D"]), m.get("kind", "comm")
     spec = EnvSpec(Box(np.zeros(n * D), np.ones(n * D)), Discrete(5))
-    pol = CommCategoricalMLPPolicy(spec, n, device=device)
-    cri = CommBaseCritic(spec, n, device=device)
+    pol = {"comm": CommCategoricalMLPPolicy, "dec": DecCategoricalMLPPolicy, "cent": CentralizedCategoricalMLPPolicy}[kind](spec, n, device=device)
+    cri = GaussianMLPBaseline(spec, hidden_sizes=(64, 64, 64), device=device) if kind == "cent" else CommBaseCritic(spec, n, device=device)
+    assert set(cri.state_dict().keys()) == set(c.sd["cri0"].keys()) and set(pol.state_dict().keys()) == set(c.sd["pol0"].keys())
     pol.load_state_dict({k: torch.as_tensor(v) for k, v in c.sd["pol0"].items()})
     cri.load_state_dict({k: torch.as_tensor(v) for k, v in c.sd["cri0"].items()})       # reference checkpoints load as is
     algo = DevicePPO(pol, cri, discount=m["discount"], gae_lambda=m["gae_lambda"], policy_ent_coeff=m["ent_coeff"],
@@ -79,11 +81,12 @@ def test_process_samples_and_loss_match_reference(name):
     ret_o, raw_o, adv_o = orc.ppo_advantages(c.padded_rewards(), b["baselines"].cpu().numpy(), z["valids"], c.meta["discount"], c.meta["gae_lambda"])
     assert close(b["returns"], ret_o) and close(b["raw_adv"], raw_o) and close(b["adv"], adv_o, 2e-5)
     with torch.no_grad():
-        d, _ = pol.forward(b["obs"], b["avail"], b["dist_adjs"], b["channels"])
+        d = algo._dist(b, None)
         assert close(d.entropy().mean(-1), z["entropy"])
         assert close(d.log_prob(b["actions"]).sum(-1), z["loglik"])
         assert abs(float(algo.compute_loss(b)) - float(z["loss_before"])) <= 2e-5
-        bl0 = cri.compute_loss(b["obs"], b["returns"], b["dist_adjs"], b["channels"])
+        bl0 = cri.compute_loss(b["obs"], b["returns"], b["dist_adjs"], b["channels"]) if algo._critic_comm \
+            else cri.compute_loss(b["obs"], b["returns"])
         assert abs(float(bl0) - float(z["baseline_loss0"])) <= 1e-5 * max(1.0, abs(float(z["baseline_loss0"])))
 
 
@@ -114,7 +117,11 @@ def test_train_once_matches_reference(name):
     logits = torch.empty((8, n, 5), device="cuda")
     pol.act_device(obs, logits=logits, greedy=True)
     w = {k: v.cpu().numpy() for k, v in pol.state_dict().items()}
-    ref_logits, _, _ = orc.policy_forward(w, obs.cpu().numpy(), None, np.ones((8, n, n), np.uint8), np.ones((8, 2, n, n), np.uint8))
+    kind = c.meta.get("kind", "comm")
+    if kind == "comm":
+        ref_logits = orc.policy_forward(w, obs.cpu().numpy(), None, np.ones((8, n, n), np.uint8), np.ones((8, 2, n, n), np.uint8))[0]
+    else:
+        ref_logits = (orc.policy_forward_dec if kind == "dec" else orc.policy_forward_cent)(w, obs.cpu().numpy(), None)[0]
     assert np.abs(logits.cpu().numpy() - ref_logits).max() <= 1e-5 * max(1.0, np.abs(ref_logits).max())
 
 
@@ -197,6 +204,9 @@ def test_trainer_round_and_tabular_columns():
     spec = ScenarioSpec.from_params("co", params, seed=2)
     tr = DeviceTrainer(spec, 64, optimization_mini_epochs=1)
     out = tr.train_epoch()
+    for kind in ("dec", "cent"):            # the other two runner families run the same round
+        o2 = DeviceTrainer(spec, 64, optimization_mini_epochs=1, kind=kind).train_epoch()
+        assert np.isfinite(o2["loss_after"]) and o2["loss_after"] < o2["loss_before"] and o2["episode_stats"]["NumEpisodes"] == 64
     row = out["tabular"]
     for k in ("Iteration", "NumTrajs", "AverageDiscountedReturn", "AverageReturn", "SuccessRate", "AverageCaptureCount",
               "AverageStepCount", "AverageMovingCount", "AveragePenaltyCount", "AverageVariable", "AverageVar2", "StdReturn",
