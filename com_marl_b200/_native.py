@@ -18,7 +18,7 @@ POLICY_FLAG_RELU = 1
 MAX_AGENTS, MAX_GRID, MAX_LAYERS = 256, 64, 4
 
 EXPORTS = ("cm_abi_version", "cm_strerror", "cm_last_cuda_error", "cm_device_count", "cm_env_reset", "cm_env_step",
-           "cm_comm_update", "cm_policy_forward", "cm_policy_blob_floats", "cm_policy_cent_blob_floats", "cm_policy_workspace_bytes", "cm_policy_tc_blob_floats", "cm_policy_tc_prepare", "cm_mask_pack",
+           "cm_comm_update", "cm_policy_forward", "cm_policy_blob_floats", "cm_policy_cent_blob_floats", "cm_policy_cent_tc_blob_floats", "cm_policy_cent_workspace_bytes", "cm_policy_workspace_bytes", "cm_policy_tc_blob_floats", "cm_policy_tc_prepare", "cm_mask_pack",
            "cm_mask_unpack", "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host", "cm_ppo_advantages", "cm_adam_step")
 
 
@@ -92,6 +92,10 @@ def lib():
     L.cm_policy_blob_floats.argtypes = [C.c_int32, C.c_int32]
     L.cm_policy_cent_blob_floats.restype = C.c_size_t
     L.cm_policy_cent_blob_floats.argtypes = [C.c_int32, C.c_int32]
+    L.cm_policy_cent_tc_blob_floats.restype = C.c_size_t
+    L.cm_policy_cent_tc_blob_floats.argtypes = [C.c_int32, C.c_int32]
+    L.cm_policy_cent_workspace_bytes.restype = C.c_size_t
+    L.cm_policy_cent_workspace_bytes.argtypes = [C.c_int64]
     L.cm_policy_tc_blob_floats.restype = C.c_size_t
     L.cm_policy_tc_blob_floats.argtypes = [C.c_int32, C.c_int32]
     L.cm_policy_tc_prepare.restype = C.c_int

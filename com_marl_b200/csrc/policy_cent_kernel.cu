@@ -12,10 +12,23 @@
 // load, 3 loads per 32 FMAs.  The output layer is walked in passes of 16 agents (80 columns): a thread computes the five
 // logits of ONE agent for its four envs, so softmax / mask / sampling finish in registers (common.cuh::categorical_finish,
 // the same tail and random-stream specification as the Comm-DP / Obs-DP kernels).  Exact fp32 (FFMA, tanhf).
+//
+// math = 1: the first layer — the one real GEMM of the whole engine (M = envs, N = 128, K = n*D) — runs on the tcgen05 tensor
+// cores in its own kernel, policy_cent_l1_tc_kernel: a CTA owns 128 envs, accumulators for all 128 outputs live in tensor
+// memory (2 x 128 fp32 columns: hi*hi and the cross terms), K is walked in panels of 64 through a three-stage shared-memory
+// ring.  Per panel the CTA's 256 threads turn the fp32 observation block (the kernel's only HBM stream, next panel's loads in
+// flight in registers) into fp16 hi / lo operands in the canonical K-major core-matrix layout, one bulk async copy brings the
+// pre-split, pre-arranged [W1_hi ; W1_lo] panel (cm_policy_tc_prepare) and warp 0 issues 4 + 4 tcgen05.mma of K = 16
+// (A_hi x [B_hi ; B_lo] with N = 256, A_lo x B_hi with N = 128; error compensation x = hi + 2^-12 lo like policy_tc_kernel);
+// tcgen05.commit on the stage's mbarrier frees it for the panel three steps ahead, so conversion, copies and products of
+// neighbouring panels overlap.  The epilogue (acc0 + 2^-12 acc1 + b1, activation) writes h1 rows to the caller's workspace
+// and policy_cent_kernel<.., true> runs the remaining layers from there.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "common.cuh"
 #include "policy_layout.cuh"
+#include "tc_common.cuh"
 
 namespace cm {
 
@@ -124,7 +137,7 @@ __device__ __forceinline__ void cent_hidden(const float *__restrict__ in, int ld
     }
 }
 
-template <bool RELU>
+template <bool RELU, bool H1G>
 __global__ void __launch_bounds__(kCThreads, 2) policy_cent_kernel(const CentArgs A)
 {
     extern __shared__ __align__(16) float smem[];
@@ -141,8 +154,15 @@ __global__ void __launch_bounds__(kCThreads, 2) policy_cent_kernel(const CentArg
     const int64_t row0 = (int64_t)blockIdx.x * kCRows;
     const int rows = (int)min((int64_t)kCRows, io.n_envs - row0);
 
-    // ---- layer 1: h1 = act(obs W1 + b1), K streamed ----
-    {
+    // ---- layer 1: h1 = act(obs W1 + b1), K streamed — or the rows the tensor-core kernel left in the workspace ----
+    if (H1G) {
+        const float *__restrict__ src = A.io.workspace + row0 * kC1;
+        for (int e = tid; e < kCRows * kC1 / 4; e += kCThreads) {
+            const int r = e >> 5, c4 = e & 31;
+            const float4 v = r < rows ? __ldcg(reinterpret_cast<const float4 *>(src + (size_t)r * kC1 + c4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4 *>(h1 + r * kPH1 + c4 * 4) = v;
+        }
+    } else {
         float acc[4][8];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -235,12 +255,197 @@ __global__ void __launch_bounds__(kCThreads, 2) policy_cent_kernel(const CentArg
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// first layer on the tensor cores (math = 1)
+// ------------------------------------------------------------------------------------------------
+static constexpr int kL1Threads = 256, kL1Rows = 128, kL1KP = 64, kL1Stages = 3, kL1TmemCols = 256;
+static constexpr int kL1ABytes = kL1Rows * kL1KP * 2;                 // one of A_hi / A_lo: 16 KB
+static constexpr int kL1BBytes = 2 * kC1 * kL1KP * 2;                 // [B_hi ; B_lo] stacked along N: 32 KB
+static constexpr int kL1StageBytes = 2 * kL1ABytes + kL1BBytes;       // 64 KB
+static constexpr int kL1PanelHalves = 2 * kC1 * kL1KP;                // halves per prepared W1 panel
+static constexpr size_t kL1SmemBytes = (size_t)kL1Stages * kL1StageBytes + 128;
+
+struct CentL1Args {
+    const float *obs;
+    const __half *w1tc;
+    const float *b1;
+    float *h1;
+    int *error_flag;
+    int64_t n_envs;
+    int K, n_panels;
+};
+
+// W1 [K][128] fp32 -> per K panel of 64 the stacked [W1_hi ; W1_lo] (256 rows x 64 k) in the canonical K-major core-matrix layout
+__global__ void cent_l1_prepare_kernel(const float *__restrict__ w1, __half *__restrict__ out, int K, int n_panels)
+{
+    const int total = n_panels * kL1KP * kC1;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int p = e / (kL1KP * kC1), rem = e - p * (kL1KP * kC1), k = rem / kC1, r = rem - k * kC1;
+        const int kg = p * kL1KP + k;
+        const float v = kg < K ? w1[(size_t)kg * kC1 + r] : 0.0f;
+        const __half h = __float2half_rn(v);
+        const __half l = __float2half_rn((v - __half2float(h)) * 4096.0f);
+        auto idx = [&](int rr) { return (rr >> 3) * (kL1KP >> 3) * 64 + (k >> 3) * 64 + (rr & 7) * 8 + (k & 7); };
+        out[(size_t)p * kL1PanelHalves + idx(r)] = h;
+        out[(size_t)p * kL1PanelHalves + idx(kC1 + r)] = l;
+    }
+}
+
+// VEC: K is a multiple of 4 and the observation block is 16-byte aligned — 128-bit loads (a float4 is then either whole or absent)
+template <bool RELU, bool VEC>
+__global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const CentL1Args A)
+{
+    using namespace tc;
+    extern __shared__ __align__(1024) unsigned char l1smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(l1smem + (size_t)kL1Stages * kL1StageBytes);     // full[3], empty[3]
+    uint32_t *tmem_s = reinterpret_cast<uint32_t *>(bars + 2 * kL1Stages);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = A.K, NP = A.n_panels;
+    const int64_t row0 = (int64_t)blockIdx.x * kL1Rows;
+    const int rows = (int)min((int64_t)kL1Rows, A.n_envs - row0);
+
+    if (warp == 0) tmem_alloc(tmem_s, kL1TmemCols);
+    if (tid == 0) {
+        for (int i = 0; i < 2 * kL1Stages; ++i) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem = *tmem_s;
+    bool ok = true;
+
+    // work item j of a thread: 8 consecutive k (one 16-byte core-matrix row) of one tile row; consecutive lanes take
+    // consecutive rows of an 8-row group, so the 16-byte shared-memory stores of a quarter warp are contiguous
+    int it_row[4], it_grp[4];
+    uint32_t it_off[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int e = tid + kL1Threads * j, r8 = e & 7, grp = (e >> 3) & 7, rb = e >> 6;
+        it_row[j] = rb * 8 + r8;
+        it_grp[j] = grp;
+        it_off[j] = (uint32_t)(rb * (kL1KP >> 3) * 128 + grp * 128 + r8 * 16);
+    }
+    float raw[4][8];
+    auto fetch = [&](int p) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k0 = p * kL1KP + it_grp[j] * 8;
+            const bool rv = it_row[j] < rows;
+            const float *src = A.obs + (size_t)(row0 + (rv ? it_row[j] : 0)) * K + k0;
+            if (VEC) {
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 a = (rv && k0 < K) ? __ldg(reinterpret_cast<const float4 *>(src)) : z;
+                const float4 b = (rv && k0 + 4 < K) ? __ldg(reinterpret_cast<const float4 *>(src) + 1) : z;
+                raw[j][0] = a.x; raw[j][1] = a.y; raw[j][2] = a.z; raw[j][3] = a.w;
+                raw[j][4] = b.x; raw[j][5] = b.y; raw[j][6] = b.z; raw[j][7] = b.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) raw[j][i] = (rv && k0 + i < K) ? __ldg(src + i) : 0.0f;
+            }
+        }
+    };
+    auto stage = [&](int s) { return l1smem + (size_t)s * kL1StageBytes; };   // [A_hi | A_lo | B]
+    if (tid == 0) {
+        mbar_expect_tx(&bars[0], kL1BBytes);
+        bulk_g2s(stage(0) + 2 * kL1ABytes, A.w1tc, kL1BBytes, &bars[0]);
+    }
+    fetch(0);
+    const uint32_t idesc2 = make_idesc_f16(kL1Rows, 2 * kC1), idesc1 = make_idesc_f16(kL1Rows, kC1);
+    for (int p = 0; p < NP; ++p) {
+        const int s = p % kL1Stages;
+        // stage (p + 1) % 3 was last read by the products of panel p - 2: once they have completed it takes the next weight
+        // panel (and, one iteration later, the next operand tile)
+        if (p + 1 < NP) {
+            const int s1 = (p + 1) % kL1Stages, u1 = (p + 1) / kL1Stages;
+            if (u1 > 0) ok = mbar_wait(&bars[kL1Stages + s1], (uint32_t)(u1 - 1) & 1u) && ok;
+            if (tid == 0) {
+                mbar_expect_tx(&bars[s1], kL1BBytes);
+                bulk_g2s(stage(s1) + 2 * kL1ABytes, A.w1tc + (size_t)(p + 1) * kL1PanelHalves, kL1BBytes, &bars[s1]);
+            }
+        }
+        unsigned char *ah = stage(s), *al = ah + kL1ABytes;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float x = raw[j][2 * i], y = raw[j][2 * i + 1];
+                const __half2 hh = __floats2half2_rn(x, y);
+                const float2 hf = __half22float2(hh);
+                const __half2 ll = __floats2half2_rn((x - hf.x) * 4096.0f, (y - hf.y) * 4096.0f);
+                h[i] = *reinterpret_cast<const uint32_t *>(&hh);
+                l[i] = *reinterpret_cast<const uint32_t *>(&ll);
+            }
+            *reinterpret_cast<uint4 *>(ah + it_off[j]) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4 *>(al + it_off[j]) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        if (p + 1 < NP) fetch(p + 1);                           // in flight across the barrier and the issue below
+        fence_proxy_async();
+        fence_before_thread_sync();
+        __syncthreads();
+        if (warp == 0) {                                         // converged warp; the leader lane issues (tc_common.cuh)
+            fence_after_thread_sync();
+            const uint32_t leader = elect_one() ? 1u : 0u;
+            ok = mbar_wait(&bars[s], (uint32_t)(p / kL1Stages) & 1u) && ok;
+            const uint64_t da_hi = make_smem_desc16(smem_u32(ah), kL1KP, 0), da_lo = make_smem_desc16(smem_u32(al), kL1KP, 0);
+            const uint64_t db = make_smem_desc16(smem_u32(ah + 2 * kL1ABytes), kL1KP, 0);
+#pragma unroll
+            for (int j = 0; j < kL1KP / 16; ++j) mma_f16_pred(tmem, da_hi + 16 * j, db + 16 * j, idesc2, (p | j) ? 1u : 0u, leader);
+#pragma unroll
+            for (int j = 0; j < kL1KP / 16; ++j) mma_f16_pred(tmem + (uint32_t)kC1, da_lo + 16 * j, db + 16 * j, idesc1, 1u, leader);
+            mma_commit_pred(&bars[kL1Stages + s], leader);
+            __syncwarp();
+        }
+    }
+    // ---- epilogue: every product has completed when the last stage's commit arrives ----
+    ok = mbar_wait(&bars[kL1Stages + (NP - 1) % kL1Stages], (uint32_t)((NP - 1) / kL1Stages) & 1u) && ok;
+    fence_after_thread_sync();
+    {
+        const int quad = warp & 3, sub = warp >> 2, row = quad * 32 + lane;       // TMEM lane = tile row; two warps share a quadrant
+        const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 2
+        for (int c = 0; c < 64; c += 8) {
+            const int col = sub * 64 + c;
+            float v[8], w[8];
+            tmem_ld8(lane_addr + (uint32_t)col, v);
+            tmem_ld8(lane_addr + (uint32_t)(kC1 + col), w);
+            tmem_ld_wait();
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(A.b1 + col)), b1 = __ldg(reinterpret_cast<const float4 *>(A.b1 + col + 4));
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = cent_act<RELU>(fmaf(w[i], 1.0f / 4096.0f, v[i]) + bb[i]);
+            if (row < rows) {
+                float *dst = A.h1 + (size_t)(row0 + row) * kC1 + col;
+                *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        }
+    }
+    if (!ok && A.error_flag) atomicExch(A.error_flag, (int)CM_ECUDA);
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, kL1TmemCols);
+}
+
+template <typename Kern>
+static int cent_set_smem(Kern kern, size_t smem, bool &done)
+{
+    if (done) return CM_OK;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
+    done = true;
+    return CM_OK;
+}
+
 int launch_policy_cent(const cm_policy_desc *desc, const cm_policy_io *io, cudaStream_t stream)
 {
-    if (desc->math != 0) return CM_EUNSUPPORTED;                 // exact fp32 only
+    if (desc->math != 0 && desc->math != 1) return CM_EUNSUPPORTED;
     if (io->attention) return CM_EINVAL;                         // no communication, no attention weights
     if (io->n_envs == 0) return CM_OK;
     if (io->n_envs * desc->n_agents > (int64_t)1 << 30) return CM_EUNSUPPORTED;
+    const bool tcl1 = desc->math == 1;
+    if (tcl1 && (!io->tc_weights || !io->workspace || io->workspace_bytes < (size_t)io->n_envs * kC1 * sizeof(float))) return CM_EINVAL;
     CentArgs A;
     A.d = *desc;
     A.io = *io;
@@ -249,18 +454,53 @@ int launch_policy_cent(const cm_policy_desc *desc, const cm_policy_io *io, cudaS
     A.relu = desc->flags & CM_POLICY_FLAG_RELU;
     A.o = cent_blob_layout(desc->n_agents, desc->obs_dim);
     const size_t smem = kCentSmemFloats * sizeof(float);
-    static bool attr_set[64] = {};
+    static thread_local struct { int dev; bool set[8]; } cache = {-1, {false, false, false, false, false, false, false, false}};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ENODEVICE);
-    if (dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(policy_cent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_cent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
-        attr_set[dev] = true;
+    if (cache.dev != dev) { cache.dev = dev; for (bool &b : cache.set) b = false; }
+    int rc;
+    if (tcl1) {
+        CentL1Args L;
+        L.obs = io->obs;
+        L.w1tc = reinterpret_cast<const __half *>(io->tc_weights);
+        L.b1 = io->weights + A.o.b1;
+        L.h1 = io->workspace;
+        L.error_flag = io->error_flag;
+        L.n_envs = io->n_envs;
+        L.K = A.K;
+        L.n_panels = (A.K + kL1KP - 1) / kL1KP;
+        const unsigned grid1 = (unsigned)((io->n_envs + kL1Rows - 1) / kL1Rows);
+        const bool vec = (A.K & 3) == 0 && (reinterpret_cast<uintptr_t>(io->obs) & 15) == 0;
+        void (*k1)(const CentL1Args) = A.relu ? (vec ? policy_cent_l1_tc_kernel<true, true> : policy_cent_l1_tc_kernel<true, false>)
+                                              : (vec ? policy_cent_l1_tc_kernel<false, true> : policy_cent_l1_tc_kernel<false, false>);
+        if ((rc = cent_set_smem(k1, kL1SmemBytes, cache.set[4 + 2 * (A.relu ? 1 : 0) + (vec ? 1 : 0)]))) return rc;
+        k1<<<grid1, kL1Threads, kL1SmemBytes, stream>>>(L);
+        const cudaError_t e1 = cudaGetLastError();
+        if (e1 != cudaSuccess) return set_cuda_error(e1, CM_ECUDA);
     }
     const unsigned grid = (unsigned)((io->n_envs + kCRows - 1) / kCRows);
-    if (A.relu) policy_cent_kernel<true><<<grid, kCThreads, smem, stream>>>(A);
-    else policy_cent_kernel<false><<<grid, kCThreads, smem, stream>>>(A);
+    if (A.relu && tcl1) {
+        if ((rc = cent_set_smem(policy_cent_kernel<true, true>, smem, cache.set[0]))) return rc;
+        policy_cent_kernel<true, true><<<grid, kCThreads, smem, stream>>>(A);
+    } else if (A.relu) {
+        if ((rc = cent_set_smem(policy_cent_kernel<true, false>, smem, cache.set[1]))) return rc;
+        policy_cent_kernel<true, false><<<grid, kCThreads, smem, stream>>>(A);
+    } else if (tcl1) {
+        if ((rc = cent_set_smem(policy_cent_kernel<false, true>, smem, cache.set[2]))) return rc;
+        policy_cent_kernel<false, true><<<grid, kCThreads, smem, stream>>>(A);
+    } else {
+        if ((rc = cent_set_smem(policy_cent_kernel<false, false>, smem, cache.set[3]))) return rc;
+        policy_cent_kernel<false, false><<<grid, kCThreads, smem, stream>>>(A);
+    }
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? CM_OK : set_cuda_error(e, CM_ECUDA);
+}
+
+int cent_tc_prepare(const cm_policy_desc *desc, const float *weights, float *tc_weights, cudaStream_t stream)
+{
+    const int K = desc->n_agents * desc->obs_dim, NP = (K + kL1KP - 1) / kL1KP;
+    const CentBlob o = cent_blob_layout(desc->n_agents, desc->obs_dim);
+    cent_l1_prepare_kernel<<<256, 256, 0, stream>>>(weights + o.w1, reinterpret_cast<__half *>(tc_weights), K, NP);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? CM_OK : set_cuda_error(e, CM_ECUDA);
 }
@@ -272,3 +512,12 @@ extern "C" size_t cm_policy_cent_blob_floats(int32_t n_agents, int32_t obs_dim)
     if (n_agents < 1 || obs_dim < 1) return 0;
     return (size_t)cm::cent_blob_layout(n_agents, obs_dim).total;
 }
+
+extern "C" size_t cm_policy_cent_tc_blob_floats(int32_t n_agents, int32_t obs_dim)
+{
+    if (n_agents < 1 || obs_dim < 1) return 0;
+    const int NP = (n_agents * obs_dim + cm::kL1KP - 1) / cm::kL1KP;
+    return (size_t)NP * cm::kL1PanelHalves / 2;
+}
+
+extern "C" size_t cm_policy_cent_workspace_bytes(int64_t n_envs) { return n_envs > 0 ? (size_t)n_envs * cm::kC1 * sizeof(float) : 0; }

@@ -916,9 +916,16 @@ extern "C" size_t cm_policy_tc_blob_floats(int32_t obs_dim, int32_t n_layers)
     return (size_t)(cm::make_tc_plan(obs_dim, n_layers).total_halves + 1) / 2;
 }
 
+namespace cm { int cent_tc_prepare(const cm_policy_desc *desc, const float *weights, float *tc_weights, cudaStream_t stream); }   // policy_cent_kernel.cu
+
 extern "C" int cm_policy_tc_prepare(const cm_policy_desc *desc, const float *weights, float *tc_weights, cm_stream_t stream)
 {
     if (!desc || !weights || !tc_weights) return CM_EINVAL;
+    if (desc->kind == CM_POLICY_CENT) {
+        if (desc->n_agents < 1 || desc->n_agents > CM_MAX_AGENTS || desc->obs_dim < 1 || desc->obs_dim > 128) return CM_EUNSUPPORTED;
+        if (cm_device_count() < 1) return CM_ENODEVICE;
+        return cm::cent_tc_prepare(desc, weights, tc_weights, (cudaStream_t)stream);
+    }
     if (desc->n_layers < 1 || desc->n_layers > CM_MAX_LAYERS || desc->obs_dim < 1 || desc->obs_dim > 128) return CM_EUNSUPPORTED;
     if (cm_device_count() < 1) return CM_ENODEVICE;
     const cm::TcPlan P = cm::make_tc_plan(desc->obs_dim, desc->n_layers, cm::kTcModeComm);   // every mode reads this blob

@@ -524,7 +524,9 @@ class CentralizedCategoricalMLPPolicy(nn.Module):
     _kind = N.POLICY_CENT
 
     def __init__(self, env_spec, n_agents, hidden_sizes=(128, 64, 32), hidden_nonlinearity=torch.tanh,
-                 name="CentralizedCategoricalMLPPolicy", device="cuda", seed=1):
+                 name="CentralizedCategoricalMLPPolicy", device="cuda", seed=1, math="auto"):
+        """math: 'fp32' = every layer in exact fp32 on the CUDA cores; 'tc' = the first layer (K = n*D) on the tcgen05 tensor
+        cores with error-compensated fp16 operands (fp32-level accuracy); 'auto' = 'tc' from K = 512 inputs upwards."""
         super().__init__()
         if not hasattr(env_spec.action_space, "n"):
             raise AssertionError("Categorical policy only works with akro.Discrete action space.")
@@ -537,6 +539,8 @@ class CentralizedCategoricalMLPPolicy(nn.Module):
             self._relu = True
         else:
             raise NotImplementedError("hidden_nonlinearity must be tanh or relu (runner_*_cent.py:49)")
+        if math not in ("auto", "tc", "fp32"):
+            raise ValueError("math must be 'auto', 'tc' or 'fp32'")
         self.name, self.device = name, torch.device(device)
         self.centralized, self.vectorized, self.step = True, True, 0          # (no `comm` attribute: the sampler's switch)
         self._n_agents = int(n_agents)
@@ -544,19 +548,19 @@ class CentralizedCategoricalMLPPolicy(nn.Module):
         self._dec_obs_dim = self._obs_dim // self._n_agents
         self._action_dim = env_spec.action_space.n
         self.seed = int(seed)
+        self.math = ("tc" if self._obs_dim >= 512 else "fp32") if math == "auto" else math
         mlp = _MLP(self._obs_dim, tuple(hidden_sizes), self._action_dim * self._n_agents, output_tanh=False)
         self._layers, self._output_layers = mlp._layers, mlp._output_layers
         self.layers = [self]
         self.to(self.device)
-        self._blob = self._blob_sig = None
+        self._blob = self._blob_sig = self._tc_blob = self._tc_sig = self._tc_error = None
+        self._workspace = {}
 
     _signature = CommCategoricalMLPPolicy._signature
+    check_errors = CommCategoricalMLPPolicy.check_errors
 
     def uses_tensor_cores(self):
-        return False
-
-    def check_errors(self):
-        pass
+        return self.math == "tc"
 
     def weight_blob(self):
         """w1 [n*D][128] b1 w2 [128][64] b2 w3 [64][32] b3 w4 [32][5n] b4 (include/commarl_b200.h), rebuilt when a parameter changed"""
@@ -572,15 +576,42 @@ class CentralizedCategoricalMLPPolicy(nn.Module):
             self._blob, self._blob_sig = blob.contiguous(), sig
         return self._blob
 
+    def tc_weight_blob(self):
+        """[W1_hi ; W1_lo] per K panel of 64 in the tensor cores' operand layout (cm_policy_tc_prepare); rebuilt when a parameter changed"""
+        blob = self.weight_blob()
+        if self._tc_blob is None or self._tc_sig != self._blob_sig:
+            out = torch.empty(N.lib().cm_policy_cent_tc_blob_floats(self._n_agents, self._dec_obs_dim), dtype=torch.float32, device=self.device)
+            desc = N.PolicyDesc(self._n_agents, self._dec_obs_dim, 1, 0, 0, 1, self.seed, 0, self._kind, 0)
+            with torch.cuda.device(self.device):
+                N.check("cm_policy_tc_prepare", N.lib().cm_policy_tc_prepare(C.byref(desc), N.ptr(blob), N.ptr(out), N.stream_ptr()))
+            self._tc_blob, self._tc_sig = out, self._blob_sig
+            if self._tc_error is None:
+                self._tc_error = torch.zeros(1, dtype=torch.int32, device=self.device)
+        return self._tc_blob
+
     def act_device(self, obs, avail_bits=None, sample_u=None, tick=None, episode=None, greedy=False, probs=None, logits=None,
                    actions=None, env_id0=0, **_unused):
         """forward + sampling on device tensors (obs float32 (B, n, D) / (B, n*D)); no masks, no attention output.
-        Outputs are written into the given tensors; the call is CUDA-graph capturable."""
-        desc = N.PolicyDesc(self._n_agents, self._dec_obs_dim, 1, 0, int(greedy), 0, self.seed, env_id0, self._kind,
+        Outputs are written into the given tensors; the call is CUDA-graph capturable (with math = 'tc' after one eager call:
+        the first-layer scratch is allocated once per caller, keyed by (env_id0, B) — the rollout engine's env groups run on
+        parallel streams and must not share it)."""
+        tc = self.math == "tc"
+        B = obs.shape[0]
+        desc = N.PolicyDesc(self._n_agents, self._dec_obs_dim, 1, 0, int(greedy), int(tc), self.seed, env_id0, self._kind,
                             N.POLICY_FLAG_RELU if self._relu else 0)
         io = N.PolicyIO()
-        io.n_envs = obs.shape[0]
-        io.weights = N.ptr(self.weight_blob())
+        io.n_envs = B
+        if tc:
+            io.tc_weights = N.ptr(self.tc_weight_blob())          # (refreshes the fp32 blob as well)
+            io.error_flag = N.ptr(self._tc_error)
+            io.weights = N.ptr(self._blob)
+            ws = self._workspace.get((env_id0, B))
+            if ws is None:
+                ws = self._workspace[(env_id0, B)] = torch.empty(N.lib().cm_policy_cent_workspace_bytes(B) // 4, dtype=torch.float32,
+                                                                 device=self.device)
+            io.workspace, io.workspace_bytes = N.ptr(ws), ws.numel() * 4
+        else:
+            io.weights = N.ptr(self.weight_blob())
         for k, v in (("obs", obs), ("avail_bits", avail_bits), ("sample_u", sample_u), ("tick", tick), ("episode", episode),
                      ("probs", probs), ("logits", logits), ("actions", actions)):
             setattr(io, k, N.ptr(v))

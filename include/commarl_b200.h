@@ -164,7 +164,10 @@ typedef struct cm_policy_desc {
                                   MLP n*D -> 128 -> 64 -> 32 -> 5n over the concatenated observation of the team, softmax per
                                   agent; its own blob (cm_policy_cent_blob_floats):
                                     w1 [n*D][128] b1 [128] w2 [128][64] b2 [64] w3 [64][32] b3 [32] w4 [32][5n] b4 [5n]
-                                  exact fp32 (math = 0) only; n_layers / residual / masks / attention are not used */
+                                  math = 0: exact fp32; math = 1: the first layer (the one product whose K = n*D grows with the
+                                  team) on the tcgen05 tensor cores with error-compensated fp16 operands, needs io.tc_weights
+                                  (cm_policy_cent_tc_blob_floats, cm_policy_tc_prepare) and io.workspace
+                                  (cm_policy_cent_workspace_bytes); n_layers / residual / masks / attention are not used */
     int32_t flags;             /* CM_POLICY_FLAG_*; CENT only */
 } cm_policy_desc;
 
@@ -222,6 +225,10 @@ size_t cm_policy_blob_floats(int32_t obs_dim, int32_t n_layers);
 /* CENT: CentralizedCategoricalMLPPolicy.forward(get_actions=True) + sampling through the same cm_policy_forward call
  * (desc.kind = CM_POLICY_CENT; centralized_categorical_mlp_policy.py:61-117); length of its weight blob in floats */
 size_t cm_policy_cent_blob_floats(int32_t n_agents, int32_t obs_dim);
+/* CENT with math = 1: floats of the prepared first-layer operand (cm_policy_tc_prepare with desc.kind = CM_POLICY_CENT writes it)
+ * and bytes of scratch for the first layer's output rows */
+size_t cm_policy_cent_tc_blob_floats(int32_t n_agents, int32_t obs_dim);
+size_t cm_policy_cent_workspace_bytes(int64_t n_envs);
 /* tcgen05 variant: re-lays the fp32 weight blob out as pre-split fp16 ([B_hi ; B_lo] stacked) K-major core-matrix
  * panels, one per tensor-core product, so that the kernel fetches a layer's B operand with one bulk async copy */
 size_t cm_policy_tc_blob_floats(int32_t obs_dim, int32_t n_layers);

@@ -16,11 +16,11 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 CASES = sorted(os.path.basename(p)[8:-4] for p in glob.glob(os.path.join(GOLDEN, "centpol_*.npz")))
 
 
-def _policy(n, D, weights=None, seed=3, relu=False):
+def _policy(n, D, weights=None, seed=3, relu=False, math="auto"):
     from com_marl_b200.policy import CentralizedCategoricalMLPPolicy
     from com_marl_b200.spaces import Box, Discrete, EnvSpec
     pol = CentralizedCategoricalMLPPolicy(EnvSpec(Box(np.zeros(n * D), np.ones(n * D)), Discrete(5)), n, seed=seed,
-                                          hidden_nonlinearity=torch.relu if relu else torch.tanh)
+                                          hidden_nonlinearity=torch.relu if relu else torch.tanh, math=math)
     if weights is not None:
         pol.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()})
     return pol
@@ -30,18 +30,20 @@ def _bits(avail):
     return torch.from_numpy(((avail != 0) * np.array([1, 2, 4, 8, 16])).sum(-1).astype(np.uint8)).cuda()
 
 
+@pytest.mark.parametrize("math", ["fp32", "tc"])
 @pytest.mark.parametrize("name", CASES)
-def test_cent_policy_kernel_matches_reference_golden(name):
+def test_cent_policy_kernel_matches_reference_golden(name, math):
     z = np.load(os.path.join(GOLDEN, f"centpol_{name}.npz"))
     meta = json.loads(str(z["meta"]))
     n, D, B = meta["n"], meta["D"], meta["B"]
     w = {k[3:]: z[k] for k in z.files if k.startswith("w::")}
-    pol = _policy(n, D, w, relu=bool(meta["relu"]))
+    pol = _policy(n, D, w, relu=bool(meta["relu"]), math=math)
     assert set(pol.state_dict().keys()) == set(w.keys())            # reference checkpoints load as they are
     obs = torch.from_numpy(z["obs"]).cuda()
     probs = torch.empty((B, n, 5), device="cuda"); logits = torch.empty((B, n, 5), device="cuda")
     pol.act_device(obs, avail_bits=_bits(z["avail"].reshape(B, n, 5)), greedy=True, probs=probs, logits=logits,
                    actions=torch.empty((B, n), dtype=torch.int8, device="cuda"))
+    pol.check_errors()
     ref_logits = z["logits"].reshape(B, n, 5)
     assert np.abs(logits.cpu().numpy() - ref_logits).max() <= 1e-5 * max(1.0, np.abs(ref_logits).max())
     assert np.abs(probs.cpu().numpy() - z["probs"].reshape(B, n, 5)).max() <= 1e-5
@@ -55,9 +57,10 @@ def test_cent_policy_kernel_matches_reference_golden(name):
 
 @pytest.mark.parametrize("n,D,B,relu", [(3, 29, 16384, False), (4, 21, 5001, False), (32, 53, 2048, False), (54, 77, 777, True),
                                         (200, 53, 130, False), (256, 53, 65, False), (1, 5, 100, False), (17, 7, 63, True)])
-def test_cent_policy_kernel_matches_oracle_batched(n, D, B, relu):
+@pytest.mark.parametrize("math", ["fp32", "tc"])
+def test_cent_policy_kernel_matches_oracle_batched(n, D, B, relu, math):
     rng = np.random.default_rng(n * 1000 + D)
-    pol = _policy(n, D, relu=relu)
+    pol = _policy(n, D, relu=relu, math=math)
     with torch.no_grad():
         for k, v in pol.state_dict().items():
             if k.endswith("bias"):
@@ -70,6 +73,7 @@ def test_cent_policy_kernel_matches_oracle_batched(n, D, B, relu):
     actions = torch.empty((B, n), dtype=torch.int8, device="cuda")
     pol.act_device(torch.from_numpy(obs).cuda(), avail_bits=_bits(avail), sample_u=torch.from_numpy(u).cuda(), probs=probs,
                    logits=logits, actions=actions)
+    pol.check_errors()
     w = {k: v.cpu().numpy() for k, v in pol.state_dict().items()}
     ref_logits, ref_probs = orc.policy_forward_cent(w, obs, avail, relu=relu, dtype=np.float64)
     assert np.abs(logits.cpu().numpy() - ref_logits).max() <= 1e-5 * max(1.0, np.abs(ref_logits).max())
@@ -121,6 +125,8 @@ def test_cent_rollout_matches_oracle(scen):
     spec = ScenarioSpec.from_params(scen, params, seed=9)
     B = 300
     pol = make_policy(spec, kind="cent")
+    if scen == "pp":
+        pol.math = "tc"            # env groups on parallel streams, each with its own first-layer scratch
     eng = RolloutEngine(spec, pol, B, ring=6, use_graph=True, groups=3)
     oenv = orc.OracleVecEnv(orc.spec_from_params(scen, params, seed=9), B)
     eng.reset(); oenv.reset()
@@ -139,7 +145,7 @@ def test_cent_rollout_matches_oracle(scen):
 
 
 def test_cent_error_codes():
-    """C-ABI error behaviour of kind = CM_POLICY_CENT: exact fp32 only, no attention output"""
+    """C-ABI error behaviour of kind = CM_POLICY_CENT: math 0 / 1 only, math = 1 needs its operands, no attention output"""
     import ctypes as C
     from com_marl_b200 import _native as N
     n, D, B = 3, 29, 8
@@ -148,7 +154,7 @@ def test_cent_error_codes():
     probs = torch.empty((B, n, 5), device="cuda")
     io = N.PolicyIO()
     io.n_envs, io.weights, io.obs, io.probs = B, N.ptr(pol.weight_blob()), N.ptr(obs), N.ptr(probs)
-    for math, attn, expect in ((1, False, N.CM_EUNSUPPORTED), (0, True, N.CM_EINVAL), (0, False, N.CM_OK)):
+    for math, attn, expect in ((2, False, N.CM_EUNSUPPORTED), (1, False, N.CM_EINVAL), (0, True, N.CM_EINVAL), (0, False, N.CM_OK)):   # math = 1 without tc_weights / workspace
         desc = N.PolicyDesc(n, D, 1, 0, 1, math, 1, 0, N.POLICY_CENT, 0)
         io.attention = N.ptr(torch.empty((B, n, n), device="cuda")) if attn else None
         assert N.lib().cm_policy_forward(C.byref(desc), C.byref(io), N.stream_ptr()) == expect, (math, attn)

@@ -53,7 +53,7 @@ def main():
         print(json.dumps({"config": a.config, "kind": kind, "envs": B, "n_agents": n, "obs_dim": D,
                           "policy_ms_per_launch_whole_batch": round(ms_pol, 5), "rollout_ms_per_step": round(ms_step, 5),
                           "agent_steps_per_s": B * n / ms_step * 1e3,
-                          "cent_flop_per_agent": flop,
+                          "math": getattr(pol, "math", None), "cent_flop_per_agent": flop,
                           "cent_tflops": None if flop is None else flop * B * n / ms_pol / 1e9,
                           "obs_read_GBps": B * n * D * 4 / ms_pol / 1e6}), flush=True)
         del eng, pol
