@@ -25,6 +25,7 @@
 // and policy_cent_kernel<.., true> runs the remaining layers from there.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "policy_layout.cuh"
@@ -258,12 +259,18 @@ __global__ void __launch_bounds__(kCThreads, 2) policy_cent_kernel(const CentArg
 // ------------------------------------------------------------------------------------------------
 // first layer on the tensor cores (math = 1)
 // ------------------------------------------------------------------------------------------------
-static constexpr int kL1Threads = 256, kL1Rows = 128, kL1KP = 64, kL1Stages = 3, kL1TmemCols = 256;
-static constexpr int kL1ABytes = kL1Rows * kL1KP * 2;                 // one of A_hi / A_lo: 16 KB
-static constexpr int kL1BBytes = 2 * kC1 * kL1KP * 2;                 // [B_hi ; B_lo] stacked along N: 32 KB
-static constexpr int kL1StageBytes = 2 * kL1ABytes + kL1BBytes;       // 64 KB
+static constexpr int kL1Producers = 256, kL1Teams = 2, kL1Threads = kL1Teams * kL1Producers + 32;   // 2 teams of 8 operand-producer warps (even / odd panels) + 1 issuing warp
+static constexpr int kL1Rows = 128, kL1KP = 32, kL1TmemCols = 256;
+static constexpr int kL1RawStages = 6, kL1AStages = 3, kL1BStages = 5;         // ring depths: fp32 panels, A operands, weight panels
+static constexpr int kL1BAhead = 3;                                            // weight panels requested ahead of the one being multiplied
+static constexpr int kL1ABytes = kL1Rows * kL1KP * 2;                 // one of A_hi / A_lo: 8 KB
+static constexpr int kL1BBytes = 2 * kC1 * kL1KP * 2;                 // [B_hi ; B_lo] stacked along N: 16 KB
+static constexpr int kL1RawBytes = kL1Rows * kL1KP * 4;               // fp32 observation panel as it arrives: 16 KB
 static constexpr int kL1PanelHalves = 2 * kC1 * kL1KP;                // halves per prepared W1 panel
-static constexpr size_t kL1SmemBytes = (size_t)kL1Stages * kL1StageBytes + 128;
+static constexpr int kL1Groups = kL1KP / 8;                           // 8-column groups per row of a panel
+static constexpr int kL1Items = kL1Rows * kL1Groups / kL1Producers;   // (row, group) items per producer thread: 2
+static constexpr size_t kL1SmemBytes = (size_t)kL1AStages * 2 * kL1ABytes + (size_t)kL1BStages * kL1BBytes +
+                                       (size_t)kL1RawStages * kL1RawBytes + 256;                                   // 224 KB
 
 struct CentL1Args {
     const float *obs;
@@ -273,6 +280,7 @@ struct CentL1Args {
     int *error_flag;
     int64_t n_envs;
     int K, n_panels;
+    int debug;                    // CM_CENT_DEBUG (timing experiments only): 1 = weight panels in a per-CTA rotated order, 2 = no products, 4 = no observation copies, 8 = no conversion, 16 = always weight panel 0
 };
 
 // W1 [K][128] fp32 -> per K panel of 64 the stacked [W1_hi ; W1_lo] (256 rows x 64 k) in the canonical K-major core-matrix layout
@@ -291,22 +299,48 @@ __global__ void cent_l1_prepare_kernel(const float *__restrict__ w1, __half *__r
     }
 }
 
-// VEC: K is a multiple of 4 and the observation block is 16-byte aligned — 128-bit loads (a float4 is then either whole or absent)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+// VEC: K is a multiple of 4 and the observation block is 16-byte aligned — 16-byte copies (a chunk is then either whole or absent)
 template <bool RELU, bool VEC>
 __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const CentL1Args A)
 {
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char l1smem[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(l1smem + (size_t)kL1Stages * kL1StageBytes);     // full[3], empty[3]
-    uint32_t *tmem_s = reinterpret_cast<uint32_t *>(bars + 2 * kL1Stages);
+    unsigned char *abase = l1smem;                                                   // [3][A_hi | A_lo]
+    unsigned char *bbase = abase + (size_t)kL1AStages * 2 * kL1ABytes;               // [5][B_hi ; B_lo]
+    unsigned char *rawbase = bbase + (size_t)kL1BStages * kL1BBytes;                 // [6] fp32 panels
+    uint64_t *full_a = reinterpret_cast<uint64_t *>(rawbase + (size_t)kL1RawStages * kL1RawBytes);
+    uint64_t *empty_a = full_a + kL1AStages, *full_b = empty_a + kL1AStages, *empty_b = full_b + kL1BStages;
+    uint64_t *done_bar = empty_b + kL1BStages;                                       // all products of the tile have completed
+    uint32_t *tmem_s = reinterpret_cast<uint32_t *>(done_bar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = A.K, NP = A.n_panels;
     const int64_t row0 = (int64_t)blockIdx.x * kL1Rows;
     const int rows = (int)min((int64_t)kL1Rows, A.n_envs - row0);
+    constexpr int kIssuer = kL1Teams * kL1Producers / 32;                            // warp 16
+    const int team = warp >> 3, ptid = tid & (kL1Producers - 1);                     // producer team (panels team, team + 2, ...) and index inside it
 
-    if (warp == 0) tmem_alloc(tmem_s, kL1TmemCols);
+    if (warp == kIssuer) tmem_alloc(tmem_s, kL1TmemCols);
     if (tid == 0) {
-        for (int i = 0; i < 2 * kL1Stages; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < kL1AStages; ++i) { mbar_init(&full_a[i], kL1Producers / 32); mbar_init(&empty_a[i], 1); }
+        for (int i = 0; i < kL1BStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+        mbar_init(done_bar, 1);
         fence_mbar_init();
     }
     fence_before_thread_sync();
@@ -315,98 +349,138 @@ __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const 
     const uint32_t tmem = *tmem_s;
     bool ok = true;
 
-    // work item j of a thread: 8 consecutive k (one 16-byte core-matrix row) of one tile row; consecutive lanes take
-    // consecutive rows of an 8-row group, so the 16-byte shared-memory stores of a quarter warp are contiguous
-    int it_row[4], it_grp[4];
-    uint32_t it_off[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int e = tid + kL1Threads * j, r8 = e & 7, grp = (e >> 3) & 7, rb = e >> 6;
-        it_row[j] = rb * 8 + r8;
-        it_grp[j] = grp;
-        it_off[j] = (uint32_t)(rb * (kL1KP >> 3) * 128 + grp * 128 + r8 * 16);
-    }
-    float raw[4][8];
-    auto fetch = [&](int p) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k0 = p * kL1KP + it_grp[j] * 8;
-            const bool rv = it_row[j] < rows;
-            const float *src = A.obs + (size_t)(row0 + (rv ? it_row[j] : 0)) * K + k0;
-            if (VEC) {
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 a = (rv && k0 < K) ? __ldg(reinterpret_cast<const float4 *>(src)) : z;
-                const float4 b = (rv && k0 + 4 < K) ? __ldg(reinterpret_cast<const float4 *>(src) + 1) : z;
-                raw[j][0] = a.x; raw[j][1] = a.y; raw[j][2] = a.z; raw[j][3] = a.w;
-                raw[j][4] = b.x; raw[j][5] = b.y; raw[j][6] = b.z; raw[j][7] = b.w;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) raw[j][i] = (rv && k0 + i < K) ? __ldg(src + i) : 0.0f;
+    if (warp == kIssuer) {
+        // ================= issuing warp: weight panels (bulk async copies) and the products; never touches an operand =================
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        const uint32_t idesc2 = make_idesc_f16(kL1Rows, 2 * kC1), idesc1 = make_idesc_f16(kL1Rows, kC1);
+        auto load_b = [&](int q) {
+            const int qsrc = (A.debug & 1) ? (q + (int)blockIdx.x * 5) % NP : ((A.debug & 16) ? 0 : q);      // (timing experiments)
+            if (leader && (A.debug & 32)) mbar_arrive(&full_b[q % kL1BStages]);
+            else if (leader) {
+                mbar_expect_tx(&full_b[q % kL1BStages], kL1BBytes);
+                bulk_g2s(bbase + (size_t)(q % kL1BStages) * kL1BBytes, A.w1tc + (size_t)qsrc * kL1PanelHalves, kL1BBytes, &full_b[q % kL1BStages]);
             }
-        }
-    };
-    auto stage = [&](int s) { return l1smem + (size_t)s * kL1StageBytes; };   // [A_hi | A_lo | B]
-    if (tid == 0) {
-        mbar_expect_tx(&bars[0], kL1BBytes);
-        bulk_g2s(stage(0) + 2 * kL1ABytes, A.w1tc, kL1BBytes, &bars[0]);
-    }
-    fetch(0);
-    const uint32_t idesc2 = make_idesc_f16(kL1Rows, 2 * kC1), idesc1 = make_idesc_f16(kL1Rows, kC1);
-    for (int p = 0; p < NP; ++p) {
-        const int s = p % kL1Stages;
-        // stage (p + 1) % 3 was last read by the products of panel p - 2: once they have completed it takes the next weight
-        // panel (and, one iteration later, the next operand tile)
-        if (p + 1 < NP) {
-            const int s1 = (p + 1) % kL1Stages, u1 = (p + 1) / kL1Stages;
-            if (u1 > 0) ok = mbar_wait(&bars[kL1Stages + s1], (uint32_t)(u1 - 1) & 1u) && ok;
-            if (tid == 0) {
-                mbar_expect_tx(&bars[s1], kL1BBytes);
-                bulk_g2s(stage(s1) + 2 * kL1ABytes, A.w1tc + (size_t)(p + 1) * kL1PanelHalves, kL1BBytes, &bars[s1]);
-            }
-        }
-        unsigned char *ah = stage(s), *al = ah + kL1ABytes;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint32_t h[4], l[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float x = raw[j][2 * i], y = raw[j][2 * i + 1];
-                const __half2 hh = __floats2half2_rn(x, y);
-                const float2 hf = __half22float2(hh);
-                const __half2 ll = __floats2half2_rn((x - hf.x) * 4096.0f, (y - hf.y) * 4096.0f);
-                h[i] = *reinterpret_cast<const uint32_t *>(&hh);
-                l[i] = *reinterpret_cast<const uint32_t *>(&ll);
-            }
-            *reinterpret_cast<uint4 *>(ah + it_off[j]) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4 *>(al + it_off[j]) = make_uint4(l[0], l[1], l[2], l[3]);
-        }
-        if (p + 1 < NP) fetch(p + 1);                           // in flight across the barrier and the issue below
-        fence_proxy_async();
-        fence_before_thread_sync();
-        __syncthreads();
-        if (warp == 0) {                                         // converged warp; the leader lane issues (tc_common.cuh)
-            fence_after_thread_sync();
-            const uint32_t leader = elect_one() ? 1u : 0u;
-            ok = mbar_wait(&bars[s], (uint32_t)(p / kL1Stages) & 1u) && ok;
-            const uint64_t da_hi = make_smem_desc16(smem_u32(ah), kL1KP, 0), da_lo = make_smem_desc16(smem_u32(al), kL1KP, 0);
-            const uint64_t db = make_smem_desc16(smem_u32(ah + 2 * kL1ABytes), kL1KP, 0);
-#pragma unroll
-            for (int j = 0; j < kL1KP / 16; ++j) mma_f16_pred(tmem, da_hi + 16 * j, db + 16 * j, idesc2, (p | j) ? 1u : 0u, leader);
-#pragma unroll
-            for (int j = 0; j < kL1KP / 16; ++j) mma_f16_pred(tmem + (uint32_t)kC1, da_lo + 16 * j, db + 16 * j, idesc1, 1u, leader);
-            mma_commit_pred(&bars[kL1Stages + s], leader);
             __syncwarp();
+        };
+        for (int q = 0; q < kL1BAhead && q < NP; ++q) load_b(q);
+        for (int p = 0; p < NP; ++p) {
+            const int sa = p % kL1AStages, sb = p % kL1BStages;
+            ok = mbar_wait(&full_a[sa], (uint32_t)(p / kL1AStages) & 1u) && ok;      // the producers have written and fenced the operands
+            ok = mbar_wait(&full_b[sb], (uint32_t)(p / kL1BStages) & 1u) && ok;      // the weight panel has arrived
+            fence_after_thread_sync();
+            const uint32_t ah = smem_u32(abase + (size_t)sa * 2 * kL1ABytes), al = ah + kL1ABytes;
+            const uint64_t da_hi = make_smem_desc16(ah, kL1KP, 0), da_lo = make_smem_desc16(al, kL1KP, 0);
+            const uint64_t db = make_smem_desc16(smem_u32(bbase + (size_t)sb * kL1BBytes), kL1KP, 0);
+            const uint32_t issue = (A.debug & 2) ? 0u : leader;
+#pragma unroll
+            for (int j = 0; j < kL1KP / 16; ++j) mma_f16_pred(tmem, da_hi + 16 * j, db + 16 * j, idesc2, (p | j) ? 1u : 0u, issue);
+#pragma unroll
+            for (int j = 0; j < kL1KP / 16; ++j) mma_f16_pred(tmem + (uint32_t)kC1, da_lo + 16 * j, db + 16 * j, idesc1, 1u, issue);
+            mma_commit_pred(&empty_a[sa], leader);
+            mma_commit_pred(&empty_b[sb], leader);
+            if (p == NP - 1) mma_commit_pred(done_bar, leader);
+            __syncwarp();
+            // refill the weight ring: panel p + 3 goes where panel p - 2 was.  Its products were committed two iterations ago,
+            // so this wait does not stall the issue loop on the round trip of the newest commit (commit -> mbarrier -> poll is
+            // ~0.8 k cycles: waiting for panel p - 1 here capped the whole kernel at one panel per round trip)
+            const int q = p + kL1BAhead;
+            if (q < NP) {
+                const int prev = q - kL1BStages;                 // panel that used the slot before (p - 2)
+                if (prev >= 0) ok = mbar_wait(&empty_b[q % kL1BStages], (uint32_t)(prev / kL1BStages) & 1u) && ok;
+                load_b(q);
+            }
         }
-    }
-    // ---- epilogue: every product has completed when the last stage's commit arrives ----
-    ok = mbar_wait(&bars[kL1Stages + (NP - 1) % kL1Stages], (uint32_t)((NP - 1) / kL1Stages) & 1u) && ok;
-    fence_after_thread_sync();
-    {
-        const int quad = warp & 3, sub = warp >> 2, row = quad * 32 + lane;       // TMEM lane = tile row; two warps share a quadrant
+    } else {
+        // ================= producer warps: fp32 observations -> fp16 hi / lo operands in the canonical layout =================
+        // work item j of a thread: 8 consecutive k (one 16-byte core-matrix row of the fp16 operands, two 16-byte chunks of the
+        // fp32 panel) of one tile row.  Consecutive lanes take consecutive rows of an 8-row group: the 16-byte operand stores of
+        // a quarter warp are contiguous, and the fp32 panel is kept with its 16-byte chunks XOR-swizzled by the row
+        // (chunk ^ row % 8) so that the reads are conflict free as well.  A thread converts exactly the chunks it copied itself,
+        // so cp.async.wait_group is all the synchronisation the fp32 ring needs.
+        int it_row[kL1Items], it_grp[kL1Items];
+        uint32_t it_off[kL1Items];
+#pragma unroll
+        for (int j = 0; j < kL1Items; ++j) {
+            const int e = ptid + kL1Producers * j, r8 = e & 7, grp = (e >> 3) % kL1Groups, rb = e / (8 * kL1Groups);
+            it_row[j] = rb * 8 + r8;
+            it_grp[j] = grp;
+            it_off[j] = (uint32_t)(rb * kL1Groups * 128 + grp * 128 + r8 * 16);
+        }
+        const uint32_t raw_u32 = smem_u32(rawbase);
+        auto raw_chunk = [&](int j, int c) {    // byte offset of chunk c (0 / 1) of item j inside an fp32 panel
+            return (uint32_t)(it_row[j] * (kL1KP * 4) + (((2 * it_grp[j] + c) ^ (it_row[j] & 7)) << 4));
+        };
+        auto copy_panel = [&](int p) {          // this thread's share of observation panel p -> ring slot p % 6 (zero filled outside)
+            if (p < NP && !(A.debug & 4)) {
+                const uint32_t dst0 = raw_u32 + (uint32_t)((p % kL1RawStages) * kL1RawBytes);
+#pragma unroll
+                for (int j = 0; j < kL1Items; ++j) {
+                    const int k0 = p * kL1KP + it_grp[j] * 8;
+                    const bool rv = it_row[j] < rows;
+                    const float *src = A.obs + (size_t)(row0 + (rv ? it_row[j] : 0)) * K;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int kc = k0 + 4 * c;
+                        if (VEC) {
+                            const bool in = rv && kc < K;
+                            cp_async16(dst0 + raw_chunk(j, c), in ? src + kc : A.obs, in ? 16u : 0u);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const bool in = rv && kc + i < K;
+                                cp_async4(dst0 + raw_chunk(j, c) + 4 * i, in ? src + kc + i : A.obs, in ? 4u : 0u);
+                            }
+                        }
+                    }
+                }
+            }
+            cp_async_commit();                  // (an empty group when p >= NP keeps the group count uniform)
+        };
+        // a team converts every other panel, so a warp's chain (copy landed -> convert -> fence -> arrive) has two panel times
+        // to complete; each team keeps its current panel and the next two of its own in the fp32 ring (slots p % 6)
+        constexpr int kAhead = kL1RawStages / kL1Teams - 1;      // a team's own panels in flight beyond the current one
+#pragma unroll
+        for (int i = 0; i < kAhead; ++i) copy_panel(team + i * kL1Teams);
+        for (int p = team; p < NP; p += kL1Teams) {
+            const int sa = p % kL1AStages, ua = p / kL1AStages;
+            copy_panel(p + kAhead * kL1Teams);                   // kL1RawStages panels of observations in flight per CTA
+            cp_async_wait<kAhead>();                             // panel p has landed (this thread's chunks)
+            if (ua > 0) ok = mbar_wait(&empty_a[sa], (uint32_t)(ua - 1) & 1u) && ok;       // products of panel p - 3 are done with the stage
+            unsigned char *ah = abase + (size_t)sa * 2 * kL1ABytes, *al = ah + kL1ABytes;
+            const unsigned char *rawp = rawbase + (size_t)(p % kL1RawStages) * kL1RawBytes;
+#pragma unroll
+            for (int j = 0; j < kL1Items; ++j) {
+                if (A.debug & 8) break;
+                const float4 a = *reinterpret_cast<const float4 *>(rawp + raw_chunk(j, 0));
+                const float4 b = *reinterpret_cast<const float4 *>(rawp + raw_chunk(j, 1));
+                const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+                    const float2 hf = __half22float2(hh);
+                    const __half2 ll = __floats2half2_rn((x[2 * i] - hf.x) * 4096.0f, (x[2 * i + 1] - hf.y) * 4096.0f);
+                    h[i] = *reinterpret_cast<const uint32_t *>(&hh);
+                    l[i] = *reinterpret_cast<const uint32_t *>(&ll);
+                }
+                *reinterpret_cast<uint4 *>(ah + it_off[j]) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4 *>(al + it_off[j]) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+            if (!(A.debug & 64)) fence_proxy_async();            // generic-proxy stores -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_a[sa]);             // one arrival per warp: 256 per-thread arrivals serialise on the barrier word
+        }
+        cp_async_wait<0>();
+        // ---- epilogue: every product has completed when the commit behind the last panel arrives (a barrier of its own: a
+        // team that did not convert the last panel may be two phases behind on that panel's stage barrier, and a parity wait
+        // cannot tell two phases apart) ----
+        ok = mbar_wait(done_bar, 0u) && ok;
+        fence_after_thread_sync();
+        const int quad = warp & 3, sub = warp >> 2, row = quad * 32 + lane;       // TMEM lane = tile row; four warps share a quadrant
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 2
-        for (int c = 0; c < 64; c += 8) {
-            const int col = sub * 64 + c;
+        for (int c = 0; c < 32; c += 8) {
+            const int col = sub * 32 + c;
             float v[8], w[8];
             tmem_ld8(lane_addr + (uint32_t)col, v);
             tmem_ld8(lane_addr + (uint32_t)(kC1 + col), w);
@@ -425,7 +499,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const 
     if (!ok && A.error_flag) atomicExch(A.error_flag, (int)CM_ECUDA);
     fence_before_thread_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, kL1TmemCols);
+    if (warp == kIssuer) tmem_dealloc(tmem, kL1TmemCols);
 }
 
 template <typename Kern>
@@ -469,6 +543,8 @@ int launch_policy_cent(const cm_policy_desc *desc, const cm_policy_io *io, cudaS
         L.n_envs = io->n_envs;
         L.K = A.K;
         L.n_panels = (A.K + kL1KP - 1) / kL1KP;
+        static const int dbg = getenv("CM_CENT_DEBUG") ? atoi(getenv("CM_CENT_DEBUG")) : 0;
+        L.debug = dbg;
         const unsigned grid1 = (unsigned)((io->n_envs + kL1Rows - 1) / kL1Rows);
         const bool vec = (A.K & 3) == 0 && (reinterpret_cast<uintptr_t>(io->obs) & 15) == 0;
         void (*k1)(const CentL1Args) = A.relu ? (vec ? policy_cent_l1_tc_kernel<true, true> : policy_cent_l1_tc_kernel<true, false>)
