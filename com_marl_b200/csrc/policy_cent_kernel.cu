@@ -15,17 +15,16 @@
 //
 // math = 1: the first layer — the one real GEMM of the whole engine (M = envs, N = 128, K = n*D) — runs on the tcgen05 tensor
 // cores in its own kernel, policy_cent_l1_tc_kernel: a CTA owns 128 envs, accumulators for all 128 outputs live in tensor
-// memory (2 x 128 fp32 columns: hi*hi and the cross terms), K is walked in panels of 64 through a three-stage shared-memory
-// ring.  Per panel the CTA's 256 threads turn the fp32 observation block (the kernel's only HBM stream, next panel's loads in
-// flight in registers) into fp16 hi / lo operands in the canonical K-major core-matrix layout, one bulk async copy brings the
-// pre-split, pre-arranged [W1_hi ; W1_lo] panel (cm_policy_tc_prepare) and warp 0 issues 4 + 4 tcgen05.mma of K = 16
-// (A_hi x [B_hi ; B_lo] with N = 256, A_lo x B_hi with N = 128; error compensation x = hi + 2^-12 lo like policy_tc_kernel);
-// tcgen05.commit on the stage's mbarrier frees it for the panel three steps ahead, so conversion, copies and products of
-// neighbouring panels overlap.  The epilogue (acc0 + 2^-12 acc1 + b1, activation) writes h1 rows to the caller's workspace
-// and policy_cent_kernel<.., true> runs the remaining layers from there.
+// memory (2 x 128 fp32 columns: hi*hi and the cross terms), K is walked in panels of 32 by a warp-specialised pipeline with no
+// CTA barrier in the loop: two teams of 8 producer warps convert alternate panels (cp.async fp32 ring -> fp16 hi / lo operands
+// in the canonical K-major core-matrix layout -> fence -> one mbarrier arrival per warp) and request the pre-split,
+// pre-arranged [W1_hi ; W1_lo] panels (cm_policy_tc_prepare) with bulk async copies counted on the same barrier; one issuing
+// warp only waits, issues 2 + 2 tcgen05.mma of K = 16 (A_hi x [B_hi ; B_lo] with N = 256, A_lo x B_hi with N = 128; error
+// compensation x = hi + 2^-12 lo like policy_tc_kernel) and commits the stage's `empty` barrier.  The epilogue
+// (acc0 + 2^-12 acc1 + b1, activation) writes h1 rows to the caller's workspace and policy_cent_kernel<.., true> runs the
+// remaining layers from there.  Measurements and the experiments behind the structure: DESIGN.md 3.2.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "policy_layout.cuh"
@@ -261,16 +260,15 @@ __global__ void __launch_bounds__(kCThreads, 2) policy_cent_kernel(const CentArg
 // ------------------------------------------------------------------------------------------------
 static constexpr int kL1Producers = 256, kL1Teams = 2, kL1Threads = kL1Teams * kL1Producers + 32;   // 2 teams of 8 operand-producer warps (even / odd panels) + 1 issuing warp
 static constexpr int kL1Rows = 128, kL1KP = 32, kL1TmemCols = 256;
-static constexpr int kL1RawStages = 6, kL1AStages = 3, kL1BStages = 5;         // ring depths: fp32 panels, A operands, weight panels
-static constexpr int kL1BAhead = 3;                                            // weight panels requested ahead of the one being multiplied
+static constexpr int kL1RawStages = 6, kL1Stages = 4;                 // ring depths: fp32 panels, operand stages
 static constexpr int kL1ABytes = kL1Rows * kL1KP * 2;                 // one of A_hi / A_lo: 8 KB
 static constexpr int kL1BBytes = 2 * kC1 * kL1KP * 2;                 // [B_hi ; B_lo] stacked along N: 16 KB
+static constexpr int kL1StageBytes = 2 * kL1ABytes + kL1BBytes;       // operand stage [A_hi | A_lo | B]: 32 KB
 static constexpr int kL1RawBytes = kL1Rows * kL1KP * 4;               // fp32 observation panel as it arrives: 16 KB
 static constexpr int kL1PanelHalves = 2 * kC1 * kL1KP;                // halves per prepared W1 panel
 static constexpr int kL1Groups = kL1KP / 8;                           // 8-column groups per row of a panel
 static constexpr int kL1Items = kL1Rows * kL1Groups / kL1Producers;   // (row, group) items per producer thread: 2
-static constexpr size_t kL1SmemBytes = (size_t)kL1AStages * 2 * kL1ABytes + (size_t)kL1BStages * kL1BBytes +
-                                       (size_t)kL1RawStages * kL1RawBytes + 256;                                   // 224 KB
+static constexpr size_t kL1SmemBytes = (size_t)kL1Stages * kL1StageBytes + (size_t)kL1RawStages * kL1RawBytes + 256;   // 224 KB
 
 struct CentL1Args {
     const float *obs;
@@ -280,7 +278,6 @@ struct CentL1Args {
     int *error_flag;
     int64_t n_envs;
     int K, n_panels;
-    int debug;                    // CM_CENT_DEBUG (timing experiments only): 1 = weight panels in a per-CTA rotated order, 2 = no products, 4 = no observation copies, 8 = no conversion, 16 = always weight panel 0
 };
 
 // W1 [K][128] fp32 -> per K panel of 64 the stacked [W1_hi ; W1_lo] (256 rows x 64 k) in the canonical K-major core-matrix layout
@@ -322,12 +319,9 @@ __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const 
 {
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char l1smem[];
-    unsigned char *abase = l1smem;                                                   // [3][A_hi | A_lo]
-    unsigned char *bbase = abase + (size_t)kL1AStages * 2 * kL1ABytes;               // [5][B_hi ; B_lo]
-    unsigned char *rawbase = bbase + (size_t)kL1BStages * kL1BBytes;                 // [6] fp32 panels
-    uint64_t *full_a = reinterpret_cast<uint64_t *>(rawbase + (size_t)kL1RawStages * kL1RawBytes);
-    uint64_t *empty_a = full_a + kL1AStages, *full_b = empty_a + kL1AStages, *empty_b = full_b + kL1BStages;
-    uint64_t *done_bar = empty_b + kL1BStages;                                       // all products of the tile have completed
+    unsigned char *rawbase = l1smem + (size_t)kL1Stages * kL1StageBytes;             // [6] fp32 panels behind the [4] operand stages
+    uint64_t *full = reinterpret_cast<uint64_t *>(rawbase + (size_t)kL1RawStages * kL1RawBytes);
+    uint64_t *empty = full + kL1Stages, *done_bar = empty + kL1Stages;               // done: all products of the tile have completed
     uint32_t *tmem_s = reinterpret_cast<uint32_t *>(done_bar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = A.K, NP = A.n_panels;
@@ -338,8 +332,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const 
 
     if (warp == kIssuer) tmem_alloc(tmem_s, kL1TmemCols);
     if (tid == 0) {
-        for (int i = 0; i < kL1AStages; ++i) { mbar_init(&full_a[i], kL1Producers / 32); mbar_init(&empty_a[i], 1); }
-        for (int i = 0; i < kL1BStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+        // full[s]: one arrival per producer warp of the team that converted the panel + the expect_tx arrival of its weight copy
+        for (int i = 0; i < kL1Stages; ++i) { mbar_init(&full[i], kL1Producers / 32 + 1); mbar_init(&empty[i], 1); }
         mbar_init(done_bar, 1);
         fence_mbar_init();
     }
@@ -350,46 +344,28 @@ __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const 
     bool ok = true;
 
     if (warp == kIssuer) {
-        // ================= issuing warp: weight panels (bulk async copies) and the products; never touches an operand =================
+        // ================= issuing warp: nothing but wait -> 4 products -> commit per panel.  One warp's serial instruction
+        // stream is what paces the kernel (a wait, the descriptors, four predicated tcgen05.mma and a commit are ~0.4 k cycles),
+        // so everything else — weight copies included — lives in the producer teams =================
         const uint32_t leader = elect_one() ? 1u : 0u;
         const uint32_t idesc2 = make_idesc_f16(kL1Rows, 2 * kC1), idesc1 = make_idesc_f16(kL1Rows, kC1);
-        auto load_b = [&](int q) {
-            const int qsrc = (A.debug & 1) ? (q + (int)blockIdx.x * 5) % NP : ((A.debug & 16) ? 0 : q);      // (timing experiments)
-            if (leader && (A.debug & 32)) mbar_arrive(&full_b[q % kL1BStages]);
-            else if (leader) {
-                mbar_expect_tx(&full_b[q % kL1BStages], kL1BBytes);
-                bulk_g2s(bbase + (size_t)(q % kL1BStages) * kL1BBytes, A.w1tc + (size_t)qsrc * kL1PanelHalves, kL1BBytes, &full_b[q % kL1BStages]);
-            }
-            __syncwarp();
-        };
-        for (int q = 0; q < kL1BAhead && q < NP; ++q) load_b(q);
+        const uint64_t d0 = make_smem_desc16(smem_u32(l1smem), kL1KP, 0);            // stage 0, A_hi; the others are fixed 16-byte-unit offsets away
+        int s = 0;
+        uint32_t phase = 0;
         for (int p = 0; p < NP; ++p) {
-            const int sa = p % kL1AStages, sb = p % kL1BStages;
-            ok = mbar_wait(&full_a[sa], (uint32_t)(p / kL1AStages) & 1u) && ok;      // the producers have written and fenced the operands
-            ok = mbar_wait(&full_b[sb], (uint32_t)(p / kL1BStages) & 1u) && ok;      // the weight panel has arrived
+            ok = mbar_wait(&full[s], phase) && ok;               // operands converted and fenced, weight panel landed
             fence_after_thread_sync();
-            const uint32_t ah = smem_u32(abase + (size_t)sa * 2 * kL1ABytes), al = ah + kL1ABytes;
-            const uint64_t da_hi = make_smem_desc16(ah, kL1KP, 0), da_lo = make_smem_desc16(al, kL1KP, 0);
-            const uint64_t db = make_smem_desc16(smem_u32(bbase + (size_t)sb * kL1BBytes), kL1KP, 0);
-            const uint32_t issue = (A.debug & 2) ? 0u : leader;
+            const uint64_t da_hi = d0 + (uint64_t)((uint32_t)s * (kL1StageBytes >> 4));
+            const uint64_t da_lo = da_hi + (kL1ABytes >> 4), db = da_hi + (2 * kL1ABytes >> 4);
 #pragma unroll
-            for (int j = 0; j < kL1KP / 16; ++j) mma_f16_pred(tmem, da_hi + 16 * j, db + 16 * j, idesc2, (p | j) ? 1u : 0u, issue);
+            for (int j = 0; j < kL1KP / 16; ++j) mma_f16_pred(tmem, da_hi + 16 * j, db + 16 * j, idesc2, (p | j) ? 1u : 0u, leader);
 #pragma unroll
-            for (int j = 0; j < kL1KP / 16; ++j) mma_f16_pred(tmem + (uint32_t)kC1, da_lo + 16 * j, db + 16 * j, idesc1, 1u, issue);
-            mma_commit_pred(&empty_a[sa], leader);
-            mma_commit_pred(&empty_b[sb], leader);
-            if (p == NP - 1) mma_commit_pred(done_bar, leader);
-            __syncwarp();
-            // refill the weight ring: panel p + 3 goes where panel p - 2 was.  Its products were committed two iterations ago,
-            // so this wait does not stall the issue loop on the round trip of the newest commit (commit -> mbarrier -> poll is
-            // ~0.8 k cycles: waiting for panel p - 1 here capped the whole kernel at one panel per round trip)
-            const int q = p + kL1BAhead;
-            if (q < NP) {
-                const int prev = q - kL1BStages;                 // panel that used the slot before (p - 2)
-                if (prev >= 0) ok = mbar_wait(&empty_b[q % kL1BStages], (uint32_t)(prev / kL1BStages) & 1u) && ok;
-                load_b(q);
-            }
+            for (int j = 0; j < kL1KP / 16; ++j) mma_f16_pred(tmem + (uint32_t)kC1, da_lo + 16 * j, db + 16 * j, idesc1, 1u, leader);
+            mma_commit_pred(&empty[s], leader);
+            if (++s == kL1Stages) { s = 0; phase ^= 1u; }
         }
+        mma_commit_pred(done_bar, leader);
+        __syncwarp();
     } else {
         // ================= producer warps: fp32 observations -> fp16 hi / lo operands in the canonical layout =================
         // work item j of a thread: 8 consecutive k (one 16-byte core-matrix row of the fp16 operands, two 16-byte chunks of the
@@ -411,7 +387,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const 
             return (uint32_t)(it_row[j] * (kL1KP * 4) + (((2 * it_grp[j] + c) ^ (it_row[j] & 7)) << 4));
         };
         auto copy_panel = [&](int p) {          // this thread's share of observation panel p -> ring slot p % 6 (zero filled outside)
-            if (p < NP && !(A.debug & 4)) {
+            if (p < NP) {
                 const uint32_t dst0 = raw_u32 + (uint32_t)((p % kL1RawStages) * kL1RawBytes);
 #pragma unroll
                 for (int j = 0; j < kL1Items; ++j) {
@@ -437,20 +413,29 @@ __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const 
             cp_async_commit();                  // (an empty group when p >= NP keeps the group count uniform)
         };
         // a team converts every other panel, so a warp's chain (copy landed -> convert -> fence -> arrive) has two panel times
-        // to complete; each team keeps its current panel and the next two of its own in the fp32 ring (slots p % 6)
-        constexpr int kAhead = kL1RawStages / kL1Teams - 1;      // a team's own panels in flight beyond the current one
-#pragma unroll
-        for (int i = 0; i < kAhead; ++i) copy_panel(team + i * kL1Teams);
+        // to complete; it keeps its current panel and the next two of its own in the fp32 ring (slots p % 6).  Thread 0 of the
+        // team also requests the weight panel of the team's NEXT panel (bulk async copy into that panel's stage, completion
+        // counted on the stage's full barrier) as soon as the products that last read the stage have completed.
+        auto request_w = [&](int q) {           // one thread
+            if (q < NP) {
+                const int sq = q % kL1Stages, uq = q / kL1Stages;
+                if (uq > 0) ok = mbar_wait(&empty[sq], (uint32_t)(uq - 1) & 1u) && ok;
+                mbar_expect_tx(&full[sq], kL1BBytes);
+                bulk_g2s(l1smem + (size_t)sq * kL1StageBytes + 2 * kL1ABytes, A.w1tc + (size_t)q * kL1PanelHalves, kL1BBytes, &full[sq]);
+            }
+        };
+        copy_panel(team);
+        copy_panel(team + kL1Teams);
+        if (ptid == 0) request_w(team);
         for (int p = team; p < NP; p += kL1Teams) {
-            const int sa = p % kL1AStages, ua = p / kL1AStages;
-            copy_panel(p + kAhead * kL1Teams);                   // kL1RawStages panels of observations in flight per CTA
-            cp_async_wait<kAhead>();                             // panel p has landed (this thread's chunks)
-            if (ua > 0) ok = mbar_wait(&empty_a[sa], (uint32_t)(ua - 1) & 1u) && ok;       // products of panel p - 3 are done with the stage
-            unsigned char *ah = abase + (size_t)sa * 2 * kL1ABytes, *al = ah + kL1ABytes;
+            const int sa = p % kL1Stages, ua = p / kL1Stages;
+            copy_panel(p + 2 * kL1Teams);                        // six panels of observations in flight per CTA
+            cp_async_wait<2>();                                  // panel p has landed (this thread's chunks)
+            if (ua > 0) ok = mbar_wait(&empty[sa], (uint32_t)(ua - 1) & 1u) && ok;         // products of panel p - 4 are done with the stage
+            unsigned char *ah = l1smem + (size_t)sa * kL1StageBytes, *al = ah + kL1ABytes;
             const unsigned char *rawp = rawbase + (size_t)(p % kL1RawStages) * kL1RawBytes;
 #pragma unroll
             for (int j = 0; j < kL1Items; ++j) {
-                if (A.debug & 8) break;
                 const float4 a = *reinterpret_cast<const float4 *>(rawp + raw_chunk(j, 0));
                 const float4 b = *reinterpret_cast<const float4 *>(rawp + raw_chunk(j, 1));
                 const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -466,9 +451,10 @@ __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const 
                 *reinterpret_cast<uint4 *>(ah + it_off[j]) = make_uint4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<uint4 *>(al + it_off[j]) = make_uint4(l[0], l[1], l[2], l[3]);
             }
-            if (!(A.debug & 64)) fence_proxy_async();            // generic-proxy stores -> visible to the tensor core's async proxy
+            fence_proxy_async();                                 // generic-proxy stores -> visible to the tensor core's async proxy
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full_a[sa]);             // one arrival per warp: 256 per-thread arrivals serialise on the barrier word
+            if (lane == 0) mbar_arrive(&full[sa]);               // one arrival per warp
+            if (ptid == 0) request_w(p + kL1Teams);
         }
         cp_async_wait<0>();
         // ---- epilogue: every product has completed when the commit behind the last panel arrives (a barrier of its own: a
@@ -543,8 +529,6 @@ int launch_policy_cent(const cm_policy_desc *desc, const cm_policy_io *io, cudaS
         L.n_envs = io->n_envs;
         L.K = A.K;
         L.n_panels = (A.K + kL1KP - 1) / kL1KP;
-        static const int dbg = getenv("CM_CENT_DEBUG") ? atoi(getenv("CM_CENT_DEBUG")) : 0;
-        L.debug = dbg;
         const unsigned grid1 = (unsigned)((io->n_envs + kL1Rows - 1) / kL1Rows);
         const bool vec = (A.K & 3) == 0 && (reinterpret_cast<uintptr_t>(io->obs) & 15) == 0;
         void (*k1)(const CentL1Args) = A.relu ? (vec ? policy_cent_l1_tc_kernel<true, true> : policy_cent_l1_tc_kernel<true, false>)
