@@ -17,10 +17,10 @@
 // cores in its own kernel, policy_cent_l1_tc_kernel: a CTA owns 128 envs, accumulators for all 128 outputs live in tensor
 // memory (2 x 128 fp32 columns: hi*hi and the cross terms), K is walked in panels of 32 by a warp-specialised pipeline with no
 // CTA barrier in the loop: two teams of 8 producer warps convert alternate panels (cp.async fp32 ring -> fp16 hi / lo operands
-// in the canonical K-major core-matrix layout -> fence -> one mbarrier arrival per warp) and request the pre-split,
-// pre-arranged [W1_hi ; W1_lo] panels (cm_policy_tc_prepare) with bulk async copies counted on the same barrier; one issuing
+// in the canonical K-major core-matrix layout -> fence -> one mbarrier arrival per warp), a weight warp keeps a six-deep ring
+// of the pre-split, pre-arranged [W1_hi ; W1_lo] panels (cm_policy_tc_prepare) full with bulk async copies, and an issuing
 // warp only waits, issues 2 + 2 tcgen05.mma of K = 16 (A_hi x [B_hi ; B_lo] with N = 256, A_lo x B_hi with N = 128; error
-// compensation x = hi + 2^-12 lo like policy_tc_kernel) and commits the stage's `empty` barrier.  The epilogue
+// compensation x = hi + 2^-12 lo like policy_tc_kernel) and commits the stages' `empty` barriers.  The epilogue
 // (acc0 + 2^-12 acc1 + b1, activation) writes h1 rows to the caller's workspace and policy_cent_kernel<.., true> runs the
 // remaining layers from there.  Measurements and the experiments behind the structure: DESIGN.md 3.2.
 #include <cuda_fp16.h>
@@ -258,17 +258,17 @@ __global__ void __launch_bounds__(kCThreads, 2) policy_cent_kernel(const CentArg
 // ------------------------------------------------------------------------------------------------
 // first layer on the tensor cores (math = 1)
 // ------------------------------------------------------------------------------------------------
-static constexpr int kL1Producers = 256, kL1Teams = 2, kL1Threads = kL1Teams * kL1Producers + 32;   // 2 teams of 8 operand-producer warps (even / odd panels) + 1 issuing warp
+static constexpr int kL1Producers = 256, kL1Teams = 2, kL1Threads = kL1Teams * kL1Producers + 64;   // 2 teams of 8 operand-producer warps (even / odd panels) + issuing warp + weight warp
 static constexpr int kL1Rows = 128, kL1KP = 32, kL1TmemCols = 256;
-static constexpr int kL1RawStages = 6, kL1Stages = 4;                 // ring depths: fp32 panels, operand stages
+static constexpr int kL1RawStages = 6, kL1AStages = 2, kL1BStages = 6;         // ring depths: fp32 panels, A operands (one stage per team), weight panels
 static constexpr int kL1ABytes = kL1Rows * kL1KP * 2;                 // one of A_hi / A_lo: 8 KB
 static constexpr int kL1BBytes = 2 * kC1 * kL1KP * 2;                 // [B_hi ; B_lo] stacked along N: 16 KB
-static constexpr int kL1StageBytes = 2 * kL1ABytes + kL1BBytes;       // operand stage [A_hi | A_lo | B]: 32 KB
 static constexpr int kL1RawBytes = kL1Rows * kL1KP * 4;               // fp32 observation panel as it arrives: 16 KB
 static constexpr int kL1PanelHalves = 2 * kC1 * kL1KP;                // halves per prepared W1 panel
 static constexpr int kL1Groups = kL1KP / 8;                           // 8-column groups per row of a panel
 static constexpr int kL1Items = kL1Rows * kL1Groups / kL1Producers;   // (row, group) items per producer thread: 2
-static constexpr size_t kL1SmemBytes = (size_t)kL1Stages * kL1StageBytes + (size_t)kL1RawStages * kL1RawBytes + 256;   // 224 KB
+static constexpr size_t kL1SmemBytes = (size_t)kL1AStages * 2 * kL1ABytes + (size_t)kL1BStages * kL1BBytes +
+                                       (size_t)kL1RawStages * kL1RawBytes + 256;                                   // 224 KB
 
 struct CentL1Args {
     const float *obs;
@@ -319,21 +319,24 @@ __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const 
 {
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char l1smem[];
-    unsigned char *rawbase = l1smem + (size_t)kL1Stages * kL1StageBytes;             // [6] fp32 panels behind the [4] operand stages
-    uint64_t *full = reinterpret_cast<uint64_t *>(rawbase + (size_t)kL1RawStages * kL1RawBytes);
-    uint64_t *empty = full + kL1Stages, *done_bar = empty + kL1Stages;               // done: all products of the tile have completed
+    unsigned char *abase = l1smem;                                                   // [2][A_hi | A_lo]
+    unsigned char *bbase = abase + (size_t)kL1AStages * 2 * kL1ABytes;               // [6][B_hi ; B_lo]
+    unsigned char *rawbase = bbase + (size_t)kL1BStages * kL1BBytes;                 // [6] fp32 panels
+    uint64_t *full_a = reinterpret_cast<uint64_t *>(rawbase + (size_t)kL1RawStages * kL1RawBytes);
+    uint64_t *empty_a = full_a + kL1AStages, *full_b = empty_a + kL1AStages, *empty_b = full_b + kL1BStages;
+    uint64_t *done_bar = empty_b + kL1BStages;                                       // all products of the tile have completed
     uint32_t *tmem_s = reinterpret_cast<uint32_t *>(done_bar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = A.K, NP = A.n_panels;
     const int64_t row0 = (int64_t)blockIdx.x * kL1Rows;
     const int rows = (int)min((int64_t)kL1Rows, A.n_envs - row0);
-    constexpr int kIssuer = kL1Teams * kL1Producers / 32;                            // warp 16
+    constexpr int kIssuer = kL1Teams * kL1Producers / 32, kLoader = kIssuer + 1;     // warps 16, 17
     const int team = warp >> 3, ptid = tid & (kL1Producers - 1);                     // producer team (panels team, team + 2, ...) and index inside it
 
     if (warp == kIssuer) tmem_alloc(tmem_s, kL1TmemCols);
     if (tid == 0) {
-        // full[s]: one arrival per producer warp of the team that converted the panel + the expect_tx arrival of its weight copy
-        for (int i = 0; i < kL1Stages; ++i) { mbar_init(&full[i], kL1Producers / 32 + 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kL1AStages; ++i) { mbar_init(&full_a[i], kL1Producers / 32); mbar_init(&empty_a[i], 1); }
+        for (int i = 0; i < kL1BStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
         mbar_init(done_bar, 1);
         fence_mbar_init();
     }
@@ -343,26 +346,41 @@ __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const 
     const uint32_t tmem = *tmem_s;
     bool ok = true;
 
-    if (warp == kIssuer) {
-        // ================= issuing warp: nothing but wait -> 4 products -> commit per panel.  One warp's serial instruction
-        // stream is what paces the kernel (a wait, the descriptors, four predicated tcgen05.mma and a commit are ~0.4 k cycles),
-        // so everything else — weight copies included — lives in the producer teams =================
+    if (warp == kLoader) {
+        // ================= weight warp: keeps the six-deep weight ring full.  A 16 KB panel that every CTA of the launch asks
+        // for at about the same time takes ~2.5 k cycles to arrive, so the requests run up to six panels ahead of the products;
+        // a slot is re-requested as soon as the products that read it have completed =================
+        if (lane == 0) {
+            for (int q = 0; q < NP; ++q) {
+                const int sq = q % kL1BStages, uq = q / kL1BStages;
+                if (uq > 0) ok = mbar_wait(&empty_b[sq], (uint32_t)(uq - 1) & 1u) && ok;
+                mbar_expect_tx(&full_b[sq], kL1BBytes);
+                bulk_g2s(bbase + (size_t)sq * kL1BBytes, A.w1tc + (size_t)q * kL1PanelHalves, kL1BBytes, &full_b[sq]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == kIssuer) {
+        // ================= issuing warp: nothing but wait -> 4 products -> commit per panel (one warp's serial instruction
+        // stream paces the kernel, so everything else lives in the other warps) =================
         const uint32_t leader = elect_one() ? 1u : 0u;
         const uint32_t idesc2 = make_idesc_f16(kL1Rows, 2 * kC1), idesc1 = make_idesc_f16(kL1Rows, kC1);
-        const uint64_t d0 = make_smem_desc16(smem_u32(l1smem), kL1KP, 0);            // stage 0, A_hi; the others are fixed 16-byte-unit offsets away
-        int s = 0;
-        uint32_t phase = 0;
+        const uint64_t da0 = make_smem_desc16(smem_u32(abase), kL1KP, 0), db0 = make_smem_desc16(smem_u32(bbase), kL1KP, 0);
+        int sb = 0;
+        uint32_t phase_b = 0;
         for (int p = 0; p < NP; ++p) {
-            ok = mbar_wait(&full[s], phase) && ok;               // operands converted and fenced, weight panel landed
+            const int sa = p & 1;
+            ok = mbar_wait(&full_b[sb], phase_b) && ok;          // the weight panel has landed
+            ok = mbar_wait(&full_a[sa], (uint32_t)(p >> 1) & 1u) && ok;     // the operands are converted and fenced
             fence_after_thread_sync();
-            const uint64_t da_hi = d0 + (uint64_t)((uint32_t)s * (kL1StageBytes >> 4));
-            const uint64_t da_lo = da_hi + (kL1ABytes >> 4), db = da_hi + (2 * kL1ABytes >> 4);
+            const uint64_t da_hi = da0 + (uint64_t)((uint32_t)sa * (2 * kL1ABytes >> 4)), da_lo = da_hi + (kL1ABytes >> 4);
+            const uint64_t db = db0 + (uint64_t)((uint32_t)sb * (kL1BBytes >> 4));
 #pragma unroll
             for (int j = 0; j < kL1KP / 16; ++j) mma_f16_pred(tmem, da_hi + 16 * j, db + 16 * j, idesc2, (p | j) ? 1u : 0u, leader);
 #pragma unroll
             for (int j = 0; j < kL1KP / 16; ++j) mma_f16_pred(tmem + (uint32_t)kC1, da_lo + 16 * j, db + 16 * j, idesc1, 1u, leader);
-            mma_commit_pred(&empty[s], leader);
-            if (++s == kL1Stages) { s = 0; phase ^= 1u; }
+            mma_commit_pred(&empty_a[sa], leader);
+            mma_commit_pred(&empty_b[sb], leader);
+            if (++sb == kL1BStages) { sb = 0; phase_b ^= 1u; }
         }
         mma_commit_pred(done_bar, leader);
         __syncwarp();
@@ -412,27 +430,17 @@ __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const 
             }
             cp_async_commit();                  // (an empty group when p >= NP keeps the group count uniform)
         };
-        // a team converts every other panel, so a warp's chain (copy landed -> convert -> fence -> arrive) has two panel times
-        // to complete; it keeps its current panel and the next two of its own in the fp32 ring (slots p % 6).  Thread 0 of the
-        // team also requests the weight panel of the team's NEXT panel (bulk async copy into that panel's stage, completion
-        // counted on the stage's full barrier) as soon as the products that last read the stage have completed.
-        auto request_w = [&](int q) {           // one thread
-            if (q < NP) {
-                const int sq = q % kL1Stages, uq = q / kL1Stages;
-                if (uq > 0) ok = mbar_wait(&empty[sq], (uint32_t)(uq - 1) & 1u) && ok;
-                mbar_expect_tx(&full[sq], kL1BBytes);
-                bulk_g2s(l1smem + (size_t)sq * kL1StageBytes + 2 * kL1ABytes, A.w1tc + (size_t)q * kL1PanelHalves, kL1BBytes, &full[sq]);
-            }
-        };
+        // a team converts every other panel into its own operand stage, so a warp's chain (copy landed -> convert -> fence ->
+        // arrive) has two panel times to complete; it keeps its current panel and the next two of its own in the fp32 ring
         copy_panel(team);
         copy_panel(team + kL1Teams);
-        if (ptid == 0) request_w(team);
+        const int sa = team;
         for (int p = team; p < NP; p += kL1Teams) {
-            const int sa = p % kL1Stages, ua = p / kL1Stages;
+            const int ua = p >> 1;
             copy_panel(p + 2 * kL1Teams);                        // six panels of observations in flight per CTA
             cp_async_wait<2>();                                  // panel p has landed (this thread's chunks)
-            if (ua > 0) ok = mbar_wait(&empty[sa], (uint32_t)(ua - 1) & 1u) && ok;         // products of panel p - 4 are done with the stage
-            unsigned char *ah = l1smem + (size_t)sa * kL1StageBytes, *al = ah + kL1ABytes;
+            if (ua > 0) ok = mbar_wait(&empty_a[sa], (uint32_t)(ua - 1) & 1u) && ok;       // products of panel p - 2 are done with the stage
+            unsigned char *ah = abase + (size_t)sa * 2 * kL1ABytes, *al = ah + kL1ABytes;
             const unsigned char *rawp = rawbase + (size_t)(p % kL1RawStages) * kL1RawBytes;
 #pragma unroll
             for (int j = 0; j < kL1Items; ++j) {
@@ -453,8 +461,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const 
             }
             fence_proxy_async();                                 // generic-proxy stores -> visible to the tensor core's async proxy
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full[sa]);               // one arrival per warp
-            if (ptid == 0) request_w(p + kL1Teams);
+            if (lane == 0) mbar_arrive(&full_a[sa]);             // one arrival per warp
         }
         cp_async_wait<0>();
         // ---- epilogue: every product has completed when the commit behind the last panel arrives (a barrier of its own: a
