@@ -44,8 +44,17 @@ struct CentArgs {
     CentBlob o;
 };
 
-template <bool RELU>
-__device__ __forceinline__ float cent_act(float x) { return RELU ? fmaxf(x, 0.0f) : tanhf(x); }
+// tanh(x) = 1 - 2 / (2^(2 log2(e) x) + 1) through ex2.approx / rcp.approx (|error| ~3e-7, saturates correctly): the formulation
+// of the tensor-core kernels' epilogues, used on the math = 1 path; math = 0 keeps tanhf
+__device__ __forceinline__ float cent_tanh_fast(float x)
+{
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+template <bool RELU, bool FAST = false>
+__device__ __forceinline__ float cent_act(float x) { return RELU ? fmaxf(x, 0.0f) : (FAST ? cent_tanh_fast(x) : tanhf(x)); }
 
 // acc[4][4*J] += A[rows 4ty..][k0..k0+kc) * Bs[k][cols], Bs pitch = 64*J, kc a multiple of 4 (zero padded)
 template <int J>
@@ -78,7 +87,7 @@ __device__ __forceinline__ void cent_mac(const float *__restrict__ As, int lda, 
 }
 
 // out[row][col] = act(acc + bias[col]) for the thread's 4 x 4J block
-template <int J, bool RELU>
+template <int J, bool RELU, bool FAST = false>
 __device__ __forceinline__ void cent_store(float *__restrict__ out, int ldo, const float (&acc)[4][4 * J], const float *__restrict__ bias,
                                            int ty, int tx)
 {
@@ -88,10 +97,10 @@ __device__ __forceinline__ void cent_store(float *__restrict__ out, int ldo, con
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             float4 v;
-            v.x = cent_act<RELU>(acc[i][4 * j + 0] + bv.x);
-            v.y = cent_act<RELU>(acc[i][4 * j + 1] + bv.y);
-            v.z = cent_act<RELU>(acc[i][4 * j + 2] + bv.z);
-            v.w = cent_act<RELU>(acc[i][4 * j + 3] + bv.w);
+            v.x = cent_act<RELU, FAST>(acc[i][4 * j + 0] + bv.x);
+            v.y = cent_act<RELU, FAST>(acc[i][4 * j + 1] + bv.y);
+            v.z = cent_act<RELU, FAST>(acc[i][4 * j + 2] + bv.z);
+            v.w = cent_act<RELU, FAST>(acc[i][4 * j + 3] + bv.w);
             *reinterpret_cast<float4 *>(out + (ty * 4 + i) * ldo + j * 64 + tx * 4) = v;
         }
     }
@@ -99,7 +108,7 @@ __device__ __forceinline__ void cent_store(float *__restrict__ out, int ldo, con
 
 // hidden layer with its input already in shared memory: out = act(in[64][K] W[K][64*J] + b), W streamed in 32-row chunks.
 // (32-wide layer: J = 1 with the upper half of the 64 columns padded by zeros — W has only N = 32 real columns.)
-template <int J, bool RELU>
+template <int J, bool RELU, bool FAST>
 __device__ __forceinline__ void cent_hidden(const float *__restrict__ in, int ldi, int K, const float *__restrict__ W, int N,
                                             const float *__restrict__ bias, float *__restrict__ out, int ldo, float *__restrict__ Bch,
                                             int tid, int ty, int tx)
@@ -127,12 +136,12 @@ __device__ __forceinline__ void cent_hidden(const float *__restrict__ in, int ld
             for (int i = 0; i < 4; ++i) {
                 const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + tx * 4));
                 float4 v;
-                v.x = cent_act<RELU>(acc[i][0] + bv.x); v.y = cent_act<RELU>(acc[i][1] + bv.y);
-                v.z = cent_act<RELU>(acc[i][2] + bv.z); v.w = cent_act<RELU>(acc[i][3] + bv.w);
+                v.x = cent_act<RELU, FAST>(acc[i][0] + bv.x); v.y = cent_act<RELU, FAST>(acc[i][1] + bv.y);
+                v.z = cent_act<RELU, FAST>(acc[i][2] + bv.z); v.w = cent_act<RELU, FAST>(acc[i][3] + bv.w);
                 *reinterpret_cast<float4 *>(out + (ty * 4 + i) * ldo + tx * 4) = v;
             }
         } else {
-            cent_store<J, RELU>(out, ldo, acc, bias, ty, tx);
+            cent_store<J, RELU, FAST>(out, ldo, acc, bias, ty, tx);
         }
     }
 }
@@ -201,8 +210,8 @@ __global__ void __launch_bounds__(kCThreads, 2) policy_cent_kernel(const CentArg
         cent_store<2, RELU>(h1, kPH1, acc, wts + o.b1, ty, tx);
     }
     // ---- layers 2, 3 ----
-    cent_hidden<1, RELU>(h1, kPH1, kC1, wts + o.w2, kC2, wts + o.b2, h2, kPH2, Bch, tid, ty, tx);
-    cent_hidden<1, RELU>(h2, kPH2, kC2, wts + o.w3, kC3, wts + o.b3, h3, kPH3, Bch, tid, ty, tx);
+    cent_hidden<1, RELU, H1G>(h1, kPH1, kC1, wts + o.w2, kC2, wts + o.b2, h2, kPH2, Bch, tid, ty, tx);
+    cent_hidden<1, RELU, H1G>(h2, kPH2, kC2, wts + o.w3, kC3, wts + o.b3, h3, kPH3, Bch, tid, ty, tx);
     // ---- output layer in passes of 16 agents; thread = one agent x four envs ----
     const int NO = A.NO;
     for (int a0 = 0; a0 < n; a0 += kCAgentsPerPass) {
@@ -400,34 +409,45 @@ __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const 
             it_grp[j] = grp;
             it_off[j] = (uint32_t)(rb * kL1Groups * 128 + grp * 128 + r8 * 16);
         }
-        const uint32_t raw_u32 = smem_u32(rawbase);
         auto raw_chunk = [&](int j, int c) {    // byte offset of chunk c (0 / 1) of item j inside an fp32 panel
             return (uint32_t)(it_row[j] * (kL1KP * 4) + (((2 * it_grp[j] + c) ^ (it_row[j] & 7)) << 4));
         };
+        // everything a copy needs except the panel index is fixed per item and lives in registers: the global address of the
+        // item's first column, the number of columns left in its row from there (0 for a row outside the batch) and the
+        // shared-memory address of its two chunks in ring slot 0.  A chunk outside the matrix is a zero-fill copy (source size
+        // 0: nothing is read, so its address needs no clamping).
+        const float *it_src[kL1Items];
+        int it_left[kL1Items];
+        uint32_t it_dst[kL1Items][2];
+#pragma unroll
+        for (int j = 0; j < kL1Items; ++j) {
+            const bool rv = it_row[j] < rows;
+            it_src[j] = rv ? A.obs + (size_t)(row0 + it_row[j]) * K + it_grp[j] * 8 : A.obs;
+            it_left[j] = rv ? K - it_grp[j] * 8 : 0;
+            it_dst[j][0] = smem_u32(rawbase) + raw_chunk(j, 0);
+            it_dst[j][1] = smem_u32(rawbase) + raw_chunk(j, 1);
+        }
+        uint32_t copy_slot = (uint32_t)team * kL1RawBytes;      // ring slot of the team's next copy: p % 6 for p = team, team + 2, ...
         auto copy_panel = [&](int p) {          // this thread's share of observation panel p -> ring slot p % 6 (zero filled outside)
             if (p < NP) {
-                const uint32_t dst0 = raw_u32 + (uint32_t)((p % kL1RawStages) * kL1RawBytes);
+                const int kp = p * kL1KP;
 #pragma unroll
                 for (int j = 0; j < kL1Items; ++j) {
-                    const int k0 = p * kL1KP + it_grp[j] * 8;
-                    const bool rv = it_row[j] < rows;
-                    const float *src = A.obs + (size_t)(row0 + (rv ? it_row[j] : 0)) * K;
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
-                        const int kc = k0 + 4 * c;
+                        const int left = it_left[j] - kp - 4 * c;                   // columns of the row from this chunk on
+                        const uint32_t dst = it_dst[j][c] + copy_slot;
                         if (VEC) {
-                            const bool in = rv && kc < K;
-                            cp_async16(dst0 + raw_chunk(j, c), in ? src + kc : A.obs, in ? 16u : 0u);
+                            cp_async16(dst, it_src[j] + kp + 4 * c, left > 0 ? 16u : 0u);
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const bool in = rv && kc + i < K;
-                                cp_async4(dst0 + raw_chunk(j, c) + 4 * i, in ? src + kc + i : A.obs, in ? 4u : 0u);
-                            }
+                            for (int i = 0; i < 4; ++i) cp_async4(dst + 4 * i, it_src[j] + kp + 4 * c + i, left > i ? 4u : 0u);
                         }
                     }
                 }
             }
+            copy_slot += kL1Teams * kL1RawBytes;
+            if (copy_slot >= (uint32_t)kL1RawStages * kL1RawBytes) copy_slot -= (uint32_t)kL1RawStages * kL1RawBytes;
             cp_async_commit();                  // (an empty group when p >= NP keeps the group count uniform)
         };
         // a team converts every other panel into its own operand stage, so a warp's chain (copy landed -> convert -> fence ->
@@ -435,13 +455,16 @@ __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const 
         copy_panel(team);
         copy_panel(team + kL1Teams);
         const int sa = team;
+        uint32_t read_slot = (uint32_t)team * kL1RawBytes;
         for (int p = team; p < NP; p += kL1Teams) {
             const int ua = p >> 1;
             copy_panel(p + 2 * kL1Teams);                        // six panels of observations in flight per CTA
             cp_async_wait<2>();                                  // panel p has landed (this thread's chunks)
             if (ua > 0) ok = mbar_wait(&empty_a[sa], (uint32_t)(ua - 1) & 1u) && ok;       // products of panel p - 2 are done with the stage
             unsigned char *ah = abase + (size_t)sa * 2 * kL1ABytes, *al = ah + kL1ABytes;
-            const unsigned char *rawp = rawbase + (size_t)(p % kL1RawStages) * kL1RawBytes;
+            const unsigned char *rawp = rawbase + read_slot;
+            read_slot += kL1Teams * kL1RawBytes;
+            if (read_slot >= (uint32_t)kL1RawStages * kL1RawBytes) read_slot -= (uint32_t)kL1RawStages * kL1RawBytes;
 #pragma unroll
             for (int j = 0; j < kL1Items; ++j) {
                 const float4 a = *reinterpret_cast<const float4 *>(rawp + raw_chunk(j, 0));
@@ -481,7 +504,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) policy_cent_l1_tc_kernel(const 
             const float4 b0 = __ldg(reinterpret_cast<const float4 *>(A.b1 + col)), b1 = __ldg(reinterpret_cast<const float4 *>(A.b1 + col + 4));
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = cent_act<RELU>(fmaf(w[i], 1.0f / 4096.0f, v[i]) + bb[i]);
+            for (int i = 0; i < 8; ++i) v[i] = cent_act<RELU, true>(fmaf(w[i], 1.0f / 4096.0f, v[i]) + bb[i]);
             if (row < rows) {
                 float *dst = A.h1 + (size_t)(row0 + row) * kC1 + col;
                 *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
