@@ -366,7 +366,7 @@ def run_b200_arm(args):
 
     def pol_phase(h):
         pin = outs[h]["pinned"]            # host (pinned) buffers filled by the previous step of this half
-        a, _, ev = pol.get_actions_host(pin["obs"], pin["adj_bits"], pin["chan_bits"], slot=h, sync=False, stream=hstreams[h])
+        a, _, ev = pol.get_actions_host(pin["obs"], pin["adj_bits"], pin["chan_bits"], inputs_arena=True, slot=h, sync=False, stream=hstreams[h])
         return a, ev
 
     def env_phase(h, acts):

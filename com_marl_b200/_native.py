@@ -16,10 +16,12 @@ CH_FC, CH_FL, CH_IID, CH_GE = 0, 1, 2, 3
 POLICY_COMM, POLICY_DEC, POLICY_CENT = 0, 1, 2
 POLICY_FLAG_RELU = 1
 MAX_AGENTS, MAX_GRID, MAX_LAYERS = 256, 64, 4
+ABI_VERSION = 2
 
 EXPORTS = ("cm_abi_version", "cm_strerror", "cm_last_cuda_error", "cm_device_count", "cm_env_reset", "cm_env_step",
            "cm_comm_update", "cm_policy_forward", "cm_policy_blob_floats", "cm_policy_cent_blob_floats", "cm_policy_cent_tc_blob_floats", "cm_policy_cent_workspace_bytes", "cm_policy_workspace_bytes", "cm_policy_tc_blob_floats", "cm_policy_tc_prepare", "cm_mask_pack",
-           "cm_mask_unpack", "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host", "cm_ppo_advantages", "cm_adam_step")
+           "cm_mask_unpack", "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host", "cm_rollout_step_host", "cm_ppo_advantages",
+           "cm_adam_step")
 
 
 class EnvDesc(C.Structure):
@@ -44,7 +46,7 @@ class StepIO(C.Structure):
                 ("chan_planes", C.c_int32), ("auto_reset", C.c_int32), ("obs", C.c_void_p), ("reward", C.c_void_p),
                 ("done", C.c_void_p), ("counts", C.c_void_p), ("prey_alive_out", C.c_void_p),
                 ("success_out", C.c_void_p), ("adj_bits", C.c_void_p), ("chan_bits", C.c_void_p), ("ave_deg", C.c_void_p),
-                ("error_flag", C.c_void_p), ("stats", C.c_void_p)]
+                ("error_flag", C.c_void_p), ("stats", C.c_void_p), ("host_arena", C.c_int32)]
 
 
 class PolicyDesc(C.Structure):
@@ -58,7 +60,7 @@ class PolicyIO(C.Structure):
                [(k, C.c_void_p) for k in ("weights", "obs", "adj_bits", "chan_bits", "avail_bits", "sample_u", "tick",
                                           "episode", "probs", "logits", "attention", "actions", "tc_weights",
                                           "error_flag", "workspace")] + \
-               [("workspace_bytes", C.c_size_t)]
+               [("workspace_bytes", C.c_size_t), ("host_arena", C.c_int32)]
 
 
 class NativeError(RuntimeError):
@@ -107,14 +109,16 @@ def lib():
     L.cm_policy_forward_host.argtypes = [C.POINTER(PolicyDesc), C.POINTER(PolicyIO), C.POINTER(PolicyIO), C.c_int64, C.c_void_p]
     L.cm_env_step_host.argtypes = [C.POINTER(EnvDesc), C.POINTER(EnvState), C.POINTER(StepIO), C.POINTER(StepIO), C.c_void_p]
     L.cm_env_reset_host.argtypes = [C.POINTER(EnvDesc), C.POINTER(EnvState), C.POINTER(StepIO), C.POINTER(StepIO), C.c_void_p]
+    L.cm_rollout_step_host.argtypes = [C.POINTER(PolicyDesc), C.POINTER(PolicyIO), C.POINTER(PolicyIO), C.POINTER(EnvDesc),
+                                       C.POINTER(EnvState), C.POINTER(StepIO), C.POINTER(StepIO), C.c_void_p]
     L.cm_ppo_advantages.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int32,
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cm_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
                                C.c_float, C.c_int32, C.c_float, C.c_void_p]
     for fn in ("cm_env_reset", "cm_env_step", "cm_comm_update", "cm_policy_forward", "cm_mask_pack", "cm_mask_unpack",
-               "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host", "cm_ppo_advantages", "cm_adam_step"):
+               "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host", "cm_rollout_step_host", "cm_ppo_advantages", "cm_adam_step"):
         getattr(L, fn).restype = C.c_int
-    if L.cm_abi_version() != 1:
+    if L.cm_abi_version() != ABI_VERSION:
         raise ImportError("libcommarl_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -86,3 +86,22 @@ def allreduce_gradients(module: torch.nn.Module, group=None) -> int:
         g.copy_(flat[off:off + g.numel()].view_as(g))
         off += g.numel()
     return off
+
+
+def bind_to_gpu_numa(gpu_index: int) -> str:
+    """Pin this process (and the pinned host arenas it allocates afterwards: first touch) to the CPU cores NVML reports as
+    local to the GPU, so that a rank's host <-> device traffic stays on its own socket / memory controller when several
+    ranks share a box.  Returns a short description; a no-op when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cores = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = cores & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"cpus {min(allowed)}-{max(allowed)} ({len(allowed)} cores local to GPU {gpu_index})"
+        return "NVML affinity mask does not intersect the allowed cores: left unchanged"
+    except Exception as e:                       # NVML absent, container without the permission, ...
+        return f"unchanged ({type(e).__name__})"

@@ -192,6 +192,7 @@ class BatchedEnv:
         if getattr(self, "_hio", None) is None:
             pin = self._pinned()
             hio = N.StepIO()
+            hio.host_arena = 1          # the pinned outputs mirror the device output arena (_out_specs order / padding)
             hio.actions = pin["actions"].data_ptr()
             for k in self._HOST_OUT:
                 setattr(hio, "success_out" if k == "success" else k, pin[k].data_ptr())

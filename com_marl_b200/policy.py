@@ -23,6 +23,16 @@ from torch.distributions import Categorical
 from . import _native as N
 
 
+def _refresh_in_place(old, new):
+    """Kernel weight blobs live in PERSISTENT device buffers: a refresh after a parameter update writes the same
+    allocation, so device pointers baked into captured CUDA graphs (RolloutEngine) or cached call structs stay valid
+    and the next replay reads the current weights."""
+    if old is not None and old.numel() == new.numel() and old.device == new.device:
+        old.copy_(new)
+        return old
+    return new.contiguous()
+
+
 class _MLP(nn.Module):
     """Parameter layout of garage's MultiHeadedMLPModule with one head
     (garage/torch/modules/multi_headed_mlp_module.py:60-100): _layers.i.linear, _output_layers.0.linear."""
@@ -149,7 +159,8 @@ class CommCategoricalMLPPolicy(nn.Module):
             blob = torch.cat([p.detach().to(self.device, torch.float32).contiguous().reshape(-1) for p in parts])
             expect = N.lib().cm_policy_blob_floats(self._dec_obs_dim, L)
             assert blob.numel() == expect, (blob.numel(), expect)
-            self._blob, self._blob_sig = blob.contiguous(), sig
+            self._blob = _refresh_in_place(self._blob, blob)
+            self._blob_sig = sig
         return self._blob
 
     def uses_tensor_cores(self):
@@ -161,7 +172,8 @@ class CommCategoricalMLPPolicy(nn.Module):
         if self._tc_blob is None or self._tc_sig != self._blob_sig:
             L = self.n_gcn_layers
             n_floats = N.lib().cm_policy_tc_blob_floats(self._dec_obs_dim, L)
-            out = torch.empty(n_floats, dtype=torch.float32, device=self.device)
+            # written in place from the second time on: a captured CUDA graph keeps pointing at live, current weights
+            out = self._tc_blob if self._tc_blob is not None else torch.empty(n_floats, dtype=torch.float32, device=self.device)
             desc = N.PolicyDesc(self._n_agents, self._dec_obs_dim, L, int(self.residual), 0, 1, self.seed, 0, self._kind)
             with torch.cuda.device(self.device):
                 N.check("cm_policy_tc_prepare", N.lib().cm_policy_tc_prepare(C.byref(desc), N.ptr(blob), N.ptr(out), N.stream_ptr()))
@@ -169,6 +181,14 @@ class CommCategoricalMLPPolicy(nn.Module):
             if self._tc_error is None:
                 self._tc_error = torch.zeros(1, dtype=torch.int32, device=self.device)
         return self._tc_blob
+
+    def refresh_weights(self):
+        """bring the kernel weight blobs up to date with the parameters (in place; cheap signature check when nothing
+        changed) — the rollout engine calls this before replaying a captured graph"""
+        if self.uses_tensor_cores():
+            self.tc_weight_blob()
+        else:
+            self.weight_blob()
 
     def check_errors(self):
         if self._tc_error is not None and int(self._tc_error.item()):
@@ -251,7 +271,8 @@ class CommCategoricalMLPPolicy(nn.Module):
 
     _host_calls = 0
 
-    def get_actions_host(self, obs, adj_bits, chan_bits, greedy=False, return_pinned=False, slot=0, sync=True, stream=None):
+    def get_actions_host(self, obs, adj_bits, chan_bits, greedy=False, return_pinned=False, slot=0, sync=True, stream=None,
+                         inputs_arena=False):
         """Batched rollout call with HOST buffers and bit-row masks (what BatchedEnv.step_host returns): numpy obs
         (B, n, D) / (B, n*D), int32 bit rows in; numpy actions (B, n) int8 and probs (B, n, 5) out.  Pinned staging
         buffers are allocated once; inputs that already are pinned torch tensors (e.g. ``step_host(...)["pinned"]``) are
@@ -260,7 +281,10 @@ class CommCategoricalMLPPolicy(nn.Module):
         Split-phase use (``sync=False``): everything is enqueued on the CURRENT stream and the call returns
         ``(actions, probs, event)`` at once; the outputs are valid after ``event.synchronize()``.  ``slot`` selects an
         independent set of staging buffers, so that several env batches can be in flight on different streams (the
-        H2D copies of one batch then overlap the D2H copies of another: PCIe is full duplex)."""
+        H2D copies of one batch then overlap the D2H copies of another: PCIe is full duplex).
+        ``inputs_arena=True`` declares that pinned ``obs, adj_bits, chan_bits`` are neighbours in ONE host arena in this
+        order with 256-byte padding (``BatchedEnv.step_host(...)["pinned"]`` is): the library then moves them with a single
+        DMA transfer (cm_policy_io.host_arena); undeclared pinned inputs are copied one array at a time."""
         n, D, L, dev = self._n_agents, self._dec_obs_dim, self.n_gcn_layers, self.device
         B = obs.shape[0]
         stages = self.__dict__.setdefault("_stages", {})
@@ -297,6 +321,7 @@ class CommCategoricalMLPPolicy(nn.Module):
                     pinned_in = False
             # the same pinned tensors again (the env's persistent host buffers): nothing to re-derive next time
             st["last_in"] = (obs, adj_bits, chan_bits) if pinned_in else (None, None, None)
+            hio.host_arena = int((not pinned_in) or bool(inputs_arena))     # own staging arena, or declared by the caller
         sig = self._signature()
         cs = st.get("structs")
         if cs is None or cs[0] != (sig, bool(greedy)):
@@ -422,6 +447,7 @@ class DecCategoricalMLPPolicy(nn.Module):
 
     _signature = CommCategoricalMLPPolicy._signature
     tc_weight_blob = CommCategoricalMLPPolicy.tc_weight_blob
+    refresh_weights = CommCategoricalMLPPolicy.refresh_weights
     check_errors = CommCategoricalMLPPolicy.check_errors
     _act_device = CommCategoricalMLPPolicy.act_device
     _call_structs = CommCategoricalMLPPolicy._call_structs
@@ -443,7 +469,8 @@ class DecCategoricalMLPPolicy(nn.Module):
                      sd["_output_layers.0.linear.weight"].t(), sd["_output_layers.0.linear.bias"]]
             blob = torch.cat([p.detach().to(dev, torch.float32).contiguous().reshape(-1) for p in parts])
             assert blob.numel() == N.lib().cm_policy_blob_floats(self._dec_obs_dim, 1)
-            self._blob, self._blob_sig = blob.contiguous(), sig
+            self._blob = _refresh_in_place(self._blob, blob)
+            self._blob_sig = sig
         return self._blob
 
     def act_device(self, obs, avail_bits=None, sample_u=None, tick=None, episode=None, greedy=False, probs=None, logits=None,
@@ -557,6 +584,7 @@ class CentralizedCategoricalMLPPolicy(nn.Module):
         self._workspace = {}
 
     _signature = CommCategoricalMLPPolicy._signature
+    refresh_weights = CommCategoricalMLPPolicy.refresh_weights
     check_errors = CommCategoricalMLPPolicy.check_errors
 
     def uses_tensor_cores(self):
@@ -573,14 +601,16 @@ class CentralizedCategoricalMLPPolicy(nn.Module):
             parts += [sd["_output_layers.0.linear.weight"].t(), sd["_output_layers.0.linear.bias"]]
             blob = torch.cat([p.detach().to(self.device, torch.float32).contiguous().reshape(-1) for p in parts])
             assert blob.numel() == N.lib().cm_policy_cent_blob_floats(self._n_agents, self._dec_obs_dim)
-            self._blob, self._blob_sig = blob.contiguous(), sig
+            self._blob = _refresh_in_place(self._blob, blob)
+            self._blob_sig = sig
         return self._blob
 
     def tc_weight_blob(self):
         """[W1_hi ; W1_lo] per K panel of 64 in the tensor cores' operand layout (cm_policy_tc_prepare); rebuilt when a parameter changed"""
         blob = self.weight_blob()
         if self._tc_blob is None or self._tc_sig != self._blob_sig:
-            out = torch.empty(N.lib().cm_policy_cent_tc_blob_floats(self._n_agents, self._dec_obs_dim), dtype=torch.float32, device=self.device)
+            out = self._tc_blob if self._tc_blob is not None else \
+                torch.empty(N.lib().cm_policy_cent_tc_blob_floats(self._n_agents, self._dec_obs_dim), dtype=torch.float32, device=self.device)
             desc = N.PolicyDesc(self._n_agents, self._dec_obs_dim, 1, 0, 0, 1, self.seed, 0, self._kind, 0)
             with torch.cuda.device(self.device):
                 N.check("cm_policy_tc_prepare", N.lib().cm_policy_tc_prepare(C.byref(desc), N.ptr(blob), N.ptr(out), N.stream_ptr()))
@@ -595,6 +625,13 @@ class CentralizedCategoricalMLPPolicy(nn.Module):
         Outputs are written into the given tensors; the call is CUDA-graph capturable (with math = 'tc' after one eager call:
         the first-layer scratch is allocated once per caller, keyed by (env_id0, B) — the rollout engine's env groups run on
         parallel streams and must not share it)."""
+        desc, io = self._call_structs(obs, None, None, avail_bits, sample_u, tick, episode, greedy, probs, logits, None, actions, env_id0, 0)
+        with torch.cuda.device(self.device):
+            N.check("cm_policy_forward", N.lib().cm_policy_forward(C.byref(desc), C.byref(io), N.stream_ptr()))
+
+    def _call_structs(self, obs, adj_bits, chan_bits, avail_bits, sample_u, tick, episode, greedy, probs, logits, attention,
+                      actions, env_id0, ws_slot):
+        """descriptor + io struct of one cm_policy_forward call on device tensors (masks / attention do not exist for CENT)"""
         tc = self.math == "tc"
         B = obs.shape[0]
         desc = N.PolicyDesc(self._n_agents, self._dec_obs_dim, 1, 0, int(greedy), int(tc), self.seed, env_id0, self._kind,
@@ -615,8 +652,7 @@ class CentralizedCategoricalMLPPolicy(nn.Module):
         for k, v in (("obs", obs), ("avail_bits", avail_bits), ("sample_u", sample_u), ("tick", tick), ("episode", episode),
                      ("probs", probs), ("logits", logits), ("actions", actions)):
             setattr(io, k, N.ptr(v))
-        with torch.cuda.device(self.device):
-            N.check("cm_policy_forward", N.lib().cm_policy_forward(C.byref(desc), C.byref(io), N.stream_ptr()))
+        return desc, io
 
     # ---- reference call surface ----
     def forward(self, obs_n, avail_actions_n, get_actions=False):

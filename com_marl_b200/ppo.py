@@ -128,7 +128,9 @@ class FlatAdam:
         dev = self.params[0].device
         n = sum(p.numel() for p in self.params)
         self.flat = torch.empty(n, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        # gradient bucket + ONE extra slot that carries this rank's sample weight through the same all-reduce
+        self._bucket = torch.zeros(n + 1, dtype=torch.float32, device=dev)
+        self.grad = self._bucket[:n]
         o = 0
         for p in self.params:
             k = p.numel()
@@ -140,12 +142,19 @@ class FlatAdam:
         self.lr, self.betas, self.eps, self.steps = float(lr), betas, float(eps), 0
 
     def zero_grad(self):
-        self.grad.zero_()
+        self._bucket.zero_()
 
-    def all_reduce(self, group=None):
+    def all_reduce(self, group=None, weight=1.0):
+        """Data-parallel gradient of the UNION minibatch: every rank's gradient is the gradient of a mean over its own
+        `weight` samples (valid steps for the policy loss, batch elements for the baseline loss), so the union's gradient is
+        sum_r w_r g_r / sum_r w_r.  The weight travels in the bucket's extra slot: one collective per optimizer step.  A rank
+        whose slice is empty (weight 0, zero gradient) still takes part — the collective count is rank-invariant."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.grad, group=group)
-            self.grad.div_(dist.get_world_size(group))
+            w = float(weight)
+            self.grad.mul_(w)
+            self._bucket[-1] = w
+            dist.all_reduce(self._bucket, group=group)
+            self.grad.div_(self._bucket[-1].clamp_min(1e-30))
 
     def clip_coefficient(self, max_norm):
         """torch.nn.utils.clip_grad_norm_: min(1, max_norm / (||g|| + 1e-6)); returns (coefficient, norm) as 0-d tensors"""
@@ -186,6 +195,32 @@ def ppo_advantages(rewards, baselines, valids, discount, gae_lambda, center=True
     return out
 
 
+def _world(group=None):
+    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def global_max(value, device, group=None):
+    """max over ranks of a non-negative integer (no-op without a process group)"""
+    if _world(group) == 1:
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())
+
+
+def minibatch_plan(P, n_minibatches, device="cpu", group=None):
+    """[(start, stop)] slices of the shuffled path ids, one per optimizer step of a mini-epoch.  A single process cuts exactly
+    like the reference (centralized_ma_ppo.py:236-241: step = ceil(P / n_minibatches), range(0, P, step)).  With several ranks
+    the local path counts differ, and so would the slice counts (P = 4 gives 2 slices, P = 5 gives 3): every optimizer step
+    issues collectives, so the count must not depend on the rank — it is the maximum over ranks, and a rank that has run out of
+    paths appends EMPTY slices (zero gradient, weight 0) and still takes part in the all-reduces."""
+    P = int(P)
+    step = int(np.ceil(P / n_minibatches)) if P > 0 else 1
+    plan = [(s0, min(s0 + step, P)) for s0 in range(0, P, step)]
+    n_it = global_max(len(plan), device, group)
+    return plan + [(P, P)] * (n_it - len(plan))
+
+
 class DevicePPO:
     """CentralizedMAPPO's update (centralized_ma_ppo.py) on one GPU per rank, for the three runner families: a Comm-DP or Obs-DP
     policy with CommBaseCritic (runner_*_comm.py, runner_*_obsDP.py:61), or a CENT policy with GaussianMLPBaseline.  Like the reference, the policy call takes the
@@ -218,7 +253,7 @@ class DevicePPO:
         """paths: the sampler's list of dicts (…vectorized_sampler.py:192-224).  Returns a dict of device tensors padded to
         the longest path like the reference, plus baselines / returns / advantages."""
         dev, n = self.device, self.policy._n_agents
-        P, Tmax = len(paths), max(len(p["rewards"]) for p in paths)
+        P, Tmax = len(paths), global_max(max(len(p["rewards"]) for p in paths), dev, self.group)
 
         def pad(key, dtype, fill):
             first = np.asarray(paths[0][key])
@@ -246,7 +281,7 @@ class DevicePPO:
         nth = done.cumsum(0) - done                          # episodes finished before step k in env b = index of k's episode
         fin = done.sum(0)                                    # finished episodes per env
         P = int(fin.sum())
-        if P == 0:
+        if global_max(P, dev, self.group) == 0:              # (collective: a single rank must not bail out alone)
             raise ValueError("no episode finished inside the recorded trajectory")
         valid = nth < fin[None, :]                           # step belongs to an episode that finishes inside the window
         off = fin.cumsum(0) - fin                            # first path id of env b
@@ -259,7 +294,9 @@ class DevicePPO:
         ends = done.bool() & valid
         valids = torch.zeros(P, dtype=torch.int64, device=dev)
         valids.index_put_((pid[ends],), t_in[ends] + 1)
-        Tmax = int(valids.max())
+        # every rank pads to the job-wide longest path: the baseline loss is a mean over the PADDED batch like the
+        # reference's, so the union batch of all ranks is only reproduced when the padding agrees
+        Tmax = global_max(int(valids.max()) if P else 0, dev, self.group)
         src = torch.full((P * Tmax,), -1, dtype=torch.int64, device=dev)
         flat = (ks * B + torch.arange(B, device=dev)[None, :])
         src.index_put_(((pid * Tmax + t_in)[valid],), flat[valid])
@@ -335,22 +372,28 @@ class DevicePPO:
             old_ll = d0.log_prob(b["actions"]).sum(-1)              # the frozen old policy (:204) evaluated once
             loss_before = float(self.compute_loss(b, None, old_ll))
         ids_all = np.random.permutation(P) if shuffled_ids is None else np.asarray(shuffled_ids)
-        step = int(np.ceil(P / self.n_minibatches))
+        plan = minibatch_plan(P, self.n_minibatches, self.device, self.group)
+        T = int(b["rewards"].shape[1])
         losses, bl_losses, gnorms = [], [], []
         for _ in range(self.mini_epochs):
-            for start in range(0, P, step):
-                ids = torch.as_tensor(ids_all[start:min(start + step, P)], device=self.device)
+            for start, stop in plan:
                 self.baseline_opt.zero_grad()
                 self.opt.zero_grad()
-                if self._critic_comm:
-                    bl = self.baseline.compute_loss(b["obs"][ids], b["returns"][ids], b["dist_adjs"][ids], b["channels"][ids])
-                else:
-                    bl = self.baseline.compute_loss(b["obs"][ids], b["returns"][ids])
-                bl.backward()
-                loss = self.compute_loss(b, ids, old_ll)
-                loss.backward()
-                self.opt.all_reduce(self.group)
-                self.baseline_opt.all_reduce(self.group)
+                w_pol = w_bl = 0.0
+                loss = bl = None
+                if stop > start:
+                    ids = torch.as_tensor(ids_all[start:stop], device=self.device)
+                    if self._critic_comm:
+                        bl = self.baseline.compute_loss(b["obs"][ids], b["returns"][ids], b["dist_adjs"][ids], b["channels"][ids])
+                    else:
+                        bl = self.baseline.compute_loss(b["obs"][ids], b["returns"][ids])
+                    bl.backward()
+                    loss = self.compute_loss(b, ids, old_ll)
+                    loss.backward()
+                    if _world(self.group) > 1:
+                        w_pol, w_bl = float(b["mask"][ids].sum()), float((stop - start) * T)
+                self.opt.all_reduce(self.group, w_pol)
+                self.baseline_opt.all_reduce(self.group, w_bl)
                 scale = 1.0
                 if self.clip_grad_norm is not None:
                     coef, norm = self.opt.clip_coefficient(self.clip_grad_norm)
@@ -358,7 +401,8 @@ class DevicePPO:
                     gnorms.append(float(norm) * scale)             # policy.grad_norm() after clipping (:254-255)
                 self.opt.step(scale)
                 self.baseline_opt.step(1.0)
-                losses.append(float(loss.detach())); bl_losses.append(float(bl.detach()))
+                losses.append(float(loss.detach()) if loss is not None else float("nan"))
+                bl_losses.append(float(bl.detach()) if bl is not None else float("nan"))
         with torch.no_grad():
             loss_after = float(self.compute_loss(b, None, old_ll))
             kl = float(self.kl(b, old_probs))

@@ -140,6 +140,9 @@ class RolloutEngine:
         if self.steps_done:
             self._carry()
         if self.use_graph and self._warm:
+            # the graph holds raw pointers to the policy's weight blobs: they are persistent buffers refreshed IN PLACE, so
+            # bringing them up to date here (outside the graph) is all a parameter update needs — no re-capture
+            self.policy.refresh_weights()
             if self._graph is None:
                 self._capture()
             self._graph.replay()
@@ -161,3 +164,136 @@ class RolloutEngine:
 
     def agent_steps(self) -> int:
         return self.steps_done * self.B * self.env.n
+
+
+class HostRollout:
+    """The sampler's loop with HOST buffers, one C call per env part and step (cm_rollout_step_host): the garage-sampler
+    boundary (centralized_ma_on_policy_vectorized_sampler.py:119-231) as the unit of work instead of the two step-level calls.
+
+    Observations, masks and env state never leave the device between steps — the policy reads what the previous step left
+    in HBM — so the per-step traffic is: H2D the availability bytes (the sampler's get_avail_actions(), :128-131), D2H
+    everything the sampler appends to its running paths (next observation, adjacency / channel bit rows, ave_deg, reward,
+    done, counts, prey_alive, success, actions, action probabilities and — ``record_attention`` — the attention weights).
+
+    The envs are cut into ``parts`` independent batches, each with its own stream, device output arena and ``host_slots``
+    pinned host arenas; one part's D2H transfers run while the other parts' kernels execute.  ``submit()`` enqueues one step
+    of every part into the next host slot and returns at once; ``collect()`` waits for the oldest submitted step and returns
+    its host views (valid until that slot is submitted again, i.e. for ``host_slots - 1`` further submits).  Because step
+    t + 1 needs nothing from the host, a caller may keep ``host_slots - 1`` steps in flight; ``step()`` = submit + collect.
+    Results are identical to RolloutEngine's (global env ids key the random streams)."""
+
+    def __init__(self, spec: ScenarioSpec, policy, n_envs: int, device="cuda", env_id0: int = 0, parts: int = 4,
+                 host_slots: int = 2, record_attention: bool = False, greedy: bool = False):
+        import ctypes as C
+        from . import _native as N
+        self._C, self._N = C, N
+        self.spec, self.policy, self.B = spec, policy, int(n_envs)
+        self.device = torch.device(device)
+        self.greedy, self.slots = bool(greedy), max(1, int(host_slots))
+        P = max(1, min(int(parts), self.B))
+        cuts = [self.B * g // P for g in range(P + 1)]
+        self.ranges = [(cuts[g], cuts[g + 1]) for g in range(P) if cuts[g + 1] > cuts[g]]
+        comm = bool(getattr(policy, "comm", False))
+        self.record_attention = bool(record_attention) and comm
+        self.parts = []
+        n = spec.n_agents
+        for g, (b0, b1) in enumerate(self.ranges):
+            Bp = b1 - b0
+            env = BatchedEnv(spec, Bp, device=device, env_id0=env_id0 + b0)
+            pspecs = [("actions", (Bp, n), torch.int8), ("probs", (Bp, n, 5), torch.float32)]
+            if self.record_attention:
+                pspecs.append(("attention", (Bp, n, n), torch.float32))
+            pdev = N.arena(pspecs, device=self.device)
+            avail_dev = torch.full((Bp, n), 0x1F, dtype=torch.uint8, device=self.device)
+            part = dict(env=env, range=(b0, b1), stream=torch.cuda.Stream(device=self.device), pdev=pdev, avail_dev=avail_dev,
+                        env_dev=env._io(pdev["actions"]), slots=[])
+            for _ in range(self.slots):
+                eh, ph = N.arena(env._out_specs(), pinned=True), N.arena(pspecs, pinned=True)
+                avail = torch.full((Bp, n), 0x1F, dtype=torch.uint8).pin_memory()
+                env_host, pol_host = N.StepIO(), N.PolicyIO()
+                env_host.host_arena = pol_host.host_arena = 1
+                for k, _, _ in env._out_specs():
+                    setattr(env_host, k, eh[k].data_ptr())
+                for k, _, _ in pspecs:
+                    setattr(pol_host, k, ph[k].data_ptr())
+                pol_host.avail_bits = avail.data_ptr()
+                views = {k: v.numpy() for k, v in list(eh.items()) + list(ph.items()) if k != "_arena"}
+                views["success"] = views.pop("success_out")
+                views["avail_bits"] = avail.numpy()
+                views["env_ids"] = (env_id0 + b0, env_id0 + b1)
+                part["slots"].append(dict(env_host=env_host, pol_host=pol_host, views=views, event=torch.cuda.Event(), keep=(eh, ph, avail)))
+            self.parts.append(part)
+        self._submitted = self._collected = 0
+        self.kernel_launches = 0
+
+    def _pol_structs(self, part, g):
+        env, pdev = part["env"], part["pdev"]
+        pol = self.policy
+        if getattr(pol, "comm", False):
+            return pol._call_structs(env.obs, env.adj_bits, env.chan_bits, part["avail_dev"], None, env.tick, env.episode, self.greedy,
+                                     pdev["probs"], None, pdev.get("attention"), pdev["actions"], env.env_id0, g)
+        return pol._call_structs(env.obs, None, None, part["avail_dev"], None, env.tick, env.episode, self.greedy, pdev["probs"], None,
+                                 None, pdev["actions"], env.env_id0, g)
+
+    def reset(self):
+        """env.reset() of every env; returns the per-part host views (obs, adj_bits, chan_bits, ave_deg are meaningful)"""
+        C, N = self._C, self._N
+        torch.cuda.set_device(self.device)
+        out = []
+        for part in self.parts:
+            env, sl = part["env"], part["slots"][0]
+            N.check("cm_env_reset_host", N.lib().cm_env_reset_host(C.byref(env.desc), C.byref(env.state), C.byref(part["env_dev"]),
+                                                                   C.byref(sl["env_host"]), part["stream"].cuda_stream))
+            part["stream"].synchronize()
+            out.append(sl["views"])
+        self._submitted = self._collected = 0
+        return out
+
+    def submit(self):
+        """enqueue one rollout step of every part (asynchronous)"""
+        C, N = self._C, self._N
+        assert self._submitted - self._collected < self.slots, "collect() the oldest step before submitting into its host slot"
+        if torch.cuda.current_device() != (self.device.index or 0):
+            torch.cuda.set_device(self.device)
+        self.policy.refresh_weights()
+        s = self._submitted % self.slots
+        for g, part in enumerate(self.parts):
+            cs = part.get("pol")
+            if cs is None:
+                cs = part["pol"] = self._pol_structs(part, g)
+            env, sl = part["env"], part["slots"][s]
+            N.check("cm_rollout_step_host", N.lib().cm_rollout_step_host(
+                C.byref(cs[0]), C.byref(cs[1]), C.byref(sl["pol_host"]), C.byref(env.desc), C.byref(env.state),
+                C.byref(part["env_dev"]), C.byref(sl["env_host"]), part["stream"].cuda_stream))
+            sl["event"].record(part["stream"])
+        self._submitted += 1
+        self.kernel_launches += 2 * len(self.parts)
+
+    def collect(self):
+        """wait for the oldest submitted step; returns one dict of host views per part"""
+        assert self._collected < self._submitted, "nothing in flight"
+        s = self._collected % self.slots
+        out = []
+        for part in self.parts:
+            part["slots"][s]["event"].synchronize()
+            out.append(part["slots"][s]["views"])
+        self._collected += 1
+        return out
+
+    def step(self):
+        self.submit()
+        return self.collect()
+
+    def bytes_per_step(self):
+        """(h2d, d2h) bytes one step moves"""
+        h2d = d2h = 0
+        for part in self.parts:
+            eh, ph, avail = part["slots"][0]["keep"]
+            h2d += avail.numel()
+            d2h += sum(v.numel() * v.element_size() for k, v in list(eh.items()) + list(ph.items()) if k != "_arena")
+        return h2d, d2h
+
+    def check_errors(self):
+        for part in self.parts:
+            part["env"].check_errors()
+        self.policy.check_errors()

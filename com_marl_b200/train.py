@@ -20,7 +20,7 @@ class DeviceTrainer:
     def __init__(self, spec, n_envs, device="cuda", env_id0=0, seed=1, kind="comm", **ppo_args):
         """kind: 'comm' / 'dec' (runner_*_comm.py / runner_*_obsDP.py:61: Comm-DP / Obs-DP policy + CommBaseCritic), 'cent'
         (runner_*_cent.py:60-62: CENT policy + GaussianMLPBaseline(hidden_sizes=(64, 64, 64)))"""
-        self.spec, self.device = spec, torch.device(device)
+        self.spec, self.device, self.seed = spec, torch.device(device), int(seed)
         n, Dobs = spec.n_agents, spec.obs_dim
         spec.max_path_length = spec.max_steps
         torch.manual_seed(seed)                              # identical initial weights on every rank
@@ -40,14 +40,16 @@ class DeviceTrainer:
         """one round: rollout of max_steps steps for every env, then the PPO update.  Returns timings and statistics."""
         dev = self.device
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        np.random.seed(1000 + self.epoch)                    # the same path permutation on every rank is not required
         ev[0].record()
         self.engine.reset()
         self.engine.run_chunk()
         ev[1].record()
         batch = self.algo.batch_from_trajectory(self.engine.traj)
         ev[2].record()
-        out = self.algo.train_once(batch=batch)
+        # the path permutation comes from a private generator keyed by (seed, epoch): the process-global numpy stream is the
+        # user's (the same permutation on every rank is not required)
+        perm = np.random.default_rng([self.seed, self.epoch]).permutation(int(batch["rewards"].shape[0]))
+        out = self.algo.train_once(batch=batch, shuffled_ids=perm)
         ev[3].record()
         torch.cuda.synchronize(dev)
         self.engine.env.check_errors()

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 1
+#define CM_ABI_VERSION 2   /* 2: host_arena members, cm_rollout_step_host */
 #define CM_MAX_AGENTS 256   /* n, p */
 #define CM_MAX_GRID 64      /* grid side incl. Coverage's wall border */
 #define CM_MAX_LAYERS 4     /* n_gcn_layers */
@@ -134,6 +134,11 @@ typedef struct cm_step_io {
                                   finished [7] episodes [8] return sum [9] length sum [10] success sum [11..15] counts sums
                                   — the sums behind AverageReturn / SuccessRate / AverageCaptureCount ... that
                                   centralized_ma_ppo.py:345-372 logs from `paths` */
+    int32_t host_arena;        /* read from the `host` struct of the *_host calls only.  Non-zero = the caller declares that the
+                                  non-NULL buffers of that struct are carved from ONE host arena in the member order the call
+                                  copies them, with the same padding (<= 1 KB) as the buffers of the `dev` struct: the library
+                                  may then move neighbouring arrays, padding bytes included, with a single DMA transfer.
+                                  0 = unrelated caller buffers: one transfer per array, nothing outside them is touched */
 } cm_step_io;
 
 /* Weight blob of CommCategoricalMLPPolicy (comm_categorical_mlp_policy.py + comm_base_net.py), float32,
@@ -192,6 +197,7 @@ typedef struct cm_policy_io {
     int32_t *error_flag;       /* DEVICE i32[1], optional: set when a bounded device-side wait times out */
     float *workspace;          /* teams with n > 64 only: cm_policy_workspace_bytes() bytes of scratch (stays L2 resident) */
     size_t workspace_bytes;
+    int32_t host_arena;        /* `host` struct of the *_host calls only; see cm_step_io.host_arena */
 } cm_policy_io;
 
 int cm_abi_version(void);
@@ -255,6 +261,23 @@ int cm_env_step_host(const cm_env_desc *desc, const cm_env_state *state, const c
                      cm_stream_t stream);
 int cm_env_reset_host(const cm_env_desc *desc, const cm_env_state *state, const cm_step_io *dev, const cm_step_io *host,
                       cm_stream_t stream);
+
+/* One iteration of the sampler's loop for B envs as ONE call — the garage-sampler boundary
+ * (CentralizedMAOnPolicyVectorizedSampler.obtain_samples, centralized_ma_on_policy_vectorized_sampler.py:119-231: read
+ * dist_adj / channels / avail_actions of every env :123-131, policy.get_actions :134, vec_env.step :143, append to the
+ * running paths :158-191).  Observations, masks and the env state stay on the device between calls — the policy reads
+ * the observation / bit rows the previous step (or reset) left in pol_dev->obs / adj_bits / chan_bits, which must be the
+ * buffers env_dev->obs / adj_bits / chan_bits point to — so NO observation travels host -> device:
+ *   H2D   pol_host->avail_bits (the sampler's per-step get_avail_actions(), :128-131), when given;
+ *   run   cm_policy_forward(pol_desc, pol_dev)  then  cm_env_step(env_desc, state, env_dev) with env_dev->actions ==
+ *         pol_dev->actions;
+ *   D2H   what the sampler appends per step, for every non-NULL member: pol_host->actions, probs, logits, attention;
+ *         env_host->obs, adj_bits, chan_bits (the NEXT observation / communication state), reward, done, counts,
+ *         prey_alive_out, success_out, ave_deg.
+ * Asynchronous on `stream` like the other host calls. */
+int cm_rollout_step_host(const cm_policy_desc *pol_desc, const cm_policy_io *pol_dev, const cm_policy_io *pol_host,
+                         const cm_env_desc *env_desc, const cm_env_state *state, const cm_step_io *env_dev,
+                         const cm_step_io *env_host, cm_stream_t stream);
 
 /* ---- PPO update helpers (the network forward / backward is torch autograd, com_marl_b200/ppo.py) ----
  * cm_ppo_advantages: rows of the padded [P][T] batch of CentralizedMAPPO.process_samples (centralized_ma_ppo.py:612-659):

@@ -27,7 +27,7 @@ out = env.reset_host()
 def it(out, prof=None):
     pin = out["pinned"]
     t0 = time.perf_counter()
-    a, p, ev = pol.get_actions_host(pin["obs"], pin["adj_bits"], pin["chan_bits"], sync=False)
+    a, p, ev = pol.get_actions_host(pin["obs"], pin["adj_bits"], pin["chan_bits"], inputs_arena=True, sync=False)
     t1 = time.perf_counter(); ev.synchronize(); t2 = time.perf_counter()
     o, ev = env.step_host(a, sync=False)
     t3 = time.perf_counter(); ev.synchronize(); t4 = time.perf_counter()

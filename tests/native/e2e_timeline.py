@@ -17,7 +17,7 @@ E = lambda: torch.cuda.Event(enable_timing=True)
 def pol_phase(h, rec=None):
     pin = outs[h]["pinned"]
     if rec is not None: s = E(); s.record(streams[h])
-    a, _, ev = pol.get_actions_host(pin["obs"], pin["adj_bits"], pin["chan_bits"], slot=h, sync=False, stream=streams[h])
+    a, _, ev = pol.get_actions_host(pin["obs"], pin["adj_bits"], pin["chan_bits"], inputs_arena=True, slot=h, sync=False, stream=streams[h])
     if rec is not None: e = E(); e.record(streams[h]); rec.append(("pol%d" % h, s, e, time.perf_counter()))
     return a, ev
 def env_phase(h, acts, rec=None):

@@ -68,7 +68,7 @@ def main():
     env = BatchedEnv(spec, 33)
     out = env.reset_host()
     for _ in range(8):
-        acts, _ = pol.get_actions_host(out["pinned"]["obs"], out["pinned"]["adj_bits"], out["pinned"]["chan_bits"], return_pinned=True)
+        acts, _ = pol.get_actions_host(out["pinned"]["obs"], out["pinned"]["adj_bits"], out["pinned"]["chan_bits"], return_pinned=True, inputs_arena=True)
         out = env.step_host(acts)
     env.check_errors()
     from com_marl_b200.ppo import ppo_advantages

@@ -163,3 +163,69 @@ def test_host_buffer_api_equals_device_path():
         assert np.array_equal(out["obs"], devc.obs.cpu().numpy())
         assert np.array_equal(out["reward"], devc.reward.cpu().numpy()) and np.array_equal(out["done"], devc.done.cpu().numpy())
         assert np.array_equal(out["chan_bits"], devc.chan_bits.cpu().numpy())
+
+
+@pytest.mark.parametrize("scen,kind,parts", [("pp", "comm", 3), ("co", "comm", 4), ("pp", "dec", 2), ("co", "cent", 2)])
+def test_host_rollout_step_equals_device_rollout(scen, kind, parts):
+    """HostRollout (cm_rollout_step_host: one C call = policy forward -> env step on device-resident state + D2H of what the
+    sampler appends, per env part) delivers to pinned host memory exactly the trajectory RolloutEngine records on the device,
+    with two steps in flight (submit before collect) and auto-resets inside the window."""
+    from com_marl_b200.rollout import HostRollout, RolloutEngine, make_policy
+    if scen == "pp":
+        params, spec = _mk("pp", 10, 1, 0.08, 2, 0.3, {"max_env_steps": 12})
+    else:
+        params, spec = _mk("co", 10, 1, 0.03, 2, 0.1, {"max_env_steps": 14})
+    pol = make_policy(spec, kind=kind)
+    B, K, n = 203, 30, spec.n_agents
+    eng = RolloutEngine(spec, pol, B, ring=K, use_graph=False, record_attention=(kind == "comm"))
+    eng.reset()
+    eng.run_chunk()
+    t = {k: v.cpu().numpy() for k, v in eng.traj.items()}
+    hr = HostRollout(spec, pol, B, parts=parts, host_slots=2, record_attention=(kind == "comm"))
+    first = hr.reset()
+    cat = lambda outs, k: np.concatenate([o[k] for o in outs], axis=0)  # noqa: E731
+    assert np.array_equal(cat(first, "obs"), t["obs"][0]) and np.array_equal(cat(first, "adj_bits"), t["adj_bits"][0])
+    h2d, d2h = hr.bytes_per_step()
+    assert h2d == B * n and d2h >= B * n * (spec.obs_dim * 4 + 21)
+    hr.submit()
+    for k in range(K):
+        if k + 1 < K:
+            hr.submit()                      # step k + 1 is enqueued before step k's host buffers are read
+        outs = hr.collect()
+        assert [o["env_ids"] for o in outs] == [(b0, b1) for b0, b1 in hr.ranges]
+        for key, ref in (("actions", t["actions"][k]), ("probs", t["probs"][k]), ("reward", t["reward"][k]), ("done", t["done"][k]),
+                         ("counts", t["counts"][k]), ("success", t["success"][k]), ("obs", t["obs"][k + 1]),
+                         ("adj_bits", t["adj_bits"][k + 1]), ("chan_bits", t["chan_bits"][k + 1]), ("ave_deg", t["ave_deg"][k + 1])):
+            assert np.array_equal(cat(outs, key), ref), (key, k)
+        if kind == "comm":
+            assert np.array_equal(cat(outs, "attention"), t["attention"][k])
+    assert t["done"].sum() > 0
+    hr.check_errors()
+    assert hr.kernel_launches == 2 * K * len(hr.ranges)
+
+
+def test_graph_replay_sees_updated_weights():
+    """The captured rollout graph holds raw pointers to the policy's kernel weight blobs; the blobs are persistent buffers
+    refreshed in place, so a parameter update between replays (what DevicePPO / FlatAdam do) is picked up by the next replay
+    — no stale or freed weight memory."""
+    from com_marl_b200.rollout import RolloutEngine, make_policy
+    params, spec = _mk("pp", 10, 1, 0.08, 2, 0.3, {"max_env_steps": 20})
+    pol = make_policy(spec)
+    a = RolloutEngine(spec, pol, 150, ring=4, use_graph=True)
+    b = RolloutEngine(spec, pol, 150, ring=4, use_graph=False)
+    for e in (a, b):
+        e.reset()
+        e.run(8)                 # a: eager chunk, then capture + replay
+    assert a._graph is not None
+    ptrs = (pol._blob.data_ptr(), pol._tc_blob.data_ptr())
+    g = torch.Generator(device="cuda").manual_seed(3)
+    with torch.no_grad():
+        for p in pol.parameters():
+            p.add_(0.3 * torch.randn(p.shape, device=p.device, generator=g))     # in-place update bumps the version counters
+    junk = [torch.randn(1 << 20, device="cuda") for _ in range(8)]               # whatever was freed would be reused here
+    for e in (a, b):
+        e.run(8)
+    assert (pol._blob.data_ptr(), pol._tc_blob.data_ptr()) == ptrs
+    for k in ("obs", "actions", "probs", "reward", "done"):
+        assert torch.equal(a.traj[k], b.traj[k]), k
+    del junk

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     lib = N.lib()
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.cm_abi_version() == 1
+    assert lib.cm_abi_version() == N.ABI_VERSION
     assert lib.cm_strerror(N.CM_EACTION) == b"Action Not found!"
     assert lib.cm_policy_blob_floats(21, 2) == 42309 and lib.cm_policy_blob_floats(53, 2) == 46405
     assert lib.cm_policy_cent_blob_floats(4, 21) == 84 * 128 + 128 + 8256 + 2080 + 33 * 20   # n*D -> 128 -> 64 -> 32 -> 5n
@@ -166,3 +166,15 @@ def test_truncate_paths():
     out = _truncate_paths([mk(10), mk(10), mk(10)], max_samples=4 * 14, n_agents=4)
     assert [len(p["rewards"]) for p in out] == [10, 4]
     assert out[1]["observations"].shape == (4, 8) and out[1]["env_infos"]["prey_alive"].shape == (4, 2)
+
+
+def test_ppo_data_parallel_update_world_size_2_gloo():
+    """The PPO update's collectives under gloo with two ranks holding 4 and 5 paths: the weighted gradient all-reduce
+    reproduces the single-process update on the union batch, both ranks end with identical weights, and the unequal local
+    slice counts (2 vs 3 under 3 minibatches) do not deadlock (com_marl_b200.ppo.minibatch_plan)."""
+    import ppo_dp_util
+    from com_marl_b200.ppo import minibatch_plan
+    assert minibatch_plan(4, 3) == [(0, 2), (2, 4)] and minibatch_plan(5, 3) == [(0, 2), (2, 4), (4, 5)]   # the reference's cut
+    assert minibatch_plan(0, 3) == []
+    single, ranks = ppo_dp_util.run("cpu")
+    ppo_dp_util.check(single, ranks)

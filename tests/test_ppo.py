@@ -218,3 +218,13 @@ def test_trainer_round_and_tabular_columns():
     assert row["NumTrajs"] == 64 * spec.n_agents and out["episode_stats"]["NumEpisodes"] == 64
     assert abs(row["AverageReturn"] - out["episode_stats"]["AverageReturn"]) <= 1e-9 * max(1.0, abs(row["AverageReturn"]))
     assert row["MinReturn"] <= row["AverageReturn"] <= row["MaxReturn"]
+
+
+@pytest.mark.gpu
+def test_data_parallel_update_equals_union_update_on_gpu_kernels():
+    """Two ranks (two processes sharing cuda:0, gloo) update on a 4 | 5 split of nine paths with the real kernels
+    (cm_adam_step): the result equals the single-process update on the union batch, both ranks hold identical weights,
+    unequal local slice counts do not deadlock (tests/ppo_dp_util.py)."""
+    import ppo_dp_util
+    single, ranks = ppo_dp_util.run("cuda")
+    ppo_dp_util.check(single, ranks)

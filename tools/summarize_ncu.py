@@ -31,9 +31,20 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__warp_issue_stalled_not_selected_per_warp_active.pct", "smsp__warp_issue_stalled_selected_per_warp_active.pct"]
 
 
+_TC_MODES = {"0": "comm", "1": "dec", "2": "enc", "3": "head"}
+
+
 def _kname(full):
-    """cm::policy_tc_kernel<1>(cm::TcArgs) -> policy_tc_kernel"""
-    return re.sub(r"<.*>", "", full.split("(")[0]).split("::")[-1].replace("void ", "").strip()
+    """cm::policy_tc_kernel<4, 0>(cm::TcArgs) -> policy_tc_kernel<comm>; other kernels lose their template arguments.
+    The mode argument of policy_tc_kernel is kept: the encoder and head launches of the large-team pipeline are different
+    kernels with different traffic and must not collide in traffic.json."""
+    head = full.split("(")[0]
+    base = re.sub(r"<.*>", "", head).split("::")[-1].replace("void ", "").strip()
+    if base == "policy_tc_kernel":
+        m = re.search(r"<\s*\d+\s*,\s*(\d+)\s*>", head)
+        if m:
+            return f"{base}<{_TC_MODES.get(m.group(1), m.group(1))}>"
+    return base
 
 
 def main(tag, cfg):
