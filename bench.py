@@ -1,22 +1,31 @@
 #!/usr/bin/env python
 """bench.py — agent-steps/s of the batched rollout hot path (env step + comm + comm-GNN policy forward).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one rollout iteration over the whole batch: cm_policy_forward (forward + action sampling) followed by
 cm_env_step (PredatorPrey/Coverage step, auto-reset, observation windows, adjacency + channel masks).  The default
-workload is BASELINE.json configs[1]: Coverage --map 10 --sen 1 --den 0.03 --loss 0, 16384 envs per B200 (weak
-scaling: every GPU steps its own 16384 envs; the only collective is the episode-statistics all-gather after the
-timed region).  One JSON line is printed by rank 0:
+workload is the configuration BASELINE.json's metric is quoted on, configs[2]: Predator-Prey --map 20 --sen 2 --den 0.08
+--cap 4 --loss 0.2 (comm graph d^2 <= 162, IID packet drops, prey random walk), 65536 envs per B200 (weak scaling: every
+GPU steps its own 65536 envs; the only collective of the rollout is the episode-statistics all-gather after the timed
+region).  One JSON line is printed by rank 0:
 
-  value      device-resident rollout: inputs live in HBM, K steps replayed from one CUDA graph.
-  e2e        the same loop through the host-buffer API (BatchedEnv.step_host + policy.get_actions_host): every step
-             copies observations + masks host->device for the policy, actions host->device for the env and reads
-             observations / rewards / dones / masks / probabilities back into pinned host memory.
-  roofline   the dominant kernel (policy forward, fp32 FFMA) against the measured bf16 tensor peak, plus the env
-             kernel against the measured HBM copy bandwidth (kernel durations from CUDA events around each launch).
-  cpu_baseline  the oracle port (C env oracle + numpy policy) on the box's host cores, bounded sample.
+  value      device-resident rollout: inputs live in HBM, steps replayed from one CUDA graph of `ring` iterations.  The
+             timed region is at least --min-seconds long whatever --steps says (the graph is replayed more often and the
+             real step count is reported), so it contains time-limit resets and several clock samples.
+  e2e        the same loop through the sampler-level host-buffer call (HostRollout = cm_rollout_step_host): one C call per
+             env part and step runs policy -> env on device-resident state, copies the availability bytes host -> device
+             and everything the sampler appends per step (next observation, masks, reward, done, counts, actions,
+             probabilities ...) device -> pinned host memory.  `e2e.step_api` is the step-level pair of calls
+             (policy.get_actions_host + BatchedEnv.step_host: observations travel both ways) kept as a secondary figure.
+  roofline   the dominant kernel (policy forward) against the measured bf16 tensor peak, plus the env kernel against the
+             measured HBM copy bandwidth (kernel durations from CUDA events around graphs of launches of ONE kernel).
+  configs    a bounded sweep over the other BASELINE configs (c1..c5) with the same measurements, and `c5_ppo`: rollout +
+             PPO update of config 5 (with N > 1: gradient all-reduces over NCCL inside the timed region).  With N > 1 the
+             sweep is c4 + c5_ppo (the configs BASELINE shards over GPUs).
+  cpu_baseline  the oracle port (C env oracle + numpy policy) on the box's host cores, bounded sample; next to it the
+             survey-time figure of the real (pure Python) reference, labelled as measured elsewhere.
 
 `--impl reference` times that CPU port on all host cores (the reference itself is pure Python and is not present
 on the GPU box; oracle/ is its pinned restatement).
@@ -43,12 +52,15 @@ CONFIGS = {
     "c5": ("pp", 50, 2, 0.08, 4, 0.0, 2048),
 }
 WORKLOAD_TEXT = {
-    "c1": "Predator-Prey --map 10 --sen 1 --den 0.04 --cap 2 --loss 0",
+    "c1": "Predator-Prey --map 10 --sen 1 --den 0.04 --cap 2 --loss 0, 16384 envs per B200",
     "c2": "Coverage --map 10 --sen 1 --den 0.03 --loss 0, 16384 batched envs per B200",
     "c3": "Predator-Prey --map 20 --sen 2 --den 0.08 --cap 4 --loss 0.2 (IID drops), 65536 envs per B200",
-    "c4": "Coverage --map 30 --sen 2 --den 0.06 --loss 0.1",
-    "c5": "Predator-Prey --map 50 --sen 2 --den 0.08 --cap 4",
+    "c4": "Coverage --map 30 --sen 2 --den 0.06 --loss 0.1, 16384 envs per B200",
+    "c5": "Predator-Prey --map 50 --sen 2 --den 0.08 --cap 4, 2048 envs per B200",
 }
+# the unmodified pure-Python reference (garage sampler + ma_gym env + CPU torch policy), one core,
+# measured while the survey was written — NOT on this box; the reference cannot travel to the GPU box.
+REFERENCE_PYTHON = {"c1": 1.6e3, "c2": 1.7e3, "c3": 5.3e3, "c4": 6.0e3, "c5": 7.2e3}
 METRIC = "agent-steps/sec, batched PP/Coverage step+comm+policy rollout"
 UNIT = "agent-steps/s"
 
@@ -142,6 +154,12 @@ def cpu_port_throughput(cfg, procs, envs_per_proc, steps):
     return sum(a / t for a, t in res), sum(a for a, _ in res)
 
 
+def reference_python_note(cfg):
+    return {"value": REFERENCE_PYTHON[cfg], "unit": UNIT, "cores": 1,
+            "where": "survey container (8-vCPU Xeon, Sapphire Rapids), NOT this box — BASELINE.md §2; the unmodified pure-Python "
+                     "reference (garage sampler + ma_gym env + CPU torch policy) cannot travel to the GPU box"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -163,7 +181,8 @@ def run_reference_arm(args):
             "config": {"workload": WORKLOAD_TEXT[args.config], "config": args.config},
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{cores} processes x {envs_per_proc} envs x {steps_cpu} steps of the oracle port "
-                                       f"(C env oracle + numpy fp32 policy, 1 thread each), wall {wall:.1f}s"},
+                                       f"(C env oracle + numpy fp32 policy, 1 thread each), wall {wall:.1f}s",
+                             "reference_python": reference_python_note(args.config)},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), file=args.out, flush=True)
@@ -181,7 +200,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -192,11 +211,12 @@ class ClockSampler:
             self.lines.append((time.time(), ln.strip()))
 
     def stop(self, t_lo, t_hi):
+        """median SM clock and throttle reasons of the samples taken INSIDE [t_lo, t_hi] (the timed region)"""
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.1)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, power = [], None, set(), []
         for ts, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -206,91 +226,119 @@ class ClockSampler:
             except ValueError:
                 continue
             mx = mxc
-            if t_lo - 0.05 <= ts <= t_hi + 0.15:
+            if t_lo <= ts <= t_hi + 0.05:
                 sm.append(clk)
+                try:
+                    power.append(float(f[3]))
+                except ValueError:
+                    pass
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        if not sm:  # timed region shorter than one sample: fall back to every sample taken
-            sm = [float(ln.split(",")[1]) for _, ln in self.lines if len(ln.split(",")) >= 9] or [0.0]
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power) if power else None, "region_s": t_hi - t_lo}
 
 
 # ------------------------------------------------------------------------------------------------
-def run_b200_arm(args):
-    import torch
-    import torch.distributed as dist
-    from com_marl_b200 import distributed as D
-    from com_marl_b200.rollout import RolloutEngine, make_policy
-    from com_marl_b200.scenario import ScenarioSpec
+# one configuration on this rank's GPU
+# ------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from com_marl_b200 import distributed as D
+        self.torch, self.dist, self.D = torch, dist, D
+        self.rank, self.local_rank, self.world = D.init_from_env()
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl b200 needs a GPU: the engine has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.numa = D.bind_to_gpu_numa(self.local_rank)
+        self.args = args
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        self.tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+        self.peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        try:
+            self.traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            self.traffic = {}
 
-    rank, local_rank, world = D.init_from_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl b200 needs a GPU: the engine has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    scen, params = params_for(args.config)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+
+def measure_config(cx, cfg, steps_req, warm_req, min_seconds, full, clocks=None, e2e_seconds=0.5):
+    """rollout value / kernel rooflines / e2e of one BASELINE config on this rank's GPU; every rank runs it, all return the
+    same record (times are max over ranks)."""
+    torch, args, dev = cx.torch, cx.args, cx.dev
+    from com_marl_b200.rollout import HostRollout, RolloutEngine, make_policy
+    from com_marl_b200.scenario import ScenarioSpec
+    scen, params = params_for(cfg)
     spec = ScenarioSpec.from_params(scen, params, seed=1)
-    B = args.envs or CONFIGS[args.config][6]
+    B = (args.envs if (args.envs and cfg == args.config) else CONFIGS[cfg][6])
     n, Dobs, L = spec.n_agents, spec.obs_dim, spec.n_layers
     ring = args.ring
-    steps = max(ring, (args.steps // ring) * ring)
-    warm = max(3 * ring, ((args.warmup + ring - 1) // ring) * ring)
     pol = make_policy(spec, device=dev)
     groups = args.groups if args.groups > 0 else (4 if n <= 64 else 1)
-    eng = RolloutEngine(spec, pol, B, device=dev, env_id0=rank * B, ring=ring, use_graph=True, groups=groups)
+    eng = RolloutEngine(spec, pol, B, device=dev, env_id0=cx.rank * B, ring=ring, use_graph=True, groups=groups)
     eng.reset()
-    eng.run(warm)                                   # untimed: first chunk eager, graph captured on the second
+    warm = max(3 * ring, ((warm_req + ring - 1) // ring) * ring)
+    eng.run(warm - ring)                            # untimed: first chunk eager, graph captured on the second
     torch.cuda.synchronize(dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-        time.sleep(0.25)
-    # ---------------- value: device-resident rollout ----------------
+    # pilot (still warm-up): one replay, to size the timed region
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(); eng.run(ring); ev1.record()
+    torch.cuda.synchronize(dev)
+    pilot_ms, = cx.max_over_ranks(ev0.elapsed_time(ev1) / ring)
+    steps = max(ring, ((steps_req + ring - 1) // ring) * ring)
+    floor_steps = int(np.ceil(min_seconds * 1e3 / max(pilot_ms, 1e-6) / ring)) * ring
+    steps = max(steps, floor_steps)
+    # ---------------- value: device-resident rollout ----------------
     launches0 = eng.kernel_launches
-    barrier(); torch.cuda.synchronize(dev)
+    cx.barrier(); torch.cuda.synchronize(dev)
     t_lo = time.time()
     ev0.record()
     eng.run(steps)
     ev1.record()
-    torch.cuda.synchronize(dev); barrier()
+    torch.cuda.synchronize(dev); cx.barrier()
     t_hi = time.time()
     ms = ev0.elapsed_time(ev1)
     launches = eng.kernel_launches - launches0
     eng.env.check_errors()
-    # ---------------- per-kernel durations: CUDA events around a CUDA graph of 32 launches of ONE kernel ----------------
+    pol.check_errors()
+    clock_info = clocks.stop(t_lo, t_hi) if clocks is not None else None
+    stats = cx.D.gather_stats(eng.local_stats())          # the rollout's only collective (NCCL over NVLink)
+    # ---------------- per-kernel durations: CUDA events around a CUDA graph of launches of ONE kernel ----------------
     # (events around single eager launches would include the host's launch gaps, which are of the order of these kernels)
     eng._carry()
     t = eng.traj
-    reps = 32
-
-    # the launches of the timed region are per env group: time exactly that launch size (group 0), alone
+    reps = 32 if full else 16
     gb0, gb1 = eng._ranges[0]
     Bk, ek = gb1 - gb0, eng._envs[0]
 
-    def policy_once(k):
-        pol.act_device(t["obs"][k, gb0:gb1], t["adj_bits"][k, gb0:gb1], t["chan_bits"][k, gb0:gb1], tick=ek.tick, episode=ek.episode,
-                       probs=t["probs"][k, gb0:gb1], actions=t["actions"][k, gb0:gb1], env_id0=ek.env_id0)
+    def policy_call(k, e, b0, b1):
+        pol.act_device(t["obs"][k, b0:b1], t["adj_bits"][k, b0:b1], t["chan_bits"][k, b0:b1], tick=e.tick, episode=e.episode,
+                       probs=t["probs"][k, b0:b1], actions=t["actions"][k, b0:b1], env_id0=e.env_id0)
 
-    def env_once(k):
-        ek.step(t["actions"][k, gb0:gb1],
-                out=dict(obs=t["obs"][k + 1, gb0:gb1], adj_bits=t["adj_bits"][k + 1, gb0:gb1], chan_bits=t["chan_bits"][k + 1, gb0:gb1],
-                         ave_deg=t["ave_deg"][k + 1, gb0:gb1], reward=t["reward"][k, gb0:gb1], done=t["done"][k, gb0:gb1],
-                         counts=t["counts"][k, gb0:gb1], prey_alive_out=t["prey_alive_out"][k, gb0:gb1], success_out=t["success"][k, gb0:gb1]))
+    def env_call(k, e, b0, b1):
+        e.step(t["actions"][k, b0:b1],
+               out=dict(obs=t["obs"][k + 1, b0:b1], adj_bits=t["adj_bits"][k + 1, b0:b1], chan_bits=t["chan_bits"][k + 1, b0:b1],
+                        ave_deg=t["ave_deg"][k + 1, b0:b1], reward=t["reward"][k, b0:b1], done=t["done"][k, b0:b1],
+                        counts=t["counts"][k, b0:b1], prey_alive_out=t["prey_alive_out"][k, b0:b1], success_out=t["success"][k, b0:b1]))
 
-    def time_graph(fn):
-        for k in range(2):
-            fn(k)                                   # warm (also keeps the ring consistent: slot k feeds slot k + 1)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for k in range(reps):
-                fn(k % ring)
+    def replay_ms(g, per):
         torch.cuda.synchronize(dev)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g.replay()
@@ -299,34 +347,23 @@ def run_b200_arm(args):
             g.replay()
         b.record()
         torch.cuda.synchronize(dev)
-        return a.elapsed_time(b) / (3 * reps)
+        return a.elapsed_time(b) / (3 * per)
 
-    pol_alone_ms = time_graph(policy_once)
-    env_alone_ms = time_graph(env_once)
+    def time_alone(fn):
+        for k in range(2):
+            fn(k, ek, gb0, gb1)                     # warm (also keeps the ring consistent: slot k feeds slot k + 1)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for k in range(reps):
+                fn(k % ring, ek, gb0, gb1)
+        return replay_ms(g, reps)
 
-    def time_groups(which):
+    def time_groups(fn, alone):
         """all env groups' launches of one kernel, concurrently on the groups' streams like in the timed region: the
         wall time of one such round / number of groups = the launch duration under the concurrency it really runs at"""
         G = len(eng._ranges)
         if G == 1:
-            return pol_alone_ms if which == "policy" else env_alone_ms
-
-        def round_(k):
-            if which == "policy":
-                for g, (b0, b1) in enumerate(eng._ranges):
-                    eg = eng._envs[g]
-                    with torch.cuda.stream(eng._streams[g]):
-                        pol.act_device(t["obs"][k, b0:b1], t["adj_bits"][k, b0:b1], t["chan_bits"][k, b0:b1], tick=eg.tick,
-                                       episode=eg.episode, probs=t["probs"][k, b0:b1], actions=t["actions"][k, b0:b1], env_id0=eg.env_id0)
-            else:
-                for g, (b0, b1) in enumerate(eng._ranges):
-                    eg = eng._envs[g]
-                    with torch.cuda.stream(eng._streams[g]):
-                        eg.step(t["actions"][k, b0:b1],
-                                out=dict(obs=t["obs"][k + 1, b0:b1], adj_bits=t["adj_bits"][k + 1, b0:b1], chan_bits=t["chan_bits"][k + 1, b0:b1],
-                                         ave_deg=t["ave_deg"][k + 1, b0:b1], reward=t["reward"][k, b0:b1], done=t["done"][k, b0:b1],
-                                         counts=t["counts"][k, b0:b1], prey_alive_out=t["prey_alive_out"][k, b0:b1],
-                                         success_out=t["success"][k, b0:b1]))
+            return alone
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr):
             main = torch.cuda.current_stream(dev)
@@ -334,46 +371,155 @@ def run_b200_arm(args):
             for st in eng._streams:
                 st.wait_event(fork)
             for k in range(reps):
-                round_(k % ring)
+                for g, (b0, b1) in enumerate(eng._ranges):
+                    with torch.cuda.stream(eng._streams[g]):
+                        fn(k % ring, eng._envs[g], b0, b1)
             for st in eng._streams:
                 j = torch.cuda.Event(); j.record(st); main.wait_event(j)
-        torch.cuda.synchronize(dev)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        gr.replay()
-        a.record()
-        for _ in range(3):
-            gr.replay()
-        b.record()
-        torch.cuda.synchronize(dev)
-        return a.elapsed_time(b) / (3 * reps * G)
+        return replay_ms(gr, reps * G)
 
-    pol_ms = time_groups("policy")
-    env_ms = time_groups("env")
-    eng.steps_done += 16 * reps
-    clock_info = clocks.stop(t_lo, t_hi) if rank == 0 else None
-    # ---------------- e2e: host buffers through the public step / get_actions API ----------------
-    # The env batch is cut into `e2e_batches` independent halves that ping-pong through the split-phase host API on their own
-    # streams: while one half's step results travel device -> host, the other half's observations travel host -> device
-    # (PCIe is full duplex).  Every iteration still moves EVERY env's inputs H2D and results D2H and advances all of them.
-    from com_marl_b200.envs import BatchedEnv
+    pol_alone_ms = time_alone(policy_call)
+    env_alone_ms = time_alone(env_call)
+    pol_ms = time_groups(policy_call, pol_alone_ms)
+    env_ms = time_groups(env_call, env_alone_ms)
+    n_groups = len(eng._ranges)
+    episode_stats = cx.D.summarize_stats(stats, spec.scenario, n)
+    tc = pol.uses_tensor_cores()
+    # ---------------- value with the attention weights recorded (the reference returns them every step) ----------------
+    att = None
+    del eng, t, ek
+    torch.cuda.empty_cache()
+    if full and getattr(pol, "comm", False):
+        ring_a = min(ring, 16)
+        eng = RolloutEngine(spec, pol, B, device=dev, env_id0=cx.rank * B, ring=ring_a, use_graph=True, groups=groups, record_attention=True)
+        eng.reset()
+        eng.run(3 * ring_a)
+        torch.cuda.synchronize(dev)
+        sa = max(ring_a, int(np.ceil(0.5 * steps / ring_a)) * ring_a)
+        cx.barrier(); torch.cuda.synchronize(dev)
+        ev0.record(); eng.run(sa); ev1.record()
+        torch.cuda.synchronize(dev); cx.barrier()
+        ms_a, = cx.max_over_ranks(ev0.elapsed_time(ev1))
+        att = {"value": sa * B * n * cx.world / (ms_a * 1e-3), "unit": UNIT, "steps": sa, "ms_per_step": ms_a / sa,
+               "attention_bytes_per_step": B * n * n * 4,
+               "note": "the same device-resident loop with agent_infos['attention_weights'] (B x n x n fp32) written into the "
+                       "trajectory ring by the policy kernel every step"}
+        del eng
+        torch.cuda.empty_cache()
+    # ---------------- e2e: host buffers through the sampler-level call ----------------
     NB = args.e2e_batches if (args.e2e_batches > 0 and B % max(1, args.e2e_batches) == 0) else 1
+    hr = HostRollout(spec, pol, B, device=dev, env_id0=cx.rank * B, parts=NB, host_slots=2)
+    hr.reset()
+    checksum = [0.0]
+
+    def e2e_loop(k):
+        """k steps, one step in flight ahead of the one whose host buffers are read"""
+        hr.submit()
+        for i in range(k):
+            if i + 1 < k:
+                hr.submit()
+            outs = hr.collect()
+            checksum[0] += float(outs[0]["reward"][0])         # the host really reads the step's result
+    e2e_loop(4)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter(); e2e_loop(4); pilot = (time.perf_counter() - t0) / 4
+    pilot, = cx.max_over_ranks(pilot)
+    e2e_steps = int(max(8, min(args.e2e_steps, np.ceil(e2e_seconds / max(pilot, 1e-6)))))
+    cx.barrier(); torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    e2e_loop(e2e_steps)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    cx.barrier()
+    hr.check_errors()
+    h2d, d2h = hr.bytes_per_step()
+    del hr
+    torch.cuda.empty_cache()
+    step_api = None
+    if full:
+        step_api = measure_e2e_step_api(cx, spec, pol, B, NB, e2e_seconds)
+    ms_max, e2e_max = cx.max_over_ranks(ms, e2e_s)
+    agent_steps = steps * B * n * cx.world
+    value = agent_steps / (ms_max * 1e-3)
+    flops = policy_flops_per_agent(Dobs, n, L) * Bk * n               # per launch (one env group)
+    env_bytes = env_bytes_per_agent_step(spec) * Bk * n
+    kname = ("policy_tc_kernel<comm>" if n <= 64 else "policy_tc_kernel<enc> + policy_attn_mma_kernel + policy_tc_kernel<head>") if tc \
+        else ("policy_small_kernel" if n <= 64 else "policy_large_kernel")
+    traffic = cx.traffic.get(cfg, {}) if B == CONFIGS[cfg][6] else {}
+    if n <= 64:
+        pol_traffic = traffic.get(kname, traffic.get("policy_tc_kernel"))
+    else:
+        parts = [traffic.get(k) for k in ("policy_tc_kernel<enc>", "policy_attn_mma_kernel", "policy_tc_kernel<head>")]
+        pol_traffic = sum(parts) if all(p is not None for p in parts) else None
+    # what the tensor pipe actually executes per 128-row tile: 3 passes over the padded dense layers
+    Dp = (Dobs + 15) // 16 * 16
+    dense_mac = Dp * 128 + 128 * 64 + 64 * 64 * (1 + L) + 64 * 128 + 128 * 64 + 64 * 32 + 32 * 16
+    rows_per_tile = (128 // n) * n if n <= 64 else 128            # whole envs per tile (n <= 64) / any 128 rows (large teams)
+    tc_flops = (3 * 2 * dense_mac * 128 * ((Bk * n + rows_per_tile - 1) // rows_per_tile)) if tc else 0
+    pol_tflops = flops / (pol_ms * 1e-3) / 1e12
+    env_gbs = env_bytes / (env_ms * 1e-3) / 1e9
+    rec = {
+        "value": value, "unit": UNIT, "steps": steps, "warmup": warm, "ms_per_step": ms_max / steps, "timed_region_s": ms_max * 1e-3,
+        "gpu_launches": launches * cx.world,
+        "config": {"workload": WORKLOAD_TEXT[cfg], "config": cfg, "envs_per_gpu": B, "n_agents": n,
+                   "obs_dim": Dobs, "ring_slots": ring, "env_groups": n_groups,
+                   "attention": ("not recorded in `value` (RolloutEngine(record_attention=False)); `value_with_attention` times the "
+                                 "loop that writes it") if full else "not recorded",
+                   "l2": f"inputs are produced by the previous step; the trajectory ring ({ring + 1} slots, "
+                         f"{(ring + 1) * B * n * Dobs * 4 / 2**20:.0f} MiB of observations) is larger than the 126 MB L2, "
+                         "so no slot survives a ring cycle in cache",
+                   "streams": "on-device Philox4x32-10 (spawn, prey walk, channel draws, action sampling)"},
+        "e2e": {"value": e2e_steps * B * n * cx.world / e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "batches": NB, "ms_per_step": 1e3 * e2e_max / e2e_steps,
+                "api": "HostRollout.submit/collect = cm_rollout_step_host, the sampler-level boundary (one C call per env part and step: "
+                       "H2D availability bytes, policy forward -> env step on device-resident state, D2H next observation + masks + "
+                       "ave_deg + reward + done + counts + prey_alive + success + actions + probabilities into pinned host memory); "
+                       f"{NB} env parts on their own streams, one step in flight ahead of the one the host reads",
+                "step_api": step_api},
+        "roofline": {"bound": "tensor", "kernel": kname,
+                     "achieved": pol_tflops, "peak": cx.tc_peak, "unit": "TFLOP/s", "frac": pol_tflops / cx.tc_peak, "traffic": pol_traffic,
+                     "peak_source": cx.peak_src + ", bf16 dense sustained; the kernel issues A_hi x [B_hi;B_lo] and A_lo x B_hi in fp16 per "
+                                    "algorithmic product (error compensation) on padded K, so the tensor pipe executes ~3.3x the algorithmic FLOPs counted here",
+                     "flop_per_launch": flops, "tensor_flop_issued_per_launch": tc_flops, "ms_per_launch": pol_ms,
+                     "share_of_step": pol_ms / (pol_ms + env_ms), "envs_per_launch": Bk, "launches_per_step": n_groups,
+                     "ms_per_launch_alone": pol_alone_ms,
+                     "note": "one launch = one env group; ms_per_launch = wall time of the groups' concurrent launches (separate streams, as in "
+                             "the timed region; CUDA graph, CUDA events) / number of groups; ms_per_launch_alone = the same launch with the GPU to itself"},
+        "roofline_env": {"bound": "hbm", "kernel": "env_kernel", "achieved": env_gbs, "peak": cx.hbm_peak, "unit": "GB/s",
+                         "frac": env_gbs / cx.hbm_peak, "traffic": traffic.get("env_kernel"), "bytes_per_launch": env_bytes, "ms_per_launch": env_ms,
+                         "bytes_per_agent_step": env_bytes_per_agent_step(spec), "peak_source": cx.peak_src, "envs_per_launch": Bk,
+                         "launches_per_step": n_groups, "ms_per_launch_alone": env_alone_ms},
+        "episode_stats": episode_stats,
+    }
+    if att is not None:
+        rec["value_with_attention"] = att
+    if clock_info is not None:
+        rec["clocks"] = clock_info
+    rec["_tc"] = tc
+    return rec
+
+
+def measure_e2e_step_api(cx, spec, pol, B, NB, seconds):
+    """the step-level pair of host calls (round 1's e2e): policy.get_actions_host + BatchedEnv.step_host — observations +
+    masks + actions go H2D and every result D2H each step; event-driven antiphase over NB env parts"""
+    torch, dev = cx.torch, cx.dev
+    from com_marl_b200.envs import BatchedEnv
+    n = spec.n_agents
     Bh = B // NB
-    henvs = [BatchedEnv(spec, Bh, device=dev, env_id0=rank * B + h * Bh) for h in range(NB)]
+    henvs = [BatchedEnv(spec, Bh, device=dev, env_id0=cx.rank * B + h * Bh) for h in range(NB)]
     hstreams = [torch.cuda.Stream(dev) for _ in range(NB)]
     outs = [e.reset_host() for e in henvs]
     torch.cuda.synchronize(dev)
-    e2e_steps = max(5, min(steps, args.e2e_steps))
 
     def pol_phase(h):
-        pin = outs[h]["pinned"]            # host (pinned) buffers filled by the previous step of this half
-        a, _, ev = pol.get_actions_host(pin["obs"], pin["adj_bits"], pin["chan_bits"], inputs_arena=True, slot=h, sync=False, stream=hstreams[h])
+        pin = outs[h]["pinned"]            # host (pinned) buffers filled by the previous step of this part
+        a, _, ev = pol.get_actions_host(pin["obs"], pin["adj_bits"], pin["chan_bits"], inputs_arena=True, slot=100 + h, sync=False,
+                                        stream=hstreams[h])
         return a, ev
 
     def env_phase(h, acts):
         return henvs[h].step_host(acts, sync=False, stream=hstreams[h])
 
-    # event-driven ping-pong: a half's next call is enqueued as soon as ITS previous call has finished, while the other
-    # halves' copies / kernels keep the bus and the SMs busy.  Odd halves start one policy phase ahead (antiphase).
     phase, pend, evs = {}, {}, {}
     for h in range(NB):
         pend[h], evs[h] = pol_phase(h)
@@ -383,7 +529,7 @@ def run_b200_arm(args):
             outs[h], evs[h] = env_phase(h, pend[h])
             phase[h] = "env"
 
-    def e2e_iteration():                   # every half advances by one full step (one policy call + one env step)
+    def iteration():                   # every part advances by one full step (one policy call + one env step)
         for _ in range(2):
             for h in range(NB):
                 evs[h].synchronize()
@@ -395,105 +541,120 @@ def run_b200_arm(args):
                     phase[h] = "pol"
 
     for _ in range(3):
-        e2e_iteration()
-    barrier(); torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_iteration()
+        iteration()
     torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    barrier()
+    t0 = time.perf_counter(); iteration(); iteration(); pilot = (time.perf_counter() - t0) / 2
+    pilot, = cx.max_over_ranks(pilot)
+    k = int(max(5, min(cx.args.e2e_steps, np.ceil(seconds / max(pilot, 1e-6)))))
+    cx.barrier(); torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(k):
+        iteration()
+    torch.cuda.synchronize(dev)
+    s = time.perf_counter() - t0
+    cx.barrier()
     for e in henvs:
         e.check_errors()
     ph2d, pd2h = pol.host_call_bytes(B)
     eh2d, ed2h = [sum(x) for x in zip(*[e.host_step_bytes() for e in henvs])]
-    # ---------------- reduce over ranks ----------------
-    vec = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(vec, op=dist.ReduceOp.MAX)
-    ms_max, e2e_max = float(vec[0]), float(vec[1])
-    stats = D.gather_stats(eng.local_stats())          # the path's only collective (NCCL over NVLink)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+    s_max, = cx.max_over_ranks(s)
+    del henvs
+    pol.__dict__.pop("_stages", None)
+    torch.cuda.empty_cache()
+    return {"value": k * B * n * cx.world / s_max, "unit": UNIT, "h2d_bytes_per_step": ph2d + eh2d, "d2h_bytes_per_step": pd2h + ed2h,
+            "steps": k, "api": "policy.get_actions_host + BatchedEnv.step_host = cm_policy_forward_host + cm_env_step_host"}
+
+
+def measure_c5_ppo(cx, envs, rounds=2):
+    """BASELINE configs[4]: PP 50/2/.08 cap 4, comm-GNN rollout + PPO update; with N > 1 every optimizer step all-reduces the
+    flat policy and critic gradient buckets over NCCL inside the timed region."""
+    torch, dev = cx.torch, cx.dev
+    from com_marl_b200.scenario import ScenarioSpec
+    from com_marl_b200.train import DeviceTrainer
+    scen, params = params_for("c5")
+    spec = ScenarioSpec.from_params(scen, params, seed=1)
+    tr = DeviceTrainer(spec, envs, device=dev, env_id0=cx.rank * envs, optimization_mini_epochs=2)
+    tr.train_epoch()                         # warm-up round (allocations, cuBLAS handles, NCCL communicator)
+    torch.cuda.synchronize(dev)
+    cx.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    outs = [tr.train_epoch() for _ in range(rounds)]
+    ev1.record()
+    torch.cuda.synchronize(dev); cx.barrier()
+    ms, = cx.max_over_ranks(ev0.elapsed_time(ev1))
+    o = outs[-1]
+    steps_opt = len(o["losses"])
+    csum = torch.tensor([tr.weights_checksum()], dtype=torch.float64, device=dev)
+    lo, hi = csum.clone(), csum.clone()
+    if cx.world > 1:
+        cx.dist.all_reduce(lo, op=cx.dist.ReduceOp.MIN); cx.dist.all_reduce(hi, op=cx.dist.ReduceOp.MAX)
+    agent_steps = rounds * o["agent_steps"] * cx.world
+    rec = {"value": agent_steps / (ms * 1e-3), "unit": UNIT, "what": "rollout of one 200-step horizon for every env + PPO update "
+           f"({steps_opt} optimizer steps = 2 mini-epochs x 3 minibatches; policy and critic gradient buckets "
+           + ("all-reduced over NCCL every step" if cx.world > 1 else "no all-reduce at N = 1") + "), per round",
+           "workload": WORKLOAD_TEXT["c5"].replace("2048", str(envs)), "envs_per_gpu": envs, "rounds": rounds, "ms_per_round": ms / rounds,
+           "rollout_ms": o["rollout_ms"], "batch_ms": o["batch_ms"], "update_ms": o["update_ms"], "optimizer_steps_per_round": steps_opt,
+           "allreduce_calls_per_round": (2 * steps_opt) if cx.world > 1 else 0, "n_paths_per_rank": o["n_paths"],
+           "loss_before": o["loss_before"], "loss_after": o["loss_after"], "kl": o["kl"],
+           "weights_identical_on_all_ranks": bool(float(lo) == float(hi))}
+    del tr
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_b200_arm(args):
+    cx = Ctx(args)
+    clocks = ClockSampler(cx.local_rank) if cx.rank == 0 else None
+    if clocks is not None:
+        clocks.start()
+        time.sleep(0.2)
+    main = measure_config(cx, args.config, args.steps, args.warmup, args.min_seconds, True, clocks)
+    sweep = {}
+    if not args.no_sweep:
+        names = [c for c in (("c4",) if cx.world > 1 else ("c1", "c2", "c3", "c4", "c5")) if c != args.config]
+        for c in names:
+            r = measure_config(cx, c, 0, 0, args.min_seconds, False, None, e2e_seconds=0.3)
+            sweep[c] = {k: r[k] for k in ("value", "ms_per_step", "steps", "timed_region_s", "e2e", "roofline", "roofline_env")}
+            sweep[c]["workload"] = r["config"]["workload"]
+            for k in ("api", "step_api"):
+                sweep[c]["e2e"].pop(k, None)
+        sweep["c5_ppo"] = measure_c5_ppo(cx, args.ppo_envs)
+    if cx.rank != 0:
+        if cx.world > 1:
+            cx.dist.destroy_process_group()
         return
-    agent_steps = steps * B * n * world
-    value = agent_steps / (ms_max * 1e-3)
-    e2e_value = e2e_steps * B * n * world / e2e_max
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    traffic = {}
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.config, {}) if B == CONFIGS[args.config][6] else {}
-    except Exception:
-        pass
-    flops = policy_flops_per_agent(Dobs, n, L) * Bk * n               # per launch (one env group)
-    env_bytes = env_bytes_per_agent_step(spec) * Bk * n
-    tc = pol.uses_tensor_cores()
-    kname = ("policy_tc_kernel" if n <= 64 else "policy_tc_kernel(enc) + policy_attn_kernel + policy_tc_kernel(head)") if tc \
-        else ("policy_small_kernel" if n <= 64 else "policy_large_kernel")
-    kdesc = ("the kernel issues A_hi x [B_hi;B_lo] and A_lo x B_hi in fp16 per algorithmic product (error compensation) on K "
-             "padded to 16/64, so the tensor pipe executes ~3.3x the algorithmic FLOPs counted here" if tc
-             else "the kernel itself is exact fp32 FFMA")
-    # what the tensor pipe actually executes per 128-row tile: 3 passes over the padded dense layers
-    Dp = (Dobs + 15) // 16 * 16
-    dense_mac = Dp * 128 + 128 * 64 + 64 * 64 * (1 + L) + 64 * 128 + 128 * 64 + 64 * 32 + 32 * 16
-    rows_per_tile = (128 // n) * n if n <= 64 else 128            # whole envs per tile (n <= 64) / any 128 rows (large teams)
-    tc_flops = (3 * 2 * dense_mac * 128 * ((Bk * n + rows_per_tile - 1) // rows_per_tile)) if tc else 0
-    pol_tflops = flops / (pol_ms * 1e-3) / 1e12
-    env_gbs = env_bytes / (env_ms * 1e-3) / 1e9
+    tc = main.pop("_tc")
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
-        "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": cx.world, "steps": main["steps"], "warmup": main["warmup"],
+        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": ("f32-equivalent: error-compensated fp16-split tcgen05 products (x = hi + 2^-12 lo) with fp32 accumulation in TMEM (policy)"
                   if tc else "f32 FFMA (policy)") + " + u8/u16/u64 bit rows (env, comm)",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD_TEXT[args.config], "config": args.config, "envs_per_gpu": B, "n_agents": n,
-                   "obs_dim": Dobs, "ring_slots": ring, "env_groups": len(eng._ranges),
-                   "l2": f"inputs are produced by the previous step; the trajectory ring ({ring + 1} slots, "
-                         f"{(ring + 1) * B * n * Dobs * 4 / 2**20:.0f} MiB of observations) is larger than the 126 MB L2, "
-                         "so no slot survives a ring cycle in cache",
-                   "streams": "on-device Philox4x32-10 (spawn, prey walk, channel draws, action sampling)"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ph2d + eh2d, "d2h_bytes_per_step": pd2h + ed2h,
-                "steps": e2e_steps, "batches": NB,
-                "api": "policy.get_actions_host + BatchedEnv.step_host = cm_policy_forward_host + cm_env_step_host (one C call each: H2D, kernel, "
-                       f"D2H on pinned host buffers); split-phase calls, the env batch cut into {NB} independent halves on their own "
-                       "streams in antiphase, so one half's kernels and host work hide behind the other's copies; every env's "
-                       "observations + masks + actions go H2D and its results D2H every step, one host wait per call"},
-        "gpu_launches": launches * world,
-        "roofline": {"bound": "tensor", "kernel": kname,
-                     "achieved": pol_tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": pol_tflops / tc_peak, "traffic": traffic.get(kname),
-                     "peak_source": peak_src + ", bf16 dense sustained; " + kdesc,
-                     "flop_per_launch": flops, "tensor_flop_issued_per_launch": tc_flops, "ms_per_launch": pol_ms, "share_of_step": pol_ms / (pol_ms + env_ms),
-                     "envs_per_launch": Bk, "launches_per_step": len(eng._ranges),
-                     "ms_per_launch_alone": pol_alone_ms,
-                     "note": "one launch = one env group; ms_per_launch = wall time of the groups' concurrent launches (separate streams, as in "
-                             "the timed region; CUDA graph of 32 rounds, CUDA events) / number of groups; ms_per_launch_alone = the same launch with the GPU to itself"},
-        "roofline_env": {"bound": "hbm", "kernel": "env_kernel", "achieved": env_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": env_gbs / hbm_peak, "traffic": traffic.get("env_kernel"), "bytes_per_launch": env_bytes, "ms_per_launch": env_ms,
-                         "bytes_per_agent_step": env_bytes_per_agent_step(spec), "peak_source": peak_src, "envs_per_launch": Bk,
-                         "launches_per_step": len(eng._ranges), "ms_per_launch_alone": env_alone_ms},
-        "clocks": clock_info,
-        "episode_stats": D.summarize_stats(stats, spec.scenario, n),
+        "data": "synthetic", "timed_region_s": main["timed_region_s"],
+        "steps_note": f"--steps {args.steps} / --warmup {args.warmup} were rounded up to whole {args.ring}-step graph replays and to a timed "
+                      f"region of at least {args.min_seconds} s",
+        "config": main["config"], "e2e": main["e2e"], "gpu_launches": main["gpu_launches"],
+        "roofline": main["roofline"], "roofline_env": main["roofline_env"], "clocks": main.get("clocks"),
+        "episode_stats": main["episode_stats"], "host_affinity": cx.numa,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if "value_with_attention" in main:
+        line["value_with_attention"] = main["value_with_attention"]
+    if sweep:
+        line["configs"] = sweep
+    if cx.world == 1 and not args.no_cpu_baseline:
         t0 = time.perf_counter()
+        n = main["config"]["n_agents"]
         Bc = max(8, min(512, 40000 // n))
         pilot_rate, _ = cpu_port_throughput(args.config, 1, Bc, 10)
         Sc = int(max(10, min(200000, 10.0 * pilot_rate / (Bc * n))))      # ~10 s of single-thread CPU work
         rate, _ = cpu_port_throughput(args.config, 1, Bc, Sc)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"{Bc} envs x {Sc} steps of the oracle port (C env oracle + numpy fp32 policy), "
-                                          f"1 thread, {time.perf_counter() - t0:.1f}s"}
+                                          f"1 thread, {time.perf_counter() - t0:.1f}s",
+                                "reference_python": reference_python_note(args.config)}
     print(json.dumps(line), file=args.out, flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if cx.world > 1:
+        cx.dist.destroy_process_group()
 
 
 def _quiet_stdout():
@@ -509,15 +670,18 @@ def _quiet_stdout():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2048)
+    ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=192)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
-    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the config's)")
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU of --config (default: the config's)")
     ap.add_argument("--ring", type=int, default=64, help="trajectory ring slots = steps per CUDA graph")
-    ap.add_argument("--e2e-steps", type=int, default=200)
-    ap.add_argument("--e2e-batches", type=int, default=4, help="independent env halves of the e2e (host-buffer) loop")
+    ap.add_argument("--min-seconds", type=float, default=0.25, help="floor on the timed region of `value`")
+    ap.add_argument("--e2e-steps", type=int, default=2000, help="cap on the steps of an e2e (host-buffer) loop")
+    ap.add_argument("--e2e-batches", type=int, default=4, help="independent env parts of the e2e (host-buffer) loops")
     ap.add_argument("--groups", type=int, default=0, help="independent env groups, each a policy->step chain on its own stream (0: 4 for teams <= 64, else 1)")
+    ap.add_argument("--ppo-envs", type=int, default=32, help="envs per GPU of the c5_ppo sub-record")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the configs sweep and the c5_ppo sub-record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.out = _quiet_stdout()

@@ -358,6 +358,19 @@ class _WrapperBase:
         o = self._vec.obs[0].cpu().numpy()
         return o.reshape(-1) if self.centralized else [o[i] for i in range(self.n_agents)]
 
+    def inject_streams(self, prey_cand=None, chan_u=None):
+        """Parity mode of the public API: pre-drawn random streams consumed one slice per call instead of the Philox streams —
+        ``prey_cand`` int8 [steps, p, 5] (the np.random.choice candidates of prey_random_move, predator_prey.py:396-407; step s
+        uses slice s) and ``chan_u`` float32 [steps + 1, planes, n, n] (the torch.rand draws of get_iid_channel /
+        get_next_state_matrix; the first reset() uses slice 0, step s slice s + 1, and a reset() after step s re-reads slice
+        s + 1 — how tests/golden/make_golden.py fed the reference).  SURVEY.md §8c's injection points."""
+        self._inj_cand = None if prey_cand is None else np.asarray(prey_cand, dtype=np.int8)
+        self._inj_u = None if chan_u is None else np.asarray(chan_u, dtype=np.float32)
+        self._inj_t = 0
+
+    _inj_cand = _inj_u = None
+    _inj_t = 0
+
     def seed(self, n):
         self._seed = n
         self._vec.desc.seed = int(n)
@@ -369,7 +382,7 @@ class _WrapperBase:
 
     def reset(self, epoch=-1):
         self.epoch = epoch
-        self._vec.reset()
+        self._vec.reset(chan_u=None if self._inj_u is None else self._inj_u[self._inj_t][None])
         if self._scenario == "co":
             self.ave_trput = self.spec_b200.ave_trput
             self.bound_return = self.spec_b200.bound_return
@@ -381,7 +394,10 @@ class _WrapperBase:
         a = np.asarray(actions).reshape(1, self.n_agents)
         if ((a < 0) | (a > 4)).any():
             raise Exception("Action Not found!")       # predator_prey.py:255 / coverage.py:347
-        v.step(a.astype(np.int8))
+        t = self._inj_t
+        v.step(a.astype(np.int8), prey_cand=None if self._inj_cand is None else self._inj_cand[t][None],
+               chan_u=None if self._inj_u is None else self._inj_u[t + 1][None])
+        self._inj_t = t + 1
         reward = float(v.reward[0].item())
         det = v.details()[0]
         details = dict(reward=reward, capture_cnt=det[0], step_cnt=1, move_cnt=det[1], penalty_cnt=det[2],

@@ -189,6 +189,9 @@ class HostRollout:
         self._C, self._N = C, N
         self.spec, self.policy, self.B = spec, policy, int(n_envs)
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        device = self.device
         self.greedy, self.slots = bool(greedy), max(1, int(host_slots))
         P = max(1, min(int(parts), self.B))
         cuts = [self.B * g // P for g in range(P + 1)]

@@ -38,7 +38,10 @@ def main():
     #       cent = runner_*_cent.py:48-63 (CENT + GaussianMLPBaseline(64, 64, 64))
     for case, (scenario, m, sen, den, cap, loss, T, n_paths, kind) in dict(
             pp=("pp", 10, 1, 0.04, 2, 0.3, 14, 7, "comm"), co=("co", 10, 1, 0.03, 2, 0.0, 11, 6, "comm"),
-            pp_dec=("pp", 10, 1, 0.04, 2, 0.3, 12, 6, "dec"), co_cent=("co", 10, 1, 0.03, 2, 0.0, 13, 7, "cent")).items():
+            pp_dec=("pp", 10, 1, 0.04, 2, 0.3, 12, 6, "dec"), co_cent=("co", 10, 1, 0.03, 2, 0.0, 13, 7, "cent"),
+            # BASELINE config 3's shape (n = 32, IID drops), a large team (n = 72 > one 64-row tile) and config 5's team (n = 200)
+            pp_c3=("pp", 20, 2, 0.08, 4, 0.2, 10, 4, "comm"), pp_n72=("pp", 30, 2, 0.08, 4, 0.0, 6, 3, "comm"),
+            pp_c5=("pp", 50, 2, 0.08, 4, 0.0, 4, 3, "comm")).items():
         if only and case not in only:
             continue
         comm = kind == "comm"

@@ -131,6 +131,8 @@ def _install_akro():
             return Discrete(space.n)
         return Box(space.low, space.high)
 
+    for cls, qn in ((_A, "Space"), (Discrete, "Discrete"), (Box, "Box")):      # picklable like the real akro classes (checkpoints)
+        cls.__module__, cls.__qualname__ = "akro", qn
     _mod("akro", Discrete=Discrete, Box=Box, from_gym=from_gym, Space=_A, Dict=_A, Tuple=_A, Image=_A)
 
 

@@ -242,11 +242,12 @@ def test_mask_pack_unpack_roundtrip():
     assert np.array_equal(d.astype(np.uint8), _unpack_bits(env.chan_bits.cpu().numpy(), spec.n_agents))
 
 
-@pytest.mark.parametrize("name", ["pp_c1", "co_c2", "co_hard"])
+@pytest.mark.parametrize("name", ["pp_c1", "pp_c3", "pp_capture", "pp_rcom2", "co_c2", "co_hard", "co_c4"])
 def test_gym_wrapper_contract_matches_reference(name):
-    """The B=1 wrappers return what the reference wrappers return (shapes, tuple structure, details dict);
-    for Coverage (no random stream inside step) a whole episode through the public reset()/step() API
-    reproduces the reference's observations, rewards, details and comm attributes."""
+    """The B=1 wrappers return what the reference wrappers return (shapes, tuple structure, details dict), and a WHOLE
+    episode through the public reset()/step() API reproduces the reference's observations, rewards, details, done flags,
+    prey_alive infos, success and comm attributes — PredatorPrey with the reference's prey-move candidates and packet-loss
+    uniforms injected through the wrapper (inject_streams: the streams the fixture's generator fed the reference)."""
     from com_marl_b200.envs import PredatorPreyWrapper, CoverageWrapper
     case = EnvCase(name)
     z = case.z
@@ -254,6 +255,8 @@ def test_gym_wrapper_contract_matches_reference(name):
     kw = dict(max_steps=case.T) if case.scenario == "co" else {}
     env = cls(centralized=True, other_agent_visible=True, params=case.params, **kw)
     env._vec.set_spawn_queue(z["spawn_agent"][None], z["spawn_prey"][None] if case.p else None)
+    use_u = env.spec_b200.channel in (2, 3)
+    env.inject_streams(prey_cand=case.cand if case.p else None, chan_u=case.chan_u if use_u else None)
     obs = env.reset()
     D = env.spec_b200.obs_dim
     assert obs.shape == (case.n * D,) and np.array_equal(obs, z["obs"][0])
@@ -261,24 +264,27 @@ def test_gym_wrapper_contract_matches_reference(name):
     assert env.spec.observation_space is env.observation_space
     assert env.get_avail_actions().shape == (case.n * 5,)
     assert env.dist_adj.shape == (case.n, case.n) and env.channels.shape == (case.L, case.n, case.n)
+    assert np.array_equal(env.channels.astype(np.uint8), case.unpack("chan", 0))
     assert env.bound_return == pytest.approx(case.meta["bound_return"])
-    o, (r, det), done, info = env.step(case.actions[0])
-    assert o.shape == obs.shape and isinstance(r, float) and isinstance(done, bool)
-    assert set(det) == {"reward", "capture_cnt", "step_cnt", "move_cnt", "penalty_cnt", "variable", "vars2"}
-    if case.scenario == "co":
-        assert r == z["reward"][0] and np.array_equal(o, z["obs"][1])
-        for s in range(1, case.steps):
-            o, (r, det), done, info = env.step(case.actions[s])
-            assert r == z["reward"][s] and done == bool(z["done"][s])
-            assert [det["capture_cnt"], det["move_cnt"], det["penalty_cnt"], det["variable"], det["vars2"]] == list(z["details"][s])
-            assert env.success == z["success"][s]
-            if done:
-                break
-            assert np.array_equal(o, z["obs"][s + 1])
-            assert np.array_equal(env.channels.astype(np.uint8), case.unpack("chan", s + 1))
-            assert np.array_equal(np.asarray(env.dist_adj).astype(np.uint8), case.unpack("adj", s + 1))
-        assert done
-    else:
-        assert "prey_alive" in info and info["prey_alive"].shape == (case.p,)
+    episodes = 0
+    for s in range(case.steps):
+        o, (r, det), done, info = env.step(case.actions[s])
+        if s == 0:
+            assert o.shape == obs.shape and isinstance(r, float) and isinstance(done, bool)
+            assert set(det) == {"reward", "capture_cnt", "step_cnt", "move_cnt", "penalty_cnt", "variable", "vars2"}
+        assert r == z["reward"][s] and done == bool(z["done"][s]), s
+        assert [det["capture_cnt"], det["move_cnt"], det["penalty_cnt"], det["variable"], det["vars2"]] == list(z["details"][s])
+        assert env.success == z["success"][s]
+        if case.scenario == "pp":
+            assert "prey_alive" in info and np.array_equal(info["prey_alive"], z["prey_alive"][s].astype(bool))
+        if done:                                   # like the sampler's VecEnvExecutor: reset, the reset observation replaces o
+            episodes += 1
+            o = env.reset()
+        assert np.array_equal(o, z["obs"][s + 1])
+        assert np.array_equal(env.channels.astype(np.uint8), case.unpack("chan", s + 1))
+        assert np.array_equal(np.asarray(env.dist_adj).astype(np.uint8), case.unpack("adj", s + 1))
+        if env.spec_b200.rcom != 0:
+            assert env.ave_deg == np.float32(z["ave_deg"][s + 1])
+    assert episodes == int(z["done"].sum()) >= 1
     with pytest.raises(Exception, match="Action Not found"):
         env.step([9] * case.n)

@@ -229,3 +229,72 @@ def test_graph_replay_sees_updated_weights():
     for k in ("obs", "actions", "probs", "reward", "done"):
         assert torch.equal(a.traj[k], b.traj[k]), k
     del junk
+
+
+@pytest.mark.parametrize("case", ["pp", "co", "pp_c3"])
+def test_sampler_paths_content_and_reference_layout(case):
+    """DeviceRolloutSampler.obtain_samples against (1) the reference sampler's own paths stored in tests/golden/ppo_*.npz
+    (recorded from CentralizedMAOnPolicyVectorizedSampler by make_golden_ppo.py): same keys, trailing shapes and dtypes
+    (observations are float32 here — documented deviation), availability all ones; (2) an independent cut of the device
+    trajectory a RolloutEngine with the same seed and env ids records (itself replayed on the oracle in
+    test_fused_rollout_matches_oracle): every array of every path is exactly the episode's slice."""
+    import json
+    from types import SimpleNamespace
+    from com_marl_b200.envs import CoverageWrapper, PredatorPreyWrapper
+    from com_marl_b200.rollout import RolloutEngine, make_policy
+    from com_marl_b200.sampler import DeviceRolloutSampler
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"ppo_{case}.npz"))
+    m = json.loads(str(z["meta"]))
+    scen, T = m["scenario"], int(m["T"])
+    params = ref_harness.scenario_params(scen, int(m["map"]), int(m["sen"]), m["den"], cap=int(m["cap"]),
+                                         loss=0.3 if case == "pp" else (0.2 if case == "pp_c3" else 0.0), max_env_steps=T)
+    env = (PredatorPreyWrapper(centralized=True, other_agent_visible=True, params=params) if scen == "pp"
+           else CoverageWrapper(centralized=True, other_agent_visible=True, max_steps=T, params=params))
+    spec = env.spec_b200
+    n, D, p, L, B, K = spec.n_agents, spec.obs_dim, spec.n_preys, spec.n_layers, 9, 2 * T + 3
+    assert (n, D) == (m["n"], m["D"])
+    pol = make_policy(spec)
+    sampler = DeviceRolloutSampler(SimpleNamespace(policy=pol, max_path_length=T), env, n_envs=B, chunk=K)
+    sampler.start_worker()
+    paths = sampler.obtain_samples(0, batch_size=1)            # one chunk of K steps, whole paths
+    # (1) layout of the reference sampler's paths
+    for key in ("observations", "actions", "avail_actions", "rewards", "dist_adjs", "channels"):
+        ref = z[f"path0::{key}"]
+        for pth in paths:
+            assert pth[key].shape[1:] == ref.shape[1:], key
+            if key != "observations" and not (key == "dist_adjs" and spec.rcom == 0):
+                assert pth[key].dtype == ref.dtype, (key, pth[key].dtype, ref.dtype)
+        assert np.array_equal(np.unique(z["path0::avail_actions"]), [1]) and all((pth["avail_actions"] == 1).all() for pth in paths)
+    # (2) content: an engine with the same seed / env ids records the same trajectory; cut it independently
+    spec.max_path_length = T
+    eng = RolloutEngine(spec, pol, B, ring=K, use_graph=False, record_attention=True)
+    eng.reset()
+    eng.run_chunk()
+    t = {k: v.cpu().numpy() for k, v in eng.traj.items()}
+    unpack = lambda bits: ((bits.view(np.uint32)[..., np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(np.float32)  # noqa: E731
+    want = []
+    for e in range(B):
+        start = 0
+        for k in np.nonzero(t["done"][:, e])[0]:
+            want.append((e, start, int(k) + 1))
+            start = int(k) + 1
+    assert len(want) == len(paths) >= B
+    for pth, (e, a, b) in zip(paths, want):
+        sl, T_ = slice(a, b), b - a
+        assert np.array_equal(pth["observations"], t["obs"][sl, e].reshape(T_, n * D))
+        assert np.array_equal(pth["actions"], t["actions"][sl, e].astype(np.int64))
+        assert np.array_equal(pth["rewards"], t["reward"][sl, e]) and pth["rewards"].dtype == np.float64
+        assert np.array_equal(pth["dones"], t["done"][sl, e].astype(bool))
+        assert np.array_equal(pth["dist_adjs"], unpack(t["adj_bits"][sl, e]).reshape(T_, n * n))
+        assert np.array_equal(pth["channels"], unpack(t["chan_bits"][sl, e]).reshape(T_, L * n, n))
+        assert np.array_equal(pth["agent_infos"]["action_probs"], t["probs"][sl, e])
+        assert np.array_equal(pth["agent_infos"]["attention_weights"], t["attention"][sl, e])
+        if p:
+            assert np.array_equal(pth["env_infos"]["prey_alive"], t["prey_alive_out"][sl, e, :p].astype(bool))
+        if spec.rcom != 0:
+            assert np.array_equal(pth["ave_degs"], t["ave_deg"][sl, e])
+        assert pth["success"][0] == t["success"][b - 1, e]
+        for det, c, r in zip(pth["rewards_details"], t["counts"][sl, e], t["reward"][sl, e]):
+            assert det["reward"] == r and det["step_cnt"] == 1
+            assert det["capture_cnt"] == (int(c[0]) if scen == "pp" else c[0] / float(n)) and det["move_cnt"] == c[1] / float(n)
+    sampler.shutdown_worker()

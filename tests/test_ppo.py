@@ -11,7 +11,9 @@ import pytest
 from oracle import oracle as orc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CASES = ["pp", "co", "pp_dec", "co_cent"]
+# pp_c3: BASELINE config 3's team (n = 32, IID drops); pp_n72 / pp_c5: teams larger than one 64-row tile (n = 72, and config
+# 5's n = 200, where the reference's per-step losses swing from -0.15 to +0.14: the joint ratio is a product over 200 agents)
+CASES = ["pp", "co", "pp_dec", "co_cent", "pp_c3", "pp_n72", "pp_c5"]
 
 
 class PPOCase:
