@@ -18,6 +18,13 @@
 //     row, the residual copy of E — stays in TENSOR MEMORY: the query is read straight from its accumulator by
 //     all four warps of the row's lane quadrant, the attention row and E are parked in dead accumulator columns
 //     with tcgen05.st and read back with tcgen05.ld.
+//   * teams of 17 .. 64 agents run the n x n part on the tensor cores too (kVec = 0): an env occupies a SLOT of 32 or 64 tile
+//     rows; scores = Q E^T as one 128 x 128 x 64 product over the whole tile (B operand = the E operand already in shared
+//     memory; the cross-env blocks are computed and ignored), softmax per row from tensor memory, and per layer the aggregation
+//     TRANSPOSED per env:  out_e^T [64 x S] = (H_l Wg_l)_e^T [64 x S keys] * A_e^T [S keys x S rows]  — an M = 64 product whose
+//     A operand is the value rows as written (MN-major) and whose B operand is the compact masked attention rows (K-major),
+//     so nothing is padded to the tile's 128 keys; the result comes back to the row-per-thread mapping through a swizzled fp32
+//     buffer.  Smaller teams keep the exact CUDA-core loops (a slot would waste most of the tile).
 // TMEM lane = tile row = thread (row = 32 * (warp % 4) + lane); the four warps that share a lane quadrant
 // split the accumulator columns.  Epilogues read TMEM with tcgen05.ld, apply bias + tanh, and write the next
 // A operand (hi / lo) straight into the canonical layout.
@@ -54,6 +61,7 @@ struct TcArgs {
     cm_policy_io io;
     TcPlan plan;
     int envs_per_tile;
+    int slot;                    // Comm-DP: tile rows per env — n (dense packing, CUDA-core attention) or 32 / 64 (tensor-core attention)
     int64_t n_tiles;
     int mode;                    // kTcModeComm / Dec / Enc / Head
     int in_dim;                  // width of the input rows (obs_dim; 64 in head mode: the rows are X = E + H_L)
@@ -81,6 +89,28 @@ __device__ __forceinline__ void write_act(unsigned char *act, int Kp, int row, i
         const uint32_t off = canon_off16(row, c0 + g, Kp);
         *reinterpret_cast<uint4 *>(act + off) = *reinterpret_cast<const uint4 *>(h);
         *reinterpret_cast<uint4 *>(act + lo_off + off) = *reinterpret_cast<const uint4 *>(l);
+    }
+}
+
+// Operands of the transposed aggregation product.  Single accumulator, so the remainder is NOT rescaled: x' = s x,
+// hi = fp16(x'), lo = fp16(x' - hi); the power-of-two scale s keeps lo out of the fp16 subnormals (values: s = 2^6, attention
+// weights: s = 2^10; the product is rescaled by 2^-16 in the epilogue).  Same chunked layout as write_act.
+static constexpr float kVScale = 64.0f, kPScale = 1024.0f, kPVUnscale = 1.0f / 65536.0f;
+template <int CW>
+__device__ __forceinline__ void write_unscaled(unsigned char *buf, int Kp, uint32_t lo_off, int row, int c0, const float (&v)[CW], float scale)
+{
+#pragma unroll
+    for (int g = 0; g < CW; g += 8) {
+        __align__(16) __half h[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float x = v[g + i] * scale;
+            h[i] = __float2half_rn(x);
+            l[i] = __float2half_rn(x - __half2float(h[i]));
+        }
+        const uint32_t off = canon_off16(row, c0 + g, Kp);
+        *reinterpret_cast<uint4 *>(buf + off) = *reinterpret_cast<const uint4 *>(h);
+        *reinterpret_cast<uint4 *>(buf + lo_off + off) = *reinterpret_cast<const uint4 *>(l);
     }
 }
 
@@ -260,6 +290,81 @@ __device__ __forceinline__ void scores_softmax(uint32_t lane_addr, const float *
     }
 }
 
+// Tensor-core attention: the scores of the whole tile are in tensor memory (hi*hi in columns [0, 128), the cross terms
+// in [128, 256), scaled by 2^12); the env of this row owns the key columns j0 .. j0 + n.  Thread (row, sub) takes the KT
+// consecutive keys sub * KT ..; same exchange and same result placement as scores_softmax.
+template <int KT>
+__device__ __forceinline__ void softmax_tc(uint32_t lane_addr, float *red, float *attn_row, int row, int j0, int sub, int n, bool valid)
+{
+    const int k0 = sub * KT;
+    const int nk = valid ? max(0, min(KT, n - k0)) : 0;
+    float sc[KT];
+#pragma unroll
+    for (int c = 0; c < KT; c += 8) {
+        float t0[8], t1[8];
+        tmem_ld8(lane_addr + (uint32_t)(j0 + k0 + c), t0);
+        tmem_ld8(lane_addr + (uint32_t)(128 + j0 + k0 + c), t1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sc[c + i] = fmaf(t1[i], 1.0f / 4096.0f, t0[i]);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < KT; ++t)
+        if (t < nk) mx = fmaxf(mx, sc[t]);
+    float sum = 0.0f;
+#pragma unroll
+    for (int t = 0; t < KT; ++t) {
+        sc[t] = t < nk ? __expf(sc[t] - mx) : 0.0f;
+        sum += sc[t];
+    }
+    red[sub * kTPitch + row] = mx;
+    red[(4 + sub) * kTPitch + row] = sum;
+    fence_before_thread_sync();
+    __syncthreads();                      // every thread has read its scores
+    fence_after_thread_sync();
+    float gm = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) gm = fmaxf(gm, red[s * kTPitch + row]);
+    float z = 0.0f;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const float ms = red[s * kTPitch + row];
+        z += ms > -INFINITY ? red[(4 + s) * kTPitch + row] * __expf(ms - gm) : 0.0f;
+    }
+    const float scale = nk > 0 ? __expf(mx - gm) / z : 0.0f;
+#pragma unroll
+    for (int t = 0; t < KT; ++t) sc[t] *= scale;
+    if (attn_row) {                       // unmasked softmax (agent_infos['attention_weights'])
+#pragma unroll
+        for (int t = 0; t < KT; ++t)
+            if (t < nk) attn_row[k0 + t] = sc[t];
+    }
+    tmem_st<8>(lane_addr + kColM + (uint32_t)k0, sc);
+    if constexpr (KT > 8) tmem_st<8>(lane_addr + kColM + (uint32_t)k0 + 8u, sc + 8);
+}
+
+// masked attention row of layer l -> B operand of the transposed aggregation (compact [128 rows][S keys], K-major) + this
+// thread's part of the row's masked sum
+template <int KT>
+__device__ __forceinline__ float masked_p_operand(uint32_t lane_addr, unsigned char *pbuf, int S, int row, int sub, int n, uint32_t m0, uint32_t m1)
+{
+    const int k0 = sub * KT;
+    float p[KT];
+    tmem_ld8(lane_addr + kColM + (uint32_t)k0, *reinterpret_cast<float(*)[8]>(p));
+    if constexpr (KT > 8) tmem_ld8(lane_addr + kColM + (uint32_t)k0 + 8u, *reinterpret_cast<float(*)[8]>(p + 8));
+    tmem_ld_wait();
+    const uint32_t mbits = (k0 < 32 ? m0 : m1) >> (k0 & 31);
+    float den = 0.0f;
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+        p[j] = (k0 + j < n && ((mbits >> j) & 1u)) ? p[j] : 0.0f;
+        den += p[j];
+    }
+    write_unscaled<KT>(pbuf, S, (uint32_t)kTcRows * S * 2, row, k0, p, kPScale);
+    return den;
+}
+
 // bias offsets inside the shared-memory bias table
 static constexpr int kBEnc1 = 0, kBEnc2 = 128, kBGcn = 192, kBH1 = 448, kBH2 = 576, kBH3 = 640, kBH4 = 672, kW4 = 680, kBiasFloats = 680 + kC3 * CM_ACTIONS;   // kW4: head_w4 [32][5] k-major
 
@@ -277,7 +382,8 @@ struct MmaOp { uint32_t dcol, acc, abuf; };   // accumulator block, accumulate f
 
 // kVec: width (in floats) of the shared-memory loads of the attention loops — 4 when the team size is a multiple of 4,
 // 2 when it is even, else 1 (the keys / values of an env start at a multiple of n floats).  One instantiation per width,
-// so that small odd teams (n = 3) carry none of the vector code.
+// so that small odd teams (n = 3) carry none of the vector code.  kVec = 0: the attention runs on the tensor cores (teams
+// of 17 .. 64 agents, env slots of 32 / 64 rows) and the kernel carries none of the CUDA-core attention loops.
 // kMode: kTcModeComm / Dec / Enc / Head as a template parameter, so that the Comm-DP kernel carries none of the other modes'
 // code (the kernel is instruction-fetch sensitive: its SASS is several times the instruction cache).
 template <int kVec, int kMode>
@@ -402,6 +508,26 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         issue_loads();
     };
     const MmaOp none = {0u, 0u, 0u};
+    // the same hand-shake for products whose operands are both written by the CTA (no weight stage is consumed)
+    auto run_custom = [&](auto issue) {
+        fence_proxy_async();
+        fence_before_thread_sync();
+        __syncthreads();
+        if (warp == 0) {
+            fence_after_thread_sync();
+            const uint32_t leader = elect_one() ? 1u : 0u;
+            if (!(CM_TC_DEBUG & 1)) issue(leader);
+            mma_commit_pred(&bars[2], leader);
+            __syncwarp();
+            ok = mbar_wait(&bars[2], m_phase) && ok;
+            fence_before_thread_sync();
+        }
+        m_phase ^= 1;
+        __syncthreads();
+        fence_after_thread_sync();
+    };
+    constexpr bool kAttnTc = kVec == 0;
+    const int S = A.slot, slog = S == 64 ? 6 : 5;          // (slog is only meaningful with kAttnTc: S = 32 or 64)
 
     // dense epilogue of a 64-wide product: this thread's 16 columns -> bias, tanh -> next A operand (K panel of 64)
     auto epi64 = [&](uint32_t blk, int bias0, unsigned char *dst) {
@@ -488,11 +614,17 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int row0, rows;
         tile_rows(tile, row0, rows);
-        const bool valid = row < rows;
-        const int g = row0 + row;
+        bool valid = row < rows;
+        int g = row0 + row;
         // Comm-DP: env index inside the tile / agent index / first row of the env; Obs-DP rows are independent
-        const int el = valid ? (dec ? g / n : row / n) : 0;
-        const int il = valid ? (dec ? g - el * n : row - el * n) : 0, j0 = dec ? 0 : el * n;
+        int el = valid ? (dec ? g / n : row / n) : 0;
+        int il = valid ? (dec ? g - el * n : row - el * n) : 0, j0 = dec ? 0 : el * n;
+        if constexpr (kAttnTc) {            // env slots of S tile rows: slot el holds agents 0 .. n - 1, the rest of the slot is padding
+            el = row >> slog; il = row & (S - 1); j0 = el << slog;
+            valid = il < n && el * n < rows;
+            g = row0 + el * n + il;
+            if (!valid) { el = 0; il = 0; }
+        }
         const int env = dec ? el : row0 / n + el;
         const bool next_has = tile + (int)gridDim.x < n_tiles;
         si = 0;
@@ -512,11 +644,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                 for (int e8 = tid; e8 < kTcRows * kg; e8 += kTcThreads) {           // one group of 8 columns of one row
                     const int r = (int)(((uint32_t)e8 * inv) >> 16), k8 = (e8 - r * kg) << 3;
                     __align__(16) __half h[8], l[8];
+                    int rr = r;                                  // row of the tile's observation block behind tile row r
+                    if constexpr (kAttnTc) { const int e_ = r >> slog, i_ = r & (S - 1); rr = i_ < n ? e_ * n + i_ : rows; }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int k = kofs + k8 + j, i = r * Din + k;
+                        const int k = kofs + k8 + j, i = rr * Din + k;
                         float x = 0.0f;
-                        if (r < rows && k < Din) x = i < ns ? stage[a + i] : __ldg(src + i);
+                        if (rr < rows && k < Din) x = i < ns ? stage[a + i] : __ldg(src + i);
                         split16(x, h[j], l[j]);
                     }
                     const uint32_t off = canon_off16(r, k8, Kp);
@@ -539,7 +673,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
             const float4 *bp = reinterpret_cast<const float4 *>(bias_s + kBEnc2 + 16 * sub);
 #pragma unroll
             for (int q = 0; q < 4; ++q) tanh4(v + 4 * q, w + 4 * q, bp[q]);
-            if (!dec) {
+            if (!dec && !kAttnTc) {
 #pragma unroll
                 for (int c = 0; c < 16; ++c) KV[(16 * sub + c) * kTPitch + row] = v[c];
             }
@@ -575,6 +709,141 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
             run_mma(1, MmaOp{kR1, 0u, 0u}, none);
         } else {
         if (mode == kTcModeComm) {
+        if constexpr (kAttnTc) {
+        // ================= tensor-core attention (17 <= n <= 64; env slots of S = 32 / 64 rows) =================
+        load_mask(env, il, 0, valid);
+        run_mma(1, MmaOp{kR0, 0u, 0u}, none);                              // Q = E Wa -> R0
+        {   // the query rows become the A operand of the score product (the second operand buffer is idle)
+            float q[16];
+            ld_acc<16>(lane_addr + kR0, 64, 16 * sub, q);
+            write_act<16>(ACT2, 64, row, 16 * sub, q);
+        }
+        // scores of the whole tile: [128 rows] x [128 keys] = Q E^T; the B operand [E_hi ; E_lo] IS the A operand the encoder
+        // epilogue left in ACT (same K-major core-matrix layout, lo block 128 rows further).  hi*hi -> columns [0, 128),
+        // cross terms -> [128, 256): the whole tensor memory of the CTA — H_0 Wg_0 is issued afterwards.
+        CM_TP(0);
+        run_custom([&](uint32_t leader) { issue_layer(tmem + kR0, ACT2, ACT, 128, 64, 0u, leader); });
+        {
+            float *attn_row = (io.attention && valid) ? io.attention + (size_t)g * n : nullptr;
+            if (S == 32) softmax_tc<8>(lane_addr, red, attn_row, row, j0, sub, n, valid);
+            else softmax_tc<16>(lane_addr, red, attn_row, row, j0, sub, n, valid);
+        }
+        const uint32_t v_lo = (uint32_t)kTcRows * 64 * 2;                  // lo block of the value operand / of a 64-wide A operand
+        {   // E (this thread's 16 columns of the A operand) -> tensor memory, for the residual: ACT becomes the attention operand.
+            // (the barriers of the product below separate these reads from the first attention rows written into ACT)
+            if (d.residual) {
+                float ev[16];
+#pragma unroll
+                for (int g8 = 0; g8 < 16; g8 += 8) {
+                    const uint32_t off = canon_off16(row, 16 * sub + g8, 64);
+                    const uint4 hq = *reinterpret_cast<const uint4 *>(ACT + off);
+                    const uint4 lq = *reinterpret_cast<const uint4 *>(ACT + v_lo + off);
+                    const __half2 *hh = reinterpret_cast<const __half2 *>(&hq), *ll = reinterpret_cast<const __half2 *>(&lq);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 hf = __half22float2(hh[i]), lf = __half22float2(ll[i]);
+                        ev[g8 + 2 * i] = fmaf(lf.x, 1.0f / 4096.0f, hf.x);
+                        ev[g8 + 2 * i + 1] = fmaf(lf.y, 1.0f / 4096.0f, hf.y);
+                    }
+                }
+                tmem_st<8>(lane_addr + kColE + (uint32_t)(16 * sub), ev);
+                tmem_st<8>(lane_addr + kColE + (uint32_t)(16 * sub + 8), ev + 8);
+                tmem_st_wait();
+            }
+            tmem_st_wait();
+        }
+        CM_TP(1);
+        run_mma(1, MmaOp{kR1, 0u, 0u}, none);                              // H_0 Wg_0 -> R1 (the scores are dead)
+        {   // values -> A operand of the transposed aggregation (as written: [key][64], i.e. MN-major)
+            float v[16];
+            ld_acc<16>(lane_addr + kR1, 64, 16 * sub, v);
+            write_unscaled<16>(ACT2, 64, v_lo, row, 16 * sub, v, kVScale);
+        }
+        CM_TP(2);
+        const int n_slots = kTcRows >> slog;                                // envs per tile
+        for (int l = 0; l < L; ++l) {
+            // A_l = M * Range * chan_l (comm_base_net.py:101): this thread's keys -> B operand rows in ACT (E / H_l are dead
+            // there); the row's masked sum through one exchange
+            const float dpart = S == 32 ? masked_p_operand<8>(lane_addr, ACT, S, row, sub, n, m0, m1)
+                                        : masked_p_operand<16>(lane_addr, ACT, S, row, sub, n, m0, m1);
+            red[sub * kTPitch + row] = dpart;
+            // out_e^T [64 x S] = V_e^T [64 x S keys] A_e^T [S keys x S rows] for every env slot e, three fp16 products each
+            // into ONE accumulator (columns e S .. of R1; row c of the result = lane 32 (c / 16) + c % 16)
+            run_custom([&](uint32_t leader) {
+                const uint32_t idesc = make_idesc_f16(64, S) | kIdescAMajorMN;
+                const uint32_t a0 = smem_u32(ACT2), b0 = smem_u32(ACT), p_lo = (uint32_t)kTcRows * S * 2;
+                for (int e = 0; e < n_slots; ++e) {
+                    const uint32_t dcol = tmem + kR1 + (uint32_t)(e << slog);
+                    const uint32_t ae = a0 + (uint32_t)e * (uint32_t)S * 128u;                       // key rows e S ..: 128 bytes per key
+                    const uint32_t be = b0 + (uint32_t)e * (uint32_t)(S >> 3) * (uint32_t)(S >> 3) * 128u;   // query rows e S ..
+                    for (int j = 0; j < (S >> 4); ++j) {
+                        const uint64_t da_hi = make_smem_desc16_mn(ae + (uint32_t)j * 2048u, 64), da_lo = make_smem_desc16_mn(ae + v_lo + (uint32_t)j * 2048u, 64);
+                        const uint64_t db_hi = make_smem_desc16(be, S, j), db_lo = make_smem_desc16(be + p_lo, S, j);
+                        mma_f16_pred(dcol, da_hi, db_hi, idesc, j ? 1u : 0u, leader);
+                        mma_f16_pred(dcol, da_hi, db_lo, idesc, 1u, leader);
+                        mma_f16_pred(dcol, da_lo, db_hi, idesc, 1u, leader);
+                    }
+                }
+            });
+            const float den = ((red[row] + red[kTPitch + row]) + red[2 * kTPitch + row]) + red[3 * kTPitch + row];
+            CM_TP(3 + 4 * l);
+            {   // out^T (tensor memory: lane = column c, columns = tile rows) -> T[c][row] fp32, 16-byte chunks XOR-swizzled by c
+                const int c = 16 * quad + (lane & 15);
+                float4 *Tc = reinterpret_cast<float4 *>(KV + c * kTPitch);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float v8[8];
+                    tmem_ld8(lane_addr + kR1 + (uint32_t)(32 * sub + 8 * i), v8);
+                    tmem_ld_wait();
+                    if (lane < 16) {
+                        const int rc = (32 * sub + 8 * i) >> 2;
+                        Tc[rc ^ (c & 7)] = make_float4(v8[0], v8[1], v8[2], v8[3]);
+                        Tc[(rc + 1) ^ (c & 7)] = make_float4(v8[4], v8[5], v8[6], v8[7]);
+                    }
+                }
+                fence_before_thread_sync();
+                __syncthreads();
+                fence_after_thread_sync();
+            }
+            // H_{l+1} = tanh(out / (sum + 1e-12) + b) for this thread's 16 columns (graph_conv_module.py:51-72)
+            const float inv = kTanhScale * kPVUnscale / (den + 1e-12f);
+            float v[16];
+            const float4 *bp = reinterpret_cast<const float4 *>(bias_s + kBGcn + l * 64 + 16 * sub);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 b4 = bp[q];
+                float t4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c = 16 * sub + 4 * q + i;
+                    t4[i] = KV[c * kTPitch + ((((row >> 2) ^ (c & 7)) << 2) | (row & 3))];
+                }
+                v[4 * q + 0] = tanh_scaled(fmaf(t4[0], inv, b4.x));
+                v[4 * q + 1] = tanh_scaled(fmaf(t4[1], inv, b4.y));
+                v[4 * q + 2] = tanh_scaled(fmaf(t4[2], inv, b4.z));
+                v[4 * q + 3] = tanh_scaled(fmaf(t4[3], inv, b4.w));
+            }
+            if (d.residual && l + 1 == L) {               // X = E + H_L (comm_base_net.py:105-106)
+                float ev[16];
+                tmem_ld8(lane_addr + kColE + (uint32_t)(16 * sub), *reinterpret_cast<float(*)[8]>(ev));
+                tmem_ld8(lane_addr + kColE + (uint32_t)(16 * sub + 8), *reinterpret_cast<float(*)[8]>(ev + 8));
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] += ev[c];
+            }
+            write_act<16>(ACT, 64, row, 16 * sub, v);
+            CM_TP(4 + 4 * l);
+            if (l + 1 < L) {
+                load_mask(env, il, l + 1, valid);
+                run_mma(1, MmaOp{kR1, 0u, 0u}, none);         // H_{l+1} Wg_{l+1} -> R1 (the transposed result has been read)
+                CM_TP(5 + 4 * l);
+                float hv[16];
+                ld_acc<16>(lane_addr + kR1, 64, 16 * sub, hv);
+                write_unscaled<16>(ACT2, 64, v_lo, row, 16 * sub, hv, kVScale);
+            }
+        }
+        } else {
+        // ================= exact CUDA-core attention (n <= 16) =================
         load_mask(env, il, 0, valid);
         run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR1, 0u, 0u});
         // ---------------- scores, softmax (exact per environment, CUDA cores); attention row -> TMEM ----------------
@@ -714,6 +983,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                 __syncthreads();
             }
         }
+        }   // CUDA-core attention
         // ---------------- categorical head ----------------
         run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR1, 0u, 0u});                       // 64 -> 128 as two output halves
         }   // Comm-DP only (head mode enters here: its first two products came with the input rows)
@@ -839,6 +1109,13 @@ __global__ void tc_prepare_kernel(const float *__restrict__ w, __half *__restric
     }
 }
 
+// experiments / cross-checks only: CM_TC_ATTENTION=cuda keeps the CUDA-core attention loops for every team size
+static bool cm_tc_attention_disabled()
+{
+    static const int off = [] { const char *e = getenv("CM_TC_ATTENTION"); return (e && e[0] == 'c') ? 1 : 0; }();
+    return off != 0;
+}
+
 static size_t tc_smem_bytes() { return (size_t)kActBytes + kWBytes + (64 + 8) * kTPitch * 4 + kBiasFloats * 4 + 64; }
 
 static int launch_tc_mode(const cm_policy_desc *desc, const cm_policy_io *io, int mode, int in_dim, float *scr_e, float *scr_q,
@@ -855,17 +1132,22 @@ static int launch_tc_mode(const cm_policy_desc *desc, const cm_policy_io *io, in
     A.in_dim = in_dim;
     A.scr_e = scr_e; A.scr_q = scr_q; A.scr_hw = scr_hw;
     A.plan = make_tc_plan(desc->obs_dim, desc->n_layers, mode);
-    A.envs_per_tile = rows_mode ? 0 : kTcRows / desc->n_agents;
+    // Comm-DP teams of 17 .. 64 agents: attention on the tensor cores, an env per slot of 32 / 64 tile rows (a slot is a
+    // multiple of the warp size, so a warp's rows share their env's key columns); smaller teams: dense packing, CUDA cores
+    const bool attn_tc = !rows_mode && desc->n_agents > 16 && !cm_tc_attention_disabled();
+    A.slot = rows_mode ? 0 : (attn_tc ? (desc->n_agents <= 32 ? 32 : 64) : desc->n_agents);
+    A.envs_per_tile = rows_mode ? 0 : kTcRows / A.slot;
     A.n_tiles = rows_mode ? (io->n_envs * desc->n_agents + kTcRows - 1) / kTcRows : (io->n_envs + A.envs_per_tile - 1) / A.envs_per_tile;
     const size_t smem = tc_smem_bytes();
-    const int vec = rows_mode ? 1 : ((desc->n_agents & 3) == 0 ? 4 : ((desc->n_agents & 1) == 0 ? 2 : 1));
+    const int vec = rows_mode ? 1 : (attn_tc ? 0 : ((desc->n_agents & 3) == 0 ? 4 : ((desc->n_agents & 1) == 0 ? 2 : 1)));
     void (*kernel)(const TcArgs) =
         mode == kTcModeDec ? policy_tc_kernel<1, kTcModeDec>
         : mode == kTcModeEnc ? policy_tc_kernel<1, kTcModeEnc>
         : mode == kTcModeHead ? policy_tc_kernel<1, kTcModeHead>
+        : vec == 0 ? policy_tc_kernel<0, kTcModeComm>
         : vec == 4 ? policy_tc_kernel<4, kTcModeComm> : (vec == 2 ? policy_tc_kernel<2, kTcModeComm> : policy_tc_kernel<1, kTcModeComm>);
-    static thread_local struct { int dev; int sms; } cache[6] = {{-1, 0}, {-1, 0}, {-1, 0}, {-1, 0}, {-1, 0}, {-1, 0}};
-    auto &cc = cache[mode == kTcModeComm ? (vec >> 1) : 2 + mode];
+    static thread_local struct { int dev; int sms; } cache[7] = {{-1, 0}, {-1, 0}, {-1, 0}, {-1, 0}, {-1, 0}, {-1, 0}, {-1, 0}};
+    auto &cc = cache[mode == kTcModeComm ? (vec == 0 ? 6 : (vec >> 1)) : 2 + mode];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ENODEVICE);
     if (cc.dev != dev) {

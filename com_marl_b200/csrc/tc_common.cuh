@@ -49,6 +49,20 @@ __device__ __forceinline__ uint64_t make_smem_desc16(uint32_t smem_addr, int K, 
     d |= (uint64_t)1 << 46;
     return d;
 }
+// MN-major operand (memory [K][M or N], the M / N index contiguous) without swizzle, stored in the same chunked form as a
+// K-major tile of `cols` columns written row by row:  byte(k, m) = (k / 8) * (cols / 8) * 128 + (m / 8) * 128 + (k % 8) * 16 + (m % 8) * 2.
+// Measured on B200 (tests/native/mn_probe.cu): for an MN-major operand LBO is the stride between groups of 8 K rows and SBO
+// the stride between 16-byte chunks (8 elements) along M / N; an instruction of K = 16 consumes two K groups.
+__device__ __forceinline__ uint64_t make_smem_desc16_mn(uint32_t smem_addr, int cols)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(((uint32_t)(cols >> 3) * 128u) >> 4) << 16;   // LBO: next group of 8 K rows
+    d |= (uint64_t)(128u >> 4) << 32;                             // SBO: next 8 elements along M / N
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+static constexpr uint32_t kIdescAMajorMN = 1u << 15, kIdescBMajorMN = 1u << 16;   // instruction descriptor: operand is MN-major
 // kind::f16 with fp16 operands (format 0), fp32 accumulate
 __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N)
 {

@@ -59,6 +59,7 @@ def test_policy_kernel_matches_reference_golden(name, math):
 @pytest.mark.parametrize("math", ["fp32", "tc", "tc_fp32attn"])
 @pytest.mark.parametrize("n,D,B,ploss", [(3, 29, 16384, 0.0), (4, 21, 5000, 0.3), (32, 53, 2048, 0.2), (54, 77, 777, 0.1),
                                          (7, 53, 1001, 0.5), (64, 29, 64, 0.4), (1, 21, 100, 0.0),
+                                         (16, 53, 333, 0.2), (17, 21, 250, 0.3), (33, 29, 203, 0.1), (40, 77, 131, 0.5),
                                          (65, 21, 70, 0.2), (72, 53, 301, 0.3), (200, 53, 97, 0.2), (256, 29, 9, 0.5),
                                          (129, 29, 33, 0.3), (96, 77, 40, 0.1), (193, 21, 5, 0.6)])
 def test_policy_kernel_matches_oracle_batched(n, D, B, ploss, math):
