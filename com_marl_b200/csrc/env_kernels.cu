@@ -21,6 +21,11 @@ namespace cm {
 
 typedef unsigned long long u64;
 
+// 1: exact parallel move resolution (resolve_agents / resolve_preys); 0: the order-dependent loops on the group's lane 0.
+// Both are bit-exact against the reference; which one is compiled in is a measured choice.
+#ifndef CM_ENV_PARALLEL_MOVES
+#define CM_ENV_PARALLEL_MOVES 0
+#endif
 static constexpr int kWarpsPerCta = 8;
 // per-CTA constants in shared memory: wall rows [64] u64 | k / n as IEEE doubles for k = 0 .. n (<= 256) [257] f64
 static constexpr int kConstBytes = 64 * 8 + 264 * 8;
@@ -48,11 +53,19 @@ struct Scratch {
     int8_t *act;     // [n_pad]
     uint8_t *kcnt;   // [p_pad] agents around prey j
     int8_t *mv;      // [p_pad] screened random move of prey j
+    // parallel move resolution (resolve_agents / resolve_preys)
+    u64 *x1, *x2, *x3;   // [G] each: cells that may change / cells targeted once / cells targeted more than once
+    uint16_t *tgtA;  // [n_pad] target cell of agent i (0xFFFF: does not try to move)
+    uint16_t *finA;  // [n_pad] position of agent i after its turn
+    uint16_t *tgtP;  // [p_pad]
+    uint16_t *finP;  // [p_pad]
+    uint8_t *alvF;   // [p_pad] prey j alive after its turn
+    uint8_t *slow;   // [max(n_pad, p_pad)] entity must be resolved in index order
 };
 
 __host__ __device__ inline int env_warp_bytes(int n_pad, int p_pad, int G)
 {
-    return 2 * G * 8 + 6 * n_pad * 4 + n_pad * 2 + p_pad * 2 + p_pad + n_pad + p_pad + p_pad;
+    return 5 * G * 8 + 6 * n_pad * 4 + 3 * n_pad * 2 + 3 * p_pad * 2 + p_pad + n_pad + p_pad + p_pad + p_pad + (n_pad > p_pad ? n_pad : p_pad);
 }
 
 __device__ __forceinline__ Scratch carve(unsigned char *base, int n_pad, int p_pad, int G)
@@ -60,13 +73,22 @@ __device__ __forceinline__ Scratch carve(unsigned char *base, int n_pad, int p_p
     Scratch s;
     s.occA = reinterpret_cast<u64 *>(base);
     s.occB = s.occA + G;
-    s.win = reinterpret_cast<uint32_t *>(s.occB + G);
+    s.x1 = s.occB + G;
+    s.x2 = s.x1 + G;
+    s.x3 = s.x2 + G;
+    s.win = reinterpret_cast<uint32_t *>(s.x3 + G);
     s.posA = reinterpret_cast<uint16_t *>(s.win + 6 * n_pad);
-    s.posP = s.posA + n_pad;
-    s.alive = reinterpret_cast<uint8_t *>(s.posP + p_pad);
+    s.tgtA = s.posA + n_pad;
+    s.finA = s.tgtA + n_pad;
+    s.posP = s.finA + n_pad;
+    s.tgtP = s.posP + p_pad;
+    s.finP = s.tgtP + p_pad;
+    s.alive = reinterpret_cast<uint8_t *>(s.finP + p_pad);
     s.act = reinterpret_cast<int8_t *>(s.alive + p_pad);
     s.kcnt = reinterpret_cast<uint8_t *>(s.act + n_pad);
     s.mv = reinterpret_cast<int8_t *>(s.kcnt + p_pad);
+    s.alvF = reinterpret_cast<uint8_t *>(s.mv + p_pad);
+    s.slow = s.alvF + p_pad;
     return s;
 }
 
@@ -144,6 +166,8 @@ struct Grp {
         return v;
     }
     __device__ __forceinline__ int any(int pred) const { return __any_sync(mask, pred); }
+    // bit k = predicate of the group's lane k
+    __device__ __forceinline__ unsigned ballot(int pred) const { return (__ballot_sync(mask, pred) & mask) >> (__ffs(mask) - 1); }
     __device__ __forceinline__ int bcast0(int v) const { return __shfl_sync(mask, v, 0, gs); }
 };
 
@@ -201,7 +225,7 @@ __device__ __forceinline__ uint32_t link_row_bits(ChanSrc &src, int plane, int i
 // ------------------------------------------------------------------------------------------------
 // communication state: get_graph + channels (env_communication.py:91-157,200-243)
 // ------------------------------------------------------------------------------------------------
-__device__ void comm_update(const EnvArgs &A, const Scratch &S, int64_t b, const Grp &G, const RngKey &key, bool at_reset)
+__device__ __forceinline__ void comm_update(const EnvArgs &A, const Scratch &S, int64_t b, const Grp &G, const RngKey &key, bool at_reset)
 {
     const cm_env_desc &d = A.d;
     const int n = d.n_agents, L = d.n_layers, W = (n + 31) >> 5;
@@ -295,7 +319,7 @@ __device__ void comm_update(const EnvArgs &A, const Scratch &S, int64_t b, const
 // ------------------------------------------------------------------------------------------------
 // reset / spawn (predator_prey.py:150-171,206-232; coverage.py:172-196,221-246)
 // ------------------------------------------------------------------------------------------------
-__device__ void reset_env(const EnvArgs &A, const Scratch &S, const u64 *wall, int64_t b, const Grp &G,
+__device__ __forceinline__ void reset_env(const EnvArgs &A, const Scratch &S, const u64 *wall, int64_t b, const Grp &G,
                           RngKey &key, int &t, int &total_capture)
 {
     const cm_env_desc &d = A.d;
@@ -369,7 +393,7 @@ __device__ void reset_env(const EnvArgs &A, const Scratch &S, const u64 *wall, i
 // (window after window, <= 75 bits -> 3 words) next to the agent's 3 scalar features.  Phase 2: the env's [n][D] block is
 // contiguous, so the group streams it out flat — consecutive lanes store consecutive floats (fully coalesced), one
 // shift + mask + convert per float, no divergent select chain.
-__device__ void write_obs(const EnvArgs &A, const Scratch &S, const u64 *wall, int64_t b, const Grp &G, int t)
+__device__ __forceinline__ void write_obs(const EnvArgs &A, const Scratch &S, const u64 *wall, int64_t b, const Grp &G, int t)
 {
     const cm_env_desc &d = A.d;
     if (!A.io.obs) return;
@@ -415,6 +439,204 @@ __device__ void write_obs(const EnvArgs &A, const Scratch &S, const u64 *wall, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// Parallel move resolution.  The reference moves entities ONE AFTER ANOTHER in index order (agents:
+// predator_prey.py:497-500,240-261 / coverage.py:330-375; preys: predator_prey.py:417-432 / :460-478), so an entity sees
+// its predecessors where they ended up and its successors where they started.  Almost all moves of a step do not interact:
+// an entity takes the FAST path — its outcome is read off the occupancy at the start of the loop, all lanes in parallel —
+// unless a cell it depends on may change during the loop (it is the position of another entity that may move or vanish,
+// or somebody else targets it too); those few are resolved in index order afterwards, each by the whole lane group (every
+// lane compares its own entities' positions "at that turn": final for lower indices, initial for higher ones).  The
+// interaction test may over-approximate (it ignores index order); the slow path is always exact.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool test_bit(const u64 *rows, uint16_t cell) { return (rows[cell & 0xFF] >> (cell >> 8)) & 1ull; }
+// atomically sets the cell's bit, returns whether it was set before
+__device__ __forceinline__ bool test_and_set(u64 *rows, uint16_t cell)
+{
+    const int c = cell >> 8;
+    const unsigned bit = 1u << (c & 31);
+    return atomicOr(reinterpret_cast<unsigned int *>(rows + (cell & 0xFF)) + (c >> 5), bit) & bit;
+}
+__device__ __forceinline__ bool adjacent4(uint16_t a, uint16_t b)
+{
+    const int dr = (int)(a & 0xFF) - (int)(b & 0xFF), dc = (int)(a >> 8) - (int)(b >> 8);
+    return dr * dr + dc * dc == 1;
+}
+
+// entities in the 4-neighbourhood of the IN-GRID cell (r, c), counted on rows combined on the fly (kOr: a | b, else a & ~b);
+// rows carry no bits at columns >= G
+template <bool kOr>
+__device__ __forceinline__ int count4_in(const u64 *a, const u64 *b, int r, int c, int G)
+{
+    auto row = [&](int rr) { return kOr ? (a[rr] | b[rr]) : (a[rr] & ~b[rr]); };
+    int cnt = __popcll(((row(r) << 1) >> c) & 5ull);
+    if (r > 0) cnt += (int)((row(r - 1) >> c) & 1ull);
+    if (r + 1 < G) cnt += (int)((row(r + 1) >> c) & 1ull);
+    return cnt;
+}
+
+// Agents of one env.  `fixed` = rows of the cells that block a move and do not change while agents move (PredatorPrey: the
+// preys; Coverage: the walls).  On return S.finA holds every agent's position after the loop (S.posA still the initial one)
+// and S.tgtA its target (0xFFFF: NOOP, or a move off the grid when !count_oob).  Returns this lane's number of movers that were blocked
+// (Coverage's penalty count; moves off the grid included).
+__device__ __forceinline__ int resolve_agents(const Scratch &S, const Grp &G, int n, int Gd, const u64 *fixed)
+{
+    for (int r = G.gl; r < Gd; r += G.gs) { S.x1[r] = 0ull; S.x2[r] = 0ull; S.x3[r] = 0ull; }
+    G.sync();
+    int blocked = 0;
+#pragma unroll 1
+    for (int i = G.gl; i < n; i += G.gs) {
+        const int a = S.act[i];
+        const uint16_t q = S.posA[i];
+        uint16_t tg = 0xFFFF;
+        if (a != 4) {
+            const int nr = (q & 0xFF) + d_row(a), nc = (q >> 8) + d_col(a);
+            if (nr >= 0 && nr < Gd && nc >= 0 && nc < Gd) tg = (uint16_t)(nr | (nc << 8));
+            else ++blocked;
+        }
+        S.tgtA[i] = tg;
+        S.finA[i] = q;
+        if (tg != 0xFFFF) {
+            set_bit(S.x1, q & 0xFF, q >> 8);                       // a mover's cell may become free
+            if (test_and_set(S.x2, tg)) set_bit(S.x3, tg & 0xFF, tg >> 8);   // targeted more than once
+        }
+    }
+    G.sync();
+#pragma unroll 1
+    for (int i = G.gl; i < n; i += G.gs) {
+        const uint16_t tg = S.tgtA[i];
+        bool slow = false;
+        if (tg != 0xFFFF) {
+            slow = test_bit(S.x1, tg) || test_bit(S.x3, tg);
+            if (!slow) {                                           // nobody else touches the target: the initial occupancy decides
+                if (test_bit(S.occA, tg) || test_bit(fixed, tg)) ++blocked;
+                else S.finA[i] = tg;
+            }
+        }
+        S.slow[i] = slow;
+    }
+    G.sync();
+#pragma unroll 1
+    for (int base = 0; base < n; base += G.gs) {
+        unsigned m = G.ballot(base + G.gl < n && S.slow[base + G.gl]);
+        while (m) {
+            const int is = base + __ffs(m) - 1;
+            m &= m - 1;
+            const uint16_t tg = S.tgtA[is];
+            int hit = 0;
+#pragma unroll 1
+            for (int k = G.gl; k < n; k += G.gs)
+                if (k != is) hit |= (k > is ? S.posA[k] : S.finA[k]) == tg;
+            const bool free = !G.any(hit) && !test_bit(fixed, tg);
+            if (G.gl == (is & (G.gs - 1))) {
+                if (free) S.finA[is] = tg;
+                else ++blocked;
+            }
+            G.sync();
+        }
+    }
+    return blocked;
+}
+
+// Preys of one env (PredatorPrey), after the agents have moved (S.occA final) and S.kcnt / S.mv have been computed.  On
+// return S.finP / S.alvF hold every prey's position / alive flag after the loop.  Returns this lane's (captures | penalties << 16).
+__device__ __forceinline__ int resolve_preys(const Scratch &S, const Grp &G, int p, int Gd, int load)
+{
+    for (int r = G.gl; r < Gd; r += G.gs) { S.x1[r] = 0ull; S.x2[r] = 0ull; S.x3[r] = 0ull; }
+    G.sync();
+#pragma unroll 1
+    for (int j = G.gl; j < p; j += G.gs) {
+        const uint16_t q = S.posP[j];
+        uint16_t tg = 0xFFFF;
+        const int al = S.alive[j];
+        if (al) {
+            const int mv = S.mv[j];
+            if (mv != 4) {
+                const int nr = (q & 0xFF) + d_row(mv), nc = (q >> 8) + d_col(mv);
+                if (nr >= 0 && nr < Gd && nc >= 0 && nc < Gd) tg = (uint16_t)(nr | (nc << 8));
+            }
+            if (S.kcnt[j] >= 1 || tg != 0xFFFF) set_bit(S.x1, q & 0xFF, q >> 8);     // may be captured or walk away
+            if (tg != 0xFFFF && test_and_set(S.x2, tg)) set_bit(S.x3, tg & 0xFF, tg >> 8);
+        }
+        S.tgtP[j] = tg;
+        S.finP[j] = q;
+        S.alvF[j] = (uint8_t)al;
+    }
+    G.sync();
+    // capture rule of one prey given the preys around it (:419-431 / :462-477; edges dict :123-144)
+    auto need_of = [&](int r, int c, int prey_nb) {
+        if (load == 2) return load;
+        const int re = (r == 0 || r == Gd - 1), ce = (c == 0 || c == Gd - 1);
+        const int nadj = (re && ce) ? 2 : ((re || ce) ? 3 : load);
+        return min(load, nadj - prey_nb);
+    };
+    int capture = 0, penalty = 0;
+#pragma unroll 1
+    for (int j = G.gl; j < p; j += G.gs) {
+        bool slow = false;
+        if (S.alive[j]) {
+            const uint16_t q = S.posP[j], tg = S.tgtP[j];
+            const int r = q & 0xFF, c = q >> 8, k = S.kcnt[j];
+            // Captured or not (only preys next to an agent are tested)?  The rule of reward_individual looks at the preys
+            // around this one, which may change during the loop; its outcome is fixed anyway when it is the same for the
+            // FEWEST preys that can be around (those that surely stay) and for the MOST (every cell a prey stands on or walks
+            // to — its own target, one of the four cells, does not count unless it is somebody else's too)
+            int state = 0;                                         // 0 stays, 1 captured, 2 depends on the order
+            if (k >= 1) {
+                if (load == 2) state = 1;                          // reward_default: need = load = 2 <= k ... see below
+                else {
+                    const int own = (tg != 0xFFFF && !test_bit(S.occB, tg) && !test_bit(S.x3, tg)) ? 1 : 0;
+                    const int most = count4_in<true>(S.occB, S.x2, r, c, Gd) - own, fewest = count4_in<false>(S.occB, S.x1, r, c, Gd);
+                    const bool cap_most = need_of(r, c, most) <= k, cap_fewest = need_of(r, c, fewest) <= k;
+                    state = cap_most == cap_fewest ? (int)cap_most : 2;
+                }
+                if (load == 2) state = load <= k;
+            }
+            const bool walk_slow = tg != 0xFFFF && (test_bit(S.x1, tg) || test_bit(S.x3, tg));
+            slow = state == 2 || (state == 0 && walk_slow);
+            if (!slow) {
+                if (state == 1) { ++capture; S.alvF[j] = 0; }
+                else {
+                    penalty += k >= 1;
+                    if (tg != 0xFFFF && !test_bit(S.occA, tg) && !test_bit(S.occB, tg)) S.finP[j] = tg;
+                }
+            }
+        }
+        S.slow[j] = slow;
+    }
+    G.sync();
+#pragma unroll 1
+    for (int base = 0; base < p; base += G.gs) {
+        unsigned m = G.ballot(base + G.gl < p && S.slow[base + G.gl]);
+        while (m) {
+            const int js = base + __ffs(m) - 1;
+            m &= m - 1;
+            const uint16_t q = S.posP[js], tg = S.tgtP[js];
+            const int r = q & 0xFF, c = q >> 8, k = S.kcnt[js];
+            int around = 0, hit = 0;
+#pragma unroll 1
+            for (int o = G.gl; o < p; o += G.gs) {
+                if (o == js) continue;
+                const bool al = o > js ? S.alive[o] != 0 : S.alvF[o] != 0;
+                const uint16_t po = o > js ? S.posP[o] : S.finP[o];
+                around += al && adjacent4(po, q);
+                hit |= al && po == tg;
+            }
+            const bool owner = G.gl == (js & (G.gs - 1));
+            bool gone = false;
+            if (k >= 1) {
+                const int prey_nb = load != 2 ? G.sum(around) : 0;
+                if (need_of(r, c, prey_nb) <= k) { gone = true; if (owner) { ++capture; S.alvF[js] = 0; } }
+                else if (owner) ++penalty;
+            }
+            const bool blocked = G.any(hit) || tg == 0xFFFF || test_bit(S.occA, tg);
+            if (owner && !gone && !blocked) S.finP[js] = tg;
+            G.sync();
+        }
+    }
+    return capture | (penalty << 16);
+}
+
+// ------------------------------------------------------------------------------------------------
 // the kernel: mode 0 = VecEnvExecutor.step, 1 = reset(mask), 2 = comm only
 // ------------------------------------------------------------------------------------------------
 #ifdef CM_ENV_TRACE
@@ -423,8 +645,20 @@ __device__ void write_obs(const EnvArgs &A, const Scratch &S, const u64 *wall, i
 #define CM_ETP(k) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) env_kernel(const EnvArgs A)
+// Specialised on the scenario, the channel family and whether pre-drawn streams are injected: the kernel is bound by
+// instruction FETCH (ncu: 1-3 warps per issue slot wait for instructions; every warp walks a long, divergent path through
+// the code of one env), so an instantiation carries only the code of its own scenario / channel / stream source — the
+// descriptor fields are overwritten with the template constants and the branches on them fold after inlining.
+// kChan: 0 = FC / FL (told apart at run time), CM_CH_IID, CM_CH_GE.
+template <int kScen, int kChan, bool kInj>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) env_kernel(const EnvArgs A_in)
 {
+    EnvArgs A = A_in;
+    A.d.scenario = kScen;
+    if (kChan != 0) A.d.channel = kChan;
+    else if (A.d.channel != CM_CH_FL) A.d.channel = CM_CH_FC;
+    if (kScen == CM_COVERAGE) { A.d.n_preys = 0; A.s.prey_pos = nullptr; A.s.prey_alive = nullptr; }
+    if (!kInj) { A.io.prey_cand = nullptr; A.io.chan_u = nullptr; A.io.spawn_agent = nullptr; A.io.spawn_prey = nullptr; }
 #ifdef CM_ENV_TRACE
     long long trace_t[12] = {0};
 #endif
@@ -467,10 +701,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) env_kernel(const EnvArgs
         int moved = 0, bad = 0;
         CM_ETP(2);
 
-        if (A.mode == 1) {
-            reset_env(A, S, wall, b, G, key, t, total_capture);
-            did_reset = true;
-        } else {
+        bool do_reset = A.mode == 1;              // (reset_env has ONE call site, after the step logic: code size)
+        if (!do_reset) {
             // ---- stage the env in shared memory and rebuild the row bitmaps from the positions ----
             for (int r = G.gl; r < Gd; r += G.gs) { S.occA[r] = 0ull; S.occB[r] = co ? A.s.visited[b * Gd + r] : 0ull; }
             for (int i = G.gl; i < n; i += G.gs) S.posA[i] = A.s.agent_pos[b * n + i];
@@ -506,7 +738,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) env_kernel(const EnvArgs
             int c0 = 0, c2 = 0, c3 = 0, c4 = 0;   // counts (see commarl_b200.h)
             double reward = 0.0;
             int env_done = 0;
+#if CM_ENV_PARALLEL_MOVES
+            // ---- agents move one after another, lower index first (predator_prey.py:497-500,240-261; coverage.py:330-375):
+            // resolved in parallel, exactly (resolve_agents); PredatorPrey's preys stand still meanwhile, Coverage's walls always ----
+            const int blocked_moves = resolve_agents(S, G, n, Gd, co ? wall : S.occB);
+#endif
             if (!co) {
+#if CM_ENV_PARALLEL_MOVES
+                for (int r = G.gl; r < Gd; r += G.gs) S.occA[r] = 0ull;
+                G.sync();
+                for (int i = G.gl; i < n; i += G.gs) {
+                    const uint16_t q = S.finA[i];
+                    S.posA[i] = q;
+                    set_bit(S.occA, q & 0xFF, q >> 8);
+                }
+                G.sync();
+#else
                 // ---- agents move one after another, lower index first (predator_prey.py:497-500,240-261) ----
                 if (G.gl == 0) {
                     // the action and position of agent i + 1 are loaded while agent i is resolved: the only loop-carried
@@ -528,6 +775,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) env_kernel(const EnvArgs
                     }
                 }
                 G.sync();
+#endif
                 // ---- order-independent part of the prey loop, lane-parallel ----
                 // Agents stand still while preys are processed, and prey j's own position / alive flag only
                 // change in its own turn, so: the agent count around prey j (:419/:462), the screening of its
@@ -555,6 +803,32 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) env_kernel(const EnvArgs
                     watching += count4(S.occB, S.posA[i] & 0xFF, S.posA[i] >> 8, Gd) > 0;
                 c3 = G.sum(watching);
                 G.sync();
+#if CM_ENV_PARALLEL_MOVES
+                // ---- order-dependent part: capture test against the preys still standing, then the walk — resolved in
+                // parallel, exactly (resolve_preys) ----
+                {
+                    const int cp = resolve_preys(S, G, p, Gd, d.load);
+                    const int capture = G.sum(cp & 0xFFFF), penalty = G.sum(cp >> 16);
+                    c0 = capture;
+                    c2 = penalty;
+                    for (int r = G.gl; r < Gd; r += G.gs) S.occB[r] = 0ull;
+                    G.sync();
+                    for (int j = G.gl; j < p; j += G.gs) {
+                        const uint16_t q = S.finP[j];
+                        const uint8_t al = S.alvF[j];
+                        S.posP[j] = q;
+                        S.alive[j] = al;
+                        if (al) set_bit(S.occB, q & 0xFF, q >> 8);
+                    }
+                    if (G.gl == 0) {
+                        // :434 / :480, fixed left-to-right fp64 evaluation, no contraction
+                        reward = __dadd_rn(__dadd_rn(d.step_cost, __dmul_rn(d.capture_reward, (double)capture)),
+                                           __ddiv_rn(__dmul_rn(d.moving_cost, (double)moved), (double)n));
+                        if (d.load == 2) reward = __dadd_rn(reward, __dmul_rn(d.penalty, (double)penalty));
+                    }
+                }
+                G.sync();
+#else
                 // ---- order-dependent part: capture test against the preys still standing, then the walk ----
                 if (G.gl == 0) {
                     int capture = 0, penalty = 0;
@@ -600,6 +874,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) env_kernel(const EnvArgs
                     if (d.load == 2) reward = __dadd_rn(reward, __dmul_rn(d.penalty, (double)penalty));
                 }
                 G.sync();
+#endif
                 int any_alive = 0;
                 for (int j = G.gl; j < p; j += G.gs) {
                     any_alive |= S.alive[j];
@@ -611,6 +886,42 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) env_kernel(const EnvArgs
                     env_done = 1;
                 }
             } else {
+#if CM_ENV_PARALLEL_MOVES
+                // ---- Coverage.step (coverage.py:319-401): sequential moves over wall | agent rows, resolved in parallel,
+                // exactly (resolve_agents).  A cell is entered by at most one agent per step (the first one blocks it), so
+                // "new cell or revisit" is read off the visited map as it was before the step ----
+                {
+                    int pen = blocked_moves, cap = 0, rev = 0;
+                    for (int i = G.gl; i < n; i += G.gs) {
+                        const uint16_t q = S.finA[i];
+                        if (q != S.posA[i]) { if (test_bit(S.occB, q)) ++rev; else ++cap; }
+                    }
+                    pen = G.sum(pen); cap = G.sum(cap); rev = G.sum(rev);
+                    for (int r = G.gl; r < Gd; r += G.gs) S.occA[r] = 0ull;
+                    G.sync();                                     // every lane has read the old visited map / agent rows
+                    for (int i = G.gl; i < n; i += G.gs) {
+                        const uint16_t q = S.finA[i];
+                        if (q != S.posA[i]) set_bit(S.occB, q & 0xFF, q >> 8);
+                        S.posA[i] = q;
+                        set_bit(S.occA, q & 0xFF, q >> 8);
+                    }
+                    if (G.gl == 0) {
+                    const int lazy = n - moved;
+                    c0 = cap; c2 = pen; c3 = rev; c4 = lazy;
+                    total_capture += cap;
+                    double final_reward = 0.0;
+                    if (total_capture == d.n_empty_cells) { final_reward = d.final_reward; env_done = 1; }   // :378-382
+                    if (t >= d.max_steps) { success = env_done ? 1 : 0; env_done = 1; }                       // :385-390
+                    // get_reward :300-306; mean(x) = sum / n comes from the table of correctly rounded k / n
+                    reward = __dadd_rn(d.step_cost, __dmul_rn(d.capture_reward, mean_lut[cap]));
+                    reward = __dadd_rn(reward, __dmul_rn(d.moving_cost, mean_lut[moved]));
+                    reward = __dadd_rn(reward, __dmul_rn(d.penalty, mean_lut[pen]));
+                    reward = __dadd_rn(reward, __dmul_rn(d.lazy_penalty, mean_lut[lazy]));
+                    reward = __dadd_rn(reward, __dmul_rn(d.revisit_penalty, mean_lut[rev]));
+                    reward = __dadd_rn(reward, final_reward);
+                    }
+                }
+#else
                 // ---- Coverage.step (coverage.py:319-401): sequential moves over wall | agent rows ----
                 if (G.gl == 0) {
                     int cap = 0, pen = 0, rev = 0;
@@ -644,6 +955,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) env_kernel(const EnvArgs
                     reward = __dadd_rn(reward, __dmul_rn(d.revisit_penalty, mean_lut[rev]));
                     reward = __dadd_rn(reward, final_reward);
                 }
+#endif
                 G.sync();
                 env_done = G.bcast0(env_done);
                 total_capture = G.bcast0(total_capture);
@@ -674,10 +986,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) env_kernel(const EnvArgs
                 }
             }
             CM_ETP(6);
-            if (done && A.io.auto_reset) {        // vec_env_executor.py:36-43
-                reset_env(A, S, wall, b, G, key, t, total_capture);
-                did_reset = true;
-            }
+            do_reset = done && A.io.auto_reset;   // vec_env_executor.py:36-43
+        }
+        if (do_reset) {
+            reset_env(A, S, wall, b, G, key, t, total_capture);
+            did_reset = true;
         }
 
         CM_ETP(7);
@@ -705,6 +1018,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) env_kernel(const EnvArgs
         }
 #endif
     }
+}
+
+typedef void (*env_kernel_fn)(const EnvArgs);
+template <int kScen>
+static env_kernel_fn pick_env_kernel_s(int channel, bool inj)
+{
+    switch (channel) {
+    case CM_CH_IID: return inj ? env_kernel<kScen, CM_CH_IID, true> : env_kernel<kScen, CM_CH_IID, false>;
+    case CM_CH_GE: return inj ? env_kernel<kScen, CM_CH_GE, true> : env_kernel<kScen, CM_CH_GE, false>;
+    default: return inj ? env_kernel<kScen, 0, true> : env_kernel<kScen, 0, false>;
+    }
+}
+static env_kernel_fn pick_env_kernel(int scenario, int channel, bool inj)
+{
+    return scenario == CM_COVERAGE ? pick_env_kernel_s<CM_COVERAGE>(channel, inj) : pick_env_kernel_s<CM_PREDATOR_PREY>(channel, inj);
 }
 
 static int validate(const cm_env_desc *d, const cm_env_state *s, const cm_step_io *io, int mode)
@@ -754,25 +1082,27 @@ static int launch(const cm_env_desc *d, const cm_env_state *s, const cm_step_io 
     const size_t smem = kConstBytes + (size_t)envs_per_cta * A.warp_bytes;
     // launch geometry is cached per (device, smem) so that steady-state calls issue nothing but the launch
     // (keeps the call CUDA-graph capturable)
-    static thread_local struct { int dev; size_t smem; int ctas_per_sm; int sms; } cache = {-1, 0, 0, 0};
+    static thread_local struct { int dev; size_t smem; const void *kernel; int ctas_per_sm; int sms; } cache = {-1, 0, nullptr, 0, 0};
+    const bool inj = io->prey_cand || io->chan_u || io->spawn_agent || io->spawn_prey;
+    void (*kernel)(const EnvArgs) = pick_env_kernel(d->scenario, d->channel, inj);
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ENODEVICE);
-    if (cache.dev != dev || cache.smem != smem) {
+    if (cache.dev != dev || cache.smem != smem || cache.kernel != (const void *)kernel) {
         int sms = 0, ctas = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ECUDA);
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
         }
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, env_kernel, kWarpsPerCta * 32, smem) != cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, kWarpsPerCta * 32, smem) != cudaSuccess)
             return set_cuda_error(cudaGetLastError(), CM_ECUDA);
-        cache.dev = dev; cache.smem = smem; cache.ctas_per_sm = ctas < 1 ? 1 : ctas; cache.sms = sms;
+        cache.dev = dev; cache.smem = smem; cache.kernel = (const void *)kernel; cache.ctas_per_sm = ctas < 1 ? 1 : ctas; cache.sms = sms;
     }
     // persistent grid: a whole number of CTAs per SM, warps stride over the envs
     int64_t want = (s->n_envs + envs_per_cta - 1) / envs_per_cta;
     int64_t cap = (int64_t)cache.sms * cache.ctas_per_sm;
     int grid = (int)(want < cap ? want : cap);
-    env_kernel<<<grid, kWarpsPerCta * 32, smem, stream>>>(A);
+    kernel<<<grid, kWarpsPerCta * 32, smem, stream>>>(A);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
     return CM_OK;

@@ -127,13 +127,34 @@ __device__ __forceinline__ float tanh_scaled(float a)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
     return fmaf(-2.0f, r, 1.0f);
 }
+// Four tanh's with ONE reciprocal: 1/A = B C D / (A B C D) ...  The special-function unit (16 lanes per clock per SM) is what
+// bounds the dense epilogues locally — two MUFU per tanh occupy it for ~60 % of an epilogue — so the four reciprocals of a
+// group are replaced by one plus nine multiplications on the FMA pipe: 1.25 MUFU per tanh.  Arguments are clamped at 30
+// (tanh = 1 - 2^-29 rounds to 1 in fp32), so the product of four (2^a + 1) stays below 2^121.  |error| <= ~4e-7 absolute.
+__device__ __forceinline__ void tanh4_scaled(float &a0, float &a1, float &a2, float &a3)
+{
+    float e0, e1, e2, e3, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(a0, 30.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(a1, 30.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fminf(a2, 30.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fminf(a3, 30.0f)));
+    const float A = e0 + 1.0f, B = e1 + 1.0f, C = e2 + 1.0f, D = e3 + 1.0f;
+    const float ab = A * B, cd = C * D;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(ab * cd));
+    const float rab = r * ab, rcd = r * cd;          // 1 / (C D), 1 / (A B)
+    a0 = fmaf(-2.0f, rcd * B, 1.0f);
+    a1 = fmaf(-2.0f, rcd * A, 1.0f);
+    a2 = fmaf(-2.0f, rab * D, 1.0f);
+    a3 = fmaf(-2.0f, rab * C, 1.0f);
+}
 // tanh(acc0 + 2^-12 acc1 + bias) for 4 consecutive columns, bias4 = 2 log2(e) * bias from the shared-memory table
 __device__ __forceinline__ void tanh4(float *v, const float *w, const float4 b4)
 {
-    v[0] = tanh_scaled(fmaf(v[0], kTanhScale, fmaf(w[0], kTanhScaleLo, b4.x)));
-    v[1] = tanh_scaled(fmaf(v[1], kTanhScale, fmaf(w[1], kTanhScaleLo, b4.y)));
-    v[2] = tanh_scaled(fmaf(v[2], kTanhScale, fmaf(w[2], kTanhScaleLo, b4.z)));
-    v[3] = tanh_scaled(fmaf(v[3], kTanhScale, fmaf(w[3], kTanhScaleLo, b4.w)));
+    v[0] = fmaf(v[0], kTanhScale, fmaf(w[0], kTanhScaleLo, b4.x));
+    v[1] = fmaf(v[1], kTanhScale, fmaf(w[1], kTanhScaleLo, b4.y));
+    v[2] = fmaf(v[2], kTanhScale, fmaf(w[2], kTanhScaleLo, b4.z));
+    v[3] = fmaf(v[3], kTanhScale, fmaf(w[3], kTanhScaleLo, b4.w));
+    tanh4_scaled(v[0], v[1], v[2], v[3]);
 }
 
 // one converged warp: D[:, 0:N] (+)= A_hi B_hi^T, D[:, N:2N] (+)= A_hi B_lo^T + A_lo B_hi^T.  All lanes run the code
@@ -336,9 +357,15 @@ __device__ __forceinline__ void softmax_tc(uint32_t lane_addr, float *red, float
 #pragma unroll
     for (int t = 0; t < KT; ++t) sc[t] *= scale;
     if (attn_row) {                       // unmasked softmax (agent_infos['attention_weights'])
+        if ((n & 3) == 0) {               // rows of n floats keep 16-byte alignment: whole 32-byte sectors per thread
 #pragma unroll
-        for (int t = 0; t < KT; ++t)
-            if (t < nk) attn_row[k0 + t] = sc[t];
+            for (int t = 0; t < KT; t += 4)
+                if (t < nk) *reinterpret_cast<float4 *>(attn_row + k0 + t) = make_float4(sc[t], sc[t + 1], sc[t + 2], sc[t + 3]);
+        } else {
+#pragma unroll
+            for (int t = 0; t < KT; ++t)
+                if (t < nk) attn_row[k0 + t] = sc[t];
+        }
     }
     tmem_st<8>(lane_addr + kColM + (uint32_t)k0, sc);
     if constexpr (KT > 8) tmem_st<8>(lane_addr + kColM + (uint32_t)k0 + 8u, sc + 8);
@@ -818,10 +845,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                     const int c = 16 * sub + 4 * q + i;
                     t4[i] = KV[c * kTPitch + ((((row >> 2) ^ (c & 7)) << 2) | (row & 3))];
                 }
-                v[4 * q + 0] = tanh_scaled(fmaf(t4[0], inv, b4.x));
-                v[4 * q + 1] = tanh_scaled(fmaf(t4[1], inv, b4.y));
-                v[4 * q + 2] = tanh_scaled(fmaf(t4[2], inv, b4.z));
-                v[4 * q + 3] = tanh_scaled(fmaf(t4[3], inv, b4.w));
+                v[4 * q + 0] = fmaf(t4[0], inv, b4.x);
+                v[4 * q + 1] = fmaf(t4[1], inv, b4.y);
+                v[4 * q + 2] = fmaf(t4[2], inv, b4.z);
+                v[4 * q + 3] = fmaf(t4[3], inv, b4.w);
+                tanh4_scaled(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             }
             if (d.residual && l + 1 == L) {               // X = E + H_L (comm_base_net.py:105-106)
                 float ev[16];
@@ -930,10 +958,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 b4 = bp[q];
-                v[4 * q + 0] = tanh_scaled(fmaf(acc[4 * q + 0], inv, b4.x));
-                v[4 * q + 1] = tanh_scaled(fmaf(acc[4 * q + 1], inv, b4.y));
-                v[4 * q + 2] = tanh_scaled(fmaf(acc[4 * q + 2], inv, b4.z));
-                v[4 * q + 3] = tanh_scaled(fmaf(acc[4 * q + 3], inv, b4.w));
+                v[4 * q + 0] = fmaf(acc[4 * q + 0], inv, b4.x);
+                v[4 * q + 1] = fmaf(acc[4 * q + 1], inv, b4.y);
+                v[4 * q + 2] = fmaf(acc[4 * q + 2], inv, b4.z);
+                v[4 * q + 3] = fmaf(acc[4 * q + 3], inv, b4.w);
+                tanh4_scaled(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             }
             if (d.residual) {                             // X = E + H_L (comm_base_net.py:105-106)
                 // E is still in the A operand buffer (this thread wrote these 16 columns itself) until the first layer's
