@@ -46,7 +46,7 @@ class StepIO(C.Structure):
                 ("chan_planes", C.c_int32), ("auto_reset", C.c_int32), ("obs", C.c_void_p), ("reward", C.c_void_p),
                 ("done", C.c_void_p), ("counts", C.c_void_p), ("prey_alive_out", C.c_void_p),
                 ("success_out", C.c_void_p), ("adj_bits", C.c_void_p), ("chan_bits", C.c_void_p), ("ave_deg", C.c_void_p),
-                ("error_flag", C.c_void_p), ("stats", C.c_void_p), ("host_arena", C.c_int32)]
+                ("error_flag", C.c_void_p), ("stats", C.c_void_p), ("obs_bits", C.c_void_p), ("host_arena", C.c_int32)]
 
 
 class PolicyDesc(C.Structure):
@@ -60,7 +60,7 @@ class PolicyIO(C.Structure):
                [(k, C.c_void_p) for k in ("weights", "obs", "adj_bits", "chan_bits", "avail_bits", "sample_u", "tick",
                                           "episode", "probs", "logits", "attention", "actions", "tc_weights",
                                           "error_flag", "workspace")] + \
-               [("workspace_bytes", C.c_size_t), ("host_arena", C.c_int32)]
+               [("workspace_bytes", C.c_size_t), ("obs_bits", C.c_void_p), ("obs_nbits", C.c_int32), ("host_arena", C.c_int32)]
 
 
 class NativeError(RuntimeError):

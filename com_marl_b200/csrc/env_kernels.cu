@@ -396,7 +396,7 @@ __device__ __forceinline__ void reset_env(const EnvArgs &A, const Scratch &S, co
 __device__ __forceinline__ void write_obs(const EnvArgs &A, const Scratch &S, const u64 *wall, int64_t b, const Grp &G, int t)
 {
     const cm_env_desc &d = A.d;
-    if (!A.io.obs) return;
+    if (!A.io.obs && !A.io.obs_bits) return;
     const int n = d.n_agents, Gd = d.grid, R = d.sensing, w = 2 * R + 1, ww = w * w, np_ = A.n_pad;
     const bool co = d.scenario == CM_COVERAGE;
     const int nbits = (co ? 3 : 2) * ww, D = nbits + (co ? 2 : 3);
@@ -426,6 +426,14 @@ __device__ __forceinline__ void write_obs(const EnvArgs &A, const Scratch &S, co
         S.win[5 * np_ + i] = __float_as_uint(ft);
     }
     G.sync();
+    if (A.io.obs_bits) {                          // the packed form (24 bytes per agent), for cm_policy_forward
+        uint32_t *ob = A.io.obs_bits + (size_t)b * n * 6;
+        for (int e = G.gl; e < n * 6; e += G.gs) {
+            const int i = e / 6, wd = e - i * 6;
+            ob[e] = S.win[wd * np_ + i];
+        }
+    }
+    if (!A.io.obs) return;
     float *out = A.io.obs + (size_t)b * n * D;
     const int total = n * D;
     const uint32_t magic = (uint32_t)((0x100000000ull + (u64)D - 1ull) / (u64)D);   // e / D == umulhi(e, magic) for e < 2^25
@@ -1055,7 +1063,7 @@ static int validate(const cm_env_desc *d, const cm_env_state *s, const cm_step_i
         if (!s->ge_state) return CM_EINVAL;
     }
     if (!s->agent_pos || !s->step_count || !s->success || !s->episode || !s->tick) return CM_EINVAL;
-    if (!d->lut && io->obs) return CM_EINVAL;
+    if (!d->lut && (io->obs || io->obs_bits)) return CM_EINVAL;
     if (mode == 0 && !io->actions) return CM_EINVAL;
     if (io->spawn_agent && (io->spawn_episodes < 1 || (d->n_preys > 0 && !io->spawn_prey))) return CM_EINVAL;
     if (io->chan_u) {

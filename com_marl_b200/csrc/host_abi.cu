@@ -54,14 +54,19 @@ struct CopyRun {
     int done() { flush(); return rc; }
 };
 
-static int policy_outputs_to_host(const cm_policy_desc *desc, size_t B, const cm_policy_io *dev, const cm_policy_io *host, cudaStream_t s)
+static void add_policy_outputs(CopyRun &down, const cm_policy_desc *desc, size_t B, const cm_policy_io *dev, const cm_policy_io *host)
 {
     const size_t n = (size_t)desc->n_agents, rows = B * n;
-    CopyRun down(s, cudaMemcpyDeviceToHost, host->host_arena != 0);
     down.add(host->actions, dev->actions, rows);
     down.add(host->probs, dev->probs, rows * CM_ACTIONS * 4);
     down.add(host->logits, dev->logits, rows * CM_ACTIONS * 4);
     down.add(host->attention, dev->attention, rows * n * 4);
+}
+
+static int policy_outputs_to_host(const cm_policy_desc *desc, size_t B, const cm_policy_io *dev, const cm_policy_io *host, cudaStream_t s)
+{
+    CopyRun down(s, cudaMemcpyDeviceToHost, host->host_arena != 0);
+    add_policy_outputs(down, desc, B, dev, host);
     return down.done();
 }
 
@@ -104,12 +109,19 @@ static size_t env_obs_dim(const cm_env_desc *d)
     return d->scenario == CM_COVERAGE ? 3 * ww + 2 : 2 * ww + 3;      /* coverage.py:111-117, predator_prey.py:95-98 */
 }
 
+static void add_env_outputs(cm::CopyRun &down, const cm_env_desc *desc, size_t B, const cm_step_io *dev, const cm_step_io *host);
+
 static int env_outputs_to_host(const cm_env_desc *desc, size_t B, const cm_step_io *dev, const cm_step_io *host, cudaStream_t s)
 {
-    using namespace cm;
+    cm::CopyRun down(s, cudaMemcpyDeviceToHost, host->host_arena != 0);
+    add_env_outputs(down, desc, B, dev, host);
+    return down.done();
+}
+
+static void add_env_outputs(cm::CopyRun &down, const cm_env_desc *desc, size_t B, const cm_step_io *dev, const cm_step_io *host)
+{
     const size_t n = (size_t)desc->n_agents, p = (size_t)(desc->n_preys > 0 ? desc->n_preys : 1), L = (size_t)desc->n_layers;
     const size_t W = (n + 31) / 32, D = env_obs_dim(desc);
-    CopyRun down(s, cudaMemcpyDeviceToHost, host->host_arena != 0);
     down.add(host->obs, dev->obs, B * n * D * 4);
     down.add(host->adj_bits, dev->adj_bits, B * n * W * 4);
     down.add(host->chan_bits, dev->chan_bits, B * L * n * W * 4);
@@ -119,7 +131,6 @@ static int env_outputs_to_host(const cm_env_desc *desc, size_t B, const cm_step_
     down.add(host->prey_alive_out, dev->prey_alive_out, B * p);
     down.add(host->success_out, dev->success_out, B);
     down.add(host->ave_deg, dev->ave_deg, B * 4);
-    return down.done();
 }
 
 extern "C" int cm_env_step_host(const cm_env_desc *desc, const cm_env_state *state, const cm_step_io *dev, const cm_step_io *host,
@@ -165,7 +176,11 @@ extern "C" int cm_rollout_step_host(const cm_policy_desc *pol_desc, const cm_pol
         CM_TRY(up.done());
     }
     CM_TRY(cm_policy_forward(pol_desc, pol_dev, stream));
-    CM_TRY(policy_outputs_to_host(pol_desc, B, pol_dev, pol_host, s));
     CM_TRY(cm_env_step(env_desc, state, env_dev, stream));
-    return env_outputs_to_host(env_desc, B, env_dev, env_host, s);
+    // everything the sampler appends, as one run of transfers: with the env outputs and the policy outputs carved from ONE
+    // declared arena on both sides (HostRollout does that) the whole step result is a single DMA transfer
+    CopyRun down(s, cudaMemcpyDeviceToHost, env_host->host_arena != 0 && pol_host->host_arena != 0);
+    add_env_outputs(down, env_desc, B, env_dev, env_host);
+    add_policy_outputs(down, pol_desc, B, pol_dev, pol_host);
+    return down.done();
 }

@@ -571,7 +571,11 @@ extern "C" size_t cm_policy_workspace_bytes(int32_t n_agents, int64_t n_envs)
 extern "C" int cm_policy_forward(const cm_policy_desc *desc, const cm_policy_io *io, cm_stream_t stream)
 {
     using namespace cm;
-    if (!desc || !io || !io->weights || !io->obs) return CM_EINVAL;
+    if (!desc || !io || !io->weights) return CM_EINVAL;
+    // packed observations (cm_step_io.obs_bits) feed the tensor-core kernels of the Comm-DP / Obs-DP policies; every other path needs fp32 rows
+    const bool packed_ok = io->obs_bits && (desc->math == 1 || desc->math == 2) && desc->kind != CM_POLICY_CENT;
+    if (!io->obs && !packed_ok) return CM_EINVAL;
+    if (io->obs_bits && (io->obs_nbits < 1 || io->obs_nbits > 96 || desc->obs_dim < io->obs_nbits || desc->obs_dim - io->obs_nbits > 3)) return CM_EINVAL;
     if (!io->probs && !io->actions && !io->logits && !io->attention) return CM_EINVAL;
     if (desc->n_agents < 1 || desc->n_agents > CM_MAX_AGENTS || desc->obs_dim < 1 || desc->obs_dim > 128) return CM_EUNSUPPORTED;
     if (desc->n_layers < 1 || desc->n_layers > CM_MAX_LAYERS) return CM_EUNSUPPORTED;

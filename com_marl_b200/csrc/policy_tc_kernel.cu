@@ -159,8 +159,9 @@ __device__ __forceinline__ void tanh4(float *v, const float *w, const float4 b4)
 
 // one converged warp: D[:, 0:N] (+)= A_hi B_hi^T, D[:, N:2N] (+)= A_hi B_lo^T + A_lo B_hi^T.  All lanes run the code
 // (descriptors stay in uniform registers); the instructions are predicated on the leader lane.
+// lo_from: first K slice whose A_lo is not identically zero (packed observations: only the scalar columns have a low-order part)
 __device__ __forceinline__ void issue_layer(uint32_t d_tmem, const unsigned char *act, const unsigned char *wblk, int N, int Kp,
-                                            uint32_t accumulate, uint32_t leader)
+                                            uint32_t accumulate, uint32_t leader, int lo_from = 0)
 {
     if (CM_TC_DEBUG & 1) return;
     const uint32_t a_hi = smem_u32(act), a_lo = a_hi + (uint32_t)kTcRows * Kp * 2, b = smem_u32(wblk);
@@ -178,7 +179,7 @@ __device__ __forceinline__ void issue_layer(uint32_t d_tmem, const unsigned char
         const uint64_t da = make_smem_desc16(a_lo, Kp, 0);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (j < nk) mma_f16_pred(d_tmem + (uint32_t)N, da + 16 * j, db + 16 * j, idesc, 1u, leader);
+            if (j < nk && j >= lo_from) mma_f16_pred(d_tmem + (uint32_t)N, da + 16 * j, db + 16 * j, idesc, 1u, leader);
     }
 }
 
@@ -395,7 +396,7 @@ __device__ __forceinline__ float masked_p_operand(uint32_t lane_addr, unsigned c
 // bias offsets inside the shared-memory bias table
 static constexpr int kBEnc1 = 0, kBEnc2 = 128, kBGcn = 192, kBH1 = 448, kBH2 = 576, kBH3 = 640, kBH4 = 672, kW4 = 680, kBiasFloats = 680 + kC3 * CM_ACTIONS;   // kW4: head_w4 [32][5] k-major
 
-struct MmaOp { uint32_t dcol, acc, abuf; };   // accumulator block, accumulate flag, A operand buffer (0: ACT, 1: ACT2)
+struct MmaOp { uint32_t dcol, acc, abuf; int lo_from; };   // accumulator block, accumulate flag, A operand buffer (0: ACT, 1: ACT2), first K slice of the A_lo pass
 
 #ifdef CM_TC_TRACE
 #define CM_TPK(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && A.io.workspace) \
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
 #endif
                 const TcStage &st = P.st[si + i];
                 const MmaOp op = i ? op1 : op0;
-                issue_layer(tmem + op.dcol, op.abuf ? ACT2 : ACT, WB + (b & 1u) * (uint32_t)kSlotBytes, st.N, st.Kp, op.acc, leader);
+                issue_layer(tmem + op.dcol, op.abuf ? ACT2 : ACT, WB + (b & 1u) * (uint32_t)kSlotBytes, st.N, st.Kp, op.acc, leader, op.lo_from);
             }
             mma_commit_pred(&bars[2], leader);
             __syncwarp();
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         si += nops;
         issue_loads();
     };
-    const MmaOp none = {0u, 0u, 0u};
+    const MmaOp none = {0u, 0u, 0u, 0};
     // the same hand-shake for products whose operands are both written by the CTA (no weight stage is consumed)
     auto run_custom = [&](auto issue) {
         fence_proxy_async();
@@ -599,12 +600,16 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         if (dec) { r0 = tl * kTcRows; nr = min(kTcRows, total_rows - r0); }
         else { const int e0 = tl * A.envs_per_tile; r0 = e0 * n; nr = min(A.envs_per_tile, n_envs - e0) * n; }
     };
+    // packed observations (io.obs_bits): a row is 6 words — 3 of window bits, 3 scalar columns as float bits — staged like 6 floats
+    const bool packed = io.obs_bits != nullptr && kMode != kTcModeHead;
+    const int Dst = packed ? 6 : Din;                 // words per staged row
+    const float *obs_src = packed ? reinterpret_cast<const float *>(io.obs_bits) : io.obs;
     auto stage_obs = [&](int tl) {
         int r0s, rws;
         tile_rows(tl, r0s, rws);
-        const float *src = io.obs + (size_t)r0s * Din;
+        const float *src = obs_src + (size_t)r0s * Dst;
         const int a = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
-        const int ns = min(rws * Din, kStageFloats);
+        const int ns = min(rws * Dst, kStageFloats);
         const int nq = (a + ns + 3) >> 2;
         const uint32_t sbase = smem_u32(stage);
         for (int q = tid; q < nq; q += kTcThreads) {
@@ -662,17 +667,46 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         __syncthreads();                                   // the staged observations of this tile are visible
         CM_TP(19);
         {
-            const float *src = io.obs + (size_t)row0 * Din;
+            const float *src = obs_src + (size_t)row0 * Dst;
             const int a = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);
-            const int total_f = rows * Din, ns = min(total_f, kStageFloats);
+            const int total_f = rows * Dst, ns = min(total_f, kStageFloats);
+            const int nbits = io.obs_nbits;
             for (int pnl = 0; pnl < P.l1_panels; ++pnl) {
                 const int Kp = P.st[si].Kp, kofs = 64 * pnl, kg = Kp >> 3;          // kg = 2, 4, 6 or 8 groups of 8 columns
                 const uint32_t lo_off = (uint32_t)kTcRows * Kp * 2, inv = (65536u + (uint32_t)kg - 1u) / (uint32_t)kg;
                 for (int e8 = tid; e8 < kTcRows * kg; e8 += kTcThreads) {           // one group of 8 columns of one row
-                    const int r = (int)(((uint32_t)e8 * inv) >> 16), k8 = (e8 - r * kg) << 3;
+                    // fp32 rows: consecutive threads take consecutive column groups of a row (consecutive floats); packed rows:
+                    // consecutive threads take the SAME column group of consecutive rows, so that only the warps that own the
+                    // group with the scalar columns run the float path (no divergence inside a warp)
+                    const int r = packed ? (e8 & (kTcRows - 1)) : (int)(((uint32_t)e8 * inv) >> 16);
+                    const int k8 = packed ? (e8 >> 7) << 3 : (e8 - r * kg) << 3;
                     __align__(16) __half h[8], l[8];
                     int rr = r;                                  // row of the tile's observation block behind tile row r
                     if constexpr (kAttnTc) { const int e_ = r >> slog, i_ = r & (S - 1); rr = i_ < n ? e_ * n + i_ : rows; }
+                    if (packed) {
+                        const int kb = kofs + k8;
+                        const bool okr = rr < rows;
+                        const uint32_t *wrow = reinterpret_cast<const uint32_t *>(stage + a) + rr * 6;     // (a packed tile is always staged whole)
+                        if (kb + 8 <= nbits || kb >= Din) {
+                            // window bits expand to 0 / 1: exact in fp16, no low-order part
+                            const uint32_t b8 = (okr && kb < nbits) ? (wrow[kb >> 5] >> (kb & 31)) & 0xFFu : 0u;   // (8 | 32: one word)
+                            uint32_t *hw = reinterpret_cast<uint32_t *>(h), *lw = reinterpret_cast<uint32_t *>(l);
+#pragma unroll
+                            for (int j2 = 0; j2 < 4; ++j2) {
+                                hw[j2] = (((b8 >> (2 * j2)) & 1u) ? 0x3C00u : 0u) | (((b8 >> (2 * j2 + 1)) & 1u) ? 0x3C000000u : 0u);
+                                lw[j2] = 0u;
+                            }
+                        } else {
+                            // the group with the scalar columns (float bits in words 3..5): split like any float
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int k = kb + j;
+                                float x = 0.0f;
+                                if (okr && k < Din) x = k < nbits ? (float)((wrow[k >> 5] >> (k & 31)) & 1u) : __uint_as_float(wrow[3 + k - nbits]);
+                                split16(x, h[j], l[j]);
+                            }
+                        }
+                    } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int k = kofs + k8 + j, i = rr * Din + k;
@@ -680,11 +714,14 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                         if (rr < rows && k < Din) x = i < ns ? stage[a + i] : __ldg(src + i);
                         split16(x, h[j], l[j]);
                     }
+                    }
                     const uint32_t off = canon_off16(r, k8, Kp);
                     *reinterpret_cast<uint4 *>(ACT + off) = *reinterpret_cast<const uint4 *>(h);
                     *reinterpret_cast<uint4 *>(ACT + lo_off + off) = *reinterpret_cast<const uint4 *>(l);
                 }
-                run_mma(2, MmaOp{kR0, (uint32_t)pnl, 0u}, MmaOp{kR1, (uint32_t)pnl, 0u});
+                // packed rows: A_lo is zero before the K slice that holds the first scalar column
+                const int lo_from = packed ? max(0, min(Kp >> 4, (nbits - kofs) >> 4)) : 0;
+                run_mma(2, MmaOp{kR0, (uint32_t)pnl, 0u, lo_from}, MmaOp{kR1, (uint32_t)pnl, 0u, lo_from});
             }
         }
         // ---------------- encoder layer 2 (K = 128 as the two panels of h) -> R0 ----------------

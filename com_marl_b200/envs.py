@@ -45,6 +45,8 @@ class BatchedEnv:
         self.env_id0 = int(env_id0)
         n, p, G, L = spec.n_agents, spec.n_preys, spec.grid, spec.n_layers
         self.n, self.p, self.G, self.L, self.D, self.W = n, p, G, L, spec.obs_dim, (n + 31) // 32
+        self.obs_nbits = spec.obs_dim - (3 if spec.scenario == "pp" else 2)     # leading 0/1 window columns of an observation row
+        self.obs_bits = None                    # optional packed observation output [B, n, 6] int32 (enable_obs_bits)
         B, dev = self.B, self.device
 
         def z(shape, dt):
@@ -86,7 +88,16 @@ class BatchedEnv:
                 ("counts", (B, 6), torch.int32), ("prey_alive_out", (B, max(p, 1)), torch.uint8),
                 ("success_out", (B,), torch.uint8), ("ave_deg", (B,), torch.float32)]
 
-    _SLICED = ("agent_pos", "prey_pos", "prey_alive", "visited", "step_count", "total_capture", "success", "episode", "tick",
+    def enable_obs_bits(self):
+        """also write the packed observation (cm_step_io.obs_bits: window bits + scalar columns, 24 bytes per agent) — the
+        form the tensor-core policy kernels read instead of the fp32 rows"""
+        if self.obs_bits is None:
+            self.obs_bits = torch.zeros((self.B, self.n, 6), dtype=torch.int32, device=self.device)
+            self._io_cache.clear()
+            self._hio = None
+        return self.obs_bits
+
+    _SLICED = ("obs_bits", "agent_pos", "prey_pos", "prey_alive", "visited", "step_count", "total_capture", "success", "episode", "tick",
                "ge_state", "obs", "reward", "done", "counts", "prey_alive_out", "success_out", "adj_bits", "chan_bits", "ave_deg",
                "stats", "_spawn_agent", "_spawn_prey")
 
@@ -144,6 +155,9 @@ class BatchedEnv:
                   "error_flag", "stats"):
             t = out[k] if (out is not None and k in out) else getattr(self, k)
             setattr(io, k, N.ptr(t))
+        # the packed observation (24 bytes per agent, for cm_policy_forward) is written only when the caller gives a buffer
+        ob = out.get("obs_bits") if out is not None else getattr(self, "obs_bits", None)
+        io.obs_bits = N.ptr(ob)
         return io
 
     # ---- VecEnvExecutor surface -------------------------------------------------------------------

@@ -197,11 +197,16 @@ class CommCategoricalMLPPolicy(nn.Module):
 
     # ---- device fast path (no host copies) --------------------------------------------------------------
     def act_device(self, obs, adj_bits=None, chan_bits=None, avail_bits=None, sample_u=None, tick=None, episode=None,
-                   greedy=False, probs=None, logits=None, attention=None, actions=None, env_id0=0, ws_slot=0):
+                   greedy=False, probs=None, logits=None, attention=None, actions=None, env_id0=0, ws_slot=0, obs_bits=None,
+                   obs_nbits=0):
         """Fused forward on device tensors.  obs: float32 (B, n, D) / (B, n*D).  Outputs are written into the
-        given tensors (allocate once, reuse: the call is CUDA-graph capturable)."""
+        given tensors (allocate once, reuse: the call is CUDA-graph capturable).  ``obs_bits`` (int32 (B, n, 6), what
+        ``BatchedEnv.enable_obs_bits()`` makes the env kernel write) + ``obs_nbits``: the packed observation — the
+        tensor-core kernels read it instead of ``obs`` (24 bytes per agent row instead of 4 D; identical results)."""
         desc, io = self._call_structs(obs, adj_bits, chan_bits, avail_bits, sample_u, tick, episode, greedy, probs, logits,
                                       attention, actions, env_id0, ws_slot)
+        if obs_bits is not None and self.uses_tensor_cores():
+            io.obs_bits, io.obs_nbits = N.ptr(obs_bits), int(obs_nbits)
         with torch.cuda.device(self.device):
             N.check("cm_policy_forward", N.lib().cm_policy_forward(C.byref(desc), C.byref(io), N.stream_ptr()))
 
@@ -474,9 +479,10 @@ class DecCategoricalMLPPolicy(nn.Module):
         return self._blob
 
     def act_device(self, obs, avail_bits=None, sample_u=None, tick=None, episode=None, greedy=False, probs=None, logits=None,
-                   actions=None, env_id0=0, **_unused):
+                   actions=None, env_id0=0, obs_bits=None, obs_nbits=0, **_unused):
         """fused forward on device tensors (see CommCategoricalMLPPolicy.act_device); no masks, no attention output"""
-        self._act_device(obs, None, None, avail_bits, sample_u, tick, episode, greedy, probs, logits, None, actions, env_id0)
+        self._act_device(obs, None, None, avail_bits, sample_u, tick, episode, greedy, probs, logits, None, actions, env_id0,
+                         obs_bits=obs_bits, obs_nbits=obs_nbits)
 
     # ---- reference call surface ----
     def forward(self, obs, avail_actions, get_actions=False):

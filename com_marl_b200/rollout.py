@@ -71,6 +71,11 @@ class RolloutEngine:
             prey_alive_out=z((K, B, p), torch.uint8), success=z((K, B), torch.uint8))
         if record_attention:
             self.traj["attention"] = z((K, B, n, n), torch.float32)
+        # packed observations (24 bytes per agent): written by the env kernel next to the fp32 contract output and read by the
+        # tensor-core policy kernels instead of it (Comm-DP / Obs-DP)
+        self._packed = bool(getattr(policy, "_kind", 2) != 2 and policy.uses_tensor_cores())
+        if self._packed:
+            self.traj["obs_bits"] = z((K + 1, B, n, 6), torch.int32)
         self._graph = None
         self._warm = False
         self.steps_done = 0
@@ -85,25 +90,32 @@ class RolloutEngine:
             return
         t, e = self.traj, self._envs[g]
         b0, b1 = self._ranges[g]
+        pk = dict(obs_bits=t["obs_bits"][k, b0:b1], obs_nbits=e.obs_nbits) if self._packed else {}
         self.policy.act_device(t["obs"][k, b0:b1], adj_bits=t["adj_bits"][k, b0:b1], chan_bits=t["chan_bits"][k, b0:b1], tick=e.tick, episode=e.episode,
                                greedy=self.greedy, probs=t["probs"][k, b0:b1], actions=t["actions"][k, b0:b1],
-                               attention=t["attention"][k, b0:b1] if "attention" in t else None, env_id0=e.env_id0)
-        e.step(t["actions"][k, b0:b1],
-               out=dict(obs=t["obs"][k + 1, b0:b1], adj_bits=t["adj_bits"][k + 1, b0:b1], chan_bits=t["chan_bits"][k + 1, b0:b1],
-                        ave_deg=t["ave_deg"][k + 1, b0:b1], reward=t["reward"][k, b0:b1], done=t["done"][k, b0:b1],
-                        counts=t["counts"][k, b0:b1], prey_alive_out=t["prey_alive_out"][k, b0:b1],
-                        success_out=t["success"][k, b0:b1]))
+                               attention=t["attention"][k, b0:b1] if "attention" in t else None, env_id0=e.env_id0, **pk)
+        out = dict(obs=t["obs"][k + 1, b0:b1], adj_bits=t["adj_bits"][k + 1, b0:b1], chan_bits=t["chan_bits"][k + 1, b0:b1],
+                   ave_deg=t["ave_deg"][k + 1, b0:b1], reward=t["reward"][k, b0:b1], done=t["done"][k, b0:b1],
+                   counts=t["counts"][k, b0:b1], prey_alive_out=t["prey_alive_out"][k, b0:b1],
+                   success_out=t["success"][k, b0:b1])
+        if self._packed:
+            out["obs_bits"] = t["obs_bits"][k + 1, b0:b1]
+        e.step(t["actions"][k, b0:b1], out=out)
         self.kernel_launches += 2
 
     def _carry(self):
         """slot K (state after the last step of a chunk) becomes slot 0 of the next chunk"""
-        for k in ("obs", "adj_bits", "chan_bits", "ave_deg"):
-            self.traj[k][0].copy_(self.traj[k][self.K])
+        for k in ("obs", "adj_bits", "chan_bits", "ave_deg", "obs_bits"):
+            if k in self.traj:
+                self.traj[k][0].copy_(self.traj[k][self.K])
 
     def reset(self):
         t = self.traj
         self.env.stats.zero_()
-        self.env.reset(out=dict(obs=t["obs"][0], adj_bits=t["adj_bits"][0], chan_bits=t["chan_bits"][0], ave_deg=t["ave_deg"][0]))
+        out = dict(obs=t["obs"][0], adj_bits=t["adj_bits"][0], chan_bits=t["chan_bits"][0], ave_deg=t["ave_deg"][0])
+        if self._packed:
+            out["obs_bits"] = t["obs_bits"][0]
+        self.env.reset(out=out)
         self.steps_done = 0
 
     def _chunk_eager(self):
@@ -206,25 +218,31 @@ class HostRollout:
             pspecs = [("actions", (Bp, n), torch.int8), ("probs", (Bp, n, 5), torch.float32)]
             if self.record_attention:
                 pspecs.append(("attention", (Bp, n, n), torch.float32))
-            pdev = N.arena(pspecs, device=self.device)
+            # env outputs + policy outputs in ONE arena per side (same order, same padding): a step's whole result is one
+            # DMA transfer (csrc/host_abi.cu merges the neighbours of a declared arena)
+            specs = env._out_specs() + pspecs
+            dev_arena = N.arena(specs, device=self.device)
+            for k, _, _ in env._out_specs():             # the env writes its outputs into the combined arena
+                setattr(env, k, dev_arena[k])
+            pdev = {k: dev_arena[k] for k, _, _ in pspecs}
             avail_dev = torch.full((Bp, n), 0x1F, dtype=torch.uint8, device=self.device)
             part = dict(env=env, range=(b0, b1), stream=torch.cuda.Stream(device=self.device), pdev=pdev, avail_dev=avail_dev,
-                        env_dev=env._io(pdev["actions"]), slots=[])
+                        env_dev=env._io(pdev["actions"]), slots=[], keep=dev_arena)
             for _ in range(self.slots):
-                eh, ph = N.arena(env._out_specs(), pinned=True), N.arena(pspecs, pinned=True)
+                ha = N.arena(specs, pinned=True)
                 avail = torch.full((Bp, n), 0x1F, dtype=torch.uint8).pin_memory()
                 env_host, pol_host = N.StepIO(), N.PolicyIO()
                 env_host.host_arena = pol_host.host_arena = 1
                 for k, _, _ in env._out_specs():
-                    setattr(env_host, k, eh[k].data_ptr())
+                    setattr(env_host, k, ha[k].data_ptr())
                 for k, _, _ in pspecs:
-                    setattr(pol_host, k, ph[k].data_ptr())
+                    setattr(pol_host, k, ha[k].data_ptr())
                 pol_host.avail_bits = avail.data_ptr()
-                views = {k: v.numpy() for k, v in list(eh.items()) + list(ph.items()) if k != "_arena"}
+                views = {k: v.numpy() for k, v in ha.items() if k != "_arena"}
                 views["success"] = views.pop("success_out")
                 views["avail_bits"] = avail.numpy()
                 views["env_ids"] = (env_id0 + b0, env_id0 + b1)
-                part["slots"].append(dict(env_host=env_host, pol_host=pol_host, views=views, event=torch.cuda.Event(), keep=(eh, ph, avail)))
+                part["slots"].append(dict(env_host=env_host, pol_host=pol_host, views=views, event=torch.cuda.Event(), keep=(ha, avail)))
             self.parts.append(part)
         self._submitted = self._collected = 0
         self.kernel_launches = 0
@@ -291,9 +309,9 @@ class HostRollout:
         """(h2d, d2h) bytes one step moves"""
         h2d = d2h = 0
         for part in self.parts:
-            eh, ph, avail = part["slots"][0]["keep"]
+            ha, avail = part["slots"][0]["keep"]
             h2d += avail.numel()
-            d2h += sum(v.numel() * v.element_size() for k, v in list(eh.items()) + list(ph.items()) if k != "_arena")
+            d2h += sum(v.numel() * v.element_size() for k, v in ha.items() if k != "_arena")
         return h2d, d2h
 
     def check_errors(self):

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 2   /* 2: host_arena members, cm_rollout_step_host */
+#define CM_ABI_VERSION 2   /* 2: host_arena / obs_bits members, cm_rollout_step_host */
 #define CM_MAX_AGENTS 256   /* n, p */
 #define CM_MAX_GRID 64      /* grid side incl. Coverage's wall border */
 #define CM_MAX_LAYERS 4     /* n_gcn_layers */
@@ -134,6 +134,10 @@ typedef struct cm_step_io {
                                   finished [7] episodes [8] return sum [9] length sum [10] success sum [11..15] counts sums
                                   — the sums behind AverageReturn / SuccessRate / AverageCaptureCount ... that
                                   centralized_ma_ppo.py:345-372 logs from `paths` */
+    uint32_t *obs_bits;        /* optional [B][n][6] u32: the same observation PACKED — words 0..2: the 0/1 window columns as bits (bit k
+                                  of the 96-bit string = obs column k, k < obs_nbits = D - 3 (PredatorPrey) / D - 2 (Coverage)), words
+                                  3..5: the remaining scalar columns as float bits.  24 bytes per agent instead of 4 D; cm_policy_forward
+                                  reads it instead of `obs` when given (cm_policy_io.obs_bits) */
     int32_t host_arena;        /* read from the `host` struct of the *_host calls only.  Non-zero = the caller declares that the
                                   non-NULL buffers of that struct are carved from ONE host arena in the member order the call
                                   copies them, with the same padding (<= 1 KB) as the buffers of the `dev` struct: the library
@@ -197,6 +201,10 @@ typedef struct cm_policy_io {
     int32_t *error_flag;       /* DEVICE i32[1], optional: set when a bounded device-side wait times out */
     float *workspace;          /* teams with n > 64 only: cm_policy_workspace_bytes() bytes of scratch (stays L2 resident) */
     size_t workspace_bytes;
+    const uint32_t *obs_bits;  /* optional [B][n][6]: the packed observation cm_env_step writes (cm_step_io.obs_bits).  When given, the
+                                  tensor-core kernels (math = 1) build their first operand from it — 24 bytes per agent row instead of
+                                  4 D, the 0/1 columns need no low-order operand — and `obs` may be NULL; results are bit-identical */
+    int32_t obs_nbits;         /* number of leading 0/1 columns in obs_bits (D - 3 / D - 2) */
     int32_t host_arena;        /* `host` struct of the *_host calls only; see cm_step_io.host_arena */
 } cm_policy_io;
 

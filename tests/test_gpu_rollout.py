@@ -298,3 +298,46 @@ def test_sampler_paths_content_and_reference_layout(case):
             assert det["reward"] == r and det["step_cnt"] == 1
             assert det["capture_cnt"] == (int(c[0]) if scen == "pp" else c[0] / float(n)) and det["move_cnt"] == c[1] / float(n)
     sampler.shutdown_worker()
+
+
+@pytest.mark.parametrize("scen,kind", [("pp", "comm"), ("co", "comm"), ("pp", "dec"), ("pp_large", "comm")])
+def test_packed_observations_equal_fp32_rows(scen, kind):
+    """cm_step_io.obs_bits (window bits + scalar columns, 24 bytes per agent) is exactly the fp32 observation row, and the
+    tensor-core policy kernels fed with it (first operand built from the bits, low-order pass only for the K slice with the
+    scalar columns) return bit-identical logits / probabilities / actions to the same kernels fed with the fp32 rows."""
+    from com_marl_b200.envs import BatchedEnv
+    from com_marl_b200.rollout import make_policy
+    if scen == "pp":
+        params, spec = _mk("pp", 20, 2, 0.08, 4, 0.2, {"max_env_steps": 30})
+    elif scen == "pp_large":
+        params, spec = _mk("pp", 30, 2, 0.08, 4, 0.0, {"max_env_steps": 12})
+    else:
+        params, spec = _mk("co", 30, 2, 0.06, 2, 0.1, {"max_env_steps": 40})
+    B, n, D = 77, spec.n_agents, spec.obs_dim
+    env = BatchedEnv(spec, B)
+    bits = env.enable_obs_bits()
+    env.reset()
+    pol = make_policy(spec, kind=kind)
+    acts = torch.randint(0, 5, (B, n), dtype=torch.int8, device="cuda")
+    for _ in range(3):
+        env.step(acts)
+    nb = env.obs_nbits
+    assert nb == D - (3 if spec.scenario == "pp" else 2)
+    w = np.ascontiguousarray(bits.cpu().numpy()).view(np.uint32)                      # [B, n, 6]
+    cols = np.arange(nb)
+    unpacked = ((w[..., cols >> 5] >> (cols & 31).astype(np.uint32)) & 1).astype(np.float32)
+    scal = np.ascontiguousarray(w[..., 3:3 + D - nb]).view(np.float32)
+    assert np.array_equal(np.concatenate([unpacked, scal], axis=-1), env.obs.cpu().numpy())
+    outs = []
+    for packed in (False, True):
+        probs = torch.empty((B, n, 5), device="cuda"); logits = torch.empty((B, n, 5), device="cuda")
+        actions = torch.empty((B, n), dtype=torch.int8, device="cuda")
+        kw = dict(obs_bits=bits, obs_nbits=nb) if packed else {}
+        if kind == "comm":
+            pol.act_device(env.obs, env.adj_bits, env.chan_bits, tick=env.tick, episode=env.episode, probs=probs, logits=logits, actions=actions, **kw)
+        else:
+            pol.act_device(env.obs, tick=env.tick, episode=env.episode, probs=probs, logits=logits, actions=actions, **kw)
+        outs.append((logits.cpu(), probs.cpu(), actions.cpu()))
+    pol.check_errors()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
