@@ -431,8 +431,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
     unsigned char *ACT2 = smem + kActBytes + kWBytes;                    // second A operand (aliases KV while it is idle)
     float *red = KV + 64 * kTPitch;                                      // [8][128] softmax max / sum exchange
     float *bias_s = red + 8 * kTPitch;                                   // [704]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + kBiasFloats); // [0],[1] weight slot full, [2] MMAs done
-    uint32_t *tmem_s = reinterpret_cast<uint32_t *>(bars + 3);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + kBiasFloats); // [0],[1] weight slot full, [2] MMAs done, [3] MMAs of a multi-warp phase done
+    uint32_t *tmem_s = reinterpret_cast<uint32_t *>(bars + 4);
 
     const cm_policy_desc &d = A.d;
     const cm_policy_io &io = A.io;
@@ -449,6 +449,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         mbar_init(&bars[2], 1);
+        mbar_init(&bars[3], kVec == 0 ? (uint32_t)(kTcRows / A.slot) : 1u);      // one arrival per env slot (run_slots)
         fence_mbar_init();
     }
     fence_before_thread_sync();
@@ -551,6 +552,29 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
             fence_before_thread_sync();
         }
         m_phase ^= 1;
+        __syncthreads();
+        fence_after_thread_sync();
+    };
+    // products of INDEPENDENT accumulators issued by several warps at once (warp w issues the products of env slot w and commits
+    // them on a barrier that expects one arrival per slot): the issue path of one thread costs ~60 cycles per instruction
+    // whatever its size, so the 24 small products of an aggregation layer take a quarter of the time from four warps
+    uint32_t s_phase = 0;
+    auto run_slots = [&](int nw, auto issue) {
+        fence_proxy_async();
+        fence_before_thread_sync();
+        __syncthreads();
+        if (warp < nw) {
+            fence_after_thread_sync();
+            const uint32_t leader = elect_one() ? 1u : 0u;
+            if (!(CM_TC_DEBUG & 1)) issue(warp, leader);
+            mma_commit_pred(&bars[3], leader);
+            __syncwarp();
+        }
+        if (warp == 0) {
+            ok = mbar_wait(&bars[3], s_phase) && ok;
+            fence_before_thread_sync();
+        }
+        s_phase ^= 1;
         __syncthreads();
         fence_after_thread_sync();
     };
@@ -833,20 +857,18 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
             red[sub * kTPitch + row] = dpart;
             // out_e^T [64 x S] = V_e^T [64 x S keys] A_e^T [S keys x S rows] for every env slot e, three fp16 products each
             // into ONE accumulator (columns e S .. of R1; row c of the result = lane 32 (c / 16) + c % 16)
-            run_custom([&](uint32_t leader) {
+            run_slots(n_slots, [&](int e, uint32_t leader) {
                 const uint32_t idesc = make_idesc_f16(64, S) | kIdescAMajorMN;
                 const uint32_t a0 = smem_u32(ACT2), b0 = smem_u32(ACT), p_lo = (uint32_t)kTcRows * S * 2;
-                for (int e = 0; e < n_slots; ++e) {
-                    const uint32_t dcol = tmem + kR1 + (uint32_t)(e << slog);
-                    const uint32_t ae = a0 + (uint32_t)e * (uint32_t)S * 128u;                       // key rows e S ..: 128 bytes per key
-                    const uint32_t be = b0 + (uint32_t)e * (uint32_t)(S >> 3) * (uint32_t)(S >> 3) * 128u;   // query rows e S ..
-                    for (int j = 0; j < (S >> 4); ++j) {
-                        const uint64_t da_hi = make_smem_desc16_mn(ae + (uint32_t)j * 2048u, 64), da_lo = make_smem_desc16_mn(ae + v_lo + (uint32_t)j * 2048u, 64);
-                        const uint64_t db_hi = make_smem_desc16(be, S, j), db_lo = make_smem_desc16(be + p_lo, S, j);
-                        mma_f16_pred(dcol, da_hi, db_hi, idesc, j ? 1u : 0u, leader);
-                        mma_f16_pred(dcol, da_hi, db_lo, idesc, 1u, leader);
-                        mma_f16_pred(dcol, da_lo, db_hi, idesc, 1u, leader);
-                    }
+                const uint32_t dcol = tmem + kR1 + (uint32_t)(e << slog);
+                const uint32_t ae = a0 + (uint32_t)e * (uint32_t)S * 128u;                       // key rows e S ..: 128 bytes per key
+                const uint32_t be = b0 + (uint32_t)e * (uint32_t)(S >> 3) * (uint32_t)(S >> 3) * 128u;   // query rows e S ..
+                for (int j = 0; j < (S >> 4); ++j) {
+                    const uint64_t da_hi = make_smem_desc16_mn(ae + (uint32_t)j * 2048u, 64), da_lo = make_smem_desc16_mn(ae + v_lo + (uint32_t)j * 2048u, 64);
+                    const uint64_t db_hi = make_smem_desc16(be, S, j), db_lo = make_smem_desc16(be + p_lo, S, j);
+                    mma_f16_pred(dcol, da_hi, db_hi, idesc, j ? 1u : 0u, leader);
+                    mma_f16_pred(dcol, da_hi, db_lo, idesc, 1u, leader);
+                    mma_f16_pred(dcol, da_lo, db_hi, idesc, 1u, leader);
                 }
             });
             const float den = ((red[row] + red[kTPitch + row]) + red[2 * kTPitch + row]) + red[3 * kTPitch + row];
@@ -1182,7 +1204,7 @@ static bool cm_tc_attention_disabled()
     return off != 0;
 }
 
-static size_t tc_smem_bytes() { return (size_t)kActBytes + kWBytes + (64 + 8) * kTPitch * 4 + kBiasFloats * 4 + 64; }
+static size_t tc_smem_bytes() { return (size_t)kActBytes + kWBytes + (64 + 8) * kTPitch * 4 + kBiasFloats * 4 + 64; }   // (4 mbarriers + the TMEM base)
 
 static int launch_tc_mode(const cm_policy_desc *desc, const cm_policy_io *io, int mode, int in_dim, float *scr_e, float *scr_q,
                           float *scr_hw, cudaStream_t stream)
