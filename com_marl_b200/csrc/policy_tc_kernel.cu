@@ -131,8 +131,15 @@ __device__ __forceinline__ float tanh_scaled(float a)
 // bounds the dense epilogues locally — two MUFU per tanh occupy it for ~60 % of an epilogue — so the four reciprocals of a
 // group are replaced by one plus nine multiplications on the FMA pipe: 1.25 MUFU per tanh.  Arguments are clamped at 30
 // (tanh = 1 - 2^-29 rounds to 1 in fp32), so the product of four (2^a + 1) stays below 2^121.  |error| <= ~4e-7 absolute.
+#ifndef CM_TANH_SHARED_RCP
+#define CM_TANH_SHARED_RCP 1
+#endif
 __device__ __forceinline__ void tanh4_scaled(float &a0, float &a1, float &a2, float &a3)
 {
+#if !CM_TANH_SHARED_RCP
+    a0 = tanh_scaled(a0); a1 = tanh_scaled(a1); a2 = tanh_scaled(a2); a3 = tanh_scaled(a3);
+    return;
+#endif
     float e0, e1, e2, e3, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(a0, 30.0f)));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(a1, 30.0f)));

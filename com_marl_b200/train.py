@@ -17,7 +17,7 @@ from .spaces import Box, Discrete, EnvSpec
 
 
 class DeviceTrainer:
-    def __init__(self, spec, n_envs, device="cuda", env_id0=0, seed=1, kind="comm", **ppo_args):
+    def __init__(self, spec, n_envs, device="cuda", env_id0=0, seed=1, kind="comm", groups=1, **ppo_args):
         """kind: 'comm' / 'dec' (runner_*_comm.py / runner_*_obsDP.py:61: Comm-DP / Obs-DP policy + CommBaseCritic), 'cent'
         (runner_*_cent.py:60-62: CENT policy + GaussianMLPBaseline(hidden_sizes=(64, 64, 64)))"""
         self.spec, self.device, self.seed = spec, torch.device(device), int(seed)
@@ -32,8 +32,10 @@ class DeviceTrainer:
             self.critic = GaussianMLPBaseline(env_spec, hidden_sizes=(64, 64, 64), device=self.device)
         self.algo = DevicePPO(self.policy, self.critic, **ppo_args)
         # one chunk = one episode horizon: every env finishes at least one episode per round (time limit)
+        # the horizon is replayed from ONE captured CUDA graph: the kernel weight blobs are persistent buffers refreshed in
+        # place after every update (RolloutEngine.run_chunk -> policy.refresh_weights), so the graph stays valid
         self.engine = RolloutEngine(spec, self.policy, n_envs, device=self.device, env_id0=env_id0, ring=spec.max_steps,
-                                    use_graph=False)
+                                    use_graph=True, groups=groups)
         self.epoch = 0
 
     def train_epoch(self):
