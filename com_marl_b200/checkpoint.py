@@ -68,14 +68,22 @@ def load_reference_checkpoint(path, device="cuda", **policy_kwargs):
         D = int(_attr(ref, "_dec_obs_dim", default=sd["encoder._layers.0.linear.weight"].shape[1]))
         L = sum(1 for k in sd if k.startswith("gcn_layers.") and k.endswith(".weight"))
         cls, kw = CommCategoricalMLPPolicy, dict(n_gcn_layers=L, residual=bool(_attr(ref, "residual", default=True)),
-                                                 gcn_bias=any(k.startswith("gcn_layers.") and k.endswith(".bias") for k in sd))
+                                                 gcn_bias=any(k.startswith("gcn_layers.") and k.endswith(".bias") for k in sd),
+                                                 # layer widths / attention type as pickled (env_uitils.py:82-87)
+                                                 encoder_hidden_sizes=(int(sd["encoder._layers.0.linear.weight"].shape[0]),),
+                                                 embedding_dim=int(sd["encoder._output_layers.0.linear.weight"].shape[0]),
+                                                 categorical_mlp_hidden_sizes=tuple(int(sd[f"categorical_output_layer._layers.{i}.linear.weight"].shape[0]) for i in range(3)),
+                                                 attention_type="general" if "attention_layer.linear_in.weight" in sd else "dot")
     elif kind == "DecCategoricalMLPPolicy":
         D = int(sd["encoder._layers.0.linear.weight"].shape[1])
-        cls, kw = DecCategoricalMLPPolicy, {}
+        cls, kw = DecCategoricalMLPPolicy, dict(hidden_sizes=(int(sd["encoder._layers.0.linear.weight"].shape[0]),
+                                                              int(sd["encoder._output_layers.0.linear.weight"].shape[0]),
+                                                              int(sd["_layers.0.linear.weight"].shape[0])))
     elif kind == "CentralizedCategoricalMLPPolicy":
         D = int(sd["_layers.0.linear.weight"].shape[1]) // n
         nl = _attr(ref, "_hidden_nonlinearity")
-        cls, kw = CentralizedCategoricalMLPPolicy, dict(hidden_nonlinearity="relu" if getattr(nl, "__name__", "tanh") == "relu" else "tanh")
+        cls, kw = CentralizedCategoricalMLPPolicy, dict(hidden_nonlinearity="relu" if getattr(nl, "__name__", "tanh") == "relu" else "tanh",
+                                                        hidden_sizes=tuple(int(sd[f"_layers.{i}.linear.weight"].shape[0]) for i in range(3)))
     else:
         raise ValueError(f"{path}: unsupported policy class {kind!r} in the checkpoint")
     kw.update(policy_kwargs)

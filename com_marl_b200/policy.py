@@ -33,6 +33,19 @@ def _refresh_in_place(old, new):
     return new.contiguous()
 
 
+def _pad2(w, rows, cols):
+    """zero-padded copy of a 2-D (or 1-D: rows only) tensor — the kernels are specialised for the reference's default layer
+    widths; a narrower layer runs on them EXACTLY with its weights embedded in zeros (a padded unit computes tanh(0) = 0 and
+    feeds nothing: its outgoing weights are zero too)"""
+    if w.dim() == 1:
+        out = w.new_zeros(rows)
+        out[:w.shape[0]] = w
+        return out
+    out = w.new_zeros((rows, cols))
+    out[:w.shape[0], :w.shape[1]] = w
+    return out
+
+
 class _MLP(nn.Module):
     """Parameter layout of garage's MultiHeadedMLPModule with one head
     (garage/torch/modules/multi_headed_mlp_module.py:60-100): _layers.i.linear, _output_layers.0.linear."""
@@ -61,15 +74,18 @@ class _MLP(nn.Module):
 
 
 class _Attention(nn.Module):
-    """attention_module.py:15-51, attention_type='general'"""
+    """attention_module.py:15-51: 'general' (score = H_j^T W_a q, a bias-free ``linear_in``) or 'dot' (score = H_j^T q: no parameter)"""
 
-    def __init__(self, dim):
+    def __init__(self, dim, attention_type="general"):
         super().__init__()
-        self.linear_in = nn.Linear(dim, dim, bias=False)
+        self.attention_type = attention_type
+        if attention_type == "general":
+            self.linear_in = nn.Linear(dim, dim, bias=False)
 
     def forward(self, query):
         context = query.transpose(-2, -1)
-        return torch.softmax(torch.matmul(self.linear_in(query), context), dim=-1)
+        q = self.linear_in(query) if self.attention_type == "general" else query
+        return torch.softmax(torch.matmul(q, context), dim=-1)
 
 
 class _GraphConv(nn.Module):
@@ -100,11 +116,14 @@ class CommCategoricalMLPPolicy(nn.Module):
         super().__init__()
         if not hasattr(env_spec.action_space, "n"):
             raise AssertionError("Categorical policy only works with akro.Discrete action space.")
-        if tuple(encoder_hidden_sizes) != (128,) or embedding_dim != 64 or tuple(categorical_mlp_hidden_sizes) != (128, 64, 32):
-            raise NotImplementedError("the fused kernel is specialised for the reference's default sizes "
-                                      "(encoder (128,), embedding 64, head (128, 64, 32))")
-        if attention_type != "general":
-            raise NotImplementedError("only attention_type='general' (the reference default) is implemented")
+        enc, head = tuple(encoder_hidden_sizes), tuple(categorical_mlp_hidden_sizes)
+        if len(enc) != 1 or len(head) != 3 or enc[0] > 128 or embedding_dim > 64 or head[0] > 128 or head[1] > 64 or head[2] > 32:
+            raise NotImplementedError("the fused kernel holds one encoder hidden layer of <= 128 units, an embedding of <= 64 and a head "
+                                      "of three hidden layers of <= (128, 64, 32) units (the reference's defaults are exactly these "
+                                      "maxima; narrower layers run exactly, zero-padded)")
+        if attention_type not in ("general", "dot"):
+            raise NotImplementedError("attention_type must be 'general' or 'dot' (the reference's 'diff' has no forward path either: "
+                                      "attention_module.py:38-51)")
         self.name, self.device = name, torch.device(device)
         self.comm, self.centralized, self.step, self.eps = True, True, 0, 1e-12
         self.residual = bool(residual)
@@ -122,7 +141,7 @@ class CommCategoricalMLPPolicy(nn.Module):
             raise ValueError("math must be 'auto', 'fp32', 'tc' or 'tc_fp32attn'")
         self.math = math
         self.encoder = _MLP(self._dec_obs_dim, encoder_hidden_sizes, embedding_dim, output_tanh=True)
-        self.attention_layer = _Attention(embedding_dim)
+        self.attention_layer = _Attention(embedding_dim, attention_type)
         self.gcn_layers = nn.ModuleList([_GraphConv(embedding_dim, gcn_bias) for _ in range(self.n_gcn_layers)])
         self.categorical_output_layer = _MLP(embedding_dim, categorical_mlp_hidden_sizes, self._action_dim, output_tanh=False)
         self.to(self.device)
@@ -145,16 +164,20 @@ class CommCategoricalMLPPolicy(nn.Module):
         sig = self._signature()
         if self._blob is None or sig != self._blob_sig:
             sd = self.state_dict()
-            L, E = self.n_gcn_layers, self._embedding_dim
-            parts = [sd["encoder._layers.0.linear.weight"].t(), sd["encoder._layers.0.linear.bias"],
-                     sd["encoder._output_layers.0.linear.weight"].t(), sd["encoder._output_layers.0.linear.bias"],
-                     sd["attention_layer.linear_in.weight"].t()]
-            parts += [sd[f"gcn_layers.{l}.weight"] for l in range(L)]
-            parts += [sd.get(f"gcn_layers.{l}.bias", torch.zeros(E, device=self.device)) for l in range(L)]
-            for i in range(3):
-                parts += [sd[f"categorical_output_layer._layers.{i}.linear.weight"].t(),
-                          sd[f"categorical_output_layer._layers.{i}.linear.bias"]]
-            parts += [sd["categorical_output_layer._output_layers.0.linear.weight"].t(),
+            L, E, D = self.n_gcn_layers, self._embedding_dim, self._dec_obs_dim
+            # blob layout of include/commarl_b200.h at the kernel's widths (128 / 64 / (128, 64, 32)); narrower layers are
+            # embedded in zeros (_pad2), 'dot' attention is W_a = identity
+            att = sd["attention_layer.linear_in.weight"].t() if "attention_layer.linear_in.weight" in sd \
+                else torch.eye(E, device=self.device)
+            parts = [_pad2(sd["encoder._layers.0.linear.weight"].t(), D, 128), _pad2(sd["encoder._layers.0.linear.bias"], 128, 0),
+                     _pad2(sd["encoder._output_layers.0.linear.weight"].t(), 128, 64), _pad2(sd["encoder._output_layers.0.linear.bias"], 64, 0),
+                     _pad2(att, 64, 64)]
+            parts += [_pad2(sd[f"gcn_layers.{l}.weight"], 64, 64) for l in range(L)]
+            parts += [_pad2(sd.get(f"gcn_layers.{l}.bias", torch.zeros(E, device=self.device)), 64, 0) for l in range(L)]
+            for i, (k_in, k_out) in enumerate(((64, 128), (128, 64), (64, 32))):
+                parts += [_pad2(sd[f"categorical_output_layer._layers.{i}.linear.weight"].t(), k_in, k_out),
+                          _pad2(sd[f"categorical_output_layer._layers.{i}.linear.bias"], k_out, 0)]
+            parts += [_pad2(sd["categorical_output_layer._output_layers.0.linear.weight"].t(), 32, self._action_dim),
                       sd["categorical_output_layer._output_layers.0.linear.bias"]]
             blob = torch.cat([p.detach().to(self.device, torch.float32).contiguous().reshape(-1) for p in parts])
             expect = N.lib().cm_policy_blob_floats(self._dec_obs_dim, L)
@@ -432,9 +455,9 @@ class DecCategoricalMLPPolicy(nn.Module):
         super().__init__()
         if not hasattr(env_spec.action_space, "n"):
             raise AssertionError("CategoricalMLPPolicy only works with akro.Discrete action space.")
-        if tuple(hidden_sizes) != (128, 64, 32):
-            raise NotImplementedError("the fused kernel is specialised for the runners' sizes hidden_sizes=(128, 64, 32) "
-                                      "(exp_runners/env_uitils.py:188-189)")
+        if len(tuple(hidden_sizes)) != 3 or hidden_sizes[0] > 128 or hidden_sizes[1] > 64 or hidden_sizes[2] > 32:
+            raise NotImplementedError("the fused kernel holds hidden_sizes of three layers of <= (128, 64, 32) units (the runners' "
+                                      "sizes, exp_runners/env_uitils.py:188-189; narrower layers run exactly, zero-padded)")
         self.name, self.device = name, torch.device(device)
         self.comm, self.centralized, self.step = False, True, 0
         self.residual, self.math, self.n_gcn_layers = False, "tc", 1      # blob layout of one (unused) GCN layer
@@ -467,11 +490,12 @@ class DecCategoricalMLPPolicy(nn.Module):
         if self._blob is None or sig != self._blob_sig:
             sd, E, dev = self.state_dict(), self._embedding_dim, self.device
             z = lambda *shape: torch.zeros(shape, device=dev)  # noqa: E731
-            parts = [sd["encoder._layers.0.linear.weight"].t(), sd["encoder._layers.0.linear.bias"],
-                     sd["encoder._output_layers.0.linear.weight"].t(), sd["encoder._output_layers.0.linear.bias"],
-                     z(E, E), z(E, E), z(E), z(E, 128), z(128), z(128, 64), z(64),
-                     sd["_layers.0.linear.weight"].t(), sd["_layers.0.linear.bias"],
-                     sd["_output_layers.0.linear.weight"].t(), sd["_output_layers.0.linear.bias"]]
+            D = self._dec_obs_dim
+            parts = [_pad2(sd["encoder._layers.0.linear.weight"].t(), D, 128), _pad2(sd["encoder._layers.0.linear.bias"], 128, 0),
+                     _pad2(sd["encoder._output_layers.0.linear.weight"].t(), 128, 64), _pad2(sd["encoder._output_layers.0.linear.bias"], 64, 0),
+                     z(64, 64), z(64, 64), z(64), z(64, 128), z(128), z(128, 64), z(64),
+                     _pad2(sd["_layers.0.linear.weight"].t(), 64, 32), _pad2(sd["_layers.0.linear.bias"], 32, 0),
+                     _pad2(sd["_output_layers.0.linear.weight"].t(), 32, self._action_dim), sd["_output_layers.0.linear.bias"]]
             blob = torch.cat([p.detach().to(dev, torch.float32).contiguous().reshape(-1) for p in parts])
             assert blob.numel() == N.lib().cm_policy_blob_floats(self._dec_obs_dim, 1)
             self._blob = _refresh_in_place(self._blob, blob)
@@ -563,9 +587,9 @@ class CentralizedCategoricalMLPPolicy(nn.Module):
         super().__init__()
         if not hasattr(env_spec.action_space, "n"):
             raise AssertionError("Categorical policy only works with akro.Discrete action space.")
-        if tuple(hidden_sizes) != (128, 64, 32):
-            raise NotImplementedError("the kernel is specialised for the runners' sizes hidden_sizes=(128, 64, 32) "
-                                      "(exp_runners/env_uitils.py:188-189)")
+        if len(tuple(hidden_sizes)) != 3 or hidden_sizes[0] > 128 or hidden_sizes[1] > 64 or hidden_sizes[2] > 32:
+            raise NotImplementedError("the kernel holds hidden_sizes of three layers of <= (128, 64, 32) units (the runners' sizes, "
+                                      "exp_runners/env_uitils.py:188-189; narrower layers run exactly, zero-padded)")
         if hidden_nonlinearity in (torch.tanh, "tanh"):
             self._relu = False
         elif hidden_nonlinearity in (torch.relu, torch.nn.functional.relu, "relu"):
@@ -602,9 +626,9 @@ class CentralizedCategoricalMLPPolicy(nn.Module):
         if self._blob is None or sig != self._blob_sig:
             sd = self.state_dict()
             parts = []
-            for i in range(3):
-                parts += [sd[f"_layers.{i}.linear.weight"].t(), sd[f"_layers.{i}.linear.bias"]]
-            parts += [sd["_output_layers.0.linear.weight"].t(), sd["_output_layers.0.linear.bias"]]
+            for i, (k_in, k_out) in enumerate(((self._obs_dim, 128), (128, 64), (64, 32))):
+                parts += [_pad2(sd[f"_layers.{i}.linear.weight"].t(), k_in, k_out), _pad2(sd[f"_layers.{i}.linear.bias"], k_out, 0)]
+            parts += [_pad2(sd["_output_layers.0.linear.weight"].t(), 32, self._action_dim * self._n_agents), sd["_output_layers.0.linear.bias"]]
             blob = torch.cat([p.detach().to(self.device, torch.float32).contiguous().reshape(-1) for p in parts])
             assert blob.numel() == N.lib().cm_policy_cent_blob_floats(self._n_agents, self._dec_obs_dim)
             self._blob = _refresh_in_place(self._blob, blob)

@@ -48,13 +48,13 @@ class CommBaseCritic(nn.Module):
                  attention_type="general", n_gcn_layers=2, residual=True, gcn_bias=True, aggregator_type="sum",
                  name="base_critic", device="cuda"):
         super().__init__()
-        if attention_type != "general" or aggregator_type != "sum":
-            raise NotImplementedError("attention_type='general' and aggregator_type='sum' (the runners' settings) only")
+        if attention_type not in ("general", "dot") or aggregator_type != "sum":
+            raise NotImplementedError("attention_type 'general' / 'dot' and aggregator_type='sum' (the runners' setting) only")
         self.name, self.device = name, torch.device(device)
         self._n_agents, self.residual, self.eps = int(n_agents), bool(residual), 1e-12
         self._dec_obs_dim = int(env_spec.observation_space.flat_dim / n_agents)
         self.encoder = _MLP(self._dec_obs_dim, tuple(encoder_hidden_sizes), embedding_dim, output_tanh=True)
-        self.attention_layer = _Attention(embedding_dim)
+        self.attention_layer = _Attention(embedding_dim, attention_type)
         self.gcn_layers = nn.ModuleList([_GraphConv(embedding_dim, gcn_bias) for _ in range(int(n_gcn_layers))])
         self.baseline_aggregator = _GaussianHead(embedding_dim, tuple(decoder_hidden_sizes))
         self.to(self.device)

@@ -290,7 +290,8 @@ def policy_forward(w, obs, avail, adj, chan, dtype=np.float32):
     x = np.asarray(obs, dtype=f)
     h = np.tanh(x @ g("encoder._layers.0.linear.weight").T + g("encoder._layers.0.linear.bias"))
     E = np.tanh(h @ g("encoder._output_layers.0.linear.weight").T + g("encoder._output_layers.0.linear.bias"))
-    q = E @ g("attention_layer.linear_in.weight").T
+    # attention_module.py:38-49: 'general' scores H_j^T W_a q (linear_in), 'dot' scores H_j^T q (no parameter)
+    q = E @ g("attention_layer.linear_in.weight").T if "attention_layer.linear_in.weight" in w else E
     s = q @ np.swapaxes(E, -1, -2)
     s = s - s.max(axis=-1, keepdims=True)
     e = np.exp(s)

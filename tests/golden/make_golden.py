@@ -269,7 +269,7 @@ def run_ge_direct(ns):
     print("ge_direct written")
 
 
-def run_policy_case(ns, name, scenario, params, B, seed, loss_for_masks):
+def run_policy_case(ns, name, scenario, params, B, seed, loss_for_masks, **policy_kwargs):
     """Reference CommCategoricalMLPPolicy forward on observations taken from a reference rollout."""
     random.seed(seed)
     np.random.seed(seed)
@@ -282,7 +282,7 @@ def run_policy_case(ns, name, scenario, params, B, seed, loss_for_masks):
     genv = ns.GarageEnv(env)
     n = env.n_agents
     torch.manual_seed(1)  # policy weights = reference init under torch.manual_seed(1)
-    pol = ns.CommCategoricalMLPPolicy(genv.spec, n_agents=n)
+    pol = ns.CommCategoricalMLPPolicy(genv.spec, n_agents=n, **policy_kwargs)
     # non-zero biases so the bias paths are exercised (xavier init zeroes them)
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
@@ -312,7 +312,8 @@ def run_policy_case(ns, name, scenario, params, B, seed, loss_for_masks):
         dist, attn = pol.forward(obs_b, av_b, adj_b, ch_b, get_actions=True)
     hook.remove()
     sd = {f"w::{k}": v.detach().numpy() for k, v in pol.state_dict().items()}
-    meta = dict(name=name, scenario=scenario, n=n, D=obs_b.shape[-1] // n, B=B, L=params["n_gcn_layers"])
+    meta = dict(name=name, scenario=scenario, n=n, D=obs_b.shape[-1] // n, B=B, L=params["n_gcn_layers"],
+                policy_kwargs={k: (list(v) if isinstance(v, (tuple, list)) else v) for k, v in policy_kwargs.items()})
     np.savez_compressed(os.path.join(HERE, f"policy_{name}.npz"), meta=np.array(json.dumps(meta)),
                         obs=obs_b, avail=av_b, adj=pack_rows(adj_b), chan=pack_rows(ch_b),
                         probs=dist.probs.numpy(), attn=attn.numpy(), logits=logits["v"], **sd)

@@ -42,6 +42,8 @@ class PolicyCase:
         z = np.load(os.path.join(GOLDEN_DIR, f"policy_{name}.npz"))
         self.meta = json.loads(str(z["meta"]))
         self.n, self.D, self.B, self.L = (self.meta[k] for k in ("n", "D", "B", "L"))
+        # constructor arguments beyond the defaults (tests/golden/make_golden_shapes.py: narrower layers, 'dot' attention)
+        self.policy_kwargs = {k: (tuple(v) if isinstance(v, list) else v) for k, v in self.meta.get("policy_kwargs", {}).items()}
         self.weights = {k[3:]: z[k] for k in z.files if k.startswith("w::")}
         self.obs = z["obs"].reshape(self.B, self.n, self.D)
         self.avail = z["avail"].reshape(self.B, self.n, 5)

@@ -15,11 +15,11 @@ pytestmark = pytest.mark.gpu
 SMALL = policy_cases()
 
 
-def _policy(n, D, L, weights=None, seed=0, math="fp32"):
+def _policy(n, D, L, weights=None, seed=0, math="fp32", **kwargs):
     from com_marl_b200.policy import CommCategoricalMLPPolicy
     from com_marl_b200.spaces import Box, Discrete, EnvSpec
     torch.manual_seed(seed)
-    pol = CommCategoricalMLPPolicy(EnvSpec(Box(np.zeros(n * D), np.ones(n * D)), Discrete(5)), n, n_gcn_layers=L, math=math)
+    pol = CommCategoricalMLPPolicy(EnvSpec(Box(np.zeros(n * D), np.ones(n * D)), Discrete(5)), n, n_gcn_layers=L, math=math, **kwargs)
     if weights is not None:
         pol.load_state_dict({k: torch.as_tensor(v) for k, v in weights.items()})   # reference checkpoints load as is
     return pol
@@ -29,7 +29,7 @@ def _policy(n, D, L, weights=None, seed=0, math="fp32"):
 @pytest.mark.parametrize("name", SMALL)
 def test_policy_kernel_matches_reference_golden(name, math):
     c = PolicyCase(name)
-    pol = _policy(c.n, c.D, c.L, c.weights, math=math)
+    pol = _policy(c.n, c.D, c.L, c.weights, math=math, **c.policy_kwargs)       # (narrow / 'dot' cases: the reference's own ctor arguments)
     dist, attn = pol.forward(c.obs.reshape(c.B, -1), c.avail.reshape(c.B, -1), c.adj.astype(np.float32),
                              c.chan.astype(np.float32), get_actions=True)
     probs = dist.probs.numpy()

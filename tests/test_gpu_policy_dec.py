@@ -169,3 +169,30 @@ def test_policy_kind_error_codes():
         assert N.lib().cm_policy_forward(C.byref(desc), C.byref(io), N.stream_ptr()) == expect, (kind, math)
     torch.cuda.synchronize()
     assert torch.isfinite(probs).all()
+
+
+@pytest.mark.parametrize("kind", ["dec", "cent"])
+def test_narrow_hidden_sizes_run_zero_padded(kind):
+    """hidden_sizes below the kernels' widths (128, 64, 32) run on the same kernels, embedded in zeros: the kernel equals the
+    module's own differentiable torch forward (the training path) to 1e-5"""
+    from com_marl_b200.policy import CentralizedCategoricalMLPPolicy, DecCategoricalMLPPolicy
+    from com_marl_b200.spaces import Box, Discrete, EnvSpec
+    n, D, B = 5, 29, 97
+    spec = EnvSpec(Box(np.zeros(n * D), np.ones(n * D)), Discrete(5))
+    torch.manual_seed(3)
+    cls = DecCategoricalMLPPolicy if kind == "dec" else CentralizedCategoricalMLPPolicy
+    pol = cls(spec, n, hidden_sizes=(72, 40, 24))
+    with torch.no_grad():
+        for k, v in pol.state_dict().items():
+            if k.endswith("bias"):
+                v.uniform_(-0.1, 0.1)
+    obs = torch.rand((B, n * D), device="cuda")
+    avail = torch.ones((B, n * 5), device="cuda")
+    probs = torch.empty((B, n, 5), device="cuda")
+    pol.act_device(obs.reshape(B, n, D), probs=probs, greedy=True, actions=torch.empty((B, n), dtype=torch.int8, device="cuda"))
+    pol.check_errors()
+    with torch.no_grad():
+        ref = pol.forward(obs, avail).probs
+    assert (probs - ref).abs().max().item() <= 1e-5
+    with pytest.raises(NotImplementedError):
+        cls(spec, n, hidden_sizes=(256, 64, 32))
