@@ -582,7 +582,8 @@ def measure_c5_ppo(cx, envs, rounds=2):
     scen, params = params_for("c5")
     spec = ScenarioSpec.from_params(scen, params, seed=1)
     tr = DeviceTrainer(spec, envs, device=dev, env_id0=cx.rank * envs, optimization_mini_epochs=2)
-    tr.train_epoch()                         # warm-up round (allocations, cuBLAS handles, NCCL communicator)
+    tr.train_epoch()                         # warm-up rounds: allocations, cuBLAS handles, NCCL communicator (first, eager chunk) ...
+    tr.train_epoch()                         # ... and the capture of the rollout graph (second chunk)
     torch.cuda.synchronize(dev)
     cx.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
