@@ -438,8 +438,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
     unsigned char *ACT2 = smem + kActBytes + kWBytes;                    // second A operand (aliases KV while it is idle)
     float *red = KV + 64 * kTPitch;                                      // [8][128] softmax max / sum exchange
     float *bias_s = red + 8 * kTPitch;                                   // [704]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + kBiasFloats); // [0],[1] weight slot full, [2] MMAs done, [3] MMAs of a multi-warp phase done
-    uint32_t *tmem_s = reinterpret_cast<uint32_t *>(bars + 4);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + kBiasFloats); // [0],[1] weight slot full, [2] MMAs done, [3] MMAs of a per-slot phase done, [4] MMAs of a two-product phase done
+    uint32_t *tmem_s = reinterpret_cast<uint32_t *>(bars + 5);
 
     const cm_policy_desc &d = A.d;
     const cm_policy_io &io = A.io;
@@ -457,6 +457,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         mbar_init(&bars[1], 1);
         mbar_init(&bars[2], 1);
         mbar_init(&bars[3], kVec == 0 ? (uint32_t)(kTcRows / A.slot) : 1u);      // one arrival per env slot (run_slots)
+        mbar_init(&bars[4], 2);                                                  // one arrival per product of a two-product phase
         fence_mbar_init();
     }
     fence_before_thread_sync();
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
     fence_after_thread_sync();
     const uint32_t tmem = *tmem_s;
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    uint32_t m_phase = 0;
+    uint32_t m_phase = 0, p_phase = 0;
     bool ok = true;
 
     // ---- weight stream: the stages of the plan are consumed in order, tile after tile; warp 0 keeps the
@@ -506,30 +507,38 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
 #ifdef CM_TC_TRACE
         tr1 = clock64();
 #endif
-        if (warp == 0) {                 // whole warp, converged: waits for the weights, the leader lane issues
+        // A phase of two products is issued by TWO warps at once (warp i waits for weight block i and issues product i; both
+        // commit on a barrier that expects two arrivals): the timeline of a tile showed 0.8 - 2.3 k cycles of issue per
+        // two-product phase — one warp's instruction stream crawling through ~120 instructions while the co-resident tile's
+        // epilogue owns the issue slots — against ~0.2 k of tensor latency behind the last instruction.
+        // (two K panels of one product accumulate into the SAME block, in order: those stay with one warp)
+        const bool par = nops == 2 && op0.dcol != op1.dcol;
+        if (warp == 0 || (par && warp == 1)) {     // whole warp, converged: waits for the weights, the leader lane issues
             fence_after_thread_sync();
             const uint32_t leader = elect_one() ? 1u : 0u;
-            for (int i = 0; i < nops; ++i) {
+            for (int i = par ? warp : 0; i < (par ? warp + 1 : nops); ++i) {
                 const uint32_t b = consumed + (uint32_t)i;
                 ok = mbar_wait(&bars[b & 1u], (b >> 1) & 1u) && ok;
 #ifdef CM_TC_TRACE
-                trw[i] = clock64();
+                trw[i & 1] = clock64();
 #endif
                 const TcStage &st = P.st[si + i];
                 const MmaOp op = i ? op1 : op0;
                 issue_layer(tmem + op.dcol, op.abuf ? ACT2 : ACT, WB + (b & 1u) * (uint32_t)kSlotBytes, st.N, st.Kp, op.acc, leader, op.lo_from);
             }
-            mma_commit_pred(&bars[2], leader);
+            mma_commit_pred(par ? &bars[4] : &bars[2], leader);
             __syncwarp();
 #ifdef CM_TC_TRACE
             tr2 = clock64();
 #endif
-            // only this warp polls the completion barrier; the other fifteen sleep in the CTA barrier below and leave
-            // the issue slots to the co-resident tile
-            ok = mbar_wait(&bars[2], m_phase) && ok;
-            fence_before_thread_sync();
+            // only warp 0 polls the completion barrier; the others sleep in the CTA barrier below and leave the issue slots to
+            // the co-resident tile
+            if (warp == 0) {
+                ok = (par ? mbar_wait(&bars[4], p_phase) : mbar_wait(&bars[2], m_phase)) && ok;
+                fence_before_thread_sync();
+            }
         }
-        m_phase ^= 1;
+        if (par) p_phase ^= 1; else m_phase ^= 1;          // only the barrier that was used advances
         __syncthreads();
         fence_after_thread_sync();
 #ifdef CM_TC_TRACE
