@@ -16,12 +16,13 @@ CH_FC, CH_FL, CH_IID, CH_GE = 0, 1, 2, 3
 POLICY_COMM, POLICY_DEC, POLICY_CENT = 0, 1, 2
 POLICY_FLAG_RELU = 1
 MAX_AGENTS, MAX_GRID, MAX_LAYERS = 256, 64, 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = ("cm_abi_version", "cm_strerror", "cm_last_cuda_error", "cm_device_count", "cm_env_reset", "cm_env_step",
            "cm_comm_update", "cm_policy_forward", "cm_policy_blob_floats", "cm_policy_cent_blob_floats", "cm_policy_cent_tc_blob_floats", "cm_policy_cent_workspace_bytes", "cm_policy_workspace_bytes", "cm_policy_tc_blob_floats", "cm_policy_tc_prepare", "cm_mask_pack",
            "cm_mask_unpack", "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host", "cm_rollout_step_host", "cm_ppo_advantages",
-           "cm_adam_step")
+           "cm_adam_step", "cm_critic_blob_floats", "cm_ppo_net_workspace_floats", "cm_ppo_net")
+NET_POLICY, NET_CRITIC = 0, 1
 
 
 class EnvDesc(C.Structure):
@@ -61,6 +62,20 @@ class PolicyIO(C.Structure):
                                           "episode", "probs", "logits", "attention", "actions", "tc_weights",
                                           "error_flag", "workspace")] + \
                [("workspace_bytes", C.c_size_t), ("obs_bits", C.c_void_p), ("obs_nbits", C.c_int32), ("host_arena", C.c_int32)]
+
+
+class NetDesc(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("kind", "n_agents", "obs_dim", "n_layers", "residual")] + \
+               [(k, C.c_float) for k in ("ent_coeff", "clip_lo", "clip_hi")]
+
+
+class NetIO(C.Structure):
+    _fields_ = [("n_steps", C.c_int64)] + \
+               [(k, C.c_void_p) for k in ("weights", "grad", "obs", "adj_bits", "chan_bits", "avail_bits", "actions", "adv", "old_ll",
+                                          "valid", "returns")] + \
+               [("inv_count", C.c_float)] + \
+               [(k, C.c_void_p) for k in ("ll", "entropy", "probs", "values", "loss", "workspace")] + \
+               [("workspace_floats", C.c_size_t)]
 
 
 class NativeError(RuntimeError):
@@ -115,6 +130,12 @@ def lib():
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cm_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
                                C.c_float, C.c_int32, C.c_float, C.c_void_p]
+    L.cm_critic_blob_floats.restype = C.c_size_t
+    L.cm_critic_blob_floats.argtypes = [C.c_int32, C.c_int32]
+    L.cm_ppo_net_workspace_floats.restype = C.c_size_t
+    L.cm_ppo_net_workspace_floats.argtypes = [C.POINTER(NetDesc), C.c_int64, C.c_int32]
+    L.cm_ppo_net.restype = C.c_int
+    L.cm_ppo_net.argtypes = [C.POINTER(NetDesc), C.POINTER(NetIO), C.c_void_p]
     for fn in ("cm_env_reset", "cm_env_step", "cm_comm_update", "cm_policy_forward", "cm_mask_pack", "cm_mask_unpack",
                "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host", "cm_rollout_step_host", "cm_ppo_advantages", "cm_adam_step"):
         getattr(L, fn).restype = C.c_int

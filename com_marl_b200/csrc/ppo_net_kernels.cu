@@ -1,0 +1,1200 @@
+// ppo_net_kernels.cu — hand-written forward + backward of the comm-GNN for the PPO update: the policy
+// network of CommCategoricalMLPPolicy (comm_categorical_mlp_policy.py:48-96, comm_base_net.py:80-108) with the clipped
+// surrogate / entropy objective of CentralizedMAPPO._compute_loss (centralized_ma_ppo.py:390-438, 540-589), and the value
+// network of CommBaseCritic (comm_base_critic.py:11-120) with its Gaussian negative log-likelihood loss.  Replaces the torch
+// autograd graph (~150 library kernels per optimizer step) by ~30 launches of six kernels, all exact fp32 (FFMA):
+//
+//   net_dense_fwd     Y = act(X W + b)              rows x K x N register-tiled product, K <= 128, N in {32, 64, 128}
+//   net_dense_bwd     dZ = dY (1 - Y^2);  dX (+)= dZ W^T;  dW += X^T dZ;  db += sum dZ        (one pass over the rows)
+//   net_scores        M = softmax(Q E^T) per env                                             (attention_module.py:38-49)
+//   net_agg_fwd       H = tanh(A~ V + b),  A~ = M.adj.chan / (rowsum + 1e-12)                 (comm_base_net.py:99-104)
+//   net_agg_bwd       dV = A~^T dZ,  dM (+)= d(A~)/dM applied to dZ V^T
+//   net_softmax_bwd   dS = M (dM - <dM, M>);  dQ = dS E;  dE += dS^T Q
+//   net_policy_head   logits = g3 W4 + b4 -> softmax -> availability mask -> log-likelihood, entropy, clipped objective,
+//                     d logits -> d g3, dW4, db4      net_critic_head: V(s) = sum_i (c1_i w2 + b2), Gaussian NLL, gradients
+//
+// The n x n parts work on strips of 8 query rows per warp (register tiles of 8 rows x n/32 keys per lane for the dot
+// products; coefficient strips staged through shared memory for the aggregations); a CTA owns as many whole envs as fit
+// into 256 rows.  Activations live in a caller-provided workspace; the batch is walked in chunks of env steps.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "commarl_b200.h"
+#include "common.cuh"
+#include "policy_layout.cuh"
+
+namespace cm {
+
+static constexpr int kNP = 68;          // pitch (floats) of a [row][64] array in shared memory: 128-bit reads of 8 consecutive rows hit 32 banks
+static constexpr int kRows = 256;       // rows (agents) of the envs a CTA of the per-env kernels owns at a time
+static constexpr int kNetThreads = 256;
+
+// ------------------------------------------------------------------------------------------------------------------
+// dense layers
+// ------------------------------------------------------------------------------------------------------------------
+template <int N, int ACT>
+__global__ void __launch_bounds__(256) net_dense_fwd_kernel(const float *__restrict__ X, int ldx, const float *__restrict__ W,
+                                                            const float *__restrict__ bias, float *__restrict__ Y, int ldy, int64_t R, int K)
+{
+    constexpr int TX = N >= 64 ? 16 : N / 4, TY = 256 / TX, RI = 128 / TY, CJ = N / (4 * TX);
+    extern __shared__ float4 smem4[];
+    float *sm = reinterpret_cast<float *>(smem4);
+    const int K4 = (K + 3) & ~3, KP = K4 + 4;
+    float *Ws = sm;                    // [K4][N]
+    float *Xs = sm + (size_t)K4 * N;   // [128][KP]
+    const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < K4 * N; i += 256) Ws[i] = i < K * N ? W[i] : 0.0f;
+    float bj[CJ * 4];
+#pragma unroll
+    for (int j = 0; j < CJ; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bj[4 * j + q] = bias ? bias[4 * tx + 64 * j + q] : 0.0f;
+    const bool vec = (ldx & 3) == 0 && (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    const int64_t tiles = (R + 127) / 128;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int64_t r0 = t * 128;
+        __syncthreads();
+        if (vec) {
+            const int kq = K4 >> 2;
+            for (int i = tid; i < 128 * 32; i += 256) {
+                const int r = i >> 5, q = i & 31;
+                if (q < kq) {
+                    const int64_t gr = r0 + r;
+                    const float4 v = gr < R ? *reinterpret_cast<const float4 *>(X + gr * ldx + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4 *>(Xs + r * KP + 4 * q) = v;
+                }
+            }
+        } else {
+            for (int r = warp; r < 128; r += 8) {
+                const int64_t gr = r0 + r;
+                for (int k = lane; k < K4; k += 32) Xs[r * KP + k] = (gr < R && k < K) ? X[gr * ldx + k] : 0.0f;
+            }
+        }
+        __syncthreads();
+        float acc[RI][CJ * 4];
+#pragma unroll
+        for (int i = 0; i < RI; ++i)
+#pragma unroll
+            for (int j = 0; j < CJ * 4; ++j) acc[i][j] = 0.0f;
+        for (int k4 = 0; k4 < K4; k4 += 4) {
+            float4 xa[RI];
+#pragma unroll
+            for (int i = 0; i < RI; ++i) xa[i] = *reinterpret_cast<const float4 *>(Xs + (ty + TY * i) * KP + k4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                float4 wb[CJ];
+#pragma unroll
+                for (int j = 0; j < CJ; ++j) wb[j] = *reinterpret_cast<const float4 *>(Ws + (k4 + kk) * N + 4 * tx + 64 * j);
+#pragma unroll
+                for (int i = 0; i < RI; ++i) {
+                    const float x = kk == 0 ? xa[i].x : (kk == 1 ? xa[i].y : (kk == 2 ? xa[i].z : xa[i].w));
+#pragma unroll
+                    for (int j = 0; j < CJ; ++j) {
+                        acc[i][4 * j + 0] = fmaf(x, wb[j].x, acc[i][4 * j + 0]);
+                        acc[i][4 * j + 1] = fmaf(x, wb[j].y, acc[i][4 * j + 1]);
+                        acc[i][4 * j + 2] = fmaf(x, wb[j].z, acc[i][4 * j + 2]);
+                        acc[i][4 * j + 3] = fmaf(x, wb[j].w, acc[i][4 * j + 3]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RI; ++i) {
+            const int64_t gr = r0 + ty + TY * i;
+            if (gr >= R) continue;
+#pragma unroll
+            for (int j = 0; j < CJ; ++j) {
+                float4 o;
+                o.x = acc[i][4 * j + 0] + bj[4 * j + 0];
+                o.y = acc[i][4 * j + 1] + bj[4 * j + 1];
+                o.z = acc[i][4 * j + 2] + bj[4 * j + 2];
+                o.w = acc[i][4 * j + 3] + bj[4 * j + 3];
+                if (ACT) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
+                *reinterpret_cast<float4 *>(Y + gr * ldy + 4 * tx + 64 * j) = o;
+            }
+        }
+    }
+}
+
+// One pass over the rows for the three gradients of Y = act(X W + b): dZ = dY (1 - Y^2) (DACT) or dY;
+// dX[r][k] (+)= sum_n dZ[r][n] W[k][n];  dW[k][n] += sum_r X[r][k] dZ[r][n];  db[n] += sum_r dZ[r][n].
+// dW / db are accumulated in registers over the tiles of a persistent CTA and added to global memory once.
+template <int N, int KMAX, int DACT>
+__global__ void __launch_bounds__(256) net_dense_bwd_kernel(const float *__restrict__ dY, int lddy, const float *__restrict__ Y, int ldy,
+                                                            const float *__restrict__ X, int ldx, const float *__restrict__ W,
+                                                            float *__restrict__ dX, int lddx, int accumulate, float *__restrict__ dW,
+                                                            float *__restrict__ db, int64_t R, int K)
+{
+    constexpr int NP = N + 4, KP = KMAX + 4;
+    constexpr int KJ = KMAX / 16;                                          // phase A: k = kx + 16 j
+    constexpr int NX = N >= 64 ? 16 : N / 4, NJ = N / (4 * NX), KY = 256 / NX;   // phase B: n = 4 nx + 64 j, k = 4 ky + 4 KY i
+    constexpr int KI = (KMAX + 4 * KY - 1) / (4 * KY);
+    extern __shared__ float4 smem4[];
+    float *sm = reinterpret_cast<float *>(smem4);
+    float *Ws = sm;                         // [KMAX][NP]
+    float *dZs = Ws + KMAX * NP;            // [128][NP]
+    float *Xs = dZs + 128 * NP;             // [128][KP]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < KMAX * N; i += 256) {
+        const int k = i / N, n = i - k * N;
+        Ws[k * NP + n] = k < K ? W[k * N + n] : 0.0f;
+    }
+    float wacc[KI * 4][NJ * 4];
+#pragma unroll
+    for (int a = 0; a < KI * 4; ++a)
+#pragma unroll
+        for (int b = 0; b < NJ * 4; ++b) wacc[a][b] = 0.0f;
+    float bacc = 0.0f;
+    const int kx = tid & 15, ty = tid >> 4;
+    const int nx = tid % NX, ky = tid / NX;
+    const int64_t tiles = (R + 127) / 128;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int64_t r0 = t * 128;
+        __syncthreads();
+        // dZ tile (coalesced rows of N floats) and X tile
+        for (int i = tid; i < 128 * (N / 4); i += 256) {
+            const int r = i / (N / 4), q = i - r * (N / 4);
+            const int64_t gr = r0 + r;
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr < R) {
+                g = *reinterpret_cast<const float4 *>(dY + gr * lddy + 4 * q);
+                if (DACT) {
+                    const float4 y = *reinterpret_cast<const float4 *>(Y + gr * ldy + 4 * q);
+                    g.x *= 1.0f - y.x * y.x; g.y *= 1.0f - y.y * y.y; g.z *= 1.0f - y.z * y.z; g.w *= 1.0f - y.w * y.w;
+                }
+            }
+            *reinterpret_cast<float4 *>(dZs + r * NP + 4 * q) = g;
+        }
+        for (int r = warp; r < 128; r += 8) {
+            const int64_t gr = r0 + r;
+            for (int k = lane; k < KMAX; k += 32) Xs[r * KP + k] = (gr < R && k < K) ? X[gr * ldx + k] : 0.0f;
+        }
+        __syncthreads();
+        if (dX) {                                            // ---- phase A: dX tile
+            float acc[8][KJ];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < KJ; ++j) acc[i][j] = 0.0f;
+            for (int n4 = 0; n4 < N; n4 += 4) {
+                float4 w[KJ];
+#pragma unroll
+                for (int j = 0; j < KJ; ++j) w[j] = *reinterpret_cast<const float4 *>(Ws + (kx + 16 * j) * NP + n4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 z = *reinterpret_cast<const float4 *>(dZs + (ty + 16 * i) * NP + n4);
+#pragma unroll
+                    for (int j = 0; j < KJ; ++j)
+                        acc[i][j] = fmaf(z.x, w[j].x, fmaf(z.y, w[j].y, fmaf(z.z, w[j].z, fmaf(z.w, w[j].w, acc[i][j]))));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t gr = r0 + ty + 16 * i;
+                if (gr >= R) continue;
+#pragma unroll
+                for (int j = 0; j < KJ; ++j) {
+                    const int k = kx + 16 * j;
+                    if (k < K) {
+                        float *p = dX + gr * lddx + k;
+                        *p = accumulate ? *p + acc[i][j] : acc[i][j];
+                    }
+                }
+            }
+        }
+        // ---- phase B: dW += X^T dZ over the 128 rows of the tile
+        if (4 * ky < KMAX) {
+#pragma unroll 2
+            for (int r = 0; r < 128; ++r) {
+                float4 xa[KI], za[NJ];
+#pragma unroll
+                for (int i = 0; i < KI; ++i)
+                    xa[i] = (4 * ky + 4 * KY * i) < KMAX ? *reinterpret_cast<const float4 *>(Xs + r * KP + 4 * ky + 4 * KY * i)
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) za[j] = *reinterpret_cast<const float4 *>(dZs + r * NP + 4 * nx + 64 * j);
+#pragma unroll
+                for (int i = 0; i < KI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const float xv[4] = {xa[i].x, xa[i].y, xa[i].z, xa[i].w};
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            wacc[4 * i + a][4 * j + 0] = fmaf(xv[a], za[j].x, wacc[4 * i + a][4 * j + 0]);
+                            wacc[4 * i + a][4 * j + 1] = fmaf(xv[a], za[j].y, wacc[4 * i + a][4 * j + 1]);
+                            wacc[4 * i + a][4 * j + 2] = fmaf(xv[a], za[j].z, wacc[4 * i + a][4 * j + 2]);
+                            wacc[4 * i + a][4 * j + 3] = fmaf(xv[a], za[j].w, wacc[4 * i + a][4 * j + 3]);
+                        }
+                    }
+            }
+        }
+        if (db && tid < N) {
+            float s = 0.0f;
+            for (int r = 0; r < 128; ++r) s += dZs[r * NP + tid];
+            bacc += s;
+        }
+    }
+    if (4 * ky < KMAX) {
+#pragma unroll
+        for (int i = 0; i < KI; ++i)
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int k = 4 * ky + 4 * KY * i + a;
+                if (k < K) {
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) atomicAdd(dW + k * N + 4 * nx + 64 * j + b, wacc[4 * i + a][4 * j + b]);
+                }
+            }
+    }
+    if (db && tid < N) atomicAdd(db + tid, bacc);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// n x n parts: strips of 8 query rows per warp
+// ------------------------------------------------------------------------------------------------------------------
+// acc[i][j] = < A[min(i, nr-1)][:], B[min(lane + 32 j, n-1)][:] > over the 64 columns; A, B rows in shared memory (pitch kNP)
+template <int KT>
+__device__ __forceinline__ void strip_dots(const float *As, int nr, const float *Bs, int n, int lane, float (&acc)[8][KT])
+{
+    int kb[KT];
+#pragma unroll
+    for (int j = 0; j < KT; ++j) kb[j] = min(lane + 32 * j, n - 1) * kNP;
+    int ra[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ra[i] = min(i, nr - 1) * kNP;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < KT; ++j) acc[i][j] = 0.0f;
+#pragma unroll 2
+    for (int c = 0; c < 64; c += 4) {
+        float4 b[KT];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) b[j] = *reinterpret_cast<const float4 *>(Bs + kb[j] + c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 a = *reinterpret_cast<const float4 *>(As + ra[i] + c);
+#pragma unroll
+            for (int j = 0; j < KT; ++j) acc[i][j] = fmaf(a.x, b[j].x, fmaf(a.y, b[j].y, fmaf(a.z, b[j].z, fmaf(a.w, b[j].w, acc[i][j]))));
+        }
+    }
+}
+
+// out[i][0..1] = sum_k Cs[i][k] B[k][2 lane + {0, 1}],  k < n;  Cs [8][CP] holds zeros from n up to the next multiple of 4
+__device__ __forceinline__ void strip_agg(const float *Cs, int CP, const float *Bs, int n, int lane, float (&out)[8][2])
+{
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i][0] = out[i][1] = 0.0f;
+    for (int k = 0; k < n; k += 4) {
+        float2 b[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float2 *>(Bs + min(k + q, n - 1) * kNP + 2 * lane);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 c = *reinterpret_cast<const float4 *>(Cs + i * CP + k);
+            out[i][0] = fmaf(c.x, b[0].x, fmaf(c.y, b[1].x, fmaf(c.z, b[2].x, fmaf(c.w, b[3].x, out[i][0]))));
+            out[i][1] = fmaf(c.x, b[0].y, fmaf(c.y, b[1].y, fmaf(c.z, b[2].y, fmaf(c.w, b[3].y, out[i][1]))));
+        }
+    }
+}
+
+// rows [row0, row0 + rows) x 64 floats of a global [.][64] array -> shared memory (pitch kNP); optional second array
+// and the product form dZ = a (1 - b^2)
+__device__ __forceinline__ void load_rows64(float *dst, const float *__restrict__ src, int64_t row0, int rows, int tid)
+{
+    for (int i = tid; i < rows * 16; i += kNetThreads) {
+        const int r = i >> 4, q = i & 15;
+        *reinterpret_cast<float4 *>(dst + r * kNP + 4 * q) = *reinterpret_cast<const float4 *>(src + (row0 + r) * 64 + 4 * q);
+    }
+}
+
+struct EnvBlock { int64_t s0; int ne, rows; };
+__device__ __forceinline__ EnvBlock env_block(int64_t blk, int G, int n, int64_t S)
+{
+    EnvBlock b;
+    b.s0 = blk * G;
+    b.ne = (int)min((int64_t)G, S - b.s0);
+    b.rows = b.ne * n;
+    return b;
+}
+
+__device__ __forceinline__ uint32_t mask_word(const uint32_t *__restrict__ bits, int64_t row, int W, int j)
+{
+    return bits ? (j < W ? bits[row * W + j] : 0u) : 0xFFFFFFFFu;
+}
+
+// M[s][i][:] = softmax_k < Q[s][i], E[s][k] >
+template <int KT>
+__global__ void __launch_bounds__(kNetThreads) net_scores_kernel(const float *__restrict__ Q, const float *__restrict__ E,
+                                                                 float *__restrict__ M, int n, int G, int64_t S)
+{
+    extern __shared__ float4 smem4[];
+    float *Es = reinterpret_cast<float *>(smem4), *Qs = Es + kRows * kNP;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ns = (n + 7) >> 3;
+    const int64_t nblk = (S + G - 1) / G;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const EnvBlock eb = env_block(blk, G, n, S);
+        __syncthreads();
+        load_rows64(Es, E, eb.s0 * n, eb.rows, tid);
+        load_rows64(Qs, Q, eb.s0 * n, eb.rows, tid);
+        __syncthreads();
+        for (int st = warp; st < eb.ne * ns; st += kNetThreads / 32) {
+            const int g = st / ns, j0 = (st - g * ns) * 8, nr = min(8, n - j0);
+            float acc[8][KT];
+            strip_dots<KT>(Qs + (g * n + j0) * kNP, nr, Es + g * n * kNP, n, lane, acc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < KT; ++j) if (lane + 32 * j < n) mx = fmaxf(mx, acc[i][j]);
+                mx = warp_max(mx);
+                float sum = 0.0f;
+#pragma unroll
+                for (int j = 0; j < KT; ++j) { acc[i][j] = lane + 32 * j < n ? expf(acc[i][j] - mx) : 0.0f; sum += acc[i][j]; }
+                sum = warp_sumf(sum);
+                if (i < nr) {
+                    float *mrow = M + ((eb.s0 + g) * n + j0 + i) * (int64_t)n;
+#pragma unroll
+                    for (int j = 0; j < KT; ++j) if (lane + 32 * j < n) mrow[lane + 32 * j] = acc[i][j] / sum;
+                }
+            }
+        }
+    }
+}
+
+// H[s][i][:] = tanh( sum_k A~[i][k] V[s][k][:] + b ),  A~ = M . adj . chan_l / (rowsum + 1e-12);  optional Xout = res + H
+template <int KT>
+__global__ void __launch_bounds__(kNetThreads) net_agg_fwd_kernel(const float *__restrict__ M, const uint32_t *__restrict__ adj,
+                                                                  const uint32_t *__restrict__ chan, int L, int l,
+                                                                  const float *__restrict__ V, const float *__restrict__ bias,
+                                                                  float *__restrict__ H, const float *__restrict__ res,
+                                                                  float *__restrict__ Xout, int n, int G, int64_t S)
+{
+    extern __shared__ float4 smem4[];
+    constexpr int CP = KT * 32 + 4;
+    float *Vs = reinterpret_cast<float *>(smem4), *Call = Vs + kRows * kNP;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float *Cs = Call + warp * 8 * CP;
+    const int ns = (n + 7) >> 3, W = (n + 31) >> 5;
+    const float2 bv = make_float2(bias[2 * lane], bias[2 * lane + 1]);
+    const int64_t nblk = (S + G - 1) / G;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const EnvBlock eb = env_block(blk, G, n, S);
+        __syncthreads();
+        load_rows64(Vs, V, eb.s0 * n, eb.rows, tid);
+        __syncthreads();
+        for (int st = warp; st < eb.ne * ns; st += kNetThreads / 32) {
+            const int g = st / ns, j0 = (st - g * ns) * 8, nr = min(8, n - j0);
+            const int64_t s = eb.s0 + g;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float a[KT];
+                float sum = 0.0f;
+                const int64_t row = s * n + j0 + min(i, nr - 1);
+#pragma unroll
+                for (int j = 0; j < KT; ++j) {
+                    const int k = lane + 32 * j;
+                    const uint32_t wd = mask_word(adj, row, W, j) & mask_word(chan, (s * L + l) * n + j0 + min(i, nr - 1), W, j);
+                    a[j] = (k < n && ((wd >> lane) & 1u)) ? M[row * n + k] : 0.0f;
+                    sum += a[j];
+                }
+                sum = warp_sumf(sum) + 1e-12f;
+#pragma unroll
+                for (int j = 0; j < KT; ++j) Cs[i * CP + lane + 32 * j] = a[j] / sum;
+            }
+            __syncwarp();
+            float out[8][2];
+            strip_agg(Cs, CP, Vs + g * n * kNP, n, lane, out);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < nr) {
+                    const int64_t row = s * n + j0 + i;
+                    const float2 h = make_float2(tanhf(out[i][0] + bv.x), tanhf(out[i][1] + bv.y));
+                    *reinterpret_cast<float2 *>(H + row * 64 + 2 * lane) = h;
+                    if (Xout) {
+                        const float2 e = *reinterpret_cast<const float2 *>(res + row * 64 + 2 * lane);
+                        *reinterpret_cast<float2 *>(Xout + row * 64 + 2 * lane) = make_float2(e.x + h.x, e.y + h.y);
+                    }
+                }
+        }
+    }
+}
+
+// Backward of one graph-convolution layer's aggregation.  dZ = dH (1 - H^2);  dV = A~^T dZ;  db += sum dZ;
+// dA~ = dZ V^T;  dM (+)= mask (dA~ - <dA~, A~>) / (rowsum + 1e-12).  A~ strips are parked TRANSPOSED in CT so that the
+// second pass (key strips) reads contiguous coefficient rows.
+template <int KT>
+__global__ void __launch_bounds__(kNetThreads) net_agg_bwd_kernel(const float *__restrict__ M, const uint32_t *__restrict__ adj,
+                                                                  const uint32_t *__restrict__ chan, int L, int l,
+                                                                  const float *__restrict__ V, const float *__restrict__ H,
+                                                                  const float *__restrict__ dH, float *__restrict__ dV,
+                                                                  float *__restrict__ dM, int dm_accumulate, float *__restrict__ CT,
+                                                                  float *__restrict__ db, int n, int G, int64_t S)
+{
+    extern __shared__ float4 smem4[];
+    constexpr int CP = KT * 32 + 4;
+    float *Vs = reinterpret_cast<float *>(smem4), *dZs = Vs + kRows * kNP, *Call = dZs + kRows * kNP;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float *Cs = Call + warp * 8 * CP;
+    const int ns = (n + 7) >> 3, W = (n + 31) >> 5;
+    float bacc = 0.0f;
+    const int64_t nblk = (S + G - 1) / G;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const EnvBlock eb = env_block(blk, G, n, S);
+        __syncthreads();
+        load_rows64(Vs, V, eb.s0 * n, eb.rows, tid);
+        for (int i = tid; i < eb.rows * 16; i += kNetThreads) {
+            const int r = i >> 4, q = i & 15;
+            const int64_t o = (eb.s0 * n + r) * 64 + 4 * q;
+            float4 g = *reinterpret_cast<const float4 *>(dH + o);
+            const float4 h = *reinterpret_cast<const float4 *>(H + o);
+            g.x *= 1.0f - h.x * h.x; g.y *= 1.0f - h.y * h.y; g.z *= 1.0f - h.z * h.z; g.w *= 1.0f - h.w * h.w;
+            *reinterpret_cast<float4 *>(dZs + r * kNP + 4 * q) = g;
+        }
+        __syncthreads();
+        if (tid < 64) {
+            float sacc = 0.0f;
+            for (int r = 0; r < eb.rows; ++r) sacc += dZs[r * kNP + tid];
+            bacc += sacc;
+        }
+        for (int st = warp; st < eb.ne * ns; st += kNetThreads / 32) {          // pass 1: query strips
+            const int g = st / ns, j0 = (st - g * ns) * 8, nr = min(8, n - j0);
+            const int64_t s = eb.s0 + g;
+            float acc[8][KT];
+            strip_dots<KT>(dZs + (g * n + j0) * kNP, nr, Vs + g * n * kNP, n, lane, acc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i >= nr) continue;                        // (warp-uniform)
+                const int64_t row = s * n + j0 + i;
+                float a[KT];
+                bool on[KT];
+                float sum = 0.0f;
+#pragma unroll
+                for (int j = 0; j < KT; ++j) {
+                    const int k = lane + 32 * j;
+                    const uint32_t wd = mask_word(adj, row, W, j) & mask_word(chan, (s * L + l) * n + j0 + i, W, j);
+                    on[j] = k < n && ((wd >> lane) & 1u);
+                    a[j] = on[j] ? M[row * n + k] : 0.0f;
+                    sum += a[j];
+                }
+                sum = warp_sumf(sum) + 1e-12f;
+                float dot = 0.0f;
+#pragma unroll
+                for (int j = 0; j < KT; ++j) { a[j] = a[j] / sum; dot = fmaf(acc[i][j], a[j], dot); }
+                dot = warp_sumf(dot);
+#pragma unroll
+                for (int j = 0; j < KT; ++j) {
+                    const int k = lane + 32 * j;
+                    if (k < n) {
+                        const float dm = on[j] ? (acc[i][j] - dot) / sum : 0.0f;
+                        float *p = dM + row * n + k;
+                        *p = dm_accumulate ? *p + dm : dm;
+                        CT[(s * n + k) * n + j0 + i] = a[j];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int st = warp; st < eb.ne * ns; st += kNetThreads / 32) {          // pass 2: key strips
+            const int g = st / ns, k0 = (st - g * ns) * 8, nk = min(8, n - k0);
+            const int64_t s = eb.s0 + g;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < KT; ++j) {
+                    const int q = lane + 32 * j;
+                    Cs[i * CP + q] = (i < nk && q < n) ? CT[(s * n + k0 + i) * n + q] : 0.0f;
+                }
+            __syncwarp();
+            float out[8][2];
+            strip_agg(Cs, CP, dZs + g * n * kNP, n, lane, out);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < nk) *reinterpret_cast<float2 *>(dV + (s * n + k0 + i) * 64 + 2 * lane) = make_float2(out[i][0], out[i][1]);
+        }
+    }
+    if (db && tid < 64) atomicAdd(db + tid, bacc);
+}
+
+// dS = M (dM - <dM, M>) per query row;  dQ = dS E;  dE += dS^T Q
+template <int KT>
+__global__ void __launch_bounds__(kNetThreads) net_softmax_bwd_kernel(const float *__restrict__ M, const float *__restrict__ dM,
+                                                                      const float *__restrict__ E, const float *__restrict__ Q,
+                                                                      float *__restrict__ dQ, float *__restrict__ dE,
+                                                                      float *__restrict__ CT, int n, int G, int64_t S)
+{
+    extern __shared__ float4 smem4[];
+    constexpr int CP = KT * 32 + 4;
+    float *Es = reinterpret_cast<float *>(smem4), *Qs = Es + kRows * kNP, *Call = Qs + kRows * kNP;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float *Cs = Call + warp * 8 * CP;
+    const int ns = (n + 7) >> 3;
+    const int64_t nblk = (S + G - 1) / G;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const EnvBlock eb = env_block(blk, G, n, S);
+        __syncthreads();
+        load_rows64(Es, E, eb.s0 * n, eb.rows, tid);
+        load_rows64(Qs, Q, eb.s0 * n, eb.rows, tid);
+        __syncthreads();
+        for (int st = warp; st < eb.ne * ns; st += kNetThreads / 32) {          // pass 1: query strips
+            const int g = st / ns, j0 = (st - g * ns) * 8, nr = min(8, n - j0);
+            const int64_t s = eb.s0 + g;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t row = s * n + j0 + min(i, nr - 1);
+                float m[KT], d[KT];
+                float dot = 0.0f;
+#pragma unroll
+                for (int j = 0; j < KT; ++j) {
+                    const int k = lane + 32 * j;
+                    m[j] = k < n ? M[row * n + k] : 0.0f;
+                    d[j] = k < n ? dM[row * n + k] : 0.0f;
+                    dot = fmaf(m[j], d[j], dot);
+                }
+                dot = warp_sumf(dot);
+#pragma unroll
+                for (int j = 0; j < KT; ++j) {
+                    const int k = lane + 32 * j;
+                    const float ds = i < nr ? m[j] * (d[j] - dot) : 0.0f;
+                    Cs[i * CP + k] = ds;
+                    if (i < nr && k < n) CT[(s * n + k) * n + j0 + i] = ds;
+                }
+            }
+            __syncwarp();
+            float out[8][2];
+            strip_agg(Cs, CP, Es + g * n * kNP, n, lane, out);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < nr) *reinterpret_cast<float2 *>(dQ + (s * n + j0 + i) * 64 + 2 * lane) = make_float2(out[i][0], out[i][1]);
+        }
+        __syncthreads();
+        for (int st = warp; st < eb.ne * ns; st += kNetThreads / 32) {          // pass 2: key strips
+            const int g = st / ns, k0 = (st - g * ns) * 8, nk = min(8, n - k0);
+            const int64_t s = eb.s0 + g;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < KT; ++j) {
+                    const int q = lane + 32 * j;
+                    Cs[i * CP + q] = (i < nk && q < n) ? CT[(s * n + k0 + i) * n + q] : 0.0f;
+                }
+            __syncwarp();
+            float out[8][2];
+            strip_agg(Cs, CP, Qs + g * n * kNP, n, lane, out);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < nk) {
+                    float2 *p = reinterpret_cast<float2 *>(dE + (s * n + k0 + i) * 64 + 2 * lane);
+                    const float2 o = *p;
+                    *p = make_float2(o.x + out[i][0], o.y + out[i][1]);
+                }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// heads + losses
+// ------------------------------------------------------------------------------------------------------------------
+struct PolicyHeadArgs {
+    const float *g3;             // [R][32] last hidden layer
+    const float *w4, *b4;        // [32][5], [5]
+    const uint8_t *avail_bits;   // [R] or NULL
+    const int64_t *actions;      // [R] or NULL (forward only: no log-likelihood)
+    const float *adv, *old_ll;   // [S]
+    const uint8_t *valid;        // [S] or NULL
+    float inv_count, ent_coeff, clip_lo, clip_hi;
+    float *ll, *ent, *probs, *loss;
+    float *dg3, *dw4, *db4;      // NULL: forward only
+    int n, G;
+    int64_t S;
+};
+
+__global__ void __launch_bounds__(kNetThreads) net_policy_head_kernel(const PolicyHeadArgs a)
+{
+    __shared__ float w4s[32 * CM_ACTIONS + CM_ACTIONS];
+    __shared__ float ll_row[kRows], ent_row[kRows], gll_env[kRows], gent_env[kRows];
+    __shared__ float red[32 * CM_ACTIONS + CM_ACTIONS];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n = a.n;
+    const float eps = 1.1920928955078125e-07f;                   // torch.finfo(float32).eps: probs_to_logits clamps to [eps, 1 - eps]
+    for (int i = tid; i < 32 * CM_ACTIONS + CM_ACTIONS; i += kNetThreads) {
+        w4s[i] = i < 32 * CM_ACTIONS ? a.w4[i] : a.b4[i - 32 * CM_ACTIONS];
+        red[i] = 0.0f;
+    }
+    const int64_t nblk = (a.S + a.G - 1) / a.G;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const EnvBlock eb = env_block(blk, a.G, n, a.S);
+        __syncthreads();
+        const bool active = tid < eb.rows;
+        const int64_t row = eb.s0 * n + (active ? tid : 0);
+        float g[32], p[CM_ACTIONS], q[CM_ACTIONS], lc[CM_ACTIONS];
+        float msum = 1.0f;
+        uint32_t av = 0x1Fu;
+        int act = 0;
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(a.g3 + row * 32);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const float4 v = src[k]; g[4 * k] = v.x; g[4 * k + 1] = v.y; g[4 * k + 2] = v.z; g[4 * k + 3] = v.w; }
+            float z[CM_ACTIONS];
+#pragma unroll
+            for (int j = 0; j < CM_ACTIONS; ++j) z[j] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+#pragma unroll
+                for (int j = 0; j < CM_ACTIONS; ++j) z[j] = fmaf(g[k], w4s[k * CM_ACTIONS + j], z[j]);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < CM_ACTIONS; ++j) { z[j] += w4s[32 * CM_ACTIONS + j]; mx = fmaxf(mx, z[j]); }
+            float sum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < CM_ACTIONS; ++j) { p[j] = expf(z[j] - mx); sum += p[j]; }
+            if (a.avail_bits) av = a.avail_bits[row];
+            msum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < CM_ACTIONS; ++j) { p[j] = p[j] / sum; q[j] = ((av >> j) & 1u) ? p[j] : 0.0f; msum += q[j]; }
+            float ent = 0.0f;
+#pragma unroll
+            for (int j = 0; j < CM_ACTIONS; ++j) {
+                q[j] = q[j] / msum;
+                lc[j] = logf(fminf(fmaxf(q[j], eps), 1.0f - eps));
+                ent -= q[j] * lc[j];
+            }
+            if (a.actions) act = (int)a.actions[row];
+            float lp = 0.0f;
+#pragma unroll
+            for (int j = 0; j < CM_ACTIONS; ++j) if (j == act) lp = lc[j];
+            if (active) {
+                ll_row[tid] = lp;
+                ent_row[tid] = ent;
+                if (a.probs)
+#pragma unroll
+                    for (int j = 0; j < CM_ACTIONS; ++j) a.probs[row * CM_ACTIONS + j] = q[j];
+            }
+        }
+        __syncthreads();
+        if (tid < eb.ne) {                                        // one thread per env: sums in agent order
+            float ll = 0.0f, en = 0.0f;
+            for (int i = 0; i < n; ++i) { ll += ll_row[tid * n + i]; en += ent_row[tid * n + i]; }
+            en = en / (float)n;
+            const int64_t s = eb.s0 + tid;
+            if (a.ll) a.ll[s] = ll;
+            if (a.ent) a.ent[s] = en;
+            float gl = 0.0f, ge = 0.0f;
+            const bool valid = a.valid ? a.valid[s] != 0 : true;
+            if (a.adv && valid) {
+                const float old = a.old_ll ? a.old_ll[s] : ll;
+                const float ratio = expf(ll - old), adv = a.adv[s];
+                const float rc = fminf(fmaxf(ratio, a.clip_lo), a.clip_hi);
+                const float s1 = ratio * adv, s2 = rc * adv;
+                const float in = (ratio >= a.clip_lo && ratio <= a.clip_hi) ? 1.0f : 0.0f;
+                // torch.min's gradient goes to the smaller argument, half to each on a tie; clamp passes it inside [lo, hi]
+                const float gr = s1 < s2 ? adv : (s1 > s2 ? adv * in : 0.5f * adv + 0.5f * adv * in);
+                if (a.loss) atomicAdd(a.loss, -(fminf(s1, s2) + a.ent_coeff * en) * a.inv_count);
+                gl = -a.inv_count * gr * ratio;
+                ge = -a.inv_count * a.ent_coeff / (float)n;
+            }
+            gll_env[tid] = gl;
+            gent_env[tid] = ge;
+        }
+        if (!a.dg3) continue;
+        __syncthreads();
+        float gz[CM_ACTIONS];
+        {
+            const int e = active ? tid / n : 0;
+            const float gl = active ? gll_env[e] : 0.0f, ge = active ? gent_env[e] : 0.0f;
+            float gq[CM_ACTIONS];
+            float proj = 0.0f;
+#pragma unroll
+            for (int j = 0; j < CM_ACTIONS; ++j) {
+                const float in = (q[j] >= eps && q[j] <= 1.0f - eps) ? 1.0f : 0.0f;
+                gq[j] = ge * (-lc[j] - in);
+                if (j == act) gq[j] += gl * (in > 0.0f ? 1.0f / q[j] : 0.0f);
+                proj = fmaf(gq[j], q[j], proj);
+            }
+            float dot = 0.0f;
+            float gp[CM_ACTIONS];
+#pragma unroll
+            for (int j = 0; j < CM_ACTIONS; ++j) {
+                gp[j] = ((av >> j) & 1u) ? (gq[j] - proj) / msum : 0.0f;
+                dot = fmaf(gp[j], p[j], dot);
+            }
+#pragma unroll
+            for (int j = 0; j < CM_ACTIONS; ++j) gz[j] = active ? p[j] * (gp[j] - dot) : 0.0f;
+        }
+        if (active) {
+            float4 *dst = reinterpret_cast<float4 *>(a.dg3 + row * 32);
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+                float o[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float v = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < CM_ACTIONS; ++j) v = fmaf(gz[j], w4s[(4 * k4 + c) * CM_ACTIONS + j], v);
+                    o[c] = v;
+                }
+                dst[k4] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+#pragma unroll
+            for (int j = 0; j < CM_ACTIONS; ++j) {
+                const float v = warp_sumf(active ? g[k] * gz[j] : 0.0f);
+                if (lane == 0) atomicAdd(&red[k * CM_ACTIONS + j], v);
+            }
+#pragma unroll
+        for (int j = 0; j < CM_ACTIONS; ++j) {
+            const float v = warp_sumf(gz[j]);
+            if (lane == 0) atomicAdd(&red[32 * CM_ACTIONS + j], v);
+        }
+    }
+    if (a.dg3) {
+        __syncthreads();
+        for (int i = tid; i < 32 * CM_ACTIONS + CM_ACTIONS; i += kNetThreads)
+            atomicAdd(i < 32 * CM_ACTIONS ? a.dw4 + i : a.db4 + (i - 32 * CM_ACTIONS), red[i]);
+    }
+}
+
+struct CriticHeadArgs {
+    const float *c1;             // [R][64] decoder hidden layer
+    const float *w2, *b2, *log_std;   // [64], [1], [1]
+    const float *returns;        // [S] or NULL (forward only)
+    float inv_count;
+    float *values, *loss;
+    float *dc1, *dw2, *db2, *dlog_std;
+    int n, G;
+    int64_t S;
+};
+
+__global__ void __launch_bounds__(kNetThreads) net_critic_head_kernel(const CriticHeadArgs a)
+{
+    __shared__ float w2s[64], v_row[kRows], gv_env[kRows], red[66];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n = a.n;
+    if (tid < 64) w2s[tid] = a.w2[tid];
+    if (tid < 66) red[tid] = 0.0f;
+    const float b2 = a.b2[0];
+    const float lmin = logf(1e-6f);
+    const float ls = a.log_std[0];
+    const float lsc = fmaxf(ls, lmin), sd = expf(lsc);
+    const int64_t nblk = (a.S + a.G - 1) / a.G;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const EnvBlock eb = env_block(blk, a.G, n, a.S);
+        __syncthreads();
+        const bool active = tid < eb.rows;
+        const int64_t row = eb.s0 * n + (active ? tid : 0);
+        float c[64];
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(a.c1 + row * 64);
+            float v = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float4 x = src[k];
+                c[4 * k] = x.x; c[4 * k + 1] = x.y; c[4 * k + 2] = x.z; c[4 * k + 3] = x.w;
+                v = fmaf(x.x, w2s[4 * k], fmaf(x.y, w2s[4 * k + 1], fmaf(x.z, w2s[4 * k + 2], fmaf(x.w, w2s[4 * k + 3], v))));
+            }
+            if (active) v_row[tid] = v + b2;
+        }
+        __syncthreads();
+        if (tid < eb.ne) {
+            float V = 0.0f;
+            for (int i = 0; i < n; ++i) V += v_row[tid * n + i];
+            const int64_t s = eb.s0 + tid;
+            if (a.values) a.values[s] = V;
+            float gv = 0.0f;
+            if (a.returns) {
+                const float d = (a.returns[s] - V) / sd;
+                if (a.loss) atomicAdd(a.loss, (0.5f * d * d + logf(sd) + 0.91893853320467274178f) * a.inv_count);
+                gv = -d / sd * a.inv_count;
+                if (a.dlog_std && ls >= lmin) atomicAdd(&red[65], (1.0f - d * d) * a.inv_count);
+            }
+            gv_env[tid] = gv;
+        }
+        if (!a.dc1) continue;
+        __syncthreads();
+        const float gv = active ? gv_env[tid / n] : 0.0f;
+        if (active) {
+            float4 *dst = reinterpret_cast<float4 *>(a.dc1 + row * 64);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) dst[k] = make_float4(gv * w2s[4 * k], gv * w2s[4 * k + 1], gv * w2s[4 * k + 2], gv * w2s[4 * k + 3]);
+        }
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            const float v = warp_sumf(c[k] * gv);
+            if (lane == 0) atomicAdd(&red[k], v);
+        }
+        const float v = warp_sumf(gv);
+        if (lane == 0) atomicAdd(&red[64], v);
+    }
+    if (a.dc1) {
+        __syncthreads();
+        if (tid < 64) atomicAdd(a.dw2 + tid, red[tid]);
+        if (tid == 64) atomicAdd(a.db2, red[64]);
+        if (tid == 65 && a.dlog_std) atomicAdd(a.dlog_std, red[65]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side: launch helpers and the two entry points
+// ------------------------------------------------------------------------------------------------------------------
+struct CriticBlob { int enc_w1, enc_b1, enc_w2, enc_b2, att_w, gcn_w, gcn_b, dec_w1, dec_b1, dec_w2, dec_b2, log_std, total; };
+static CriticBlob critic_blob_layout(int D, int L)
+{
+    CriticBlob o;
+    int p = 0;
+    o.enc_w1 = p; p += D * kH1;
+    o.enc_b1 = p; p += kH1;
+    o.enc_w2 = p; p += kH1 * kE;
+    o.enc_b2 = p; p += kE;
+    o.att_w = p; p += kE * kE;
+    o.gcn_w = p; p += L * kE * kE;
+    o.gcn_b = p; p += L * kE;
+    o.dec_w1 = p; p += kE * 64;
+    o.dec_b1 = p; p += 64;
+    o.dec_w2 = p; p += 64;
+    o.dec_b2 = p; p += 1;
+    o.log_std = p; p += 1;
+    o.total = p;
+    return o;
+}
+
+static int g_sms = 0;
+static int sm_count()
+{
+    if (!g_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sms <= 0) g_sms = 148;
+    }
+    return g_sms;
+}
+
+template <typename Kern>
+static cudaError_t set_smem(Kern k, size_t bytes)
+{
+    return bytes > 48 * 1024 ? cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) : cudaSuccess;
+}
+
+#define NET_TRY(expr) do { const cudaError_t e__ = (expr); if (e__ != cudaSuccess) return e__; } while (0)
+
+template <int N, int ACT>
+static cudaError_t dense_fwd_t(const float *X, int ldx, const float *W, const float *b, float *Y, int64_t R, int K, cudaStream_t st)
+{
+    const int K4 = (K + 3) & ~3;
+    const size_t smem = ((size_t)K4 * N + 128 * (size_t)(K4 + 4)) * sizeof(float);
+    NET_TRY(set_smem(net_dense_fwd_kernel<N, ACT>, smem));
+    const int per_sm = smem > 110 * 1024 ? 1 : (smem > 72 * 1024 ? 2 : 3);
+    const int64_t tiles = (R + 127) / 128;
+    const int grid = (int)(tiles < (int64_t)sm_count() * per_sm ? tiles : (int64_t)sm_count() * per_sm);
+    net_dense_fwd_kernel<N, ACT><<<grid, 256, smem, st>>>(X, ldx, W, b, Y, N, R, K);
+    return cudaGetLastError();
+}
+
+static cudaError_t dense_fwd(const float *X, int ldx, const float *W, const float *b, float *Y, int64_t R, int K, int N, int act,
+                             cudaStream_t st)
+{
+    if (N == 128) return act ? dense_fwd_t<128, 1>(X, ldx, W, b, Y, R, K, st) : dense_fwd_t<128, 0>(X, ldx, W, b, Y, R, K, st);
+    if (N == 64) return act ? dense_fwd_t<64, 1>(X, ldx, W, b, Y, R, K, st) : dense_fwd_t<64, 0>(X, ldx, W, b, Y, R, K, st);
+    return act ? dense_fwd_t<32, 1>(X, ldx, W, b, Y, R, K, st) : dense_fwd_t<32, 0>(X, ldx, W, b, Y, R, K, st);
+}
+
+template <int N, int KMAX, int DACT>
+static cudaError_t dense_bwd_t(const float *dY, const float *Y, const float *X, int ldx, const float *W, float *dX, int accumulate,
+                               float *dW, float *db, int64_t R, int K, cudaStream_t st)
+{
+    const size_t smem = ((size_t)KMAX * (N + 4) + 128 * (size_t)(N + 4) + 128 * (size_t)(KMAX + 4)) * sizeof(float);
+    NET_TRY(set_smem(net_dense_bwd_kernel<N, KMAX, DACT>, smem));
+    const int per_sm = smem > 110 * 1024 ? 1 : 2;
+    const int64_t tiles = (R + 127) / 128;
+    const int grid = (int)(tiles < (int64_t)sm_count() * per_sm ? tiles : (int64_t)sm_count() * per_sm);
+    net_dense_bwd_kernel<N, KMAX, DACT><<<grid, 256, smem, st>>>(dY, N, Y, N, X, ldx, W, dX, K, accumulate, dW, db, R, K);
+    return cudaGetLastError();
+}
+
+template <int N, int DACT>
+static cudaError_t dense_bwd_n(const float *dY, const float *Y, const float *X, int ldx, const float *W, float *dX, int accumulate,
+                               float *dW, float *db, int64_t R, int K, cudaStream_t st)
+{
+    return K <= 64 ? dense_bwd_t<N, 64, DACT>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st)
+                   : dense_bwd_t<N, 128, DACT>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st);
+}
+
+// gradients of Y = act(X W + b), Y [R][N]; dX [R][K] (lddx = K) may be NULL
+static cudaError_t dense_bwd(const float *dY, const float *Y, const float *X, int ldx, const float *W, float *dX, int accumulate,
+                             float *dW, float *db, int64_t R, int K, int N, int dact, cudaStream_t st)
+{
+    if (N == 128) return dact ? dense_bwd_n<128, 1>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st)
+                              : dense_bwd_n<128, 0>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st);
+    if (N == 64) return dact ? dense_bwd_n<64, 1>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st)
+                             : dense_bwd_n<64, 0>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st);
+    return dact ? dense_bwd_n<32, 1>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st)
+                : dense_bwd_n<32, 0>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st);
+}
+
+static int env_group(int n) { return n >= kRows ? 1 : kRows / n; }
+static int env_grid(int n, int64_t S, int per_sm)
+{
+    const int G = env_group(n);
+    const int64_t nblk = (S + G - 1) / G;
+    return (int)(nblk < (int64_t)sm_count() * per_sm ? nblk : (int64_t)sm_count() * per_sm);
+}
+
+struct EnvCall {
+    int n, L;
+    int64_t S;
+    const uint32_t *adj, *chan;
+    cudaStream_t st;
+};
+
+template <int KT>
+static cudaError_t scores_t(const EnvCall &c, const float *Q, const float *E, float *M)
+{
+    const size_t smem = 2 * (size_t)kRows * kNP * sizeof(float);
+    NET_TRY(set_smem(net_scores_kernel<KT>, smem));
+    net_scores_kernel<KT><<<env_grid(c.n, c.S, 1), kNetThreads, smem, c.st>>>(Q, E, M, c.n, env_group(c.n), c.S);
+    return cudaGetLastError();
+}
+template <int KT>
+static cudaError_t agg_fwd_t(const EnvCall &c, int l, const float *M, const float *V, const float *bias, float *H, const float *res,
+                             float *Xout)
+{
+    const size_t smem = ((size_t)kRows * kNP + 8 * 8 * (size_t)(KT * 32 + 4)) * sizeof(float);
+    NET_TRY(set_smem(net_agg_fwd_kernel<KT>, smem));
+    net_agg_fwd_kernel<KT><<<env_grid(c.n, c.S, smem > 110 * 1024 ? 1 : 2), kNetThreads, smem, c.st>>>(M, c.adj, c.chan, c.L, l, V, bias, H,
+                                                                                                    res, Xout, c.n, env_group(c.n), c.S);
+    return cudaGetLastError();
+}
+template <int KT>
+static cudaError_t agg_bwd_t(const EnvCall &c, int l, const float *M, const float *V, const float *H, const float *dH, float *dV,
+                             float *dM, int dm_acc, float *CT, float *db)
+{
+    const size_t smem = (2 * (size_t)kRows * kNP + 8 * 8 * (size_t)(KT * 32 + 4)) * sizeof(float);
+    NET_TRY(set_smem(net_agg_bwd_kernel<KT>, smem));
+    net_agg_bwd_kernel<KT><<<env_grid(c.n, c.S, 1), kNetThreads, smem, c.st>>>(M, c.adj, c.chan, c.L, l, V, H, dH, dV, dM, dm_acc, CT, db,
+                                                                            c.n, env_group(c.n), c.S);
+    return cudaGetLastError();
+}
+template <int KT>
+static cudaError_t softmax_bwd_t(const EnvCall &c, const float *M, const float *dM, const float *E, const float *Q, float *dQ, float *dE,
+                                 float *CT)
+{
+    const size_t smem = (2 * (size_t)kRows * kNP + 8 * 8 * (size_t)(KT * 32 + 4)) * sizeof(float);
+    NET_TRY(set_smem(net_softmax_bwd_kernel<KT>, smem));
+    net_softmax_bwd_kernel<KT><<<env_grid(c.n, c.S, 1), kNetThreads, smem, c.st>>>(M, dM, E, Q, dQ, dE, CT, c.n, env_group(c.n), c.S);
+    return cudaGetLastError();
+}
+
+#define KT_DISPATCH(fn, ...)                                              \
+    do {                                                                  \
+        const int kt__ = (c.n + 31) / 32;                                 \
+        if (kt__ <= 1) return fn<1>(__VA_ARGS__);                         \
+        if (kt__ <= 2) return fn<2>(__VA_ARGS__);                         \
+        if (kt__ <= 4) return fn<4>(__VA_ARGS__);                         \
+        if (kt__ <= 7) return fn<7>(__VA_ARGS__);                         \
+        return fn<8>(__VA_ARGS__);                                        \
+    } while (0)
+
+static cudaError_t scores(const EnvCall &c, const float *Q, const float *E, float *M) { KT_DISPATCH(scores_t, c, Q, E, M); }
+static cudaError_t agg_fwd(const EnvCall &c, int l, const float *M, const float *V, const float *bias, float *H, const float *res,
+                           float *Xout) { KT_DISPATCH(agg_fwd_t, c, l, M, V, bias, H, res, Xout); }
+static cudaError_t agg_bwd(const EnvCall &c, int l, const float *M, const float *V, const float *H, const float *dH, float *dV, float *dM,
+                           int dm_acc, float *CT, float *db) { KT_DISPATCH(agg_bwd_t, c, l, M, V, H, dH, dV, dM, dm_acc, CT, db); }
+static cudaError_t softmax_bwd(const EnvCall &c, const float *M, const float *dM, const float *E, const float *Q, float *dQ, float *dE,
+                               float *CT) { KT_DISPATCH(softmax_bwd_t, c, M, dM, E, Q, dQ, dE, CT); }
+
+// workspace of one chunk of `steps` env steps (floats)
+static constexpr size_t kWsSlack = 160;      // alignment of the base pointer and of each of the <= 30 carved arrays
+struct NetWs {
+    float *h1, *E, *Q, *M, *V[CM_MAX_LAYERS], *H[CM_MAX_LAYERS], *X, *g1, *g2, *g3, *t32, *t64a, *t64b, *t64c, *t128, *dM, *CT;
+};
+static size_t ws_floats_per_step(int n, int L, bool backward)
+{
+    size_t rows = 128 + 64 + 64 + (size_t)L * 128 + 64 + 128 + 64 + 32;
+    size_t sq = 1;
+    if (backward) { rows += 32 + 3 * 64 + 128; sq += 2; }
+    return (size_t)n * rows + sq * (size_t)n * n;
+}
+static NetWs carve(float *p, int n, int L, int64_t steps, bool backward)
+{
+    NetWs w;
+    const size_t R = (size_t)steps * n, S2 = (size_t)steps * n * n;
+    auto take = [&](size_t k) { float *q = p; p += (k + 3) & ~(size_t)3; return q; };      // every array 16-byte aligned
+    w.h1 = take(R * 128); w.E = take(R * 64); w.Q = take(R * 64); w.M = take(S2);
+    for (int l = 0; l < L; ++l) { w.V[l] = take(R * 64); w.H[l] = take(R * 64); }
+    w.X = take(R * 64); w.g1 = take(R * 128); w.g2 = take(R * 64); w.g3 = take(R * 32);
+    w.t32 = w.t64a = w.t64b = w.t64c = w.t128 = w.dM = w.CT = nullptr;
+    if (backward) {
+        w.t32 = take(R * 32); w.t64a = take(R * 64); w.t64b = take(R * 64); w.t64c = take(R * 64); w.t128 = take(R * 128);
+        w.dM = take(S2); w.CT = take(S2);
+    }
+    return w;
+}
+
+// the shared trunk: encoder -> attention -> graph convolutions -> X
+static cudaError_t trunk_fwd(const cm_net_desc &d, const EnvCall &c, const float *wts, const Blob &o, const float *obs, const NetWs &w)
+{
+    const int64_t R = c.S * d.n_agents;
+    NET_TRY(dense_fwd(obs, d.obs_dim, wts + o.enc_w1, wts + o.enc_b1, w.h1, R, d.obs_dim, 128, 1, c.st));
+    NET_TRY(dense_fwd(w.h1, 128, wts + o.enc_w2, wts + o.enc_b2, w.E, R, 128, 64, 1, c.st));
+    NET_TRY(dense_fwd(w.E, 64, wts + o.att_w, nullptr, w.Q, R, 64, 64, 0, c.st));
+    NET_TRY(scores(c, w.Q, w.E, w.M));
+    for (int l = 0; l < d.n_layers; ++l) {
+        const float *Hin = l == 0 ? w.E : w.H[l - 1];
+        NET_TRY(dense_fwd(Hin, 64, wts + o.gcn_w + l * kE * kE, nullptr, w.V[l], R, 64, 64, 0, c.st));
+        const bool last = l == d.n_layers - 1;
+        NET_TRY(agg_fwd(c, l, w.M, w.V[l], wts + o.gcn_b + l * kE, w.H[l], (last && d.residual) ? w.E : nullptr,
+                        (last && d.residual) ? w.X : nullptr));
+    }
+    return cudaSuccess;
+}
+
+// dXin (gradient of the trunk's output X = E + H_L or H_L, in w.t64b) -> parameter gradients of the trunk
+static cudaError_t trunk_bwd(const cm_net_desc &d, const EnvCall &c, const float *wts, float *grad, const Blob &o, const float *obs,
+                             const NetWs &w)
+{
+    const int64_t R = c.S * d.n_agents;
+    const int L = d.n_layers;
+    float *dE = w.t64b;                       // with the residual connection the gradient of X is the first term of dE
+    const float *dHl = w.t64b;
+    bool dE_init = d.residual != 0;
+    if (!d.residual) {                        // dX is dH_L only: park it, dE starts empty
+        NET_TRY(cudaMemcpyAsync(w.t64a, w.t64b, (size_t)R * 64 * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+        dHl = w.t64a;
+    }
+    for (int l = L - 1; l >= 0; --l) {
+        NET_TRY(agg_bwd(c, l, w.M, w.V[l], w.H[l], dHl, w.t64c, w.dM, l != L - 1, w.CT, grad + o.gcn_b + l * kE));
+        const float *Hin = l == 0 ? w.E : w.H[l - 1];
+        if (l == 0) {
+            NET_TRY(dense_bwd(w.t64c, nullptr, Hin, 64, wts + o.gcn_w, dE, dE_init ? 1 : 0, grad + o.gcn_w, nullptr, R, 64, 64, 0, c.st));
+            dE_init = true;
+        } else {
+            NET_TRY(dense_bwd(w.t64c, nullptr, Hin, 64, wts + o.gcn_w + l * kE * kE, w.t64a, 0, grad + o.gcn_w + l * kE * kE, nullptr, R, 64,
+                              64, 0, c.st));
+            dHl = w.t64a;
+        }
+    }
+    NET_TRY(softmax_bwd(c, w.M, w.dM, w.E, w.Q, w.t64c, dE, w.CT));
+    NET_TRY(dense_bwd(w.t64c, nullptr, w.E, 64, wts + o.att_w, dE, 1, grad + o.att_w, nullptr, R, 64, 64, 0, c.st));
+    NET_TRY(dense_bwd(dE, w.E, w.h1, 128, wts + o.enc_w2, w.t128, 0, grad + o.enc_w2, grad + o.enc_b2, R, 128, 64, 1, c.st));
+    NET_TRY(dense_bwd(w.t128, w.h1, obs, d.obs_dim, wts + o.enc_w1, nullptr, 0, grad + o.enc_w1, grad + o.enc_b1, R, d.obs_dim, 128, 1, c.st));
+    return cudaSuccess;
+}
+
+static Blob trunk_of(const CriticBlob &cb)
+{
+    Blob o = {};
+    o.enc_w1 = cb.enc_w1; o.enc_b1 = cb.enc_b1; o.enc_w2 = cb.enc_w2; o.enc_b2 = cb.enc_b2; o.att_w = cb.att_w;
+    o.gcn_w = cb.gcn_w; o.gcn_b = cb.gcn_b;
+    return o;
+}
+
+static cudaError_t run_chunk(const cm_net_desc &d, const cm_net_io &io, int64_t s0, int64_t steps, float *wsp, cudaStream_t st)
+{
+    const int n = d.n_agents, D = d.obs_dim, L = d.n_layers, W = (n + 31) / 32;
+    const bool backward = io.grad != nullptr;
+    const NetWs w = carve(wsp, n, L, steps, backward);
+    const int64_t R = steps * n, r0 = s0 * n;
+    EnvCall c;
+    c.n = n; c.L = L; c.S = steps; c.st = st;
+    c.adj = io.adj_bits ? io.adj_bits + r0 * W : nullptr;
+    c.chan = io.chan_bits ? io.chan_bits + s0 * L * n * W : nullptr;
+    const float *obs = io.obs + r0 * D;
+    const float *wts = io.weights;
+    const int G = env_group(n);
+    if (d.kind == CM_NET_POLICY) {
+        const Blob o = blob_layout(D, L);
+        NET_TRY(trunk_fwd(d, c, wts, o, obs, w));
+        const float *Xin = d.residual ? w.X : w.H[L - 1];
+        NET_TRY(dense_fwd(Xin, 64, wts + o.head_w1, wts + o.head_b1, w.g1, R, 64, 128, 1, st));
+        NET_TRY(dense_fwd(w.g1, 128, wts + o.head_w2, wts + o.head_b2, w.g2, R, 128, 64, 1, st));
+        NET_TRY(dense_fwd(w.g2, 64, wts + o.head_w3, wts + o.head_b3, w.g3, R, 64, 32, 1, st));
+        PolicyHeadArgs a = {};
+        a.g3 = w.g3; a.w4 = wts + o.head_w4; a.b4 = wts + o.head_b4;
+        a.avail_bits = io.avail_bits ? io.avail_bits + r0 : nullptr;
+        a.actions = io.actions ? io.actions + r0 : nullptr;
+        a.adv = io.adv ? io.adv + s0 : nullptr;
+        a.old_ll = io.old_ll ? io.old_ll + s0 : nullptr;
+        a.valid = io.valid ? io.valid + s0 : nullptr;
+        a.inv_count = io.inv_count; a.ent_coeff = d.ent_coeff; a.clip_lo = d.clip_lo; a.clip_hi = d.clip_hi;
+        a.ll = io.ll ? io.ll + s0 : nullptr;
+        a.ent = io.entropy ? io.entropy + s0 : nullptr;
+        a.probs = io.probs ? io.probs + r0 * CM_ACTIONS : nullptr;
+        a.loss = io.loss;
+        a.n = n; a.G = G; a.S = steps;
+        if (backward) { a.dg3 = w.t32; a.dw4 = io.grad + o.head_w4; a.db4 = io.grad + o.head_b4; }
+        net_policy_head_kernel<<<env_grid(n, steps, 4), kNetThreads, 0, st>>>(a);
+        NET_TRY(cudaGetLastError());
+        if (!backward) return cudaSuccess;
+        float *g = io.grad;
+        NET_TRY(dense_bwd(w.t32, w.g3, w.g2, 64, wts + o.head_w3, w.t64a, 0, g + o.head_w3, g + o.head_b3, R, 64, 32, 1, st));
+        NET_TRY(dense_bwd(w.t64a, w.g2, w.g1, 128, wts + o.head_w2, w.t128, 0, g + o.head_w2, g + o.head_b2, R, 128, 64, 1, st));
+        NET_TRY(dense_bwd(w.t128, w.g1, Xin, 64, wts + o.head_w1, w.t64b, 0, g + o.head_w1, g + o.head_b1, R, 64, 128, 1, st));
+        return trunk_bwd(d, c, wts, g, o, obs, w);
+    }
+    const CriticBlob cb = critic_blob_layout(D, L);
+    const Blob o = trunk_of(cb);
+    NET_TRY(trunk_fwd(d, c, wts, o, obs, w));
+    const float *Xin = d.residual ? w.X : w.H[L - 1];
+    NET_TRY(dense_fwd(Xin, 64, wts + cb.dec_w1, wts + cb.dec_b1, w.g2, R, 64, 64, 1, st));
+    CriticHeadArgs a = {};
+    a.c1 = w.g2; a.w2 = wts + cb.dec_w2; a.b2 = wts + cb.dec_b2; a.log_std = wts + cb.log_std;
+    a.returns = io.returns ? io.returns + s0 : nullptr;
+    a.inv_count = io.inv_count;
+    a.values = io.values ? io.values + s0 : nullptr;
+    a.loss = io.loss;
+    a.n = n; a.G = G; a.S = steps;
+    if (backward) { a.dc1 = w.t64a; a.dw2 = io.grad + cb.dec_w2; a.db2 = io.grad + cb.dec_b2; a.dlog_std = io.grad + cb.log_std; }
+    net_critic_head_kernel<<<env_grid(n, steps, 4), kNetThreads, 0, st>>>(a);
+    NET_TRY(cudaGetLastError());
+    if (!backward) return cudaSuccess;
+    NET_TRY(dense_bwd(w.t64a, w.g2, Xin, 64, wts + cb.dec_w1, w.t64b, 0, io.grad + cb.dec_w1, io.grad + cb.dec_b1, R, 64, 64, 1, st));
+    return trunk_bwd(d, c, wts, io.grad, o, obs, w);
+}
+
+}  // namespace cm
+
+extern "C" size_t cm_critic_blob_floats(int32_t obs_dim, int32_t n_layers)
+{
+    return (size_t)cm::critic_blob_layout(obs_dim, n_layers).total;
+}
+
+extern "C" size_t cm_ppo_net_workspace_floats(const cm_net_desc *desc, int64_t chunk_steps, int32_t backward)
+{
+    if (!desc || chunk_steps < 1) return 0;
+    return cm::ws_floats_per_step(desc->n_agents, desc->n_layers, backward != 0) * (size_t)chunk_steps + cm::kWsSlack;
+}
+
+extern "C" int cm_ppo_net(const cm_net_desc *desc, const cm_net_io *io, cm_stream_t stream)
+{
+    using namespace cm;
+    if (!desc || !io || !io->weights || !io->obs || !io->workspace || io->n_steps < 0) return CM_EINVAL;
+    const cm_net_desc &d = *desc;
+    if (d.kind != CM_NET_POLICY && d.kind != CM_NET_CRITIC) return CM_EINVAL;
+    if (d.n_agents < 1 || d.n_agents > CM_MAX_AGENTS || d.obs_dim < 1 || d.obs_dim > 128 || d.n_layers < 1 || d.n_layers > CM_MAX_LAYERS)
+        return CM_EUNSUPPORTED;
+    if (io->grad && d.kind == CM_NET_POLICY && (!io->actions || !io->adv)) return CM_EINVAL;
+    if (io->grad && d.kind == CM_NET_CRITIC && !io->returns) return CM_EINVAL;
+    if (io->n_steps == 0) return CM_OK;
+    if (cm_device_count() <= 0) return CM_ENODEVICE;
+    const bool backward = io->grad != nullptr;
+    const size_t per_step = ws_floats_per_step(d.n_agents, d.n_layers, backward);
+    if (io->workspace_floats < per_step + kWsSlack) return CM_EINVAL;
+    const int64_t chunk = (int64_t)((io->workspace_floats - kWsSlack) / per_step);
+    float *wsp = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(io->workspace) + 15) & ~(uintptr_t)15);
+    for (int64_t s0 = 0; s0 < io->n_steps; s0 += chunk) {
+        int64_t steps = io->n_steps - s0 < chunk ? io->n_steps - s0 : chunk;
+        const cudaError_t e = run_chunk(d, *io, s0, steps, wsp, (cudaStream_t)stream);
+        if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
+    }
+    return CM_OK;
+}

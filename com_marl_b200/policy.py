@@ -159,28 +159,31 @@ class CommCategoricalMLPPolicy(nn.Module):
             plist = self.__dict__["_plist"] = list(self.parameters())
         return tuple([(p.data_ptr(), p._version) for p in plist])
 
+    def _pack_blob(self, sd):
+        """state dict -> flat float32 blob in the layout of include/commarl_b200.h at the kernel's widths (128 / 64 / (128, 64,
+        32)); narrower layers are embedded in zeros (_pad2), 'dot' attention is W_a = identity.  Pure tensor plumbing: also
+        used with index tensors to derive the parameter <-> blob maps of the fused PPO update (ppo_fused._BlobMap)."""
+        L, E, D = self.n_gcn_layers, self._embedding_dim, self._dec_obs_dim
+        att = sd["attention_layer.linear_in.weight"].t() if "attention_layer.linear_in.weight" in sd \
+            else torch.eye(E, device=self.device)
+        parts = [_pad2(sd["encoder._layers.0.linear.weight"].t(), D, 128), _pad2(sd["encoder._layers.0.linear.bias"], 128, 0),
+                 _pad2(sd["encoder._output_layers.0.linear.weight"].t(), 128, 64), _pad2(sd["encoder._output_layers.0.linear.bias"], 64, 0),
+                 _pad2(att, 64, 64)]
+        parts += [_pad2(sd[f"gcn_layers.{l}.weight"], 64, 64) for l in range(L)]
+        parts += [_pad2(sd.get(f"gcn_layers.{l}.bias", torch.zeros(E, device=self.device)), 64, 0) for l in range(L)]
+        for i, (k_in, k_out) in enumerate(((64, 128), (128, 64), (64, 32))):
+            parts += [_pad2(sd[f"categorical_output_layer._layers.{i}.linear.weight"].t(), k_in, k_out),
+                      _pad2(sd[f"categorical_output_layer._layers.{i}.linear.bias"], k_out, 0)]
+        parts += [_pad2(sd["categorical_output_layer._output_layers.0.linear.weight"].t(), 32, self._action_dim),
+                  sd["categorical_output_layer._output_layers.0.linear.bias"]]
+        return torch.cat([p.detach().to(self.device, torch.float32).contiguous().reshape(-1) for p in parts])
+
     def weight_blob(self):
         """float32 device blob, every dense weight k-major; rebuilt when a parameter changed."""
         sig = self._signature()
         if self._blob is None or sig != self._blob_sig:
-            sd = self.state_dict()
-            L, E, D = self.n_gcn_layers, self._embedding_dim, self._dec_obs_dim
-            # blob layout of include/commarl_b200.h at the kernel's widths (128 / 64 / (128, 64, 32)); narrower layers are
-            # embedded in zeros (_pad2), 'dot' attention is W_a = identity
-            att = sd["attention_layer.linear_in.weight"].t() if "attention_layer.linear_in.weight" in sd \
-                else torch.eye(E, device=self.device)
-            parts = [_pad2(sd["encoder._layers.0.linear.weight"].t(), D, 128), _pad2(sd["encoder._layers.0.linear.bias"], 128, 0),
-                     _pad2(sd["encoder._output_layers.0.linear.weight"].t(), 128, 64), _pad2(sd["encoder._output_layers.0.linear.bias"], 64, 0),
-                     _pad2(att, 64, 64)]
-            parts += [_pad2(sd[f"gcn_layers.{l}.weight"], 64, 64) for l in range(L)]
-            parts += [_pad2(sd.get(f"gcn_layers.{l}.bias", torch.zeros(E, device=self.device)), 64, 0) for l in range(L)]
-            for i, (k_in, k_out) in enumerate(((64, 128), (128, 64), (64, 32))):
-                parts += [_pad2(sd[f"categorical_output_layer._layers.{i}.linear.weight"].t(), k_in, k_out),
-                          _pad2(sd[f"categorical_output_layer._layers.{i}.linear.bias"], k_out, 0)]
-            parts += [_pad2(sd["categorical_output_layer._output_layers.0.linear.weight"].t(), 32, self._action_dim),
-                      sd["categorical_output_layer._output_layers.0.linear.bias"]]
-            blob = torch.cat([p.detach().to(self.device, torch.float32).contiguous().reshape(-1) for p in parts])
-            expect = N.lib().cm_policy_blob_floats(self._dec_obs_dim, L)
+            blob = self._pack_blob(self.state_dict())
+            expect = N.lib().cm_policy_blob_floats(self._dec_obs_dim, self.n_gcn_layers)
             assert blob.numel() == expect, (blob.numel(), expect)
             self._blob = _refresh_in_place(self._blob, blob)
             self._blob_sig = sig

@@ -23,7 +23,7 @@ import torch.distributed as dist
 from torch import nn
 
 from . import _native as N
-from .policy import _Attention, _GraphConv, _MLP
+from .policy import _Attention, _GraphConv, _MLP, _pad2
 
 
 class _GaussianHead(nn.Module):
@@ -57,7 +57,28 @@ class CommBaseCritic(nn.Module):
         self.attention_layer = _Attention(embedding_dim, attention_type)
         self.gcn_layers = nn.ModuleList([_GraphConv(embedding_dim, gcn_bias) for _ in range(int(n_gcn_layers))])
         self.baseline_aggregator = _GaussianHead(embedding_dim, tuple(decoder_hidden_sizes))
+        self._embedding_dim = int(embedding_dim)
+        enc, dec = tuple(encoder_hidden_sizes), tuple(decoder_hidden_sizes)
+        # shapes the hand-written update kernels hold (narrower layers run exactly, zero-padded)
+        self._fusable = len(enc) == 1 and enc[0] <= 128 and embedding_dim <= 64 and len(dec) == 1 and dec[0] <= 64
         self.to(self.device)
+
+    def _pack_blob(self, sd):
+        """state dict -> the critic blob of cm_ppo_net (include/commarl_b200.h): the trunk like the policy blob, then
+        dec_w1 [64][64] dec_b1 [64] dec_w2 [64] dec_b2 [1] log_std [1]"""
+        E, dev = self._embedding_dim, self.device
+        att = sd["attention_layer.linear_in.weight"].t() if "attention_layer.linear_in.weight" in sd else torch.eye(E, device=dev)
+        parts = [_pad2(sd["encoder._layers.0.linear.weight"].t(), self._dec_obs_dim, 128), _pad2(sd["encoder._layers.0.linear.bias"], 128, 0),
+                 _pad2(sd["encoder._output_layers.0.linear.weight"].t(), 128, 64), _pad2(sd["encoder._output_layers.0.linear.bias"], 64, 0),
+                 _pad2(att, 64, 64)]
+        L = len(self.gcn_layers)
+        parts += [_pad2(sd[f"gcn_layers.{l}.weight"], 64, 64) for l in range(L)]
+        parts += [_pad2(sd.get(f"gcn_layers.{l}.bias", torch.zeros(E, device=dev)), 64, 0) for l in range(L)]
+        m = "baseline_aggregator._mean_module."
+        parts += [_pad2(sd[m + "_layers.0.linear.weight"].t(), 64, 64), _pad2(sd[m + "_layers.0.linear.bias"], 64, 0),
+                  _pad2(sd[m + "_output_layers.0.linear.weight"].t(), 64, 1), sd[m + "_output_layers.0.linear.bias"],
+                  sd["baseline_aggregator._init_std"]]
+        return torch.cat([p.detach().to(dev, torch.float32).contiguous().reshape(-1) for p in parts])
 
     def _values(self, obs_n, dist_adj, channels):
         n = self._n_agents
@@ -229,7 +250,7 @@ class DevicePPO:
 
     def __init__(self, policy, baseline, discount=0.99, gae_lambda=0.97, center_adv=True, positive_adv=False,
                  policy_ent_coeff=0.1, entropy_method="regularized", clip_grad_norm=7, optimization_n_minibatches=3,
-                 optimization_mini_epochs=10, policy_lr=3e-4, adam_eps=1e-5, process_group=None):
+                 optimization_mini_epochs=10, policy_lr=3e-4, adam_eps=1e-5, process_group=None, fused="auto"):
         if entropy_method not in ("regularized", "no_entropy"):
             raise NotImplementedError("entropy_method 'max' (entropy added to the rewards) is not implemented")
         if entropy_method == "no_entropy" and policy_ent_coeff != 0.0:
@@ -247,6 +268,14 @@ class DevicePPO:
         self.group = process_group
         self.opt = FlatAdam(policy, lr=policy_lr, eps=adam_eps)
         self.baseline_opt = FlatAdam(baseline, lr=policy_lr, eps=adam_eps)
+        # fused = hand-written forward / backward kernels (cm_ppo_net) instead of torch autograd: the Comm-DP family
+        # (CommCategoricalMLPPolicy + CommBaseCritic); 'auto' = wherever they apply
+        from .ppo_fused import FusedCommNets
+        can = FusedCommNets.supports(policy, baseline) and getattr(baseline, "_fusable", False) and self.device.type == "cuda"
+        if fused is True and not can:
+            raise NotImplementedError("fused=True needs a CommCategoricalMLPPolicy with a CommBaseCritic of the kernel's shapes on a GPU")
+        self._fused = FusedCommNets(policy, baseline, self.opt, self.baseline_opt, self.ent_coeff, self.lr_clip_range) \
+            if (can and fused in (True, "auto")) else None
 
     # ---- process_samples ----------------------------------------------------------------------------------------
     def process_samples(self, paths):
@@ -309,20 +338,30 @@ class DevicePPO:
             return y.reshape((P, Tmax) + x.shape[2:])
 
         L = traj["chan_bits"].shape[2]
-        adj = _unpack_mask(traj["adj_bits"][:K].reshape(K * B, n, -1).index_select(0, g), n)
-        chan = _unpack_mask(traj["chan_bits"][:K].reshape(K * B, L, n, -1).index_select(0, g), n)
-        adj[pad] = 1.0
-        chan[pad] = 1.0
+        adj_bits = traj["adj_bits"][:K].reshape(K * B, n, -1).index_select(0, g)
+        chan_bits = traj["chan_bits"][:K].reshape(K * B, L, n, -1).index_select(0, g)
         b = dict(obs=take(traj["obs"], 0.0).reshape(P, Tmax, -1), actions=take(traj["actions"], 0).to(torch.int64),
                  rewards=take(traj["reward"], 0.0), valids=valids.to(torch.int32),
-                 dist_adjs=adj.reshape(P, Tmax, n * n), channels=chan.reshape(P, Tmax, L * n, n),
                  avail=torch.ones((P, Tmax, n * 5), dtype=torch.float32, device=dev))
+        if self._fused is not None:          # the update kernels read the bit rows: no dense (P, T, n, n) masks at all
+            adj_bits[pad] = -1
+            chan_bits[pad] = -1
+            b["adj_bits"], b["chan_bits"] = adj_bits.reshape(P, Tmax, n, -1), chan_bits.reshape(P, Tmax, L, n, -1)
+        else:
+            adj, chan = _unpack_mask(adj_bits, n), _unpack_mask(chan_bits, n)
+            adj[pad] = 1.0
+            chan[pad] = 1.0
+            b["dist_adjs"], b["channels"] = adj.reshape(P, Tmax, n * n), chan.reshape(P, Tmax, L * n, n)
         return self.finish_batch(b)
 
     def finish_batch(self, b):
         """baselines (critic, no grad), returns and advantages for a padded device batch with the keys of process_samples"""
         with torch.no_grad():
-            if self._critic_comm:
+            if self._fused is not None:
+                self._fused.cri_map.refresh()
+                b["_flat"] = self._fused.prepare(b)
+                b["baselines"] = self._fused.critic_call(b["_flat"])["values"].reshape(b["rewards"].shape)
+            elif self._critic_comm:
                 b["baselines"] = self.baseline.forward(b["obs"], b["avail"], b["dist_adjs"], b["channels"]).float()
             else:
                 b["baselines"] = self.baseline.forward(b["obs"]).float()
@@ -365,6 +404,8 @@ class DevicePPO:
         """One policy-optimisation round.  ``paths`` (sampler output) or an already padded device ``batch``.
         ``shuffled_ids``: the path permutation (np.random.permutation in the reference)."""
         b = self.process_samples(paths) if batch is None else batch
+        if self._fused is not None:
+            return self._train_once_fused(b, shuffled_ids)
         P = b["rewards"].shape[0]
         with torch.no_grad():
             d0 = self._dist(b, None)
@@ -410,3 +451,63 @@ class DevicePPO:
             entropy = float(d1.entropy().mean(-1).mean())
         return dict(loss_before=loss_before, loss_after=loss_after, kl=kl, entropy=entropy, losses=losses,
                     baseline_losses=bl_losses, grad_norms=gnorms, n_paths=P)
+
+    def _train_once_fused(self, b, shuffled_ids=None):
+        """train_once on the hand-written kernels (ppo_fused.FusedCommNets): the same loop, losses, clipping, all-reduces and
+        Adam steps; every network forward / backward is ONE cm_ppo_net call."""
+        F = self._fused
+        f = b.get("_flat") or F.prepare(b)
+        P, T = b["rewards"].shape
+        raw_adv, ret_all = b["adv"].reshape(-1), b["returns"].reshape(-1)
+        adv_all = raw_adv - raw_adv.min() if self.positive_adv else raw_adv
+        n_valid_all = max(int(f["valids_host"].sum()), 1)
+        with torch.no_grad():
+            F.pol_map.refresh()
+            F.cri_map.refresh()
+            old = F.policy_call(f, None, want_probs=True)
+            old_ll, old_probs = old["ll"], old["probs"]
+            loss_before = F.policy_call(f, None, adv=adv_all, old_ll=old_ll, inv_count=1.0 / n_valid_all)["loss"]
+            ids_all = np.random.permutation(P) if shuffled_ids is None else np.asarray(shuffled_ids)
+            plan = minibatch_plan(P, self.n_minibatches, self.device, self.group)
+            losses, bl_losses, gnorms = [], [], []
+            nan = torch.full((1,), float("nan"), device=self.device)
+            for _ in range(self.mini_epochs):
+                for start, stop in plan:
+                    self.baseline_opt.zero_grad()
+                    self.opt.zero_grad()
+                    w_pol = w_bl = 0.0
+                    loss = bl = nan
+                    if stop > start:
+                        ids = ids_all[start:stop]
+                        idx_all = F.step_index(f, ids, valid_only=False)
+                        bl = F.critic_call(f, idx_all, returns=ret_all.index_select(0, idx_all), backward=True)["loss"]
+                        F.cri_map.scatter_grad(self.baseline_opt.grad)
+                        idx = F.step_index(f, ids, valid_only=True)
+                        adv = raw_adv.index_select(0, idx)
+                        if self.positive_adv:         # shifted by the minimum over the minibatch's padded rows (centralized_ma_ppo.py:428-429)
+                            adv = adv - raw_adv.index_select(0, idx_all).min()
+                        loss = F.policy_call(f, idx, adv=adv, old_ll=old_ll.index_select(0, idx), backward=True,
+                                             inv_count=1.0 / max(idx.numel(), 1))["loss"]
+                        F.pol_map.scatter_grad(self.opt.grad)
+                        w_pol, w_bl = float(idx.numel()), float((stop - start) * T)
+                    self.opt.all_reduce(self.group, w_pol)
+                    self.baseline_opt.all_reduce(self.group, w_bl)
+                    scale = 1.0
+                    if self.clip_grad_norm is not None:
+                        coef, norm = self.opt.clip_coefficient(self.clip_grad_norm)
+                        scale = float(coef)
+                        gnorms.append(norm * coef)
+                    self.opt.step(scale)
+                    self.baseline_opt.step(1.0)
+                    F.pol_map.refresh()
+                    F.cri_map.refresh()
+                    losses.append(loss)
+                    bl_losses.append(bl)
+            after = F.policy_call(f, None, adv=adv_all, old_ll=old_ll, want_probs=True, inv_count=1.0 / n_valid_all)
+            new = after["probs"]
+            t = old_probs * (old_probs.clamp_min(1e-38).log() - new.clamp_min(1e-38).log())
+            kl = float(torch.where(old_probs > 0, t, torch.zeros_like(t)).sum(-1).mean())
+            entropy = float(after["entropy"].mean())
+        tolist = lambda xs: [float(x) for x in torch.cat([x.reshape(1) for x in xs]).cpu()] if xs else []  # noqa: E731
+        return dict(loss_before=float(loss_before), loss_after=float(after["loss"]), kl=kl, entropy=entropy, losses=tolist(losses),
+                    baseline_losses=tolist(bl_losses), grad_norms=tolist(gnorms), n_paths=P)

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define CM_ABI_VERSION 2   /* 2: host_arena / obs_bits members, cm_rollout_step_host */
+#define CM_ABI_VERSION 3   /* 2: host_arena / obs_bits members, cm_rollout_step_host; 3: cm_ppo_net */
 #define CM_MAX_AGENTS 256   /* n, p */
 #define CM_MAX_GRID 64      /* grid side incl. Coverage's wall border */
 #define CM_MAX_LAYERS 4     /* n_gcn_layers */
@@ -301,6 +301,55 @@ int cm_ppo_advantages(const double *rewards, const float *baselines, const int32
                       cm_stream_t stream);
 int cm_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
                  float beta2, float eps, int32_t step, float grad_scale, cm_stream_t stream);
+
+/* ---- PPO update: hand-written forward + backward of the comm-GNN (csrc/ppo_net_kernels.cu) -----------------------------
+ * cm_ppo_net runs ONE network over n_steps env steps of n agents each — the flattened (path, t) pairs of a minibatch of
+ * CentralizedMAPPO.train_once (centralized_ma_ppo.py:207-262):
+ *   kind = CM_NET_POLICY  CommCategoricalMLPPolicy.forward(get_actions=False) (comm_categorical_mlp_policy.py:48-96) followed by
+ *                         _compute_loss / _compute_objective (centralized_ma_ppo.py:390-438, 540-589): joint log-likelihood of
+ *                         the taken actions, mean entropy over the agents, ratio = exp(ll - old_ll), clipped surrogate
+ *                         min(ratio adv, clip(ratio, clip_lo, clip_hi) adv) + ent_coeff entropy;  loss = -sum over the valid steps
+ *                         * inv_count.  Weights / gradient in the layout of the rollout blob (cm_policy_blob_floats).
+ *   kind = CM_NET_CRITIC  CommBaseCritic.compute_loss (comm_base_critic.py:11-120): the same trunk, decoder 64 -> 64 (tanh) -> 1,
+ *                         V(s) = sum over agents, loss = mean Gaussian negative log-likelihood of `returns` with the learnt
+ *                         log-std (clamped at log 1e-6).  Blob (cm_critic_blob_floats): enc_w1 [D][128] enc_b1 enc_w2 [128][64]
+ *                         enc_b2 att_w [64][64] gcn_w[l] [64][64] gcn_b[l] [64] dec_w1 [64][64] dec_b1 [64] dec_w2 [64] dec_b2 [1]
+ *                         log_std [1], dense weights K-major like the policy blob.
+ * grad == NULL: forward only (ll / entropy / probs / values / loss outputs).  grad != NULL: the parameter gradients of `loss`
+ * are ADDED to grad (same layout as weights; the caller zeroes it) — exact fp32 like the autograd graph they replace.
+ * Activations live in `workspace`; the steps are walked in chunks of as many steps as the workspace holds
+ * (cm_ppo_net_workspace_floats(desc, chunk_steps, backward) floats hold one chunk).  Stream-ordered, capturable. */
+typedef enum cm_net_kind { CM_NET_POLICY = 0, CM_NET_CRITIC = 1 } cm_net_kind;
+typedef struct cm_net_desc {
+    int32_t kind;              /* cm_net_kind */
+    int32_t n_agents, obs_dim, n_layers, residual;
+    float ent_coeff;           /* policy_ent_coeff ('regularized'), 0 otherwise */
+    float clip_lo, clip_hi;    /* 1 -/+ lr_clip_range (hard-coded 0.1 at centralized_ma_ppo.py:121) */
+} cm_net_desc;
+typedef struct cm_net_io {
+    int64_t n_steps;           /* S */
+    const float *weights;      /* fp32 blob */
+    float *grad;               /* or NULL */
+    const float *obs;          /* [S][n][D] */
+    const uint32_t *adj_bits;  /* [S][n][W] or NULL = all ones */
+    const uint32_t *chan_bits; /* [S][L][n][W] or NULL = all ones */
+    const uint8_t *avail_bits; /* policy: [S][n], bit a = action a available, or NULL */
+    const int64_t *actions;    /* policy: [S][n] */
+    const float *adv;          /* policy: [S] advantages; NULL = no objective (forward only) */
+    const float *old_ll;       /* policy: [S] log-likelihood under the frozen old policy; NULL = ratio 1 */
+    const uint8_t *valid;      /* policy: [S] 0 = padded step (no contribution), or NULL = all valid */
+    const float *returns;      /* critic: [S] */
+    float inv_count;           /* 1 / (number of steps the mean of the loss runs over) */
+    float *ll, *entropy;       /* policy outputs [S], optional */
+    float *probs;              /* policy output [S][n][5], optional */
+    float *values;             /* critic output [S], optional */
+    float *loss;               /* DEVICE f32[1], optional: the loss is ADDED to it */
+    float *workspace;
+    size_t workspace_floats;
+} cm_net_io;
+size_t cm_critic_blob_floats(int32_t obs_dim, int32_t n_layers);
+size_t cm_ppo_net_workspace_floats(const cm_net_desc *desc, int64_t chunk_steps, int32_t backward);
+int cm_ppo_net(const cm_net_desc *desc, const cm_net_io *io, cm_stream_t stream);
 
 /* dense float32 masks (the reference's dist_adj (B,n,n) / channels (B,L,n,n)) <-> bit rows */
 int cm_mask_pack(const float *dense, uint32_t *bits, int64_t rows, int32_t n, cm_stream_t stream);

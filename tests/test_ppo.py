@@ -45,7 +45,7 @@ def test_oracle_advantages_match_reference(name):
     assert np.abs(adv - c.z["adv"]).max() <= 2e-5 * max(1.0, np.abs(c.z["adv"]).max())
 
 
-def _build(c, device="cuda"):
+def _build(c, device="cuda", fused="auto"):
     import torch
     from com_marl_b200.policy import CentralizedCategoricalMLPPolicy, CommCategoricalMLPPolicy, DecCategoricalMLPPolicy
     from com_marl_b200.ppo import CommBaseCritic, DevicePPO, GaussianMLPBaseline
@@ -60,7 +60,7 @@ def _build(c, device="cuda"):
     cri.load_state_dict({k: torch.as_tensor(v) for k, v in c.sd["cri0"].items()})       # reference checkpoints load as is
     algo = DevicePPO(pol, cri, discount=m["discount"], gae_lambda=m["gae_lambda"], policy_ent_coeff=m["ent_coeff"],
                      clip_grad_norm=m["clip_grad_norm"], optimization_n_minibatches=int(m["n_minibatches"]),
-                     optimization_mini_epochs=int(m["mini_epochs"]), policy_lr=m["lr"], adam_eps=m["adam_eps"])
+                     optimization_mini_epochs=int(m["mini_epochs"]), policy_lr=m["lr"], adam_eps=m["adam_eps"], fused=fused)
     return pol, cri, algo
 
 
@@ -93,12 +93,17 @@ def test_process_samples_and_loss_match_reference(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("name", CASES)
-def test_train_once_matches_reference(name):
+def test_train_once_matches_reference(name, fused):
     """the whole optimisation loop (2 mini-epochs x 3 minibatches, clip_grad_norm, both Adam steps through cm_adam_step):
-    per-step losses, gradient norms and the final policy / critic weights equal the reference's"""
+    per-step losses, gradient norms and the final policy / critic weights equal the reference's — with the network forward /
+    backward on torch autograd (fused=False) and on the hand-written kernels (fused=True: cm_ppo_net, the Comm-DP family)"""
     c = PPOCase(name)
-    pol, cri, algo = _build(c)
+    if fused and c.meta.get("kind", "comm") != "comm":
+        pytest.skip("the hand-written update kernels cover the Comm-DP family (CommCategoricalMLPPolicy + CommBaseCritic)")
+    pol, cri, algo = _build(c, fused=fused)
+    assert (algo._fused is not None) == fused
     z = c.z
     out = algo.train_once(paths=c.paths, shuffled_ids=z["shuffled_ids"])
     assert abs(out["loss_before"] - float(z["loss_before"])) <= 2e-5
@@ -146,7 +151,7 @@ def test_device_trajectory_batch_equals_paths(scen, m, den, T):
     pol = make_policy(spec)
     n, D, L, B, K = spec.n_agents, spec.obs_dim, spec.n_layers, 37, 32
     cri = CommBaseCritic(EnvSpec(Box(np.zeros(n * D), np.ones(n * D)), Discrete(5)), n)
-    algo = DevicePPO(pol, cri, optimization_mini_epochs=2)
+    algo = DevicePPO(pol, cri, optimization_mini_epochs=2, fused=False)
     eng = RolloutEngine(spec, pol, B, ring=K, use_graph=False)
     eng.reset()
     eng.run_chunk()
@@ -170,8 +175,20 @@ def test_device_trajectory_batch_equals_paths(scen, m, den, T):
         assert torch.equal(b[k], ref[k]), k
     for k in ("baselines", "returns", "adv"):
         assert (b[k] - ref[k]).abs().max().item() <= 1e-5 * max(1.0, ref[k].abs().max().item()), k
-    out = algo.train_once(batch=b)
+    # the same trajectory through the hand-written update kernels (bit-row masks straight from the ring, no dense masks)
+    import copy
+    pol2, cri2 = copy.deepcopy(pol), copy.deepcopy(cri)
+    algo2 = DevicePPO(pol2, cri2, optimization_mini_epochs=2, fused=True)
+    b2 = algo2.batch_from_trajectory(eng.traj)
+    assert "dist_adjs" not in b2 and torch.equal(b2["obs"], b["obs"]) and torch.equal(b2["valids"], b["valids"])
+    for k in ("baselines", "returns", "adv"):
+        assert (b2[k] - b[k]).abs().max().item() <= 2e-5 * max(1.0, b[k].abs().max().item()), k
+    ids = np.random.RandomState(1).permutation(b["rewards"].shape[0])
+    out = algo.train_once(batch=b, shuffled_ids=ids)
     assert np.isfinite(out["loss_after"]) and out["loss_after"] < out["loss_before"] and out["kl"] >= 0
+    out2 = algo2.train_once(batch=b2, shuffled_ids=ids)
+    for k in ("loss_before", "loss_after", "kl"):
+        assert abs(out[k] - out2[k]) <= 1e-4 * max(1.0, abs(out[k])), k
 
 
 @pytest.mark.gpu
