@@ -27,8 +27,8 @@
 namespace cm {
 
 static constexpr int kNP = 68;          // pitch (floats) of a [row][64] array in shared memory: 128-bit reads of 8 consecutive rows hit 32 banks
-static constexpr int kRows = 256;       // rows (agents) of the envs a CTA of the per-env kernels owns at a time
-static constexpr int kNetThreads = 256;
+static constexpr int kRows = 256;       // most rows (agents) of the envs a CTA of the per-env kernels owns at a time
+static constexpr int kNetThreads = 256; // head kernels: one thread per row
 
 // ------------------------------------------------------------------------------------------------------------------
 // dense layers
@@ -119,41 +119,43 @@ __global__ void __launch_bounds__(256) net_dense_fwd_kernel(const float *__restr
 
 // One pass over the rows for the three gradients of Y = act(X W + b): dZ = dY (1 - Y^2) (DACT) or dY;
 // dX[r][k] (+)= sum_n dZ[r][n] W[k][n];  dW[k][n] += sum_r X[r][k] dZ[r][n];  db[n] += sum_r dZ[r][n].
-// dW / db are accumulated in registers over the tiles of a persistent CTA and added to global memory once.
+// 16 warps: warps 0-7 form the dX tile while warps 8-15 reduce dW / db over the same tile in shared memory (two independent
+// FMA streams on one copy of the operands); dW / db stay in registers over the tiles of a persistent CTA and are added to
+// global memory once.
 template <int N, int KMAX, int DACT>
-__global__ void __launch_bounds__(256) net_dense_bwd_kernel(const float *__restrict__ dY, int lddy, const float *__restrict__ Y, int ldy,
+__global__ void __launch_bounds__(512) net_dense_bwd_kernel(const float *__restrict__ dY, int lddy, const float *__restrict__ Y, int ldy,
                                                             const float *__restrict__ X, int ldx, const float *__restrict__ W,
                                                             float *__restrict__ dX, int lddx, int accumulate, float *__restrict__ dW,
                                                             float *__restrict__ db, int64_t R, int K)
 {
     constexpr int NP = N + 4, KP = KMAX + 4;
-    constexpr int KJ = KMAX / 16;                                          // phase A: k = kx + 16 j
-    constexpr int NX = N >= 64 ? 16 : N / 4, NJ = N / (4 * NX), KY = 256 / NX;   // phase B: n = 4 nx + 64 j, k = 4 ky + 4 KY i
+    constexpr int KJ = KMAX / 16;                                          // dX warps: k = kx + 16 j
+    constexpr int NX = N >= 64 ? 16 : N / 4, NJ = N / (4 * NX), KY = 256 / NX;   // dW warps: n = 4 nx + 64 j, k = 4 ky + 4 KY i
     constexpr int KI = (KMAX + 4 * KY - 1) / (4 * KY);
+    constexpr int NB = NJ * 4, NACC = (8 * KJ > KI * 4 * NB) ? 8 * KJ : KI * 4 * NB;
     extern __shared__ float4 smem4[];
     float *sm = reinterpret_cast<float *>(smem4);
     float *Ws = sm;                         // [KMAX][NP]
     float *dZs = Ws + KMAX * NP;            // [128][NP]
     float *Xs = dZs + 128 * NP;             // [128][KP]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < KMAX * N; i += 256) {
+    const bool role_w = tid >= 256;         // (warp-uniform)
+    const int t = tid & 255;
+    for (int i = tid; i < KMAX * N; i += 512) {
         const int k = i / N, n = i - k * N;
         Ws[k * NP + n] = k < K ? W[k * N + n] : 0.0f;
     }
-    float wacc[KI * 4][NJ * 4];
+    float acc[NACC];                        // dX warps: the tile's [8][KJ] block; dW warps: the running [KI * 4][NB] block
 #pragma unroll
-    for (int a = 0; a < KI * 4; ++a)
-#pragma unroll
-        for (int b = 0; b < NJ * 4; ++b) wacc[a][b] = 0.0f;
+    for (int a = 0; a < NACC; ++a) acc[a] = 0.0f;
     float bacc = 0.0f;
-    const int kx = tid & 15, ty = tid >> 4;
-    const int nx = tid % NX, ky = tid / NX;
+    const int kx = t & 15, ty = t >> 4;
+    const int nx = t % NX, ky = t / NX;
     const int64_t tiles = (R + 127) / 128;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int64_t r0 = t * 128;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t r0 = tile * 128;
         __syncthreads();
-        // dZ tile (coalesced rows of N floats) and X tile
-        for (int i = tid; i < 128 * (N / 4); i += 256) {
+        for (int i = tid; i < 128 * (N / 4); i += 512) {
             const int r = i / (N / 4), q = i - r * (N / 4);
             const int64_t gr = r0 + r;
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -166,90 +168,92 @@ __global__ void __launch_bounds__(256) net_dense_bwd_kernel(const float *__restr
             }
             *reinterpret_cast<float4 *>(dZs + r * NP + 4 * q) = g;
         }
-        for (int r = warp; r < 128; r += 8) {
+        for (int r = warp; r < 128; r += 16) {
             const int64_t gr = r0 + r;
             for (int k = lane; k < KMAX; k += 32) Xs[r * KP + k] = (gr < R && k < K) ? X[gr * ldx + k] : 0.0f;
         }
         __syncthreads();
-        if (dX) {                                            // ---- phase A: dX tile
-            float acc[8][KJ];
+        if (!role_w) {                                       // ---- dX tile
+            if (dX) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+                for (int a = 0; a < 8 * KJ; ++a) acc[a] = 0.0f;
+                for (int n4 = 0; n4 < N; n4 += 4) {
+                    float4 w[KJ];
 #pragma unroll
-                for (int j = 0; j < KJ; ++j) acc[i][j] = 0.0f;
-            for (int n4 = 0; n4 < N; n4 += 4) {
-                float4 w[KJ];
+                    for (int j = 0; j < KJ; ++j) w[j] = *reinterpret_cast<const float4 *>(Ws + (kx + 16 * j) * NP + n4);
 #pragma unroll
-                for (int j = 0; j < KJ; ++j) w[j] = *reinterpret_cast<const float4 *>(Ws + (kx + 16 * j) * NP + n4);
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 z = *reinterpret_cast<const float4 *>(dZs + (ty + 16 * i) * NP + n4);
+#pragma unroll
+                        for (int j = 0; j < KJ; ++j)
+                            acc[i * KJ + j] = fmaf(z.x, w[j].x, fmaf(z.y, w[j].y, fmaf(z.z, w[j].z, fmaf(z.w, w[j].w, acc[i * KJ + j]))));
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float4 z = *reinterpret_cast<const float4 *>(dZs + (ty + 16 * i) * NP + n4);
+                    const int64_t gr = r0 + ty + 16 * i;
+                    if (gr >= R) continue;
 #pragma unroll
-                    for (int j = 0; j < KJ; ++j)
-                        acc[i][j] = fmaf(z.x, w[j].x, fmaf(z.y, w[j].y, fmaf(z.z, w[j].z, fmaf(z.w, w[j].w, acc[i][j]))));
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int64_t gr = r0 + ty + 16 * i;
-                if (gr >= R) continue;
-#pragma unroll
-                for (int j = 0; j < KJ; ++j) {
-                    const int k = kx + 16 * j;
-                    if (k < K) {
-                        float *p = dX + gr * lddx + k;
-                        *p = accumulate ? *p + acc[i][j] : acc[i][j];
-                    }
-                }
-            }
-        }
-        // ---- phase B: dW += X^T dZ over the 128 rows of the tile
-        if (4 * ky < KMAX) {
-#pragma unroll 2
-            for (int r = 0; r < 128; ++r) {
-                float4 xa[KI], za[NJ];
-#pragma unroll
-                for (int i = 0; i < KI; ++i)
-                    xa[i] = (4 * ky + 4 * KY * i) < KMAX ? *reinterpret_cast<const float4 *>(Xs + r * KP + 4 * ky + 4 * KY * i)
-                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) za[j] = *reinterpret_cast<const float4 *>(dZs + r * NP + 4 * nx + 64 * j);
-#pragma unroll
-                for (int i = 0; i < KI; ++i)
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        const float xv[4] = {xa[i].x, xa[i].y, xa[i].z, xa[i].w};
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            wacc[4 * i + a][4 * j + 0] = fmaf(xv[a], za[j].x, wacc[4 * i + a][4 * j + 0]);
-                            wacc[4 * i + a][4 * j + 1] = fmaf(xv[a], za[j].y, wacc[4 * i + a][4 * j + 1]);
-                            wacc[4 * i + a][4 * j + 2] = fmaf(xv[a], za[j].z, wacc[4 * i + a][4 * j + 2]);
-                            wacc[4 * i + a][4 * j + 3] = fmaf(xv[a], za[j].w, wacc[4 * i + a][4 * j + 3]);
+                    for (int j = 0; j < KJ; ++j) {
+                        const int k = kx + 16 * j;
+                        if (k < K) {
+                            float *p = dX + gr * lddx + k;
+                            *p = accumulate ? *p + acc[i * KJ + j] : acc[i * KJ + j];
                         }
                     }
-            }
-        }
-        if (db && tid < N) {
-            float s = 0.0f;
-            for (int r = 0; r < 128; ++r) s += dZs[r * NP + tid];
-            bacc += s;
-        }
-    }
-    if (4 * ky < KMAX) {
-#pragma unroll
-        for (int i = 0; i < KI; ++i)
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const int k = 4 * ky + 4 * KY * i + a;
-                if (k < K) {
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) atomicAdd(dW + k * N + 4 * nx + 64 * j + b, wacc[4 * i + a][4 * j + b]);
                 }
             }
+        } else {                                             // ---- dW += X^T dZ, db += sum dZ over the 128 rows of the tile
+            if (4 * ky < KMAX) {
+#pragma unroll 2
+                for (int r = 0; r < 128; ++r) {
+                    float4 xa[KI], za[NJ];
+#pragma unroll
+                    for (int i = 0; i < KI; ++i)
+                        xa[i] = (4 * ky + 4 * KY * i) < KMAX ? *reinterpret_cast<const float4 *>(Xs + r * KP + 4 * ky + 4 * KY * i)
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) za[j] = *reinterpret_cast<const float4 *>(dZs + r * NP + 4 * nx + 64 * j);
+#pragma unroll
+                    for (int i = 0; i < KI; ++i)
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            const float xv[4] = {xa[i].x, xa[i].y, xa[i].z, xa[i].w};
+#pragma unroll
+                            for (int a = 0; a < 4; ++a) {
+                                float *o = acc + (4 * i + a) * NB + 4 * j;
+                                o[0] = fmaf(xv[a], za[j].x, o[0]);
+                                o[1] = fmaf(xv[a], za[j].y, o[1]);
+                                o[2] = fmaf(xv[a], za[j].z, o[2]);
+                                o[3] = fmaf(xv[a], za[j].w, o[3]);
+                            }
+                        }
+                }
+            }
+            if (db && t < N) {
+                float s = 0.0f;
+                for (int r = 0; r < 128; ++r) s += dZs[r * NP + t];
+                bacc += s;
+            }
+        }
     }
-    if (db && tid < N) atomicAdd(db + tid, bacc);
+    if (role_w) {
+        if (4 * ky < KMAX) {
+#pragma unroll
+            for (int i = 0; i < KI; ++i)
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int k = 4 * ky + 4 * KY * i + a;
+                    if (k < K) {
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) atomicAdd(dW + k * N + 4 * nx + 64 * j + b, acc[(4 * i + a) * NB + 4 * j + b]);
+                    }
+                }
+        }
+        if (db && t < N) atomicAdd(db + t, bacc);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -269,7 +273,7 @@ __device__ __forceinline__ void strip_dots(const float *As, int nr, const float 
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < KT; ++j) acc[i][j] = 0.0f;
-#pragma unroll 2
+#pragma unroll 1
     for (int c = 0; c < 64; c += 4) {
         float4 b[KT];
 #pragma unroll
@@ -305,7 +309,7 @@ __device__ __forceinline__ void strip_agg(const float *Cs, int CP, const float *
 // and the product form dZ = a (1 - b^2)
 __device__ __forceinline__ void load_rows64(float *dst, const float *__restrict__ src, int64_t row0, int rows, int tid)
 {
-    for (int i = tid; i < rows * 16; i += kNetThreads) {
+    for (int i = tid; i < rows * 16; i += blockDim.x) {
         const int r = i >> 4, q = i & 15;
         *reinterpret_cast<float4 *>(dst + r * kNP + 4 * q) = *reinterpret_cast<const float4 *>(src + (row0 + r) * 64 + 4 * q);
     }
@@ -327,12 +331,12 @@ __device__ __forceinline__ uint32_t mask_word(const uint32_t *__restrict__ bits,
 }
 
 // M[s][i][:] = softmax_k < Q[s][i], E[s][k] >
-template <int KT>
-__global__ void __launch_bounds__(kNetThreads) net_scores_kernel(const float *__restrict__ Q, const float *__restrict__ E,
-                                                                 float *__restrict__ M, int n, int G, int64_t S)
+template <int KT, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) net_scores_kernel(const float *__restrict__ Q, const float *__restrict__ E,
+                                                                 float *__restrict__ M, int n, int G, int cap, int64_t S)
 {
     extern __shared__ float4 smem4[];
-    float *Es = reinterpret_cast<float *>(smem4), *Qs = Es + kRows * kNP;
+    float *Es = reinterpret_cast<float *>(smem4), *Qs = Es + cap * kNP;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ns = (n + 7) >> 3;
     const int64_t nblk = (S + G - 1) / G;
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(kNetThreads) net_scores_kernel(const float *__
         load_rows64(Es, E, eb.s0 * n, eb.rows, tid);
         load_rows64(Qs, Q, eb.s0 * n, eb.rows, tid);
         __syncthreads();
-        for (int st = warp; st < eb.ne * ns; st += kNetThreads / 32) {
+        for (int st = warp; st < eb.ne * ns; st += THREADS / 32) {
             const int g = st / ns, j0 = (st - g * ns) * 8, nr = min(8, n - j0);
             float acc[8][KT];
             strip_dots<KT>(Qs + (g * n + j0) * kNP, nr, Es + g * n * kNP, n, lane, acc);
@@ -367,16 +371,16 @@ __global__ void __launch_bounds__(kNetThreads) net_scores_kernel(const float *__
 }
 
 // H[s][i][:] = tanh( sum_k A~[i][k] V[s][k][:] + b ),  A~ = M . adj . chan_l / (rowsum + 1e-12);  optional Xout = res + H
-template <int KT>
-__global__ void __launch_bounds__(kNetThreads) net_agg_fwd_kernel(const float *__restrict__ M, const uint32_t *__restrict__ adj,
+template <int KT, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) net_agg_fwd_kernel(const float *__restrict__ M, const uint32_t *__restrict__ adj,
                                                                   const uint32_t *__restrict__ chan, int L, int l,
                                                                   const float *__restrict__ V, const float *__restrict__ bias,
                                                                   float *__restrict__ H, const float *__restrict__ res,
-                                                                  float *__restrict__ Xout, int n, int G, int64_t S)
+                                                                  float *__restrict__ Xout, int n, int G, int cap, int64_t S)
 {
     extern __shared__ float4 smem4[];
     constexpr int CP = KT * 32 + 4;
-    float *Vs = reinterpret_cast<float *>(smem4), *Call = Vs + kRows * kNP;
+    float *Vs = reinterpret_cast<float *>(smem4), *Call = Vs + cap * kNP;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *Cs = Call + warp * 8 * CP;
     const int ns = (n + 7) >> 3, W = (n + 31) >> 5;
@@ -387,7 +391,7 @@ __global__ void __launch_bounds__(kNetThreads) net_agg_fwd_kernel(const float *_
         __syncthreads();
         load_rows64(Vs, V, eb.s0 * n, eb.rows, tid);
         __syncthreads();
-        for (int st = warp; st < eb.ne * ns; st += kNetThreads / 32) {
+        for (int st = warp; st < eb.ne * ns; st += THREADS / 32) {
             const int g = st / ns, j0 = (st - g * ns) * 8, nr = min(8, n - j0);
             const int64_t s = eb.s0 + g;
             __syncwarp();
@@ -428,17 +432,17 @@ __global__ void __launch_bounds__(kNetThreads) net_agg_fwd_kernel(const float *_
 // Backward of one graph-convolution layer's aggregation.  dZ = dH (1 - H^2);  dV = A~^T dZ;  db += sum dZ;
 // dA~ = dZ V^T;  dM (+)= mask (dA~ - <dA~, A~>) / (rowsum + 1e-12).  A~ strips are parked TRANSPOSED in CT so that the
 // second pass (key strips) reads contiguous coefficient rows.
-template <int KT>
-__global__ void __launch_bounds__(kNetThreads) net_agg_bwd_kernel(const float *__restrict__ M, const uint32_t *__restrict__ adj,
+template <int KT, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) net_agg_bwd_kernel(const float *__restrict__ M, const uint32_t *__restrict__ adj,
                                                                   const uint32_t *__restrict__ chan, int L, int l,
                                                                   const float *__restrict__ V, const float *__restrict__ H,
                                                                   const float *__restrict__ dH, float *__restrict__ dV,
                                                                   float *__restrict__ dM, int dm_accumulate, float *__restrict__ CT,
-                                                                  float *__restrict__ db, int n, int G, int64_t S)
+                                                                  float *__restrict__ db, int n, int G, int cap, int64_t S)
 {
     extern __shared__ float4 smem4[];
     constexpr int CP = KT * 32 + 4;
-    float *Vs = reinterpret_cast<float *>(smem4), *dZs = Vs + kRows * kNP, *Call = dZs + kRows * kNP;
+    float *Vs = reinterpret_cast<float *>(smem4), *dZs = Vs + cap * kNP, *Call = dZs + cap * kNP;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *Cs = Call + warp * 8 * CP;
     const int ns = (n + 7) >> 3, W = (n + 31) >> 5;
@@ -448,7 +452,7 @@ __global__ void __launch_bounds__(kNetThreads) net_agg_bwd_kernel(const float *_
         const EnvBlock eb = env_block(blk, G, n, S);
         __syncthreads();
         load_rows64(Vs, V, eb.s0 * n, eb.rows, tid);
-        for (int i = tid; i < eb.rows * 16; i += kNetThreads) {
+        for (int i = tid; i < eb.rows * 16; i += THREADS) {
             const int r = i >> 4, q = i & 15;
             const int64_t o = (eb.s0 * n + r) * 64 + 4 * q;
             float4 g = *reinterpret_cast<const float4 *>(dH + o);
@@ -462,7 +466,7 @@ __global__ void __launch_bounds__(kNetThreads) net_agg_bwd_kernel(const float *_
             for (int r = 0; r < eb.rows; ++r) sacc += dZs[r * kNP + tid];
             bacc += sacc;
         }
-        for (int st = warp; st < eb.ne * ns; st += kNetThreads / 32) {          // pass 1: query strips
+        for (int st = warp; st < eb.ne * ns; st += THREADS / 32) {          // pass 1: query strips
             const int g = st / ns, j0 = (st - g * ns) * 8, nr = min(8, n - j0);
             const int64_t s = eb.s0 + g;
             float acc[8][KT];
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(kNetThreads) net_agg_bwd_kernel(const float *_
             }
         }
         __syncthreads();
-        for (int st = warp; st < eb.ne * ns; st += kNetThreads / 32) {          // pass 2: key strips
+        for (int st = warp; st < eb.ne * ns; st += THREADS / 32) {          // pass 2: key strips
             const int g = st / ns, k0 = (st - g * ns) * 8, nk = min(8, n - k0);
             const int64_t s = eb.s0 + g;
             __syncwarp();
@@ -523,15 +527,15 @@ __global__ void __launch_bounds__(kNetThreads) net_agg_bwd_kernel(const float *_
 }
 
 // dS = M (dM - <dM, M>) per query row;  dQ = dS E;  dE += dS^T Q
-template <int KT>
-__global__ void __launch_bounds__(kNetThreads) net_softmax_bwd_kernel(const float *__restrict__ M, const float *__restrict__ dM,
+template <int KT, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) net_softmax_bwd_kernel(const float *__restrict__ M, const float *__restrict__ dM,
                                                                       const float *__restrict__ E, const float *__restrict__ Q,
                                                                       float *__restrict__ dQ, float *__restrict__ dE,
-                                                                      float *__restrict__ CT, int n, int G, int64_t S)
+                                                                      float *__restrict__ CT, int n, int G, int cap, int64_t S)
 {
     extern __shared__ float4 smem4[];
     constexpr int CP = KT * 32 + 4;
-    float *Es = reinterpret_cast<float *>(smem4), *Qs = Es + kRows * kNP, *Call = Qs + kRows * kNP;
+    float *Es = reinterpret_cast<float *>(smem4), *Qs = Es + cap * kNP, *Call = Qs + cap * kNP;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *Cs = Call + warp * 8 * CP;
     const int ns = (n + 7) >> 3;
@@ -542,7 +546,7 @@ __global__ void __launch_bounds__(kNetThreads) net_softmax_bwd_kernel(const floa
         load_rows64(Es, E, eb.s0 * n, eb.rows, tid);
         load_rows64(Qs, Q, eb.s0 * n, eb.rows, tid);
         __syncthreads();
-        for (int st = warp; st < eb.ne * ns; st += kNetThreads / 32) {          // pass 1: query strips
+        for (int st = warp; st < eb.ne * ns; st += THREADS / 32) {          // pass 1: query strips
             const int g = st / ns, j0 = (st - g * ns) * 8, nr = min(8, n - j0);
             const int64_t s = eb.s0 + g;
             __syncwarp();
@@ -575,7 +579,7 @@ __global__ void __launch_bounds__(kNetThreads) net_softmax_bwd_kernel(const floa
                 if (i < nr) *reinterpret_cast<float2 *>(dQ + (s * n + j0 + i) * 64 + 2 * lane) = make_float2(out[i][0], out[i][1]);
         }
         __syncthreads();
-        for (int st = warp; st < eb.ne * ns; st += kNetThreads / 32) {          // pass 2: key strips
+        for (int st = warp; st < eb.ne * ns; st += THREADS / 32) {          // pass 2: key strips
             const int g = st / ns, k0 = (st - g * ns) * 8, nk = min(8, n - k0);
             const int64_t s = eb.s0 + g;
             __syncwarp();
@@ -596,6 +600,253 @@ __global__ void __launch_bounds__(kNetThreads) net_softmax_bwd_kernel(const floa
                     const float2 o = *p;
                     *p = make_float2(o.x + out[i][0], o.y + out[i][1]);
                 }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// small teams (n <= 8): one THREAD per agent row.  A strip of 8 query rows would be mostly padding here (n = 3, 4 in
+// BASELINE configs 1 and 2); instead every thread keeps its row's 64 columns in registers and walks the <= 8 rows of its own
+// env in shared memory.  Same formulas, same outputs as the strip kernels above.
+// ------------------------------------------------------------------------------------------------------------------
+static constexpr int kSmallN = 8, kSmallRows = 128;
+
+__device__ __forceinline__ void row_load64(float (&v)[64], const float *__restrict__ src)
+{
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const float4 x = *reinterpret_cast<const float4 *>(src + 4 * q);
+        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+    }
+}
+// out[:] = sum_k coef[k] rows[k][:], k < n (rows in shared memory, pitch kNP)
+__device__ __forceinline__ void row_combine(float (&out)[64], const float (&coef)[kSmallN], const float *rows, int n)
+{
+#pragma unroll
+    for (int c = 0; c < 64; ++c) out[c] = 0.0f;
+    for (int k = 0; k < n; ++k) {
+        float ck = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kSmallN; ++j) if (j == k) ck = coef[j];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float4 b = *reinterpret_cast<const float4 *>(rows + k * kNP + 4 * q);
+            out[4 * q] = fmaf(ck, b.x, out[4 * q]); out[4 * q + 1] = fmaf(ck, b.y, out[4 * q + 1]);
+            out[4 * q + 2] = fmaf(ck, b.z, out[4 * q + 2]); out[4 * q + 3] = fmaf(ck, b.w, out[4 * q + 3]);
+        }
+    }
+}
+__device__ __forceinline__ float row_dot(const float (&v)[64], const float *row)
+{
+    float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 16; q += 2) {
+        const float4 a = *reinterpret_cast<const float4 *>(row + 4 * q), b = *reinterpret_cast<const float4 *>(row + 4 * q + 4);
+        s0 = fmaf(v[4 * q], a.x, fmaf(v[4 * q + 1], a.y, fmaf(v[4 * q + 2], a.z, fmaf(v[4 * q + 3], a.w, s0))));
+        s1 = fmaf(v[4 * q + 4], b.x, fmaf(v[4 * q + 5], b.y, fmaf(v[4 * q + 6], b.z, fmaf(v[4 * q + 7], b.w, s1))));
+    }
+    return s0 + s1;
+}
+__device__ __forceinline__ void row_store64(float *__restrict__ dst, const float (&v)[64])
+{
+#pragma unroll
+    for (int q = 0; q < 16; ++q) *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+// masked, renormalised attention row of agent `row` (global row index) in layer l: a[k], k < n; returns rowsum + 1e-12
+__device__ __forceinline__ float small_coef(float (&a)[kSmallN], const float *__restrict__ M, const uint32_t *__restrict__ adj,
+                                            const uint32_t *__restrict__ chan, int64_t row, int64_t chan_row, int n)
+{
+    const uint32_t wd = (adj ? adj[row] : 0xFFFFFFFFu) & (chan ? chan[chan_row] : 0xFFFFFFFFu);
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kSmallN; ++k) {
+        a[k] = (k < n && ((wd >> k) & 1u)) ? M[row * n + k] : 0.0f;
+        sum += a[k];
+    }
+    sum += 1e-12f;
+#pragma unroll
+    for (int k = 0; k < kSmallN; ++k) a[k] = a[k] / sum;
+    return sum;
+}
+
+__global__ void __launch_bounds__(kSmallRows) net_small_scores_kernel(const float *__restrict__ Q, const float *__restrict__ E,
+                                                                      float *__restrict__ M, int n, int G, int64_t S)
+{
+    __shared__ __align__(16) float Es[kSmallRows * kNP];
+    const int tid = threadIdx.x;
+    const int64_t nblk = (S + G - 1) / G;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const EnvBlock eb = env_block(blk, G, n, S);
+        __syncthreads();
+        load_rows64(Es, E, eb.s0 * n, eb.rows, tid);
+        __syncthreads();
+        if (tid >= eb.rows) continue;
+        const int e = tid / n;
+        const int64_t row = eb.s0 * n + tid;
+        float q[64];
+        row_load64(q, Q + row * 64);
+        float sc[kSmallN];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < kSmallN; ++k) {
+            sc[k] = k < n ? row_dot(q, Es + (e * n + k) * kNP) : -INFINITY;
+            mx = fmaxf(mx, sc[k]);
+        }
+        float sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kSmallN; ++k) { sc[k] = k < n ? expf(sc[k] - mx) : 0.0f; sum += sc[k]; }
+#pragma unroll
+        for (int k = 0; k < kSmallN; ++k) if (k < n) M[row * n + k] = sc[k] / sum;
+    }
+}
+
+__global__ void __launch_bounds__(kSmallRows) net_small_agg_fwd_kernel(const float *__restrict__ M, const uint32_t *__restrict__ adj,
+                                                                       const uint32_t *__restrict__ chan, int L, int l,
+                                                                       const float *__restrict__ V, const float *__restrict__ bias,
+                                                                       float *__restrict__ H, const float *__restrict__ res,
+                                                                       float *__restrict__ Xout, int n, int G, int64_t S)
+{
+    __shared__ __align__(16) float Vs[kSmallRows * kNP];
+    __shared__ float bs[64];
+    const int tid = threadIdx.x;
+    if (tid < 64) bs[tid] = bias[tid];
+    const int64_t nblk = (S + G - 1) / G;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const EnvBlock eb = env_block(blk, G, n, S);
+        __syncthreads();
+        load_rows64(Vs, V, eb.s0 * n, eb.rows, tid);
+        __syncthreads();
+        if (tid >= eb.rows) continue;
+        const int e = tid / n, i = tid - e * n;
+        const int64_t s = eb.s0 + e, row = s * n + i;
+        float a[kSmallN], out[64];
+        small_coef(a, M, adj, chan, row, (s * L + l) * n + i, n);
+        row_combine(out, a, Vs + e * n * kNP, n);
+#pragma unroll
+        for (int c = 0; c < 64; ++c) out[c] = tanhf(out[c] + bs[c]);
+        row_store64(H + row * 64, out);
+        if (Xout) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const float4 x = *reinterpret_cast<const float4 *>(res + row * 64 + 4 * q);
+                *reinterpret_cast<float4 *>(Xout + row * 64 + 4 * q) =
+                    make_float4(x.x + out[4 * q], x.y + out[4 * q + 1], x.z + out[4 * q + 2], x.w + out[4 * q + 3]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSmallRows) net_small_agg_bwd_kernel(const float *__restrict__ M, const uint32_t *__restrict__ adj,
+                                                                       const uint32_t *__restrict__ chan, int L, int l,
+                                                                       const float *__restrict__ V, const float *__restrict__ H,
+                                                                       const float *__restrict__ dH, float *__restrict__ dV,
+                                                                       float *__restrict__ dM, int dm_accumulate, float *__restrict__ db,
+                                                                       int n, int G, int64_t S)
+{
+    extern __shared__ float4 smem4[];
+    float *Vs = reinterpret_cast<float *>(smem4), *dZs = Vs + kSmallRows * kNP, *As = dZs + kSmallRows * kNP;
+    const int tid = threadIdx.x;
+    float bacc = 0.0f;
+    const int64_t nblk = (S + G - 1) / G;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const EnvBlock eb = env_block(blk, G, n, S);
+        __syncthreads();
+        load_rows64(Vs, V, eb.s0 * n, eb.rows, tid);
+        __syncthreads();
+        const bool active = tid < eb.rows;
+        const int e = active ? tid / n : 0, i = active ? tid - e * n : 0;
+        const int64_t s = eb.s0 + e, row = s * n + i;
+        if (active) {
+            float dz[64];
+            {
+                float h[64];
+                row_load64(dz, dH + row * 64);
+                row_load64(h, H + row * 64);
+#pragma unroll
+                for (int c = 0; c < 64; ++c) dz[c] *= 1.0f - h[c] * h[c];
+            }
+            row_store64(dZs + tid * kNP, dz);
+            float a[kSmallN];
+            const float sum = small_coef(a, M, adj, chan, row, (s * L + l) * n + i, n);
+            float da[kSmallN];
+            float dot = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kSmallN; ++k) {
+                da[k] = k < n ? row_dot(dz, Vs + (e * n + k) * kNP) : 0.0f;
+                dot = fmaf(da[k], a[k], dot);
+                As[tid * kSmallN + k] = a[k];
+            }
+            const uint32_t wd = (adj ? adj[row] : 0xFFFFFFFFu) & (chan ? chan[(s * L + l) * n + i] : 0xFFFFFFFFu);
+#pragma unroll
+            for (int k = 0; k < kSmallN; ++k)
+                if (k < n) {
+                    const float dm = ((wd >> k) & 1u) ? (da[k] - dot) / sum : 0.0f;
+                    float *p = dM + row * n + k;
+                    *p = dm_accumulate ? *p + dm : dm;
+                }
+        }
+        __syncthreads();
+        if (tid < 64) {
+            float sacc = 0.0f;
+            for (int r = 0; r < eb.rows; ++r) sacc += dZs[r * kNP + tid];
+            bacc += sacc;
+        }
+        if (active) {                                   // dV of key row (e, i): sum over the env's query rows
+            float ct[kSmallN], out[64];
+#pragma unroll
+            for (int q = 0; q < kSmallN; ++q) ct[q] = q < n ? As[(e * n + q) * kSmallN + i] : 0.0f;
+            row_combine(out, ct, dZs + e * n * kNP, n);
+            row_store64(dV + row * 64, out);
+        }
+    }
+    if (db && tid < 64) atomicAdd(db + tid, bacc);
+}
+
+__global__ void __launch_bounds__(kSmallRows) net_small_softmax_bwd_kernel(const float *__restrict__ M, const float *__restrict__ dM,
+                                                                           const float *__restrict__ E, const float *__restrict__ Q,
+                                                                           float *__restrict__ dQ, float *__restrict__ dE, int n, int G,
+                                                                           int64_t S)
+{
+    extern __shared__ float4 smem4[];
+    float *Es = reinterpret_cast<float *>(smem4), *Qs = Es + kSmallRows * kNP, *Ds = Qs + kSmallRows * kNP;
+    const int tid = threadIdx.x;
+    const int64_t nblk = (S + G - 1) / G;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const EnvBlock eb = env_block(blk, G, n, S);
+        __syncthreads();
+        load_rows64(Es, E, eb.s0 * n, eb.rows, tid);
+        load_rows64(Qs, Q, eb.s0 * n, eb.rows, tid);
+        __syncthreads();
+        const bool active = tid < eb.rows;
+        const int e = active ? tid / n : 0, i = active ? tid - e * n : 0;
+        const int64_t row = (eb.s0 + e) * n + i;
+        if (active) {
+            float ds[kSmallN], m[kSmallN];
+            float dot = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kSmallN; ++k) {
+                m[k] = k < n ? M[row * n + k] : 0.0f;
+                ds[k] = k < n ? dM[row * n + k] : 0.0f;
+                dot = fmaf(m[k], ds[k], dot);
+            }
+#pragma unroll
+            for (int k = 0; k < kSmallN; ++k) { ds[k] = m[k] * (ds[k] - dot); Ds[tid * kSmallN + k] = ds[k]; }
+            float out[64];
+            row_combine(out, ds, Es + e * n * kNP, n);
+            row_store64(dQ + row * 64, out);
+        }
+        __syncthreads();
+        if (active) {
+            float ct[kSmallN], out[64];
+#pragma unroll
+            for (int q = 0; q < kSmallN; ++q) ct[q] = q < n ? Ds[(e * n + q) * kSmallN + i] : 0.0f;
+            row_combine(out, ct, Qs + e * n * kNP, n);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                float4 *p = reinterpret_cast<float4 *>(dE + row * 64 + 4 * q);
+                const float4 o = *p;
+                *p = make_float4(o.x + out[4 * q], o.y + out[4 * q + 1], o.z + out[4 * q + 2], o.w + out[4 * q + 3]);
+            }
         }
     }
 }
@@ -893,7 +1144,9 @@ static cudaError_t dense_fwd_t(const float *X, int ldx, const float *W, const fl
     const int K4 = (K + 3) & ~3;
     const size_t smem = ((size_t)K4 * N + 128 * (size_t)(K4 + 4)) * sizeof(float);
     NET_TRY(set_smem(net_dense_fwd_kernel<N, ACT>, smem));
-    const int per_sm = smem > 110 * 1024 ? 1 : (smem > 72 * 1024 ? 2 : 3);
+    int per_sm = 1;
+    NET_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, net_dense_fwd_kernel<N, ACT>, 256, smem));
+    if (per_sm < 1) per_sm = 1;
     const int64_t tiles = (R + 127) / 128;
     const int grid = (int)(tiles < (int64_t)sm_count() * per_sm ? tiles : (int64_t)sm_count() * per_sm);
     net_dense_fwd_kernel<N, ACT><<<grid, 256, smem, st>>>(X, ldx, W, b, Y, N, R, K);
@@ -914,10 +1167,12 @@ static cudaError_t dense_bwd_t(const float *dY, const float *Y, const float *X, 
 {
     const size_t smem = ((size_t)KMAX * (N + 4) + 128 * (size_t)(N + 4) + 128 * (size_t)(KMAX + 4)) * sizeof(float);
     NET_TRY(set_smem(net_dense_bwd_kernel<N, KMAX, DACT>, smem));
-    const int per_sm = smem > 110 * 1024 ? 1 : 2;
+    int per_sm = 1;
+    NET_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, net_dense_bwd_kernel<N, KMAX, DACT>, 512, smem));
+    if (per_sm < 1) per_sm = 1;
     const int64_t tiles = (R + 127) / 128;
     const int grid = (int)(tiles < (int64_t)sm_count() * per_sm ? tiles : (int64_t)sm_count() * per_sm);
-    net_dense_bwd_kernel<N, KMAX, DACT><<<grid, 256, smem, st>>>(dY, N, Y, N, X, ldx, W, dX, K, accumulate, dW, db, R, K);
+    net_dense_bwd_kernel<N, KMAX, DACT><<<grid, 512, smem, st>>>(dY, N, Y, N, X, ldx, W, dX, K, accumulate, dW, db, R, K);
     return cudaGetLastError();
 }
 
@@ -941,12 +1196,24 @@ static cudaError_t dense_bwd(const float *dY, const float *Y, const float *X, in
                 : dense_bwd_n<32, 0>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st);
 }
 
-static int env_group(int n) { return n >= kRows ? 1 : kRows / n; }
+static int env_group(int n) { return n >= kRows ? 1 : kRows / n; }          // head kernels: one thread per row, 256 rows per CTA
 static int env_grid(int n, int64_t S, int per_sm)
 {
     const int G = env_group(n);
     const int64_t nblk = (S + G - 1) / G;
     return (int)(nblk < (int64_t)sm_count() * per_sm ? nblk : (int64_t)sm_count() * per_sm);
+}
+
+// n x n kernels: a CTA owns G whole envs at a time, at most `cap` rows: 64 rows for small teams (many CTAs per SM hide the
+// latency of the short strips), 128 up to n = 64, one env beyond
+struct EnvGeom { int G, cap; };
+static EnvGeom env_geom(int n)
+{
+    EnvGeom g;
+    const int target = n <= 16 ? 64 : 128;
+    g.G = n >= target ? 1 : target / n;
+    g.cap = (g.G * n + 3) & ~3;
+    return g;
 }
 
 struct EnvCall {
@@ -956,41 +1223,78 @@ struct EnvCall {
     cudaStream_t st;
 };
 
+static const size_t kSmemMax = 227 * 1024;
+template <typename Kern>
+static cudaError_t env_launch_dims(Kern k, int threads, size_t smem, const EnvCall &c, int *grid)
+{
+    NET_TRY(set_smem(k, smem));
+    int per_sm = 1;
+    NET_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const EnvGeom g = env_geom(c.n);
+    const int64_t nblk = (c.S + g.G - 1) / g.G;
+    *grid = (int)(nblk < (int64_t)sm_count() * per_sm ? nblk : (int64_t)sm_count() * per_sm);
+    return cudaSuccess;
+}
+static size_t cs_floats(int KT, int threads) { return (size_t)(threads / 32) * 8 * (KT * 32 + 4); }
+
 template <int KT>
 static cudaError_t scores_t(const EnvCall &c, const float *Q, const float *E, float *M)
 {
-    const size_t smem = 2 * (size_t)kRows * kNP * sizeof(float);
-    NET_TRY(set_smem(net_scores_kernel<KT>, smem));
-    net_scores_kernel<KT><<<env_grid(c.n, c.S, 1), kNetThreads, smem, c.st>>>(Q, E, M, c.n, env_group(c.n), c.S);
+    const EnvGeom g = env_geom(c.n);
+    const size_t smem = 2 * (size_t)g.cap * kNP * sizeof(float);
+    int grid;
+    NET_TRY(env_launch_dims(net_scores_kernel<KT, 256>, 256, smem, c, &grid));
+    net_scores_kernel<KT, 256><<<grid, 256, smem, c.st>>>(Q, E, M, c.n, g.G, g.cap, c.S);
     return cudaGetLastError();
 }
 template <int KT>
 static cudaError_t agg_fwd_t(const EnvCall &c, int l, const float *M, const float *V, const float *bias, float *H, const float *res,
                              float *Xout)
 {
-    const size_t smem = ((size_t)kRows * kNP + 8 * 8 * (size_t)(KT * 32 + 4)) * sizeof(float);
-    NET_TRY(set_smem(net_agg_fwd_kernel<KT>, smem));
-    net_agg_fwd_kernel<KT><<<env_grid(c.n, c.S, smem > 110 * 1024 ? 1 : 2), kNetThreads, smem, c.st>>>(M, c.adj, c.chan, c.L, l, V, bias, H,
-                                                                                                    res, Xout, c.n, env_group(c.n), c.S);
+    const EnvGeom g = env_geom(c.n);
+    const size_t smem = ((size_t)g.cap * kNP + cs_floats(KT, 256)) * sizeof(float);
+    int grid;
+    NET_TRY(env_launch_dims(net_agg_fwd_kernel<KT, 256>, 256, smem, c, &grid));
+    net_agg_fwd_kernel<KT, 256><<<grid, 256, smem, c.st>>>(M, c.adj, c.chan, c.L, l, V, bias, H, res, Xout, c.n, g.G, g.cap, c.S);
     return cudaGetLastError();
 }
+// the two backward kernels hold two row blocks: large teams (one env per CTA, a CTA per SM) run them with 16 warps when the
+// coefficient strips of 16 warps still fit
 template <int KT>
 static cudaError_t agg_bwd_t(const EnvCall &c, int l, const float *M, const float *V, const float *H, const float *dH, float *dV,
                              float *dM, int dm_acc, float *CT, float *db)
 {
-    const size_t smem = (2 * (size_t)kRows * kNP + 8 * 8 * (size_t)(KT * 32 + 4)) * sizeof(float);
-    NET_TRY(set_smem(net_agg_bwd_kernel<KT>, smem));
-    net_agg_bwd_kernel<KT><<<env_grid(c.n, c.S, 1), kNetThreads, smem, c.st>>>(M, c.adj, c.chan, c.L, l, V, H, dH, dV, dM, dm_acc, CT, db,
-                                                                            c.n, env_group(c.n), c.S);
+    const EnvGeom g = env_geom(c.n);
+    const size_t rows = 2 * (size_t)g.cap * kNP;
+    const bool wide = c.n > 64 && (rows + cs_floats(KT, 512)) * sizeof(float) <= kSmemMax;
+    const size_t smem = (rows + cs_floats(KT, wide ? 512 : 256)) * sizeof(float);
+    int grid;
+    if (wide) {
+        NET_TRY(env_launch_dims(net_agg_bwd_kernel<KT, 512>, 512, smem, c, &grid));
+        net_agg_bwd_kernel<KT, 512><<<grid, 512, smem, c.st>>>(M, c.adj, c.chan, c.L, l, V, H, dH, dV, dM, dm_acc, CT, db, c.n, g.G, g.cap, c.S);
+    } else {
+        NET_TRY(env_launch_dims(net_agg_bwd_kernel<KT, 256>, 256, smem, c, &grid));
+        net_agg_bwd_kernel<KT, 256><<<grid, 256, smem, c.st>>>(M, c.adj, c.chan, c.L, l, V, H, dH, dV, dM, dm_acc, CT, db, c.n, g.G, g.cap, c.S);
+    }
     return cudaGetLastError();
 }
 template <int KT>
 static cudaError_t softmax_bwd_t(const EnvCall &c, const float *M, const float *dM, const float *E, const float *Q, float *dQ, float *dE,
                                  float *CT)
 {
-    const size_t smem = (2 * (size_t)kRows * kNP + 8 * 8 * (size_t)(KT * 32 + 4)) * sizeof(float);
-    NET_TRY(set_smem(net_softmax_bwd_kernel<KT>, smem));
-    net_softmax_bwd_kernel<KT><<<env_grid(c.n, c.S, 1), kNetThreads, smem, c.st>>>(M, dM, E, Q, dQ, dE, CT, c.n, env_group(c.n), c.S);
+    const EnvGeom g = env_geom(c.n);
+    const size_t rows = 2 * (size_t)g.cap * kNP;
+    const bool wide = c.n > 64 && (rows + cs_floats(KT, 512)) * sizeof(float) <= kSmemMax;
+    const size_t smem = (rows + cs_floats(KT, wide ? 512 : 256)) * sizeof(float);
+    int grid;
+    if (wide) {
+        NET_TRY(env_launch_dims(net_softmax_bwd_kernel<KT, 512>, 512, smem, c, &grid));
+        net_softmax_bwd_kernel<KT, 512><<<grid, 512, smem, c.st>>>(M, dM, E, Q, dQ, dE, CT, c.n, g.G, g.cap, c.S);
+    } else {
+        NET_TRY(env_launch_dims(net_softmax_bwd_kernel<KT, 256>, 256, smem, c, &grid));
+        net_softmax_bwd_kernel<KT, 256><<<grid, 256, smem, c.st>>>(M, dM, E, Q, dQ, dE, CT, c.n, g.G, g.cap, c.S);
+    }
     return cudaGetLastError();
 }
 
@@ -1004,13 +1308,52 @@ static cudaError_t softmax_bwd_t(const EnvCall &c, const float *M, const float *
         return fn<8>(__VA_ARGS__);                                        \
     } while (0)
 
-static cudaError_t scores(const EnvCall &c, const float *Q, const float *E, float *M) { KT_DISPATCH(scores_t, c, Q, E, M); }
+static const size_t kSmallBwdSmem = (2 * (size_t)kSmallRows * kNP + (size_t)kSmallRows * kSmallN) * sizeof(float);
+static int small_grid(const EnvCall &c, int per_sm)
+{
+    const int G = kSmallRows / c.n;
+    const int64_t nblk = (c.S + G - 1) / G;
+    return (int)(nblk < (int64_t)sm_count() * per_sm ? nblk : (int64_t)sm_count() * per_sm);
+}
+static cudaError_t scores(const EnvCall &c, const float *Q, const float *E, float *M)
+{
+    if (c.n <= kSmallN) {
+        net_small_scores_kernel<<<small_grid(c, 6), kSmallRows, 0, c.st>>>(Q, E, M, c.n, kSmallRows / c.n, c.S);
+        return cudaGetLastError();
+    }
+    KT_DISPATCH(scores_t, c, Q, E, M);
+}
 static cudaError_t agg_fwd(const EnvCall &c, int l, const float *M, const float *V, const float *bias, float *H, const float *res,
-                           float *Xout) { KT_DISPATCH(agg_fwd_t, c, l, M, V, bias, H, res, Xout); }
+                           float *Xout)
+{
+    if (c.n <= kSmallN) {
+        net_small_agg_fwd_kernel<<<small_grid(c, 6), kSmallRows, 0, c.st>>>(M, c.adj, c.chan, c.L, l, V, bias, H, res, Xout, c.n,
+                                                                             kSmallRows / c.n, c.S);
+        return cudaGetLastError();
+    }
+    KT_DISPATCH(agg_fwd_t, c, l, M, V, bias, H, res, Xout);
+}
 static cudaError_t agg_bwd(const EnvCall &c, int l, const float *M, const float *V, const float *H, const float *dH, float *dV, float *dM,
-                           int dm_acc, float *CT, float *db) { KT_DISPATCH(agg_bwd_t, c, l, M, V, H, dH, dV, dM, dm_acc, CT, db); }
+                           int dm_acc, float *CT, float *db)
+{
+    if (c.n <= kSmallN) {
+        NET_TRY(set_smem(net_small_agg_bwd_kernel, kSmallBwdSmem));
+        net_small_agg_bwd_kernel<<<small_grid(c, 3), kSmallRows, kSmallBwdSmem, c.st>>>(M, c.adj, c.chan, c.L, l, V, H, dH, dV, dM, dm_acc, db, c.n,
+                                                                             kSmallRows / c.n, c.S);
+        return cudaGetLastError();
+    }
+    KT_DISPATCH(agg_bwd_t, c, l, M, V, H, dH, dV, dM, dm_acc, CT, db);
+}
 static cudaError_t softmax_bwd(const EnvCall &c, const float *M, const float *dM, const float *E, const float *Q, float *dQ, float *dE,
-                               float *CT) { KT_DISPATCH(softmax_bwd_t, c, M, dM, E, Q, dQ, dE, CT); }
+                               float *CT)
+{
+    if (c.n <= kSmallN) {
+        NET_TRY(set_smem(net_small_softmax_bwd_kernel, kSmallBwdSmem));
+        net_small_softmax_bwd_kernel<<<small_grid(c, 3), kSmallRows, kSmallBwdSmem, c.st>>>(M, dM, E, Q, dQ, dE, c.n, kSmallRows / c.n, c.S);
+        return cudaGetLastError();
+    }
+    KT_DISPATCH(softmax_bwd_t, c, M, dM, E, Q, dQ, dE, CT);
+}
 
 // workspace of one chunk of `steps` env steps (floats)
 static constexpr size_t kWsSlack = 160;      // alignment of the base pointer and of each of the <= 30 carved arrays

@@ -61,7 +61,7 @@ class FusedCommNets:
     """policy + critic of the Comm-DP runners on cm_ppo_net.  ``chunk_rows``: agent rows of activations kept in the workspace
     at a time (the kernels walk a minibatch in chunks; gradients add up)."""
 
-    def __init__(self, policy, critic, opt, baseline_opt, ent_coeff, clip_range, chunk_rows=65536):
+    def __init__(self, policy, critic, opt, baseline_opt, ent_coeff, clip_range, chunk_rows=262144):
         self.policy, self.critic = policy, critic
         self.device = policy.device
         self.n, self.D, self.L = policy._n_agents, policy._dec_obs_dim, policy.n_gcn_layers

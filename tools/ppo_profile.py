@@ -15,13 +15,14 @@ def main():
     ap.add_argument("--config", default="c1")
     ap.add_argument("--envs", type=int, default=1024)
     ap.add_argument("--mini-epochs", type=int, default=2)
+    ap.add_argument("--fused", default="auto", choices=["auto", "0", "1"])
     args = ap.parse_args()
     import bench
     from com_marl_b200.scenario import ScenarioSpec
     from com_marl_b200.train import DeviceTrainer
     scen, params = bench.params_for(args.config)
     spec = ScenarioSpec.from_params(scen, params, seed=1)
-    tr = DeviceTrainer(spec, args.envs, optimization_mini_epochs=args.mini_epochs)
+    tr = DeviceTrainer(spec, args.envs, optimization_mini_epochs=args.mini_epochs, fused={"auto": "auto", "0": False, "1": True}[args.fused])
     tr.train_epoch()
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
