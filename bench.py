@@ -606,6 +606,8 @@ def measure_c5_ppo(cx, envs, rounds=2):
            "rollout_ms": o["rollout_ms"], "batch_ms": o["batch_ms"], "update_ms": o["update_ms"], "optimizer_steps_per_round": steps_opt,
            "allreduce_calls_per_round": (2 * steps_opt) if cx.world > 1 else 0, "n_paths_per_rank": o["n_paths"],
            "loss_before": o["loss_before"], "loss_after": o["loss_after"], "kl": o["kl"],
+           "update_path": ("hand-written forward + backward kernels (cm_ppo_net: exact fp32, csrc/ppo_net_kernels.cu) + cm_adam_step"
+                           if tr.algo._fused is not None else "torch autograd + cm_adam_step"),
            "weights_identical_on_all_ranks": bool(float(lo) == float(hi))}
     del tr
     torch.cuda.empty_cache()

@@ -1253,10 +1253,17 @@ static cudaError_t agg_fwd_t(const EnvCall &c, int l, const float *M, const floa
                              float *Xout)
 {
     const EnvGeom g = env_geom(c.n);
-    const size_t smem = ((size_t)g.cap * kNP + cs_floats(KT, 256)) * sizeof(float);
+    const size_t rows = (size_t)g.cap * kNP;
+    const bool wide = c.n > 64 && (rows + cs_floats(KT, 512)) * sizeof(float) <= kSmemMax;      // one env per CTA: 16 warps share it
+    const size_t smem = (rows + cs_floats(KT, wide ? 512 : 256)) * sizeof(float);
     int grid;
-    NET_TRY(env_launch_dims(net_agg_fwd_kernel<KT, 256>, 256, smem, c, &grid));
-    net_agg_fwd_kernel<KT, 256><<<grid, 256, smem, c.st>>>(M, c.adj, c.chan, c.L, l, V, bias, H, res, Xout, c.n, g.G, g.cap, c.S);
+    if (wide) {
+        NET_TRY(env_launch_dims(net_agg_fwd_kernel<KT, 512>, 512, smem, c, &grid));
+        net_agg_fwd_kernel<KT, 512><<<grid, 512, smem, c.st>>>(M, c.adj, c.chan, c.L, l, V, bias, H, res, Xout, c.n, g.G, g.cap, c.S);
+    } else {
+        NET_TRY(env_launch_dims(net_agg_fwd_kernel<KT, 256>, 256, smem, c, &grid));
+        net_agg_fwd_kernel<KT, 256><<<grid, 256, smem, c.st>>>(M, c.adj, c.chan, c.L, l, V, bias, H, res, Xout, c.n, g.G, g.cap, c.S);
+    }
     return cudaGetLastError();
 }
 // the two backward kernels hold two row blocks: large teams (one env per CTA, a CTA per SM) run them with 16 warps when the

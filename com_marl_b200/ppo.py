@@ -464,9 +464,10 @@ class DevicePPO:
         with torch.no_grad():
             F.pol_map.refresh()
             F.cri_map.refresh()
-            old = F.policy_call(f, None, want_probs=True)
-            old_ll, old_probs = old["ll"], old["probs"]
-            loss_before = F.policy_call(f, None, adv=adv_all, old_ll=old_ll, inv_count=1.0 / n_valid_all)["loss"]
+            # ONE forward of the frozen old policy (:204) gives old_ll, old_probs and LossBefore: against itself the ratio is 1
+            # (the kernel takes old_ll = NULL as "the new log-likelihood, detached"), the surrogate is the advantage
+            old = F.policy_call(f, None, adv=adv_all, want_probs=True, inv_count=1.0 / n_valid_all)
+            old_ll, old_probs, loss_before = old["ll"], old["probs"], old["loss"]
             ids_all = np.random.permutation(P) if shuffled_ids is None else np.asarray(shuffled_ids)
             plan = minibatch_plan(P, self.n_minibatches, self.device, self.group)
             losses, bl_losses, gnorms = [], [], []
