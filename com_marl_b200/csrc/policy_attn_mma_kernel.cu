@@ -31,9 +31,8 @@
 
 namespace cm {
 
-static constexpr int kMThreads = 256, kMWarps = 8;
 static constexpr int kEhPitch = 72;          // halves per key row of E hi / lo (144 B: 8 rows x 4 lanes hit 32 distinct banks)
-static constexpr int kQPitch = 72;           // floats per query row of a warp's slice
+static constexpr int kQhPitch = 72;          // halves per query row (hi / lo) of a warp's slice
 static constexpr int kWgPitch = 72;          // halves per output column of the transposed Wg
 
 struct AttnMmaArgs {
@@ -85,11 +84,147 @@ __device__ __forceinline__ float quad_sum(float v)
     return v + __shfl_xor_sync(0xFFFFFFFFu, v, 2);
 }
 
-// NS = number of 16-key slices (NK = 16 NS keys >= n)
-template <int NS>
-__global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const AttnMmaArgs A)
+// scores of one block of U <= 8 key tiles (8 U keys) starting at tile nt0: s[u] = Q E^T; three fp16 products per tile into
+// one fp32 accumulator, issued U tiles apart (an HMMA needs its accumulator back before the next one on it can start)
+template <int U>
+__device__ __forceinline__ void score_block(float (&s)[8][4], const __half *Qh, const __half *Ql, const __half *Eh, const __half *El,
+                                            int nt0, int g, int t)
 {
-    constexpr int NK = 16 * NS, NT = 2 * NS, HWP = NK + 8;     // keys, 8-key tiles, halves per row of the transposed values
+#pragma unroll
+    for (int u = 0; u < U; ++u) s[u][0] = s[u][1] = s[u][2] = s[u][3] = 0.0f;
+#pragma unroll 1
+    for (int ks = 0; ks < 4; ++ks) {                            // (rolled: the body alone is 3 U HMMAs; the kernel is I-cache bound otherwise)
+        const int k0 = 16 * ks + 2 * t;
+        uint32_t ah[4], al[4];
+        ah[0] = *reinterpret_cast<const uint32_t *>(Qh + g * kQhPitch + k0);
+        ah[1] = *reinterpret_cast<const uint32_t *>(Qh + (g + 8) * kQhPitch + k0);
+        ah[2] = *reinterpret_cast<const uint32_t *>(Qh + g * kQhPitch + k0 + 8);
+        ah[3] = *reinterpret_cast<const uint32_t *>(Qh + (g + 8) * kQhPitch + k0 + 8);
+        al[0] = *reinterpret_cast<const uint32_t *>(Ql + g * kQhPitch + k0);
+        al[1] = *reinterpret_cast<const uint32_t *>(Ql + (g + 8) * kQhPitch + k0);
+        al[2] = *reinterpret_cast<const uint32_t *>(Ql + g * kQhPitch + k0 + 8);
+        al[3] = *reinterpret_cast<const uint32_t *>(Ql + (g + 8) * kQhPitch + k0 + 8);
+        uint32_t bh[U][2], bl[U][2];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const __half *eh = Eh + (8 * (nt0 + u) + g) * kEhPitch + k0, *el = El + (8 * (nt0 + u) + g) * kEhPitch + k0;
+            bh[u][0] = *reinterpret_cast<const uint32_t *>(eh); bh[u][1] = *reinterpret_cast<const uint32_t *>(eh + 8);
+            bl[u][0] = *reinterpret_cast<const uint32_t *>(el); bl[u][1] = *reinterpret_cast<const uint32_t *>(el + 8);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) mma16816(s[u], ah, bh[u][0], bh[u][1]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) mma16816(s[u], ah, bl[u][0], bl[u][1]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) mma16816(s[u], al, bh[u][0], bh[u][1]);
+    }
+}
+
+struct StripState {               // rows g (index 0) and g + 8 (index 1) of the strip
+    float m0, m1;                 // running maximum of the scores
+    float z0, z1;                 // this lane's part of sum exp(s - m)
+    float d0, d1;                 // this lane's part of sum mask exp(s - m)
+};
+
+// one block of U key tiles of a strip: scores, running maximum + rescaling, exp, mask, aggregation into oacc
+template <int U>
+__device__ __forceinline__ void attn_block(StripState &st, float (&oacc)[8][4], const __half *Qh, const __half *Ql, const __half *Eh,
+                                           const __half *El, const __half *Vh, const __half *Vl, int HWP, const uint32_t *Mw, int nt0,
+                                           int n, int g, int t)
+{
+    float s[8][4];
+    score_block<U>(s, Qh, Ql, Eh, El, nt0, g, t);
+    float bm0 = -1e30f, bm1 = -1e30f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int key = 8 * (nt0 + u) + 2 * t;
+        if (key < n) { bm0 = fmaxf(bm0, s[u][0]); bm1 = fmaxf(bm1, s[u][2]); }
+        if (key + 1 < n) { bm0 = fmaxf(bm0, s[u][1]); bm1 = fmaxf(bm1, s[u][3]); }
+    }
+    const float mn0 = fmaxf(st.m0, quad_max(bm0)), mn1 = fmaxf(st.m1, quad_max(bm1));
+    const float sc0 = __expf(st.m0 - mn0), sc1 = __expf(st.m1 - mn1);
+    st.m0 = mn0; st.m1 = mn1;
+    st.z0 *= sc0; st.d0 *= sc0; st.z1 *= sc1; st.d1 *= sc1;
+#pragma unroll
+    for (int ot = 0; ot < 8; ++ot) { oacc[ot][0] *= sc0; oacc[ot][1] *= sc0; oacc[ot][2] *= sc1; oacc[ot][3] *= sc1; }
+    // exp, mask (comm_base_net.py:101): the masked, un-normalised rows stay in the accumulators
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int nt = nt0 + u, key = 8 * nt + 2 * t;
+        const float e00 = key < n ? __expf(s[u][0] - mn0) : 0.0f, e01 = key + 1 < n ? __expf(s[u][1] - mn0) : 0.0f;
+        const float e10 = key < n ? __expf(s[u][2] - mn1) : 0.0f, e11 = key + 1 < n ? __expf(s[u][3] - mn1) : 0.0f;
+        st.z0 += e00 + e01;
+        st.z1 += e10 + e11;
+        const uint32_t w0 = Mw[g * 8 + (nt >> 2)] >> (8 * (nt & 3) + 2 * t);
+        const uint32_t w1 = Mw[(g + 8) * 8 + (nt >> 2)] >> (8 * (nt & 3) + 2 * t);
+        s[u][0] = (w0 & 1u) ? e00 : 0.0f;
+        s[u][1] = (w0 & 2u) ? e01 : 0.0f;
+        s[u][2] = (w1 & 1u) ? e10 : 0.0f;
+        s[u][3] = (w1 & 2u) ? e11 : 0.0f;
+        st.d0 += s[u][0] + s[u][1];
+        st.d1 += s[u][2] + s[u][3];
+    }
+    // aggregation: out[16][64] += a (H_l Wg_l): the C fragments of tiles 2s, 2s+1 are the A fragment of key slice s
+#pragma unroll
+    for (int ss = 0; ss < U / 2; ++ss) {
+        uint32_t ah[4], al[4];
+        split2(s[2 * ss][0], s[2 * ss][1], ah[0], al[0]);
+        split2(s[2 * ss][2], s[2 * ss][3], ah[1], al[1]);
+        split2(s[2 * ss + 1][0], s[2 * ss + 1][1], ah[2], al[2]);
+        split2(s[2 * ss + 1][2], s[2 * ss + 1][3], ah[3], al[3]);
+        const int k0 = 8 * (nt0 + 2 * ss) + 2 * t;
+#pragma unroll
+        for (int o0 = 0; o0 < 8; o0 += 4) {
+            uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const __half *vh = Vh + (8 * (o0 + u) + g) * HWP + k0, *vl = Vl + (8 * (o0 + u) + g) * HWP + k0;
+                bh[u][0] = *reinterpret_cast<const uint32_t *>(vh); bh[u][1] = *reinterpret_cast<const uint32_t *>(vh + 8);
+                bl[u][0] = *reinterpret_cast<const uint32_t *>(vl); bl[u][1] = *reinterpret_cast<const uint32_t *>(vl + 8);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mma16816(oacc[o0 + u], ah, bh[u][0], bh[u][1]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mma16816(oacc[o0 + u], ah, bl[u][0], bl[u][1]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mma16816(oacc[o0 + u], al, bh[u][0], bh[u][1]);
+        }
+    }
+}
+
+// the UNMASKED softmax of one block of U key tiles with the final maximum and sum (agent_infos['attention_weights'])
+template <int U>
+__device__ __forceinline__ void attn_record_block(float *att0, float *att1, bool v0, bool v1, const StripState &st, float is0, float is1,
+                                                  const __half *Qh, const __half *Ql, const __half *Eh, const __half *El, int nt0, int n,
+                                                  int g, int t)
+{
+    float s[8][4];
+    score_block<U>(s, Qh, Ql, Eh, El, nt0, g, t);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int key = 8 * (nt0 + u) + 2 * t;
+        if (v0 && key < n) att0[key] = __expf(s[u][0] - st.m0) * is0;
+        if (v0 && key + 1 < n) att0[key + 1] = __expf(s[u][1] - st.m0) * is0;
+        if (v1 && key < n) att1[key] = __expf(s[u][2] - st.m1) * is1;
+        if (v1 && key + 1 < n) att1[key + 1] = __expf(s[u][3] - st.m1) * is1;
+    }
+}
+
+// NS = number of 16-key slices (NK = 16 NS keys >= n); WARPS = warps per CTA (16, or 8 where the operands of the largest
+// teams leave no room for 16 query slices).
+//
+// A strip's n keys are walked in BLOCKS of 64 (flash-attention style) so that a warp holds 8 score tiles at a time instead
+// of n / 8: 16 warps of <= 128 registers share an env instead of 8 warps of 248 — the strip is a dependent chain of HMMAs
+// and shuffles, and the number of chains in flight is what the tensor pipe's utilisation follows.  Running per row:
+// m (max), z = sum exp(s - m), d = sum mask exp(s - m), out = sum mask exp(s - m) V; a larger maximum rescales z, d and out.
+// The reference's softmax -> mask -> renormalise (comm_base_net.py:101-103) is then
+//   A~ V = out / (d + 1e-12 z)        (p = exp(s - m) / z;  A~ = p mask / (sum p mask + 1e-12))
+// exactly, in fp32.  The unmasked softmax itself (agent_infos['attention_weights']) is written, when asked for, by a second
+// walk over the blocks with the final m and z.
+template <int NS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) policy_attn_mma_kernel(const AttnMmaArgs A)
+{
+    constexpr int NK = 16 * NS, NT = 2 * NS, NFULL = NT / 8, TAIL = NT % 8, HWP = NK + 8, THREADS = WARPS * 32;   // key blocks of 8 tiles + a tail
     extern __shared__ __align__(16) unsigned char smraw[];
     __half *Eh = reinterpret_cast<__half *>(smraw);            // [NK][72]
     __half *El = Eh + NK * kEhPitch;
@@ -97,11 +232,11 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
     __half *Vl = Vh + 64 * HWP;
     __half *Wh = Vl + 64 * HWP;                                // [64][72]    Wg_{l+1}^T hi
     __half *Wl = Wh + 64 * kWgPitch;
-    float *Qs = reinterpret_cast<float *>(Wl + 64 * kWgPitch); // [8 warps][16][72] query rows
-    uint32_t *Ms = reinterpret_cast<uint32_t *>(Qs + kMWarps * 16 * kQPitch);   // [8 warps][16][8] mask words
+    __half *Qs = Wl + 64 * kWgPitch;                           // [WARPS][2][16][72] query rows hi / lo
+    uint32_t *Ms = reinterpret_cast<uint32_t *>(Qs + WARPS * 2 * 16 * kQhPitch);   // [WARPS][16][8] mask words
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    float *Qw = Qs + warp * 16 * kQPitch;
+    __half *Qh = Qs + warp * 2 * 16 * kQhPitch, *Ql = Qh + 16 * kQhPitch;
     uint32_t *Mw = Ms + warp * 16 * 8;
     const int n = A.d.n_agents, L = A.d.n_layers, W = (n + 31) >> 5;
     const Blob o = blob_layout(A.d.obs_dim, L);
@@ -113,8 +248,7 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
         // ---- keys: E rows -> fp16 hi / lo ----
         // (unconditional loads from a clamped row, zeroed afterwards: predicated loads are not batched by the compiler)
 #pragma unroll 4
-        for (int it = 0; it < NS; ++it) {
-            const int e = tid + it * kMThreads;
+        for (int e = tid; e < NK * 16; e += THREADS) {
             const int j = e >> 4, c = (e & 15) << 2;
             float4 v = __ldcg(reinterpret_cast<const float4 *>(A.scr_e + (r_env + min(j, n - 1)) * 64 + c));
             if (j >= n) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -128,8 +262,7 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
             if (l) __syncthreads();                            // every warp wrote its H_l Wg_l rows and is done with the old operands
             // ---- values: H_l Wg_l rows -> transposed fp16 hi / lo [col][key] ----
 #pragma unroll 4
-            for (int it = 0; it < NS; ++it) {
-                const int e = tid + it * kMThreads;
+            for (int e = tid; e < NK * 16; e += THREADS) {
                 const int j = e % NK, c = (e / NK) << 2;       // consecutive threads take consecutive keys: neighbouring halves
                 float4 v = __ldcg(reinterpret_cast<const float4 *>(A.scr_hw + (r_env + min(j, n - 1)) * 64 + c));
                 if (j >= n) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -145,8 +278,7 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
             if (l + 1 < L) {
                 const float *wg = A.weights + o.gcn_w + (size_t)(l + 1) * kE * kE;
 #pragma unroll 4
-                for (int it = 0; it < kE * kE / kMThreads; ++it) {
-                    const int e = tid + it * kMThreads;
+                for (int e = tid; e < kE * kE; e += THREADS) {
                     const int k = e >> 6, c = e & 63;
                     const float v = __ldg(wg + e);
                     const __half h = __float2half_rn(v);
@@ -156,152 +288,59 @@ __global__ void __launch_bounds__(kMThreads, 1) policy_attn_mma_kernel(const Att
             }
             __syncthreads();
             const float *bias = A.weights + o.gcn_b + l * kE;
-            for (int strip = warp; strip < n_strips; strip += kMWarps) {
+            for (int strip = warp; strip < n_strips; strip += WARPS) {
                 const int i0 = strip << 4;                     // first query row of the strip; this lane owns rows i0+g, i0+g+8
                 __syncwarp();
-                // ---- query rows and neighbour mask words -> the warp's slice ----
-                // (all 8 + 8 loads of the strip are issued before the first store: one L2 round trip per strip)
-                float4 qv[8];
-                uint32_t mv[4];
+                // ---- query rows (fp16 hi / lo) and neighbour mask words -> the warp's slice ----
+                // (all 8 + 4 loads of the strip are issued before the first store: one L2 round trip per strip)
+                {
+                    float4 qv[8];
+                    uint32_t mv[4];
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int e = lane + 32 * it, r = e >> 4, c = (e & 15) << 2;
-                    qv[it] = __ldcg(reinterpret_cast<const float4 *>(A.scr_q + (r_env + min(i0 + r, n - 1)) * 64 + c));
+                    for (int it = 0; it < 8; ++it) {
+                        const int e = lane + 32 * it, r = e >> 4, c = (e & 15) << 2;
+                        qv[it] = __ldcg(reinterpret_cast<const float4 *>(A.scr_q + (r_env + min(i0 + r, n - 1)) * 64 + c));
+                    }
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int e = lane + 32 * it, r = e >> 3, w = e & 7;
+                        const size_t row = r_env + min(i0 + r, n - 1);
+                        const int wc = min(w, W - 1);
+                        const uint32_t ma = A.adj_bits ? __ldg(A.adj_bits + row * W + wc) : 0xFFFFFFFFu;
+                        const uint32_t mc = A.chan_bits ? __ldg(A.chan_bits + (((size_t)env * L + l) * n + min(i0 + r, n - 1)) * W + wc) : 0xFFFFFFFFu;
+                        mv[it] = (i0 + r < n && w < W) ? (ma & mc) : 0u;
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int e = lane + 32 * it, r = e >> 4, c = (e & 15) << 2;
+                        if (i0 + r >= n) qv[it] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        uint32_t h0, l0, h1, l1;
+                        split2(qv[it].x, qv[it].y, h0, l0);
+                        split2(qv[it].z, qv[it].w, h1, l1);
+                        *reinterpret_cast<uint2 *>(Qh + r * kQhPitch + c) = make_uint2(h0, h1);
+                        *reinterpret_cast<uint2 *>(Ql + r * kQhPitch + c) = make_uint2(l0, l1);
+                    }
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) Mw[lane + 32 * it] = mv[it];
                 }
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int e = lane + 32 * it, r = e >> 3, w = e & 7;
-                    const size_t row = r_env + min(i0 + r, n - 1);
-                    const int wc = min(w, W - 1);
-                    const uint32_t ma = A.adj_bits ? __ldg(A.adj_bits + row * W + wc) : 0xFFFFFFFFu;
-                    const uint32_t mc = A.chan_bits ? __ldg(A.chan_bits + (((size_t)env * L + l) * n + min(i0 + r, n - 1)) * W + wc) : 0xFFFFFFFFu;
-                    mv[it] = (i0 + r < n && w < W) ? (ma & mc) : 0u;
-                }
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int e = lane + 32 * it, r = e >> 4;
-                    if (i0 + r >= n) qv[it] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                }
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int e = lane + 32 * it, r = e >> 4, c = (e & 15) << 2;
-                    *reinterpret_cast<float4 *>(Qw + r * kQPitch + c) = qv[it];
-                }
-#pragma unroll
-                for (int it = 0; it < 4; ++it) Mw[lane + 32 * it] = mv[it];
                 __syncwarp();
-                // ---- scores: S[16][NK] = Q E^T, three fp16 products per tile into one fp32 accumulator ----
-                float s[NT][4];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
-#pragma unroll 1
-                for (int ks = 0; ks < 4; ++ks) {                    // (rolled: the body alone is 3 NT HMMAs; the kernel is I-cache bound otherwise)
-                    const int k0 = 16 * ks + 2 * t;
-                    const float2 q00 = *reinterpret_cast<const float2 *>(Qw + g * kQPitch + k0);
-                    const float2 q10 = *reinterpret_cast<const float2 *>(Qw + (g + 8) * kQPitch + k0);
-                    const float2 q01 = *reinterpret_cast<const float2 *>(Qw + g * kQPitch + k0 + 8);
-                    const float2 q11 = *reinterpret_cast<const float2 *>(Qw + (g + 8) * kQPitch + k0 + 8);
-                    uint32_t ah[4], al[4];
-                    split2(q00.x, q00.y, ah[0], al[0]);
-                    split2(q10.x, q10.y, ah[1], al[1]);
-                    split2(q01.x, q01.y, ah[2], al[2]);
-                    split2(q11.x, q11.y, ah[3], al[3]);
-                    // four key tiles at a time: the three products of a tile go into ONE accumulator, so they are issued
-                    // four tiles apart (an HMMA needs its accumulator back before the next one on it can start)
-#pragma unroll
-                    for (int n0 = 0; n0 < NT; n0 += 4) {
-                        uint32_t bh[4][2], bl[4][2];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (n0 + u < NT) {
-                                const __half *eh = Eh + (8 * (n0 + u) + g) * kEhPitch + k0, *el = El + (8 * (n0 + u) + g) * kEhPitch + k0;
-                                bh[u][0] = *reinterpret_cast<const uint32_t *>(eh); bh[u][1] = *reinterpret_cast<const uint32_t *>(eh + 8);
-                                bl[u][0] = *reinterpret_cast<const uint32_t *>(el); bl[u][1] = *reinterpret_cast<const uint32_t *>(el + 8);
-                            }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) if (n0 + u < NT) mma16816(s[n0 + u], ah, bh[u][0], bh[u][1]);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) if (n0 + u < NT) mma16816(s[n0 + u], ah, bl[u][0], bl[u][1]);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) if (n0 + u < NT) mma16816(s[n0 + u], al, bh[u][0], bh[u][1]);
-                    }
-                }
-                // ---- softmax over the keys (attention_module.py:44-49): rows g (c0, c1) and g + 8 (c2, c3) of every tile ----
-                float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const int key = 8 * nt + 2 * t;
-                    if (key < n) { mx0 = fmaxf(mx0, s[nt][0]); mx1 = fmaxf(mx1, s[nt][2]); }
-                    if (key + 1 < n) { mx0 = fmaxf(mx0, s[nt][1]); mx1 = fmaxf(mx1, s[nt][3]); }
-                }
-                mx0 = quad_max(mx0);
-                mx1 = quad_max(mx1);
-                float sum0 = 0.0f, sum1 = 0.0f;
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const int key = 8 * nt + 2 * t;
-                    s[nt][0] = key < n ? __expf(s[nt][0] - mx0) : 0.0f;
-                    s[nt][1] = key + 1 < n ? __expf(s[nt][1] - mx0) : 0.0f;
-                    s[nt][2] = key < n ? __expf(s[nt][2] - mx1) : 0.0f;
-                    s[nt][3] = key + 1 < n ? __expf(s[nt][3] - mx1) : 0.0f;
-                    sum0 += s[nt][0] + s[nt][1];
-                    sum1 += s[nt][2] + s[nt][3];
-                }
-                sum0 = quad_sum(sum0);
-                sum1 = quad_sum(sum1);
-                // ---- mask, masked sums (comm_base_net.py:101-103); the un-normalised masked rows stay in the accumulators ----
                 const bool v0 = i0 + g < n, v1 = i0 + g + 8 < n;
-                const float is0 = 1.0f / sum0, is1 = 1.0f / sum1;
-                float den0 = 0.0f, den1 = 0.0f;
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const int key = 8 * nt + 2 * t;
-                    const float p00 = s[nt][0] * is0, p01 = s[nt][1] * is0, p10 = s[nt][2] * is1, p11 = s[nt][3] * is1;
-                    if (l == 0 && A.attention) {               // the UNMASKED softmax (comm_base_net.py:93)
-                        if (v0 && key < n) A.attention[(r_env + i0 + g) * n + key] = p00;
-                        if (v0 && key + 1 < n) A.attention[(r_env + i0 + g) * n + key + 1] = p01;
-                        if (v1 && key < n) A.attention[(r_env + i0 + g + 8) * n + key] = p10;
-                        if (v1 && key + 1 < n) A.attention[(r_env + i0 + g + 8) * n + key + 1] = p11;
-                    }
-                    const uint32_t w0 = Mw[g * 8 + (nt >> 2)] >> (8 * (nt & 3) + 2 * t);
-                    const uint32_t w1 = Mw[(g + 8) * 8 + (nt >> 2)] >> (8 * (nt & 3) + 2 * t);
-                    s[nt][0] = (w0 & 1u) ? p00 : 0.0f;
-                    s[nt][1] = (w0 & 2u) ? p01 : 0.0f;
-                    s[nt][2] = (w1 & 1u) ? p10 : 0.0f;
-                    s[nt][3] = (w1 & 2u) ? p11 : 0.0f;
-                    den0 += s[nt][0] + s[nt][1];
-                    den1 += s[nt][2] + s[nt][3];
-                }
-                den0 = 1.0f / (quad_sum(den0) + 1e-12f);       // (reciprocals: one division per row instead of one per element)
-                den1 = 1.0f / (quad_sum(den1) + 1e-12f);
-                // ---- aggregation: out[16][64] = A (H_l Wg_l): the C fragments of tiles 2s, 2s+1 are the A fragment of key slice s ----
+                StripState st = {-1e30f, -1e30f, 0.0f, 0.0f, 0.0f, 0.0f};
                 float oacc[8][4];
 #pragma unroll
                 for (int ot = 0; ot < 8; ++ot) oacc[ot][0] = oacc[ot][1] = oacc[ot][2] = oacc[ot][3] = 0.0f;
-#pragma unroll
-                for (int ss = 0; ss < NS; ++ss) {
-                    uint32_t ah[4], al[4];
-                    split2(s[2 * ss][0], s[2 * ss][1], ah[0], al[0]);
-                    split2(s[2 * ss][2], s[2 * ss][3], ah[1], al[1]);
-                    split2(s[2 * ss + 1][0], s[2 * ss + 1][1], ah[2], al[2]);
-                    split2(s[2 * ss + 1][2], s[2 * ss + 1][3], ah[3], al[3]);
-                    const int k0 = 16 * ss + 2 * t;
-#pragma unroll
-                    for (int o0 = 0; o0 < 8; o0 += 4) {
-                        uint32_t bh[4][2], bl[4][2];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const __half *vh = Vh + (8 * (o0 + u) + g) * HWP + k0, *vl = Vl + (8 * (o0 + u) + g) * HWP + k0;
-                            bh[u][0] = *reinterpret_cast<const uint32_t *>(vh); bh[u][1] = *reinterpret_cast<const uint32_t *>(vh + 8);
-                            bl[u][0] = *reinterpret_cast<const uint32_t *>(vl); bl[u][1] = *reinterpret_cast<const uint32_t *>(vl + 8);
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) mma16816(oacc[o0 + u], ah, bh[u][0], bh[u][1]);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) mma16816(oacc[o0 + u], ah, bl[u][0], bl[u][1]);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) mma16816(oacc[o0 + u], al, bh[u][0], bh[u][1]);
-                    }
+#pragma unroll 1
+                for (int kb = 0; kb < NFULL; ++kb) attn_block<8>(st, oacc, Qh, Ql, Eh, El, Vh, Vl, HWP, Mw, 8 * kb, n, g, t);
+                if (TAIL) attn_block<TAIL ? TAIL : 2>(st, oacc, Qh, Ql, Eh, El, Vh, Vl, HWP, Mw, 8 * NFULL, n, g, t);
+                const float z0 = quad_sum(st.z0), z1 = quad_sum(st.z1);
+                const float den0 = 1.0f / fmaf(1e-12f, z0, quad_sum(st.d0)), den1 = 1.0f / fmaf(1e-12f, z1, quad_sum(st.d1));
+                // ---- the UNMASKED softmax (comm_base_net.py:93), when recorded: a second walk with the final m and z ----
+                if (l == 0 && A.attention) {
+                    const float is0 = 1.0f / z0, is1 = 1.0f / z1;
+                    float *att0 = A.attention + (r_env + i0 + g) * n, *att1 = A.attention + (r_env + i0 + g + 8) * n;
+#pragma unroll 1
+                    for (int kb = 0; kb < NFULL; ++kb) attn_record_block<8>(att0, att1, v0, v1, st, is0, is1, Qh, Ql, Eh, El, 8 * kb, n, g, t);
+                    if (TAIL) attn_record_block<TAIL ? TAIL : 2>(att0, att1, v0, v1, st, is0, is1, Qh, Ql, Eh, El, 8 * NFULL, n, g, t);
                 }
                 // ---- H_{l+1} = tanh(out / (sum + 1e-12) + b): rows g / g + 8, columns 8 ot + 2t, + 1 ----
 #pragma unroll
@@ -381,23 +420,25 @@ template <int NS>
 static int launch_attn_mma_t(const AttnMmaArgs &A, cudaStream_t stream)
 {
     constexpr int NK = 16 * NS;
-    constexpr size_t smem = (size_t)(2 * NK * kEhPitch + 2 * 64 * (NK + 8) + 2 * 64 * kWgPitch) * sizeof(__half) +
-                            (size_t)kMWarps * 16 * kQPitch * sizeof(float) + (size_t)kMWarps * 16 * 8 * sizeof(uint32_t);
+    constexpr size_t base = (size_t)(2 * NK * kEhPitch + 2 * 64 * (NK + 8) + 2 * 64 * kWgPitch) * sizeof(__half);
+    constexpr size_t per_warp = (size_t)2 * 16 * kQhPitch * sizeof(__half) + (size_t)16 * 8 * sizeof(uint32_t);
+    constexpr int WARPS = base + 16 * per_warp <= 227 * 1024 ? 16 : 8;
+    constexpr size_t smem = base + WARPS * per_warp;
     static thread_local struct { int dev; int slots; } cache = {-1, 0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ENODEVICE);
     if (cache.dev != dev) {
         int sms = 0, ctas = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), CM_ECUDA);
-        cudaError_t e = cudaFuncSetAttribute(policy_attn_mma_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(policy_attn_mma_kernel<NS, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_cuda_error(e, CM_ECUDA);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, policy_attn_mma_kernel<NS>, kMThreads, smem) != cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, policy_attn_mma_kernel<NS, WARPS>, WARPS * 32, smem) != cudaSuccess)
             return set_cuda_error(cudaGetLastError(), CM_ECUDA);
         cache.dev = dev;
         cache.slots = sms * (ctas < 1 ? 1 : ctas);
     }
     const int grid = (int)(A.n_envs < cache.slots ? A.n_envs : cache.slots);
-    policy_attn_mma_kernel<NS><<<grid, kMThreads, smem, stream>>>(A);
+    policy_attn_mma_kernel<NS, WARPS><<<grid, WARPS * 32, smem, stream>>>(A);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? CM_OK : set_cuda_error(e, CM_ECUDA);
 }
