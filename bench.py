@@ -51,12 +51,19 @@ CONFIGS = {
     "c4": ("co", 30, 2, 0.06, 2, 0.1, 16384),
     "c5": ("pp", 50, 2, 0.08, 4, 0.0, 2048),
 }
+# sweep-only variants: BASELINE configs[2] names "Gilbert-Elliot drops" although `--loss 0.2` on the reference's command line
+# reaches the IID channel only (init_communication forces FC / IID / FL, env_communication.py:35-43; the GE branch needs
+# env.channelType set by hand): c3 is the CLI's IID reading, c3_ge the same workload on the Gilbert-Elliot Markov channel
+# (Pgb = 0.0196, Pbg = 0.282: the reference's defaults, one transition per GCN layer)
+VARIANTS = {"c3_ge": ("c3", dict(channel_type="GE"))}
 WORKLOAD_TEXT = {
     "c1": "Predator-Prey --map 10 --sen 1 --den 0.04 --cap 2 --loss 0, 16384 envs per B200",
     "c2": "Coverage --map 10 --sen 1 --den 0.03 --loss 0, 16384 batched envs per B200",
     "c3": "Predator-Prey --map 20 --sen 2 --den 0.08 --cap 4 --loss 0.2 (IID drops), 65536 envs per B200",
     "c4": "Coverage --map 30 --sen 2 --den 0.06 --loss 0.1, 16384 envs per B200",
     "c5": "Predator-Prey --map 50 --sen 2 --den 0.08 --cap 4, 2048 envs per B200",
+    "c3_ge": "Predator-Prey --map 20 --sen 2 --den 0.08 --cap 4, Gilbert-Elliot drops (Pgb 0.0196, Pbg 0.282, a transition per GCN layer), "
+             "65536 envs per B200",
 }
 # the unmodified pure-Python reference (garage sampler + ma_gym env + CPU torch policy), one core,
 # measured while the survey was written — NOT on this box; the reference cannot travel to the GPU box.
@@ -285,9 +292,10 @@ def measure_config(cx, cfg, steps_req, warm_req, min_seconds, full, clocks=None,
     torch, args, dev = cx.torch, cx.args, cx.dev
     from com_marl_b200.rollout import HostRollout, RolloutEngine, make_policy
     from com_marl_b200.scenario import ScenarioSpec
-    scen, params = params_for(cfg)
-    spec = ScenarioSpec.from_params(scen, params, seed=1)
-    B = (args.envs if (args.envs and cfg == args.config) else CONFIGS[cfg][6])
+    base_cfg, spec_over = VARIANTS.get(cfg, (cfg, {}))
+    scen, params = params_for(base_cfg)
+    spec = ScenarioSpec.from_params(scen, params, seed=1, **spec_over)
+    B = (args.envs if (args.envs and cfg == args.config) else CONFIGS[base_cfg][6])
     n, Dobs, L = spec.n_agents, spec.obs_dim, spec.n_layers
     ring = args.ring
     pol = make_policy(spec, device=dev)
@@ -450,7 +458,7 @@ def measure_config(cx, cfg, steps_req, warm_req, min_seconds, full, clocks=None,
     env_bytes = env_bytes_per_agent_step(spec) * Bk * n
     kname = ("policy_tc_kernel<comm>" if n <= 64 else "policy_tc_kernel<enc> + policy_attn_mma_kernel + policy_tc_kernel<head>") if tc \
         else ("policy_small_kernel" if n <= 64 else "policy_large_kernel")
-    traffic = cx.traffic.get(cfg, {}) if B == CONFIGS[cfg][6] else {}
+    traffic = cx.traffic.get(cfg, {}) if (cfg in CONFIGS and B == CONFIGS[cfg][6]) else {}
     if n <= 64:
         pol_traffic = traffic.get(kname, traffic.get("policy_tc_kernel"))
     else:
@@ -623,7 +631,7 @@ def run_b200_arm(args):
     main = measure_config(cx, args.config, args.steps, args.warmup, args.min_seconds, True, clocks)
     sweep = {}
     if not args.no_sweep:
-        names = [c for c in (("c4",) if cx.world > 1 else ("c1", "c2", "c3", "c4", "c5")) if c != args.config]
+        names = [c for c in (("c4",) if cx.world > 1 else ("c1", "c2", "c3", "c3_ge", "c4", "c5")) if c != args.config]
         for c in names:
             r = measure_config(cx, c, 0, 0, args.min_seconds, False, None, e2e_seconds=0.3)
             sweep[c] = {k: r[k] for k in ("value", "ms_per_step", "steps", "timed_region_s", "e2e", "roofline", "roofline_env")}
