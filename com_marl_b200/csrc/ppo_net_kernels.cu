@@ -23,6 +23,7 @@
 #include "commarl_b200.h"
 #include "common.cuh"
 #include "policy_layout.cuh"
+#include "tc_common.cuh"
 
 namespace cm {
 
@@ -33,7 +34,10 @@ static constexpr int kNetThreads = 256; // head kernels: one thread per row
 // ------------------------------------------------------------------------------------------------------------------
 // dense layers
 // ------------------------------------------------------------------------------------------------------------------
-template <int N, int ACT>
+// ASYNC: the X tiles (rows of K floats, 16-byte aligned) arrive by one bulk async copy per row (cp.async.bulk, mbarrier
+// complete_tx) into a two-stage ring: the next tile is in flight while the products of the current one run.  Unaligned inputs
+// (the observation rows, D floats) take the synchronous load.
+template <int N, int ACT, int ASYNC>
 __global__ void __launch_bounds__(256) net_dense_fwd_kernel(const float *__restrict__ X, int ldx, const float *__restrict__ W,
                                                             const float *__restrict__ bias, float *__restrict__ Y, int ldy, int64_t R, int K)
 {
@@ -42,7 +46,8 @@ __global__ void __launch_bounds__(256) net_dense_fwd_kernel(const float *__restr
     float *sm = reinterpret_cast<float *>(smem4);
     const int K4 = (K + 3) & ~3, KP = K4 + 4;
     float *Ws = sm;                    // [K4][N]
-    float *Xs = sm + (size_t)K4 * N;   // [128][KP]
+    float *Xs0 = sm + (size_t)K4 * N;  // [stages][128][KP]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Xs0 + (size_t)(ASYNC ? 2 : 1) * 128 * KP);
     const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < K4 * N; i += 256) Ws[i] = i < K * N ? W[i] : 0.0f;
     float bj[CJ * 4];
@@ -50,28 +55,36 @@ __global__ void __launch_bounds__(256) net_dense_fwd_kernel(const float *__restr
     for (int j = 0; j < CJ; ++j)
 #pragma unroll
         for (int q = 0; q < 4; ++q) bj[4 * j + q] = bias ? bias[4 * tx + 64 * j + q] : 0.0f;
-    const bool vec = (ldx & 3) == 0 && (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
     const int64_t tiles = (R + 127) / 128;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int64_t r0 = t * 128;
+    if (ASYNC) {
+        if (tid == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::fence_mbar_init(); }
         __syncthreads();
-        if (vec) {
-            const int kq = K4 >> 2;
-            for (int i = tid; i < 128 * 32; i += 256) {
-                const int r = i >> 5, q = i & 31;
-                if (q < kq) {
-                    const int64_t gr = r0 + r;
-                    const float4 v = gr < R ? *reinterpret_cast<const float4 *>(X + gr * ldx + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    *reinterpret_cast<float4 *>(Xs + r * KP + 4 * q) = v;
-                }
-            }
+    }
+    auto issue = [&](int64_t tile, int stage) {
+        const int64_t r0 = tile * 128;
+        const int rows = (int)min((int64_t)128, R - r0);
+        if (tid == 0) tc::mbar_expect_tx(&bars[stage], (uint32_t)rows * (uint32_t)K * 4u);
+        if (tid < rows) tc::bulk_g2s(Xs0 + (size_t)stage * 128 * KP + tid * KP, X + (r0 + tid) * ldx, (uint32_t)K * 4u, &bars[stage]);
+    };
+    if (ASYNC && (int64_t)blockIdx.x < tiles) issue(blockIdx.x, 0);
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        const int64_t r0 = t * 128;
+        const float *Xs = Xs0;
+        if (ASYNC) {
+            const int stage = it & 1;
+            if (t + gridDim.x < tiles) issue(t + gridDim.x, stage ^ 1);     // (that stage was last read before the barrier below)
+            tc::mbar_wait(&bars[stage], (uint32_t)(it >> 1) & 1u);
+            Xs = Xs0 + (size_t)stage * 128 * KP;
         } else {
+            __syncthreads();
+            float *Xw = Xs0;
             for (int r = warp; r < 128; r += 8) {
                 const int64_t gr = r0 + r;
-                for (int k = lane; k < K4; k += 32) Xs[r * KP + k] = (gr < R && k < K) ? X[gr * ldx + k] : 0.0f;
+                for (int k = lane; k < K4; k += 32) Xw[r * KP + k] = (gr < R && k < K) ? X[gr * ldx + k] : 0.0f;
             }
+            __syncthreads();
         }
-        __syncthreads();
         float acc[RI][CJ * 4];
 #pragma unroll
         for (int i = 0; i < RI; ++i)
@@ -114,30 +127,36 @@ __global__ void __launch_bounds__(256) net_dense_fwd_kernel(const float *__restr
                 *reinterpret_cast<float4 *>(Y + gr * ldy + 4 * tx + 64 * j) = o;
             }
         }
+        if (ASYNC) __syncthreads();                          // every warp is done with this stage: it may be refilled
     }
 }
 
-// One pass over the rows for the three gradients of Y = act(X W + b): dZ = dY (1 - Y^2) (DACT) or dY;
-// dX[r][k] (+)= sum_n dZ[r][n] W[k][n];  dW[k][n] += sum_r X[r][k] dZ[r][n];  db[n] += sum_r dZ[r][n].
-// 16 warps: warps 0-7 form the dX tile while warps 8-15 reduce dW / db over the same tile in shared memory (two independent
-// FMA streams on one copy of the operands); dW / db stay in registers over the tiles of a persistent CTA and are added to
-// global memory once.
-template <int N, int KMAX, int DACT>
-__global__ void __launch_bounds__(512) net_dense_bwd_kernel(const float *__restrict__ dY, int lddy, const float *__restrict__ Y, int ldy,
-                                                            const float *__restrict__ X, int ldx, const float *__restrict__ W,
-                                                            float *__restrict__ dX, int lddx, int accumulate, float *__restrict__ dW,
-                                                            float *__restrict__ db, int64_t R, int K)
+// One pass over the rows for the three gradients of Y = X W + b given dZ = dL/d(X W + b):
+//   dX[r][k] = ((accumulate ? dX[r][k] : 0) + sum_n dZ[r][n] W[k][n]) * (xact ? 1 - X[r][k]^2 : 1)
+//   dW[k][n] += sum_r X[r][k] dZ[r][n];   db[n] += sum_r dZ[r][n].
+// xact folds the tanh derivative of the layer BELOW into the hand-over (X is that layer's output and already sits in
+// shared memory), so every backward layer reads plain dZ rows.  16 warps: warps 0-7 form the dX tile while warps 8-15 reduce
+// dW / db over the same tile in shared memory (two independent FMA streams on one copy of the operands); dW / db stay in
+// registers over the tiles of a persistent CTA and are added to global memory once.  ASYNC: dZ and X tiles arrive by one bulk
+// async copy per row into a two-stage ring (the next tile is in flight during the products); unaligned X rows (the
+// observations) take the synchronous load.  ROWS = rows per tile (128, or 64 where two stages of 128 do not fit).
+template <int N, int KMAX, int ROWS, int ASYNC>
+__global__ void __launch_bounds__(512) net_dense_bwd_kernel(const float *__restrict__ dZ, const float *__restrict__ X, int ldx,
+                                                            const float *__restrict__ W, float *__restrict__ dX, int lddx, int accumulate,
+                                                            int xact, float *__restrict__ dW, float *__restrict__ db, int64_t R, int K)
 {
     constexpr int NP = N + 4, KP = KMAX + 4;
-    constexpr int KJ = KMAX / 16;                                          // dX warps: k = kx + 16 j
+    constexpr int RI = ROWS / 16;                                          // dX warps: rows ty + 16 i, k = kx + 16 j
+    constexpr int KJ = KMAX / 16;
     constexpr int NX = N >= 64 ? 16 : N / 4, NJ = N / (4 * NX), KY = 256 / NX;   // dW warps: n = 4 nx + 64 j, k = 4 ky + 4 KY i
     constexpr int KI = (KMAX + 4 * KY - 1) / (4 * KY);
-    constexpr int NB = NJ * 4, NACC = (8 * KJ > KI * 4 * NB) ? 8 * KJ : KI * 4 * NB;
+    constexpr int NB = NJ * 4, NACC = (RI * KJ > KI * 4 * NB) ? RI * KJ : KI * 4 * NB;
+    constexpr int STAGE = ROWS * (NP + KP);                               // floats per stage: dZ tile, then X tile
     extern __shared__ float4 smem4[];
     float *sm = reinterpret_cast<float *>(smem4);
     float *Ws = sm;                         // [KMAX][NP]
-    float *dZs = Ws + KMAX * NP;            // [128][NP]
-    float *Xs = dZs + 128 * NP;             // [128][KP]
+    float *St0 = Ws + KMAX * NP;            // [stages][ dZs [ROWS][NP] | Xs [ROWS][KP] ]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(St0 + (size_t)(ASYNC ? 2 : 1) * STAGE);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool role_w = tid >= 256;         // (warp-uniform)
     const int t = tid & 255;
@@ -145,44 +164,71 @@ __global__ void __launch_bounds__(512) net_dense_bwd_kernel(const float *__restr
         const int k = i / N, n = i - k * N;
         Ws[k * NP + n] = k < K ? W[k * N + n] : 0.0f;
     }
-    float acc[NACC];                        // dX warps: the tile's [8][KJ] block; dW warps: the running [KI * 4][NB] block
+    float acc[NACC];                        // dX warps: the tile's [RI][KJ] block; dW warps: the running [KI * 4][NB] block
 #pragma unroll
     for (int a = 0; a < NACC; ++a) acc[a] = 0.0f;
     float bacc = 0.0f;
     const int kx = t & 15, ty = t >> 4;
     const int nx = t % NX, ky = t / NX;
-    const int64_t tiles = (R + 127) / 128;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int64_t r0 = tile * 128;
+    const int64_t tiles = (R + ROWS - 1) / ROWS;
+    if (ASYNC) {
+        if (tid == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::fence_mbar_init(); }
         __syncthreads();
-        for (int i = tid; i < 128 * (N / 4); i += 512) {
-            const int r = i / (N / 4), q = i - r * (N / 4);
-            const int64_t gr = r0 + r;
-            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gr < R) {
-                g = *reinterpret_cast<const float4 *>(dY + gr * lddy + 4 * q);
-                if (DACT) {
-                    const float4 y = *reinterpret_cast<const float4 *>(Y + gr * ldy + 4 * q);
-                    g.x *= 1.0f - y.x * y.x; g.y *= 1.0f - y.y * y.y; g.z *= 1.0f - y.z * y.z; g.w *= 1.0f - y.w * y.w;
-                }
+        if (KMAX > K)                        // (columns the copies never write)
+            for (int i = tid; i < 2 * ROWS * (KMAX - K); i += 512) {
+                const int st = i / (ROWS * (KMAX - K)), q = i - st * ROWS * (KMAX - K);
+                St0[(size_t)st * STAGE + ROWS * NP + (q / (KMAX - K)) * KP + K + q % (KMAX - K)] = 0.0f;
             }
-            *reinterpret_cast<float4 *>(dZs + r * NP + 4 * q) = g;
-        }
-        for (int r = warp; r < 128; r += 16) {
-            const int64_t gr = r0 + r;
-            for (int k = lane; k < KMAX; k += 32) Xs[r * KP + k] = (gr < R && k < K) ? X[gr * ldx + k] : 0.0f;
-        }
+    }
+    auto issue = [&](int64_t tile, int stage) {
+        const int64_t r0 = tile * ROWS;
+        const int rows = (int)min((int64_t)ROWS, R - r0);
+        float *dst = St0 + (size_t)stage * STAGE;
+        if (tid == 0) tc::mbar_expect_tx(&bars[stage], (uint32_t)rows * (uint32_t)(N + K) * 4u);
+        if (tid < rows) tc::bulk_g2s(dst + tid * NP, dZ + (r0 + tid) * N, (uint32_t)N * 4u, &bars[stage]);
+        else if (tid >= 256 && tid - 256 < rows)
+            tc::bulk_g2s(dst + ROWS * NP + (tid - 256) * KP, X + (r0 + tid - 256) * ldx, (uint32_t)K * 4u, &bars[stage]);
+    };
+    if (ASYNC) {
         __syncthreads();
+        if ((int64_t)blockIdx.x < tiles) issue(blockIdx.x, 0);
+    }
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int64_t r0 = tile * ROWS;
+        const int rows = (int)min((int64_t)ROWS, R - r0);
+        const float *dZs = St0, *Xs = St0 + ROWS * NP;
+        if (ASYNC) {
+            const int stage = it & 1;
+            if (tile + gridDim.x < tiles) issue(tile + gridDim.x, stage ^ 1);
+            tc::mbar_wait(&bars[stage], (uint32_t)(it >> 1) & 1u);
+            dZs = St0 + (size_t)stage * STAGE;
+            Xs = dZs + ROWS * NP;
+        } else {
+            __syncthreads();
+            float *dZw = St0, *Xw = St0 + ROWS * NP;
+            for (int i = tid; i < ROWS * (N / 4); i += 512) {
+                const int r = i / (N / 4), q = i - r * (N / 4);
+                const int64_t gr = r0 + r;
+                *reinterpret_cast<float4 *>(dZw + r * NP + 4 * q) =
+                    gr < R ? *reinterpret_cast<const float4 *>(dZ + gr * N + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            for (int r = warp; r < ROWS; r += 16) {
+                const int64_t gr = r0 + r;
+                for (int k = lane; k < KMAX; k += 32) Xw[r * KP + k] = (gr < R && k < K) ? X[gr * ldx + k] : 0.0f;
+            }
+            __syncthreads();
+        }
         if (!role_w) {                                       // ---- dX tile
             if (dX) {
 #pragma unroll
-                for (int a = 0; a < 8 * KJ; ++a) acc[a] = 0.0f;
+                for (int a = 0; a < RI * KJ; ++a) acc[a] = 0.0f;
                 for (int n4 = 0; n4 < N; n4 += 4) {
                     float4 w[KJ];
 #pragma unroll
                     for (int j = 0; j < KJ; ++j) w[j] = *reinterpret_cast<const float4 *>(Ws + (kx + 16 * j) * NP + n4);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < RI; ++i) {
                         const float4 z = *reinterpret_cast<const float4 *>(dZs + (ty + 16 * i) * NP + n4);
 #pragma unroll
                         for (int j = 0; j < KJ; ++j)
@@ -190,23 +236,25 @@ __global__ void __launch_bounds__(512) net_dense_bwd_kernel(const float *__restr
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int64_t gr = r0 + ty + 16 * i;
-                    if (gr >= R) continue;
+                for (int i = 0; i < RI; ++i) {
+                    const int r = ty + 16 * i;
+                    if (r >= rows) continue;
 #pragma unroll
                     for (int j = 0; j < KJ; ++j) {
                         const int k = kx + 16 * j;
                         if (k < K) {
-                            float *p = dX + gr * lddx + k;
-                            *p = accumulate ? *p + acc[i * KJ + j] : acc[i * KJ + j];
+                            float *p = dX + (r0 + r) * lddx + k;
+                            float v = accumulate ? *p + acc[i * KJ + j] : acc[i * KJ + j];
+                            if (xact) { const float x = Xs[r * KP + k]; v *= 1.0f - x * x; }
+                            *p = v;
                         }
                     }
                 }
             }
-        } else {                                             // ---- dW += X^T dZ, db += sum dZ over the 128 rows of the tile
+        } else {                                             // ---- dW += X^T dZ, db += sum dZ over the valid rows of the tile
             if (4 * ky < KMAX) {
 #pragma unroll 2
-                for (int r = 0; r < 128; ++r) {
+                for (int r = 0; r < rows; ++r) {
                     float4 xa[KI], za[NJ];
 #pragma unroll
                     for (int i = 0; i < KI; ++i)
@@ -232,10 +280,11 @@ __global__ void __launch_bounds__(512) net_dense_bwd_kernel(const float *__restr
             }
             if (db && t < N) {
                 float s = 0.0f;
-                for (int r = 0; r < 128; ++r) s += dZs[r * NP + t];
+                for (int r = 0; r < rows; ++r) s += dZs[r * NP + t];
                 bacc += s;
             }
         }
+        if (ASYNC) __syncthreads();                          // every warp is done with this stage: it may be refilled
     }
     if (role_w) {
         if (4 * ky < KMAX) {
@@ -863,7 +912,7 @@ struct PolicyHeadArgs {
     const uint8_t *valid;        // [S] or NULL
     float inv_count, ent_coeff, clip_lo, clip_hi;
     float *ll, *ent, *probs, *loss;
-    float *dg3, *dw4, *db4;      // NULL: forward only
+    float *dg3, *dw4, *db4;      // NULL: forward only; dg3 receives dZ of the last hidden layer: d g3 (1 - g3^2)
     int n, G;
     int64_t S;
 };
@@ -990,7 +1039,7 @@ __global__ void __launch_bounds__(kNetThreads) net_policy_head_kernel(const Poli
                     float v = 0.0f;
 #pragma unroll
                     for (int j = 0; j < CM_ACTIONS; ++j) v = fmaf(gz[j], w4s[(4 * k4 + c) * CM_ACTIONS + j], v);
-                    o[c] = v;
+                    o[c] = v * (1.0f - g[4 * k4 + c] * g[4 * k4 + c]);           // dZ of the last hidden layer (tanh)
                 }
                 dst[k4] = make_float4(o[0], o[1], o[2], o[3]);
             }
@@ -1076,7 +1125,10 @@ __global__ void __launch_bounds__(kNetThreads) net_critic_head_kernel(const Crit
         if (active) {
             float4 *dst = reinterpret_cast<float4 *>(a.dc1 + row * 64);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) dst[k] = make_float4(gv * w2s[4 * k], gv * w2s[4 * k + 1], gv * w2s[4 * k + 2], gv * w2s[4 * k + 3]);
+            for (int k = 0; k < 16; ++k)                  // dZ of the decoder's hidden layer (tanh)
+                dst[k] = make_float4(gv * w2s[4 * k] * (1.0f - c[4 * k] * c[4 * k]), gv * w2s[4 * k + 1] * (1.0f - c[4 * k + 1] * c[4 * k + 1]),
+                                     gv * w2s[4 * k + 2] * (1.0f - c[4 * k + 2] * c[4 * k + 2]),
+                                     gv * w2s[4 * k + 3] * (1.0f - c[4 * k + 3] * c[4 * k + 3]));
         }
 #pragma unroll
         for (int k = 0; k < 64; ++k) {
@@ -1138,19 +1190,28 @@ static cudaError_t set_smem(Kern k, size_t bytes)
 
 #define NET_TRY(expr) do { const cudaError_t e__ = (expr); if (e__ != cudaSuccess) return e__; } while (0)
 
-template <int N, int ACT>
-static cudaError_t dense_fwd_t(const float *X, int ldx, const float *W, const float *b, float *Y, int64_t R, int K, cudaStream_t st)
+static const size_t kSmemMax = 227 * 1024;
+
+template <int N, int ACT, int ASYNC>
+static cudaError_t dense_fwd_a(const float *X, int ldx, const float *W, const float *b, float *Y, int64_t R, int K, cudaStream_t st)
 {
     const int K4 = (K + 3) & ~3;
-    const size_t smem = ((size_t)K4 * N + 128 * (size_t)(K4 + 4)) * sizeof(float);
-    NET_TRY(set_smem(net_dense_fwd_kernel<N, ACT>, smem));
+    const size_t smem = ((size_t)K4 * N + (ASYNC ? 2 : 1) * 128 * (size_t)(K4 + 4)) * sizeof(float) + 16;
+    NET_TRY(set_smem(net_dense_fwd_kernel<N, ACT, ASYNC>, smem));
     int per_sm = 1;
-    NET_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, net_dense_fwd_kernel<N, ACT>, 256, smem));
+    NET_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, net_dense_fwd_kernel<N, ACT, ASYNC>, 256, smem));
     if (per_sm < 1) per_sm = 1;
     const int64_t tiles = (R + 127) / 128;
     const int grid = (int)(tiles < (int64_t)sm_count() * per_sm ? tiles : (int64_t)sm_count() * per_sm);
-    net_dense_fwd_kernel<N, ACT><<<grid, 256, smem, st>>>(X, ldx, W, b, Y, N, R, K);
+    net_dense_fwd_kernel<N, ACT, ASYNC><<<grid, 256, smem, st>>>(X, ldx, W, b, Y, N, R, K);
     return cudaGetLastError();
+}
+static bool rows_aligned(const float *X, int ldx, int K) { return (ldx & 3) == 0 && (K & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0; }
+
+template <int N, int ACT>
+static cudaError_t dense_fwd_t(const float *X, int ldx, const float *W, const float *b, float *Y, int64_t R, int K, cudaStream_t st)
+{
+    return rows_aligned(X, ldx, K) ? dense_fwd_a<N, ACT, 1>(X, ldx, W, b, Y, R, K, st) : dense_fwd_a<N, ACT, 0>(X, ldx, W, b, Y, R, K, st);
 }
 
 static cudaError_t dense_fwd(const float *X, int ldx, const float *W, const float *b, float *Y, int64_t R, int K, int N, int act,
@@ -1161,39 +1222,41 @@ static cudaError_t dense_fwd(const float *X, int ldx, const float *W, const floa
     return act ? dense_fwd_t<32, 1>(X, ldx, W, b, Y, R, K, st) : dense_fwd_t<32, 0>(X, ldx, W, b, Y, R, K, st);
 }
 
-template <int N, int KMAX, int DACT>
-static cudaError_t dense_bwd_t(const float *dY, const float *Y, const float *X, int ldx, const float *W, float *dX, int accumulate,
-                               float *dW, float *db, int64_t R, int K, cudaStream_t st)
+template <int N, int KMAX, int ROWS, int ASYNC>
+static cudaError_t dense_bwd_a(const float *dZ, const float *X, int ldx, const float *W, float *dX, int accumulate, int xact, float *dW,
+                               float *db, int64_t R, int K, cudaStream_t st)
 {
-    const size_t smem = ((size_t)KMAX * (N + 4) + 128 * (size_t)(N + 4) + 128 * (size_t)(KMAX + 4)) * sizeof(float);
-    NET_TRY(set_smem(net_dense_bwd_kernel<N, KMAX, DACT>, smem));
+    const size_t smem = ((size_t)KMAX * (N + 4) + (ASYNC ? 2 : 1) * (size_t)ROWS * (N + 4 + KMAX + 4)) * sizeof(float) + 16;
+    NET_TRY(set_smem(net_dense_bwd_kernel<N, KMAX, ROWS, ASYNC>, smem));
     int per_sm = 1;
-    NET_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, net_dense_bwd_kernel<N, KMAX, DACT>, 512, smem));
+    NET_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, net_dense_bwd_kernel<N, KMAX, ROWS, ASYNC>, 512, smem));
     if (per_sm < 1) per_sm = 1;
-    const int64_t tiles = (R + 127) / 128;
+    const int64_t tiles = (R + ROWS - 1) / ROWS;
     const int grid = (int)(tiles < (int64_t)sm_count() * per_sm ? tiles : (int64_t)sm_count() * per_sm);
-    net_dense_bwd_kernel<N, KMAX, DACT><<<grid, 512, smem, st>>>(dY, N, Y, N, X, ldx, W, dX, K, accumulate, dW, db, R, K);
+    net_dense_bwd_kernel<N, KMAX, ROWS, ASYNC><<<grid, 512, smem, st>>>(dZ, X, ldx, W, dX, K, accumulate, xact, dW, db, R, K);
     return cudaGetLastError();
 }
 
-template <int N, int DACT>
-static cudaError_t dense_bwd_n(const float *dY, const float *Y, const float *X, int ldx, const float *W, float *dX, int accumulate,
-                               float *dW, float *db, int64_t R, int K, cudaStream_t st)
+template <int N, int KMAX>
+static cudaError_t dense_bwd_t(const float *dZ, const float *X, int ldx, const float *W, float *dX, int accumulate, int xact, float *dW,
+                               float *db, int64_t R, int K, cudaStream_t st)
 {
-    return K <= 64 ? dense_bwd_t<N, 64, DACT>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st)
-                   : dense_bwd_t<N, 128, DACT>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st);
+    // two stages of 128-row tiles where they fit into shared memory, else of 64-row tiles
+    constexpr bool fits = ((size_t)KMAX * (N + 4) + 2 * (size_t)128 * (N + 4 + KMAX + 4)) * sizeof(float) + 16 <= 227 * 1024;
+    if (!rows_aligned(X, ldx, K)) return dense_bwd_a<N, KMAX, 128, 0>(dZ, X, ldx, W, dX, accumulate, xact, dW, db, R, K, st);
+    return dense_bwd_a<N, KMAX, fits ? 128 : 64, 1>(dZ, X, ldx, W, dX, accumulate, xact, dW, db, R, K, st);
 }
 
-// gradients of Y = act(X W + b), Y [R][N]; dX [R][K] (lddx = K) may be NULL
-static cudaError_t dense_bwd(const float *dY, const float *Y, const float *X, int ldx, const float *W, float *dX, int accumulate,
-                             float *dW, float *db, int64_t R, int K, int N, int dact, cudaStream_t st)
+// gradients of Y = X W + b from dZ [R][N]; dX [R][K] (lddx = K) may be NULL; xact: dX *= 1 - X^2
+static cudaError_t dense_bwd(const float *dZ, const float *X, int ldx, const float *W, float *dX, int accumulate, int xact, float *dW,
+                             float *db, int64_t R, int K, int N, cudaStream_t st)
 {
-    if (N == 128) return dact ? dense_bwd_n<128, 1>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st)
-                              : dense_bwd_n<128, 0>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st);
-    if (N == 64) return dact ? dense_bwd_n<64, 1>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st)
-                             : dense_bwd_n<64, 0>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st);
-    return dact ? dense_bwd_n<32, 1>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st)
-                : dense_bwd_n<32, 0>(dY, Y, X, ldx, W, dX, accumulate, dW, db, R, K, st);
+    if (N == 128) return K <= 64 ? dense_bwd_t<128, 64>(dZ, X, ldx, W, dX, accumulate, xact, dW, db, R, K, st)
+                                 : dense_bwd_t<128, 128>(dZ, X, ldx, W, dX, accumulate, xact, dW, db, R, K, st);
+    if (N == 64) return K <= 64 ? dense_bwd_t<64, 64>(dZ, X, ldx, W, dX, accumulate, xact, dW, db, R, K, st)
+                                : dense_bwd_t<64, 128>(dZ, X, ldx, W, dX, accumulate, xact, dW, db, R, K, st);
+    return K <= 64 ? dense_bwd_t<32, 64>(dZ, X, ldx, W, dX, accumulate, xact, dW, db, R, K, st)
+                   : dense_bwd_t<32, 128>(dZ, X, ldx, W, dX, accumulate, xact, dW, db, R, K, st);
 }
 
 static int env_group(int n) { return n >= kRows ? 1 : kRows / n; }          // head kernels: one thread per row, 256 rows per CTA
@@ -1223,7 +1286,6 @@ struct EnvCall {
     cudaStream_t st;
 };
 
-static const size_t kSmemMax = 227 * 1024;
 template <typename Kern>
 static cudaError_t env_launch_dims(Kern k, int threads, size_t smem, const EnvCall &c, int *grid)
 {
@@ -1425,18 +1487,19 @@ static cudaError_t trunk_bwd(const cm_net_desc &d, const EnvCall &c, const float
         NET_TRY(agg_bwd(c, l, w.M, w.V[l], w.H[l], dHl, w.t64c, w.dM, l != L - 1, w.CT, grad + o.gcn_b + l * kE));
         const float *Hin = l == 0 ? w.E : w.H[l - 1];
         if (l == 0) {
-            NET_TRY(dense_bwd(w.t64c, nullptr, Hin, 64, wts + o.gcn_w, dE, dE_init ? 1 : 0, grad + o.gcn_w, nullptr, R, 64, 64, 0, c.st));
+            NET_TRY(dense_bwd(w.t64c, Hin, 64, wts + o.gcn_w, dE, dE_init ? 1 : 0, 0, grad + o.gcn_w, nullptr, R, 64, 64, c.st));
             dE_init = true;
         } else {
-            NET_TRY(dense_bwd(w.t64c, nullptr, Hin, 64, wts + o.gcn_w + l * kE * kE, w.t64a, 0, grad + o.gcn_w + l * kE * kE, nullptr, R, 64,
-                              64, 0, c.st));
+            NET_TRY(dense_bwd(w.t64c, Hin, 64, wts + o.gcn_w + l * kE * kE, w.t64a, 0, 0, grad + o.gcn_w + l * kE * kE, nullptr, R, 64, 64,
+                              c.st));
             dHl = w.t64a;
         }
     }
     NET_TRY(softmax_bwd(c, w.M, w.dM, w.E, w.Q, w.t64c, dE, w.CT));
-    NET_TRY(dense_bwd(w.t64c, nullptr, w.E, 64, wts + o.att_w, dE, 1, grad + o.att_w, nullptr, R, 64, 64, 0, c.st));
-    NET_TRY(dense_bwd(dE, w.E, w.h1, 128, wts + o.enc_w2, w.t128, 0, grad + o.enc_w2, grad + o.enc_b2, R, 128, 64, 1, c.st));
-    NET_TRY(dense_bwd(w.t128, w.h1, obs, d.obs_dim, wts + o.enc_w1, nullptr, 0, grad + o.enc_w1, grad + o.enc_b1, R, d.obs_dim, 128, 1, c.st));
+    // the last term of dE (through Q = E W_a); the same pass turns the sum into dZ of the embedding layer: dE (1 - E^2)
+    NET_TRY(dense_bwd(w.t64c, w.E, 64, wts + o.att_w, dE, 1, 1, grad + o.att_w, nullptr, R, 64, 64, c.st));
+    NET_TRY(dense_bwd(dE, w.h1, 128, wts + o.enc_w2, w.t128, 0, 1, grad + o.enc_w2, grad + o.enc_b2, R, 128, 64, c.st));
+    NET_TRY(dense_bwd(w.t128, obs, d.obs_dim, wts + o.enc_w1, nullptr, 0, 0, grad + o.enc_w1, grad + o.enc_b1, R, d.obs_dim, 128, c.st));
     return cudaSuccess;
 }
 
@@ -1486,9 +1549,10 @@ static cudaError_t run_chunk(const cm_net_desc &d, const cm_net_io &io, int64_t 
         NET_TRY(cudaGetLastError());
         if (!backward) return cudaSuccess;
         float *g = io.grad;
-        NET_TRY(dense_bwd(w.t32, w.g3, w.g2, 64, wts + o.head_w3, w.t64a, 0, g + o.head_w3, g + o.head_b3, R, 64, 32, 1, st));
-        NET_TRY(dense_bwd(w.t64a, w.g2, w.g1, 128, wts + o.head_w2, w.t128, 0, g + o.head_w2, g + o.head_b2, R, 128, 64, 1, st));
-        NET_TRY(dense_bwd(w.t128, w.g1, Xin, 64, wts + o.head_w1, w.t64b, 0, g + o.head_w1, g + o.head_b1, R, 64, 128, 1, st));
+        // (the head kernel hands over dZ of the last hidden layer; every layer's dX pass applies the tanh derivative of the one below)
+        NET_TRY(dense_bwd(w.t32, w.g2, 64, wts + o.head_w3, w.t64a, 0, 1, g + o.head_w3, g + o.head_b3, R, 64, 32, st));
+        NET_TRY(dense_bwd(w.t64a, w.g1, 128, wts + o.head_w2, w.t128, 0, 1, g + o.head_w2, g + o.head_b2, R, 128, 64, st));
+        NET_TRY(dense_bwd(w.t128, Xin, 64, wts + o.head_w1, w.t64b, 0, 0, g + o.head_w1, g + o.head_b1, R, 64, 128, st));
         return trunk_bwd(d, c, wts, g, o, obs, w);
     }
     const CriticBlob cb = critic_blob_layout(D, L);
@@ -1507,7 +1571,7 @@ static cudaError_t run_chunk(const cm_net_desc &d, const cm_net_io &io, int64_t 
     net_critic_head_kernel<<<env_grid(n, steps, 4), kNetThreads, 0, st>>>(a);
     NET_TRY(cudaGetLastError());
     if (!backward) return cudaSuccess;
-    NET_TRY(dense_bwd(w.t64a, w.g2, Xin, 64, wts + cb.dec_w1, w.t64b, 0, io.grad + cb.dec_w1, io.grad + cb.dec_b1, R, 64, 64, 1, st));
+    NET_TRY(dense_bwd(w.t64a, Xin, 64, wts + cb.dec_w1, w.t64b, 0, 0, io.grad + cb.dec_w1, io.grad + cb.dec_b1, R, 64, 64, st));
     return trunk_bwd(d, c, wts, io.grad, o, obs, w);
 }
 
