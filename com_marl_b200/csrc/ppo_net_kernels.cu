@@ -221,6 +221,15 @@ __global__ void __launch_bounds__(512) net_dense_bwd_kernel(const float *__restr
         }
         if (!role_w) {                                       // ---- dX tile
             if (dX) {
+                // the old values of an accumulating pass are requested BEFORE the products: their latency hides behind the FMAs
+                float old[RI * KJ];
+#pragma unroll
+                for (int i = 0; i < RI; ++i)
+#pragma unroll
+                    for (int j = 0; j < KJ; ++j) {
+                        const int r = ty + 16 * i, k = kx + 16 * j;
+                        old[i * KJ + j] = (accumulate && r < rows && k < K) ? dX[(r0 + r) * lddx + k] : 0.0f;
+                    }
 #pragma unroll
                 for (int a = 0; a < RI * KJ; ++a) acc[a] = 0.0f;
                 for (int n4 = 0; n4 < N; n4 += 4) {
@@ -243,10 +252,9 @@ __global__ void __launch_bounds__(512) net_dense_bwd_kernel(const float *__restr
                     for (int j = 0; j < KJ; ++j) {
                         const int k = kx + 16 * j;
                         if (k < K) {
-                            float *p = dX + (r0 + r) * lddx + k;
-                            float v = accumulate ? *p + acc[i * KJ + j] : acc[i * KJ + j];
+                            float v = old[i * KJ + j] + acc[i * KJ + j];
                             if (xact) { const float x = Xs[r * KP + k]; v *= 1.0f - x * x; }
-                            *p = v;
+                            dX[(r0 + r) * lddx + k] = v;
                         }
                     }
                 }
