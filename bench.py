@@ -699,7 +699,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2000, help="cap on the steps of an e2e (host-buffer) loop")
     ap.add_argument("--e2e-batches", type=int, default=4, help="independent env parts of the e2e (host-buffer) loops")
     ap.add_argument("--groups", type=int, default=0, help="independent env groups, each a policy->step chain on its own stream (0: 4 for teams <= 64, else 1)")
-    ap.add_argument("--ppo-envs", type=int, default=32, help="envs per GPU of the c5_ppo sub-record")
+    ap.add_argument("--ppo-envs", type=int, default=128, help="envs per GPU of the c5_ppo sub-record")
     ap.add_argument("--no-sweep", action="store_true", help="skip the configs sweep and the c5_ppo sub-record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -178,3 +178,37 @@ def test_ppo_data_parallel_update_world_size_2_gloo():
     assert minibatch_plan(0, 3) == []
     single, ranks = ppo_dp_util.run("cpu")
     ppo_dp_util.check(single, ranks)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(attention_type="dot", gcn_bias=False),
+                                dict(encoder_hidden_sizes=(96,), embedding_dim=48, categorical_mlp_hidden_sizes=(100, 40, 24))])
+def test_fused_update_blob_maps_round_trip(kw):
+    """ppo_fused._BlobMap (host logic of the hand-written PPO update): the gather map derived from the module's own packing
+    function reproduces the kernel weight blob from FlatAdam's flat bucket — transposes, zero padding of narrower layers, the
+    constant identity of 'dot' attention — and the inverse map returns a blob-layout gradient to the flat gradient bucket."""
+    import torch
+    from com_marl_b200.policy import CommCategoricalMLPPolicy
+    from com_marl_b200.ppo import CommBaseCritic, FlatAdam
+    from com_marl_b200.ppo_fused import _BlobMap
+    from com_marl_b200.spaces import Box, Discrete, EnvSpec
+    torch.manual_seed(3)
+    n, D = 5, 21
+    spec = EnvSpec(Box(np.zeros(n * D), np.ones(n * D)), Discrete(5))
+    ckw = {k: v for k, v in kw.items() if k != "categorical_mlp_hidden_sizes"}
+    if "embedding_dim" in kw:
+        ckw["decoder_hidden_sizes"] = (56,)
+    for mod in (CommCategoricalMLPPolicy(spec, n, device="cpu", **kw), CommBaseCritic(spec, n, device="cpu", **ckw)):
+        with torch.no_grad():
+            for p in mod.parameters():
+                p.add_(0.1 * torch.randn_like(p))
+        opt = FlatAdam(mod)
+        m = _BlobMap(mod, mod._pack_blob, opt.flat)
+        assert torch.equal(m.refresh(), mod._pack_blob(mod.state_dict()))
+        # after an in-place update of the bucket the refreshed blob follows (the parameters are views of it)
+        opt.flat.mul_(1.5)
+        assert torch.equal(m.refresh(), mod._pack_blob(mod.state_dict()))
+        fake = {k: torch.randn_like(p) for k, p in mod.named_parameters()}
+        m.grad.copy_(mod._pack_blob(fake))
+        out = torch.empty_like(opt.grad)
+        m.scatter_grad(out)
+        assert torch.equal(out, torch.cat([fake[k].reshape(-1) for k, _ in mod.named_parameters()]))
