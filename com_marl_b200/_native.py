@@ -21,7 +21,7 @@ ABI_VERSION = 3
 EXPORTS = ("cm_abi_version", "cm_strerror", "cm_last_cuda_error", "cm_device_count", "cm_env_reset", "cm_env_step",
            "cm_comm_update", "cm_policy_forward", "cm_policy_blob_floats", "cm_policy_cent_blob_floats", "cm_policy_cent_tc_blob_floats", "cm_policy_cent_workspace_bytes", "cm_policy_workspace_bytes", "cm_policy_tc_blob_floats", "cm_policy_tc_prepare", "cm_mask_pack",
            "cm_mask_unpack", "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host", "cm_rollout_step_host", "cm_ppo_advantages",
-           "cm_adam_step", "cm_critic_blob_floats", "cm_ppo_net_workspace_floats", "cm_ppo_net")
+           "cm_adam_step", "cm_adam_step_dev", "cm_critic_blob_floats", "cm_ppo_net_workspace_floats", "cm_ppo_net")
 NET_POLICY, NET_CRITIC = 0, 1
 
 
@@ -130,6 +130,9 @@ def lib():
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cm_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
                                C.c_float, C.c_int32, C.c_float, C.c_void_p]
+    L.cm_adam_step_dev.restype = C.c_int
+    L.cm_adam_step_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
+                                   C.c_float, C.c_int32, C.c_void_p, C.c_void_p]
     L.cm_critic_blob_floats.restype = C.c_size_t
     L.cm_critic_blob_floats.argtypes = [C.c_int32, C.c_int32]
     L.cm_ppo_net_workspace_floats.restype = C.c_size_t

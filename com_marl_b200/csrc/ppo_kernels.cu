@@ -72,8 +72,10 @@ __global__ void ppo_advantages_kernel(const double *__restrict__ rewards, const 
 // torch.optim Adam as the reference drives it (my_optimizer/adam.py:57-120 -> torch.optim._functional.adam, no amsgrad,
 // no weight decay) over a flat bucket; grad_scale folds the clip_grad_norm_ coefficient into the same pass.
 __global__ void adam_step_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
-                                 int64_t n, float beta1, float beta2, float eps, float step_size, float inv_sqrt_bc2, float grad_scale)
+                                 int64_t n, float beta1, float beta2, float eps, float step_size, float inv_sqrt_bc2, float grad_scale,
+                                 const float *__restrict__ grad_scale_dev)
 {
+    if (grad_scale_dev) grad_scale = *grad_scale_dev;       // the clip coefficient straight from the reduction that produced it
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float gi = g[i] * grad_scale;
         const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
@@ -109,8 +111,8 @@ extern "C" int cm_ppo_advantages(const double *rewards, const float *baselines, 
     return e == cudaSuccess ? CM_OK : set_cuda_error(e, CM_ECUDA);
 }
 
-extern "C" int cm_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
-                            float beta2, float eps, int32_t step, float grad_scale, cm_stream_t stream)
+static int adam_step_impl(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                          float beta2, float eps, int32_t step, float grad_scale, const float *grad_scale_dev, cm_stream_t stream)
 {
     using namespace cm;
     if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || step < 1) return CM_EINVAL;
@@ -120,7 +122,20 @@ extern "C" int cm_adam_step(float *params, const float *grads, float *exp_avg, f
     const int64_t want = (n + 255) / 256;
     const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
     adam_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, beta1, beta2, eps, step_size,
-                                                            inv_sqrt_bc2, grad_scale);
+                                                            inv_sqrt_bc2, grad_scale, grad_scale_dev);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? CM_OK : set_cuda_error(e, CM_ECUDA);
+}
+
+extern "C" int cm_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                            float beta2, float eps, int32_t step, float grad_scale, cm_stream_t stream)
+{
+    return adam_step_impl(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, nullptr, stream);
+}
+
+extern "C" int cm_adam_step_dev(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                                float beta2, float eps, int32_t step, const float *grad_scale_dev, cm_stream_t stream)
+{
+    if (!grad_scale_dev) return CM_EINVAL;
+    return adam_step_impl(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, 1.0f, grad_scale_dev, stream);
 }

@@ -183,11 +183,20 @@ class FlatAdam:
         return torch.clamp(max_norm / (norm + 1e-6), max=1.0), norm
 
     def step(self, grad_scale=1.0):
+        """grad_scale: a float, or a 0-d / 1-element float32 DEVICE tensor (the clip coefficient as computed on the device:
+        no host synchronisation between the backward pass and the step)"""
         self.steps += 1
         with torch.cuda.device(self.flat.device):
-            N.check("cm_adam_step", N.lib().cm_adam_step(N.ptr(self.flat), N.ptr(self.grad), N.ptr(self.exp_avg), N.ptr(self.exp_avg_sq),
-                                                         self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.steps,
-                                                         float(grad_scale), N.stream_ptr()))
+            if isinstance(grad_scale, torch.Tensor):
+                self._scale = grad_scale.detach().to(torch.float32).reshape(1).contiguous()      # (kept alive until the next step)
+                N.check("cm_adam_step_dev", N.lib().cm_adam_step_dev(N.ptr(self.flat), N.ptr(self.grad), N.ptr(self.exp_avg),
+                                                                     N.ptr(self.exp_avg_sq), self.flat.numel(), self.lr, self.betas[0],
+                                                                     self.betas[1], self.eps, self.steps, N.ptr(self._scale),
+                                                                     N.stream_ptr()))
+            else:
+                N.check("cm_adam_step", N.lib().cm_adam_step(N.ptr(self.flat), N.ptr(self.grad), N.ptr(self.exp_avg), N.ptr(self.exp_avg_sq),
+                                                             self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.steps,
+                                                             float(grad_scale), N.stream_ptr()))
         for p in self.params:                 # the kernel wrote the parameters behind autograd's back: bump the version
             torch.autograd.graph.increment_version(p)      # counters, so that the policy rebuilds its kernel weight blobs
 
@@ -472,31 +481,40 @@ class DevicePPO:
             plan = minibatch_plan(P, self.n_minibatches, self.device, self.group)
             losses, bl_losses, gnorms = [], [], []
             nan = torch.full((1,), float("nan"), device=self.device)
+            # the minibatches are the same in every mini-epoch: their rows are gathered once, before the loop (no index upload,
+            # no gather and no host synchronisation inside it)
+            mbs = []
+            for start, stop in plan:
+                if stop <= start:
+                    mbs.append(None)
+                    continue
+                ids = ids_all[start:stop]
+                idx_all = F.step_index(f, ids, valid_only=False)
+                idx = F.step_index(f, ids, valid_only=True)
+                adv = raw_adv.index_select(0, idx)
+                if self.positive_adv:             # shifted by the minimum over the minibatch's padded rows (centralized_ma_ppo.py:428-429)
+                    adv = adv - raw_adv.index_select(0, idx_all).min()
+                mbs.append(dict(cri=F.subset(f, idx_all, policy=False), ret=ret_all.index_select(0, idx_all), pol=F.subset(f, idx),
+                                adv=adv, old=old_ll.index_select(0, idx), n_valid=int(idx.numel()), n_all=int(idx_all.numel())))
             for _ in range(self.mini_epochs):
-                for start, stop in plan:
+                for mb in mbs:
                     self.baseline_opt.zero_grad()
                     self.opt.zero_grad()
                     w_pol = w_bl = 0.0
                     loss = bl = nan
-                    if stop > start:
-                        ids = ids_all[start:stop]
-                        idx_all = F.step_index(f, ids, valid_only=False)
-                        bl = F.critic_call(f, idx_all, returns=ret_all.index_select(0, idx_all), backward=True)["loss"]
+                    if mb is not None:
+                        bl = F.critic_call(mb["cri"], None, returns=mb["ret"], backward=True)["loss"]
                         F.cri_map.scatter_grad(self.baseline_opt.grad)
-                        idx = F.step_index(f, ids, valid_only=True)
-                        adv = raw_adv.index_select(0, idx)
-                        if self.positive_adv:         # shifted by the minimum over the minibatch's padded rows (centralized_ma_ppo.py:428-429)
-                            adv = adv - raw_adv.index_select(0, idx_all).min()
-                        loss = F.policy_call(f, idx, adv=adv, old_ll=old_ll.index_select(0, idx), backward=True,
-                                             inv_count=1.0 / max(idx.numel(), 1))["loss"]
+                        loss = F.policy_call(mb["pol"], None, adv=mb["adv"], old_ll=mb["old"], backward=True,
+                                             inv_count=1.0 / max(mb["n_valid"], 1))["loss"]
                         F.pol_map.scatter_grad(self.opt.grad)
-                        w_pol, w_bl = float(idx.numel()), float((stop - start) * T)
+                        w_pol, w_bl = float(mb["n_valid"]), float(mb["n_all"])
                     self.opt.all_reduce(self.group, w_pol)
                     self.baseline_opt.all_reduce(self.group, w_bl)
                     scale = 1.0
                     if self.clip_grad_norm is not None:
                         coef, norm = self.opt.clip_coefficient(self.clip_grad_norm)
-                        scale = float(coef)
+                        scale = coef                            # stays on the device (cm_adam_step_dev): no host round trip per step
                         gnorms.append(norm * coef)
                     self.opt.step(scale)
                     self.baseline_opt.step(1.0)

@@ -110,10 +110,19 @@ class FusedCommNets:
         ids = np.asarray(path_ids, dtype=np.int64)
         if valid_only:
             v = f["valids_host"][ids]
-            idx = np.concatenate([p * T + np.arange(k) for p, k in zip(ids, v)]) if len(ids) else np.zeros(0, np.int64)
+            first = np.cumsum(v) - v                                     # position of each path's first step in the output
+            idx = np.repeat(ids * T - first, v) + np.arange(int(v.sum()), dtype=np.int64)
         else:
             idx = (ids[:, None] * T + np.arange(T)[None, :]).reshape(-1)
         return torch.from_numpy(idx).to(self.device)
+
+    def subset(self, f, idx, policy=True):
+        """the rows `idx` of the flat batch gathered ONCE (a minibatch is walked again in every mini-epoch): a flat batch of its
+        own, to be passed to policy_call / critic_call with idx = None"""
+        keys = ("obs", "adj", "chan") + (("avail", "actions", "valid") if policy else ())
+        g = {k: f[k].index_select(0, idx) for k in keys}
+        g["P"], g["T"] = 1, int(idx.numel())
+        return g
 
     # ---- one call ------------------------------------------------------------------------------------------------
     def _workspace(self, desc, steps, backward):
@@ -132,6 +141,8 @@ class FusedCommNets:
         sel = (lambda x: x) if idx is None else (lambda x: x.index_select(0, idx))
         keep = dict(obs=sel(f["obs"]), adj=sel(f["adj"]), chan=sel(f["chan"]))
         S = keep["obs"].shape[0]
+        if backward:
+            (self.pol_map if desc is self.pol_desc else self.cri_map).grad.zero_()
         io = N.NetIO()
         io.n_steps = S
         io.weights = N.ptr(wmap.blob)
@@ -166,8 +177,6 @@ class FusedCommNets:
             if inv_count is None:
                 inv_count = 1.0 / max(float(keep["valid"].sum()), 1.0)
             io.inv_count = float(inv_count)
-        if backward:
-            self.pol_map.grad.zero_()
         if S:
             self._run(self.pol_desc, io)
         return out
@@ -184,8 +193,6 @@ class FusedCommNets:
             io.loss = N.ptr(loss)
             out["loss"] = loss
             io.inv_count = 1.0 / max(S, 1)
-        if backward:
-            self.cri_map.grad.zero_()
         if S:
             self._run(self.cri_desc, io)
         return out

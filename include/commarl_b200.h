@@ -301,6 +301,10 @@ int cm_ppo_advantages(const double *rewards, const float *baselines, const int32
                       cm_stream_t stream);
 int cm_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
                  float beta2, float eps, int32_t step, float grad_scale, cm_stream_t stream);
+/* the same step with the gradient scale read from DEVICE memory (the clip_grad_norm_ coefficient as the norm reduction left it:
+ * no host round trip between the backward pass and the optimizer step) */
+int cm_adam_step_dev(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                     float beta2, float eps, int32_t step, const float *grad_scale_dev, cm_stream_t stream);
 
 /* ---- PPO update: hand-written forward + backward of the comm-GNN (csrc/ppo_net_kernels.cu) -----------------------------
  * cm_ppo_net runs ONE network over n_steps env steps of n agents each — the flattened (path, t) pairs of a minibatch of
