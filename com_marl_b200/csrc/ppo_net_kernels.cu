@@ -389,7 +389,7 @@ __device__ __forceinline__ uint32_t mask_word(const uint32_t *__restrict__ bits,
 
 // M[s][i][:] = softmax_k < Q[s][i], E[s][k] >
 template <int KT, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) net_scores_kernel(const float *__restrict__ Q, const float *__restrict__ E,
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 1) net_scores_kernel(const float *__restrict__ Q, const float *__restrict__ E,
                                                                  float *__restrict__ M, int n, int G, int cap, int64_t S)
 {
     extern __shared__ float4 smem4[];
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) net_scores_ke
 
 // H[s][i][:] = tanh( sum_k A~[i][k] V[s][k][:] + b ),  A~ = M . adj . chan_l / (rowsum + 1e-12);  optional Xout = res + H
 template <int KT, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) net_agg_fwd_kernel(const float *__restrict__ M, const uint32_t *__restrict__ adj,
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 1) net_agg_fwd_kernel(const float *__restrict__ M, const uint32_t *__restrict__ adj,
                                                                   const uint32_t *__restrict__ chan, int L, int l,
                                                                   const float *__restrict__ V, const float *__restrict__ bias,
                                                                   float *__restrict__ H, const float *__restrict__ res,
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) net_agg_fwd_k
 // dA~ = dZ V^T;  dM (+)= mask (dA~ - <dA~, A~>) / (rowsum + 1e-12).  A~ strips are parked TRANSPOSED in CT so that the
 // second pass (key strips) reads contiguous coefficient rows.
 template <int KT, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) net_agg_bwd_kernel(const float *__restrict__ M, const uint32_t *__restrict__ adj,
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 1) net_agg_bwd_kernel(const float *__restrict__ M, const uint32_t *__restrict__ adj,
                                                                   const uint32_t *__restrict__ chan, int L, int l,
                                                                   const float *__restrict__ V, const float *__restrict__ H,
                                                                   const float *__restrict__ dH, float *__restrict__ dV,
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) net_agg_bwd_k
 
 // dS = M (dM - <dM, M>) per query row;  dQ = dS E;  dE += dS^T Q
 template <int KT, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) net_softmax_bwd_kernel(const float *__restrict__ M, const float *__restrict__ dM,
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 1) net_softmax_bwd_kernel(const float *__restrict__ M, const float *__restrict__ dM,
                                                                       const float *__restrict__ E, const float *__restrict__ Q,
                                                                       float *__restrict__ dQ, float *__restrict__ dE,
                                                                       float *__restrict__ CT, int n, int G, int cap, int64_t S)
@@ -1275,13 +1275,13 @@ static int env_grid(int n, int64_t S, int per_sm)
     return (int)(nblk < (int64_t)sm_count() * per_sm ? nblk : (int64_t)sm_count() * per_sm);
 }
 
-// n x n kernels: a CTA owns G whole envs at a time, at most `cap` rows: 64 rows for small teams (many CTAs per SM hide the
-// latency of the short strips), 128 up to n = 64, one env beyond
+// n x n kernels: a CTA owns G whole envs at a time, at most `cap` rows: 64 rows up to n = 32 (three or more CTAs per SM hide the
+// latency of the short strips: the kernels wait on global loads), 128 up to n = 64, one env beyond
 struct EnvGeom { int G, cap; };
 static EnvGeom env_geom(int n)
 {
     EnvGeom g;
-    const int target = n <= 16 ? 64 : 128;
+    const int target = n <= 32 ? 64 : 128;
     g.G = n >= target ? 1 : target / n;
     g.cap = (g.G * n + 3) & ~3;
     return g;
