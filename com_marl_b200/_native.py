@@ -22,7 +22,7 @@ EXPORTS = ("cm_abi_version", "cm_strerror", "cm_last_cuda_error", "cm_device_cou
            "cm_comm_update", "cm_policy_forward", "cm_policy_blob_floats", "cm_policy_cent_blob_floats", "cm_policy_cent_tc_blob_floats", "cm_policy_cent_workspace_bytes", "cm_policy_workspace_bytes", "cm_policy_tc_blob_floats", "cm_policy_tc_prepare", "cm_mask_pack",
            "cm_mask_unpack", "cm_policy_forward_host", "cm_env_step_host", "cm_env_reset_host", "cm_rollout_step_host", "cm_ppo_advantages",
            "cm_adam_step", "cm_adam_step_dev", "cm_critic_blob_floats", "cm_ppo_net_workspace_floats", "cm_ppo_net")
-NET_POLICY, NET_CRITIC = 0, 1
+NET_POLICY, NET_CRITIC, NET_POLICY_DEC = 0, 1, 2
 
 
 class EnvDesc(C.Structure):

@@ -1532,13 +1532,21 @@ static cudaError_t run_chunk(const cm_net_desc &d, const cm_net_io &io, int64_t 
     const float *obs = io.obs + r0 * D;
     const float *wts = io.weights;
     const int G = env_group(n);
-    if (d.kind == CM_NET_POLICY) {
+    if (d.kind == CM_NET_POLICY || d.kind == CM_NET_POLICY_DEC) {
+        const bool dec = d.kind == CM_NET_POLICY_DEC;        // Obs-DP: encoder D -> 128 -> 64 and head 64 -> 32 -> 5 per agent row, no communication
         const Blob o = blob_layout(D, L);
-        NET_TRY(trunk_fwd(d, c, wts, o, obs, w));
-        const float *Xin = d.residual ? w.X : w.H[L - 1];
-        NET_TRY(dense_fwd(Xin, 64, wts + o.head_w1, wts + o.head_b1, w.g1, R, 64, 128, 1, st));
-        NET_TRY(dense_fwd(w.g1, 128, wts + o.head_w2, wts + o.head_b2, w.g2, R, 128, 64, 1, st));
-        NET_TRY(dense_fwd(w.g2, 64, wts + o.head_w3, wts + o.head_b3, w.g3, R, 64, 32, 1, st));
+        const float *Xin = nullptr;
+        if (dec) {
+            NET_TRY(dense_fwd(obs, D, wts + o.enc_w1, wts + o.enc_b1, w.h1, R, D, 128, 1, st));
+            NET_TRY(dense_fwd(w.h1, 128, wts + o.enc_w2, wts + o.enc_b2, w.E, R, 128, 64, 1, st));
+            NET_TRY(dense_fwd(w.E, 64, wts + o.head_w3, wts + o.head_b3, w.g3, R, 64, 32, 1, st));
+        } else {
+            NET_TRY(trunk_fwd(d, c, wts, o, obs, w));
+            Xin = d.residual ? w.X : w.H[L - 1];
+            NET_TRY(dense_fwd(Xin, 64, wts + o.head_w1, wts + o.head_b1, w.g1, R, 64, 128, 1, st));
+            NET_TRY(dense_fwd(w.g1, 128, wts + o.head_w2, wts + o.head_b2, w.g2, R, 128, 64, 1, st));
+            NET_TRY(dense_fwd(w.g2, 64, wts + o.head_w3, wts + o.head_b3, w.g3, R, 64, 32, 1, st));
+        }
         PolicyHeadArgs a = {};
         a.g3 = w.g3; a.w4 = wts + o.head_w4; a.b4 = wts + o.head_b4;
         a.avail_bits = io.avail_bits ? io.avail_bits + r0 : nullptr;
@@ -1557,6 +1565,11 @@ static cudaError_t run_chunk(const cm_net_desc &d, const cm_net_io &io, int64_t 
         NET_TRY(cudaGetLastError());
         if (!backward) return cudaSuccess;
         float *g = io.grad;
+        if (dec) {
+            NET_TRY(dense_bwd(w.t32, w.E, 64, wts + o.head_w3, w.t64b, 0, 1, g + o.head_w3, g + o.head_b3, R, 64, 32, st));
+            NET_TRY(dense_bwd(w.t64b, w.h1, 128, wts + o.enc_w2, w.t128, 0, 1, g + o.enc_w2, g + o.enc_b2, R, 128, 64, st));
+            return dense_bwd(w.t128, obs, D, wts + o.enc_w1, nullptr, 0, 0, g + o.enc_w1, g + o.enc_b1, R, D, 128, st);
+        }
         // (the head kernel hands over dZ of the last hidden layer; every layer's dX pass applies the tanh derivative of the one below)
         NET_TRY(dense_bwd(w.t32, w.g2, 64, wts + o.head_w3, w.t64a, 0, 1, g + o.head_w3, g + o.head_b3, R, 64, 32, st));
         NET_TRY(dense_bwd(w.t64a, w.g1, 128, wts + o.head_w2, w.t128, 0, 1, g + o.head_w2, g + o.head_b2, R, 128, 64, st));
@@ -1601,10 +1614,10 @@ extern "C" int cm_ppo_net(const cm_net_desc *desc, const cm_net_io *io, cm_strea
     using namespace cm;
     if (!desc || !io || !io->weights || !io->obs || !io->workspace || io->n_steps < 0) return CM_EINVAL;
     const cm_net_desc &d = *desc;
-    if (d.kind != CM_NET_POLICY && d.kind != CM_NET_CRITIC) return CM_EINVAL;
+    if (d.kind != CM_NET_POLICY && d.kind != CM_NET_CRITIC && d.kind != CM_NET_POLICY_DEC) return CM_EINVAL;
     if (d.n_agents < 1 || d.n_agents > CM_MAX_AGENTS || d.obs_dim < 1 || d.obs_dim > 128 || d.n_layers < 1 || d.n_layers > CM_MAX_LAYERS)
         return CM_EUNSUPPORTED;
-    if (io->grad && d.kind == CM_NET_POLICY && (!io->actions || !io->adv)) return CM_EINVAL;
+    if (io->grad && d.kind != CM_NET_CRITIC && (!io->actions || !io->adv)) return CM_EINVAL;
     if (io->grad && d.kind == CM_NET_CRITIC && !io->returns) return CM_EINVAL;
     if (io->n_steps == 0) return CM_OK;
     if (cm_device_count() <= 0) return CM_ENODEVICE;

@@ -486,20 +486,22 @@ class DecCategoricalMLPPolicy(nn.Module):
     def uses_tensor_cores(self):
         return True
 
-    def weight_blob(self):
+    def _pack_blob(self, sd):
         """the Comm-DP blob layout (include/commarl_b200.h) with the unused blocks zero: enc_w1/b1, enc_w2/b2 <- encoder,
         head_w3/b3 <- _layers.0, head_w4/b4 <- _output_layers.0"""
+        dev, D = self.device, self._dec_obs_dim
+        z = lambda *shape: torch.zeros(shape, device=dev)  # noqa: E731
+        parts = [_pad2(sd["encoder._layers.0.linear.weight"].t(), D, 128), _pad2(sd["encoder._layers.0.linear.bias"], 128, 0),
+                 _pad2(sd["encoder._output_layers.0.linear.weight"].t(), 128, 64), _pad2(sd["encoder._output_layers.0.linear.bias"], 64, 0),
+                 z(64, 64), z(64, 64), z(64), z(64, 128), z(128), z(128, 64), z(64),
+                 _pad2(sd["_layers.0.linear.weight"].t(), 64, 32), _pad2(sd["_layers.0.linear.bias"], 32, 0),
+                 _pad2(sd["_output_layers.0.linear.weight"].t(), 32, self._action_dim), sd["_output_layers.0.linear.bias"]]
+        return torch.cat([p.detach().to(dev, torch.float32).contiguous().reshape(-1) for p in parts])
+
+    def weight_blob(self):
         sig = self._signature()
         if self._blob is None or sig != self._blob_sig:
-            sd, E, dev = self.state_dict(), self._embedding_dim, self.device
-            z = lambda *shape: torch.zeros(shape, device=dev)  # noqa: E731
-            D = self._dec_obs_dim
-            parts = [_pad2(sd["encoder._layers.0.linear.weight"].t(), D, 128), _pad2(sd["encoder._layers.0.linear.bias"], 128, 0),
-                     _pad2(sd["encoder._output_layers.0.linear.weight"].t(), 128, 64), _pad2(sd["encoder._output_layers.0.linear.bias"], 64, 0),
-                     z(64, 64), z(64, 64), z(64), z(64, 128), z(128), z(128, 64), z(64),
-                     _pad2(sd["_layers.0.linear.weight"].t(), 64, 32), _pad2(sd["_layers.0.linear.bias"], 32, 0),
-                     _pad2(sd["_output_layers.0.linear.weight"].t(), 32, self._action_dim), sd["_output_layers.0.linear.bias"]]
-            blob = torch.cat([p.detach().to(dev, torch.float32).contiguous().reshape(-1) for p in parts])
+            blob = self._pack_blob(self.state_dict())
             assert blob.numel() == N.lib().cm_policy_blob_floats(self._dec_obs_dim, 1)
             self._blob = _refresh_in_place(self._blob, blob)
             self._blob_sig = sig

@@ -1,11 +1,11 @@
 """Hand-written forward / backward of the PPO update for the Comm-DP family (csrc/ppo_net_kernels.cu, cm_ppo_net).
 
-``FusedCommNets`` is what ``DevicePPO`` drives instead of torch autograd when the policy is a ``CommCategoricalMLPPolicy``
-and the baseline a ``CommBaseCritic`` (runner_*_comm.py): per optimizer step ONE C call per network computes the loss of
+``FusedCommNets`` is what ``DevicePPO`` drives instead of torch autograd when the baseline is a ``CommBaseCritic`` and the
+policy a ``CommCategoricalMLPPolicy`` (runner_*_comm.py) or a ``DecCategoricalMLPPolicy`` (runner_*_obsDP.py): per optimizer step ONE C call per network computes the loss of
 centralized_ma_ppo.py:390-438 / comm_base_critic.py and the gradient of every parameter, exact fp32.  The parameters stay
 torch tensors (views of FlatAdam's flat bucket): a precomputed index map turns the flat bucket into the kernels' weight blob
 (K-major, zero-padded to the kernel widths) with one gather, and the gradient blob back into the flat gradient bucket with
-another.  The Obs-DP and CENT runner families keep the autograd path.
+another.  The CENT runner family keeps the autograd path.
 """
 import ctypes as C
 
@@ -64,13 +64,15 @@ class FusedCommNets:
     def __init__(self, policy, critic, opt, baseline_opt, ent_coeff, clip_range, chunk_rows=262144):
         self.policy, self.critic = policy, critic
         self.device = policy.device
-        self.n, self.D, self.L = policy._n_agents, policy._dec_obs_dim, policy.n_gcn_layers
+        # L = layers of the communication masks in the batch (the critic's; the Obs-DP policy has none of its own)
+        self.n, self.D, self.L = policy._n_agents, policy._dec_obs_dim, len(critic.gcn_layers)
         self.W = (self.n + 31) // 32
         self.pol_map = _BlobMap(policy, policy._pack_blob, opt.flat)
         self.cri_map = _BlobMap(critic, critic._pack_blob, baseline_opt.flat)
-        assert self.pol_map.const.numel() == N.lib().cm_policy_blob_floats(self.D, self.L)
+        self.dec = not getattr(policy, "comm", False)
+        assert self.pol_map.const.numel() == N.lib().cm_policy_blob_floats(self.D, policy.n_gcn_layers)
         assert self.cri_map.const.numel() == N.lib().cm_critic_blob_floats(self.D, self.L)
-        self.pol_desc = N.NetDesc(N.NET_POLICY, self.n, self.D, self.L, int(policy.residual), float(ent_coeff),
+        self.pol_desc = N.NetDesc(N.NET_POLICY_DEC if self.dec else N.NET_POLICY, self.n, self.D, policy.n_gcn_layers, int(policy.residual), float(ent_coeff),
                                   1.0 - float(clip_range), 1.0 + float(clip_range))
         self.cri_desc = N.NetDesc(N.NET_CRITIC, self.n, self.D, len(critic.gcn_layers), int(critic.residual), 0.0, 0.0, 0.0)
         self.chunk_steps = max(1, int(chunk_rows) // self.n)
@@ -79,10 +81,13 @@ class FusedCommNets:
 
     @staticmethod
     def supports(policy, critic):
-        from .policy import CommCategoricalMLPPolicy
+        from .policy import CommCategoricalMLPPolicy, DecCategoricalMLPPolicy
         from .ppo import CommBaseCritic
-        return (type(policy) is CommCategoricalMLPPolicy and type(critic) is CommBaseCritic and policy._dec_obs_dim <= 128
-                and policy._n_agents == critic._n_agents and len(critic.gcn_layers) == policy.n_gcn_layers)
+        if type(critic) is not CommBaseCritic or policy._dec_obs_dim > 128 or policy._n_agents != critic._n_agents:
+            return False
+        if type(policy) is DecCategoricalMLPPolicy:              # Obs-DP runners: no communication in the policy
+            return True
+        return type(policy) is CommCategoricalMLPPolicy and len(critic.gcn_layers) == policy.n_gcn_layers
 
     # ---- batch ---------------------------------------------------------------------------------------------------
     def prepare(self, b):
@@ -94,7 +99,8 @@ class FusedCommNets:
         if "adj_bits" in b:
             f["adj"], f["chan"] = b["adj_bits"].reshape(S, n, W).contiguous(), b["chan_bits"].reshape(S, L, n, W).contiguous()
         else:
-            pack = self.policy.pack_mask
+            from .policy import CommCategoricalMLPPolicy
+            pack = CommCategoricalMLPPolicy.pack_mask            # (static: cm_mask_pack)
             f["adj"] = pack(b["dist_adjs"].reshape(S, n, n), n)
             f["chan"] = pack(b["channels"].reshape(S, L, n, n), n)
         av = b["avail"].reshape(S, n, 5)

@@ -314,6 +314,9 @@ int cm_adam_step_dev(float *params, const float *grads, float *exp_avg, float *e
  *                         the taken actions, mean entropy over the agents, ratio = exp(ll - old_ll), clipped surrogate
  *                         min(ratio adv, clip(ratio, clip_lo, clip_hi) adv) + ent_coeff entropy;  loss = -sum over the valid steps
  *                         * inv_count.  Weights / gradient in the layout of the rollout blob (cm_policy_blob_floats).
+ *   kind = CM_NET_POLICY_DEC  DecCategoricalMLPPolicy.forward (dec_categorical_mlp_policy.py:107-124, 198-226: encoder D -> 128 -> 64,
+ *                         head 64 -> 32 -> 5 per agent row, no masks) with the same objective; blob = the rollout blob of the Obs-DP
+ *                         kind (enc_w1/b1, enc_w2/b2, head_w3/b3, head_w4/b4 filled, n_layers = 1).
  *   kind = CM_NET_CRITIC  CommBaseCritic.compute_loss (comm_base_critic.py:11-120): the same trunk, decoder 64 -> 64 (tanh) -> 1,
  *                         V(s) = sum over agents, loss = mean Gaussian negative log-likelihood of `returns` with the learnt
  *                         log-std (clamped at log 1e-6).  Blob (cm_critic_blob_floats): enc_w1 [D][128] enc_b1 enc_w2 [128][64]
@@ -323,7 +326,7 @@ int cm_adam_step_dev(float *params, const float *grads, float *exp_avg, float *e
  * are ADDED to grad (same layout as weights; the caller zeroes it) — exact fp32 like the autograd graph they replace.
  * Activations live in `workspace`; the steps are walked in chunks of as many steps as the workspace holds
  * (cm_ppo_net_workspace_floats(desc, chunk_steps, backward) floats hold one chunk).  Stream-ordered, capturable. */
-typedef enum cm_net_kind { CM_NET_POLICY = 0, CM_NET_CRITIC = 1 } cm_net_kind;
+typedef enum cm_net_kind { CM_NET_POLICY = 0, CM_NET_CRITIC = 1, CM_NET_POLICY_DEC = 2 } cm_net_kind;
 typedef struct cm_net_desc {
     int32_t kind;              /* cm_net_kind */
     int32_t n_agents, obs_dim, n_layers, residual;

@@ -179,3 +179,49 @@ def test_chunked_walk_equals_single_chunk():
     F.chunk_steps, F._ws = 5, None
     F.policy_call(f, idx, adv=adv, backward=True, inv_count=1.0 / idx.numel())
     assert _rel(F.pol_map.grad, g1) <= 1e-5
+
+
+@pytest.mark.parametrize("n,D", [(4, 21), (32, 53), (200, 53)])
+def test_fused_obs_dp_policy_equals_autograd(n, D):
+    """the Obs-DP runner family (DecCategoricalMLPPolicy + CommBaseCritic, runner_*_obsDP.py): cm_ppo_net kind = CM_NET_POLICY_DEC"""
+    import torch
+    from com_marl_b200.policy import DecCategoricalMLPPolicy
+    from com_marl_b200.ppo import CommBaseCritic, DevicePPO
+    from com_marl_b200.spaces import Box, Discrete, EnvSpec
+    _, _, b0 = _make(n, D, 2, 3, 4, seed=n + 1)
+    torch.manual_seed(n)
+    spec = EnvSpec(Box(np.zeros(n * D), np.ones(n * D)), Discrete(5))
+    pa, pf = DecCategoricalMLPPolicy(spec, n), DecCategoricalMLPPolicy(spec, n)
+    ca, cf = CommBaseCritic(spec, n), CommBaseCritic(spec, n)
+    with torch.no_grad():
+        for p in pa.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    pf.load_state_dict(pa.state_dict())
+    cf.load_state_dict(ca.state_dict())
+    auto, fused = DevicePPO(pa, ca, fused=False), DevicePPO(pf, cf, fused=True)
+    assert fused._fused is not None and fused._fused.dec
+    ba, bf = auto.finish_batch(dict(b0)), fused.finish_batch(dict(b0))
+    assert _rel(bf["baselines"], ba["baselines"]) <= 2e-5
+    F, f = fused._fused, bf["_flat"]
+    with torch.no_grad():
+        d = auto._dist(ba, None)
+        ll = d.log_prob(ba["actions"]).sum(-1)
+        F.pol_map.refresh()
+        out = F.policy_call(f, None, want_probs=True)
+    assert _rel(out["ll"].reshape(3, 4), ll) <= 2e-5 and _rel(out["probs"].reshape(3, 4, n, 5), d.probs) <= 2e-5
+    old = ll + 0.1 * torch.randn_like(ll)
+    auto.opt.zero_grad()
+    loss_ref = auto.compute_loss(ba, None, old)
+    loss_ref.backward()
+    idx = F.step_index(f, np.arange(3), valid_only=True)
+    res = F.policy_call(f, idx, adv=ba["adv"].reshape(-1).index_select(0, idx), old_ll=old.reshape(-1).index_select(0, idx), backward=True,
+                        inv_count=1.0 / idx.numel())
+    g = torch.empty_like(fused.opt.grad)
+    F.pol_map.scatter_grad(g)
+    tol = max(1.0, n / 32.0)
+    assert abs(float(res["loss"]) - float(loss_ref.detach())) <= 2e-5 * tol * max(1.0, abs(float(loss_ref.detach())))
+    assert _rel(g, auto.opt.grad) <= 1e-4 * tol
+    oa = auto.train_once(batch=ba, shuffled_ids=np.arange(3))
+    of = fused.train_once(batch=bf, shuffled_ids=np.arange(3))
+    for k in ("loss_before", "loss_after", "kl"):
+        assert abs(oa[k] - of[k]) <= 2e-4 * tol * max(1.0, abs(oa[k])), k

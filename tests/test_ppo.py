@@ -100,8 +100,8 @@ def test_train_once_matches_reference(name, fused):
     per-step losses, gradient norms and the final policy / critic weights equal the reference's — with the network forward /
     backward on torch autograd (fused=False) and on the hand-written kernels (fused=True: cm_ppo_net, the Comm-DP family)"""
     c = PPOCase(name)
-    if fused and c.meta.get("kind", "comm") != "comm":
-        pytest.skip("the hand-written update kernels cover the Comm-DP family (CommCategoricalMLPPolicy + CommBaseCritic)")
+    if fused and c.meta.get("kind", "comm") == "cent":
+        pytest.skip("the hand-written update kernels cover the Comm-DP and Obs-DP families (CommBaseCritic); CENT keeps autograd")
     pol, cri, algo = _build(c, fused=fused)
     assert (algo._fused is not None) == fused
     z = c.z
