@@ -344,22 +344,36 @@ __device__ __forceinline__ void strip_dots(const float *As, int nr, const float 
     }
 }
 
-// out[i][0..1] = sum_k Cs[i][k] B[k][2 lane + {0, 1}],  k < n;  Cs [8][CP] holds zeros from n up to the next multiple of 4
-__device__ __forceinline__ void strip_agg(const float *Cs, int CP, const float *Bs, int n, int lane, float (&out)[8][2])
+// res[r][0..3] = sum_k Cs[4 h + r][k] B[k][4 l + {0..3}],  k < n,  h = lane / 16, l = lane % 16:  every lane owns FOUR of the 64
+// columns, the two half-warps take alternate groups of four keys (one 128-bit operand read feeds 16 FMAs, half the shared-memory
+// traffic per FMA of a two-column layout) and exchange their partial sums at the end; afterwards half h holds rows 4 h .. 4 h + 3 of
+// the strip.  Cs [8][CP] holds zeros from n up to the next multiple of 8.
+__device__ __forceinline__ void strip_agg4(const float *Cs, int CP, const float *Bs, int n, int lane, float (&res)[4][4])
 {
+    const int half = lane >> 4, l16 = lane & 15;
+    float out[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) out[i][0] = out[i][1] = 0.0f;
-    for (int k = 0; k < n; k += 4) {
-        float2 b[4];
+    for (int i = 0; i < 8; ++i) out[i][0] = out[i][1] = out[i][2] = out[i][3] = 0.0f;
+    for (int k = 4 * half; k < n; k += 8) {
+        float4 b[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float2 *>(Bs + min(k + q, n - 1) * kNP + 2 * lane);
+        for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4 *>(Bs + min(k + q, n - 1) * kNP + 4 * l16);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float4 c = *reinterpret_cast<const float4 *>(Cs + i * CP + k);
             out[i][0] = fmaf(c.x, b[0].x, fmaf(c.y, b[1].x, fmaf(c.z, b[2].x, fmaf(c.w, b[3].x, out[i][0]))));
             out[i][1] = fmaf(c.x, b[0].y, fmaf(c.y, b[1].y, fmaf(c.z, b[2].y, fmaf(c.w, b[3].y, out[i][1]))));
+            out[i][2] = fmaf(c.x, b[0].z, fmaf(c.y, b[1].z, fmaf(c.z, b[2].z, fmaf(c.w, b[3].z, out[i][2]))));
+            out[i][3] = fmaf(c.x, b[0].w, fmaf(c.y, b[1].w, fmaf(c.z, b[2].w, fmaf(c.w, b[3].w, out[i][3]))));
         }
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float other = __shfl_xor_sync(0xFFFFFFFFu, out[i][c], 16);
+            if ((i >> 2) == half) res[i & 3][c] = out[i][c] + other;
+        }
 }
 
 // rows [row0, row0 + rows) x 64 floats of a global [.][64] array -> shared memory (pitch kNP); optional second array
@@ -432,7 +446,7 @@ template <int KT, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 1) net_agg_fwd_kernel(const float *__restrict__ M, const uint32_t *__restrict__ adj,
                                                                   const uint32_t *__restrict__ chan, int L, int l,
                                                                   const float *__restrict__ V, const float *__restrict__ bias,
-                                                                  float *__restrict__ H, const float *__restrict__ res,
+                                                                  float *__restrict__ H, const float *__restrict__ res_in,
                                                                   float *__restrict__ Xout, int n, int G, int cap, int64_t S)
 {
     extern __shared__ float4 smem4[];
@@ -441,7 +455,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *Cs = Call + warp * 8 * CP;
     const int ns = (n + 7) >> 3, W = (n + 31) >> 5;
-    const float2 bv = make_float2(bias[2 * lane], bias[2 * lane + 1]);
+    const float4 bv = *reinterpret_cast<const float4 *>(bias + 4 * (lane & 15));
     const int64_t nblk = (S + G - 1) / G;
     for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         const EnvBlock eb = env_block(blk, G, n, S);
@@ -469,19 +483,22 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 
                 for (int j = 0; j < KT; ++j) Cs[i * CP + lane + 32 * j] = a[j] / sum;
             }
             __syncwarp();
-            float out[8][2];
-            strip_agg(Cs, CP, Vs + g * n * kNP, n, lane, out);
+            float res[4][4];
+            strip_agg4(Cs, CP, Vs + g * n * kNP, n, lane, res);
+            const int half = lane >> 4, l16 = lane & 15;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int r = 0; r < 4; ++r) {
+                const int i = 4 * half + r;
                 if (i < nr) {
                     const int64_t row = s * n + j0 + i;
-                    const float2 h = make_float2(tanhf(out[i][0] + bv.x), tanhf(out[i][1] + bv.y));
-                    *reinterpret_cast<float2 *>(H + row * 64 + 2 * lane) = h;
+                    const float4 h = make_float4(tanhf(res[r][0] + bv.x), tanhf(res[r][1] + bv.y), tanhf(res[r][2] + bv.z), tanhf(res[r][3] + bv.w));
+                    *reinterpret_cast<float4 *>(H + row * 64 + 4 * l16) = h;
                     if (Xout) {
-                        const float2 e = *reinterpret_cast<const float2 *>(res + row * 64 + 2 * lane);
-                        *reinterpret_cast<float2 *>(Xout + row * 64 + 2 * lane) = make_float2(e.x + h.x, e.y + h.y);
+                        const float4 e = *reinterpret_cast<const float4 *>(res_in + row * 64 + 4 * l16);
+                        *reinterpret_cast<float4 *>(Xout + row * 64 + 4 * l16) = make_float4(e.x + h.x, e.y + h.y, e.z + h.z, e.w + h.w);
                     }
                 }
+            }
         }
     }
 }
@@ -573,11 +590,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 
                     Cs[i * CP + q] = (i < nk && q < n) ? CT[(s * n + k0 + i) * n + q] : 0.0f;
                 }
             __syncwarp();
-            float out[8][2];
-            strip_agg(Cs, CP, dZs + g * n * kNP, n, lane, out);
+            float res[4][4];
+            strip_agg4(Cs, CP, dZs + g * n * kNP, n, lane, res);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (i < nk) *reinterpret_cast<float2 *>(dV + (s * n + k0 + i) * 64 + 2 * lane) = make_float2(out[i][0], out[i][1]);
+            for (int r = 0; r < 4; ++r) {
+                const int i = 4 * (lane >> 4) + r;
+                if (i < nk)
+                    *reinterpret_cast<float4 *>(dV + (s * n + k0 + i) * 64 + 4 * (lane & 15)) = make_float4(res[r][0], res[r][1], res[r][2], res[r][3]);
+            }
         }
     }
     if (db && tid < 64) atomicAdd(db + tid, bacc);
@@ -629,11 +649,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 
                 }
             }
             __syncwarp();
-            float out[8][2];
-            strip_agg(Cs, CP, Es + g * n * kNP, n, lane, out);
+            float res[4][4];
+            strip_agg4(Cs, CP, Es + g * n * kNP, n, lane, res);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (i < nr) *reinterpret_cast<float2 *>(dQ + (s * n + j0 + i) * 64 + 2 * lane) = make_float2(out[i][0], out[i][1]);
+            for (int r = 0; r < 4; ++r) {
+                const int i = 4 * (lane >> 4) + r;
+                if (i < nr)
+                    *reinterpret_cast<float4 *>(dQ + (s * n + j0 + i) * 64 + 4 * (lane & 15)) = make_float4(res[r][0], res[r][1], res[r][2], res[r][3]);
+            }
         }
         __syncthreads();
         for (int st = warp; st < eb.ne * ns; st += THREADS / 32) {          // pass 2: key strips
@@ -648,15 +671,17 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 
                     Cs[i * CP + q] = (i < nk && q < n) ? CT[(s * n + k0 + i) * n + q] : 0.0f;
                 }
             __syncwarp();
-            float out[8][2];
-            strip_agg(Cs, CP, Qs + g * n * kNP, n, lane, out);
+            float res[4][4];
+            strip_agg4(Cs, CP, Qs + g * n * kNP, n, lane, res);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int r = 0; r < 4; ++r) {
+                const int i = 4 * (lane >> 4) + r;
                 if (i < nk) {
-                    float2 *p = reinterpret_cast<float2 *>(dE + (s * n + k0 + i) * 64 + 2 * lane);
-                    const float2 o = *p;
-                    *p = make_float2(o.x + out[i][0], o.y + out[i][1]);
+                    float4 *p = reinterpret_cast<float4 *>(dE + (s * n + k0 + i) * 64 + 4 * (lane & 15));
+                    const float4 o = *p;
+                    *p = make_float4(o.x + res[r][0], o.y + res[r][1], o.z + res[r][2], o.w + res[r][3]);
                 }
+            }
         }
     }
 }
