@@ -1,6 +1,6 @@
 // ppo_kernels.cu — the two hand-written pieces of the PPO update: per-path returns / GAE advantages /
 // advantage normalisation, and the fused Adam step over a flat parameter bucket.  The network forward / backward of the
-// update is torch autograd (com_marl_b200/ppo.py); these kernels replace the Python-side tensor plumbing around it.
+// update is csrc/ppo_net_kernels.cu (cm_ppo_net); these kernels replace the Python-side tensor plumbing around it.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>

@@ -11,9 +11,12 @@ Mirrors, with the reference's semantics and hyper-parameter names:
                                     ``optimization_n_minibatches`` slices, ``optimization_mini_epochs`` passes, critic loss,
                                     clip_grad_norm_ on the policy, both Adam steps.
 Returns, GAE advantages and their per-path normalisation run in ``cm_ppo_advantages`` and both Adam steps in
-``cm_adam_step`` (hand-written CUDA over flat parameter buckets, csrc/ppo_kernels.cu); the network forward / backward is
-torch autograd over the policy's differentiable ``forward``.  With more than one rank the flat gradient buckets are
-all-reduced (NCCL) before clipping — the only collective of the update.
+``cm_adam_step`` (hand-written CUDA over flat parameter buckets, csrc/ppo_kernels.cu).  The network forward / backward of the
+Comm-DP and Obs-DP runner families (CommBaseCritic with a CommCategoricalMLPPolicy or a DecCategoricalMLPPolicy) runs on the
+hand-written kernels of csrc/ppo_net_kernels.cu (``cm_ppo_net`` through ppo_fused.FusedCommNets, ``fused='auto'``); the CENT
+family and ``fused=False`` (the kernels' cross-check) use torch autograd over the policies' differentiable ``forward``.  With
+more than one rank the flat gradient buckets are all-reduced (NCCL) before clipping — the only collective of the update
+(SURVEY.md §8e).
 """
 import ctypes as C
 

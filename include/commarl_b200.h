@@ -287,7 +287,7 @@ int cm_rollout_step_host(const cm_policy_desc *pol_desc, const cm_policy_io *pol
                          const cm_env_desc *env_desc, const cm_env_state *state, const cm_step_io *env_dev,
                          const cm_step_io *env_host, cm_stream_t stream);
 
-/* ---- PPO update helpers (the network forward / backward is torch autograd, com_marl_b200/ppo.py) ----
+/* ---- PPO update helpers (the network forward / backward: cm_ppo_net below) ----
  * cm_ppo_advantages: rows of the padded [P][T] batch of CentralizedMAPPO.process_samples (centralized_ma_ppo.py:612-659):
  *   returns  = tensor_utils.discount_cumsum of the valid steps (garage/misc/tensor_utils.py:7-23; float64 recursion),
  *   raw_adv  = compute_advantages (garage/torch/algos/_utils.py:56-113) over the whole padded row, baselines of the
