@@ -299,7 +299,9 @@ def measure_config(cx, cfg, steps_req, warm_req, min_seconds, full, clocks=None,
     n, Dobs, L = spec.n_agents, spec.obs_dim, spec.n_layers
     ring = args.ring
     pol = make_policy(spec, device=dev)
-    groups = args.groups if args.groups > 0 else (4 if n <= 64 else 1)
+    # independent env groups: 4 chains for teams up to 64 (8 when a chain still gets ~2000 policy tiles per launch — C3: measured
+    # 849 -> 864 M agent-steps/s; smaller batches lose with 8), one chain for the three-launch pipeline of large teams
+    groups = args.groups if args.groups > 0 else ((8 if B * n >= (1 << 21) else 4) if n <= 64 else 1)
     eng = RolloutEngine(spec, pol, B, device=dev, env_id0=cx.rank * B, ring=ring, use_graph=True, groups=groups)
     eng.reset()
     warm = max(3 * ring, ((warm_req + ring - 1) // ring) * ring)
@@ -698,7 +700,7 @@ def main():
     ap.add_argument("--min-seconds", type=float, default=0.25, help="floor on the timed region of `value`")
     ap.add_argument("--e2e-steps", type=int, default=2000, help="cap on the steps of an e2e (host-buffer) loop")
     ap.add_argument("--e2e-batches", type=int, default=4, help="independent env parts of the e2e (host-buffer) loops")
-    ap.add_argument("--groups", type=int, default=0, help="independent env groups, each a policy->step chain on its own stream (0: 4 for teams <= 64, else 1)")
+    ap.add_argument("--groups", type=int, default=0, help="independent env groups, each a policy->step chain on its own stream (0: 4 or 8 for teams <= 64, else 1)")
     ap.add_argument("--ppo-envs", type=int, default=128, help="envs per GPU of the c5_ppo sub-record")
     ap.add_argument("--no-sweep", action="store_true", help="skip the configs sweep and the c5_ppo sub-record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
