@@ -61,7 +61,7 @@ class FusedCommNets:
     """policy + critic of the Comm-DP runners on cm_ppo_net.  ``chunk_rows``: agent rows of activations kept in the workspace
     at a time (the kernels walk a minibatch in chunks; gradients add up)."""
 
-    def __init__(self, policy, critic, opt, baseline_opt, ent_coeff, clip_range, chunk_rows=262144):
+    def __init__(self, policy, critic, opt, baseline_opt, ent_coeff, clip_range, chunk_rows=524288):
         self.policy, self.critic = policy, critic
         self.device = policy.device
         # L = layers of the communication masks in the batch (the critic's; the Obs-DP policy has none of its own)
@@ -75,7 +75,11 @@ class FusedCommNets:
         self.pol_desc = N.NetDesc(N.NET_POLICY_DEC if self.dec else N.NET_POLICY, self.n, self.D, policy.n_gcn_layers, int(policy.residual), float(ent_coeff),
                                   1.0 - float(clip_range), 1.0 + float(clip_range))
         self.cri_desc = N.NetDesc(N.NET_CRITIC, self.n, self.D, len(critic.gcn_layers), int(critic.residual), 0.0, 0.0, 0.0)
+        import os
+        chunk_rows = int(os.environ.get("CM_PPO_CHUNK_ROWS", chunk_rows))          # (experiments)
         self.chunk_steps = max(1, int(chunk_rows) // self.n)
+        if self.n > 64 and self.chunk_steps > 148:        # one env per CTA in the n x n kernels: whole waves of the 148 SMs
+            self.chunk_steps = self.chunk_steps // 148 * 148
         self._ws = None
         self._scalar = torch.zeros(2, dtype=torch.float32, device=self.device)
 
