@@ -376,6 +376,32 @@ __device__ __forceinline__ void strip_agg4(const float *Cs, int CP, const float 
         }
 }
 
+// The warp's coefficient strip Cs [8][CP] (rows j0 .. j0 + nr - 1 of an env's n x n matrix) -> the env's TRANSPOSED scratch:
+// CTenv[k][j0 + i] = Cs[i][k].  One lane per key writes the strip's eight values of its key as two 128-bit stores (a whole
+// 32-byte sector) — eight 4-byte stores from eight instructions to the same sector cost the L2 eight partial writes.
+template <int KT>
+__device__ __forceinline__ void store_strip_transposed(float *__restrict__ CTenv, const float *Cs, int CP, int n, int j0, int nr, int lane)
+{
+    const bool vec = nr == 8 && (n & 3) == 0;          // (j0 is a multiple of 8, the scratch 16-byte aligned: rows of n floats stay aligned)
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+        const int k = lane + 32 * j;
+        if (k < n) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = Cs[i * CP + k];
+            float *dst = CTenv + (int64_t)k * n + j0;
+            if (vec) {
+                *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (i < nr) dst[i] = v[i];
+            }
+        }
+    }
+}
+
 // rows [row0, row0 + rows) x 64 floats of a global [.][64] array -> shared memory (pitch kNP); optional second array
 // and the product form dZ = a (1 - b^2)
 __device__ __forceinline__ void load_rows64(float *dst, const float *__restrict__ src, int64_t row0, int rows, int tid)
@@ -545,6 +571,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 
             const int64_t s = eb.s0 + g;
             float acc[8][KT];
             strip_dots<KT>(dZs + (g * n + j0) * kNP, nr, Vs + g * n * kNP, n, lane, acc);
+            __syncwarp();
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (i >= nr) continue;                        // (warp-uniform)
@@ -572,10 +599,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 
                         const float dm = on[j] ? (acc[i][j] - dot) / sum : 0.0f;
                         float *p = dM + row * n + k;
                         *p = dm_accumulate ? *p + dm : dm;
-                        CT[(s * n + k) * n + j0 + i] = a[j];
+                        Cs[i * CP + k] = a[j];
                     }
                 }
             }
+            __syncwarp();
+            store_strip_transposed<KT>(CT + s * n * n, Cs, CP, n, j0, nr, lane);      // A~^T for the second pass
         }
         __syncthreads();
         for (int st = warp; st < eb.ne * ns; st += THREADS / 32) {          // pass 2: key strips
@@ -645,10 +674,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 
                     const int k = lane + 32 * j;
                     const float ds = i < nr ? m[j] * (d[j] - dot) : 0.0f;
                     Cs[i * CP + k] = ds;
-                    if (i < nr && k < n) CT[(s * n + k) * n + j0 + i] = ds;
                 }
             }
             __syncwarp();
+            store_strip_transposed<KT>(CT + s * n * n, Cs, CP, n, j0, nr, lane);      // dS^T for the second pass
             float res[4][4];
             strip_agg4(Cs, CP, Es + g * n * kNP, n, lane, res);
 #pragma unroll
