@@ -427,6 +427,43 @@ __device__ __forceinline__ uint32_t mask_word(const uint32_t *__restrict__ bits,
     return bits ? (j < W ? bits[row * W + j] : 0u) : 0xFFFFFFFFu;
 }
 
+// The masked, renormalised attention rows of a strip, A~ = M . adj . chan_l / (rowsum + 1e-12)  ->  the warp's Cs [8][CP]
+// (zeros beyond n and in the rows >= nr).  The strip's 8 x n values of M are requested in ONE batch before any arithmetic (one
+// global round trip per strip; the mask words follow while they are in flight).  sums[i] = rowsum + 1e-12; bit j of on[i]: this
+// lane's key lane + 32 j is a neighbour of row i.
+template <int KT>
+__device__ __forceinline__ void strip_coef(float *Cs, int CP, float (&sums)[8], uint32_t (&on)[8], const float *__restrict__ M,
+                                           const uint32_t *__restrict__ adj, const uint32_t *__restrict__ chan, int64_t s, int L, int l,
+                                           int n, int W, int j0, int nr, int lane)
+{
+    float m[8][KT];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t row = s * n + j0 + min(i, nr - 1);
+#pragma unroll
+        for (int j = 0; j < KT; ++j) m[i][j] = lane + 32 * j < n ? M[row * n + lane + 32 * j] : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int ri = j0 + min(i, nr - 1);
+        uint32_t bits = 0u;
+        float sum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+            const uint32_t wd = mask_word(adj, s * n + ri, W, j) & mask_word(chan, (s * L + l) * n + ri, W, j);
+            const bool o = lane + 32 * j < n && ((wd >> lane) & 1u);
+            bits |= (o ? 1u : 0u) << j;
+            m[i][j] = o ? m[i][j] : 0.0f;
+            sum += m[i][j];
+        }
+        sum = warp_sumf(sum) + 1e-12f;
+        sums[i] = sum;
+        on[i] = bits;
+#pragma unroll
+        for (int j = 0; j < KT; ++j) Cs[i * CP + lane + 32 * j] = i < nr ? m[i][j] / sum : 0.0f;
+    }
+}
+
 // M[s][i][:] = softmax_k < Q[s][i], E[s][k] >
 template <int KT, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 1) net_scores_kernel(const float *__restrict__ Q, const float *__restrict__ E,
@@ -492,21 +529,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 
             const int g = st / ns, j0 = (st - g * ns) * 8, nr = min(8, n - j0);
             const int64_t s = eb.s0 + g;
             __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float a[KT];
-                float sum = 0.0f;
-                const int64_t row = s * n + j0 + min(i, nr - 1);
-#pragma unroll
-                for (int j = 0; j < KT; ++j) {
-                    const int k = lane + 32 * j;
-                    const uint32_t wd = mask_word(adj, row, W, j) & mask_word(chan, (s * L + l) * n + j0 + min(i, nr - 1), W, j);
-                    a[j] = (k < n && ((wd >> lane) & 1u)) ? M[row * n + k] : 0.0f;
-                    sum += a[j];
-                }
-                sum = warp_sumf(sum) + 1e-12f;
-#pragma unroll
-                for (int j = 0; j < KT; ++j) Cs[i * CP + lane + 32 * j] = a[j] / sum;
+            {
+                float sums[8];
+                uint32_t on[8];
+                strip_coef<KT>(Cs, CP, sums, on, M, adj, chan, s, L, l, n, W, j0, nr, lane);
             }
             __syncwarp();
             float res[4][4];
@@ -530,14 +556,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 
 }
 
 // Backward of one graph-convolution layer's aggregation.  dZ = dH (1 - H^2);  dV = A~^T dZ;  db += sum dZ;
-// dA~ = dZ V^T;  dM (+)= mask (dA~ - <dA~, A~>) / (rowsum + 1e-12).  A~ strips are parked TRANSPOSED in CT so that the
+// dA~ = dZ V^T;  dM_l = mask (dA~ - <dA~, A~>) / (rowsum + 1e-12) (this layer's own array).  A~ strips are parked TRANSPOSED in CT so that the
 // second pass (key strips) reads contiguous coefficient rows.
 template <int KT, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 1) net_agg_bwd_kernel(const float *__restrict__ M, const uint32_t *__restrict__ adj,
                                                                   const uint32_t *__restrict__ chan, int L, int l,
                                                                   const float *__restrict__ V, const float *__restrict__ H,
                                                                   const float *__restrict__ dH, float *__restrict__ dV,
-                                                                  float *__restrict__ dM, int dm_accumulate, float *__restrict__ CT,
+                                                                  float *__restrict__ dM, float *__restrict__ CT,
                                                                   float *__restrict__ db, int n, int G, int cap, int64_t S)
 {
     extern __shared__ float4 smem4[];
@@ -569,41 +595,27 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 
         for (int st = warp; st < eb.ne * ns; st += THREADS / 32) {          // pass 1: query strips
             const int g = st / ns, j0 = (st - g * ns) * 8, nr = min(8, n - j0);
             const int64_t s = eb.s0 + g;
+            // A~ first (its global loads go out in one batch), then dA~ = dZ V^T, then dM of THIS layer (no read-modify-write: the
+            // layers' contributions are summed by net_softmax_bwd)
+            float sums[8];
+            uint32_t on[8];
+            __syncwarp();
+            strip_coef<KT>(Cs, CP, sums, on, M, adj, chan, s, L, l, n, W, j0, nr, lane);
             float acc[8][KT];
             strip_dots<KT>(dZs + (g * n + j0) * kNP, nr, Vs + g * n * kNP, n, lane, acc);
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (i >= nr) continue;                        // (warp-uniform)
-                const int64_t row = s * n + j0 + i;
-                float a[KT];
-                bool on[KT];
-                float sum = 0.0f;
-#pragma unroll
-                for (int j = 0; j < KT; ++j) {
-                    const int k = lane + 32 * j;
-                    const uint32_t wd = mask_word(adj, row, W, j) & mask_word(chan, (s * L + l) * n + j0 + i, W, j);
-                    on[j] = k < n && ((wd >> lane) & 1u);
-                    a[j] = on[j] ? M[row * n + k] : 0.0f;
-                    sum += a[j];
-                }
-                sum = warp_sumf(sum) + 1e-12f;
                 float dot = 0.0f;
 #pragma unroll
-                for (int j = 0; j < KT; ++j) { a[j] = a[j] / sum; dot = fmaf(acc[i][j], a[j], dot); }
+                for (int j = 0; j < KT; ++j) dot = fmaf(acc[i][j], Cs[i * CP + lane + 32 * j], dot);
                 dot = warp_sumf(dot);
+                float *drow = dM + (s * n + j0 + i) * (int64_t)n;
 #pragma unroll
-                for (int j = 0; j < KT; ++j) {
-                    const int k = lane + 32 * j;
-                    if (k < n) {
-                        const float dm = on[j] ? (acc[i][j] - dot) / sum : 0.0f;
-                        float *p = dM + row * n + k;
-                        *p = dm_accumulate ? *p + dm : dm;
-                        Cs[i * CP + k] = a[j];
-                    }
-                }
+                for (int j = 0; j < KT; ++j)
+                    if (lane + 32 * j < n) drow[lane + 32 * j] = ((on[i] >> j) & 1u) ? (acc[i][j] - dot) / sums[i] : 0.0f;
             }
-            __syncwarp();
             store_strip_transposed<KT>(CT + s * n * n, Cs, CP, n, j0, nr, lane);      // A~^T for the second pass
         }
         __syncthreads();
@@ -635,6 +647,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 
 // dS = M (dM - <dM, M>) per query row;  dQ = dS E;  dE += dS^T Q
 template <int KT, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 1) net_softmax_bwd_kernel(const float *__restrict__ M, const float *__restrict__ dM,
+                                                                      int L, int64_t dm_stride,
                                                                       const float *__restrict__ E, const float *__restrict__ Q,
                                                                       float *__restrict__ dQ, float *__restrict__ dE,
                                                                       float *__restrict__ CT, int n, int G, int cap, int64_t S)
@@ -657,23 +670,33 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (KT <= 2 ? 3 : 2) : 
             const int64_t s = eb.s0 + g;
             __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int64_t row = s * n + j0 + min(i, nr - 1);
-                float m[KT], d[KT];
-                float dot = 0.0f;
+            for (int h = 0; h < 2; ++h) {                    // four rows at a time: their loads (M and the layers' dM) in one batch
+                float m[4][KT], d[4][KT];
 #pragma unroll
-                for (int j = 0; j < KT; ++j) {
-                    const int k = lane + 32 * j;
-                    m[j] = k < n ? M[row * n + k] : 0.0f;
-                    d[j] = k < n ? dM[row * n + k] : 0.0f;
-                    dot = fmaf(m[j], d[j], dot);
+                for (int r = 0; r < 4; ++r) {
+                    const int64_t row = s * n + j0 + min(4 * h + r, nr - 1);
+#pragma unroll
+                    for (int j = 0; j < KT; ++j) {
+                        const int k = lane + 32 * j;
+                        m[r][j] = k < n ? M[row * n + k] : 0.0f;
+                        d[r][j] = k < n ? dM[row * n + k] : 0.0f;
+                    }
+                    for (int ll = 1; ll < L; ++ll)
+#pragma unroll
+                        for (int j = 0; j < KT; ++j) {
+                            const int k = lane + 32 * j;
+                            if (k < n) d[r][j] += dM[ll * dm_stride + row * n + k];
+                        }
                 }
-                dot = warp_sumf(dot);
 #pragma unroll
-                for (int j = 0; j < KT; ++j) {
-                    const int k = lane + 32 * j;
-                    const float ds = i < nr ? m[j] * (d[j] - dot) : 0.0f;
-                    Cs[i * CP + k] = ds;
+                for (int r = 0; r < 4; ++r) {
+                    const int i = 4 * h + r;
+                    float dot = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < KT; ++j) dot = fmaf(m[r][j], d[r][j], dot);
+                    dot = warp_sumf(dot);
+#pragma unroll
+                    for (int j = 0; j < KT; ++j) Cs[i * CP + lane + 32 * j] = i < nr ? m[r][j] * (d[r][j] - dot) : 0.0f;
                 }
             }
             __syncwarp();
@@ -851,7 +874,7 @@ __global__ void __launch_bounds__(kSmallRows) net_small_agg_bwd_kernel(const flo
                                                                        const uint32_t *__restrict__ chan, int L, int l,
                                                                        const float *__restrict__ V, const float *__restrict__ H,
                                                                        const float *__restrict__ dH, float *__restrict__ dV,
-                                                                       float *__restrict__ dM, int dm_accumulate, float *__restrict__ db,
+                                                                       float *__restrict__ dM, float *__restrict__ db,
                                                                        int n, int G, int64_t S)
 {
     extern __shared__ float4 smem4[];
@@ -892,8 +915,7 @@ __global__ void __launch_bounds__(kSmallRows) net_small_agg_bwd_kernel(const flo
             for (int k = 0; k < kSmallN; ++k)
                 if (k < n) {
                     const float dm = ((wd >> k) & 1u) ? (da[k] - dot) / sum : 0.0f;
-                    float *p = dM + row * n + k;
-                    *p = dm_accumulate ? *p + dm : dm;
+                    dM[row * n + k] = dm;                 // (this layer's own array)
                 }
         }
         __syncthreads();
@@ -913,10 +935,10 @@ __global__ void __launch_bounds__(kSmallRows) net_small_agg_bwd_kernel(const flo
     if (db && tid < 64) atomicAdd(db + tid, bacc);
 }
 
-__global__ void __launch_bounds__(kSmallRows) net_small_softmax_bwd_kernel(const float *__restrict__ M, const float *__restrict__ dM,
-                                                                           const float *__restrict__ E, const float *__restrict__ Q,
-                                                                           float *__restrict__ dQ, float *__restrict__ dE, int n, int G,
-                                                                           int64_t S)
+__global__ void __launch_bounds__(kSmallRows) net_small_softmax_bwd_kernel(const float *__restrict__ M, const float *__restrict__ dM, int L,
+                                                                           int64_t dm_stride, const float *__restrict__ E,
+                                                                           const float *__restrict__ Q, float *__restrict__ dQ,
+                                                                           float *__restrict__ dE, int n, int G, int64_t S)
 {
     extern __shared__ float4 smem4[];
     float *Es = reinterpret_cast<float *>(smem4), *Qs = Es + kSmallRows * kNP, *Ds = Qs + kSmallRows * kNP;
@@ -937,7 +959,8 @@ __global__ void __launch_bounds__(kSmallRows) net_small_softmax_bwd_kernel(const
 #pragma unroll
             for (int k = 0; k < kSmallN; ++k) {
                 m[k] = k < n ? M[row * n + k] : 0.0f;
-                ds[k] = k < n ? dM[row * n + k] : 0.0f;
+                ds[k] = 0.0f;
+                for (int ll = 0; ll < L; ++ll) if (k < n) ds[k] += dM[ll * dm_stride + row * n + k];
                 dot = fmaf(m[k], ds[k], dot);
             }
 #pragma unroll
@@ -1394,7 +1417,7 @@ static cudaError_t agg_fwd_t(const EnvCall &c, int l, const float *M, const floa
 // coefficient strips of 16 warps still fit
 template <int KT>
 static cudaError_t agg_bwd_t(const EnvCall &c, int l, const float *M, const float *V, const float *H, const float *dH, float *dV,
-                             float *dM, int dm_acc, float *CT, float *db)
+                             float *dM, float *CT, float *db)
 {
     const EnvGeom g = env_geom(c.n);
     const size_t rows = 2 * (size_t)g.cap * kNP;
@@ -1403,16 +1426,16 @@ static cudaError_t agg_bwd_t(const EnvCall &c, int l, const float *M, const floa
     int grid;
     if (wide) {
         NET_TRY(env_launch_dims(net_agg_bwd_kernel<KT, 512>, 512, smem, c, &grid));
-        net_agg_bwd_kernel<KT, 512><<<grid, 512, smem, c.st>>>(M, c.adj, c.chan, c.L, l, V, H, dH, dV, dM, dm_acc, CT, db, c.n, g.G, g.cap, c.S);
+        net_agg_bwd_kernel<KT, 512><<<grid, 512, smem, c.st>>>(M, c.adj, c.chan, c.L, l, V, H, dH, dV, dM, CT, db, c.n, g.G, g.cap, c.S);
     } else {
         NET_TRY(env_launch_dims(net_agg_bwd_kernel<KT, 256>, 256, smem, c, &grid));
-        net_agg_bwd_kernel<KT, 256><<<grid, 256, smem, c.st>>>(M, c.adj, c.chan, c.L, l, V, H, dH, dV, dM, dm_acc, CT, db, c.n, g.G, g.cap, c.S);
+        net_agg_bwd_kernel<KT, 256><<<grid, 256, smem, c.st>>>(M, c.adj, c.chan, c.L, l, V, H, dH, dV, dM, CT, db, c.n, g.G, g.cap, c.S);
     }
     return cudaGetLastError();
 }
 template <int KT>
-static cudaError_t softmax_bwd_t(const EnvCall &c, const float *M, const float *dM, const float *E, const float *Q, float *dQ, float *dE,
-                                 float *CT)
+static cudaError_t softmax_bwd_t(const EnvCall &c, const float *M, const float *dM, int64_t dm_stride, const float *E, const float *Q,
+                                 float *dQ, float *dE, float *CT)
 {
     const EnvGeom g = env_geom(c.n);
     const size_t rows = 2 * (size_t)g.cap * kNP;
@@ -1421,10 +1444,10 @@ static cudaError_t softmax_bwd_t(const EnvCall &c, const float *M, const float *
     int grid;
     if (wide) {
         NET_TRY(env_launch_dims(net_softmax_bwd_kernel<KT, 512>, 512, smem, c, &grid));
-        net_softmax_bwd_kernel<KT, 512><<<grid, 512, smem, c.st>>>(M, dM, E, Q, dQ, dE, CT, c.n, g.G, g.cap, c.S);
+        net_softmax_bwd_kernel<KT, 512><<<grid, 512, smem, c.st>>>(M, dM, c.L, dm_stride, E, Q, dQ, dE, CT, c.n, g.G, g.cap, c.S);
     } else {
         NET_TRY(env_launch_dims(net_softmax_bwd_kernel<KT, 256>, 256, smem, c, &grid));
-        net_softmax_bwd_kernel<KT, 256><<<grid, 256, smem, c.st>>>(M, dM, E, Q, dQ, dE, CT, c.n, g.G, g.cap, c.S);
+        net_softmax_bwd_kernel<KT, 256><<<grid, 256, smem, c.st>>>(M, dM, c.L, dm_stride, E, Q, dQ, dE, CT, c.n, g.G, g.cap, c.S);
     }
     return cudaGetLastError();
 }
@@ -1465,25 +1488,25 @@ static cudaError_t agg_fwd(const EnvCall &c, int l, const float *M, const float 
     KT_DISPATCH(agg_fwd_t, c, l, M, V, bias, H, res, Xout);
 }
 static cudaError_t agg_bwd(const EnvCall &c, int l, const float *M, const float *V, const float *H, const float *dH, float *dV, float *dM,
-                           int dm_acc, float *CT, float *db)
+                           float *CT, float *db)
 {
     if (c.n <= kSmallN) {
         NET_TRY(set_smem(net_small_agg_bwd_kernel, kSmallBwdSmem));
-        net_small_agg_bwd_kernel<<<small_grid(c, 3), kSmallRows, kSmallBwdSmem, c.st>>>(M, c.adj, c.chan, c.L, l, V, H, dH, dV, dM, dm_acc, db, c.n,
+        net_small_agg_bwd_kernel<<<small_grid(c, 3), kSmallRows, kSmallBwdSmem, c.st>>>(M, c.adj, c.chan, c.L, l, V, H, dH, dV, dM, db, c.n,
                                                                              kSmallRows / c.n, c.S);
         return cudaGetLastError();
     }
-    KT_DISPATCH(agg_bwd_t, c, l, M, V, H, dH, dV, dM, dm_acc, CT, db);
+    KT_DISPATCH(agg_bwd_t, c, l, M, V, H, dH, dV, dM, CT, db);
 }
-static cudaError_t softmax_bwd(const EnvCall &c, const float *M, const float *dM, const float *E, const float *Q, float *dQ, float *dE,
-                               float *CT)
+static cudaError_t softmax_bwd(const EnvCall &c, const float *M, const float *dM, int64_t dm_stride, const float *E, const float *Q,
+                               float *dQ, float *dE, float *CT)
 {
     if (c.n <= kSmallN) {
         NET_TRY(set_smem(net_small_softmax_bwd_kernel, kSmallBwdSmem));
-        net_small_softmax_bwd_kernel<<<small_grid(c, 3), kSmallRows, kSmallBwdSmem, c.st>>>(M, dM, E, Q, dQ, dE, c.n, kSmallRows / c.n, c.S);
+        net_small_softmax_bwd_kernel<<<small_grid(c, 3), kSmallRows, kSmallBwdSmem, c.st>>>(M, dM, c.L, dm_stride, E, Q, dQ, dE, c.n, kSmallRows / c.n, c.S);
         return cudaGetLastError();
     }
-    KT_DISPATCH(softmax_bwd_t, c, M, dM, E, Q, dQ, dE, CT);
+    KT_DISPATCH(softmax_bwd_t, c, M, dM, dm_stride, E, Q, dQ, dE, CT);
 }
 
 // workspace of one chunk of `steps` env steps (floats)
@@ -1495,7 +1518,7 @@ static size_t ws_floats_per_step(int n, int L, bool backward)
 {
     size_t rows = 128 + 64 + 64 + (size_t)L * 128 + 64 + 128 + 64 + 32;
     size_t sq = 1;
-    if (backward) { rows += 32 + 3 * 64 + 128; sq += 2; }
+    if (backward) { rows += 32 + 3 * 64 + 128; sq += 1 + (size_t)L; }          // dM: one n x n array per layer
     return (size_t)n * rows + sq * (size_t)n * n;
 }
 static NetWs carve(float *p, int n, int L, int64_t steps, bool backward)
@@ -1509,7 +1532,7 @@ static NetWs carve(float *p, int n, int L, int64_t steps, bool backward)
     w.t32 = w.t64a = w.t64b = w.t64c = w.t128 = w.dM = w.CT = nullptr;
     if (backward) {
         w.t32 = take(R * 32); w.t64a = take(R * 64); w.t64b = take(R * 64); w.t64c = take(R * 64); w.t128 = take(R * 128);
-        w.dM = take(S2); w.CT = take(S2);
+        w.dM = take(S2 * L); w.CT = take(S2);
     }
     return w;
 }
@@ -1538,6 +1561,7 @@ static cudaError_t trunk_bwd(const cm_net_desc &d, const EnvCall &c, const float
 {
     const int64_t R = c.S * d.n_agents;
     const int L = d.n_layers;
+    const size_t S2 = (size_t)c.S * d.n_agents * d.n_agents;          // layer l's dM array starts at w.dM + l * S2 (scalar accesses only)
     float *dE = w.t64b;                       // with the residual connection the gradient of X is the first term of dE
     const float *dHl = w.t64b;
     bool dE_init = d.residual != 0;
@@ -1546,7 +1570,7 @@ static cudaError_t trunk_bwd(const cm_net_desc &d, const EnvCall &c, const float
         dHl = w.t64a;
     }
     for (int l = L - 1; l >= 0; --l) {
-        NET_TRY(agg_bwd(c, l, w.M, w.V[l], w.H[l], dHl, w.t64c, w.dM, l != L - 1, w.CT, grad + o.gcn_b + l * kE));
+        NET_TRY(agg_bwd(c, l, w.M, w.V[l], w.H[l], dHl, w.t64c, w.dM + (size_t)l * S2, w.CT, grad + o.gcn_b + l * kE));
         const float *Hin = l == 0 ? w.E : w.H[l - 1];
         if (l == 0) {
             NET_TRY(dense_bwd(w.t64c, Hin, 64, wts + o.gcn_w, dE, dE_init ? 1 : 0, 0, grad + o.gcn_w, nullptr, R, 64, 64, c.st));
@@ -1557,7 +1581,7 @@ static cudaError_t trunk_bwd(const cm_net_desc &d, const EnvCall &c, const float
             dHl = w.t64a;
         }
     }
-    NET_TRY(softmax_bwd(c, w.M, w.dM, w.E, w.Q, w.t64c, dE, w.CT));
+    NET_TRY(softmax_bwd(c, w.M, w.dM, (int64_t)S2, w.E, w.Q, w.t64c, dE, w.CT));
     // the last term of dE (through Q = E W_a); the same pass turns the sum into dZ of the embedding layer: dE (1 - E^2)
     NET_TRY(dense_bwd(w.t64c, w.E, 64, wts + o.att_w, dE, 1, 1, grad + o.att_w, nullptr, R, 64, 64, c.st));
     NET_TRY(dense_bwd(dE, w.h1, 128, wts + o.enc_w2, w.t128, 0, 1, grad + o.enc_w2, grad + o.enc_b2, R, 128, 64, c.st));
