@@ -13,6 +13,7 @@
 // Semantics follow the reference exactly (file:line cited at each step); the data model does not.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "commarl_b200.h"
 #include "common.cuh"
@@ -26,7 +27,10 @@ typedef unsigned long long u64;
 #ifndef CM_ENV_PARALLEL_MOVES
 #define CM_ENV_PARALLEL_MOVES 0
 #endif
-static constexpr int kWarpsPerCta = 8;
+#ifndef CM_ENV_WARPS
+#define CM_ENV_WARPS 8
+#endif
+static constexpr int kWarpsPerCta = CM_ENV_WARPS;   // 24 warps per SM either way (80 registers)
 // per-CTA constants in shared memory: wall rows [64] u64 | k / n as IEEE doubles for k = 0 .. n (<= 256) [257] f64
 static constexpr int kConstBytes = 64 * 8 + 264 * 8;
 
@@ -65,7 +69,12 @@ struct Scratch {
 
 __host__ __device__ inline int env_warp_bytes(int n_pad, int p_pad, int G)
 {
-    return 5 * G * 8 + 6 * n_pad * 4 + 3 * n_pad * 2 + 3 * p_pad * 2 + p_pad + n_pad + p_pad + p_pad + p_pad + (n_pad > p_pad ? n_pad : p_pad);
+    const int base = 2 * G * 8 + 6 * n_pad * 4 + n_pad * 2 + p_pad * 2 + p_pad + n_pad + p_pad + p_pad;
+#if CM_ENV_PARALLEL_MOVES
+    return base + 3 * G * 8 + 2 * n_pad * 2 + 2 * p_pad * 2 + p_pad + (n_pad > p_pad ? n_pad : p_pad);
+#else
+    return base;                                   // the scratch of the parallel move resolution is not carved out
+#endif
 }
 
 __device__ __forceinline__ Scratch carve(unsigned char *base, int n_pad, int p_pad, int G)
@@ -73,6 +82,7 @@ __device__ __forceinline__ Scratch carve(unsigned char *base, int n_pad, int p_p
     Scratch s;
     s.occA = reinterpret_cast<u64 *>(base);
     s.occB = s.occA + G;
+#if CM_ENV_PARALLEL_MOVES
     s.x1 = s.occB + G;
     s.x2 = s.x1 + G;
     s.x3 = s.x2 + G;
@@ -84,11 +94,23 @@ __device__ __forceinline__ Scratch carve(unsigned char *base, int n_pad, int p_p
     s.tgtP = s.posP + p_pad;
     s.finP = s.tgtP + p_pad;
     s.alive = reinterpret_cast<uint8_t *>(s.finP + p_pad);
+#else
+    s.x1 = s.x2 = s.x3 = nullptr;
+    s.tgtA = s.finA = s.tgtP = s.finP = nullptr;
+    s.win = reinterpret_cast<uint32_t *>(s.occB + G);
+    s.posA = reinterpret_cast<uint16_t *>(s.win + 6 * n_pad);
+    s.posP = s.posA + n_pad;
+    s.alive = reinterpret_cast<uint8_t *>(s.posP + p_pad);
+#endif
     s.act = reinterpret_cast<int8_t *>(s.alive + p_pad);
     s.kcnt = reinterpret_cast<uint8_t *>(s.act + n_pad);
     s.mv = reinterpret_cast<int8_t *>(s.kcnt + p_pad);
+#if CM_ENV_PARALLEL_MOVES
     s.alvF = reinterpret_cast<uint8_t *>(s.mv + p_pad);
     s.slow = s.alvF + p_pad;
+#else
+    s.alvF = s.slow = nullptr;
+#endif
     return s;
 }
 
@@ -659,7 +681,7 @@ __device__ __forceinline__ int resolve_preys(const Scratch &S, const Grp &G, int
 // descriptor fields are overwritten with the template constants and the branches on them fold after inlining.
 // kChan: 0 = FC / FL (told apart at run time), CM_CH_IID, CM_CH_GE.
 template <int kScen, int kChan, bool kInj>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) env_kernel(const EnvArgs A_in)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 24 / kWarpsPerCta) env_kernel(const EnvArgs A_in)
 {
     EnvArgs A = A_in;
     A.d.scenario = kScen;
@@ -1085,7 +1107,17 @@ static int launch(const cm_env_desc *d, const cm_env_state *s, const cm_step_io 
     A.p_pad = (d->n_preys + 7) & ~7;
     A.warp_bytes = (env_warp_bytes(A.n_pad, A.p_pad, d->grid) + 15) & ~15;
     const int team = d->n_agents > d->n_preys ? d->n_agents : d->n_preys;
-    A.group = team <= 4 ? 4 : (team <= 8 ? 8 : (team <= 16 ? 16 : 32));
+    // Lanes per env.  Small teams: the smallest power of two >= the team.  Larger teams: every loop strides by the group size, so
+    // a group may be SMALLER than the team — the lane-parallel loops then cost the same warp instructions per env, while the
+    // order-dependent loops of the group's lane 0 (45 % of the warp instructions at n = 32 with one env per warp) are shared
+    // by the 2 or 4 envs of a warp.  Measured at C3 (n = 32): 0.085 / 0.067 / 0.056 ms per 8192 envs with 32 / 16 / 8 lanes.
+    // The smallest group whose shared memory still lets three CTAs share an SM wins (C5, n = 200: 32 lanes).
+    A.group = team <= 4 ? 4 : 8;
+    while (A.group < 32 && kConstBytes + (size_t)kWarpsPerCta * (32 / A.group) * A.warp_bytes > (size_t)225 * 1024 * kWarpsPerCta / 24) A.group *= 2;
+    {   // experiments only: CM_ENV_GROUP=4|8|16|32 overrides the lanes per env
+        static const int forced = [] { const char *e = getenv("CM_ENV_GROUP"); return e ? atoi(e) : 0; }();
+        if (forced == 4 || forced == 8 || forced == 16 || forced == 32) A.group = forced;
+    }
     const int envs_per_cta = kWarpsPerCta * (32 / A.group);
     const size_t smem = kConstBytes + (size_t)envs_per_cta * A.warp_bytes;
     // launch geometry is cached per (device, smem) so that steady-state calls issue nothing but the launch
