@@ -74,6 +74,16 @@ __device__ __forceinline__ void split16(float x, __half &hi, __half &lo)
     hi = __float2half_rn(x);
     lo = __float2half_rn((x - __half2float(hi)) * 4096.0f);
 }
+// the same for two values at once: ONE packed conversion per pair (the scalar form costs a conversion and a byte permute
+// per value — the conversions of the activations are the largest instruction class of the epilogues)
+__device__ __forceinline__ void split16x2(float x0, float x1, uint32_t &hi, uint32_t &lo)
+{
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn((x0 - hf.x) * 4096.0f, (x1 - hf.y) * 4096.0f);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
 
 // write CW (8 or 16) consecutive columns, starting at local column c0 (a multiple of 8) of a Kp-wide panel, of row `row`
 // as the next A operand: hi block, then the lo block 128 * Kp halves further
@@ -83,12 +93,14 @@ __device__ __forceinline__ void write_act(unsigned char *act, int Kp, int row, i
     const uint32_t lo_off = (uint32_t)kTcRows * Kp * 2;
 #pragma unroll
     for (int g = 0; g < CW; g += 8) {
-        __align__(16) __half h[8], l[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) split16(v[g + i], h[i], l[i]);
+        uint4 h, l;
+        split16x2(v[g + 0], v[g + 1], h.x, l.x);
+        split16x2(v[g + 2], v[g + 3], h.y, l.y);
+        split16x2(v[g + 4], v[g + 5], h.z, l.z);
+        split16x2(v[g + 6], v[g + 7], h.w, l.w);
         const uint32_t off = canon_off16(row, c0 + g, Kp);
-        *reinterpret_cast<uint4 *>(act + off) = *reinterpret_cast<const uint4 *>(h);
-        *reinterpret_cast<uint4 *>(act + lo_off + off) = *reinterpret_cast<const uint4 *>(l);
+        *reinterpret_cast<uint4 *>(act + off) = h;
+        *reinterpret_cast<uint4 *>(act + lo_off + off) = l;
     }
 }
 
@@ -96,21 +108,27 @@ __device__ __forceinline__ void write_act(unsigned char *act, int Kp, int row, i
 // hi = fp16(x'), lo = fp16(x' - hi); the power-of-two scale s keeps lo out of the fp16 subnormals (values: s = 2^6, attention
 // weights: s = 2^10; the product is rescaled by 2^-16 in the epilogue).  Same chunked layout as write_act.
 static constexpr float kVScale = 64.0f, kPScale = 1024.0f, kPVUnscale = 1.0f / 65536.0f;
+__device__ __forceinline__ void split_unscaled_x2(float x0, float x1, uint32_t &hi, uint32_t &lo)
+{
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
 template <int CW>
 __device__ __forceinline__ void write_unscaled(unsigned char *buf, int Kp, uint32_t lo_off, int row, int c0, const float (&v)[CW], float scale)
 {
 #pragma unroll
     for (int g = 0; g < CW; g += 8) {
-        __align__(16) __half h[8], l[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float x = v[g + i] * scale;
-            h[i] = __float2half_rn(x);
-            l[i] = __float2half_rn(x - __half2float(h[i]));
-        }
+        uint4 h, l;
+        split_unscaled_x2(v[g + 0] * scale, v[g + 1] * scale, h.x, l.x);
+        split_unscaled_x2(v[g + 2] * scale, v[g + 3] * scale, h.y, l.y);
+        split_unscaled_x2(v[g + 4] * scale, v[g + 5] * scale, h.z, l.z);
+        split_unscaled_x2(v[g + 6] * scale, v[g + 7] * scale, h.w, l.w);
         const uint32_t off = canon_off16(row, c0 + g, Kp);
-        *reinterpret_cast<uint4 *>(buf + off) = *reinterpret_cast<const uint4 *>(h);
-        *reinterpret_cast<uint4 *>(buf + lo_off + off) = *reinterpret_cast<const uint4 *>(l);
+        *reinterpret_cast<uint4 *>(buf + off) = h;
+        *reinterpret_cast<uint4 *>(buf + lo_off + off) = l;
     }
 }
 
@@ -389,11 +407,13 @@ __device__ __forceinline__ float masked_p_operand(uint32_t lane_addr, unsigned c
     tmem_ld8(lane_addr + kColM + (uint32_t)k0, *reinterpret_cast<float(*)[8]>(p));
     if constexpr (KT > 8) tmem_ld8(lane_addr + kColM + (uint32_t)k0 + 8u, *reinterpret_cast<float(*)[8]>(p + 8));
     tmem_ld_wait();
-    const uint32_t mbits = (k0 < 32 ? m0 : m1) >> (k0 & 31);
+    // the keys beyond the team are cleared in the mask word once (one bit test + select per key)
+    const int left = n - k0;
+    const uint32_t mbits = ((k0 < 32 ? m0 : m1) >> (k0 & 31)) & (left >= 32 ? 0xFFFFFFFFu : (left > 0 ? (1u << left) - 1u : 0u));
     float den = 0.0f;
 #pragma unroll
     for (int j = 0; j < KT; ++j) {
-        p[j] = (k0 + j < n && ((mbits >> j) & 1u)) ? p[j] : 0.0f;
+        p[j] = (mbits & (1u << j)) ? p[j] : 0.0f;
         den += p[j];
     }
     write_unscaled<KT>(pbuf, S, (uint32_t)kTcRows * S * 2, row, k0, p, kPScale);
@@ -720,7 +740,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                     // group with the scalar columns run the float path (no divergence inside a warp)
                     const int r = packed ? (e8 & (kTcRows - 1)) : (int)(((uint32_t)e8 * inv) >> 16);
                     const int k8 = packed ? (e8 >> 7) << 3 : (e8 - r * kg) << 3;
-                    __align__(16) __half h[8], l[8];
+                    uint4 hq, lq;
+                    uint32_t *hw = &hq.x, *lw = &lq.x;
                     int rr = r;                                  // row of the tile's observation block behind tile row r
                     if constexpr (kAttnTc) { const int e_ = r >> slog, i_ = r & (S - 1); rr = i_ < n ? e_ * n + i_ : rows; }
                     if (packed) {
@@ -730,7 +751,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                         if (kb + 8 <= nbits || kb >= Din) {
                             // window bits expand to 0 / 1: exact in fp16, no low-order part
                             const uint32_t b8 = (okr && kb < nbits) ? (wrow[kb >> 5] >> (kb & 31)) & 0xFFu : 0u;   // (8 | 32: one word)
-                            uint32_t *hw = reinterpret_cast<uint32_t *>(h), *lw = reinterpret_cast<uint32_t *>(l);
 #pragma unroll
                             for (int j2 = 0; j2 < 4; ++j2) {
                                 hw[j2] = (((b8 >> (2 * j2)) & 1u) ? 0x3C00u : 0u) | (((b8 >> (2 * j2 + 1)) & 1u) ? 0x3C000000u : 0u);
@@ -738,26 +758,30 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                             }
                         } else {
                             // the group with the scalar columns (float bits in words 3..5): split like any float
+                            float x[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const int k = kb + j;
-                                float x = 0.0f;
-                                if (okr && k < Din) x = k < nbits ? (float)((wrow[k >> 5] >> (k & 31)) & 1u) : __uint_as_float(wrow[3 + k - nbits]);
-                                split16(x, h[j], l[j]);
+                                x[j] = 0.0f;
+                                if (okr && k < Din) x[j] = k < nbits ? (float)((wrow[k >> 5] >> (k & 31)) & 1u) : __uint_as_float(wrow[3 + k - nbits]);
                             }
+#pragma unroll
+                            for (int j2 = 0; j2 < 4; ++j2) split16x2(x[2 * j2], x[2 * j2 + 1], hw[j2], lw[j2]);
                         }
                     } else {
+                        float x[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int k = kofs + k8 + j, i = rr * Din + k;
-                        float x = 0.0f;
-                        if (rr < rows && k < Din) x = i < ns ? stage[a + i] : __ldg(src + i);
-                        split16(x, h[j], l[j]);
-                    }
+                        for (int j = 0; j < 8; ++j) {
+                            const int k = kofs + k8 + j, i = rr * Din + k;
+                            x[j] = 0.0f;
+                            if (rr < rows && k < Din) x[j] = i < ns ? stage[a + i] : __ldg(src + i);
+                        }
+#pragma unroll
+                        for (int j2 = 0; j2 < 4; ++j2) split16x2(x[2 * j2], x[2 * j2 + 1], hw[j2], lw[j2]);
                     }
                     const uint32_t off = canon_off16(r, k8, Kp);
-                    *reinterpret_cast<uint4 *>(ACT + off) = *reinterpret_cast<const uint4 *>(h);
-                    *reinterpret_cast<uint4 *>(ACT + lo_off + off) = *reinterpret_cast<const uint4 *>(l);
+                    *reinterpret_cast<uint4 *>(ACT + off) = hq;
+                    *reinterpret_cast<uint4 *>(ACT + lo_off + off) = lq;
                 }
                 // packed rows: A_lo is zero before the K slice that holds the first scalar column
                 const int lo_from = packed ? max(0, min(Kp >> 4, (nbits - kofs) >> 4)) : 0;
@@ -889,18 +913,21 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
             });
             const float den = ((red[row] + red[kTPitch + row]) + red[2 * kTPitch + row]) + red[3 * kTPitch + row];
             CM_TP(3 + 4 * l);
-            {   // out^T (tensor memory: lane = column c, columns = tile rows) -> T[c][row] fp32, 16-byte chunks XOR-swizzled by c
+            {   // out^T (tensor memory: lane = column c, columns = tile rows) -> T[row][64] fp32, the 16-byte chunk index
+                // XOR-swizzled by (row & 7): a lane stores its 8 consecutive rows as scalars (the 16 lanes of a store hit 16
+                // different banks), a thread reads its 16 columns back as four 128-bit loads (8 lanes = 8 different chunks);
+                // row & 7 == j is a compile-time constant on the store side
                 const int c = 16 * quad + (lane & 15);
-                float4 *Tc = reinterpret_cast<float4 *>(KV + c * kTPitch);
+                float *Tw = KV + (32 * sub) * 64 + (c & 3);
+                const int cq = c >> 2;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float v8[8];
                     tmem_ld8(lane_addr + kR1 + (uint32_t)(32 * sub + 8 * i), v8);
                     tmem_ld_wait();
                     if (lane < 16) {
-                        const int rc = (32 * sub + 8 * i) >> 2;
-                        Tc[rc ^ (c & 7)] = make_float4(v8[0], v8[1], v8[2], v8[3]);
-                        Tc[(rc + 1) ^ (c & 7)] = make_float4(v8[4], v8[5], v8[6], v8[7]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) Tw[(8 * i + j) * 64 + ((cq ^ j) << 2)] = v8[j];
                     }
                 }
                 fence_before_thread_sync();
@@ -908,22 +935,18 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
                 fence_after_thread_sync();
             }
             // H_{l+1} = tanh(out / (sum + 1e-12) + b) for this thread's 16 columns (graph_conv_module.py:51-72)
-            const float inv = kTanhScale * kPVUnscale / (den + 1e-12f);
+            const float inv = __fdividef(kTanhScale * kPVUnscale, den + 1e-12f);
             float v[16];
             const float4 *bp = reinterpret_cast<const float4 *>(bias_s + kBGcn + l * 64 + 16 * sub);
+            const float4 *Tr = reinterpret_cast<const float4 *>(KV + row * 64);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 b4 = bp[q];
-                float t4[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int c = 16 * sub + 4 * q + i;
-                    t4[i] = KV[c * kTPitch + ((((row >> 2) ^ (c & 7)) << 2) | (row & 3))];
-                }
-                v[4 * q + 0] = fmaf(t4[0], inv, b4.x);
-                v[4 * q + 1] = fmaf(t4[1], inv, b4.y);
-                v[4 * q + 2] = fmaf(t4[2], inv, b4.z);
-                v[4 * q + 3] = fmaf(t4[3], inv, b4.w);
+                const float4 t4 = Tr[(4 * sub + q) ^ (row & 7)];
+                v[4 * q + 0] = fmaf(t4.x, inv, b4.x);
+                v[4 * q + 1] = fmaf(t4.y, inv, b4.y);
+                v[4 * q + 2] = fmaf(t4.z, inv, b4.z);
+                v[4 * q + 3] = fmaf(t4.w, inv, b4.w);
                 tanh4_scaled(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             }
             if (d.residual && l + 1 == L) {               // X = E + H_L (comm_base_net.py:105-106)
