@@ -340,6 +340,14 @@ __device__ __forceinline__ void scores_softmax(uint32_t lane_addr, const float *
 // Tensor-core attention: the scores of the whole tile are in tensor memory (hi*hi in columns [0, 128), the cross terms
 // in [128, 256), scaled by 2^12); the env of this row owns the key columns j0 .. j0 + n.  Thread (row, sub) takes the KT
 // consecutive keys sub * KT ..; same exchange and same result placement as scores_softmax.
+// e^x through ex2.approx.ftz (what __expf does, minus its denormal-range fix-up: results below 2^-126 flush to zero,
+// which the sums here cannot tell from the exact value); exp_fast(-inf) = 0
+__device__ __forceinline__ float exp_fast(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
 template <int KT>
 __device__ __forceinline__ void softmax_tc(uint32_t lane_addr, float *red, float *attn_row, int row, int j0, int sub, int n, bool valid)
 {
@@ -355,14 +363,20 @@ __device__ __forceinline__ void softmax_tc(uint32_t lane_addr, float *red, float
 #pragma unroll
         for (int i = 0; i < 8; ++i) sc[c + i] = fmaf(t1[i], 1.0f / 4096.0f, t0[i]);
     }
+    // keys beyond the team (or every key of a padding row) score -inf once; everything below is branch-free:
+    // exp_fast(-inf - m) = 0, and a thread without keys publishes max = -inf, sum = 0
+    const uint32_t live = nk >= 32 ? 0xFFFFFFFFu : (1u << nk) - 1u;
     float mx = -INFINITY;
 #pragma unroll
-    for (int t = 0; t < KT; ++t)
-        if (t < nk) mx = fmaxf(mx, sc[t]);
+    for (int t = 0; t < KT; ++t) {
+        sc[t] = (live & (1u << t)) ? sc[t] : -INFINITY;
+        mx = fmaxf(mx, sc[t]);
+    }
+    const float mref = nk > 0 ? mx : 0.0f;             // (-inf) - (-inf) would be NaN
     float sum = 0.0f;
 #pragma unroll
     for (int t = 0; t < KT; ++t) {
-        sc[t] = t < nk ? __expf(sc[t] - mx) : 0.0f;
+        sc[t] = exp_fast(sc[t] - mref);
         sum += sc[t];
     }
     red[sub * kTPitch + row] = mx;
@@ -370,16 +384,15 @@ __device__ __forceinline__ void softmax_tc(uint32_t lane_addr, float *red, float
     fence_before_thread_sync();
     __syncthreads();                      // every thread has read its scores
     fence_after_thread_sync();
-    float gm = -INFINITY;
+    float ms[4];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) gm = fmaxf(gm, red[s * kTPitch + row]);
+    for (int s = 0; s < 4; ++s) ms[s] = red[s * kTPitch + row];
+    const float gm = fmaxf(fmaxf(ms[0], ms[1]), fmaxf(ms[2], ms[3]));
+    const float gref = nk > 0 ? gm : 0.0f;             // rows without keys: every maximum is -inf, the result is discarded
     float z = 0.0f;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const float ms = red[s * kTPitch + row];
-        z += ms > -INFINITY ? red[(4 + s) * kTPitch + row] * __expf(ms - gm) : 0.0f;
-    }
-    const float scale = nk > 0 ? __expf(mx - gm) / z : 0.0f;
+    for (int s = 0; s < 4; ++s) z = fmaf(red[(4 + s) * kTPitch + row], exp_fast(ms[s] - gref), z);
+    const float scale = nk > 0 ? __fdividef(exp_fast(mx - gm), z) : 0.0f;
 #pragma unroll
     for (int t = 0; t < KT; ++t) sc[t] *= scale;
     if (attn_row) {                       // unmasked softmax (agent_infos['attention_weights'])
@@ -733,7 +746,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
             const int nbits = io.obs_nbits;
             for (int pnl = 0; pnl < P.l1_panels; ++pnl) {
                 const int Kp = P.st[si].Kp, kofs = 64 * pnl, kg = Kp >> 3;          // kg = 2, 4, 6 or 8 groups of 8 columns
-                const uint32_t lo_off = (uint32_t)kTcRows * Kp * 2, inv = (65536u + (uint32_t)kg - 1u) / (uint32_t)kg;
+                const uint32_t lo_off = (uint32_t)kTcRows * Kp * 2, inv = packed ? 0u : (65536u + (uint32_t)kg - 1u) / (uint32_t)kg;   // (a run-time division: only where it is used)
                 for (int e8 = tid; e8 < kTcRows * kg; e8 += kTcThreads) {           // one group of 8 columns of one row
                     // fp32 rows: consecutive threads take consecutive column groups of a row (consecutive floats); packed rows:
                     // consecutive threads take the SAME column group of consecutive rows, so that only the warps that own the
