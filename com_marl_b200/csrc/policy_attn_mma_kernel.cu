@@ -73,6 +73,17 @@ __device__ __forceinline__ float tanh_fast(float x)
     return fmaf(-2.0f, r, 1.0f);
 }
 
+// 2^x (ex2.approx.ftz); exponentials are taken in the log2 domain: exp(s - m) = 2^(s log2(e) - m log2(e)) is ONE fused
+// multiply-add and one special-function instruction (__expf costs six: subtract, scale, denormal range test and fix-up).
+// The rounding of m log2(e) is common to a row's keys and to its rescaling factors, so it cancels in out / (d + 1e-12 z).
+static constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_fast(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ float quad_max(float v)
 {
     v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, 1));
@@ -121,7 +132,7 @@ __device__ __forceinline__ void score_block(float (&s)[8][4], const __half *Qh, 
 }
 
 struct StripState {               // rows g (index 0) and g + 8 (index 1) of the strip
-    float m0, m1;                 // running maximum of the scores
+    float m0, m1;                 // running maximum of the scores times log2(e): the reference point of the exponentials
     float z0, z1;                 // this lane's part of sum exp(s - m)
     float d0, d1;                 // this lane's part of sum mask exp(s - m)
 };
@@ -141,9 +152,10 @@ __device__ __forceinline__ void attn_block(StripState &st, float (&oacc)[8][4], 
         if (key < n) { bm0 = fmaxf(bm0, s[u][0]); bm1 = fmaxf(bm1, s[u][2]); }
         if (key + 1 < n) { bm0 = fmaxf(bm0, s[u][1]); bm1 = fmaxf(bm1, s[u][3]); }
     }
-    const float mn0 = fmaxf(st.m0, quad_max(bm0)), mn1 = fmaxf(st.m1, quad_max(bm1));
-    const float sc0 = __expf(st.m0 - mn0), sc1 = __expf(st.m1 - mn1);
-    st.m0 = mn0; st.m1 = mn1;
+    // st.m0 / st.m1 hold the running maximum in the log2 domain (x -> fl(x log2(e)) is monotone: it commutes with the maximum)
+    const float ms0 = fmaxf(st.m0, quad_max(bm0) * kLog2e), ms1 = fmaxf(st.m1, quad_max(bm1) * kLog2e);
+    const float sc0 = ex2_fast(st.m0 - ms0), sc1 = ex2_fast(st.m1 - ms1);
+    st.m0 = ms0; st.m1 = ms1;
     st.z0 *= sc0; st.d0 *= sc0; st.z1 *= sc1; st.d1 *= sc1;
 #pragma unroll
     for (int ot = 0; ot < 8; ++ot) { oacc[ot][0] *= sc0; oacc[ot][1] *= sc0; oacc[ot][2] *= sc1; oacc[ot][3] *= sc1; }
@@ -151,8 +163,8 @@ __device__ __forceinline__ void attn_block(StripState &st, float (&oacc)[8][4], 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int nt = nt0 + u, key = 8 * nt + 2 * t;
-        const float e00 = key < n ? __expf(s[u][0] - mn0) : 0.0f, e01 = key + 1 < n ? __expf(s[u][1] - mn0) : 0.0f;
-        const float e10 = key < n ? __expf(s[u][2] - mn1) : 0.0f, e11 = key + 1 < n ? __expf(s[u][3] - mn1) : 0.0f;
+        const float e00 = key < n ? ex2_fast(fmaf(s[u][0], kLog2e, -ms0)) : 0.0f, e01 = key + 1 < n ? ex2_fast(fmaf(s[u][1], kLog2e, -ms0)) : 0.0f;
+        const float e10 = key < n ? ex2_fast(fmaf(s[u][2], kLog2e, -ms1)) : 0.0f, e11 = key + 1 < n ? ex2_fast(fmaf(s[u][3], kLog2e, -ms1)) : 0.0f;
         st.z0 += e00 + e01;
         st.z1 += e10 + e11;
         const uint32_t w0 = Mw[g * 8 + (nt >> 2)] >> (8 * (nt & 3) + 2 * t);
@@ -203,10 +215,10 @@ __device__ __forceinline__ void attn_record_block(float *att0, float *att1, bool
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int key = 8 * (nt0 + u) + 2 * t;
-        if (v0 && key < n) att0[key] = __expf(s[u][0] - st.m0) * is0;
-        if (v0 && key + 1 < n) att0[key + 1] = __expf(s[u][1] - st.m0) * is0;
-        if (v1 && key < n) att1[key] = __expf(s[u][2] - st.m1) * is1;
-        if (v1 && key + 1 < n) att1[key + 1] = __expf(s[u][3] - st.m1) * is1;
+        if (v0 && key < n) att0[key] = ex2_fast(fmaf(s[u][0], kLog2e, -st.m0)) * is0;
+        if (v0 && key + 1 < n) att0[key + 1] = ex2_fast(fmaf(s[u][1], kLog2e, -st.m0)) * is0;
+        if (v1 && key < n) att1[key] = ex2_fast(fmaf(s[u][2], kLog2e, -st.m1)) * is1;
+        if (v1 && key + 1 < n) att1[key + 1] = ex2_fast(fmaf(s[u][3], kLog2e, -st.m1)) * is1;
     }
 }
 
