@@ -228,6 +228,28 @@ __device__ __forceinline__ uint32_t link_row_bits(ChanSrc &src, int plane, int i
         return bits;
     }
     const uint32_t q0 = (uint32_t)((plane * n + i) * n + w * 32), q1 = q0 + (uint32_t)jn;   // draw indices [q0, q1)
+    // Thresholds inside (0, 1) — every probability but the degenerate ones — compare as INTEGERS: a draw is u = k 2^-24 with
+    // k = word >> 8 (exact in fp32), so u >= thr <=> k >= ceil(thr 2^24) =: T <=> word >= T << 8, and u < thr <=> word < T << 8;
+    // the diagonal's u + 1 lies in [1, 2): never below such a threshold, always at or above it.  One compare + select per link
+    // instead of convert / scale / add / compare / select; blocks that lie inside the row take four links at once.
+    const float t24 = thr * 16777216.0f;
+    if (t24 > 0.0f && t24 <= 16777215.0f) {
+        const uint32_t tw = (uint32_t)ceilf(t24) << 8;
+        for (uint32_t blk = q0 >> 2; blk <= (q1 - 1u) >> 2; ++blk) {
+            const uint4 r4 = rng_block(src.key, kStreamChan, blk);
+            const uint32_t b4 = (kLess ? (uint32_t)(r4.x < tw) : (uint32_t)(r4.x >= tw)) | (kLess ? (uint32_t)(r4.y < tw) : (uint32_t)(r4.y >= tw)) << 1 |
+                                (kLess ? (uint32_t)(r4.z < tw) : (uint32_t)(r4.z >= tw)) << 2 | (kLess ? (uint32_t)(r4.w < tw) : (uint32_t)(r4.w >= tw)) << 3;
+            const int sft = (int)(blk * 4u) - (int)q0;                         // position of the block's first draw in the row
+            if (sft >= 0 && sft + 4 <= jn) bits |= b4 << sft;
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (sft + k >= 0 && sft + k < jn) bits |= ((b4 >> k) & 1u) << (sft + k);
+            }
+        }
+        if ((i >> 5) == w) bits = kLess ? bits & ~(1u << (i & 31)) : bits | (1u << (i & 31));
+        return bits;
+    }
     for (uint32_t blk = q0 >> 2; blk <= (q1 - 1u) >> 2; ++blk) {
         const uint4 r4 = rng_block(src.key, kStreamChan, blk);
         const uint32_t ws[4] = {r4.x, r4.y, r4.z, r4.w};
@@ -459,12 +481,31 @@ __device__ __forceinline__ void write_obs(const EnvArgs &A, const Scratch &S, co
     float *out = A.io.obs + (size_t)b * n * D;
     const int total = n * D;
     const uint32_t magic = (uint32_t)((0x100000000ull + (u64)D - 1ull) / (u64)D);   // e / D == umulhi(e, magic) for e < 2^25
-#pragma unroll 4
-    for (int e = G.gl; e < total; e += G.gs) {
-        const int i = (int)__umulhi((uint32_t)e, magic), k = e - i * D;
-        const int kk = k < nbits ? k : 96 + 32 * (k - nbits);             // bit index, or the word of the scalar feature
+    auto value = [&](int i, int k) -> float {                                 // column k of agent i's row
+        const int kk = k < nbits ? k : 96 + 32 * (k - nbits);                 // bit index, or the word of the scalar feature
         const uint32_t word = S.win[(kk >> 5) * np_ + i];
-        out[e] = k < nbits ? (float)((word >> (kk & 31)) & 1u) : __uint_as_float(word);
+        return k < nbits ? (float)((word >> (kk & 31)) & 1u) : __uint_as_float(word);
+    };
+    // the block is streamed out as 128-bit stores: a lane builds four consecutive floats (agent / column advanced
+    // incrementally: one division per four floats), the lanes of a group store consecutive 16-byte pieces; the <= 3 floats
+    // before the first 16-byte boundary and after the last one go out as scalars
+    const int head = min(total, (int)((4u - (uint32_t)((reinterpret_cast<uintptr_t>(out) >> 2) & 3u)) & 3u));
+    const int nv = (total - head) >> 2;
+    for (int e = G.gl; e < head; e += G.gs) out[e] = value(0, e);             // (head <= 3 < D)
+#pragma unroll 2
+    for (int v = G.gl; v < nv; v += G.gs) {
+        const int e = head + 4 * v;
+        int i = (int)__umulhi((uint32_t)e, magic), k = e - i * D;
+        float4 f;
+        f.x = value(i, k); if (++k == D) { k = 0; ++i; }
+        f.y = value(i, k); if (++k == D) { k = 0; ++i; }
+        f.z = value(i, k); if (++k == D) { k = 0; ++i; }
+        f.w = value(i, k);
+        *reinterpret_cast<float4 *>(out + e) = f;
+    }
+    for (int e = head + 4 * nv + G.gl; e < total; e += G.gs) {
+        const int i = (int)__umulhi((uint32_t)e, magic);
+        out[e] = value(i, e - i * D);
     }
 }
 
