@@ -129,6 +129,11 @@ GENERATED = [
     ("max_pp", "pp", 64, 2, 0.08, 4, 0.1, 6, 26, {"n_agents": 256, "n_preys": 256, "max_env_steps": 12}, None),
     ("max_co", "co", 60, 2, 0.06, 2, 0.1, 6, 26, {"max_env_steps": 12}, None),
     ("tiny", "pp", 10, 0, 0.01, 2, 0.0, 300, 30, {"n_agents": 1, "n_preys": 1, "max_env_steps": 10}, None),
+    # loss thresholds at the ends of (0, 1): the kernel compares the draws as integers against ceil(p 2^24) << 8, the oracle
+    # as floats; teams that are not a multiple of 4 walk Philox blocks that straddle the row ends
+    ("loss_hi", "pp", 10, 1, 0.08, 2, 0.999999, 512, 40, {"n_agents": 7, "n_preys": 3, "max_env_steps": 20}, None),
+    ("loss_lo", "pp", 10, 1, 0.08, 2, 1e-7, 512, 40, {"n_agents": 13, "n_preys": 5, "max_env_steps": 20}, None),
+    ("ge_ends", "pp", 10, 1, 0.08, 2, 0.2, 512, 60, {"n_agents": 9, "max_env_steps": 25}, dict(Pgb=0.999, Pbg=1e-6, GE_INIT=1, loss_apply=1)),
 ]
 
 
