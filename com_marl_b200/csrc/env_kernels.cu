@@ -1,13 +1,14 @@
 // env_kernels.cu — batched PredatorPrey / Coverage step, reset, observation windows and communication
-// state for sm_100a.  One warp owns one environment instance.
+// state for sm_100a.  A group of 4, 8, 16 or 32 lanes owns one environment instance (8 lanes for teams of up
+// to ~56 agents: a warp then walks 4 envs at once and their order-dependent loops share its instructions).
 //
 // B200 mapping: state lives in HBM as SoA rows (positions u16, flags u8, bit rows u64);
-// a warp stages its env in shared memory, rebuilds the occupancy of the grid as 64-bit ROW BITMAPS
+// a lane group stages its env in shared memory, rebuilds the occupancy of the grid as 64-bit ROW BITMAPS
 // (agents / preys or visited / walls) instead of the reference's grid of strings, runs the two
 // order-dependent loops (agent moves, prey capture+walk) on one lane over those bitmaps while all the
 // order-independent work (neighbour counts, candidate screening, watching flags, window extraction,
 // adjacency, channel draws) is done lane-parallel, and streams the fp32 observation block out with
-// fully coalesced stores.  Everything here is integer/bit work bound by HBM traffic and issue slots;
+// fully coalesced 128-bit stores.  Everything here is integer/bit work bound by HBM traffic and issue slots;
 // no tensor cores are involved on purpose.
 //
 // Semantics follow the reference exactly (file:line cited at each step); the data model does not.

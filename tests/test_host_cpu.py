@@ -212,3 +212,26 @@ def test_fused_update_blob_maps_round_trip(kw):
         out = torch.empty_like(opt.grad)
         m.scatter_grad(out)
         assert torch.equal(out, torch.cat([fake[k].reshape(-1) for k, _ in mod.named_parameters()]))
+
+
+def test_channel_draw_integer_threshold_is_the_float_compare():
+    """env_kernel compares a channel draw as an integer (csrc/env_kernels.cu link_row_bits): u = (word >> 8) * 2^-24 in fp32,
+    u >= thr <=> word >= ceil(thr * 2^24) << 8 and u < thr <=> word < ceil(thr * 2^24) << 8 for every fp32 threshold with
+    0 < thr * 2^24 <= 2^24 - 1.  Checked here against the float compare the oracle (and the reference, with torch.rand's 24-bit
+    lattice) performs: thresholds at the ends of the range, the loss rates of the BASELINE configs, random ones; words around
+    the switching point of each threshold and random ones."""
+    rng = np.random.default_rng(0)
+    thrs = np.concatenate([np.float32([0.2, 0.1, 0.5, 0.3, 0.0196, 0.282, 0.999, 0.999999, 1e-6, 1e-7, 2.0 ** -24, 1.0 - 2.0 ** -24]),
+                           rng.random(200, dtype=np.float32), np.float32(rng.random(100) * 1e-5)]).astype(np.float32)
+    for thr in thrs:
+        t24 = np.float32(thr) * np.float32(16777216.0)
+        assert 0.0 < t24 <= 16777215.0
+        T = int(np.ceil(t24))
+        tw = np.uint64(T) << np.uint64(8)
+        ks = np.clip(np.arange(T - 3, T + 4), 0, (1 << 24) - 1).astype(np.uint64)
+        words = np.concatenate([(ks << np.uint64(8)), (ks << np.uint64(8)) | np.uint64(0xFF), rng.integers(0, 1 << 32, 64, dtype=np.uint64)])
+        u = (words >> np.uint64(8)).astype(np.float32) * np.float32(5.9604644775390625e-08)      # common.cuh::u24
+        assert np.array_equal(u >= thr, words >= tw), thr
+        assert np.array_equal(u < thr, words < tw), thr
+        # the diagonal link: u + 1 lies in [1, 2), never below / always at or above a threshold inside (0, 1)
+        assert np.all((u + np.float32(1.0)) >= thr) and not np.any((u + np.float32(1.0)) < thr)
