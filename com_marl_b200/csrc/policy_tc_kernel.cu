@@ -208,6 +208,25 @@ __device__ __forceinline__ void issue_layer(uint32_t d_tmem, const unsigned char
     }
 }
 
+// scores of the whole tile into ONE accumulator block of 128 columns: D = Q_hi E_lo^T + Q_lo E_hi^T (remainders scaled by
+// 2^12), then D = D 2^-12 + Q_hi E_hi^T (mma_f16_scale12_pred on the first K slice) — the other 128 columns of the CTA's tensor
+// memory keep H_0 Wg_0, so that product shares a phase with Q = E Wa.  qbuf / ebuf: [128][64] fp16 hi, lo 16 KB further.
+__device__ __forceinline__ void issue_scores(uint32_t d_tmem, const unsigned char *qbuf, const unsigned char *ebuf, uint32_t leader)
+{
+    if (CM_TC_DEBUG & 1) return;
+    const uint32_t lo = (uint32_t)kTcRows * 64 * 2;
+    const uint32_t idesc = make_idesc_f16(kTcRows, 128);
+    const uint64_t q_hi = make_smem_desc16(smem_u32(qbuf), 64, 0), q_lo = make_smem_desc16(smem_u32(qbuf) + lo, 64, 0);
+    const uint64_t e_hi = make_smem_desc16(smem_u32(ebuf), 64, 0), e_lo = make_smem_desc16(smem_u32(ebuf) + lo, 64, 0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mma_f16_pred(d_tmem, q_hi + 16 * j, e_lo + 16 * j, idesc, j ? 1u : 0u, leader);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mma_f16_pred(d_tmem, q_lo + 16 * j, e_hi + 16 * j, idesc, 1u, leader);
+    mma_f16_scale12_pred(d_tmem, q_hi, e_hi, idesc, leader);
+#pragma unroll
+    for (int j = 1; j < 4; ++j) mma_f16_pred(d_tmem, q_hi + 16 * j, e_hi + 16 * j, idesc, 1u, leader);
+}
+
 // raw accumulator read-out: acc0 -> v, acc1 -> w (the caller fuses the combination with bias and scale)
 template <int CW>
 __device__ __forceinline__ void ld_acc_raw(uint32_t blk, int N, int col, float (&v)[CW], float (&w)[CW])
@@ -337,8 +356,8 @@ __device__ __forceinline__ void scores_softmax(uint32_t lane_addr, const float *
     }
 }
 
-// Tensor-core attention: the scores of the whole tile are in tensor memory (hi*hi in columns [0, 128), the cross terms
-// in [128, 256), scaled by 2^12); the env of this row owns the key columns j0 .. j0 + n.  Thread (row, sub) takes the KT
+// Tensor-core attention: the scores of the whole tile are in tensor memory, columns [0, 128) (issue_scores: one accumulator
+// block); the env of this row owns the key columns j0 .. j0 + n.  Thread (row, sub) takes the KT
 // consecutive keys sub * KT ..; same exchange and same result placement as scores_softmax.
 // e^x through ex2.approx.ftz (what __expf does, minus its denormal-range fix-up: results below 2^-126 flush to zero,
 // which the sums here cannot tell from the exact value); exp_fast(-inf) = 0
@@ -355,14 +374,8 @@ __device__ __forceinline__ void softmax_tc(uint32_t lane_addr, float *red, float
     const int nk = valid ? max(0, min(KT, n - k0)) : 0;
     float sc[KT];
 #pragma unroll
-    for (int c = 0; c < KT; c += 8) {
-        float t0[8], t1[8];
-        tmem_ld8(lane_addr + (uint32_t)(j0 + k0 + c), t0);
-        tmem_ld8(lane_addr + (uint32_t)(128 + j0 + k0 + c), t1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sc[c + i] = fmaf(t1[i], 1.0f / 4096.0f, t0[i]);
-    }
+    for (int c = 0; c < KT; c += 8) tmem_ld8(lane_addr + (uint32_t)(j0 + k0 + c), *reinterpret_cast<float(*)[8]>(sc + c));
+    tmem_ld_wait();
     // keys beyond the team (or every key of a padding row) score -inf once; everything below is branch-free:
     // exp_fast(-inf - m) = 0, and a thread without keys publishes max = -inf, sum = 0
     const uint32_t live = nk >= 32 ? 0xFFFFFFFFu : (1u << nk) - 1u;
@@ -853,17 +866,17 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         if constexpr (kAttnTc) {
         // ================= tensor-core attention (17 <= n <= 64; env slots of S = 32 / 64 rows) =================
         load_mask(env, il, 0, valid);
-        run_mma(1, MmaOp{kR0, 0u, 0u}, none);                              // Q = E Wa -> R0
+        run_mma(2, MmaOp{kR0, 0u, 0u}, MmaOp{kR1, 0u, 0u});                // Q = E Wa -> R0, H_0 Wg_0 -> R1 (one phase, two issuing warps)
         {   // the query rows become the A operand of the score product (the second operand buffer is idle)
             float q[16];
             ld_acc<16>(lane_addr + kR0, 64, 16 * sub, q);
             write_act<16>(ACT2, 64, row, 16 * sub, q);
         }
         // scores of the whole tile: [128 rows] x [128 keys] = Q E^T; the B operand [E_hi ; E_lo] IS the A operand the encoder
-        // epilogue left in ACT (same K-major core-matrix layout, lo block 128 rows further).  hi*hi -> columns [0, 128),
-        // cross terms -> [128, 256): the whole tensor memory of the CTA — H_0 Wg_0 is issued afterwards.
+        // epilogue left in ACT (same K-major core-matrix layout, lo block 128 rows further).  One accumulator block, columns
+        // [0, 128) (issue_scores); H_0 Wg_0 waits in R1 until the softmax is done.
         CM_TP(0);
-        run_custom([&](uint32_t leader) { issue_layer(tmem + kR0, ACT2, ACT, 128, 64, 0u, leader); });
+        run_custom([&](uint32_t leader) { issue_scores(tmem + kR0, ACT2, ACT, leader); });
         {
             float *attn_row = (io.attention && valid) ? io.attention + (size_t)g * n : nullptr;
             if (S == 32) softmax_tc<8>(lane_addr, red, attn_row, row, j0, sub, n, valid);
@@ -871,7 +884,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
         }
         const uint32_t v_lo = (uint32_t)kTcRows * 64 * 2;                  // lo block of the value operand / of a 64-wide A operand
         {   // E (this thread's 16 columns of the A operand) -> tensor memory, for the residual: ACT becomes the attention operand.
-            // (the barriers of the product below separate these reads from the first attention rows written into ACT)
+            // (the barrier below separates these reads from the first attention rows written into ACT)
             if (d.residual) {
                 float ev[16];
 #pragma unroll
@@ -894,8 +907,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const TcArgs A
             tmem_st_wait();
         }
         CM_TP(1);
-        run_mma(1, MmaOp{kR1, 0u, 0u}, none);                              // H_0 Wg_0 -> R1 (the scores are dead)
-        {   // values -> A operand of the transposed aggregation (as written: [key][64], i.e. MN-major)
+        {   // values (H_0 Wg_0, in R1 since the phase of the query product) -> A operand of the transposed aggregation (as
+            // written: [key][64], i.e. MN-major); the score product has read the query rows out of this buffer
+            // (barrier: every thread has read its E columns out of ACT and the softmax exchange out of `red` before the first
+            // layer's attention rows and masked sums are written there — the product phase that used to sit here did that)
+            __syncthreads();
             float v[16];
             ld_acc<16>(lane_addr + kR1, 64, 16 * sub, v);
             write_unscaled<16>(ACT2, 64, v_lo, row, 16 * sub, v, kVScale);

@@ -95,6 +95,20 @@ __device__ __forceinline__ void mma_f16_pred(uint32_t d_tmem, uint64_t a_desc, u
         "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
         : "memory");
 }
+// D = A B + D 2^-12 (scale-input-d, an immediate of kind::f16 / kind::tf32): the accumulator that holds the low-order cross
+// terms — computed with the remainders scaled by 2^12 — takes the high-order product on top, so hi*hi + 2^-12 (hi*lo + lo*hi)
+// needs ONE accumulator block instead of two.  The scaling by a power of two is exact.
+__device__ __forceinline__ void mma_f16_scale12_pred(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t leader)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "setp.ne.b32 q, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 12;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(leader)
+        : "memory");
+}
 __device__ __forceinline__ void mma_commit_pred(uint64_t *bar, uint32_t leader)
 {
     asm volatile(
