@@ -300,8 +300,8 @@ def measure_config(cx, cfg, steps_req, warm_req, min_seconds, full, clocks=None,
     ring = args.ring
     pol = make_policy(spec, device=dev)
     # independent env groups: 4 chains for teams up to 64 (8 when a chain still gets ~2000 policy tiles per launch — C3: measured
-    # 849 -> 864 M agent-steps/s; smaller batches lose with 8), one chain for the three-launch pipeline of large teams
-    groups = args.groups if args.groups > 0 else ((8 if B * n >= (1 << 21) else 4) if n <= 64 else 1)
+    # 849 -> 864 M agent-steps/s; smaller batches lose with 8), two chains for the three-launch pipeline of large teams (C5: 315 -> 320 M)
+    groups = args.groups if args.groups > 0 else ((8 if B * n >= (1 << 21) else 4) if n <= 64 else 2)
     eng = RolloutEngine(spec, pol, B, device=dev, env_id0=cx.rank * B, ring=ring, use_graph=True, groups=groups)
     eng.reset()
     warm = max(3 * ring, ((warm_req + ring - 1) // ring) * ring)
@@ -343,7 +343,8 @@ def measure_config(cx, cfg, steps_req, warm_req, min_seconds, full, clocks=None,
     def policy_call(k, e, b0, b1):
         pk = dict(obs_bits=t["obs_bits"][k, b0:b1], obs_nbits=e.obs_nbits) if packed else {}
         pol.act_device(t["obs"][k, b0:b1], t["adj_bits"][k, b0:b1], t["chan_bits"][k, b0:b1], tick=e.tick, episode=e.episode,
-                       probs=t["probs"][k, b0:b1], actions=t["actions"][k, b0:b1], env_id0=e.env_id0, **pk)
+                       probs=t["probs"][k, b0:b1], actions=t["actions"][k, b0:b1], env_id0=e.env_id0,
+                       ws_slot=eng._envs.index(e) if e in eng._envs else 0, **pk)
 
     def env_call(k, e, b0, b1):
         out = dict(obs=t["obs"][k + 1, b0:b1], adj_bits=t["adj_bits"][k + 1, b0:b1], chan_bits=t["chan_bits"][k + 1, b0:b1],
@@ -700,7 +701,7 @@ def main():
     ap.add_argument("--min-seconds", type=float, default=0.25, help="floor on the timed region of `value`")
     ap.add_argument("--e2e-steps", type=int, default=2000, help="cap on the steps of an e2e (host-buffer) loop")
     ap.add_argument("--e2e-batches", type=int, default=4, help="independent env parts of the e2e (host-buffer) loops")
-    ap.add_argument("--groups", type=int, default=0, help="independent env groups, each a policy->step chain on its own stream (0: 4 or 8 for teams <= 64, else 1)")
+    ap.add_argument("--groups", type=int, default=0, help="independent env groups, each a policy->step chain on its own stream (0: 4 or 8 for teams <= 64, else 2)")
     ap.add_argument("--ppo-envs", type=int, default=128, help="envs per GPU of the c5_ppo sub-record")
     ap.add_argument("--no-sweep", action="store_true", help="skip the configs sweep and the c5_ppo sub-record")
     ap.add_argument("--no-cpu-baseline", action="store_true")

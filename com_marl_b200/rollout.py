@@ -48,8 +48,9 @@ class RolloutEngine:
         # chains.  Each chain runs on its own stream (forked / joined inside the captured graph): there is no device-wide
         # barrier between a step of one group and the next step of another, so partially filled waves of one launch
         # are covered by the launches of the other groups.  Results are identical for every G (global env ids key the
-        # random streams).  Large teams (n > 64) share one policy scratch buffer and stay in a single group.
-        G = max(1, min(int(groups), self.B)) if (spec.n_agents <= 64 or not getattr(policy, "comm", True)) else 1
+        # random streams).  Large teams (n > 64) hand rows between their three policy launches through a scratch buffer: every
+        # group has its own (ws_slot = group index).
+        G = max(1, min(int(groups), self.B))
         self.groups = G
         cuts = [self.B * g // G for g in range(G + 1)]
         self._ranges = [(cuts[g], cuts[g + 1]) for g in range(G) if cuts[g + 1] > cuts[g]]
@@ -93,7 +94,7 @@ class RolloutEngine:
         pk = dict(obs_bits=t["obs_bits"][k, b0:b1], obs_nbits=e.obs_nbits) if self._packed else {}
         self.policy.act_device(t["obs"][k, b0:b1], adj_bits=t["adj_bits"][k, b0:b1], chan_bits=t["chan_bits"][k, b0:b1], tick=e.tick, episode=e.episode,
                                greedy=self.greedy, probs=t["probs"][k, b0:b1], actions=t["actions"][k, b0:b1],
-                               attention=t["attention"][k, b0:b1] if "attention" in t else None, env_id0=e.env_id0, **pk)
+                               attention=t["attention"][k, b0:b1] if "attention" in t else None, env_id0=e.env_id0, ws_slot=g, **pk)
         out = dict(obs=t["obs"][k + 1, b0:b1], adj_bits=t["adj_bits"][k + 1, b0:b1], chan_bits=t["chan_bits"][k + 1, b0:b1],
                    ave_deg=t["ave_deg"][k + 1, b0:b1], reward=t["reward"][k, b0:b1], done=t["done"][k, b0:b1],
                    counts=t["counts"][k, b0:b1], prey_alive_out=t["prey_alive_out"][k, b0:b1],

@@ -77,18 +77,25 @@ def test_graph_replay_equals_eager():
     assert torch.equal(a.env.stats, b.env.stats)
 
 
-@pytest.mark.parametrize("scen,groups", [("pp", 3), ("co", 4), ("pp", 7)])
+@pytest.mark.parametrize("scen,groups", [("pp", 3), ("co", 4), ("pp", 7), ("pp_large", 2), ("pp_large", 3)])
 def test_env_groups_equal_single_chain(scen, groups):
     """G independent env groups on G streams (forked / joined inside the captured graph) give exactly the trajectory of
-    the single chain: the random streams are keyed by global env ids, the groups only remove device-wide barriers."""
+    the single chain: the random streams are keyed by global env ids, the groups only remove device-wide barriers.
+    pp_large: a team of 72 agents — the three-launch policy pipeline, whose groups hand their rows over through scratch
+    buffers of their own (ws_slot)."""
     from com_marl_b200.rollout import RolloutEngine, make_policy
+    B = 301
     if scen == "pp":
         params, spec = _mk("pp", 10, 1, 0.08, 2, 0.3, {"max_env_steps": 20})
+    elif scen == "pp_large":
+        params, spec = _mk("pp", 30, 2, 0.08, 4, 0.2, {"max_env_steps": 20})
+        assert spec.n_agents > 64
+        B = 37
     else:
         params, spec = _mk("co", 10, 1, 0.03, 2, 0.1, {"max_env_steps": 25})
     pol = make_policy(spec)
-    a = RolloutEngine(spec, pol, 301, ring=5, use_graph=True, groups=1)
-    b = RolloutEngine(spec, pol, 301, ring=5, use_graph=True, groups=groups)
+    a = RolloutEngine(spec, pol, B, ring=5, use_graph=True, groups=1)
+    b = RolloutEngine(spec, pol, B, ring=5, use_graph=True, groups=groups)
     assert len(b._ranges) == groups
     for e in (a, b):
         e.reset()
