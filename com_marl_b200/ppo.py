@@ -145,7 +145,13 @@ class GaussianMLPBaseline(nn.Module):
 class FlatAdam:
     """The reference's Adam (my_optimizer/adam.py) over ONE flat fp32 bucket: parameters and gradients of the module are
     re-seated as views of two flat tensors, so that the gradient all-reduce is one NCCL call, the gradient norm one
-    reduction and the optimizer step one kernel (cm_adam_step)."""
+    reduction and the optimizer step one kernel (cm_adam_step).
+
+    Every element of the bucket is stepped, also those of a parameter that received no gradient in this backward pass (its
+    slice of the zeroed bucket stays 0).  The reference's Adam skips parameters whose ``grad is None`` (com_marl/torch/algos/my_optimizer/adam.py:79-80).  The two
+    agree as long as a parameter either always or never receives a gradient: with moments that are still zero a zero gradient
+    moves nothing (0 / (0 + eps)), and that is the case for every network of the three runner families (a parameter outside the
+    loss's graph — e.g. the attention weights of a policy run without communication — never gets one)."""
 
     def __init__(self, module, lr=3e-4, betas=(0.9, 0.999), eps=1e-5):
         self.params = [p for p in module.parameters() if p.requires_grad]
