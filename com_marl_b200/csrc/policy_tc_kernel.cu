@@ -20,7 +20,8 @@
 //     with tcgen05.st and read back with tcgen05.ld.
 //   * teams of 17 .. 64 agents run the n x n part on the tensor cores too (kVec = 0): an env occupies a SLOT of 32 or 64 tile
 //     rows; scores = Q E^T as one 128 x 128 x 64 product over the whole tile (B operand = the E operand already in shared
-//     memory; the cross-env blocks are computed and ignored), softmax per row from tensor memory, and per layer the aggregation
+//     memory; the cross-env blocks are computed and ignored) into ONE accumulator block — the cross terms first, the high-order
+//     product on top through tcgen05.mma's scale-input-d form, D = A B + D 2^-12 —, softmax per row from tensor memory, and per layer the aggregation
 //     TRANSPOSED per env:  out_e^T [64 x S] = (H_l Wg_l)_e^T [64 x S keys] * A_e^T [S keys x S rows]  — an M = 64 product whose
 //     A operand is the value rows as written (MN-major) and whose B operand is the compact masked attention rows (K-major),
 //     so nothing is padded to the tile's 128 keys; the result comes back to the row-per-thread mapping through a swizzled fp32
