@@ -55,6 +55,33 @@ def main():
             lst = [vals]
         out[name] = {"alone_GBps_per_rank": [round(float(v[0]), 1) for v in lst], "all_ranks_at_once_GBps_per_rank": [round(float(v[1]), 1) for v in lst],
                      "sum_at_once_GBps": round(float(sum(v[1] for v in lst)), 1)}
+    # both directions of ONE GPU at once, each on a copy stream of its own (rank 0; the others wait): does a step that uploads
+    # while the previous one downloads get the sum of the two directions?
+    barrier()
+    if rank == 0:
+        s_up, s_down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        reps = 8
+
+        def both():
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            s_up.wait_event(e0); s_down.wait_event(e0)
+            for _ in range(reps):
+                with torch.cuda.stream(s_up):
+                    ddst.copy_(hsrc, non_blocking=True)
+                with torch.cuda.stream(s_down):
+                    dst.copy_(src, non_blocking=True)
+            for st in (s_up, s_down):
+                j = torch.cuda.Event(); j.record(st); torch.cuda.current_stream(dev).wait_event(j)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) * 1e-3
+
+        both()
+        t = both()
+        out["h2d_and_d2h_one_gpu_two_streams"] = {"GBps_each_direction": round(reps * nbytes / t / 1e9, 1), "GBps_sum": round(2 * reps * nbytes / t / 1e9, 1)}
+    barrier()
     if rank == 0:
         print(json.dumps({"n_gpus": world, "transfer_bytes": nbytes, **out}), flush=True)
     if world > 1:
